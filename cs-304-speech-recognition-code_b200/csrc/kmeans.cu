@@ -1,0 +1,211 @@
+// Segmental K-means sufficient statistics for sm_100a.
+//
+// Replaces the accumulation half of the reference's M-step:
+//   Signal.order_by_state                      signal.py:23-47   (contiguous run per state, increasing order)
+//   SortedSignals.transition_probabilities     signal.py:81-91   (consecutive-pair counts)
+//   _update_middleware_parameters              hidden_markov_model.py:320-350 (per-state mean / np.cov inputs)
+//   HiddenMarkovModelMultiWord._remux_path_and_signal  hidden_markov_model.py:602-636 (cut the chain alignment
+//       per word label, re-base to the word's first state, final piece never flushed)
+//
+// align_kernel:  one thread per utterance walks the alignment once, writes for every frame the
+//                bucket (global state id of the word model it is credited to, 0xFFFF = none) and
+//                adds integer transition counts with atomics (integer => order independent).
+// accum_kernel:  grid = (bucket, chunk of frames).  A CTA scans the bucket ids of its chunk,
+//                compacts the matching frames in order, and every thread owns <= 4 entries of
+//                the packed statistics vector  [N | sum x | upper triangle of sum x x^T]  (float64,
+//                data shifted by shift_g for conditioning) which it updates from a shared-memory
+//                copy of the frame.  No floating-point atomics: partials per chunk, then
+// reduce_kernel: sums the chunk partials in a fixed order => bitwise reproducible statistics.
+// Algorithmic HBM bytes: 4*D + 2 per frame (features once + bucket id; re-scans of the id array hit L2).
+#include "common.cuh"
+
+namespace loe {
+
+constexpr int kAccThreads = 256;
+constexpr int kAccBatch = 16;
+constexpr int kMaxDimK = 40;               // D + 1 (constant-one column) must fit
+
+// ------------------------------------------------------------------------------------------
+__global__ void align_kernel(const int8_t* __restrict__ path, const int64_t* __restrict__ frm_off, int n_utt,
+                             const int32_t* __restrict__ tr_off, const int32_t* __restrict__ col,
+                             const int32_t* __restrict__ word, const int32_t* __restrict__ word_lo,
+                             const int32_t* __restrict__ utt_tr, int remux, int n_glob,
+                             uint16_t* __restrict__ bucket, int32_t* __restrict__ counts) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_utt) return;
+    const int64_t f0 = frm_off[u];
+    const int T = (int)(frm_off[u + 1] - f0);
+    const int tr = utt_tr ? utt_tr[u] : 0;
+    const int p0 = tr_off[tr];
+    const int P = tr_off[tr + 1] - p0;
+    const int8_t* __restrict__ pth = path + f0;
+    uint16_t* __restrict__ bk = bucket + f0;
+    for (int t = 0; t < T; ++t) bk[t] = 0xFFFF;
+    if (T <= 0 || pth[0] < 0 || pth[0] >= P) return;     // T == 1 gives path [-1]: nothing is credited
+
+    int seg_start = 0;
+    while (seg_start < T) {
+        // segment = maximal run of frames whose position carries the same word label
+        const int pfirst = pth[seg_start];
+        if (pfirst < 0 || pfirst >= P) break;
+        int seg_end = T;
+        if (remux) {
+            const int lab = word[p0 + pfirst];
+            seg_end = seg_start + 1;
+            while (seg_end < T) {
+                const int p = pth[seg_end];
+                if (p < 0 || p >= P || word[p0 + p] != lab) break;
+                ++seg_end;
+            }
+            if (seg_end == T) break;                      // final piece is never flushed (:614-636)
+        }
+        const int lo = remux ? word_lo[p0 + pfirst] : 0;
+        int n_states = P;
+        if (remux) { n_states = 1; while (lo + n_states < P && word_lo[p0 + lo + n_states] == lo) ++n_states; }
+        const int gbase = col[p0 + lo];
+        // order_by_state: accept frames while the local state sequence is non-decreasing in [0, n)
+        int last = 0; bool ok = true;
+        int prev_local = 0;
+        for (int t = seg_start; t < seg_end; ++t) {
+            const int local = (int)pth[t] - lo;
+            const bool in_range = local >= 0 && local < n_states;
+            if (ok && in_range && local >= last) { bk[t] = (uint16_t)(gbase + local); last = local; }
+            else ok = false;
+            if (t > seg_start && in_range && prev_local >= 0 && prev_local < n_states)
+                atomicAdd(counts + (size_t)(gbase + prev_local) * n_glob + (gbase + local), 1);
+            prev_local = local;
+        }
+        seg_start = seg_end;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kAccThreads)
+accum_kernel(const float* __restrict__ feat, const uint16_t* __restrict__ bucket, int64_t total_frames, int dim,
+             int64_t chunk, const float* __restrict__ shift, double* __restrict__ part) {
+    const int g = blockIdx.x;
+    const int c = blockIdx.y;
+    const int n_chunks = gridDim.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int K = dim + 1;                                   // augmented with a constant 1
+    const int stride = 1 + dim + dim * (dim + 1) / 2;
+
+    __shared__ double s_x[kAccBatch][kMaxDimK];
+    __shared__ float s_shift[kMaxDimK];
+    __shared__ int64_t s_list[kAccThreads];
+    __shared__ int s_wcount[kAccThreads / 32];
+
+    // entry -> (i, j) with the convention x[dim] == 1:  e = 0 -> (dim, dim);  1..dim -> (e-1, dim)
+    int ei[4], ej[4];
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int e = tid + q * kAccThreads;
+        int i = dim, j = dim;
+        if (e >= 1 && e <= dim) { i = e - 1; j = dim; }
+        else if (e > dim && e < stride) {
+            int r = e - 1 - dim, row = 0;
+            while (r >= dim - row) { r -= dim - row; ++row; }
+            i = row; j = row + r;
+        }
+        ei[q] = i; ej[q] = j;
+    }
+    if (tid < K) s_shift[tid] = (tid < dim) ? shift[(size_t)g * dim + tid] : 0.f;
+    __syncthreads();
+
+    const int64_t f_begin = (int64_t)c * chunk;
+    const int64_t f_end = min(total_frames, f_begin + chunk);
+    for (int64_t base = f_begin; base < f_end; base += kAccThreads) {
+        const int64_t f = base + tid;
+        const bool match = f < f_end && bucket[f] == (uint16_t)g;
+        const unsigned bal = __ballot_sync(0xffffffffu, match);
+        if (lane == 0) s_wcount[warp] = __popc(bal);
+        __syncthreads();
+        int off = 0, n_match = 0;
+#pragma unroll
+        for (int w = 0; w < kAccThreads / 32; ++w) { if (w < warp) off += s_wcount[w]; n_match += s_wcount[w]; }
+        if (match) s_list[off + __popc(bal & ((1u << lane) - 1))] = f;
+        __syncthreads();
+        for (int b0 = 0; b0 < n_match; b0 += kAccBatch) {
+            const int nb = min(kAccBatch, n_match - b0);
+            for (int i = tid; i < nb * K; i += kAccThreads) {
+                const int r = i / K, k = i - r * K;
+                s_x[r][k] = (k < dim) ? (double)(feat[s_list[b0 + r] * dim + k] - s_shift[k]) : 1.0;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (tid + q * kAccThreads < stride) {
+                    double a = acc[q];
+                    for (int r = 0; r < nb; ++r) a = fma(s_x[r][ei[q]], s_x[r][ej[q]], a);
+                    acc[q] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    double* dst = part + ((size_t)g * n_chunks + c) * stride;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int e = tid + q * kAccThreads;
+        if (e < stride) dst[e] = acc[q];
+    }
+}
+
+__global__ void reduce_kernel(const double* __restrict__ part, int n_chunks, int stride, double* __restrict__ stats) {
+    const int g = blockIdx.x;
+    for (int e = threadIdx.x; e < stride; e += blockDim.x) {
+        double a = 0.0;
+        const double* p = part + (size_t)g * n_chunks * stride + e;
+        for (int c = 0; c < n_chunks; ++c) a += p[(size_t)c * stride];
+        stats[(size_t)g * stride + e] = a;
+    }
+}
+
+static void kmeans_chunking(int64_t total_frames, int64_t* chunk, int* n_chunks) {
+    int64_t ch = 16384;
+    while ((total_frames + ch - 1) / ch > 128) ch *= 2;
+    *chunk = ch;
+    *n_chunks = (int)((total_frames + ch - 1) / ch);
+    if (*n_chunks < 1) *n_chunks = 1;
+}
+
+}  // namespace loe
+
+extern "C" int loe_align_dev(const int8_t* path_dev, const int64_t* frm_off_dev, int n_utt,
+                             const int32_t* tr_off_dev, const int32_t* col_dev, const int32_t* word_dev,
+                             const int32_t* word_lo_dev, const int32_t* utt_tr_dev, int remux, int n_glob,
+                             uint16_t* bucket_dev, int32_t* counts_dev, void* stream) {
+    using namespace loe;
+    if (n_utt <= 0) return LOE_OK;
+    if (n_glob >= 0xFFFF) { set_error("too many global states"); return LOE_ERR_VALUE; }
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    align_kernel<<<(unsigned)((n_utt + 127) / 128), 128, 0, s>>>(path_dev, frm_off_dev, n_utt, tr_off_dev, col_dev, word_dev,
+                                                                word_lo_dev, utt_tr_dev, remux, n_glob, bucket_dev, counts_dev);
+    LOE_LAUNCH_CHECK("align_kernel");
+    return LOE_OK;
+}
+
+extern "C" int64_t loe_kmeans_ws_doubles(int64_t total_frames, int n_glob, int dim) {
+    int64_t chunk; int n_chunks;
+    loe::kmeans_chunking(total_frames, &chunk, &n_chunks);
+    return (int64_t)n_glob * n_chunks * (1 + dim + dim * (dim + 1) / 2);
+}
+
+extern "C" int loe_kmeans_dev(const float* feat_dev, const uint16_t* bucket_dev, int64_t total_frames, int dim,
+                              int n_glob, const float* shift_dev, double* part_ws_dev, double* stats_dev, void* stream) {
+    using namespace loe;
+    if (n_glob <= 0) return LOE_OK;
+    if (dim + 1 > kMaxDimK) { set_error("kmeans kernel supports dim <= %d (got %d)", kMaxDimK - 1, dim); return LOE_ERR_UNSUPPORTED; }
+    const int stride = 1 + dim + dim * (dim + 1) / 2;
+    if (stride > 4 * kAccThreads) { set_error("statistics vector too long"); return LOE_ERR_UNSUPPORTED; }
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    int64_t chunk; int n_chunks;
+    kmeans_chunking(total_frames, &chunk, &n_chunks);
+    dim3 grid((unsigned)n_glob, (unsigned)n_chunks);
+    accum_kernel<<<grid, kAccThreads, 0, s>>>(feat_dev, bucket_dev, total_frames, dim, chunk, shift_dev, part_ws_dev);
+    LOE_LAUNCH_CHECK("accum_kernel");
+    reduce_kernel<<<(unsigned)n_glob, 256, 0, s>>>(part_ws_dev, n_chunks, stride, stats_dev);
+    LOE_LAUNCH_CHECK("reduce_kernel");
+    return LOE_OK;
+}

@@ -1,0 +1,250 @@
+"""Per-process device engine: owns the CUDA device buffers (torch tensors) and drives the C ABI.
+
+PyTorch is plumbing here (device memory, streams, torch.distributed); every computation is a
+hand-written kernel behind include/loe_b200.h.  The engine is created lazily on first use and
+never crosses a fork: callers that use ``ProcessPoolExecutor`` (as the reference's scripts do)
+get a fresh engine per worker process.  There is no CPU fallback -- without a CUDA device or
+without the built library every entry point raises.
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _native
+from ._trellis import HostTrellis, stack
+
+_ENGINE = None
+_ENGINE_PID = None
+
+PRECISIONS = {"fp32": 0, "fp64": 1, "tc": 2}
+
+
+def default_precision() -> str:
+    return os.environ.get("LOE_B200_EMISSION", "fp32")
+
+
+class NoCudaDevice(RuntimeError):
+    pass
+
+
+@dataclass
+class GaussPack:
+    """Flat device copy of a list of MultivariateNormal (scipy frozen) objects."""
+    n_states: int
+    dim: int
+    mean32: "torch.Tensor"
+    u32: "torch.Tensor"
+    cst32: "torch.Tensor"
+    mean64: "torch.Tensor"
+    u64: "torch.Tensor"
+    cst64: "torch.Tensor"
+
+
+@dataclass
+class TrellisPack:
+    tr_off: "torch.Tensor"
+    col: "torch.Tensor"
+    band: "torch.Tensor"
+    flags: "torch.Tensor"
+    word: "torch.Tensor"
+    word_lo: "torch.Tensor"
+    max_pos: int
+    max_ends: int
+    n_trellis: int
+
+
+@dataclass
+class Batch:
+    """A batch of utterances resident on the device."""
+    feat: "torch.Tensor"          # [F, D] float32
+    frm_off: "torch.Tensor"       # [n+1] int64 (device)
+    frm_off_host: np.ndarray      # [n+1] int64
+    n_utt: int
+    max_frames: int
+
+    @property
+    def total_frames(self) -> int:
+        return int(self.frm_off_host[-1])
+
+
+def host_gauss_arrays(normals) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """(mean [S,D], U [S,D,D], cst [S]) in float64 from MultivariateNormal objects
+    (hidden_markov_model.py:20-48; scipy frozen: mean, cov_object._LP, ._log_pdet, ._rank)."""
+    means = np.stack([np.asarray(mn._core.mean, dtype=np.float64) for mn in normals])
+    us = np.stack([np.asarray(mn._core.cov_object._LP, dtype=np.float64) for mn in normals])
+    cst = np.array([-0.5 * (mn._core.cov_object._rank * np.log(2 * np.pi) + mn._core.cov_object._log_pdet)
+                    for mn in normals], dtype=np.float64)
+    return means, us, cst
+
+
+class Engine:
+    def __init__(self, device: Optional[int] = None):
+        import torch
+
+        self.torch = torch
+        self.lib = _native.load()
+        if not torch.cuda.is_available():
+            raise NoCudaDevice("no CUDA device visible: loe_speech_recognition (B200 build) has no CPU fallback")
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0")) if torch.cuda.device_count() > 1 else 0
+        self.device = torch.device("cuda", device)
+        torch.cuda.set_device(self.device)
+        self._mel_cache = {}
+        self.launches = 0           # kernels launched through the C ABI (bench.py reports it)
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self) -> int:
+        return self.torch.cuda.current_stream(self.device).cuda_stream
+
+    def _to_dev(self, arr: np.ndarray):
+        t = self.torch.from_numpy(np.ascontiguousarray(arr))
+        return t.to(self.device, non_blocking=False)
+
+    def empty(self, shape, dtype):
+        return self.torch.empty(shape, dtype=dtype, device=self.device)
+
+    @staticmethod
+    def _p(t) -> int:
+        return 0 if t is None else t.data_ptr()
+
+    # ------------------------------------------------------------------ packing
+    def pack_gaussians(self, normals) -> GaussPack:
+        means, us, cst = host_gauss_arrays(normals)
+        return self.pack_gauss_arrays(means, us, cst)
+
+    def pack_gauss_arrays(self, means, us, cst) -> GaussPack:
+        return GaussPack(
+            n_states=means.shape[0], dim=means.shape[1],
+            mean32=self._to_dev(means.astype(np.float32)), u32=self._to_dev(us.astype(np.float32)),
+            cst32=self._to_dev(cst.astype(np.float32)),
+            mean64=self._to_dev(means), u64=self._to_dev(us), cst64=self._to_dev(cst))
+
+    def pack_trellises(self, trellises: List[HostTrellis]) -> TrellisPack:
+        off, col, band, flags, word, word_lo, max_pos, max_ends = stack(trellises)
+        if max_pos > _native.LOE_MAX_POS:
+            raise OverflowError(f"{max_pos} trellis positions: the int8 path of the reference holds at most "
+                                f"{_native.LOE_MAX_POS}")
+        return TrellisPack(self._to_dev(off), self._to_dev(col), self._to_dev(band), self._to_dev(flags),
+                           self._to_dev(word), self._to_dev(word_lo), max_pos, max_ends, len(trellises))
+
+    # ------------------------------------------------------------------ batches
+    def upload_features(self, feats: Sequence[np.ndarray], dim: Optional[int] = None) -> Batch:
+        lens = np.array([f.shape[0] for f in feats], dtype=np.int64)
+        if dim is not None:
+            for f in feats:
+                assert f.shape[1] == dim
+        off = np.concatenate(([0], np.cumsum(lens))).astype(np.int64)
+        flat = np.concatenate([np.asarray(f, dtype=np.float32) for f in feats], axis=0) if len(feats) > 1 \
+            else np.ascontiguousarray(feats[0], dtype=np.float32)
+        return Batch(self._to_dev(flat), self._to_dev(off), off, len(feats), int(lens.max()))
+
+    # ------------------------------------------------------------------ MFCC
+    def _mel_tables(self, sample_rate):
+        key = float(sample_rate)
+        if key not in self._mel_cache:
+            from .mfcc import mel_filterbank_sparse
+            start, length, w = mel_filterbank_sparse(sample_rate)
+            self._mel_cache[key] = (self._to_dev(start), self._to_dev(length), self._to_dev(w))
+        return self._mel_cache[key]
+
+    def mfcc_device(self, pcm, pcm_off, frm_off, n_utt, total_frames, max_frames, min_frames, sample_rate=16000,
+                    out=None, mel_ws=None, utt_max=None):
+        """PCM (device) -> features [total_frames, 39] (device).  All tensors on this device."""
+        torch = self.torch
+        start, length, w = self._mel_tables(sample_rate)
+        if out is None:
+            out = self.empty((total_frames, 39), torch.float32)
+        if mel_ws is None:
+            mel_ws = self.empty((total_frames, 40), torch.float32)
+        if utt_max is None:
+            utt_max = self.empty((n_utt,), torch.float32)
+        _native.check(self.lib.loe_mfcc_dev(pcm.data_ptr(), pcm_off.data_ptr(), frm_off.data_ptr(), n_utt, total_frames,
+                                            max_frames, min_frames, start.data_ptr(), length.data_ptr(), w.data_ptr(),
+                                            mel_ws.data_ptr(), utt_max.data_ptr(), out.data_ptr(), self._stream()))
+        self.launches += 2
+        return out
+
+    def upload_pcm(self, signals: Sequence[np.ndarray]):
+        lens = np.array([s.shape[0] for s in signals], dtype=np.int64)
+        pcm_off = np.concatenate(([0], np.cumsum(lens))).astype(np.int64)
+        frames = 1 + lens // 160
+        frm_off = np.concatenate(([0], np.cumsum(frames))).astype(np.int64)
+        flat = np.concatenate([np.asarray(s, dtype=np.float32) for s in signals]) if len(signals) > 1 \
+            else np.ascontiguousarray(signals[0], dtype=np.float32)
+        return self._to_dev(flat), self._to_dev(pcm_off), self._to_dev(frm_off), frm_off, frames
+
+    def mfcc(self, signals: Sequence[np.ndarray], sample_rate=16000) -> Batch:
+        pcm, pcm_off, frm_off_dev, frm_off, frames = self.upload_pcm(signals)
+        feat = self.mfcc_device(pcm, pcm_off, frm_off_dev, len(signals), int(frm_off[-1]), int(frames.max()),
+                                int(frames.min()), sample_rate)
+        return Batch(feat, frm_off_dev, frm_off, len(signals), int(frames.max()))
+
+    # ------------------------------------------------------------------ emission
+    def emission(self, feat, gp: GaussPack, precision: Optional[str] = None, out=None, ld: Optional[int] = None):
+        torch = self.torch
+        precision = precision or default_precision()
+        n_frames, dim = int(feat.shape[0]), int(feat.shape[1])
+        if dim != gp.dim:
+            raise AssertionError(f"feature dimension {dim} != model dimension {gp.dim}")
+        if ld is None:
+            ld = gp.n_states
+        if out is None:
+            out = self.empty((n_frames, ld), torch.float32)
+        code = PRECISIONS[precision]
+        mean, u, cst = (gp.mean64, gp.u64, gp.cst64) if code == 1 else (gp.mean32, gp.u32, gp.cst32)
+        _native.check(self.lib.loe_emission_dev(feat.data_ptr(), n_frames, dim, mean.data_ptr(), u.data_ptr(), cst.data_ptr(),
+                                                gp.n_states, out.data_ptr(), ld, code, self._stream()))
+        self.launches += 1
+        return out
+
+    # ------------------------------------------------------------------ Viterbi
+    def viterbi(self, scores, batch_frm_off, n_utt, max_frames, total_frames, tp: TrellisPack, utt_tr=None,
+                loop=False, penalty=0.0, penalty_f64=False, want_end_scores=True):
+        torch = self.torch
+        path = self.empty((total_frames,), torch.int8)
+        best = self.empty((n_utt,), torch.int32)
+        best_score = self.empty((n_utt,), torch.float32)
+        end_scores = self.empty((n_utt, tp.max_ends), torch.float32) if want_end_scores else None
+        bp_ws = None
+        if not self.lib.loe_viterbi_bp_fits(max_frames, tp.max_pos):
+            bp_ws = self.empty((total_frames * _native.LOE_MAX_POS,), torch.uint8)
+        _native.check(self.lib.loe_viterbi_dev(
+            scores.data_ptr(), int(scores.shape[1]), batch_frm_off.data_ptr(), n_utt, max_frames,
+            tp.tr_off.data_ptr(), tp.col.data_ptr(), tp.band.data_ptr(), tp.flags.data_ptr(), tp.max_pos,
+            self._p(utt_tr), 1 if loop else 0, float(penalty), 1 if penalty_f64 else 0,
+            path.data_ptr(), self._p(end_scores), tp.max_ends, best.data_ptr(), best_score.data_ptr(),
+            self._p(bp_ws), self._stream()))
+        self.launches += 1
+        return path, end_scores, best, best_score
+
+    # ------------------------------------------------------------------ K-means statistics
+    def kmeans_stats(self, feat, path, frm_off, n_utt, total_frames, tp: TrellisPack, utt_tr, remux: bool,
+                     n_glob: int, shift):
+        """Returns (stats [n_glob, 1+D+D(D+1)/2] float64, counts [n_glob, n_glob] int32) on the device."""
+        torch = self.torch
+        dim = int(feat.shape[1])
+        bucket = self.empty((total_frames,), torch.int16)
+        counts = torch.zeros((n_glob, n_glob), dtype=torch.int32, device=self.device)
+        _native.check(self.lib.loe_align_dev(path.data_ptr(), frm_off.data_ptr(), n_utt, tp.tr_off.data_ptr(), tp.col.data_ptr(),
+                                             tp.word.data_ptr(), tp.word_lo.data_ptr(), self._p(utt_tr), 1 if remux else 0,
+                                             n_glob, bucket.data_ptr(), counts.data_ptr(), self._stream()))
+        stride = 1 + dim + dim * (dim + 1) // 2
+        ws = self.empty((int(self.lib.loe_kmeans_ws_doubles(total_frames, n_glob, dim)),), torch.float64)
+        stats = self.empty((n_glob, stride), torch.float64)
+        _native.check(self.lib.loe_kmeans_dev(feat.data_ptr(), bucket.data_ptr(), total_frames, dim, n_glob, shift.data_ptr(),
+                                              ws.data_ptr(), stats.data_ptr(), self._stream()))
+        self.launches += 3
+        return stats, counts, bucket
+
+
+def get_engine() -> Engine:
+    """The engine of this process (created on first use; never inherited across fork)."""
+    global _ENGINE, _ENGINE_PID
+    if _ENGINE is None or _ENGINE_PID != os.getpid():
+        _ENGINE = Engine()
+        _ENGINE_PID = os.getpid()
+    return _ENGINE

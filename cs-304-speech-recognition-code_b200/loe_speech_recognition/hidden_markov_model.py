@@ -1,0 +1,637 @@
+"""HMM decoder and trainers -- the reference's public classes, backed by the sm_100a kernels.
+
+Reference: src/loe_speech_recognition/hidden_markov_model.py (all line numbers below).
+Same class names, constructor / classmethod signatures, attribute names, exceptions and
+on-disk layout (``<root>/<label>/{log_trans_probs,multivariate_normals}.pickle``); the
+per-(frame, state) Python loops are replaced by three launches:
+
+  loe_emission_dev   all Gaussian log-densities of a batch        (:46-48)
+  loe_viterbi_dev    trellis walk + backtrace, one CTA/utterance  (:160-208, :481-581, :591)
+  loe_align_dev + loe_kmeans_dev   sufficient statistics of the M-step (:320-350, :602-636)
+
+Added (does not alter existing signatures): ``predict_batch`` on the decoders -- the
+reference API is one utterance per call, which cannot fill a GPU.
+
+The scipy frozen distributions stay the model's persistent form (the pickles embed them); the
+device copy ("pack") is rebuilt lazily whenever the Python-side model objects change.
+"""
+from __future__ import annotations
+
+import logging
+import os
+import pickle
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Self, Sequence, Tuple
+
+import numpy as np
+import scipy as sp
+import scipy.stats
+from numpy.typing import NDArray
+from tqdm import tqdm
+
+from . import _trellis
+from .model_boundary import ModelBoundary
+from .signal import Signal, SortedSignals
+from .transition_probability import LogTransitionProbabilities, TransitionProbabilities
+
+logger = logging.getLogger(__name__)
+
+
+def _engine():
+    from ._engine import get_engine
+    return get_engine()
+
+
+@dataclass
+class MultivariateNormal:
+    """Full-covariance Gaussian; persistent form = scipy frozen distribution (:20-48)."""
+    dim_of_features: int = field(init=False)
+    _core: "sp.stats._multivariate.multivariate_normal_frozen" = field(init=False)
+
+    @classmethod
+    def from_means_covariances(cls, mean: NDArray[np.float32], covariance: NDArray[np.float32]) -> Self:
+        mn = cls()
+        # raises LinAlgError (singular) / ValueError (non-finite, not PSD) exactly like the reference
+        mn._core = sp.stats.multivariate_normal(mean=mean, cov=covariance, allow_singular=False)
+        mn.dim_of_features = mean.shape[0]
+        return mn
+
+    def log_pdf(self, x: NDArray) -> float:
+        """Single-frame log-density through the emission kernel (np.float32, like :46-48)."""
+        assert x.shape[0] == self.dim_of_features
+        eng = _engine()
+        gp = eng.pack_gaussians([self])
+        feat = eng._to_dev(np.asarray(x, dtype=np.float32)[None, :])
+        return eng.emission(feat, gp).cpu().numpy()[0, 0]
+
+
+# ----------------------------------------------------------------------------------------
+# device packs, cached on the Python objects but never pickled
+# ----------------------------------------------------------------------------------------
+class _PackCache:
+    """Mixin: drops device handles when pickled (ProcessPoolExecutor ships models to workers)."""
+
+    _PACK_ATTRS = ("_pack_cache",)
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        for k in self._PACK_ATTRS:
+            state.pop(k, None)
+        return state
+
+    def _cached(self, key, builder):
+        cache = self.__dict__.get("_pack_cache")
+        if cache is None or cache[0] != key or cache[2] != os.getpid():
+            cache = (key, builder(), os.getpid())
+            self.__dict__["_pack_cache"] = cache
+        return cache[1]
+
+
+def _model_key(normals, ltp):
+    return (id(normals), len(normals), id(ltp), tuple(id(n._core) for n in normals),
+            len(ltp._core), id(ltp._core))
+
+
+@dataclass
+class HiddenMarkovModel(_PackCache):
+    label: str
+    isMultiProcessing: bool = field(default=True)
+    isTqdm: bool = field(default=True)
+    _multivariate_normals: List[MultivariateNormal] = field(default_factory=list)
+    _log_transition_probs: LogTransitionProbabilities = field(default_factory=LogTransitionProbabilities)
+
+    def __str__(self) -> str:
+        return self.label
+
+    @property
+    def num_of_states(self) -> int:
+        return len(self._multivariate_normals)
+
+    @property
+    def dim_of_features(self) -> int:
+        return self._multivariate_normals[0].dim_of_features
+
+    # -- device side ---------------------------------------------------------------------
+    def _trellis_kind(self) -> str:
+        return "word"
+
+    def _host_trellis(self) -> _trellis.HostTrellis:
+        return _trellis.build([self._log_transition_probs.to_dense()], [0], [0], "word")
+
+    def _packs(self):
+        def build():
+            eng = _engine()
+            return eng.pack_gaussians(self._multivariate_normals), eng.pack_trellises([self._host_trellis()])
+        return self._cached(_model_key(self._multivariate_normals, self._log_transition_probs), build)
+
+    def predict(self, signal: NDArray[np.float32]) -> Tuple[float, NDArray[np.int8]]:
+        assert len(self._multivariate_normals) > 0
+        assert self.dim_of_features == signal.shape[1]
+        return self._viterbi(signal)
+
+    def _viterbi(self, observation_sequence: NDArray[np.float32]) -> Tuple[float, NDArray[np.int8]]:
+        scores, paths = self.predict_batch([observation_sequence])
+        return scores[0], paths[0]
+
+    def predict_batch(self, signals: Sequence[NDArray[np.float32]], precision: Optional[str] = None
+                      ) -> Tuple[NDArray[np.float32], List[NDArray[np.int8]]]:
+        """Viterbi scores and state paths of many utterances in one pass (added entry point)."""
+        eng = _engine()
+        gp, tp = self._packs()
+        batch = eng.upload_features(signals, self.dim_of_features)
+        scores = eng.emission(batch.feat, gp, precision)
+        path, _, _, best_score = eng.viterbi(scores, batch.frm_off, batch.n_utt, batch.max_frames, batch.total_frames, tp,
+                                             want_end_scores=False)
+        path_h = path.cpu().numpy()
+        off = batch.frm_off_host
+        return best_score.cpu().numpy(), [path_h[off[i]:off[i + 1]] for i in range(batch.n_utt)]
+
+    # -- persistence (:93-158) ------------------------------------------------------------
+    def save(self, parent_folder_path: str = "./cache") -> None:
+        folder = os.path.join(parent_folder_path, f"{self.label}")
+        os.makedirs(folder, exist_ok=True)
+        with open(os.path.join(folder, "log_trans_probs.pickle"), "wb") as f:
+            pickle.dump(self._log_transition_probs, f, pickle.HIGHEST_PROTOCOL)
+        with open(os.path.join(folder, "multivariate_normals.pickle"), "wb") as f:
+            pickle.dump(self._multivariate_normals, f, pickle.HIGHEST_PROTOCOL)
+        logger.info(f"Finish saving all files for {self.label} model")
+
+    @classmethod
+    def from_folder(cls, model_folder_path: str) -> Self:
+        if not os.path.isdir(model_folder_path):
+            raise FileNotFoundError
+        model = cls(cls._model_folder_name_parser(model_folder_path))
+        with open(os.path.join(model_folder_path, "log_trans_probs.pickle"), "rb") as f:
+            model._log_transition_probs = pickle.load(f)
+        with open(os.path.join(model_folder_path, "multivariate_normals.pickle"), "rb") as f:
+            model._multivariate_normals = pickle.load(f)
+        return model
+
+    @staticmethod
+    def _model_folder_name_parser(folder_path: str) -> str:
+        return str(folder_path.split("/")[-1])
+
+
+# ----------------------------------------------------------------------------------------
+# M-step from device statistics (shared by the isolated and the embedded trainer)
+# ----------------------------------------------------------------------------------------
+def _unpack_stats(stats: np.ndarray, dim: int):
+    """stats [S, 1+D+D(D+1)/2] -> (N [S], s1 [S,D], S2 [S,D,D] symmetric)."""
+    S = stats.shape[0]
+    n = stats[:, 0]
+    s1 = stats[:, 1:1 + dim]
+    iu = np.triu_indices(dim)
+    s2 = np.zeros((S, dim, dim), dtype=np.float64)
+    s2[:, iu[0], iu[1]] = stats[:, 1 + dim:]
+    s2[:, iu[1], iu[0]] = stats[:, 1 + dim:]
+    return n, s1, s2
+
+
+@dataclass
+class HiddenMarkovModelTrainable(HiddenMarkovModel):
+    class HMMTrainMeanFail(Exception):
+        def __init__(self, *args: object) -> None:
+            super().__init__(*args)
+            logger.warning("Cannot use all the state for the HMM")
+
+    class HMMTrainConverge(Exception):
+        def __init__(self, *args: object) -> None:
+            super().__init__(*args)
+            logger.info("Successfully train the HMM model")
+
+    _means: NDArray[np.float32] = field(init=False)
+    _covariances: NDArray[np.float32] = field(init=False)
+    _transition_probs: TransitionProbabilities = field(init=False)
+
+    @property
+    def num_of_states(self) -> int:
+        return self._means.shape[0]
+
+    @classmethod
+    def from_data(cls, label: str, mfccs: List[NDArray[np.float32]], num_of_states: int = 5,
+                  max_iterations: int = 100, isMultiProcessingTraining: bool = True, isTqdm: bool = True) -> Self:
+        """Segmental K-means for one word (:233-281).  ``isMultiProcessingTraining`` is accepted for
+        compatibility; the E-step is one batched device pass either way.  Under an initialised
+        torch.distributed group the utterances are sharded by rank and the statistics summed with
+        one all-reduce per iteration (every rank returns the same model)."""
+        from . import _dist
+
+        model = cls(label, isMultiProcessing=isMultiProcessingTraining, isTqdm=isTqdm)
+        model._means, model._covariances, model._transition_probs = model._init_parameters(mfccs[0], num_of_states)
+        model._update_inference_weights()
+        eng = _engine()
+        shard = _dist.shard(list(mfccs))
+        batch = eng.upload_features(shard, mfccs[0].shape[1]) if len(shard) else None
+        bar = tqdm(desc=f"Train {model.label} model", total=max_iterations, position=1, disable=not model.isTqdm)
+        for it in range(max_iterations):
+            try:
+                model._train_device(batch)
+                model._update_inference_weights()
+            except cls.HMMTrainMeanFail:
+                logger.error("Failed to train model")
+                raise
+            except cls.HMMTrainConverge:
+                logger.info(f"Finish training model {str(model)} after {it} iterations")
+                break
+            bar.update()
+        bar.close()
+        model._update_inference_weights()
+        return model
+
+    def _update_inference_weights(self) -> None:
+        self._log_transition_probs = LogTransitionProbabilities.from_transition_probability(self._transition_probs)
+        self._multivariate_normals = self.get_multivariate_normals(self._means, self._covariances)
+
+    # -- E-step on the device ---------------------------------------------------------------
+    def _device_statistics(self, batch):
+        """Align ``batch`` with the current model and return (stats [S, stride], counts [S,S]) as
+        host float64 / int64 arrays, summed over ranks when torch.distributed is initialised."""
+        from . import _dist
+
+        eng = _engine()
+        S, D = self._means.shape
+        if batch is not None:
+            gp, tp = self._packs()
+            scores = eng.emission(batch.feat, gp)
+            path, _, _, _ = eng.viterbi(scores, batch.frm_off, batch.n_utt, batch.max_frames, batch.total_frames, tp,
+                                        want_end_scores=False)
+            shift = eng._to_dev(np.ascontiguousarray(self._means, dtype=np.float32))
+            stats, counts, _ = eng.kmeans_stats(batch.feat, path, batch.frm_off, batch.n_utt, batch.total_frames, tp,
+                                                None, False, S, shift)
+        else:
+            stats = eng.torch.zeros((S, 1 + D + D * (D + 1) // 2), dtype=eng.torch.float64, device=eng.device)
+            counts = eng.torch.zeros((S, S), dtype=eng.torch.int32, device=eng.device)
+        stats, counts = _dist.allreduce_stats(stats, counts)
+        return stats.cpu().numpy(), counts.cpu().numpy().astype(np.int64)
+
+    def _train_device(self, batch) -> None:
+        stats, counts = self._device_statistics(batch)
+        self._update_from_statistics(stats, counts, shift=self._means.astype(np.float64))
+
+    def _train(self, mfccs: List[NDArray[np.float32]]) -> None:
+        """One iteration over a list of feature matrices (:294-318)."""
+        self._train_device(_engine().upload_features(mfccs, mfccs[0].shape[1]))
+
+    def _update_from_statistics(self, stats: np.ndarray, counts: np.ndarray, shift: np.ndarray) -> None:
+        """M-step (:320-350) from sufficient statistics accumulated around ``shift``:
+        means, the means-only convergence test BEFORE covariances / transitions are touched,
+        np.cov-style covariance (N-1) + 1e-3 I, row-normalised transition counts."""
+        S, D = shift.shape
+        n, s1, s2 = _unpack_stats(stats, D)
+        if np.any(n == 0):
+            raise self.HMMTrainMeanFail
+        new_means = (shift + s1 / n[:, None]).astype(np.float32)
+        if np.allclose(new_means, self._means):
+            raise self.HMMTrainConverge
+        self._means = new_means
+        with np.errstate(all="ignore"):
+            centred = s2 - s1[:, :, None] * s1[:, None, :] / n[:, None, None]
+            cov = centred / (n - 1.0)[:, None, None]
+            self._covariances = (cov + np.eye(D) * 0.001).astype(np.float32)
+            probs = (counts / np.sum(counts, axis=1, keepdims=True)).astype(np.float32)
+        self._transition_probs = TransitionProbabilities.from_transition_probability(probs)
+
+    def _update_middleware_parameters(self, sorted_signals: SortedSignals) -> None:
+        """Reference entry point (:320-350) for hand-built SortedSignals: the frames are shipped to
+        the device once and reduced by the statistics kernel."""
+        eng = _engine()
+        sigs = sorted_signals._signals
+        S, D = self._means.shape
+        if not sigs:
+            raise self.HMMTrainMeanFail
+        feats = [np.asarray(s.signal, dtype=np.float32) for s in sigs]
+        batch = eng.upload_features(feats, D)
+        path = eng._to_dev(np.concatenate([np.asarray(s.path, dtype=np.int8) for s in sigs]))
+        tp = eng.pack_trellises([_trellis.build([np.zeros((S, S), np.float32)], [0], [0], "word")])
+        shift = eng._to_dev(np.ascontiguousarray(self._means, dtype=np.float32))
+        stats, counts, _ = eng.kmeans_stats(batch.feat, path, batch.frm_off, batch.n_utt, batch.total_frames, tp,
+                                            None, False, S, shift)
+        self._update_from_statistics(stats.cpu().numpy(), counts.cpu().numpy().astype(np.int64),
+                                     shift=self._means.astype(np.float64))
+
+    def _train_external(self, signals: List[Signal]) -> None:
+        sorted_signals = SortedSignals(self.num_of_states)
+        for s in signals:
+            sorted_signals.append(s)
+        self._update_middleware_parameters(sorted_signals)
+
+    @classmethod
+    def _init_parameters(cls, sample_signal: NDArray[np.float32], num_of_states: int):
+        """Uniform segmentation of the FIRST utterance, covariance 0.01 I, uniform forward
+        transitions (:359-389).  One utterance: host arithmetic."""
+        D = sample_signal.shape[1]
+        seg = int(sample_signal.shape[0] / num_of_states)
+        means = np.array([np.average(sample_signal[i * seg:(i + 1) * seg, :], axis=0) for i in range(num_of_states)],
+                         dtype=np.float32)
+        return means, cls._init_covariance(D, num_of_states), TransitionProbabilities.from_num_of_states(num_of_states)
+
+    @staticmethod
+    def _init_covariance(dim_of_features: int, num_of_states: int) -> NDArray[np.float32]:
+        return (np.tile(np.eye(dim_of_features), (num_of_states, 1, 1)) * 0.01).astype(np.float32)
+
+    @staticmethod
+    def get_multivariate_normals(means: NDArray[np.float32], covariances: NDArray[np.float32]) -> List[MultivariateNormal]:
+        return [MultivariateNormal.from_means_covariances(mean=m, covariance=c) for m, c in zip(means, covariances)]
+
+
+# ----------------------------------------------------------------------------------------
+# digit-loop decoder (:413-581)
+# ----------------------------------------------------------------------------------------
+def _penalty_args(penalty) -> Tuple[float, bool]:
+    """np.float64 penalties (the default np.log(0.005)) make the reference evaluate word-start
+    candidates in float64; Python scalars and np.float32 are weak and stay float32."""
+    f64 = isinstance(penalty, np.float64) or (isinstance(penalty, np.ndarray) and penalty.dtype == np.float64)
+    return float(penalty), bool(f64)
+
+
+@dataclass
+class HiddenMarkovModelInference(_PackCache):
+    _multivariate_normals: List[MultivariateNormal] = field(default_factory=list)
+    _log_transition_probs: LogTransitionProbabilities = field(init=False)
+    _model_boundaries: ModelBoundary = field(init=False)
+    _log_transition_probability_between_words: float = field(default=np.log(0.005))
+
+    @classmethod
+    def from_folder(cls, folder_path: str, models_to_load: List[str]) -> Self:
+        inf = cls()
+        ltp = LogTransitionProbabilities()
+        normals: List[MultivariateNormal] = []
+        labels: List[str] = []
+        mb = ModelBoundary()
+        for name in sorted(os.listdir(folder_path)):
+            path = os.path.join(folder_path, name)
+            label = HiddenMarkovModel._model_folder_name_parser(path)
+            if label not in models_to_load:
+                continue
+            hmm = HiddenMarkovModel.from_folder(path)
+            ltp.append(hmm._log_transition_probs)
+            normals.extend(hmm._multivariate_normals)
+            mb.append(hmm.num_of_states)
+            labels.append(label)
+        inf._log_transition_probs = ltp
+        inf._multivariate_normals = normals
+        mb.add_model_labels(labels)
+        inf._model_boundaries = mb
+        return inf
+
+    @classmethod
+    def from_models(cls, models: Sequence[HiddenMarkovModel]) -> Self:
+        """Same as from_folder for in-memory word models, in the order given (added)."""
+        inf = cls()
+        ltp = LogTransitionProbabilities()
+        mb = ModelBoundary()
+        normals: List[MultivariateNormal] = []
+        for m in models:
+            ltp.append(m._log_transition_probs)
+            normals.extend(m._multivariate_normals)
+            mb.append(len(m._multivariate_normals))
+        mb.add_model_labels([m.label for m in models])
+        inf._log_transition_probs, inf._multivariate_normals, inf._model_boundaries = ltp, normals, mb
+        return inf
+
+    def _packs(self):
+        def build():
+            eng = _engine()
+            mb = self._model_boundaries
+            dense = self._log_transition_probs.to_dense()
+            lows, sizes = mb.lower_boundaries, mb.sizes
+            blocks = [dense[a:a + n, a:a + n] for a, n in zip(lows, sizes)]
+            tr = _trellis.build(blocks, lows, list(range(len(sizes))), "loop")
+            return eng.pack_gaussians(self._multivariate_normals), eng.pack_trellises([tr])
+        return self._cached(_model_key(self._multivariate_normals, self._log_transition_probs), build)
+
+    def predict(self, signal: NDArray[np.float32]) -> str:
+        score, path = self._viterbi(observation_sequence=signal)
+        return "".join(self._model_boundaries.get_labels(path))
+
+    def _viterbi(self, observation_sequence: NDArray[np.float32]) -> Tuple[float, NDArray[np.int8]]:
+        scores, paths = self.viterbi_batch([observation_sequence])
+        return scores[0], paths[0]
+
+    def viterbi_batch(self, signals: Sequence[NDArray[np.float32]], precision: Optional[str] = None):
+        eng = _engine()
+        batch = eng.upload_features(signals, self._multivariate_normals[0].dim_of_features)
+        best_score, path = self._decode_device(batch, precision)
+        path_h = path.cpu().numpy()
+        off = batch.frm_off_host
+        return best_score.cpu().numpy(), [path_h[off[i]:off[i + 1]] for i in range(batch.n_utt)]
+
+    def _decode_device(self, batch, precision: Optional[str] = None):
+        """features (device) -> (best_score [n], path [F]) on the device: two launches."""
+        eng = _engine()
+        gp, tp = self._packs()
+        pen, f64 = _penalty_args(self._log_transition_probability_between_words)   # read per call: scripts poke it
+        scores = eng.emission(batch.feat, gp, precision)
+        path, _, _, best_score = eng.viterbi(scores, batch.frm_off, batch.n_utt, batch.max_frames, batch.total_frames, tp,
+                                             loop=True, penalty=pen, penalty_f64=f64, want_end_scores=False)
+        return best_score, path
+
+    def predict_batch(self, signals: Sequence[NDArray[np.float32]], precision: Optional[str] = None) -> List[str]:
+        """Digit strings of many (T, 39) feature matrices in one pass (added entry point)."""
+        _, paths = self.viterbi_batch(signals, precision)
+        return ["".join(self._model_boundaries.get_labels(p)) for p in paths]
+
+    def decode_pcm_batch(self, signals: Sequence[NDArray], sample_rate: int = 16000, precision: Optional[str] = None) -> List[str]:
+        """Raw PCM -> digit strings, everything between the H2D copy of the samples and the D2H
+        copy of the state paths on the device (MFCC -> emission -> Viterbi; added entry point)."""
+        eng = _engine()
+        batch = eng.mfcc(signals, sample_rate)
+        _, path = self._decode_device(batch, precision)
+        path_h = path.cpu().numpy()
+        off = batch.frm_off_host
+        return ["".join(self._model_boundaries.get_labels(path_h[off[i]:off[i + 1]])) for i in range(batch.n_utt)]
+
+
+# ----------------------------------------------------------------------------------------
+# embedded ("continuous") training (:584-797)
+# ----------------------------------------------------------------------------------------
+@dataclass
+class HiddenMarkovModelMultiWord(HiddenMarkovModel):
+    _model_boundaries: ModelBoundary = field(init=False)
+
+    def _host_trellis(self) -> _trellis.HostTrellis:
+        mb = self._model_boundaries
+        dense = self._log_transition_probs.to_dense()
+        lows, sizes = mb.lower_boundaries, mb.sizes
+        blocks = [dense[a:a + n, a:a + n] for a, n in zip(lows, sizes)]
+        uniq = {lab: i for i, lab in enumerate(dict.fromkeys(mb._labels))}
+        return _trellis.build(blocks, lows, [uniq[l] for l in mb._labels], "chain")
+
+    def get_remuexed_signals(self, mfccs_sequences: List[NDArray[np.float32]]) -> Dict[str, List[Signal]]:
+        out: Dict[str, List[Signal]] = {label: [] for label in self._model_boundaries._labels}
+        if len(mfccs_sequences) == 0:
+            return out
+        _, paths = self.predict_batch(mfccs_sequences)
+        for x, path in zip(mfccs_sequences, paths):
+            for label, sigs in self._remux_path_and_signal(x, path, self._model_boundaries).items():
+                out[label].extend(sigs)
+        return out
+
+    @staticmethod
+    def _remux_path_and_signal(signal, path, model_boundaries: ModelBoundary) -> Dict[str, List[Signal]]:
+        """Host version of the cut-per-word step (:602-636), kept for API compatibility; the
+        trainer itself uses loe_align_dev(remux=1) and never materialises these objects."""
+        out: Dict[str, List[Signal]] = {label: [] for label in model_boundaries._labels}
+        labels = [model_boundaries.get_label(int(s)) for s in path]
+        start = 0
+        for i in range(1, len(path)):
+            if labels[i] != labels[start]:
+                lo = model_boundaries.find_lower_boundary(int(path[start]))
+                hi = model_boundaries.find_upper_boundary(int(path[start]))
+                out[labels[start]].append(Signal(num_of_state=hi - lo + 1, signal=signal[start:i], path=path[start:i] - lo))
+                start = i
+        return out
+
+    @classmethod
+    def from_labels(cls, labels: str, trainable_models: Dict[str, HiddenMarkovModelTrainable]) -> Self:
+        hmm = cls(labels)
+        hmm.isTqdm = False
+        ltp = LogTransitionProbabilities()
+        normals: List[MultivariateNormal] = []
+        mb = ModelBoundary()
+        for label in labels:
+            ltp.append(trainable_models[label]._log_transition_probs)
+            normals.extend(trainable_models[label]._multivariate_normals)
+            mb.append(len(trainable_models[label]._multivariate_normals))
+        mb.add_model_labels(list(labels))
+        hmm._log_transition_probs, hmm._multivariate_normals, hmm._model_boundaries = ltp, normals, mb
+        return hmm
+
+
+@dataclass
+class HiddenMarkovModelTrainContinuous:
+    isTqdm: bool = field(default=True)
+    isMultiProcessing: bool = field(default=True)
+    _trainable_models: Dict[str, HiddenMarkovModelTrainable] = field(default_factory=dict)
+    _models_loaded: List[str] = field(default_factory=list)
+    _num_of_finished_models: int = field(default=0)
+
+    @classmethod
+    def from_folder(cls, folder_path: str, models_to_load: List[str]) -> Self:
+        """Seeds from saved isolated models; _means = 0, cov = 0.01 I and uniform transitions are
+        placeholders, only the loaded Gaussians / log-transitions carry the seed (:679-712)."""
+        tc = cls()
+        for name in sorted(os.listdir(folder_path)):
+            path = os.path.join(folder_path, name)
+            label = HiddenMarkovModel._model_folder_name_parser(path)
+            if label not in models_to_load:
+                continue
+            m = HiddenMarkovModelTrainable.from_folder(model_folder_path=path)
+            S, D = len(m._multivariate_normals), m._multivariate_normals[0].dim_of_features
+            m._means = np.zeros((S, D), dtype=np.float32)
+            m._covariances = m._init_covariance(D, S)
+            m._transition_probs = TransitionProbabilities.from_num_of_states(S)
+            tc._trainable_models[label] = m
+        tc._models_loaded = models_to_load
+        return tc
+
+    def train(self, labeled_mfccs: Dict[str, List[NDArray[np.float32]]], max_iterations: int = 100) -> None:
+        """Embedded re-estimation (:714-731).  The utterances are uploaded once; every iteration is
+        emission + chain Viterbi + align/remux + statistics on the device, then the per-word
+        M-step in the reference's order.  Sharded by rank under torch.distributed."""
+        from . import _dist
+
+        eng = _engine()
+        items = [(lab, x) for lab, xs in labeled_mfccs.items() for x in xs]
+        items = _dist.shard(items)
+        chains = list(dict.fromkeys(self.insert_silence(lab) for lab, _ in items))
+        chain_id = {c: i for i, c in enumerate(chains)}
+        batch = eng.upload_features([x for _, x in items]) if items else None
+        utt_tr = eng._to_dev(np.array([chain_id[self.insert_silence(lab)] for lab, _ in items], dtype=np.int32)) if items else None
+        bar = tqdm(total=max_iterations, desc="Training Iteration", disable=not self.isTqdm, position=0)
+        for it in range(max_iterations):
+            try:
+                stats, counts = self._device_statistics(batch, utt_tr, chains)
+                self._update_trainable_model_parameters(statistics=(stats, counts))
+            except HiddenMarkovModelTrainable.HMMTrainMeanFail:
+                logger.error("Failed to train model")
+                raise
+            except HiddenMarkovModelTrainable.HMMTrainConverge:
+                logger.info(f"Finish training model after {it} iterations")
+                break
+            bar.update()
+        bar.close()
+
+    # global emission table: the loaded word models side by side, in _trainable_models order
+    def _global_layout(self):
+        labels = list(self._trainable_models.keys())
+        sizes = [len(self._trainable_models[l]._multivariate_normals) for l in labels]
+        starts = np.concatenate(([0], np.cumsum(sizes)[:-1])).astype(int)
+        return labels, sizes, {l: int(s) for l, s in zip(labels, starts)}, int(sum(sizes))
+
+    def _device_statistics(self, batch, utt_tr, chains):
+        from . import _dist
+
+        eng = _engine()
+        labels, sizes, start, G = self._global_layout()
+        D = self._trainable_models[labels[0]]._multivariate_normals[0].dim_of_features
+        stride = 1 + D + D * (D + 1) // 2
+        if batch is not None:
+            normals = [mn for l in labels for mn in self._trainable_models[l]._multivariate_normals]
+            gp = eng.pack_gaussians(normals)
+            label_id = {l: i for i, l in enumerate(labels)}
+            trellises = []
+            for chain in chains:
+                dens = [self._trainable_models[c]._log_transition_probs.to_dense() for c in chain]
+                trellises.append(_trellis.build(dens, [start[c] for c in chain], [label_id[c] for c in chain], "chain"))
+            tp = eng.pack_trellises(trellises)
+            scores = eng.emission(batch.feat, gp)
+            path, _, _, _ = eng.viterbi(scores, batch.frm_off, batch.n_utt, batch.max_frames, batch.total_frames, tp,
+                                        utt_tr=utt_tr, want_end_scores=False)
+            shift = eng._to_dev(np.concatenate([np.asarray(self._trainable_models[l]._means, dtype=np.float32) for l in labels]))
+            stats, counts, _ = eng.kmeans_stats(batch.feat, path, batch.frm_off, batch.n_utt, batch.total_frames, tp,
+                                                utt_tr, True, G, shift)
+        else:
+            stats = eng.torch.zeros((G, stride), dtype=eng.torch.float64, device=eng.device)
+            counts = eng.torch.zeros((G, G), dtype=eng.torch.int32, device=eng.device)
+        stats, counts = _dist.allreduce_stats(stats, counts)
+        return stats.cpu().numpy(), counts.cpu().numpy().astype(np.int64)
+
+    def _train(self, labeled_mfccs: Dict[str, List[NDArray[np.float32]]]) -> Dict[str, List[Signal]]:
+        """Reference-shaped E-step (:733-752): per label string, forced alignment + remux."""
+        out: Dict[str, List[Signal]] = {label: [] for label in self._models_loaded}
+        for item in labeled_mfccs.items():
+            for lab, sigs in self._train_process(item).items():
+                out[lab].extend(sigs)
+        return out
+
+    def _train_process(self, labels_and_mfccs) -> Dict[str, List[Signal]]:
+        labels, mfccs = labels_and_mfccs
+        hmm = HiddenMarkovModelMultiWord.from_labels(self.insert_silence(labels), self._trainable_models)
+        return hmm.get_remuexed_signals(mfccs)
+
+    def _update_trainable_model_parameters(self, remuxed_signals: Optional[Dict[str, List[Signal]]] = None,
+                                           statistics=None) -> None:
+        """Per-word M-step in dict order with the reference's stop rule (:754-770): the counter of
+        converged models is CUMULATIVE across iterations and the stop fires when it equals the
+        number of models; words after the one that fired are not updated in that iteration."""
+        if statistics is None:
+            for label, signals in remuxed_signals.items():
+                self._one_word(label, lambda m, s=signals: m._train_external(s))
+            return
+        stats, counts = statistics
+        labels, sizes, start, _ = self._global_layout()
+        for label in (l for l in self._models_loaded if l in self._trainable_models):
+            a, n = start[label], len(self._trainable_models[label]._multivariate_normals)
+            self._one_word(label, lambda m, a=a, n=n: m._update_from_statistics(
+                stats[a:a + n], counts[a:a + n, a:a + n], shift=m._means.astype(np.float64)))
+
+    def _one_word(self, label, update) -> None:
+        model = self._trainable_models[label]
+        try:
+            update(model)
+        except HiddenMarkovModelTrainable.HMMTrainConverge:
+            self._num_of_finished_models += 1
+            if self._num_of_finished_models == len(self._trainable_models):
+                raise
+        finally:
+            model._update_inference_weights()
+
+    def save(self, folder_path: str) -> None:
+        os.makedirs(folder_path, exist_ok=True)
+        for model in self._trainable_models.values():
+            model.save(folder_path)
+
+    @staticmethod
+    def insert_silence(labels: str) -> str:
+        return "".join(f"S{c}" for c in labels) + "S"

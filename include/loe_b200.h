@@ -1,0 +1,166 @@
+/*
+ * loe_b200.h -- C ABI of the B200-native hot path of loe_speech_recognition.
+ *
+ * The reference (loeeeee/CS-304-Speech-Recognition-Code) is pure Python and has no
+ * FFI / plugin interface; its boundary is the Python package API.  This header is the
+ * flat C boundary that sits directly under those classes: every entry point names the
+ * reference function(s) it replaces (paths relative to src/loe_speech_recognition/).
+ * The reference-side binding (ctypes) is shown in INTEGRATION.md and implemented in
+ * cs-304-speech-recognition-code_b200/loe_speech_recognition/_native.py.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / numpy types.
+ *   - every *_dev pointer is DEVICE memory on the current CUDA device; `stream` is a
+ *     cudaStream_t passed as void* (NULL = legacy default stream).  Calls are
+ *     asynchronous on that stream and never synchronise or allocate.
+ *   - no ownership transfer: the caller owns every buffer.
+ *   - return value: LOE_OK or an error code mapped 1:1 to the Python exception the
+ *     reference raises at the same API point (see loe_status).  loe_last_error()
+ *     returns a thread-local message for the last failing call.
+ *   - there is NO CPU fallback: without a CUDA device every compute call returns
+ *     LOE_ERR_CUDA.
+ */
+#ifndef LOE_B200_H
+#define LOE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum loe_status {
+    LOE_OK = 0,
+    LOE_ERR_CUDA = 1,        /* RuntimeError: CUDA failure (message has the cudaError string)      */
+    LOE_ERR_VALUE = 2,       /* ValueError: bad argument (e.g. < 9 frames for the delta filter,
+                                mfcc.py:39 -> scipy savgol_filter)                                    */
+    LOE_ERR_OVERFLOW = 3,    /* OverflowError: more than 128 trellis positions; the reference's
+                                tracer/path are int8 (hidden_markov_model.py:175, 498-501)          */
+    LOE_ERR_DIM = 4,         /* AssertionError: feature dimension mismatch (hidden_markov_model.py:76-77) */
+    LOE_ERR_UNSUPPORTED = 5  /* NotImplementedError: configuration outside the built kernels       */
+} loe_status;
+
+#define LOE_ABI_VERSION 1
+#define LOE_MAX_POS 128          /* trellis positions per utterance (int8 path, see above)          */
+#define LOE_N_MELS 40
+#define LOE_N_FFT 320
+#define LOE_HOP 160
+#define LOE_N_BINS 161
+#define LOE_MEL_MAXW 32          /* widest supported mel filter, in FFT bins                         */
+
+/* trellis position flags (loe_viterbi_dev / loe_align_dev) */
+#define LOE_POS_INIT 1           /* receives logpdf(x_0) + self-loop at t = 0                        */
+#define LOE_POS_START 2          /* word start of the loop grammar (cross-word rule applies)         */
+#define LOE_POS_END 4            /* termination candidate / word end                                 */
+
+int loe_abi_version(void);
+const char* loe_last_error(void);
+/* number of CUDA devices visible, or a negative loe_status */
+int loe_device_count(void);
+
+/* --------------------------------------------------------------------------------------
+ * MFCC front end.  Replaces MFCC.__post_init__ / MFCC.normalize_mfccs / MFCC.batch
+ * (mfcc.py:24-44, 50-69, 71-84) and the librosa calls behind them (melspectrogram
+ * n_fft=320 hop=160 periodic Hann centre-padded, slaney mel 40 bands, power_to_db with the
+ * per-utterance maximum as reference and top_db=80, DCT-II ortho 13 ceps, Savitzky-Golay
+ * delta / delta-delta of width 9, per-frame normalisation of the static block).
+ *
+ *   pcm_dev      [total_samples] float32 PCM at int16 scale, utterances back to back
+ *   pcm_off_dev  [n_utt+1] int64 sample offsets
+ *   frm_off_dev  [n_utt+1] int64 frame offsets, frames(u) = 1 + samples(u)/160
+ *   max_frames   max_u frames(u)            min_frames  min_u frames(u) (must be >= 9)
+ *   mel_start_dev[40] int32, mel_len_dev[40] int32, mel_w_dev[LOE_MEL_MAXW*40] float32:
+ *                sparse slaney filterbank, weight j of filter m at mel_w[j*40+m]
+ *   mel_ws_dev   [total_frames*40] float32 workspace (mel energies)
+ *   utt_max_dev  [n_utt] float32 workspace (per-utterance mel maximum)
+ *   feat_dev     [total_frames*39] float32 out, row-major (frame, coefficient): the
+ *                transposed (T,39) layout MFCC.batch hands to the HMM code
+ * -------------------------------------------------------------------------------------- */
+int loe_mfcc_dev(const float* pcm_dev, const int64_t* pcm_off_dev, const int64_t* frm_off_dev,
+                 int n_utt, int64_t total_frames, int max_frames, int min_frames,
+                 const int32_t* mel_start_dev, const int32_t* mel_len_dev, const float* mel_w_dev,
+                 float* mel_ws_dev, float* utt_max_dev, float* feat_dev, void* stream);
+
+/* --------------------------------------------------------------------------------------
+ * Gaussian emission scoring.  Replaces MultivariateNormal.log_pdf
+ * (hidden_markov_model.py:46-48 -> scipy multivariate_normal_frozen.logpdf) for every
+ * (frame, state) pair at once:
+ *     out[f*ld_out + s] = cst[s] - 0.5 * | (x_f - mean_s) . U_s |^2
+ * with U_s = V diag(lambda^-1/2) (scipy _PSD.U) and cst = -0.5*(D log 2pi + log_pdet).
+ *
+ *   feat_dev [n_frames*dim] float32;  mean_dev [n_states*dim];  u_dev [n_states*dim*dim]
+ *   (row i, column j at u[(s*dim+i)*dim+j]);  cst_dev [n_states]
+ *   precision: 0 = float32 SIMT, 1 = float64 SIMT (mean/u/cst are then double arrays),
+ *              2 = 3xTF32 tcgen05 tensor-core path (float32 arrays; needs dim == 39)
+ * -------------------------------------------------------------------------------------- */
+int loe_emission_dev(const float* feat_dev, int64_t n_frames, int dim,
+                     const void* mean_dev, const void* u_dev, const void* cst_dev, int n_states,
+                     float* out_dev, int ld_out, int precision, void* stream);
+
+/* --------------------------------------------------------------------------------------
+ * Viterbi + backtrace, one CTA per utterance.  Replaces HiddenMarkovModel._viterbi /
+ * _viterbi_static (hidden_markov_model.py:80-91, 160-208), HiddenMarkovModelInference.
+ * _viterbi / _viterbi_static (:463-581) and the forced alignment of
+ * HiddenMarkovModelMultiWord (:591), bit for bit (float32 recursion, lowest-index
+ * tie-breaking, "all -inf -> back-pointer 0", off-by-one backtrace, float64 word-penalty mode).
+ *
+ * A trellis is a list of positions; trellis k owns positions [tr_off[k], tr_off[k+1]).
+ *   col   [n_pos_total] int32   emission column of the position in `scores`
+ *   band  [n_pos_total*3] float32 log-transition into p from p, p-1, p-2 (-inf = not allowed)
+ *   flags [n_pos_total] uint8   LOE_POS_* bits
+ *   utt_tr_dev [n_utt] int32 trellis of each utterance (NULL: all use trellis 0)
+ *   loop: 0 = left-to-right only; 1 = digit-loop grammar (START positions additionally take
+ *         max over END positions + penalty, ties -> lowest END, self loop last)
+ *   penalty / penalty_f64: word-transition log penalty; penalty_f64 != 0 reproduces the
+ *         reference when the attribute is an np.float64 (the default np.log(0.005))
+ *   scores_dev [total_frames*ld] float32 from loe_emission_dev
+ *   path_dev   [total_frames] int8 out (position index local to the trellis; -1 when T == 1)
+ *   end_scores_dev [n_utt*max_ends] float32 out (may be NULL), END positions in order
+ *   best_dev   [n_utt] int32 out: index (among END positions) of the best end
+ *   best_score_dev [n_utt] float32 out
+ *   bp_ws_dev  workspace of total_frames*LOE_MAX_POS bytes, only used when the back-pointers
+ *              of the longest utterance do not fit in shared memory (may be NULL otherwise;
+ *              loe_viterbi_bp_fits tells)
+ * -------------------------------------------------------------------------------------- */
+int loe_viterbi_bp_fits(int max_frames, int max_pos);
+int loe_viterbi_dev(const float* scores_dev, int ld, const int64_t* frm_off_dev, int n_utt, int max_frames,
+                    const int32_t* tr_off_dev, const int32_t* col_dev, const float* band_dev,
+                    const uint8_t* flags_dev, int max_pos, const int32_t* utt_tr_dev,
+                    int loop, double penalty, int penalty_f64,
+                    int8_t* path_dev, float* end_scores_dev, int max_ends,
+                    int32_t* best_dev, float* best_score_dev, uint8_t* bp_ws_dev, void* stream);
+
+/* --------------------------------------------------------------------------------------
+ * Segmental K-means sufficient statistics.  Replaces Signal.order_by_state,
+ * SortedSignals.order_by_state / .transition_probabilities (signal.py:23-47, 68-91), the
+ * accumulation half of HiddenMarkovModelTrainable._update_middleware_parameters
+ * (hidden_markov_model.py:320-350) and HiddenMarkovModelMultiWord._remux_path_and_signal
+ * (:602-636).
+ *
+ * loe_align_dev: turns alignments into per-frame bucket ids (global state of the word model
+ * the frame is credited to, 0xFFFF = not credited) and transition counts.
+ *   word_dev [n_pos_total] int32 word-instance label id of each trellis position (positions
+ *            of one word instance are contiguous); word_lo_dev [n_pos_total] int32 first
+ *            position (local to the trellis) of the instance the position belongs to
+ *   remux: 0 = the whole utterance is one Signal (isolated training);
+ *          1 = cut where the label changes, re-base, and DROP the final piece (:614-636)
+ *   bucket_dev [total_frames] uint16 out;  counts_dev [n_glob*n_glob] int32, accumulated
+ *            (caller zeroes): counts[g_from*n_glob + g_to]
+ * loe_kmeans_dev: per bucket g:  stats[g*stride + 0] = N,  [1..D] = sum(x - shift_g),
+ *   then the upper triangle (row-major, i <= j) of sum (x-shift_g)(x-shift_g)^T, all float64,
+ *   stride = 1 + D + D(D+1)/2.  Deterministic (fixed chunking and reduction order).
+ *   shift_dev [n_glob*dim] float32 (typically the previous means);  part_ws_dev workspace of
+ *   loe_kmeans_ws_doubles(total_frames, n_glob, dim) doubles.
+ * -------------------------------------------------------------------------------------- */
+int loe_align_dev(const int8_t* path_dev, const int64_t* frm_off_dev, int n_utt,
+                  const int32_t* tr_off_dev, const int32_t* col_dev, const int32_t* word_dev,
+                  const int32_t* word_lo_dev, const int32_t* utt_tr_dev, int remux, int n_glob,
+                  uint16_t* bucket_dev, int32_t* counts_dev, void* stream);
+int64_t loe_kmeans_ws_doubles(int64_t total_frames, int n_glob, int dim);
+int loe_kmeans_dev(const float* feat_dev, const uint16_t* bucket_dev, int64_t total_frames, int dim,
+                   int n_glob, const float* shift_dev, double* part_ws_dev, double* stats_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LOE_B200_H */

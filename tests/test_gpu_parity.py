@@ -1,0 +1,320 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the golden
+fixtures produced by the unmodified reference.  Bars (BASELINE.json north_star): features and
+log-likelihoods within 1e-4 relative; state paths and digit strings bit-exact given the same
+emission scores, and on every utterance whose margin exceeds the float tolerance otherwise."""
+import numpy as np
+import pytest
+
+from helpers import LOOP_ORDER, N_STATES, WORDS, oracle_flat, rel_close, trained_word_model
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng(built_lib):
+    from loe_speech_recognition._engine import get_engine
+    return get_engine()
+
+
+# ------------------------------------------------------------------ a1 MFCC
+def test_mfcc_matches_oracle_golden(eng, golden_mfcc):
+    from loe_speech_recognition import MFCC
+    pcms = [golden_mfcc[f"pcm{i}"] for i in range(4)]
+    got = MFCC.batch(pcms, sample_rate=16000)
+    for i, g in enumerate(got):
+        ref = golden_mfcc[f"feat{i}"].T
+        assert g.shape == ref.shape and g.dtype == np.float32
+        atol = 1e-4 * np.abs(ref[:, :13]).max()          # floor for delta terms near zero
+        assert rel_close(g, ref, rtol=1e-4, atol=atol), (i, np.abs(g - ref).max())
+    single = MFCC(pcms[0], 16000).feature_vector
+    assert single.shape == (39, got[0].shape[0])
+    assert np.array_equal(single.T, got[0])
+
+
+def test_mfcc_ragged_batch_and_errors(eng):
+    from loe_speech_recognition import MFCC
+    from oracle import mfcc as OM
+    rng = np.random.default_rng(3)
+    lens = [1440, 1441, 1599, 1600, 5000, 16000, 64000, 12345]
+    pcms = [rng.normal(0, 1000, size=n).round().astype(np.float32) for n in lens]
+    got = MFCC.batch(pcms, 16000)
+    for p, g in zip(pcms, got):
+        ref = OM.mfcc_feature_vector(p).T
+        assert g.shape == ref.shape
+        assert rel_close(g, ref, rtol=1e-4, atol=1e-4 * np.abs(ref[:, :13]).max())
+    with pytest.raises(ValueError):
+        MFCC.batch([np.zeros(1000, np.float32)], 16000)      # 7 frames < 9: savgol_filter raises in the reference
+    with pytest.raises(TypeError):
+        MFCC([1.0, 2.0], 16000)
+    with pytest.raises(ValueError):
+        MFCC(np.zeros((2, 2000), np.float32), 16000)
+    assert MFCC.batch([], 16000) == []
+    z = MFCC.batch([np.zeros(4000, np.float32)], 16000)[0]   # digital silence: all-equal dB -> zero cepstra
+    assert np.all(np.isfinite(z))
+
+
+# ------------------------------------------------------------------ a2 emission
+@pytest.mark.parametrize("precision,rtol", [("fp32", 1e-4), ("fp64", 1e-6)])
+def test_emission_matches_scipy(eng, golden, precision, rtol):
+    from oracle import hmm as O
+    x = np.concatenate([golden[f"iso_feat_{i}"] for i in range(6)])
+    for w in ("1", "S", "Z"):
+        m = trained_word_model(golden, w)
+        gp = eng.pack_gaussians(m._multivariate_normals)
+        got = eng.emission(eng._to_dev(x), gp, precision).cpu().numpy()
+        means, Us, lps, _ = oracle_flat(golden, w)
+        ref = O.emission_scores(x, means, Us, lps)
+        assert got.shape == ref.shape
+        assert rel_close(got, ref, rtol=rtol), np.abs(got / ref - 1).max()
+        if precision == "fp64":
+            assert np.mean(got == ref) > 0.999       # float64 arithmetic, one rounding: bit-identical almost everywhere
+
+
+def test_emission_ill_conditioned(eng):
+    """Covariances with condition number up to 1e6 (only +1e-3 I regularises real ones)."""
+    from oracle import hmm as O
+    from loe_speech_recognition.hidden_markov_model import MultivariateNormal
+    rng = np.random.default_rng(11)
+    D = 39
+    q, _ = np.linalg.qr(rng.normal(size=(D, D)))
+    lam = np.logspace(-3, 3, D)
+    cov = ((q * lam) @ q.T).astype(np.float32)
+    cov = (cov + cov.T) / 2
+    mean = rng.normal(0, 3, size=D).astype(np.float32)
+    mn = MultivariateNormal.from_means_covariances(mean, cov)
+    x = (mean + rng.normal(size=(300, D)) * np.sqrt(lam).mean()).astype(np.float32)
+    gp = eng.pack_gaussians([mn])
+    ref = O.emission_scores(x, *[np.array([v]) for v in O.gaussian_pack(mean, cov)])
+    for precision in ("fp32", "fp64"):
+        got = eng.emission(eng._to_dev(x), gp, precision).cpu().numpy()
+        assert rel_close(got, ref, rtol=1e-4), (precision, np.abs(got / ref - 1).max())
+
+
+# ------------------------------------------------------------------ a3 word Viterbi
+def test_word_viterbi_bit_exact_given_scores(eng, golden):
+    """Feed the ORACLE's float32 emission scores to the Viterbi kernel: score and path must be
+    bit-identical to the reference's (golden) output."""
+    from loe_speech_recognition import _trellis
+    order = [str(s) for s in golden["iso_model_order"]]
+    for i in range(22):
+        x = golden[f"iso_feat_{i}"]
+        for k, w in enumerate(order):
+            from oracle import hmm as O
+            means, Us, lps, logA = oracle_flat(golden, w)
+            em = O.emission_scores(x, means, Us, lps)
+            tp = eng.pack_trellises([_trellis.build([logA], [0], [0], "word")])
+            T = x.shape[0]
+            off = eng._to_dev(np.array([0, T], dtype=np.int64))
+            path, _, _, bs = eng.viterbi(eng._to_dev(em), off, 1, T, T, tp, want_end_scores=False)
+            assert bs.cpu().numpy()[0] == golden["iso_scores"][i, k]
+            assert np.array_equal(path.cpu().numpy(), golden["iso_paths_" + str(i)][k])
+
+
+def test_isolated_predict_end_to_end(eng, golden):
+    """HiddenMarkovModel.predict / ModelCollection.predict with GPU emission (fp32 and fp64)."""
+    from loe_speech_recognition import ModelCollection
+    order = [str(s) for s in golden["iso_model_order"]]
+    models = {w: trained_word_model(golden, w) for w in order}
+    mc = ModelCollection()
+    mc._models = [models[w] for w in order]
+    feats = [golden[f"iso_feat_{i}"] for i in range(22)]
+    for precision in ("fp32", "fp64"):
+        sc = mc.scores_batch(feats, precision)
+        assert rel_close(sc, golden["iso_scores"], rtol=1e-4)
+        assert mc.predict_batch(feats, precision) == [str(s) for s in golden["iso_labels"]]
+        for k, w in enumerate(order[:3]):
+            s, paths = models[w].predict_batch(feats, precision)
+            assert rel_close(s, golden["iso_scores"][:, k], rtol=1e-4)
+            same = [np.array_equal(p, golden[f"iso_paths_{i}"][k]) for i, p in enumerate(paths)]
+            assert np.mean(same) >= (1.0 if precision == "fp64" else 0.9)
+    score, path = models["1"].predict(feats[0])
+    assert isinstance(score, np.float32) and path.dtype == np.int8 and path.shape == (feats[0].shape[0],)
+    assert mc.predict(feats[0]) == str(golden["iso_labels"][0])
+    with pytest.raises(AssertionError):
+        models["1"].predict(np.zeros((20, 13), np.float32))
+
+
+# ------------------------------------------------------------------ a4 loop Viterbi
+def _loop_inference(golden):
+    from loe_speech_recognition import HiddenMarkovModelInference
+    return HiddenMarkovModelInference.from_models([trained_word_model(golden, w) for w in LOOP_ORDER])
+
+
+PENALTIES = {"int": -100, "f64": np.log(0.005), "pyfloat": -37.25, "zero": 0}
+
+
+@pytest.mark.parametrize("name", list(PENALTIES))
+def test_loop_viterbi_bit_exact_given_scores(eng, golden, name):
+    from oracle import hmm as O
+    inf = _loop_inference(golden)
+    gp, tp = inf._packs()
+    flat = [oracle_flat(golden, w) for w in LOOP_ORDER]
+    means = np.concatenate([f[0] for f in flat]); Us = np.concatenate([f[1] for f in flat]); lps = np.concatenate([f[2] for f in flat])
+    from loe_speech_recognition.hidden_markov_model import _penalty_args
+    pen, f64 = _penalty_args(PENALTIES[name])
+    assert f64 == (name == "f64")
+    for i in range(10):
+        x = golden[f"loop_feat_{i}"]
+        em = O.emission_scores(x, means, Us, lps)
+        T = x.shape[0]
+        off = eng._to_dev(np.array([0, T], dtype=np.int64))
+        path, _, _, bs = eng.viterbi(eng._to_dev(em), off, 1, T, T, tp, loop=True, penalty=pen, penalty_f64=f64,
+                                     want_end_scores=False)
+        assert bs.cpu().numpy()[0] == golden[f"loop_scores_{name}"][i], (name, i)
+        assert np.array_equal(path.cpu().numpy(), golden[f"loop_path_{name}_{i}"]), (name, i)
+
+
+@pytest.mark.parametrize("name", list(PENALTIES))
+def test_loop_decode_strings(eng, golden, name):
+    inf = _loop_inference(golden)
+    inf._log_transition_probability_between_words = PENALTIES[name]
+    feats = [golden[f"loop_feat_{i}"] for i in range(10)]
+    want = [str(s) for s in golden[f"loop_strings_{name}"]]
+    assert inf.predict_batch(feats, "fp64") == want
+    got32 = inf.predict_batch(feats, "fp32")
+    scores, paths = inf.viterbi_batch(feats, "fp32")
+    assert rel_close(scores, golden[f"loop_scores_{name}"], rtol=1e-4)
+    # fp32 emission: any differing path must be a near-tie (margin test)
+    for i, (g, w) in enumerate(zip(got32, want)):
+        if g != w:
+            assert abs(scores[i] - golden[f"loop_scores_{name}"][i]) <= 1e-4 * abs(scores[i])
+    assert inf.predict(feats[0]) == want[0]
+
+
+def test_edge_cases_short_utterances(eng, golden):
+    """T = 2, 3, 9 (unreachable end states: -inf scores, back-pointer 0) and T = 1 (path [-1])."""
+    inf = _loop_inference(golden)
+    inf._log_transition_probability_between_words = -100
+    word = trained_word_model(golden, "1")
+    x9 = golden["edge_feat"]
+    for T in (2, 3, 9):
+        x = np.ascontiguousarray(x9[:T])
+        s, p = inf._viterbi(x)
+        assert np.array_equal(p, golden[f"edge_loop_path_T{T}"])
+        ref = golden[f"edge_loop_score_T{T}"]
+        assert (np.isinf(ref) and np.isinf(s) and s < 0) or rel_close(s, ref, rtol=1e-4)
+        s, p = word.predict(x)
+        assert np.array_equal(p, golden[f"edge_word_path_T{T}"])
+        ref = golden[f"edge_word_score_T{T}"]
+        assert (np.isinf(ref) and np.isinf(s) and s < 0) or rel_close(s, ref, rtol=1e-4)
+    s, p = word.predict(np.ascontiguousarray(x9[:1]))
+    assert p.tolist() == [-1] and np.isinf(s)
+    with pytest.raises(Exception):
+        inf.predict(np.ascontiguousarray(x9[:1]))            # reference: bare Exception from ModelBoundary
+
+
+def test_too_many_states_overflow(eng, golden):
+    from loe_speech_recognition import HiddenMarkovModelInference
+    words = [trained_word_model(golden, "1") for _ in range(26)]   # 130 states > int8 range
+    inf = HiddenMarkovModelInference.from_models(words)
+    with pytest.raises(OverflowError):
+        inf.predict(golden["iso_feat_0"])
+
+
+# ------------------------------------------------------------------ a5 segmental K-means
+def test_isolated_training_matches_reference(eng, golden):
+    from loe_speech_recognition import HiddenMarkovModelTrainable
+    for w in WORDS:
+        feats = [golden[f"train_feat_{w}_{i}"] for i in range(64) if f"train_feat_{w}_{i}" in golden.files]
+        m = HiddenMarkovModelTrainable.from_data(w, feats, num_of_states=N_STATES[w], max_iterations=4,
+                                                 isMultiProcessingTraining=False, isTqdm=False)
+        assert rel_close(m._means, golden[f"train_means_{w}"], rtol=1e-4, atol=1e-5), w
+        assert rel_close(m._covariances, golden[f"train_covs_{w}"], rtol=1e-3, atol=1e-5), w
+        got = m._log_transition_probs.to_dense(); ref = golden[f"train_logA_{w}"]
+        assert np.array_equal(np.isnan(got), np.isnan(ref)) and np.array_equal(got[~np.isnan(got)], ref[~np.isnan(ref)]), w
+
+
+def test_kmeans_statistics_exact(eng, golden):
+    """Statistics kernel against the oracle M-step on the oracle's own alignments."""
+    from oracle import hmm as O
+    from loe_speech_recognition import Signal, HiddenMarkovModelTrainable
+    w = "3"
+    feats = [golden[f"train_feat_{w}_{i}"] for i in range(8)]
+    means, Us, lps, logA = oracle_flat(golden, w)
+    tr = O.word_trellis(logA)
+    paths = [O.viterbi(O.emission_scores(x, means, Us, lps), tr)[2] for x in feats]
+    ref = O.mstep(feats, paths, 5, old_means=None)
+    m = HiddenMarkovModelTrainable(w)
+    m._means = np.zeros((5, 39), np.float32)
+    m._covariances = m._init_covariance(39, 5)
+    m._train_external([Signal(5, x, p) for x, p in zip(feats, paths)])
+    assert rel_close(m._means, ref["means"], rtol=1e-6, atol=1e-6)
+    assert rel_close(m._covariances, ref["covs"], rtol=1e-4, atol=1e-6)
+    assert np.array_equal(m._transition_probs.to_dense(), ref["trans"])
+
+
+def test_training_empty_state_raises(eng, golden):
+    from loe_speech_recognition import HiddenMarkovModelTrainable, Signal
+    x = golden["train_feat_1_0"][:12]
+    m = HiddenMarkovModelTrainable("1")
+    m._means = np.zeros((3, 39), np.float32)
+    m._covariances = m._init_covariance(39, 3)
+    path = np.array([0] * 6 + [2] * 6, dtype=np.int8)          # state 1 never visited
+    with pytest.raises(HiddenMarkovModelTrainable.HMMTrainMeanFail):
+        m._train_external([Signal(3, x, path)])
+
+
+# ------------------------------------------------------------------ a6 embedded training
+def test_embedded_training_iteration_matches_reference(eng, golden, tmp_path):
+    from loe_speech_recognition import HiddenMarkovModelTrainContinuous
+    for w in WORDS:
+        trained_word_model(golden, w).save(str(tmp_path))
+    tc = HiddenMarkovModelTrainContinuous.from_folder(str(tmp_path), list(WORDS))
+    tc.isTqdm = False
+    assert tc.insert_silence("12") == "S1S2S"
+    labeled = {}
+    for lab in [str(s) for s in golden["emb_labels"]]:
+        labeled[lab] = [golden[f"emb_feat_{lab}_{i}"] for i in range(int(golden[f"emb_count_{lab}"]))]
+    tc.train(labeled, max_iterations=1)
+    for w in WORDS:
+        m = tc._trainable_models[w]
+        assert rel_close(m._means, golden[f"emb1_means_{w}"], rtol=1e-4, atol=1e-5), w
+        assert rel_close(m._covariances, golden[f"emb1_covs_{w}"], rtol=1e-3, atol=1e-5), w
+        got = m._log_transition_probs.to_dense(); ref = golden[f"emb1_logA_{w}"]
+        assert np.array_equal(np.isnan(got), np.isnan(ref)) and np.array_equal(got[~np.isnan(got)], ref[~np.isnan(ref)]), w
+    tc.save(str(tmp_path / "out"))
+    assert (tmp_path / "out" / "S" / "multivariate_normals.pickle").exists()
+
+
+# ------------------------------------------------------------------ full pipeline + full-size properties
+def test_pcm_to_strings_pipeline(eng, golden):
+    from loe_speech_recognition import MFCC
+    from loe_speech_recognition.synthetic import string_corpus
+    inf = _loop_inference(golden)
+    inf._log_transition_probability_between_words = -100
+    utts, truth = string_corpus(seed=20, n_utts=6, n_digits=7)
+    got = inf.decode_pcm_batch(utts)
+    feats = MFCC.batch(utts, 16000)
+    assert got == inf.predict_batch(feats)
+    want = [str(s) for s in golden["loop_strings_int"]][:6]
+    assert sum(g == w for g, w in zip(got, want)) >= 5
+
+
+def test_large_batch_properties(eng, golden):
+    """Config-2-sized property checks: batch result == per-utterance result, paths valid,
+    idempotent, and batched oracle agreement on a 200-utterance sample."""
+    from oracle import hmm as O
+    from loe_speech_recognition.synthetic import string_corpus
+    inf = _loop_inference(golden)
+    inf._log_transition_probability_between_words = -100
+    utts, _ = string_corpus(seed=77, n_utts=2000, n_digits=7)
+    b = eng.mfcc(utts)
+    score, path = inf._decode_device(b, "fp32")
+    score2, path2 = inf._decode_device(b, "fp32")
+    assert eng.torch.equal(path, path2) and eng.torch.equal(score, score2)
+    path_h = path.cpu().numpy(); off = b.frm_off_host
+    assert path_h.min() >= 0 and path_h.max() < 58
+    feat_h = b.feat.cpu().numpy()
+    flat = [oracle_flat(golden, w) for w in LOOP_ORDER]
+    means = np.concatenate([f[0] for f in flat]); Us = np.concatenate([f[1] for f in flat]); lps = np.concatenate([f[2] for f in flat])
+    tr = O.loop_trellis([f[3] for f in flat])
+    idx = list(range(0, 2000, 10))
+    ems = [O.emission_scores(feat_h[off[i]:off[i + 1]], means, Us, lps) for i in idx]
+    _, _, opaths = O.viterbi_batch(ems, tr, penalty=-100)
+    same = [np.array_equal(op, path_h[off[i]:off[i + 1]]) for i, op in zip(idx, opaths)]
+    assert np.mean(same) >= 0.97, np.mean(same)
+    # exact given the kernel's own scores
+    gp, tp = inf._packs()
+    sc = eng.emission(b.feat, gp, "fp32").cpu().numpy()
+    _, _, opaths2 = O.viterbi_batch([sc[off[i]:off[i + 1]] for i in idx], tr, penalty=-100)
+    assert all(np.array_equal(op, path_h[off[i]:off[i + 1]]) for i, op in zip(idx, opaths2))
