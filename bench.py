@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""Benchmark of the decode hot path (BASELINE.json metric: end-to-end decode utterances/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Workload (config.workload): BASELINE.json configs[1] -- continuous 7-digit string decode over the
+digit-loop grammar with a silence word (12 word models, 58 states, 39-dim features), 10 000
+synthetic 16 kHz utterances per GPU.  One "step" = one pass of the hot path over that batch:
+MFCC -> Gaussian emission scoring -> loop-grammar Viterbi + backtrace -> word labels.
+
+  value  utterances/s with the PCM already resident in HBM (whole job, all ranks)
+  e2e    same through the public API with HOST buffers: H2D of the pinned PCM, the four kernels,
+         D2H of the word ids, string assembly -- every step
+  roofline      dominant kernel (emission scoring), timed live with CUDA events
+  cpu_baseline  the reference's CPU path (oracle/ref_port.py: per-(frame,state) scipy calls, process
+                pool over utterances like the reference's scripts) on a bounded sample, rank 0, N=1
+
+Multi-GPU: one process per GPU (torchrun), utterances sharded, no data-path collective (weak scaling:
+every rank decodes its own 10 000 utterances); timing = max over ranks.
+
+--impl reference times the CPU port alone on the same workload (bounded sample per step).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "cs-304-speech-recognition-code_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "end-to-end decode utterances/sec"
+UNIT = "utt/s"
+LOOP_ORDER = ("1", "2", "3", "4", "5", "6", "7", "8", "9", "O", "S", "Z")   # sorted(os.listdir), hmm.py:431
+PENALTY = -100                                                              # project5_test_ndigits_with_sil.py:62
+FLOPS_PER_FRAME = 2 * 40 * 39 * 58                                          # 2(D+1)D S, S = 58
+
+
+def golden_params():
+    g = np.load(os.path.join(ROOT, "tests", "golden", "golden_hmm.npz"))
+    return {w: (g[f"train_means_{w}"], g[f"train_covs_{w}"], g[f"train_logA_{w}"]) for w in LOOP_ORDER}
+
+
+def make_corpus(seed: int, n_utts: int, pool: int):
+    """`pool` distinct synthetic 7-digit strings, tiled to n_utts (the kernels do identical work on
+    every copy; generating 10k distinct waveforms with NumPy would dominate the run time)."""
+    from loe_speech_recognition.synthetic import string_corpus
+    utts, truth = string_corpus(seed=seed, n_utts=min(pool, n_utts), n_digits=7)
+    reps = (n_utts + len(utts) - 1) // len(utts)
+    return (utts * reps)[:n_utts], (truth * reps)[:n_utts]
+
+
+# ------------------------------------------------------------------------------------------------
+def clocks_sampler_start(gpu_index: int):
+    path = tempfile.mktemp(suffix=".csv")
+    q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    try:
+        proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                 "-i", str(gpu_index)], stdout=open(path, "w"), stderr=subprocess.DEVNULL)
+    except Exception:
+        return None, path
+    return proc, path
+
+
+def clocks_sampler_stop(proc, path):
+    if proc is None:
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+    time.sleep(0.15)
+    proc.terminate()
+    try:
+        proc.wait(timeout=5)
+    except Exception:
+        proc.kill()
+    sm, mx, reasons = [], [], set()
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    try:
+        for line in open(path):
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(path)
+    except Exception:
+        pass
+    return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+            "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_port_args():
+    params = golden_params()
+    return ([params[w][0] for w in LOOP_ORDER], [params[w][1] for w in LOOP_ORDER], [params[w][2] for w in LOOP_ORDER],
+            list(LOOP_ORDER), PENALTY)
+
+
+def run_cpu_port(utts, workers):
+    from oracle import ref_port
+    t0 = time.perf_counter()
+    out = ref_port.decode_pool(cpu_port_args(), utts, workers)
+    return time.perf_counter() - t0, out
+
+
+def impl_reference(args):
+    """The reference's CPU path (port) on the same workload; rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_sample = max(2, min(cores, 64))
+    utts, _ = make_corpus(100, n_sample, n_sample)
+    frames = sum(1 + len(u) // 160 for u in utts)
+    for _ in range(args.warmup):
+        run_cpu_port(utts[: max(1, min(cores, 4))], cores)
+    times = []
+    for _ in range(args.steps):
+        dt, _ = run_cpu_port(utts, cores)
+        times.append(dt)
+    dt = float(np.mean(times))
+    value = n_sample / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": workload_config(n_sample, n_sample, "cpu"),
+        "frames_per_s": frames / dt,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{n_sample} utterances per step ({frames} frames), ProcessPoolExecutor({cores}) over utterances, "
+                                   "oracle/ref_port.py = per-(frame,state) scipy logpdf loops of the reference + restated librosa MFCC"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(n_utts, pool, where):
+    return {"workload": "BASELINE.json configs[1]: continuous 7-digit string Viterbi decode, digit-loop grammar with silence word "
+                        "(12 word models, 58 states, full-covariance Gaussians, D=39), synthetic 16 kHz utterances ~2.9-4.6 s",
+            "utterances_per_gpu": n_utts, "distinct_utterances": pool, "penalty": PENALTY,
+            "models": "tests/golden/golden_hmm.npz (trained by the unmodified reference on the synthetic corpus)",
+            "l2": "inputs larger than L2 (PCM batch >> 126 MB)" if where == "gpu" else "n/a", "where": where}
+
+
+# ------------------------------------------------------------------------------------------------
+def impl_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    sys.path.insert(0, PKG)
+    import build as _build
+    if rank == 0:
+        _build.build()
+    if world > 1:
+        dist.barrier()
+
+    from loe_speech_recognition import HiddenMarkovModel, HiddenMarkovModelInference, HiddenMarkovModelTrainable
+    from loe_speech_recognition._engine import Batch, get_engine
+    from loe_speech_recognition.transition_probability import LogTransitionProbabilities
+
+    eng = get_engine()
+    dev = eng.device
+    params = golden_params()
+    models = []
+    for w in LOOP_ORDER:
+        m = HiddenMarkovModel(w)
+        m._multivariate_normals = HiddenMarkovModelTrainable.get_multivariate_normals(params[w][0], params[w][1])
+        m._log_transition_probs = LogTransitionProbabilities.from_dense(params[w][2])
+        models.append(m)
+    inf = HiddenMarkovModelInference.from_models(models)
+    inf._log_transition_probability_between_words = PENALTY
+    precision = args.precision
+
+    utts, truth = make_corpus(100 + rank, args.utts, args.pool)
+    n = len(utts)
+    lens = np.array([len(u) for u in utts], dtype=np.int64)
+    pcm_off = np.concatenate(([0], np.cumsum(lens))).astype(np.int64)
+    frames = 1 + lens // 160
+    frm_off = np.concatenate(([0], np.cumsum(frames))).astype(np.int64)
+    F = int(frm_off[-1])
+    pinned = torch.empty(int(pcm_off[-1]), dtype=torch.float32).pin_memory()
+    pinned.numpy()[:] = np.concatenate(utts)
+    pcm_dev = pinned.to(dev)
+    pcm_off_dev = eng._to_dev(pcm_off)
+    frm_off_dev = eng._to_dev(frm_off)
+    max_t, min_t = int(frames.max()), int(frames.min())
+    feat = torch.empty((F, 39), dtype=torch.float32, device=dev)
+    mel_ws = torch.empty((F, 40), dtype=torch.float32, device=dev)
+    utt_max = torch.empty((n,), dtype=torch.float32, device=dev)
+    gp, tp = inf._packs()
+    skip = inf._model_boundaries._labels.index("S")
+    pen = float(PENALTY)
+
+    def step_device():
+        eng.mfcc_device(pcm_dev, pcm_off_dev, frm_off_dev, n, F, max_t, min_t, 16000, out=feat, mel_ws=mel_ws, utt_max=utt_max)
+        scores = eng.emission(feat, gp, precision)
+        path, _, _, best = eng.viterbi(scores, frm_off_dev, n, max_t, F, tp, loop=True, penalty=pen, penalty_f64=False,
+                                       want_end_scores=False)
+        words, count = eng.labels(path, frm_off_dev, n, tp, skip_label=skip, max_words=32)
+        return path, words, count
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- correctness gate: device path vs per-utterance public API on a few utterances
+    path, words, count = step_device()
+    torch.cuda.synchronize()
+    labels = inf._model_boundaries._labels
+    got = ["".join(labels[k] for k in words[i, :int(count[i])].tolist()) for i in range(4)]
+    from loe_speech_recognition import MFCC
+    want = [inf.predict(x) for x in MFCC.batch(utts[:4], 16000)]
+    assert got == want, (got, want)
+
+    # ---- device-resident throughput
+    for _ in range(args.warmup):
+        step_device()
+    launches0 = eng.launches
+    clk_proc, clk_path = clocks_sampler_start(local_rank)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step_device()
+    ev1.record()
+    barrier()
+    clocks = clocks_sampler_stop(clk_proc, clk_path)
+    ms = ev0.elapsed_time(ev1) / args.steps
+    launches = eng.launches - launches0
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * n / (ms * 1e-3)
+
+    # ---- per-stage timing (instrumented pass; explains the headline, not part of it)
+    stage_ms = {"mfcc": 0.0, "emission": 0.0, "viterbi": 0.0, "labels": 0.0}
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    for _ in range(args.steps):
+        evs[0].record()
+        eng.mfcc_device(pcm_dev, pcm_off_dev, frm_off_dev, n, F, max_t, min_t, 16000, out=feat, mel_ws=mel_ws, utt_max=utt_max)
+        evs[1].record()
+        scores = eng.emission(feat, gp, precision)
+        evs[2].record()
+        path, _, _, best = eng.viterbi(scores, frm_off_dev, n, max_t, F, tp, loop=True, penalty=pen, want_end_scores=False)
+        evs[3].record()
+        eng.labels(path, frm_off_dev, n, tp, skip_label=skip, max_words=32)
+        evs[4].record()
+        torch.cuda.synchronize()
+        for k, name in enumerate(stage_ms):
+            stage_ms[name] += evs[k].elapsed_time(evs[k + 1]) / args.steps
+
+    # ---- end to end through the public API with host buffers
+    for _ in range(max(1, min(args.warmup, 3))):
+        strings = inf.decode_pcm_flat(pinned, pcm_off, 16000, precision)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        strings = inf.decode_pcm_flat(pinned, pcm_off, 16000, precision)
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e_value = world * n / e2e_s
+    acc = float(np.mean([a == b for a, b in zip(strings, truth)]))
+    h2d = int(pinned.numel() * 4 + pcm_off.nbytes + frm_off.nbytes)
+    d2h = int(n * 32 + n * 4)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    bf16 = peaks.get("bf16_tflops", 1590.0)
+    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops burst / 2: TF32 dense is half the bf16 rate; TF32 is not in the file)" \
+        if peaks else "fallback 1590/2"
+    em_tflops = F * FLOPS_PER_FRAME / (stage_ms["emission"] * 1e-3) / 1e12
+    roofline = {"kernel": {"fp32": "emission_simt_kernel<float,39>", "fp64": "emission_simt_kernel<double,39>",
+                           "tc": "emission_tc_kernel"}[precision],
+                "bound": "tensor", "achieved": em_tflops, "peak": bf16 / 2, "unit": "TFLOP/s", "frac": em_tflops / (bf16 / 2),
+                "traffic": None, "peak_source": peak_src,
+                "algorithmic": f"{FLOPS_PER_FRAME} flop/frame x {F} frames per launch",
+                "ms_per_launch": stage_ms["emission"]}
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    other = {
+        "mfcc": {"bound": "hbm", "achieved_gbs": (4 * int(pcm_off[-1]) + 156 * F) / (stage_ms["mfcc"] * 1e-3) / 1e9, "peak_gbs": hbm},
+        "viterbi": {"bound": "hbm", "achieved_gbs": (4 * 58 * F + F) / (stage_ms["viterbi"] * 1e-3) / 1e9, "peak_gbs": hbm},
+    }
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": {"fp32": "f32", "fp64": "f64", "tc": "tf32x3"}[precision], "data": "synthetic",
+        "config": {**workload_config(n, min(args.pool, n), "gpu"), "frames_per_gpu": F, "emission": precision},
+        "frames_per_s": world * F / (ms * 1e-3),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_s * 1e3, "api": "HiddenMarkovModelInference.decode_pcm_flat (pinned host PCM in, digit strings out)",
+                "string_accuracy_vs_truth": acc},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": roofline,
+        "stage_ms": stage_ms,
+        "other_kernels": other,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        n_sample = max(2, min(2 * cores, 64))
+        dt, cpu_strings = run_cpu_port(utts[:n_sample], cores)
+        same = float(np.mean([a == b for a, b in zip(cpu_strings, strings[:n_sample])]))
+        line["cpu_baseline"] = {"value": n_sample / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"{n_sample} of the {n} utterances, ProcessPoolExecutor({cores}); oracle/ref_port.py "
+                                          "(reference's per-(frame,state) scipy loops + restated librosa MFCC)",
+                                "identical_strings_vs_gpu": same}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--utts", type=int, default=10000, help="utterances per GPU")
+    ap.add_argument("--pool", type=int, default=500, help="distinct synthetic utterances (tiled to --utts)")
+    ap.add_argument("--precision", default=os.environ.get("LOE_B200_EMISSION", "fp32"), choices=["fp32", "fp64", "tc"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        impl_reference(args)
+    else:
+        impl_b200(args)
+
+
+if __name__ == "__main__":
+    main()

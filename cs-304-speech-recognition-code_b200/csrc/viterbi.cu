@@ -22,7 +22,6 @@
 namespace loe {
 
 constexpr int kPrefetch = 8;
-constexpr int kMaxEnds = LOE_MAX_POS;
 
 struct VitArgs {
     const float* scores; int ld;
@@ -196,6 +195,44 @@ viterbi_kernel(VitArgs a) {
     for (int t = tid; t < T; t += blockDim.x) a.path[f0 + t] = s_path[t];
 }
 
+// path -> word ids (model_boundary.py:107-147), one thread per utterance
+__global__ void labels_kernel(const int8_t* __restrict__ path, const int64_t* __restrict__ frm_off, int n_utt,
+                              const int32_t* __restrict__ tr_off, const int32_t* __restrict__ word,
+                              const int32_t* __restrict__ word_lo, const int32_t* __restrict__ utt_tr, int skip_label,
+                              int8_t* __restrict__ words, int max_words, int32_t* __restrict__ count) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_utt) return;
+    const int64_t f0 = frm_off[u];
+    const int T = (int)(frm_off[u + 1] - f0);
+    const int tr = utt_tr ? utt_tr[u] : 0;
+    const int p0 = tr_off[tr];
+    const int P = tr_off[tr + 1] - p0;
+    int8_t* out = words + (int64_t)u * max_words;
+    int n = 0;
+    int lo = 0, hi = -1, prev = -1;
+    bool bad = T <= 0;
+    for (int t = 0; t < T && !bad; ++t) {
+        const int cur = path[f0 + t];
+        if (cur < 0 || cur >= P) { bad = true; break; }
+        if (t > 0 && cur == prev) continue;
+        bool emit = false;
+        if (t == 0 || cur < lo || cur > hi) {
+            lo = word_lo[p0 + cur];
+            hi = lo;
+            while (hi + 1 < P && word_lo[p0 + hi + 1] == lo) ++hi;
+            emit = true;
+        } else if (prev == hi && cur == lo) {
+            emit = true;
+        }
+        if (emit) {
+            const int lab = word[p0 + cur];
+            if (lab != skip_label) { if (n < max_words) out[n] = (int8_t)lab; ++n; }
+        }
+        prev = cur;
+    }
+    count[u] = bad ? -1 : n;
+}
+
 static size_t vit_smem_bytes(int max_frames, int max_pos, bool bp_in_smem) {
     size_t b = sizeof(float) * 2 * (max_pos + 2) + sizeof(int) * (max_pos + 4);
     if (bp_in_smem) b += (size_t)max_frames * max_pos;
@@ -249,5 +286,19 @@ extern "C" int loe_viterbi_dev(const float* scores_dev, int ld, const int64_t* f
     const int threads = ((max_pos + 31) / 32) * 32;
     viterbi_kernel<<<(unsigned)n_utt, threads, smem, s>>>(a);
     LOE_LAUNCH_CHECK("viterbi_kernel");
+    return LOE_OK;
+}
+
+extern "C" int loe_labels_dev(const int8_t* path_dev, const int64_t* frm_off_dev, int n_utt,
+                              const int32_t* tr_off_dev, const int32_t* word_dev, const int32_t* word_lo_dev,
+                              const int32_t* utt_tr_dev, int skip_label,
+                              int8_t* words_dev, int max_words, int32_t* count_dev, void* stream) {
+    using namespace loe;
+    if (n_utt <= 0) return LOE_OK;
+    if (max_words <= 0) { set_error("max_words must be positive"); return LOE_ERR_VALUE; }
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    labels_kernel<<<(unsigned)((n_utt + 127) / 128), 128, 0, s>>>(path_dev, frm_off_dev, n_utt, tr_off_dev, word_dev, word_lo_dev,
+                                                                 utt_tr_dev, skip_label, words_dev, max_words, count_dev);
+    LOE_LAUNCH_CHECK("labels_kernel");
     return LOE_OK;
 }

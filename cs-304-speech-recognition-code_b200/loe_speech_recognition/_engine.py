@@ -221,6 +221,17 @@ class Engine:
         self.launches += 1
         return path, end_scores, best, best_score
 
+    def labels(self, path, frm_off, n_utt, tp: TrellisPack, utt_tr=None, skip_label=-1, max_words=32):
+        """(words int8 [n_utt, max_words], count int32 [n_utt]) on the device."""
+        torch = self.torch
+        words = self.empty((n_utt, max_words), torch.int8)
+        count = self.empty((n_utt,), torch.int32)
+        _native.check(self.lib.loe_labels_dev(path.data_ptr(), frm_off.data_ptr(), n_utt, tp.tr_off.data_ptr(),
+                                              tp.word.data_ptr(), tp.word_lo.data_ptr(), self._p(utt_tr), skip_label,
+                                              words.data_ptr(), max_words, count.data_ptr(), self._stream()))
+        self.launches += 1
+        return words, count
+
     # ------------------------------------------------------------------ K-means statistics
     def kmeans_stats(self, feat, path, frm_off, n_utt, total_frames, tp: TrellisPack, utt_tr, remux: bool,
                      n_glob: int, shift):

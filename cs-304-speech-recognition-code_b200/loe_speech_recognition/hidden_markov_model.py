@@ -426,20 +426,66 @@ class HiddenMarkovModelInference(_PackCache):
                                              loop=True, penalty=pen, penalty_f64=f64, want_end_scores=False)
         return best_score, path
 
+    def _strings_device(self, path, batch, max_words: int = 32) -> List[str]:
+        """path (device) -> digit strings: word sequence per utterance from the labels kernel
+        (model_boundary.py:107-147), only the tiny [n, max_words] id table crosses PCIe."""
+        eng = _engine()
+        _, tp = self._packs()
+        labels = self._model_boundaries._labels
+        skip = labels.index("S") if "S" in labels else -1
+        words, count = eng.labels(path, batch.frm_off, batch.n_utt, tp, skip_label=skip, max_words=max_words)
+        words_h, count_h = words.cpu().numpy(), count.cpu().numpy()
+        out: List[str] = []
+        path_h = None
+        for i in range(batch.n_utt):
+            c = int(count_h[i])
+            if 0 <= c <= max_words:
+                out.append("".join(labels[k] for k in words_h[i, :c]))
+            else:                                         # overflow or T == 1: the host routine decides (and raises)
+                if path_h is None:
+                    path_h = path.cpu().numpy()
+                off = batch.frm_off_host
+                out.append("".join(self._model_boundaries.get_labels(path_h[off[i]:off[i + 1]])))
+        return out
+
     def predict_batch(self, signals: Sequence[NDArray[np.float32]], precision: Optional[str] = None) -> List[str]:
         """Digit strings of many (T, 39) feature matrices in one pass (added entry point)."""
-        _, paths = self.viterbi_batch(signals, precision)
-        return ["".join(self._model_boundaries.get_labels(p)) for p in paths]
+        eng = _engine()
+        batch = eng.upload_features(signals, self._multivariate_normals[0].dim_of_features)
+        _, path = self._decode_device(batch, precision)
+        return self._strings_device(path, batch)
 
     def decode_pcm_batch(self, signals: Sequence[NDArray], sample_rate: int = 16000, precision: Optional[str] = None) -> List[str]:
         """Raw PCM -> digit strings, everything between the H2D copy of the samples and the D2H
-        copy of the state paths on the device (MFCC -> emission -> Viterbi; added entry point)."""
+        copy of the word ids on the device (MFCC -> emission -> Viterbi -> labels; added entry point)."""
         eng = _engine()
         batch = eng.mfcc(signals, sample_rate)
         _, path = self._decode_device(batch, precision)
-        path_h = path.cpu().numpy()
-        off = batch.frm_off_host
-        return ["".join(self._model_boundaries.get_labels(path_h[off[i]:off[i + 1]])) for i in range(batch.n_utt)]
+        return self._strings_device(path, batch)
+
+
+    def decode_pcm_flat(self, pcm_flat, sample_offsets: NDArray[np.int64], sample_rate: int = 16000,
+                        precision: Optional[str] = None) -> List[str]:
+        """Batch ingestion form of :meth:`decode_pcm_batch`: ``pcm_flat`` is ONE host buffer (numpy
+        array or pinned torch tensor, float32, utterances back to back) and ``sample_offsets`` the
+        [n+1] sample offsets.  Host->device copy of the samples, MFCC, emission, Viterbi, labels and
+        the device->host copy of the word ids all happen inside this call (added entry point)."""
+        from ._engine import Batch
+        eng = _engine()
+        torch = eng.torch
+        off = np.asarray(sample_offsets, dtype=np.int64)
+        lens = np.diff(off)
+        frames = 1 + lens // 160
+        frm_off = np.concatenate(([0], np.cumsum(frames))).astype(np.int64)
+        src = pcm_flat if isinstance(pcm_flat, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(pcm_flat, dtype=np.float32))
+        pcm = src.to(eng.device, non_blocking=True)
+        pcm_off = eng._to_dev(off)
+        frm_off_dev = eng._to_dev(frm_off)
+        feat = eng.mfcc_device(pcm, pcm_off, frm_off_dev, len(lens), int(frm_off[-1]), int(frames.max()), int(frames.min()),
+                               sample_rate)
+        batch = Batch(feat, frm_off_dev, frm_off, len(lens), int(frames.max()))
+        _, path = self._decode_device(batch, precision)
+        return self._strings_device(path, batch)
 
 
 # ----------------------------------------------------------------------------------------

@@ -131,6 +131,21 @@ int loe_viterbi_dev(const float* scores_dev, int ld, const int64_t* frm_off_dev,
                     int32_t* best_dev, float* best_score_dev, uint8_t* bp_ws_dev, void* stream);
 
 /* --------------------------------------------------------------------------------------
+ * State path -> word sequence.  Replaces ModelBoundary.get_labels / append_to_labels
+ * (model_boundary.py:107-147) for a whole batch: run-length compress the path, emit a word
+ * when the path leaves the current word's state range or re-enters its first state from its
+ * last state (repeated word); words whose label id equals skip_label (silence) are dropped.
+ *   words_dev [n_utt*max_words] int8 out: label ids (word_dev values) in order
+ *   count_dev [n_utt] int32 out: number of words (may exceed max_words: the caller re-derives
+ *             those utterances on the host), or -1 when the path holds a negative state
+ *             (T == 1: the reference raises there)
+ * -------------------------------------------------------------------------------------- */
+int loe_labels_dev(const int8_t* path_dev, const int64_t* frm_off_dev, int n_utt,
+                   const int32_t* tr_off_dev, const int32_t* word_dev, const int32_t* word_lo_dev,
+                   const int32_t* utt_tr_dev, int skip_label,
+                   int8_t* words_dev, int max_words, int32_t* count_dev, void* stream);
+
+/* --------------------------------------------------------------------------------------
  * Segmental K-means sufficient statistics.  Replaces Signal.order_by_state,
  * SortedSignals.order_by_state / .transition_probabilities (signal.py:23-47, 68-91), the
  * accumulation half of HiddenMarkovModelTrainable._update_middleware_parameters
