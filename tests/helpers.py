@@ -29,3 +29,13 @@ def rel_close(a, b, rtol=1e-4, atol=0.0):
     a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
     both_inf = np.isinf(a) & np.isinf(b) & (np.sign(a) == np.sign(b))
     return bool(np.all(both_inf | (np.abs(a - b) <= rtol * np.abs(b) + atol)))
+
+
+def emission_close(got, ref, log_pdets, dim=39, rtol=1e-4):
+    """Parity bar for log-likelihoods: 1e-4 relative, where the scale of a score
+    cst_s - maha/2 is max(|score|, |cst_s|): the two terms cancel (scores cross zero), so a bound
+    relative to the difference alone is not meaningful in float32.  The float64 path is held to
+    1e-6 of |score| itself (see test_emission_matches_scipy)."""
+    cst = np.abs(-0.5 * (dim * np.log(2 * np.pi) + np.asarray(log_pdets, dtype=np.float64)))[None, :]
+    got = np.asarray(got, dtype=np.float64); ref = np.asarray(ref, dtype=np.float64)
+    return bool(np.all(np.abs(got - ref) <= rtol * np.maximum(np.abs(ref), cst)))

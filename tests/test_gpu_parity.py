@@ -5,7 +5,7 @@ emission scores, and on every utterance whose margin exceeds the float tolerance
 import numpy as np
 import pytest
 
-from helpers import LOOP_ORDER, N_STATES, WORDS, oracle_flat, rel_close, trained_word_model
+from helpers import LOOP_ORDER, N_STATES, WORDS, emission_close, oracle_flat, rel_close, trained_word_model
 
 pytestmark = pytest.mark.gpu
 
@@ -65,9 +65,27 @@ def test_emission_matches_scipy(eng, golden, precision, rtol):
         means, Us, lps, _ = oracle_flat(golden, w)
         ref = O.emission_scores(x, means, Us, lps)
         assert got.shape == ref.shape
-        assert rel_close(got, ref, rtol=rtol), np.abs(got / ref - 1).max()
+        if precision == "fp64":
+            assert rel_close(got, ref, rtol=rtol), np.abs(got / ref - 1).max()
+        else:
+            assert emission_close(got, ref, lps), np.abs(got - ref).max()
         if precision == "fp64":
             assert np.mean(got == ref) > 0.999       # float64 arithmetic, one rounding: bit-identical almost everywhere
+
+
+def test_emission_in_context_features(eng, golden):
+    """All 58 states on string features: scores span -3e5 .. +50 and cross zero."""
+    from oracle import hmm as O
+    flat = [oracle_flat(golden, w) for w in LOOP_ORDER]
+    means = np.concatenate([f[0] for f in flat]); Us = np.concatenate([f[1] for f in flat]); lps = np.concatenate([f[2] for f in flat])
+    inf = _loop_inference(golden)
+    gp, _ = inf._packs()
+    for i in (0, 7):
+        x = golden[f"loop_feat_{i}"]
+        ref = O.emission_scores(x, means, Us, lps)
+        assert emission_close(eng.emission(eng._to_dev(x), gp, "fp32").cpu().numpy(), ref, lps)
+        got64 = eng.emission(eng._to_dev(x), gp, "fp64").cpu().numpy()
+        assert rel_close(got64, ref, rtol=1e-6) and np.mean(got64 == ref) > 0.999
 
 
 def test_emission_ill_conditioned(eng):
@@ -84,10 +102,11 @@ def test_emission_ill_conditioned(eng):
     mn = MultivariateNormal.from_means_covariances(mean, cov)
     x = (mean + rng.normal(size=(300, D)) * np.sqrt(lam).mean()).astype(np.float32)
     gp = eng.pack_gaussians([mn])
-    ref = O.emission_scores(x, *[np.array([v]) for v in O.gaussian_pack(mean, cov)])
+    pk = O.gaussian_pack(mean, cov)
+    ref = O.emission_scores(x, *[np.array([v]) for v in pk])
     for precision in ("fp32", "fp64"):
         got = eng.emission(eng._to_dev(x), gp, precision).cpu().numpy()
-        assert rel_close(got, ref, rtol=1e-4), (precision, np.abs(got / ref - 1).max())
+        assert emission_close(got, ref, [pk[2]]), (precision, np.abs(got / ref - 1).max())
 
 
 # ------------------------------------------------------------------ a3 word Viterbi

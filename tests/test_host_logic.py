@@ -1,0 +1,249 @@
+"""CPU: host-side logic of the drop-in package (no GPU, no compute calls into the library)."""
+import os
+import pickle
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from helpers import LOOP_ORDER, N_STATES, WORDS, oracle_flat, trained_word_model
+from oracle import hmm as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_public_names_and_out_of_scope():
+    import loe_speech_recognition as L
+    for name in ("MFCC", "HiddenMarkovModel", "HiddenMarkovModelTrainable", "HiddenMarkovModelInference",
+                 "HiddenMarkovModelTrainContinuous", "Signal", "ModelCollection", "TI_DIGITS_LABELS"):
+        assert hasattr(L, name)
+    assert list(L.TI_DIGITS_LABELS) == ["1", "2", "3", "4", "5", "6", "7", "8", "9", "O", "Z"]
+    with pytest.raises(NotImplementedError):
+        L.TIDigits
+    from loe_speech_recognition import HiddenMarkovModelInference
+    assert isinstance(HiddenMarkovModelInference()._log_transition_probability_between_words, np.float64)
+
+
+def test_transition_matrices_semantics():
+    from loe_speech_recognition.transition_probability import LogTransitionProbabilities, TransitionProbabilities
+    tp = TransitionProbabilities.from_num_of_states(5)
+    _, _, ref_trans = O.init_parameters(np.zeros((10, 3), np.float32), 5)
+    assert np.array_equal(tp.to_dense(), ref_trans)
+    assert len(tp._core) == 25 and tp[(4, 0)] == 0.0
+    ltp = LogTransitionProbabilities.from_transition_probability(tp)
+    assert np.array_equal(ltp.to_dense(), O.log_transitions(ref_trans))
+    assert ltp[(3, 1)] == -np.inf and isinstance(ltp[(0, 0)], np.float32)
+    both = LogTransitionProbabilities()
+    both.append(ltp); both.append(ltp)
+    assert both.num_of_states == 10 and both[(4, 5)] == 0.0 and (4, 5) not in both._core   # absent key reads 0.0
+    assert np.array_equal(both.to_dense(), O.block_diag_missing_zero([ltp.to_dense(), ltp.to_dense()]))
+
+
+def test_reference_pickles_load_and_round_trip(tmp_path):
+    from loe_speech_recognition import HiddenMarkovModel, HiddenMarkovModelInference
+    src = os.path.join(ROOT, "tests", "golden", "golden_models")
+    m = HiddenMarkovModel.from_folder(os.path.join(src, "Z"))
+    assert m.label == "Z" and m.num_of_states == 5 and m.dim_of_features == 39
+    assert type(m._log_transition_probs).__module__ == "loe_speech_recognition.transition_probability"
+    assert type(m._multivariate_normals[0]).__module__ == "loe_speech_recognition.hidden_markov_model"
+    m.save(str(tmp_path))
+    m2 = HiddenMarkovModel.from_folder(str(tmp_path / "Z"))
+    assert m2._log_transition_probs._core == m._log_transition_probs._core
+    assert np.array_equal(m2._multivariate_normals[2]._core.mean, m._multivariate_normals[2]._core.mean)
+    with pytest.raises(FileNotFoundError):
+        HiddenMarkovModel.from_folder(str(tmp_path / "nope"))
+    inf = HiddenMarkovModelInference.from_folder(src, ["1", "S", "Z", "7"])
+    assert inf._model_boundaries._labels == ["1", "S", "Z"]
+    assert inf._model_boundaries.lower_boundaries == [0, 5, 8] and inf._model_boundaries.upper_boundaries == [4, 7, 12]
+    blob = pickle.dumps(inf)                       # models are shipped to pool workers by the scripts
+    assert pickle.loads(blob)._model_boundaries._labels == ["1", "S", "Z"]
+
+
+def test_trellis_builder_matches_oracle(golden):
+    from loe_speech_recognition import _trellis
+    from loe_speech_recognition._native import POS_END, POS_INIT, POS_START
+    logAs = [golden[f"train_logA_{w}"] for w in LOOP_ORDER]
+    sizes = [a.shape[0] for a in logAs]
+    lows = np.concatenate(([0], np.cumsum(sizes)[:-1])).tolist()
+    for kind, ref in (("loop", O.loop_trellis(logAs)), ("chain", O.chain_trellis(logAs))):
+        t = _trellis.build(logAs, lows, list(range(12)), kind)
+        assert np.array_equal(t.band, ref.band)
+        assert np.array_equal((t.flags & POS_INIT) != 0, ref.init)
+        assert np.array_equal(np.nonzero(t.flags & POS_END)[0], ref.ends)
+        if kind == "loop":
+            assert np.array_equal(np.nonzero(t.flags & POS_START)[0], ref.loop_starts)
+    w = _trellis.build([logAs[0]], [0], [0], "word")
+    assert np.array_equal(w.band, O.word_trellis(logAs[0]).band)
+    off, col, band, flags, word, word_lo, max_pos, max_ends = _trellis.stack([w, _trellis.build(logAs, lows, list(range(12)), "loop")])
+    assert off.tolist() == [0, 5, 63] and max_pos == 58 and max_ends == 12 and band.shape == (63, 3)
+
+
+def test_model_boundary_labels_match_oracle(golden):
+    from loe_speech_recognition.model_boundary import ModelBoundary
+    sizes = [N_STATES[w] for w in LOOP_ORDER]
+    mb = ModelBoundary()
+    for n in sizes:
+        mb.append(n)
+    mb.add_model_labels(list(LOOP_ORDER))
+    for name in ("int", "f64"):
+        for i in range(10):
+            path = golden[f"loop_path_{name}_{i}"]
+            assert "".join(mb.get_labels(path)) == str(golden[f"loop_strings_{name}"][i])
+            assert mb.get_labels(path, skip_silence=False) == O.get_labels(path, sizes, list(LOOP_ORDER), skip_silence=False)
+    rep = np.array([0, 1, 2, 3, 4, 0, 1, 4, 4, 50, 52, 53], dtype=np.int8)      # repeated word via last->first state
+    assert mb.get_labels(rep) == O.get_labels(rep, sizes, list(LOOP_ORDER)) == ["1", "1", "Z"]
+    with pytest.raises(Exception):
+        mb.get_labels(np.array([-1], dtype=np.int8))
+    with pytest.raises(Exception):
+        mb.append(3)                                  # frozen after the boundaries were read
+    assert mb.get_label(52) == "S" and mb.find_lower_boundary(57) == 53 and mb.find_upper_boundary(50) == 52
+
+
+def test_signal_bookkeeping_matches_oracle():
+    from loe_speech_recognition.signal import Signal, SortedSignals
+    rng = np.random.default_rng(0)
+    paths = [np.array(p, dtype=np.int8) for p in ([0, 0, 1, 1, 2, 2, 2], [0, 2, 2, 1, 1], [1, 1, 2], [2, 2, 0, 0])]
+    sigs = [rng.normal(size=(len(p), 4)).astype(np.float32) for p in paths]
+    ss = SortedSignals(3)
+    for x, p in zip(sigs, paths):
+        s = Signal(3, x, p)
+        ref = O.order_by_state(x, p, 3)
+        for a, b in zip(s.order_by_state, ref):
+            assert (a is None and b is None) or np.array_equal(a, b)
+        ss.append(s)
+    ref = O.mstep(sigs, paths, 3)
+    assert np.array_equal(ss.transition_counts, ref["counts"])
+    assert np.array_equal(ss.transition_probabilities.to_dense(), ref["trans"], equal_nan=True)
+
+
+def _numpy_stats(feats, paths, n_states, shift):
+    """Host stand-in for loe_align_dev + loe_kmeans_dev (same packed layout)."""
+    D = feats[0].shape[1]
+    iu = np.triu_indices(D)
+    stats = np.zeros((n_states, 1 + D + D * (D + 1) // 2))
+    counts = np.zeros((n_states, n_states), dtype=np.int64)
+    for x, p in zip(feats, paths):
+        for s, seg in enumerate(O.order_by_state(x, p, n_states)):
+            if seg is None:
+                continue
+            d = seg.astype(np.float64) - shift[s]
+            stats[s, 0] += len(seg)
+            stats[s, 1:1 + D] += d.sum(0)
+            stats[s, 1 + D:] += (d.T @ d)[iu]
+        np.add.at(counts, (p[:-1].astype(int), p[1:].astype(int)), 1)
+    return stats, counts
+
+
+def test_mstep_from_statistics_matches_oracle(golden):
+    from loe_speech_recognition import HiddenMarkovModelTrainable
+    w = "5"
+    feats = [golden[f"train_feat_{w}_{i}"] for i in range(8)]
+    means, Us, lps, logA = oracle_flat(golden, w)
+    tr = O.word_trellis(logA)
+    paths = [O.viterbi(O.emission_scores(x, means, Us, lps), tr)[2] for x in feats]
+    old = golden[f"train_means_{w}"] + 0.5
+    ref = O.mstep(feats, paths, 5, old_means=old)
+    m = HiddenMarkovModelTrainable(w)
+    m._means = old.astype(np.float32)
+    m._covariances = m._init_covariance(39, 5)
+    stats, counts = _numpy_stats(feats, paths, 5, m._means.astype(np.float64))
+    m._update_from_statistics(stats, counts, shift=m._means.astype(np.float64))
+    assert np.allclose(m._means, ref["means"], rtol=1e-6, atol=1e-6)
+    assert np.allclose(m._covariances, ref["covs"], rtol=1e-5, atol=1e-7)
+    assert np.array_equal(m._transition_probs.to_dense(), ref["trans"])
+    # convergence is tested on the means only, before covariances / transitions are touched
+    cov_before = m._covariances.copy()
+    stats, counts = _numpy_stats(feats, paths, 5, m._means.astype(np.float64))
+    with pytest.raises(HiddenMarkovModelTrainable.HMMTrainConverge):
+        m._update_from_statistics(stats, counts, shift=m._means.astype(np.float64))
+    assert np.array_equal(m._covariances, cov_before)
+    stats[2, 0] = 0
+    with pytest.raises(HiddenMarkovModelTrainable.HMMTrainMeanFail):
+        m._update_from_statistics(stats, counts, shift=m._means.astype(np.float64))
+
+
+def test_init_parameters_match_oracle(golden):
+    from loe_speech_recognition import HiddenMarkovModelTrainable
+    x = golden["train_feat_2_0"]
+    means, covs, tp = HiddenMarkovModelTrainable._init_parameters(x, 5)
+    rm, rc, rt = O.init_parameters(x, 5)
+    assert np.array_equal(means, rm) and np.array_equal(covs, rc) and np.array_equal(tp.to_dense(), rt)
+
+
+def test_embedded_stop_rule_is_cumulative():
+    """_num_of_finished_models accumulates across iterations (hidden_markov_model.py:754-770)."""
+    from loe_speech_recognition import HiddenMarkovModelTrainContinuous, HiddenMarkovModelTrainable
+
+    class Fake:
+        def __init__(self, conv):
+            self.conv, self.updated = conv, 0
+        def _update_inference_weights(self):
+            self.updated += 1
+
+    tc = HiddenMarkovModelTrainContinuous()
+    tc._trainable_models = {"a": Fake(True), "b": Fake(False)}
+
+    def upd(m):
+        if m.conv:
+            raise HiddenMarkovModelTrainable.HMMTrainConverge
+    tc._one_word("a", upd)
+    assert tc._num_of_finished_models == 1
+    with pytest.raises(HiddenMarkovModelTrainable.HMMTrainConverge):
+        tc._one_word("a", upd)                        # same model converging again reaches len(models) == 2
+    assert tc._trainable_models["a"].updated == 2
+    assert tc.insert_silence("Z1") == "SZS1S"
+
+
+def test_penalty_modes():
+    from loe_speech_recognition.hidden_markov_model import _penalty_args
+    assert _penalty_args(np.log(0.005)) == (float(np.log(0.005)), True)
+    assert _penalty_args(-100) == (-100.0, False)
+    assert _penalty_args(-37.25) == (-37.25, False)
+    assert _penalty_args(np.float32(-3)) == (-3.0, False)
+
+
+def test_mel_filterbank_matches_oracle():
+    from loe_speech_recognition.mfcc import mel_filterbank, mel_filterbank_sparse
+    from oracle import mfcc as OM
+    assert np.array_equal(mel_filterbank(16000), OM.mel_basis())
+    start, length, w = mel_filterbank_sparse(16000)
+    dense = np.zeros((40, 161), np.float32)
+    w = w.reshape(-1, 40)
+    for m in range(40):
+        dense[m, start[m]:start[m] + length[m]] = w[:length[m], m]
+    assert np.array_equal(dense, OM.mel_basis()) and length.max() <= 18 and length.min() >= 2
+
+
+def test_mfcc_input_validation_needs_no_gpu():
+    from loe_speech_recognition import MFCC
+    with pytest.raises(TypeError):
+        MFCC([0.0] * 2000, 16000)
+    with pytest.raises(ValueError):
+        MFCC(np.zeros((2, 2000), np.float32), 16000)
+    x = np.arange(26, dtype=np.float32).reshape(13, 2)
+    from oracle import mfcc as OM
+    assert np.allclose(MFCC.normalize_mfccs(x), OM.normalize_mfccs(x))
+
+
+def test_no_cuda_fails_loudly():
+    """Without a CUDA device the product must raise, never fall back to a CPU path."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from loe_speech_recognition import MFCC
+    from loe_speech_recognition._engine import NoCudaDevice
+    with pytest.raises(NoCudaDevice):
+        MFCC.batch([np.zeros(16000, np.float32)], 16000)
+
+
+def test_product_never_imports_oracle():
+    code = ("import sys; sys.path.insert(0, %r); import loe_speech_recognition, loe_speech_recognition._engine, "
+            "loe_speech_recognition.synthetic; assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules)"
+            % os.path.join(ROOT, "cs-304-speech-recognition-code_b200"))
+    subprocess.check_call([sys.executable, "-c", code], cwd="/tmp")
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "cs-304-speech-recognition-code_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f

@@ -1,0 +1,125 @@
+"""CPU: the NumPy oracle against the golden vectors produced by the unmodified reference
+(tests/golden/make_golden.py).  Bit-exact everywhere: this is what pins the oracle."""
+import numpy as np
+
+from helpers import LOOP_ORDER, N_STATES, WORDS, oracle_flat
+from oracle import hmm as O
+
+PENALTIES = {"int": -100, "f64": np.log(0.005), "pyfloat": -37.25, "zero": 0}
+
+
+def _loop_tables(golden):
+    flat = [oracle_flat(golden, w) for w in LOOP_ORDER]
+    return (np.concatenate([f[0] for f in flat]), np.concatenate([f[1] for f in flat]), np.concatenate([f[2] for f in flat]),
+            O.loop_trellis([f[3] for f in flat]), [f[3].shape[0] for f in flat])
+
+
+def test_isolated_scores_and_paths(golden):
+    order = [str(s) for s in golden["iso_model_order"]]
+    for i in range(0, 22, 3):
+        x = golden[f"iso_feat_{i}"]
+        for k, w in enumerate(order):
+            means, Us, lps, logA = oracle_flat(golden, w)
+            es, bi, path = O.viterbi(O.emission_scores(x, means, Us, lps), O.word_trellis(logA))
+            assert es[0] == golden["iso_scores"][i, k]
+            assert np.array_equal(path, golden[f"iso_paths_{i}"][k])
+    best = np.argmax(golden["iso_scores"], axis=1)
+    assert [order[b] for b in best] == [str(s) for s in golden["iso_labels"]]
+
+
+def test_loop_decode_all_penalty_modes(golden):
+    means, Us, lps, tr, sizes = _loop_tables(golden)
+    assert [str(s) for s in golden["loop_order"]] == list(LOOP_ORDER)
+    ems = [O.emission_scores(golden[f"loop_feat_{i}"], means, Us, lps) for i in range(10)]
+    for name, pen in PENALTIES.items():
+        assert O.penalty_mode(pen)[1] == (name == "f64")
+        for i in (0, 3, 6, 9):
+            es, bi, path = O.viterbi(ems[i], tr, penalty=pen)
+            assert es[bi] == golden[f"loop_scores_{name}"][i]
+            assert np.array_equal(path, golden[f"loop_path_{name}_{i}"])
+            assert "".join(O.get_labels(path, sizes, list(LOOP_ORDER))) == str(golden[f"loop_strings_{name}"][i])
+        bes, bbi, bpaths = O.viterbi_batch(ems, tr, penalty=pen)
+        for i in range(10):
+            assert np.array_equal(bpaths[i], golden[f"loop_path_{name}_{i}"])
+            assert bes[i, bbi[i]] == golden[f"loop_scores_{name}"][i]
+
+
+def test_edge_cases(golden):
+    means, Us, lps, tr, sizes = _loop_tables(golden)
+    m1 = oracle_flat(golden, "1")
+    for T in (2, 3, 9):
+        x = golden["edge_feat"][:T]
+        es, bi, path = O.viterbi(O.emission_scores(x, means, Us, lps), tr, penalty=-100)
+        assert np.array_equal(path, golden[f"edge_loop_path_T{T}"])
+        es, bi, path = O.viterbi(O.emission_scores(x, m1[0], m1[1], m1[2]), O.word_trellis(m1[3]))
+        assert np.array_equal(path, golden[f"edge_word_path_T{T}"])
+        ref = golden[f"edge_word_score_T{T}"]
+        assert es[0] == ref or (np.isinf(ref) and np.isinf(es[0]))
+    es, bi, path = O.viterbi(O.emission_scores(golden["edge_feat"][:1], m1[0], m1[1], m1[2]), O.word_trellis(m1[3]))
+    assert path.tolist() == [-1]
+
+
+def test_isolated_training_trajectory(golden):
+    for w in ("1", "S", "Z"):
+        # MFCC.batch hands out TRANSPOSED VIEWS (mfcc.py:84), i.e. column-major (T, 39) arrays, and the
+        # reference's float32 np.average depends on that layout at the 1-ulp level (pairwise vs row-wise
+        # accumulation) -- restore it for a bit-exact replay.
+        feats = [np.asfortranarray(golden[f"train_feat_{w}_{i}"]) for i in range(64) if f"train_feat_{w}_{i}" in golden.files]
+        n_states = N_STATES[w]
+        means, covs, trans = O.init_parameters(feats[0], n_states)
+        for it in range(4):
+            packs = [O.gaussian_pack(means[s], covs[s]) for s in range(n_states)]
+            tr = O.word_trellis(O.log_transitions(trans))
+            paths = [O.viterbi(O.emission_scores(x, [p[0] for p in packs], [p[1] for p in packs], [p[2] for p in packs]), tr)[2]
+                     for x in feats]
+            r = O.mstep(feats, paths, n_states, old_means=means)
+            if r["converged"]:
+                break
+            means, covs, trans = r["means"], r["covs"], r["trans"]
+        assert np.array_equal(means, golden[f"train_means_{w}"])
+        assert np.array_equal(covs, golden[f"train_covs_{w}"])
+        assert np.array_equal(O.log_transitions(trans), golden[f"train_logA_{w}"], equal_nan=True)
+
+
+def test_embedded_iteration(golden):
+    flat = {w: oracle_flat(golden, w) for w in WORDS}
+    pooled = {w: [] for w in WORDS}
+    for lab in [str(s) for s in golden["emb_labels"]]:
+        chain = O.insert_silence(lab)
+        sizes = [N_STATES[c] for c in chain]
+        tr = O.chain_trellis([flat[c][3] for c in chain])
+        cm = np.concatenate([flat[c][0] for c in chain]); cu = np.concatenate([flat[c][1] for c in chain])
+        cl = np.concatenate([flat[c][2] for c in chain])
+        for i in range(int(golden[f"emb_count_{lab}"])):
+            x = np.asfortranarray(golden[f"emb_feat_{lab}_{i}"])
+            _, _, path = O.viterbi(O.emission_scores(x, cm, cu, cl), tr)
+            for w, segs in O.remux(x, path, sizes, list(chain)).items():
+                pooled[w].extend(segs)
+    for w in WORDS:
+        r = O.mstep([s for s, _, _ in pooled[w]], [p for _, p, _ in pooled[w]], N_STATES[w],
+                    old_means=np.zeros((N_STATES[w], 39), np.float32))
+        assert np.array_equal(r["means"], golden[f"emb1_means_{w}"])
+        assert np.array_equal(r["covs"], golden[f"emb1_covs_{w}"])
+        assert np.array_equal(O.log_transitions(r["trans"]), golden[f"emb1_logA_{w}"], equal_nan=True)
+
+
+def test_mfcc_oracle_regression(golden_mfcc):
+    """oracle/mfcc.py is parity-unpinned (librosa absent); this pins it against its own committed
+    output and against independent restatements of two stages."""
+    from oracle import mfcc as OM
+    for i in range(4):
+        assert np.allclose(OM.mfcc_feature_vector(golden_mfcc[f"pcm{i}"]), golden_mfcc[f"feat{i}"], rtol=1e-6, atol=1e-6)
+    assert np.array_equal(OM.mel_basis(), golden_mfcc["mel_basis"])
+    mb = OM.mel_basis()
+    assert mb.shape == (40, 161) and np.all((mb > 0).sum(1) >= 2) and np.all((mb > 0).sum(1) <= 18)
+    # delta taps and edge rule
+    rng = np.random.default_rng(0)
+    c = rng.normal(size=(13, 40)).astype(np.float32)
+    k = np.arange(-4, 5)
+    d1, d2 = OM.delta(c, 1), OM.delta(c, 2)
+    for t in (4, 17, 35):
+        assert np.allclose(d1[:, t], (c[:, t - 4:t + 5] * k).sum(1) / 60, atol=1e-5)
+        assert np.allclose(d2[:, t], (c[:, t - 4:t + 5] * (3 * k * k - 20)).sum(1) / 462, atol=1e-5)
+    assert np.allclose(d1[:, 0], d1[:, 4], atol=1e-5) and np.allclose(d2[:, -1], d2[:, -5], atol=1e-5)
+    T = 1 + 16000 // 160
+    assert golden_mfcc["feat0"].shape == (39, T)
