@@ -3,8 +3,7 @@
 //     score[f][s] = cst[s] - 0.5 * | (x_f - mean_s) . U_s |^2
 //
 // One thread owns one frame: its feature row lives in registers for the whole kernel, the
-// whitening matrix U_s of the current state is staged in shared memory (double buffered with
-// cp.async) and broadcast to every thread with 128-bit loads, the 39 whitened coordinates are
+// whitening matrix U_s of the current state is staged in shared memory (double buffered) and broadcast to every thread with 128-bit loads, the 39 whitened coordinates are
 // register accumulators, and the [frames x states] tile of results goes through shared memory
 // so that the global store is row-contiguous.  This is the parity anchor and the fallback for
 // dimensions the tensor-core kernel (emission_tc.cu) does not cover.
@@ -125,9 +124,6 @@ static int launch_simt(const float* feat, int64_t n_frames, const void* mean, co
     return LOE_OK;
 }
 
-int emission_tc_launch(const float* feat, int64_t n_frames, const float* mean, const float* U, const float* cst,
-                       int n_states, float* out, int ld_out, cudaStream_t s);
-
 }  // namespace loe
 
 extern "C" int loe_emission_dev(const float* feat_dev, int64_t n_frames, int dim,
@@ -137,12 +133,10 @@ extern "C" int loe_emission_dev(const float* feat_dev, int64_t n_frames, int dim
     if (n_frames <= 0 || n_states <= 0) return LOE_OK;
     if (ld_out < n_states) { set_error("ld_out (%d) < n_states (%d)", ld_out, n_states); return LOE_ERR_VALUE; }
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    if (precision == 2) {
-        if (dim != 39) { set_error("tensor-core emission path is built for dim == 39 (got %d)", dim); return LOE_ERR_UNSUPPORTED; }
-        return emission_tc_launch(feat_dev, n_frames, (const float*)mean_dev, (const float*)u_dev, (const float*)cst_dev,
-                                  n_states, out_dev, ld_out, s);
+    if (precision != 0 && precision != 1) {
+        set_error("unknown precision %d (the tensor-core path is loe_emission_tc_dev)", precision);
+        return LOE_ERR_VALUE;
     }
-    if (precision != 0 && precision != 1) { set_error("unknown precision %d", precision); return LOE_ERR_VALUE; }
 #define LOE_DISPATCH_DIM(D)                                                                                     \
     case D:                                                                                                     \
         return precision == 0 ? launch_simt<float, D>(feat_dev, n_frames, mean_dev, u_dev, cst_dev, n_states, out_dev, ld_out, s) \

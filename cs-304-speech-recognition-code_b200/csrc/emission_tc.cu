@@ -1,8 +1,312 @@
-// Tensor-core (tcgen05 / TMEM) emission scoring -- placeholder until the kernel lands.
+// Gaussian emission scoring on the 5th-generation tensor cores (tcgen05 + TMEM), 3xTF32.
+//
+// Replaces MultivariateNormal.log_pdf (hidden_markov_model.py:46-48 -> scipy _logpdf) for a whole
+// batch, recast as a dense contraction:
+//
+//     y[f, (s, j)] = sum_k  [x_f, 1][k] * W_s[k, j]          W_s = [ U_s ; -mu_s U_s ]   (K = 40)
+//     score[f, s]  = cst_s - 0.5 * sum_j y[f, (s, j)]^2
+//
+// Precision: plain TF32 misses the 1e-4 bar by two orders of magnitude, so both operands are
+// split x = x_hi + x_lo (x_hi = x rounded to TF32) and three MMAs hi*hi + lo*hi + hi*lo are
+// accumulated in fp32 in TMEM (error ~3e-6 of the operand scale, measured).  Flops are counted
+// once (2*40*39*S per frame) although three MMAs are issued.
+//
+// Decomposition: B-stationary.  CTA (n, g) owns one tile of 6 states (N = 240 columns; W hi/lo
+// = 75 KB resident in shared memory for the whole kernel, loaded once) and walks the frame
+// tiles g, g+G, ... (M = 128 frames).  The 10 CTAs of a column g walk the same frames at the
+// same pace, so the feature tile is fetched from HBM once and re-read from L2.
+//   warps 0-3  producers: coalesced load of the raw [128 x 39] tile (software-prefetched one
+//              tile ahead), hi/lo split, store in the canonical K-major no-swizzle UMMA layout
+//              (8 x 16 B core matrices; LBO = K-chunk stride, SBO = 128 B), fence.proxy.async,
+//              arrive on a_full[stage]
+//   warp  8    one thread issues 15 tcgen05.mma.kind::tf32 (M128 N240 K8) per tile and
+//              tcgen05.commit's to a_empty[stage] and tmem_full[buf]
+//   warps 4-7  epilogue: tcgen05.ld the 128 x 240 fp32 accumulator (thread = frame row),
+//              square + sum each group of 40 columns, store 6 scores per frame
+// Accumulators are double buffered in TMEM (2 x 240 of the 512 columns), A in shared memory
+// (2 stages), so staging(i+1), MMA(i) and epilogue(i-1) overlap.
 #include "common.cuh"
+
 namespace loe {
-int emission_tc_launch(const float*, int64_t, const float*, const float*, const float*, int, float*, int, cudaStream_t) {
-    set_error("tensor-core emission path not built yet");
-    return LOE_ERR_UNSUPPORTED;
+namespace tc {
+
+constexpr int kTileM = 128;
+constexpr int kK = 40;
+constexpr int kKChunks = kK / 4;        // 16-byte chunks along K
+constexpr int kKSteps = kK / 8;         // one tf32 MMA consumes K = 8
+constexpr int kColsPerState = 40;
+constexpr int kStatesPerTile = 6;
+constexpr int kTileN = kStatesPerTile * kColsPerState;   // 240
+constexpr int kTmemCols = 512;
+constexpr int kBufStride = 256;         // TMEM column offset between the two accumulators
+constexpr int kDim = 39;
+constexpr int kProducerThreads = 128;
+constexpr int kEpilogueThreads = 128;
+constexpr int kThreads = kProducerThreads + kEpilogueThreads + 32;
+
+constexpr int kALbo = kTileM * 16;      // 2048: byte stride between K-adjacent core matrices of A
+constexpr int kBLbo = kTileN * 16;      // 3840
+constexpr int kSbo = 128;               // byte stride between 8-row groups
+constexpr int kABytes = kKChunks * kALbo;   // 20480
+constexpr int kBBytes = kKChunks * kBLbo;   // 38400
+
+struct __align__(128) Smem {
+    uint8_t b_hi[kBBytes];
+    uint8_t b_lo[kBBytes];
+    uint8_t a_hi[2][kABytes];
+    uint8_t a_lo[2][kABytes];
+    float raw[kTileM * kDim + 4];
+    float cst[8];
+    uint64_t a_full[2], a_empty[2], tmem_full[2], tmem_empty[2];
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);            // start address, 16-byte units
+    d |= (uint64_t)(lbo_bytes >> 4) << 16;              // leading (K) byte offset
+    d |= (uint64_t)(kSbo >> 4) << 32;                   // stride (M/N) byte offset
+    d |= (uint64_t)1 << 46;                             // descriptor version (Blackwell)
+    return d;                                           // layout_type = 0: no swizzle
+}
+
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float tf32_round(float x) {
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+emission_tc_kernel(const float* __restrict__ feat, int64_t n_frames, const float* __restrict__ b_packed,
+                   const float* __restrict__ cst_pad, int n_states, float* __restrict__ out, int ld_out) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_tile = blockIdx.x;
+    const int g = blockIdx.y, G = gridDim.y;
+    const int n_mtiles = (int)((n_frames + kTileM - 1) / kTileM);
+
+    // ---- one-time setup: barriers, TMEM, resident B tile
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&sm.a_full[i], kProducerThreads);
+            mbar_init(&sm.a_empty[i], 1);
+            mbar_init(&sm.tmem_full[i], 1);
+            mbar_init(&sm.tmem_empty[i], kEpilogueThreads);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    {
+        const float4* src = reinterpret_cast<const float4*>(b_packed + (size_t)n_tile * (2 * kBBytes / 4));
+        float4* dst = reinterpret_cast<float4*>(sm.b_hi);             // b_hi and b_lo are contiguous
+        for (int i = tid; i < 2 * kBBytes / 16; i += kThreads) dst[i] = __ldg(src + i);
+        if (tid < kStatesPerTile) sm.cst[tid] = cst_pad[n_tile * kStatesPerTile + tid];
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = sm.tmem_base;
+
+    if (warp < 4) {
+        // =========================== producers ===========================
+        float pre[kDim];                                   // raw tile, flat element tid + 128*i
+        auto prefetch = [&](int m) {
+            const int64_t f0 = (int64_t)m * kTileM;
+            const int rows = (int)min((int64_t)kTileM, n_frames - f0);
+            const float* src = feat + f0 * kDim;
+            const int total = rows * kDim;
+#pragma unroll
+            for (int i = 0; i < kDim; ++i) {
+                const int e = tid + i * kProducerThreads;
+                pre[i] = (e < total) ? __ldg(src + e) : 0.f;
+            }
+        };
+        if (g < n_mtiles) prefetch(g);
+        int it = 0;
+        for (int m = g; m < n_mtiles; m += G, ++it) {
+            const int s = it & 1;
+            const uint32_t k = (uint32_t)(it >> 1);
+            // raw tile -> shared (flat, conflict free)
+#pragma unroll
+            for (int i = 0; i < kDim; ++i) sm.raw[tid + i * kProducerThreads] = pre[i];
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (m + G < n_mtiles) prefetch(m + G);         // next tile's loads fly during the transform
+            mbar_wait(&sm.a_empty[s], (k & 1) ^ 1);        // MMA finished reading this stage
+            const float* row = sm.raw + tid * kDim;        // stride 39 words: conflict free
+            uint8_t* ah = sm.a_hi[s] + tid * 16;
+            uint8_t* al = sm.a_lo[s] + tid * 16;
+#pragma unroll
+            for (int kc = 0; kc < kKChunks; ++kc) {
+                float v[4], h[4], l[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int c = kc * 4 + q;
+                    v[q] = (c < kDim) ? row[c] : 1.0f;     // column 39: the constant 1 of the bias row
+                    h[q] = tf32_round(v[q]);
+                    l[q] = v[q] - h[q];
+                }
+                *reinterpret_cast<float4*>(ah + kc * kALbo) = make_float4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<float4*>(al + kc * kALbo) = make_float4(l[0], l[1], l[2], l[3]);
+            }
+            fence_proxy_async();
+            mbar_arrive(&sm.a_full[s]);
+            asm volatile("bar.sync 1, 128;" ::: "memory"); // everyone done with sm.raw before it is overwritten
+        }
+    } else if (warp == 8) {
+        // =========================== MMA issuer ===========================
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTileN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+            const uint32_t b_hi = smem_u32(sm.b_hi), b_lo = smem_u32(sm.b_lo);
+            int it = 0;
+            for (int m = g; m < n_mtiles; m += G, ++it) {
+                const int s = it & 1;
+                const uint32_t k = (uint32_t)(it >> 1);
+                mbar_wait(&sm.a_full[s], k & 1);
+                mbar_wait(&sm.tmem_empty[s], (k & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d = tmem_base + (uint32_t)(s * kBufStride);
+                const uint32_t a_hi = smem_u32(sm.a_hi[s]), a_lo = smem_u32(sm.a_lo[s]);
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {
+                    const uint32_t a = (pass == 1) ? a_lo : a_hi;
+                    const uint32_t b = (pass == 2) ? b_lo : b_hi;
+#pragma unroll
+                    for (int ks = 0; ks < kKSteps; ++ks)
+                        mma_tf32(d, make_desc(a + ks * 2 * kALbo, kALbo), make_desc(b + ks * 2 * kBLbo, kBLbo), idesc,
+                                 (pass | ks) ? 1u : 0u);
+                }
+                mma_commit(&sm.a_empty[s]);
+                mma_commit(&sm.tmem_full[s]);
+            }
+        }
+    } else {
+        // =========================== epilogue ===========================
+        const int q = warp & 3;                             // TMEM lane quarter this warp may touch
+        const int r = q * 32 + lane;
+        int it = 0;
+        for (int m = g; m < n_mtiles; m += G, ++it) {
+            const int s = it & 1;
+            const uint32_t k = (uint32_t)(it >> 1);
+            mbar_wait(&sm.tmem_full[s], k & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * kBufStride);
+            float score[kStatesPerTile];
+#pragma unroll
+            for (int j = 0; j < kStatesPerTile; ++j) {
+                float v[40];
+                tmem_ld32(taddr + j * kColsPerState, v);
+                tmem_ld8(taddr + j * kColsPerState + 32, v + 32);
+                tmem_ld_wait();
+                float acc = 0.f;
+#pragma unroll
+                for (int c = 0; c < kDim; ++c) acc = fmaf(v[c], v[c], acc);
+                score[j] = sm.cst[j] - 0.5f * acc;
+            }
+            tc_fence_before();
+            mbar_arrive(&sm.tmem_empty[s]);
+            const int64_t f = (int64_t)m * kTileM + r;
+            if (f < n_frames) {
+                float* o = out + f * ld_out + n_tile * kStatesPerTile;
+#pragma unroll
+                for (int j = 0; j < kStatesPerTile; ++j)
+                    if (n_tile * kStatesPerTile + j < n_states) o[j] = score[j];
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+    }
+}
+
+}  // namespace tc
 }  // namespace loe
+
+extern "C" int loe_emission_tc_tiles(int n_states) { return (n_states + loe::tc::kStatesPerTile - 1) / loe::tc::kStatesPerTile; }
+
+extern "C" int loe_emission_tc_dev(const float* feat_dev, int64_t n_frames, int dim, const float* b_packed_dev,
+                                   const float* cst_pad_dev, int n_states, float* out_dev, int ld_out, void* stream) {
+    using namespace loe;
+    using namespace loe::tc;
+    if (n_frames <= 0 || n_states <= 0) return LOE_OK;
+    if (dim != kDim) { set_error("tensor-core emission path is built for dim == 39 (got %d)", dim); return LOE_ERR_UNSUPPORTED; }
+    if (ld_out < n_states) { set_error("ld_out (%d) < n_states (%d)", ld_out, n_states); return LOE_ERR_VALUE; }
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    static int sm_count[64] = {0};
+    int dev = 0;
+    LOE_CUDA(cudaGetDevice(&dev));
+    if (dev >= 64) dev = 63;
+    if (sm_count[dev] == 0) {
+        LOE_CUDA(cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
+        LOE_CUDA(cudaFuncSetAttribute(emission_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+    }
+    const int n_tiles = (n_states + kStatesPerTile - 1) / kStatesPerTile;
+    const int n_mtiles = (int)((n_frames + kTileM - 1) / kTileM);
+    int G = sm_count[dev] / n_tiles;
+    if (G < 1) G = 1;
+    if (G > n_mtiles) G = n_mtiles;
+    dim3 grid((unsigned)n_tiles, (unsigned)G);
+    emission_tc_kernel<<<grid, kThreads, sizeof(Smem), s>>>(feat_dev, n_frames, b_packed_dev, cst_pad_dev, n_states, out_dev, ld_out);
+    LOE_LAUNCH_CHECK("emission_tc_kernel");
+    return LOE_OK;
+}

@@ -42,6 +42,8 @@ class GaussPack:
     mean64: "torch.Tensor"
     u64: "torch.Tensor"
     cst64: "torch.Tensor"
+    b_packed: "torch.Tensor" = None     # tensor-core image (dim == 39 only)
+    cst_pad: "torch.Tensor" = None
 
 
 @dataclass
@@ -81,6 +83,32 @@ def host_gauss_arrays(normals) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
     return means, us, cst
 
 
+def _tf32_round(a: np.ndarray) -> np.ndarray:
+    bits = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+    return ((bits + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+def pack_tc_image(means: np.ndarray, us: np.ndarray, cst: np.ndarray):
+    """Host pre-pack of the tensor-core operand (layout documented at loe_emission_tc_dev):
+    W_s = [U_s ; -mean_s.U_s] in float64, split into a TF32-rounded part and the float32 residual."""
+    S, D = means.shape
+    spt, cols, K = 6, 40, 40
+    n_tiles = (S + spt - 1) // spt
+    W = np.zeros((n_tiles * spt, K, cols), dtype=np.float64)
+    W[:S, :D, :D] = us
+    W[:S, D, :D] = -np.einsum("si,sij->sj", means, us)
+    hi = _tf32_round(W.astype(np.float32))
+    lo = (W - hi.astype(np.float64)).astype(np.float32)
+    out = np.empty((n_tiles, 2, K // 4, spt * cols, 4), dtype=np.float32)
+    for h, part in enumerate((hi, lo)):
+        # part [tile, state_local, k, j] -> [tile, kc, n = state_local*40 + j, q]
+        p = part.reshape(n_tiles, spt, K // 4, 4, cols)            # [t, sl, kc, q, j]
+        out[:, h] = p.transpose(0, 2, 1, 4, 3).reshape(n_tiles, K // 4, spt * cols, 4)
+    cst_pad = np.zeros(n_tiles * spt, dtype=np.float32)
+    cst_pad[:S] = cst.astype(np.float32)
+    return np.ascontiguousarray(out.reshape(-1)), cst_pad
+
+
 class Engine:
     def __init__(self, device: Optional[int] = None):
         import torch
@@ -117,11 +145,15 @@ class Engine:
         return self.pack_gauss_arrays(means, us, cst)
 
     def pack_gauss_arrays(self, means, us, cst) -> GaussPack:
-        return GaussPack(
+        gp = GaussPack(
             n_states=means.shape[0], dim=means.shape[1],
             mean32=self._to_dev(means.astype(np.float32)), u32=self._to_dev(us.astype(np.float32)),
             cst32=self._to_dev(cst.astype(np.float32)),
             mean64=self._to_dev(means), u64=self._to_dev(us), cst64=self._to_dev(cst))
+        if gp.dim == 39:
+            b, c = pack_tc_image(means, us, cst)
+            gp.b_packed, gp.cst_pad = self._to_dev(b), self._to_dev(c)
+        return gp
 
     def pack_trellises(self, trellises: List[HostTrellis]) -> TrellisPack:
         off, col, band, flags, word, word_lo, max_pos, max_ends = stack(trellises)
@@ -195,6 +227,13 @@ class Engine:
         if out is None:
             out = self.empty((n_frames, ld), torch.float32)
         code = PRECISIONS[precision]
+        if code == 2:
+            if gp.b_packed is None:
+                raise NotImplementedError("the tensor-core emission kernel is built for 39-dimensional features")
+            _native.check(self.lib.loe_emission_tc_dev(feat.data_ptr(), n_frames, dim, gp.b_packed.data_ptr(),
+                                                       gp.cst_pad.data_ptr(), gp.n_states, out.data_ptr(), ld, self._stream()))
+            self.launches += 1
+            return out
         mean, u, cst = (gp.mean64, gp.u64, gp.cst64) if code == 1 else (gp.mean32, gp.u32, gp.cst32)
         _native.check(self.lib.loe_emission_dev(feat.data_ptr(), n_frames, dim, mean.data_ptr(), u.data_ptr(), cst.data_ptr(),
                                                 gp.n_states, out.data_ptr(), ld, code, self._stream()))

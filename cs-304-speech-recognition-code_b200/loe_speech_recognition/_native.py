@@ -29,6 +29,8 @@ SIGNATURES = {
                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "loe_emission_dev": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int,
                                  c_void_p, c_int, c_int, c_void_p]),
+    "loe_emission_tc_tiles": (c_int, [c_int]),
+    "loe_emission_tc_dev": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "loe_viterbi_bp_fits": (c_int, [c_int, c_int]),
     "loe_viterbi_dev": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,

@@ -90,12 +90,22 @@ int loe_mfcc_dev(const float* pcm_dev, const int64_t* pcm_off_dev, const int64_t
  *
  *   feat_dev [n_frames*dim] float32;  mean_dev [n_states*dim];  u_dev [n_states*dim*dim]
  *   (row i, column j at u[(s*dim+i)*dim+j]);  cst_dev [n_states]
- *   precision: 0 = float32 SIMT, 1 = float64 SIMT (mean/u/cst are then double arrays),
- *              2 = 3xTF32 tcgen05 tensor-core path (float32 arrays; needs dim == 39)
+ *   precision: 0 = float32 SIMT, 1 = float64 SIMT (mean/u/cst are then double arrays)
  * -------------------------------------------------------------------------------------- */
 int loe_emission_dev(const float* feat_dev, int64_t n_frames, int dim,
                      const void* mean_dev, const void* u_dev, const void* cst_dev, int n_states,
                      float* out_dev, int ld_out, int precision, void* stream);
+
+/* Same result on the tcgen05 tensor cores (3xTF32 split, fp32 accumulation in TMEM; dim == 39).
+ * The model is pre-packed on the host into the shared-memory image the kernel keeps resident:
+ * states are grouped in tiles of 6, tile t owns floats [t*19200, (t+1)*19200) of b_packed:
+ *     b_packed[t*19200 + h*9600 + kc*960 + n*4 + q] = part_h( W_s[4*kc + q][j] ),
+ *     s = 6*t + n/40, j = n%40, h = 0 (TF32-rounded value) / 1 (residual),
+ *     W_s = [ U_s ; -mean_s . U_s ] (40 x 39, column 39 and states >= n_states are zero)
+ * cst_pad_dev has loe_emission_tc_tiles(n_states)*6 entries (zero padded). */
+int loe_emission_tc_tiles(int n_states);
+int loe_emission_tc_dev(const float* feat_dev, int64_t n_frames, int dim, const float* b_packed_dev,
+                        const float* cst_pad_dev, int n_states, float* out_dev, int ld_out, void* stream);
 
 /* --------------------------------------------------------------------------------------
  * Viterbi + backtrace, one CTA per utterance.  Replaces HiddenMarkovModel._viterbi /
