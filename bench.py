@@ -352,7 +352,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--utts", type=int, default=10000, help="utterances per GPU")
     ap.add_argument("--pool", type=int, default=500, help="distinct synthetic utterances (tiled to --utts)")
-    ap.add_argument("--precision", default=os.environ.get("LOE_B200_EMISSION", "fp32"), choices=["fp32", "fp64", "tc"])
+    ap.add_argument("--precision", default=os.environ.get("LOE_B200_EMISSION", "tc"), choices=["fp32", "fp64", "tc"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -24,7 +24,10 @@ PRECISIONS = {"fp32": 0, "fp64": 1, "tc": 2}
 
 
 def default_precision() -> str:
-    return os.environ.get("LOE_B200_EMISSION", "fp32")
+    """"auto" = the tcgen05 3xTF32 kernel when the model is 39-dimensional, the float32 SIMT kernel
+    otherwise.  LOE_B200_EMISSION=fp32|fp64|tc overrides (fp64 reproduces scipy bit for bit almost
+    everywhere and is the mode to use when chasing a path difference)."""
+    return os.environ.get("LOE_B200_EMISSION", "auto")
 
 
 class NoCudaDevice(RuntimeError):
@@ -219,6 +222,8 @@ class Engine:
     def emission(self, feat, gp: GaussPack, precision: Optional[str] = None, out=None, ld: Optional[int] = None):
         torch = self.torch
         precision = precision or default_precision()
+        if precision == "auto":
+            precision = "tc" if gp.b_packed is not None else "fp32"
         n_frames, dim = int(feat.shape[0]), int(feat.shape[1])
         if dim != gp.dim:
             raise AssertionError(f"feature dimension {dim} != model dimension {gp.dim}")

@@ -54,7 +54,7 @@ def test_mfcc_ragged_batch_and_errors(eng):
 
 
 # ------------------------------------------------------------------ a2 emission
-@pytest.mark.parametrize("precision,rtol", [("fp32", 1e-4), ("fp64", 1e-6)])
+@pytest.mark.parametrize("precision,rtol", [("fp32", 1e-4), ("fp64", 1e-6), ("tc", 1e-4)])
 def test_emission_matches_scipy(eng, golden, precision, rtol):
     from oracle import hmm as O
     x = np.concatenate([golden[f"iso_feat_{i}"] for i in range(6)])
@@ -84,6 +84,7 @@ def test_emission_in_context_features(eng, golden):
         x = golden[f"loop_feat_{i}"]
         ref = O.emission_scores(x, means, Us, lps)
         assert emission_close(eng.emission(eng._to_dev(x), gp, "fp32").cpu().numpy(), ref, lps)
+        assert emission_close(eng.emission(eng._to_dev(x), gp, "tc").cpu().numpy(), ref, lps)
         got64 = eng.emission(eng._to_dev(x), gp, "fp64").cpu().numpy()
         assert rel_close(got64, ref, rtol=1e-6) and np.mean(got64 == ref) > 0.999
 
@@ -104,9 +105,27 @@ def test_emission_ill_conditioned(eng):
     gp = eng.pack_gaussians([mn])
     pk = O.gaussian_pack(mean, cov)
     ref = O.emission_scores(x, *[np.array([v]) for v in pk])
-    for precision in ("fp32", "fp64"):
+    for precision in ("fp32", "fp64", "tc"):
         got = eng.emission(eng._to_dev(x), gp, precision).cpu().numpy()
         assert emission_close(got, ref, [pk[2]]), (precision, np.abs(got / ref - 1).max())
+
+
+def test_emission_tc_many_tiles_and_ragged_sizes(eng, golden):
+    """Tensor-core path: frame counts around the 128-row tile edge, state counts around the 6-state
+    tile edge, more frame tiles than CTAs (pipeline phases wrap), against the fp64 kernel."""
+    rng = np.random.default_rng(5)
+    inf = _loop_inference(golden)
+    normals = inf._multivariate_normals
+    base = np.concatenate([golden[f"loop_feat_{i}"] for i in range(10)])
+    for n_states in (1, 5, 6, 7, 12, 58):
+        gp = eng.pack_gaussians(normals[:n_states])
+        lps = [mn._core.cov_object._log_pdet for mn in normals[:n_states]]
+        for n_frames in (1, 127, 128, 129, 1000, 40000):
+            x = base[rng.integers(0, len(base), size=n_frames)]
+            xd = eng._to_dev(x)
+            ref = eng.emission(xd, gp, "fp64").cpu().numpy()
+            got = eng.emission(xd, gp, "tc").cpu().numpy()
+            assert emission_close(got, ref, lps), (n_states, n_frames, np.abs(got - ref).max())
 
 
 # ------------------------------------------------------------------ a3 word Viterbi
@@ -137,7 +156,7 @@ def test_isolated_predict_end_to_end(eng, golden):
     mc = ModelCollection()
     mc._models = [models[w] for w in order]
     feats = [golden[f"iso_feat_{i}"] for i in range(22)]
-    for precision in ("fp32", "fp64"):
+    for precision in ("fp32", "fp64", "tc"):
         sc = mc.scores_batch(feats, precision)
         assert rel_close(sc, golden["iso_scores"], rtol=1e-4)
         assert mc.predict_batch(feats, precision) == [str(s) for s in golden["iso_labels"]]
@@ -190,13 +209,14 @@ def test_loop_decode_strings(eng, golden, name):
     feats = [golden[f"loop_feat_{i}"] for i in range(10)]
     want = [str(s) for s in golden[f"loop_strings_{name}"]]
     assert inf.predict_batch(feats, "fp64") == want
-    got32 = inf.predict_batch(feats, "fp32")
-    scores, paths = inf.viterbi_batch(feats, "fp32")
-    assert rel_close(scores, golden[f"loop_scores_{name}"], rtol=1e-4)
-    # fp32 emission: any differing path must be a near-tie (margin test)
-    for i, (g, w) in enumerate(zip(got32, want)):
-        if g != w:
-            assert abs(scores[i] - golden[f"loop_scores_{name}"][i]) <= 1e-4 * abs(scores[i])
+    for precision in ("fp32", "tc"):
+        got32 = inf.predict_batch(feats, precision)
+        scores, paths = inf.viterbi_batch(feats, precision)
+        assert rel_close(scores, golden[f"loop_scores_{name}"], rtol=1e-4)
+        # float32 / 3xTF32 emission: any differing path must be a near-tie (margin test)
+        for i, (g, w) in enumerate(zip(got32, want)):
+            if g != w:
+                assert abs(scores[i] - golden[f"loop_scores_{name}"][i]) <= 1e-4 * abs(scores[i])
     assert inf.predict(feats[0]) == want[0]
 
 
