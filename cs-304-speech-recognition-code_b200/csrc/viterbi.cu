@@ -18,20 +18,12 @@
 // groups of 8 frames ahead so that the per-frame critical path is shared-memory only.
 // Algorithmic HBM bytes per utterance: 4*P*T (scores) + T (path).
 #include "common.cuh"
+#include "viterbi.cuh"
 
 namespace loe {
 
 constexpr int kPrefetch = 8;
 
-struct VitArgs {
-    const float* scores; int ld;
-    const int64_t* frm_off;
-    const int32_t* tr_off; const int32_t* col; const float* band; const uint8_t* flags;
-    const int32_t* utt_tr;
-    int loop; float pen32; double pen64; int pen_f64;
-    int8_t* path; float* end_scores; int max_ends; int32_t* best; float* best_score;
-    uint8_t* bp_ws; int bp_in_smem; int max_frames; int max_pos;
-};
 
 // lowest-index argmax over a warp: (v, i) pairs
 template <typename V>
@@ -283,6 +275,8 @@ extern "C" int loe_viterbi_dev(const float* scores_dev, int ld, const int64_t* f
     a.flags = flags_dev; a.utt_tr = utt_tr_dev; a.loop = loop; a.pen32 = (float)penalty; a.pen64 = penalty; a.pen_f64 = penalty_f64;
     a.path = path_dev; a.end_scores = end_scores_dev; a.max_ends = max_ends; a.best = best_dev; a.best_score = best_score_dev;
     a.bp_ws = bp_ws_dev; a.bp_in_smem = in_smem ? 1 : 0; a.max_frames = max_frames; a.max_pos = max_pos;
+    if (viterbi_warp_launch(a, n_utt, s)) return LOE_OK;      // one warp per utterance (the common case)
+    LOE_CUDA(cudaGetLastError());
     const int threads = ((max_pos + 31) / 32) * 32;
     viterbi_kernel<<<(unsigned)n_utt, threads, smem, s>>>(a);
     LOE_LAUNCH_CHECK("viterbi_kernel");
