@@ -36,7 +36,7 @@ __host__ __device__ inline WarpLayout warp_layout(int max_frames, int max_pos, i
     const int fpw = 16 / spl;
     L.n_rows = (max_frames + fpw - 1) / fpw;
     int o = L.n_rows * 128;
-    L.off_cross = o; o += (max_frames + 3) & ~3;
+    L.off_cross = o; o += ((max_frames + 3) & ~3) + 4;
     L.off_path = o;  o += (max_frames + 3) & ~3;
     L.off_ends = o;  o += max_pos * 4;
     L.off_flags = o; o += (max_pos + 3) & ~3;
@@ -44,21 +44,21 @@ __host__ __device__ inline WarpLayout warp_layout(int max_frames, int max_pos, i
     return L;
 }
 
-template <int SPL>
+template <int SPL, bool LOOP, bool PENF64>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 viterbi_warp_kernel(VitArgs a, int n_utt) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr unsigned FULL = 0xffffffffu;
-    constexpr int FPW = 16 / SPL;
+    constexpr int FPW = 16 / SPL;                        // frames per back-pointer word
+    static_assert(kPre % 4 == 0 && (FPW % kPre == 0 || kPre % FPW == 0), "block size vs packing");
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int u = blockIdx.x * kWarpsPerCta + warp;
     if (u >= n_utt) return;
     const WarpLayout L = warp_layout(a.max_frames, a.max_pos, SPL);
     unsigned char* base = smem_raw + (size_t)warp * L.total;
     uint32_t* s_bp = reinterpret_cast<uint32_t*>(base);
-    uint8_t* s_cross = base + L.off_cross;
+    uint32_t* s_cross = reinterpret_cast<uint32_t*>(base + L.off_cross);   // 4 frames per word
     int8_t* s_path = reinterpret_cast<int8_t*>(base + L.off_path);
-    int* s_ends = reinterpret_cast<int*>(base + L.off_ends);
     uint8_t* s_flags = base + L.off_flags;
 
     const int64_t f0 = a.frm_off[u];
@@ -69,127 +69,94 @@ viterbi_warp_kernel(VitArgs a, int n_utt) {
     const int P = a.tr_off[tr + 1] - p0;
 
     float b0[SPL], b1[SPL], b2[SPL], d[SPL];
-    int col[SPL];
-    unsigned flg[SPL];
-    bool act[SPL];
+    bool act[SPL], is_start[SPL], is_end[SPL];
+    const float* __restrict__ src[SPL];                  // running pointer into the score matrix
+    const float* __restrict__ sc = a.scores + f0 * a.ld;
+    unsigned end_mask[SPL];
 #pragma unroll
     for (int i = 0; i < SPL; ++i) {
         const int p = lane * SPL + i;
         act[i] = p < P;
-        b0[i] = b1[i] = b2[i] = neg_inf(); col[i] = 0; flg[i] = 0;
+        b0[i] = b1[i] = b2[i] = neg_inf();
+        unsigned flg = 0; int col = 0;
         if (act[i]) {
             b0[i] = a.band[(p0 + p) * 3 + 0]; b1[i] = a.band[(p0 + p) * 3 + 1]; b2[i] = a.band[(p0 + p) * 3 + 2];
-            col[i] = a.col[p0 + p]; flg[i] = a.flags[p0 + p];
-            s_flags[p] = (uint8_t)flg[i];
+            col = a.col[p0 + p]; flg = a.flags[p0 + p];
+            s_flags[p] = (uint8_t)flg;
         }
+        src[i] = sc + col;
+        is_start[i] = LOOP && (flg & LOE_POS_START);
+        is_end[i] = (flg & LOE_POS_END) != 0;
+        end_mask[i] = __ballot_sync(FULL, is_end[i]);
     }
-    // END positions in order: rank by ballot prefix
-    int n_end = 0;
-    {
-        unsigned m[SPL];
+    // END positions are ordered by position = (lane, slot) lexicographically
+    int n_end = 0, lower = 0;
 #pragma unroll
-        for (int i = 0; i < SPL; ++i) m[i] = __ballot_sync(FULL, act[i] && (flg[i] & LOE_POS_END));
-        int lower = 0;                                    // END positions in lower lanes
-#pragma unroll
-        for (int i = 0; i < SPL; ++i) { lower += __popc(m[i] & ((1u << lane) - 1)); n_end += __popc(m[i]); }
-        int mine = 0;
-#pragma unroll
-        for (int i = 0; i < SPL; ++i) {
-            if (act[i] && (flg[i] & LOE_POS_END)) { s_ends[lower + mine] = lane * SPL + i; ++mine; }
-        }
-    }
-    __syncwarp();
-    // lane w keeps END positions w, w+32, ... (n_end <= P <= 32*SPL)
-    int my_end[SPL];
-    bool end_ok[SPL];
-#pragma unroll
-    for (int j = 0; j < SPL; ++j) {
-        const int w = lane + 32 * j;
-        end_ok[j] = w < n_end;
-        my_end[j] = end_ok[j] ? s_ends[w] : 0;
-    }
-    const bool loop = a.loop != 0;
+    for (int i = 0; i < SPL; ++i) { lower += __popc(end_mask[i] & ((1u << lane) - 1)); n_end += __popc(end_mask[i]); }
 
-    // gather d[] at this lane's END positions
-    auto gather_ends = [&](float* out) {
+    // max over END positions of d, and the lowest END position p with pred(d_p) true
+    auto end_max = [&]() -> float {
+        float lm = neg_inf();
 #pragma unroll
-        for (int j = 0; j < SPL; ++j) {
-            const int owner = my_end[j] / SPL, slot = my_end[j] % SPL;
-            float v = neg_inf();
-#pragma unroll
-            for (int i = 0; i < SPL; ++i) {
-                const float t = __shfl_sync(FULL, d[i], owner);
-                if (slot == i) v = t;
-            }
-            out[j] = end_ok[j] ? v : neg_inf();
-        }
+        for (int i = 0; i < SPL; ++i) lm = is_end[i] ? fmaxf(lm, d[i]) : lm;
+        return fkey_inv(__reduce_max_sync(FULL, fkey(lm)));
     };
 
-    const float* __restrict__ sc = a.scores + f0 * a.ld;
     // t = 0
 #pragma unroll
     for (int i = 0; i < SPL; ++i) {
-        const float e0 = act[i] ? __ldg(sc + col[i]) : 0.f;
-        d[i] = (act[i] && (flg[i] & LOE_POS_INIT)) ? __fadd_rn(e0, b0[i]) : neg_inf();
+        const float e0 = act[i] ? __ldg(src[i]) : 0.f;
+        const unsigned flg = act[i] ? s_flags[lane * SPL + i] : 0u;
+        d[i] = (act[i] && (flg & LOE_POS_INIT)) ? __fadd_rn(e0, b0[i]) : neg_inf();
+        src[i] += a.ld;
     }
 
     float ecur[kPre][SPL], enext[kPre][SPL];
 #pragma unroll
     for (int k = 0; k < kPre; ++k)
 #pragma unroll
-        for (int i = 0; i < SPL; ++i) {
-            const int t = 1 + k;
-            ecur[k][i] = (act[i] && t < T) ? __ldg(sc + (int64_t)t * a.ld + col[i]) : 0.f;
-        }
-    uint32_t bits = 0;
-    for (int tb = 1; tb < T; tb += kPre) {
+        for (int i = 0; i < SPL; ++i)
+            ecur[k][i] = (act[i] && 1 + k < T) ? __ldg(src[i] + (int64_t)k * a.ld) : 0.f;
+    uint32_t bits = 0, cbits = 0;
+    // frame t = 1 + j;  j runs in blocks of kPre (jb is a multiple of kPre)
+    for (int jb = 0; jb < T - 1; jb += kPre) {
+#pragma unroll
+        for (int i = 0; i < SPL; ++i) src[i] += (int64_t)kPre * a.ld;
 #pragma unroll
         for (int k = 0; k < kPre; ++k)
 #pragma unroll
-            for (int i = 0; i < SPL; ++i) {
-                const int t = tb + kPre + k;
-                enext[k][i] = (act[i] && t < T) ? __ldg(sc + (int64_t)t * a.ld + col[i]) : 0.f;
-            }
+            for (int i = 0; i < SPL; ++i)
+                enext[k][i] = (act[i] && 1 + jb + kPre + k < T) ? __ldg(src[i] + (int64_t)k * a.ld) : 0.f;
+        const int slot_base = (FPW > kPre) ? (jb & (FPW - 1)) : 0;     // position of this block inside a bp word
 #pragma unroll
         for (int k = 0; k < kPre; ++k) {
-            const int t = tb + k;
-            if (t < T) {
-                // ---- cross-word candidate
+            const int j = jb + k;
+            if (j < T - 1) {
+                // ---- cross-word candidate: fl(pen + max END d); argmax = lowest END position reaching it
                 float cross32 = neg_inf(); double cross64 = -CUDART_INF; int cross_arg = 0;
-                if (loop) {
-                    float de[SPL];
-                    gather_ends(de);
-                    float lm = de[0];
-#pragma unroll
-                    for (int j = 1; j < SPL; ++j) lm = fmaxf(lm, de[j]);
-                    const float m = fkey_inv(__reduce_max_sync(FULL, fkey(lm)));
-                    int idx = -1;
-                    if (a.pen_f64) {
+                if (LOOP) {
+                    const float m = end_max();
+                    int pos = 0x7fffffff;
+                    if (PENF64) {
                         cross64 = __dadd_rn(a.pen64, (double)m);
 #pragma unroll
-                        for (int j = 0; j < SPL; ++j) {
-                            const unsigned eq = __ballot_sync(FULL, end_ok[j] && __dadd_rn(a.pen64, (double)de[j]) == cross64);
-                            if (idx < 0 && eq) idx = 32 * j + __ffs(eq) - 1;
+                        for (int i = 0; i < SPL; ++i) {
+                            const unsigned eq = __ballot_sync(FULL, is_end[i] && __dadd_rn(a.pen64, (double)d[i]) == cross64);
+                            if (eq) pos = min(pos, (__ffs(eq) - 1) * SPL + i);
                         }
                     } else {
                         cross32 = __fadd_rn(a.pen32, m);
 #pragma unroll
-                        for (int j = 0; j < SPL; ++j) {
-                            const unsigned eq = __ballot_sync(FULL, end_ok[j] && __fadd_rn(a.pen32, de[j]) == cross32);
-                            if (idx < 0 && eq) idx = 32 * j + __ffs(eq) - 1;
+                        for (int i = 0; i < SPL; ++i) {
+                            const unsigned eq = __ballot_sync(FULL, is_end[i] && __fadd_rn(a.pen32, d[i]) == cross32);
+                            if (eq) pos = min(pos, (__ffs(eq) - 1) * SPL + i);
                         }
                     }
-                    if (idx < 0) idx = 0;
-                    int arg_j = 0;
-#pragma unroll
-                    for (int j = 0; j < SPL; ++j) {
-                        const int v = __shfl_sync(FULL, my_end[j], idx & 31);
-                        if ((idx >> 5) == j) arg_j = v;
-                    }
-                    cross_arg = arg_j;
-                    if (lane == 0) s_cross[t] = (uint8_t)cross_arg;
+                    cross_arg = (pos == 0x7fffffff) ? 0 : pos;
+                    cbits |= (uint32_t)cross_arg << (8 * (k & 3));
+                    if ((k & 3) == 3 || j == T - 2) { s_cross[j >> 2] = cbits; cbits = 0; }
                 }
-                // ---- predecessors from the lane below
+                // ---- predecessors held by the lane below
                 float up1 = __shfl_up_sync(FULL, d[SPL - 1], 1);
                 float up2 = (SPL >= 2) ? __shfl_up_sync(FULL, d[SPL >= 2 ? SPL - 2 : 0], 1) : __shfl_up_sync(FULL, d[0], 2);
                 if (lane == 0) { up1 = neg_inf(); up2 = neg_inf(); }
@@ -200,33 +167,36 @@ viterbi_warp_kernel(VitArgs a, int n_utt) {
                     const float p1 = (i >= 1) ? d[i >= 1 ? i - 1 : 0] : up1;
                     const float p2 = (i >= 2) ? d[i >= 2 ? i - 2 : 0] : (i == 1 ? up1 : up2);
                     const float e = ecur[k][i];
-                    float val; unsigned code;
-                    if (loop && (flg[i] & LOE_POS_START)) {
-                        const float selfc = __fadd_rn(b0[i], d[i]);
-                        if (a.pen_f64) {
-                            double mv = cross64; code = 3;
-                            if ((double)selfc > mv) { mv = (double)selfc; code = 0; }
-                            val = __double2float_rn(__dadd_rn(mv, (double)e));
+                    float best = __fadd_rn(b2[i], p2); unsigned code = 2;
+                    const float c1 = __fadd_rn(b1[i], p1);
+                    if (c1 > best) { best = c1; code = 1; }
+                    const float c0 = __fadd_rn(b0[i], d[i]);
+                    if (c0 > best) { best = c0; code = 0; }
+                    if (best == neg_inf()) code = 3;
+                    float val = __fadd_rn(best, e);
+                    if (LOOP) {
+                        // word start: b1 = b2 = -inf, so best == c0 (its self loop); the cross-word
+                        // candidate wins unless the self loop is strictly larger
+                        if (PENF64) {
+                            const bool use_cross = is_start[i] && !((double)c0 > cross64);
+                            const float vx = __double2float_rn(__dadd_rn(cross64, (double)e));
+                            val = use_cross ? vx : val;
+                            code = use_cross ? 3u : code;
                         } else {
-                            float mv = cross32; code = 3;
-                            if (selfc > mv) { mv = selfc; code = 0; }
-                            val = __fadd_rn(mv, e);
+                            const bool use_cross = is_start[i] && !(c0 > cross32);
+                            const float vx = __fadd_rn(cross32, e);
+                            val = use_cross ? vx : val;
+                            code = use_cross ? 3u : code;
                         }
-                    } else {
-                        float best = __fadd_rn(b2[i], p2); code = 2;
-                        const float c1 = __fadd_rn(b1[i], p1);
-                        if (c1 > best) { best = c1; code = 1; }
-                        const float c0 = __fadd_rn(b0[i], d[i]);
-                        if (c0 > best) { best = c0; code = 0; }
-                        if (best == neg_inf()) code = 3;
-                        val = __fadd_rn(best, e);
                     }
                     nd[i] = act[i] ? val : neg_inf();
-                    bits |= code << (2 * ((t % FPW) * SPL + i));
+                    const int slot = (FPW > kPre) ? (slot_base + k) : (k & (FPW - 1));
+                    bits |= code << (2 * (slot * SPL + i));
                 }
 #pragma unroll
                 for (int i = 0; i < SPL; ++i) d[i] = nd[i];
-                if ((t % FPW) == FPW - 1 || t == T - 1) { s_bp[(t / FPW) * 32 + lane] = bits; bits = 0; }
+                const bool row_done = (FPW > kPre) ? (((slot_base + k) & (FPW - 1)) == FPW - 1) : ((k & (FPW - 1)) == FPW - 1);
+                if (row_done || j == T - 2) { s_bp[(j / FPW) * 32 + lane] = bits; bits = 0; }
             }
         }
 #pragma unroll
@@ -236,40 +206,44 @@ viterbi_warp_kernel(VitArgs a, int n_utt) {
     }
     __syncwarp();
 
-    // ---- termination: best END (lowest index on ties), END scores out
-    float de[SPL];
-    gather_ends(de);
-    if (a.end_scores) {
+    // ---- termination: best END (lowest position on ties); END scores out
+    const float m = end_max();
+    int pos = 0x7fffffff;
 #pragma unroll
-        for (int j = 0; j < SPL; ++j) {
-            const int w = lane + 32 * j;
-            if (w < a.max_ends) a.end_scores[(int64_t)u * a.max_ends + w] = de[j];
-        }
+    for (int i = 0; i < SPL; ++i) {
+        const unsigned eq = __ballot_sync(FULL, is_end[i] && d[i] == m);
+        if (eq) pos = min(pos, (__ffs(eq) - 1) * SPL + i);
     }
-    float lm = de[0];
+    const int end_pos = (pos == 0x7fffffff) ? 0 : pos;
+    int bi = 0;                                          // rank of end_pos among END positions
 #pragma unroll
-    for (int j = 1; j < SPL; ++j) lm = fmaxf(lm, de[j]);
-    const float m = fkey_inv(__reduce_max_sync(FULL, fkey(lm)));
-    int bi = -1;
-#pragma unroll
-    for (int j = 0; j < SPL; ++j) {
-        const unsigned eq = __ballot_sync(FULL, end_ok[j] && de[j] == m);
-        if (bi < 0 && eq) bi = 32 * j + __ffs(eq) - 1;
+    for (int i = 0; i < SPL; ++i) {
+        const int ln = end_pos / SPL, sl = end_pos % SPL;
+        const unsigned below = (i < sl) ? ((ln == 31) ? 0xffffffffu : ((2u << ln) - 1)) : ((1u << ln) - 1);
+        bi += __popc(end_mask[i] & below);
     }
-    if (bi < 0) bi = 0;
     if (lane == 0) { a.best[u] = bi; a.best_score[u] = (n_end > 0) ? m : neg_inf(); }
+    if (a.end_scores) {
+        int mine = 0;
+#pragma unroll
+        for (int i = 0; i < SPL; ++i)
+            if (is_end[i]) { a.end_scores[(int64_t)u * a.max_ends + lower + mine] = d[i]; ++mine; }
+        for (int w = n_end + lane; w < a.max_ends; w += 32) a.end_scores[(int64_t)u * a.max_ends + w] = neg_inf();
+    }
 
-    // ---- backtrace (every lane walks the same chain; lane 0 records it)
+    // ---- backtrace (every lane walks the same chain; lane 0 records it).  frame t >= 1 is j = t-1
     auto decode = [&](int t, int p) -> int {
-        const uint32_t w = s_bp[(t / FPW) * 32 + p / SPL];
-        const unsigned code = (w >> (2 * ((t % FPW) * SPL + p % SPL))) & 3u;
+        const int j = t - 1;
+        const uint32_t w = s_bp[(j / FPW) * 32 + p / SPL];
+        const unsigned code = (w >> (2 * ((j % FPW) * SPL + p % SPL))) & 3u;
         if (code < 3) return p - (int)code;
-        return (loop && (s_flags[p] & LOE_POS_START)) ? (int)s_cross[t] : 0;
+        if (LOOP && (s_flags[p] & LOE_POS_START)) return (int)((s_cross[j >> 2] >> (8 * (j & 3))) & 0xffu);
+        return 0;
     };
     if (T == 1) {
         if (lane == 0) s_path[0] = -1;
     } else {
-        int prev = decode(T - 1, n_end > 0 ? s_ends[bi] : 0);
+        int prev = decode(T - 1, n_end > 0 ? end_pos : 0);
         if (lane == 0) s_path[T - 1] = (int8_t)prev;
         for (int t = T - 2; t >= 0; --t) {
             if (lane == 0) s_path[t] = (int8_t)prev;
@@ -280,7 +254,7 @@ viterbi_warp_kernel(VitArgs a, int n_utt) {
     for (int t = lane; t < T; t += 32) a.path[f0 + t] = s_path[t];
 }
 
-template <int SPL>
+template <int SPL, bool LOOP, bool PENF64>
 static bool launch(const VitArgs& a, int n_utt, cudaStream_t s) {
     const WarpLayout L = warp_layout(a.max_frames, a.max_pos, SPL);
     const size_t smem = (size_t)L.total * kWarpsPerCta;
@@ -289,18 +263,25 @@ static bool launch(const VitArgs& a, int n_utt, cudaStream_t s) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return false;
     if (dev >= 64 || !attr_done[dev]) {
-        if (cudaFuncSetAttribute(viterbi_warp_kernel<SPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWarpSmemCap) != cudaSuccess)
+        if (cudaFuncSetAttribute(viterbi_warp_kernel<SPL, LOOP, PENF64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)kWarpSmemCap) != cudaSuccess)
             return false;
         if (dev < 64) attr_done[dev] = true;
     }
-    viterbi_warp_kernel<SPL><<<(unsigned)((n_utt + kWarpsPerCta - 1) / kWarpsPerCta), kWarpsPerCta * 32, smem, s>>>(a, n_utt);
+    viterbi_warp_kernel<SPL, LOOP, PENF64><<<(unsigned)((n_utt + kWarpsPerCta - 1) / kWarpsPerCta), kWarpsPerCta * 32, smem, s>>>(a, n_utt);
     return cudaGetLastError() == cudaSuccess;
 }
 
+template <int SPL>
+static bool launch_spl(const VitArgs& a, int n_utt, cudaStream_t s) {
+    if (!a.loop) return launch<SPL, false, false>(a, n_utt, s);
+    return a.pen_f64 ? launch<SPL, true, true>(a, n_utt, s) : launch<SPL, true, false>(a, n_utt, s);
+}
+
 bool viterbi_warp_launch(const VitArgs& a, int n_utt, cudaStream_t s) {
-    if (a.max_pos <= 32) return launch<1>(a, n_utt, s);
-    if (a.max_pos <= 64) return launch<2>(a, n_utt, s);
-    return launch<4>(a, n_utt, s);
+    if (a.max_pos <= 32) return launch_spl<1>(a, n_utt, s);
+    if (a.max_pos <= 64) return launch_spl<2>(a, n_utt, s);
+    return launch_spl<4>(a, n_utt, s);
 }
 
 }  // namespace loe
