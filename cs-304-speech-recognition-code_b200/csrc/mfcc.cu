@@ -72,14 +72,12 @@ static int ensure_tables() {
 // Kernel A
 // ------------------------------------------------------------------------------------------
 constexpr int kWarpsA = 8;
-constexpr int kFramesPerBlockA = 32;
+constexpr int kFramesPerBlockA = 64;
+constexpr int kMelItMax = LOE_MEL_NA_MAX + LOE_MEL_NB_MAX;
 
 struct __align__(16) SmemA {
-    float hann[kNfft];
-    float w320_re[kBins + 3], w320_im[kBins + 3];
-    float w32_re[16], w32_im[16];
-    float mel_w[LOE_MEL_MAXW * kMels];
-    int mel_start[kMels], mel_len[kMels];
+    float mel_w[kMelItMax * 32];
+    int mel_bin[kMelItMax * 32];
     float2 z[kWarpsA][kHalf];           // per-warp complex spectrum of the packed sequence
     float pw[kWarpsA][kBins + 3];       // per-warp power spectrum
 };
@@ -88,10 +86,15 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 
+// Mel filterbank as a lane-balanced table (host-built, see mfcc.py:mel_lane_tables):
+//   round A, iterations [0, na):      lane l accumulates filter l          (filters 0..31)
+//   round B, iterations [na, na+nb):  lanes 4q..4q+3 share filter 32 + q   (the 8 widest filters),
+//                                     combined with two xor shuffles
+// entry (it, lane) = weight mel_w[it*32+lane] applied to power bin mel_bin[it*32+lane] (0-weight padding).
 __global__ void __launch_bounds__(kWarpsA * 32)
 mfcc_mel_kernel(const float* __restrict__ pcm, const int64_t* __restrict__ pcm_off,
-                const int64_t* __restrict__ frm_off, const int32_t* __restrict__ mel_start,
-                const int32_t* __restrict__ mel_len, const float* __restrict__ mel_w,
+                const int64_t* __restrict__ frm_off, const int32_t* __restrict__ mel_bin,
+                const float* __restrict__ mel_w, int na, int nb,
                 float* __restrict__ mel_out, float* __restrict__ utt_max) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmemA& sm = *reinterpret_cast<SmemA*>(smem_raw);
@@ -102,20 +105,35 @@ mfcc_mel_kernel(const float* __restrict__ pcm, const int64_t* __restrict__ pcm_o
     if (t_begin >= T) return;
     const int t_end = min(T, t_begin + kFramesPerBlockA);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr unsigned FULL = 0xffffffffu;
 
-    for (int i = tid; i < kNfft; i += blockDim.x) sm.hann[i] = g_mfcc_tables.hann[i];
-    for (int i = tid; i < kBins; i += blockDim.x) {
-        sm.w320_re[i] = g_mfcc_tables.w320_re[i];
-        sm.w320_im[i] = g_mfcc_tables.w320_im[i];
-    }
-    if (tid < 16) { sm.w32_re[tid] = g_mfcc_tables.w32_re[tid]; sm.w32_im[tid] = g_mfcc_tables.w32_im[tid]; }
-    for (int i = tid; i < LOE_MEL_MAXW * kMels; i += blockDim.x) sm.mel_w[i] = mel_w[i];
-    if (tid < kMels) { sm.mel_start[tid] = mel_start[tid]; sm.mel_len[tid] = mel_len[tid]; }
-    // per-lane twiddles of the 5 x 32 decomposition
-    float2 tw[5];
+    for (int i = tid; i < (na + nb) * 32; i += blockDim.x) { sm.mel_w[i] = mel_w[i]; sm.mel_bin[i] = mel_bin[i]; }
+    // per-lane constants, fixed for every frame: window taps, 5x32 twiddles, shuffle-FFT twiddles,
+    // real-input post-pass twiddles
+    float hw[10];
+    float2 tw[5], ws[4], wp[5];
 #pragma unroll
-    for (int k1 = 0; k1 < 5; ++k1)
-        tw[k1] = make_float2(g_mfcc_tables.tw160_re[k1 * 32 + lane], g_mfcc_tables.tw160_im[k1 * 32 + lane]);
+    for (int n1 = 0; n1 < 5; ++n1) {
+        const int n = 2 * (32 * n1 + lane);
+        hw[2 * n1] = g_mfcc_tables.hann[n];
+        hw[2 * n1 + 1] = g_mfcc_tables.hann[n + 1];
+        tw[n1] = make_float2(g_mfcc_tables.tw160_re[n1 * 32 + lane], g_mfcc_tables.tw160_im[n1 * 32 + lane]);
+        const int k = lane + 32 * n1;
+        wp[n1] = make_float2(g_mfcc_tables.w320_re[k], g_mfcc_tables.w320_im[k]);
+    }
+    // stage h = 16, 8, 4, 2: lanes with bit h set multiply by W_{2h}^(lane & (h-1)), the others by 1;
+    // sg = -1 for the upper lane of a butterfly (o - y), +1 for the lower (y + o)
+    float sg[5];
+#pragma unroll
+    for (int st = 0; st < 5; ++st) {
+        const int h = 16 >> st;
+        const bool upper = (lane & h) != 0;
+        sg[st] = upper ? -1.f : 1.f;
+        if (st < 4) {
+            const int j = (lane & (h - 1)) * (16 / h);
+            ws[st] = upper ? make_float2(g_mfcc_tables.w32_re[j], g_mfcc_tables.w32_im[j]) : make_float2(1.f, 0.f);
+        }
+    }
     __syncthreads();
 
     const int64_t s0 = pcm_off[u];
@@ -126,18 +144,26 @@ mfcc_mel_kernel(const float* __restrict__ pcm, const int64_t* __restrict__ pcm_o
 
     const float C1 = 0.30901699437494745f, C2 = -0.80901699437494745f;   // cos(2pi/5), cos(4pi/5)
     const float S1 = 0.95105651629515353f, S2 = 0.58778525229247314f;    // sin(2pi/5), sin(4pi/5)
+    float2* zw = sm.z[warp];
+    float* pw = sm.pw[warp];
 
     for (int t = t_begin + warp; t < t_end; t += kWarpsA) {
         // ---- load + window: z[n] = x[2n] + i x[2n+1], n = 32*n1 + lane
         float2 v[5];
         const int64_t base = (int64_t)kHop * t - kHalf;
+        if (base >= 0 && base + kNfft <= n_samples) {          // interior frame: no bounds checks
+            const float* __restrict__ xb = x + base + 2 * lane;
 #pragma unroll
-        for (int n1 = 0; n1 < 5; ++n1) {
-            const int n = 2 * (32 * n1 + lane);
-            const int64_t i0 = base + n, i1 = i0 + 1;
-            float a = (i0 >= 0 && i0 < n_samples) ? __ldg(x + i0) : 0.f;
-            float b = (i1 >= 0 && i1 < n_samples) ? __ldg(x + i1) : 0.f;
-            v[n1] = make_float2(a * sm.hann[n], b * sm.hann[n + 1]);
+            for (int n1 = 0; n1 < 5; ++n1)
+                v[n1] = make_float2(__ldg(xb + 64 * n1) * hw[2 * n1], __ldg(xb + 64 * n1 + 1) * hw[2 * n1 + 1]);
+        } else {
+#pragma unroll
+            for (int n1 = 0; n1 < 5; ++n1) {
+                const int64_t i0 = base + 2 * (32 * n1 + lane), i1 = i0 + 1;
+                const float a = (i0 >= 0 && i0 < n_samples) ? __ldg(x + i0) : 0.f;
+                const float b = (i1 >= 0 && i1 < n_samples) ? __ldg(x + i1) : 0.f;
+                v[n1] = make_float2(a * hw[2 * n1], b * hw[2 * n1 + 1]);
+            }
         }
         // ---- radix-5 over n1 (forward transform), then twiddle W_160^(lane*k1)
         float2 y[5];
@@ -158,48 +184,50 @@ mfcc_mel_kernel(const float* __restrict__ pcm, const int64_t* __restrict__ pcm_o
         }
 #pragma unroll
         for (int k1 = 1; k1 < 5; ++k1) y[k1] = cmul(y[k1], tw[k1]);
-        // ---- 32-point DIF FFT across lanes for each k1 (output in bit-reversed lane order)
+        // ---- 32-point DIF FFT across lanes for each k1 (output in bit-reversed lane order):
+        //      every lane computes (sg*y + o) * w with its own sg, w -- no divergence
 #pragma unroll
-        for (int h = 16; h >= 1; h >>= 1) {
-            const bool upper = (lane & h) != 0;
-            const int j = (lane & (h - 1)) * (16 / h);
-            const float2 w = make_float2(sm.w32_re[j], sm.w32_im[j]);
+        for (int st = 0; st < 5; ++st) {
+            const int h = 16 >> st;
 #pragma unroll
             for (int k1 = 0; k1 < 5; ++k1) {
-                float ox = __shfl_xor_sync(0xffffffffu, y[k1].x, h);
-                float oy = __shfl_xor_sync(0xffffffffu, y[k1].y, h);
-                if (upper) y[k1] = cmul(make_float2(ox - y[k1].x, oy - y[k1].y), w);
-                else       y[k1] = make_float2(y[k1].x + ox, y[k1].y + oy);
+                const float ox = __shfl_xor_sync(FULL, y[k1].x, h);
+                const float oy = __shfl_xor_sync(FULL, y[k1].y, h);
+                const float2 a = make_float2(fmaf(sg[st], y[k1].x, ox), fmaf(sg[st], y[k1].y, oy));
+                y[k1] = (st < 4) ? cmul(a, ws[st < 4 ? st : 0]) : a;
             }
         }
 #pragma unroll
-        for (int k1 = 0; k1 < 5; ++k1) sm.z[warp][k1 + 5 * brev] = y[k1];
+        for (int k1 = 0; k1 < 5; ++k1) zw[k1 + 5 * brev] = y[k1];
         __syncwarp();
-        // ---- real-input post-pass + power spectrum, bins k = lane + 32*i
-        for (int k = lane; k < kBins; k += 32) {
-            const float2 A = sm.z[warp][k == kHalf ? 0 : k];
-            const float2 Bc = sm.z[warp][k == 0 ? 0 : kHalf - k];
-            const float2 B = make_float2(Bc.x, -Bc.y);
-            const float2 E = make_float2(0.5f * (A.x + B.x), 0.5f * (A.y + B.y));
-            const float2 Dm = make_float2(A.x - B.x, A.y - B.y);
-            const float2 O = make_float2(0.5f * Dm.y, -0.5f * Dm.x);
-            const float2 X = make_float2(E.x + O.x * sm.w320_re[k] - O.y * sm.w320_im[k],
-                                         E.y + O.x * sm.w320_im[k] + O.y * sm.w320_re[k]);
-            sm.pw[warp][k] = X.x * X.x + X.y * X.y;
+        // ---- real-input post-pass + power spectrum: bins k = lane + 32*i, i < 5 (k = 0..159), then k = 160
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            const int k = lane + 32 * i;
+            const float2 A = zw[k];
+            const float2 Bc = zw[k == 0 ? 0 : kHalf - k];
+            const float2 E = make_float2(0.5f * (A.x + Bc.x), 0.5f * (A.y - Bc.y));
+            const float2 O = make_float2(0.5f * (A.y + Bc.y), -0.5f * (A.x - Bc.x));
+            const float xr = E.x + O.x * wp[i].x - O.y * wp[i].y;
+            const float xi = E.y + O.x * wp[i].y + O.y * wp[i].x;
+            pw[k] = xr * xr + xi * xi;
         }
+        if (lane == 0) { const float2 Z0 = zw[0]; const float xn = Z0.x - Z0.y; pw[kHalf] = xn * xn; }   // Nyquist bin
         __syncwarp();
-        // ---- mel filterbank: filter m = lane, lane + 32
-        for (int m = lane; m < kMels; m += 32) {
-            const int st = sm.mel_start[m], ln = sm.mel_len[m];
-            float acc = 0.f;
-            for (int j = 0; j < ln; ++j) acc = fmaf(sm.mel_w[j * kMels + m], sm.pw[warp][st + j], acc);
-            mel_out[(f0 + t) * kMels + m] = acc;
-            vmax = fmaxf(vmax, acc);
-        }
+        // ---- mel filterbank (lane-balanced table)
+        float accA = 0.f, accB = 0.f;
+        for (int it = 0; it < na; ++it) accA = fmaf(sm.mel_w[it * 32 + lane], pw[sm.mel_bin[it * 32 + lane]], accA);
+        for (int it = na; it < na + nb; ++it) accB = fmaf(sm.mel_w[it * 32 + lane], pw[sm.mel_bin[it * 32 + lane]], accB);
+        accB += __shfl_xor_sync(FULL, accB, 1);
+        accB += __shfl_xor_sync(FULL, accB, 2);
+        float* mo = mel_out + (f0 + t) * kMels;
+        mo[lane] = accA;
+        if ((lane & 3) == 0) mo[32 + (lane >> 2)] = accB;
+        vmax = fmaxf(vmax, fmaxf(accA, accB));
         __syncwarp();
     }
 #pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    for (int o = 16; o >= 1; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(FULL, vmax, o));
     if (lane == 0) atomicMax(reinterpret_cast<int*>(utt_max + u), __float_as_int(vmax));   // mel >= 0
 }
 
@@ -214,7 +242,7 @@ mfcc_ceps_kernel(const float* __restrict__ mel, const float* __restrict__ utt_ma
                  const int64_t* __restrict__ frm_off, float* __restrict__ feat) {
     __shared__ float s_lm[kHaloB][kMels + 1];
     __shared__ float s_c[kHaloB][kCeps + 1];
-    __shared__ float s_dct[kCeps][kMels];
+    __shared__ float s_dct[kCeps][kMels + 1];
     __shared__ float s_out[kTileB * kFeat];
     const int u = blockIdx.x;
     const int64_t f0 = frm_off[u];
@@ -227,7 +255,7 @@ mfcc_ceps_kernel(const float* __restrict__ mel, const float* __restrict__ utt_ma
     const int g1 = min(T - 1, max(t1 + 3, 8));
     const int ng = g1 - g0 + 1;
 
-    for (int i = tid; i < kCeps * kMels; i += blockDim.x) (&s_dct[0][0])[i] = g_mfcc_tables.dct[i];
+    for (int i = tid; i < kCeps * kMels; i += blockDim.x) s_dct[i / kMels][i % kMels] = g_mfcc_tables.dct[i];
     const float ref_db = 10.0f * log10f(fmaxf(1e-10f, utt_max[u]));
     for (int i = tid; i < ng * kMels; i += blockDim.x) {
         const int j = i / kMels, m = i - j * kMels;
@@ -281,12 +309,16 @@ mfcc_ceps_kernel(const float* __restrict__ mel, const float* __restrict__ utt_ma
 
 extern "C" int loe_mfcc_dev(const float* pcm_dev, const int64_t* pcm_off_dev, const int64_t* frm_off_dev,
                             int n_utt, int64_t total_frames, int max_frames, int min_frames,
-                            const int32_t* mel_start_dev, const int32_t* mel_len_dev, const float* mel_w_dev,
+                            const int32_t* mel_bin_dev, const float* mel_w_dev, int mel_na, int mel_nb,
                             float* mel_ws_dev, float* utt_max_dev, float* feat_dev, void* stream) {
     using namespace loe;
     if (n_utt <= 0 || total_frames <= 0) return LOE_OK;
     if (min_frames < 9) {
         set_error("MFCC needs at least 9 frames per utterance for the width-9 delta filter (got %d)", min_frames);
+        return LOE_ERR_VALUE;
+    }
+    if (mel_na < 0 || mel_nb < 0 || mel_na > LOE_MEL_NA_MAX || mel_nb > LOE_MEL_NB_MAX) {
+        set_error("mel table iteration counts out of range (na=%d, nb=%d)", mel_na, mel_nb);
         return LOE_ERR_VALUE;
     }
     int st = ensure_tables();
@@ -295,8 +327,8 @@ extern "C" int loe_mfcc_dev(const float* pcm_dev, const int64_t* pcm_off_dev, co
     LOE_CUDA(cudaMemsetAsync(utt_max_dev, 0, sizeof(float) * (size_t)n_utt, s));
     static_assert(sizeof(SmemA) <= 48 * 1024, "kernel A must fit the default dynamic shared memory limit");
     dim3 ga((unsigned)n_utt, (unsigned)((max_frames + kFramesPerBlockA - 1) / kFramesPerBlockA));
-    mfcc_mel_kernel<<<ga, kWarpsA * 32, sizeof(SmemA), s>>>(pcm_dev, pcm_off_dev, frm_off_dev, mel_start_dev,
-                                                           mel_len_dev, mel_w_dev, mel_ws_dev, utt_max_dev);
+    mfcc_mel_kernel<<<ga, kWarpsA * 32, sizeof(SmemA), s>>>(pcm_dev, pcm_off_dev, frm_off_dev, mel_bin_dev, mel_w_dev,
+                                                           mel_na, mel_nb, mel_ws_dev, utt_max_dev);
     LOE_LAUNCH_CHECK("mfcc_mel_kernel");
     dim3 gb((unsigned)n_utt, (unsigned)((max_frames + kTileB - 1) / kTileB));
     mfcc_ceps_kernel<<<gb, 256, 0, s>>>(mel_ws_dev, utt_max_dev, frm_off_dev, feat_dev);

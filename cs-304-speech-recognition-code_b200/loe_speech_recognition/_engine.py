@@ -181,16 +181,16 @@ class Engine:
     def _mel_tables(self, sample_rate):
         key = float(sample_rate)
         if key not in self._mel_cache:
-            from .mfcc import mel_filterbank_sparse
-            start, length, w = mel_filterbank_sparse(sample_rate)
-            self._mel_cache[key] = (self._to_dev(start), self._to_dev(length), self._to_dev(w))
+            from .mfcc import mel_lane_tables
+            bins, w, na, nb = mel_lane_tables(sample_rate)
+            self._mel_cache[key] = (self._to_dev(bins), self._to_dev(w), na, nb)
         return self._mel_cache[key]
 
     def mfcc_device(self, pcm, pcm_off, frm_off, n_utt, total_frames, max_frames, min_frames, sample_rate=16000,
                     out=None, mel_ws=None, utt_max=None):
         """PCM (device) -> features [total_frames, 39] (device).  All tensors on this device."""
         torch = self.torch
-        start, length, w = self._mel_tables(sample_rate)
+        bins, w, na, nb = self._mel_tables(sample_rate)
         if out is None:
             out = self.empty((total_frames, 39), torch.float32)
         if mel_ws is None:
@@ -198,7 +198,7 @@ class Engine:
         if utt_max is None:
             utt_max = self.empty((n_utt,), torch.float32)
         _native.check(self.lib.loe_mfcc_dev(pcm.data_ptr(), pcm_off.data_ptr(), frm_off.data_ptr(), n_utt, total_frames,
-                                            max_frames, min_frames, start.data_ptr(), length.data_ptr(), w.data_ptr(),
+                                            max_frames, min_frames, bins.data_ptr(), w.data_ptr(), na, nb,
                                             mel_ws.data_ptr(), utt_max.data_ptr(), out.data_ptr(), self._stream()))
         self.launches += 2
         return out

@@ -17,7 +17,8 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libloe_b200.so")
 
 LOE_OK, LOE_ERR_CUDA, LOE_ERR_VALUE, LOE_ERR_OVERFLOW, LOE_ERR_DIM, LOE_ERR_UNSUPPORTED = range(6)
 LOE_MAX_POS = 128
-LOE_MEL_MAXW = 32
+LOE_MEL_NA_MAX = 32
+LOE_MEL_NB_MAX = 16
 POS_INIT, POS_START, POS_END = 1, 2, 4
 
 # every symbol include/loe_b200.h declares: name -> (restype, argtypes)
@@ -26,7 +27,7 @@ SIGNATURES = {
     "loe_last_error": (c_char_p, []),
     "loe_device_count": (c_int, []),
     "loe_mfcc_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int,
-                             c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+                             c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "loe_emission_dev": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int,
                                  c_void_p, c_int, c_int, c_void_p]),
     "loe_emission_tc_tiles": (c_int, [c_int]),

@@ -54,24 +54,26 @@ def mel_filterbank(sample_rate: float) -> NDArray[np.float32]:
     return w
 
 
-def mel_filterbank_sparse(sample_rate: float):
-    """(start int32 [40], length int32 [40], weights float32 [LOE_MEL_MAXW*40]) with weight j
-    of filter m stored at weights[j*40 + m] (the layout loe_mfcc_dev reads)."""
+def mel_lane_tables(sample_rate: float):
+    """The filterbank in the lane-balanced layout loe_mfcc_dev reads (include/loe_b200.h):
+    (bin int32 [(na+nb)*32], weight float32 [(na+nb)*32], na, nb).  Round A: lane l owns filter l
+    (filters 0..31), one non-zero per iteration.  Round B: lanes 4q..4q+3 share filter 32+q (the
+    widest filters), non-zero j goes to lane 4q + j%4, iteration j//4."""
     dense = mel_filterbank(sample_rate)
-    start = np.zeros(N_MELS, dtype=np.int32)
-    length = np.zeros(N_MELS, dtype=np.int32)
-    w = np.zeros((_native.LOE_MEL_MAXW, N_MELS), dtype=np.float32)
-    for m in range(N_MELS):
-        nz = np.nonzero(dense[m])[0]
-        if nz.size == 0:
-            continue
-        a, b = int(nz[0]), int(nz[-1]) + 1
-        if b - a > _native.LOE_MEL_MAXW:
-            raise NotImplementedError(f"mel filter {m} spans {b - a} bins at sample_rate={sample_rate}; "
-                                      f"the kernel supports {_native.LOE_MEL_MAXW}")
-        start[m], length[m] = a, b - a
-        w[: b - a, m] = dense[m, a:b]
-    return start, length, np.ascontiguousarray(w.reshape(-1))
+    nz = [np.nonzero(dense[m])[0] for m in range(N_MELS)]
+    na = max((len(nz[m]) for m in range(32)), default=0)
+    nb = max(((len(nz[m]) + 3) // 4 for m in range(32, N_MELS)), default=0)
+    if na > _native.LOE_MEL_NA_MAX or nb > _native.LOE_MEL_NB_MAX:
+        raise NotImplementedError(f"mel filters too wide for the kernel tables at sample_rate={sample_rate}")
+    bins = np.zeros((na + nb, 32), dtype=np.int32)
+    w = np.zeros((na + nb, 32), dtype=np.float32)
+    for m in range(32):
+        for j, k in enumerate(nz[m]):
+            bins[j, m], w[j, m] = k, dense[m, k]
+    for q, m in enumerate(range(32, N_MELS)):
+        for j, k in enumerate(nz[m]):
+            bins[na + j // 4, 4 * q + j % 4], w[na + j // 4, 4 * q + j % 4] = k, dense[m, k]
+    return np.ascontiguousarray(bins.reshape(-1)), np.ascontiguousarray(w.reshape(-1)), int(na), int(nb)
 
 
 @dataclass

@@ -46,7 +46,8 @@ typedef enum loe_status {
 #define LOE_N_FFT 320
 #define LOE_HOP 160
 #define LOE_N_BINS 161
-#define LOE_MEL_MAXW 32          /* widest supported mel filter, in FFT bins                         */
+#define LOE_MEL_NA_MAX 32        /* mel lane table: max iterations of round A / round B             */
+#define LOE_MEL_NB_MAX 16
 
 /* trellis position flags (loe_viterbi_dev / loe_align_dev) */
 #define LOE_POS_INIT 1           /* receives logpdf(x_0) + self-loop at t = 0                        */
@@ -69,8 +70,11 @@ int loe_device_count(void);
  *   pcm_off_dev  [n_utt+1] int64 sample offsets
  *   frm_off_dev  [n_utt+1] int64 frame offsets, frames(u) = 1 + samples(u)/160
  *   max_frames   max_u frames(u)            min_frames  min_u frames(u) (must be >= 9)
- *   mel_start_dev[40] int32, mel_len_dev[40] int32, mel_w_dev[LOE_MEL_MAXW*40] float32:
- *                sparse slaney filterbank, weight j of filter m at mel_w[j*40+m]
+ *   mel_bin_dev [(na+nb)*32] int32, mel_w_dev [(na+nb)*32] float32: the slaney filterbank as a
+ *                lane-balanced table.  Entry (it, lane) adds mel_w * power[mel_bin] to a partial sum:
+ *                iterations [0, na): lane l accumulates filter l (filters 0..31);
+ *                iterations [na, na+nb): lanes 4q..4q+3 share filter 32+q (non-zero j of that filter
+ *                goes to lane 4q + j%4, iteration na + j/4).  Unused entries have weight 0.
  *   mel_ws_dev   [total_frames*40] float32 workspace (mel energies)
  *   utt_max_dev  [n_utt] float32 workspace (per-utterance mel maximum)
  *   feat_dev     [total_frames*39] float32 out, row-major (frame, coefficient): the
@@ -78,7 +82,7 @@ int loe_device_count(void);
  * -------------------------------------------------------------------------------------- */
 int loe_mfcc_dev(const float* pcm_dev, const int64_t* pcm_off_dev, const int64_t* frm_off_dev,
                  int n_utt, int64_t total_frames, int max_frames, int min_frames,
-                 const int32_t* mel_start_dev, const int32_t* mel_len_dev, const float* mel_w_dev,
+                 const int32_t* mel_bin_dev, const float* mel_w_dev, int mel_na, int mel_nb,
                  float* mel_ws_dev, float* utt_max_dev, float* feat_dev, void* stream);
 
 /* --------------------------------------------------------------------------------------

@@ -204,15 +204,22 @@ def test_penalty_modes():
 
 
 def test_mel_filterbank_matches_oracle():
-    from loe_speech_recognition.mfcc import mel_filterbank, mel_filterbank_sparse
+    from loe_speech_recognition.mfcc import mel_filterbank, mel_lane_tables
     from oracle import mfcc as OM
     assert np.array_equal(mel_filterbank(16000), OM.mel_basis())
-    start, length, w = mel_filterbank_sparse(16000)
+    bins, w, na, nb = mel_lane_tables(16000)
+    assert (na, nb) == (11, 5)
+    bins = bins.reshape(na + nb, 32); w = w.reshape(na + nb, 32)
     dense = np.zeros((40, 161), np.float32)
-    w = w.reshape(-1, 40)
-    for m in range(40):
-        dense[m, start[m]:start[m] + length[m]] = w[:length[m], m]
-    assert np.array_equal(dense, OM.mel_basis()) and length.max() <= 18 and length.min() >= 2
+    for it in range(na):                              # round A: lane = filter
+        for lane in range(32):
+            dense[lane, bins[it, lane]] += w[it, lane]
+    for it in range(na, na + nb):                     # round B: 4 lanes per filter
+        for lane in range(32):
+            dense[32 + lane // 4, bins[it, lane]] += w[it, lane]
+    assert np.array_equal(dense, OM.mel_basis())
+    for sr in (22050, 44100):
+        mel_lane_tables(sr)
 
 
 def test_mfcc_input_validation_needs_no_gpu():
