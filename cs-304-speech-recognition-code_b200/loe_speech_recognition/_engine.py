@@ -125,11 +125,18 @@ class Engine:
         self.device = torch.device("cuda", device)
         torch.cuda.set_device(self.device)
         self._mel_cache = {}
+        self._copy_stream = None
         self.launches = 0           # kernels launched through the C ABI (bench.py reports it)
 
     # ------------------------------------------------------------------ helpers
     def _stream(self) -> int:
         return self.torch.cuda.current_stream(self.device).cuda_stream
+
+    def copy_stream(self):
+        """Side stream for host->device copies that overlap with compute (decode_pcm_flat)."""
+        if self._copy_stream is None:
+            self._copy_stream = self.torch.cuda.Stream(device=self.device)
+        return self._copy_stream
 
     def _to_dev(self, arr: np.ndarray):
         t = self.torch.from_numpy(np.ascontiguousarray(arr))

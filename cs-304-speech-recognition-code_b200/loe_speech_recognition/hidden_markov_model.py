@@ -426,27 +426,36 @@ class HiddenMarkovModelInference(_PackCache):
                                              loop=True, penalty=pen, penalty_f64=f64, want_end_scores=False)
         return best_score, path
 
-    def _strings_device(self, path, batch, max_words: int = 32) -> List[str]:
-        """path (device) -> digit strings: word sequence per utterance from the labels kernel
-        (model_boundary.py:107-147), only the tiny [n, max_words] id table crosses PCIe."""
+    def _labels_device(self, path, batch, max_words: int = 32):
+        """Launch the labels kernel (model_boundary.py:107-147): (words int8 [n, max_words], count int32 [n])
+        on the device -- only this small id table crosses PCIe."""
         eng = _engine()
         _, tp = self._packs()
         labels = self._model_boundaries._labels
         skip = labels.index("S") if "S" in labels else -1
-        words, count = eng.labels(path, batch.frm_off, batch.n_utt, tp, skip_label=skip, max_words=max_words)
-        words_h, count_h = words.cpu().numpy(), count.cpu().numpy()
-        out: List[str] = []
-        path_h = None
-        for i in range(batch.n_utt):
-            c = int(count_h[i])
-            if 0 <= c <= max_words:
-                out.append("".join(labels[k] for k in words_h[i, :c]))
-            else:                                         # overflow or T == 1: the host routine decides (and raises)
-                if path_h is None:
-                    path_h = path.cpu().numpy()
-                off = batch.frm_off_host
-                out.append("".join(self._model_boundaries.get_labels(path_h[off[i]:off[i + 1]])))
+        return eng.labels(path, batch.frm_off, batch.n_utt, tp, skip_label=skip, max_words=max_words)
+
+    def _strings_host(self, words_h, count_h, path_getter, frm_off_host) -> List[str]:
+        """Word-id table -> strings.  Utterances whose count overflowed the table or whose path held a
+        negative state (T == 1) go through the host routine, which decides (and raises like the reference)."""
+        labels = self._model_boundaries._labels
+        n, max_words = words_h.shape
+        if all(len(l) == 1 for l in labels):
+            lut = np.frombuffer("".join(labels).encode("latin-1"), dtype=np.uint8)
+            flat = lut[np.clip(words_h, 0, len(labels) - 1)].tobytes().decode("latin-1")
+            out = [flat[i * max_words: i * max_words + c] for i, c in enumerate(count_h.tolist())]
+        else:
+            out = ["".join(labels[k] for k in words_h[i, :max(c, 0)]) for i, c in enumerate(count_h.tolist())]
+        bad = np.nonzero((count_h < 0) | (count_h > max_words))[0]
+        if bad.size:
+            path_h = path_getter()
+            for i in bad.tolist():
+                out[i] = "".join(self._model_boundaries.get_labels(path_h[frm_off_host[i]:frm_off_host[i + 1]]))
         return out
+
+    def _strings_device(self, path, batch, max_words: int = 32) -> List[str]:
+        words, count = self._labels_device(path, batch, max_words)
+        return self._strings_host(words.cpu().numpy(), count.cpu().numpy(), lambda: path.cpu().numpy(), batch.frm_off_host)
 
     def predict_batch(self, signals: Sequence[NDArray[np.float32]], precision: Optional[str] = None) -> List[str]:
         """Digit strings of many (T, 39) feature matrices in one pass (added entry point)."""
@@ -465,27 +474,65 @@ class HiddenMarkovModelInference(_PackCache):
 
 
     def decode_pcm_flat(self, pcm_flat, sample_offsets: NDArray[np.int64], sample_rate: int = 16000,
-                        precision: Optional[str] = None) -> List[str]:
+                        precision: Optional[str] = None, n_chunks: Optional[int] = None) -> List[str]:
         """Batch ingestion form of :meth:`decode_pcm_batch`: ``pcm_flat`` is ONE host buffer (numpy
         array or pinned torch tensor, float32, utterances back to back) and ``sample_offsets`` the
-        [n+1] sample offsets.  Host->device copy of the samples, MFCC, emission, Viterbi, labels and
-        the device->host copy of the word ids all happen inside this call (added entry point)."""
+        [n+1] sample offsets.  The batch is cut into chunks of whole utterances; the host->device copy
+        of chunk c+1 runs on a copy stream while chunk c goes through MFCC, emission, Viterbi and
+        labels on the compute stream, and only the word-id tables come back (added entry point)."""
         from ._engine import Batch
         eng = _engine()
         torch = eng.torch
         off = np.asarray(sample_offsets, dtype=np.int64)
-        lens = np.diff(off)
-        frames = 1 + lens // 160
-        frm_off = np.concatenate(([0], np.cumsum(frames))).astype(np.int64)
+        n = len(off) - 1
+        if n <= 0:
+            return []
         src = pcm_flat if isinstance(pcm_flat, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(pcm_flat, dtype=np.float32))
-        pcm = src.to(eng.device, non_blocking=True)
-        pcm_off = eng._to_dev(off)
-        frm_off_dev = eng._to_dev(frm_off)
-        feat = eng.mfcc_device(pcm, pcm_off, frm_off_dev, len(lens), int(frm_off[-1]), int(frames.max()), int(frames.min()),
-                               sample_rate)
-        batch = Batch(feat, frm_off_dev, frm_off, len(lens), int(frames.max()))
-        _, path = self._decode_device(batch, precision)
-        return self._strings_device(path, batch)
+        frames = 1 + np.diff(off) // 160
+        if n_chunks is None:
+            n_chunks = int(min(8, max(1, (int(off[-1]) * 4) // (64 << 20))))      # >= 64 MB per chunk
+        cuts = np.searchsorted(off, np.linspace(0, int(off[-1]), n_chunks + 1)[1:-1]).tolist()
+        bounds = sorted(set([0] + [min(max(int(c), 0), n) for c in cuts] + [n]))
+        comp = torch.cuda.current_stream(eng.device)
+        copy = eng.copy_stream()
+        copy.wait_stream(comp)
+        max_words = 32
+        words_h = torch.empty((n, max_words), dtype=torch.int8).pin_memory() if n_chunks > 1 else None
+        count_h = torch.empty((n,), dtype=torch.int32).pin_memory() if n_chunks > 1 else None
+        keep = []
+        for a, b in zip(bounds[:-1], bounds[1:]):
+            if a == b:
+                continue
+            s0, s1 = int(off[a]), int(off[b])
+            fr = frames[a:b]
+            frm_off = np.concatenate(([0], np.cumsum(fr))).astype(np.int64)
+            with torch.cuda.stream(copy):
+                pcm = src[s0:s1].to(eng.device, non_blocking=True)
+                pcm_off = torch.from_numpy(off[a:b + 1] - s0).to(eng.device, non_blocking=True)
+                frm_off_dev = torch.from_numpy(frm_off).to(eng.device, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy)
+            comp.wait_event(ev)
+            for t in (pcm, pcm_off, frm_off_dev):
+                t.record_stream(comp)
+            feat = eng.mfcc_device(pcm, pcm_off, frm_off_dev, b - a, int(frm_off[-1]), int(fr.max()), int(fr.min()), sample_rate)
+            batch = Batch(feat, frm_off_dev, frm_off, b - a, int(fr.max()))
+            _, path = self._decode_device(batch, precision)
+            words, count = self._labels_device(path, batch, max_words)
+            if n_chunks > 1:
+                words_h[a:b].copy_(words, non_blocking=True)
+                count_h[a:b].copy_(count, non_blocking=True)
+            keep.append((a, b, path, frm_off, words, count))
+        if n_chunks > 1:
+            comp.synchronize()
+            wh, ch = words_h.numpy(), count_h.numpy()
+        else:
+            wh, ch = keep[0][4].cpu().numpy(), keep[0][5].cpu().numpy()
+
+        def full_path():
+            return np.concatenate([p.cpu().numpy() for _, _, p, _, _, _ in keep])
+        frm_all = np.concatenate(([0], np.cumsum(frames))).astype(np.int64)
+        return self._strings_host(wh, ch, full_path, frm_all)
 
 
 # ----------------------------------------------------------------------------------------

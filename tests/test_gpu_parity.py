@@ -327,6 +327,14 @@ def test_pcm_to_strings_pipeline(eng, golden):
     assert got == inf.predict_batch(feats)
     want = [str(s) for s in golden["loop_strings_int"]][:6]
     assert sum(g == w for g, w in zip(got, want)) >= 5
+    # flat host buffer, chunked copy/compute overlap: same strings for any chunking
+    flat = np.concatenate(utts)
+    off = np.concatenate(([0], np.cumsum([len(u) for u in utts]))).astype(np.int64)
+    for n_chunks in (1, 2, 3, 6, 9):
+        assert inf.decode_pcm_flat(flat, off, 16000, n_chunks=n_chunks) == got
+    pinned = eng.torch.from_numpy(flat).pin_memory()
+    assert inf.decode_pcm_flat(pinned, off) == got
+    assert inf.decode_pcm_flat(flat[:0], off[:1]) == []
 
 
 def test_large_batch_properties(eng, golden):
