@@ -130,7 +130,7 @@ accum_kernel(const float* __restrict__ feat, const uint16_t* __restrict__ bucket
             const int nb = min(kAccBatch, n_match - b0);
             for (int i = tid; i < nb * K; i += kAccThreads) {
                 const int r = i / K, k = i - r * K;
-                s_x[r][k] = (k < dim) ? (double)(feat[s_list[b0 + r] * dim + k] - s_shift[k]) : 1.0;
+                s_x[r][k] = (k < dim) ? ((double)feat[s_list[b0 + r] * dim + k] - (double)s_shift[k]) : 1.0;
             }
             __syncthreads();
 #pragma unroll

@@ -365,3 +365,67 @@ def test_large_batch_properties(eng, golden):
     sc = eng.emission(b.feat, gp, "fp32").cpu().numpy()
     _, _, opaths2 = O.viterbi_batch([sc[off[i]:off[i + 1]] for i in idx], tr, penalty=-100)
     assert all(np.array_equal(op, path_h[off[i]:off[i + 1]]) for i, op in zip(idx, opaths2))
+
+
+def test_training_at_scale_matches_oracle(eng, golden):
+    """600 utterances of one word (tiled pool with noise): GPU trainer vs the oracle training loop."""
+    from oracle import hmm as O
+    from loe_speech_recognition import HiddenMarkovModelTrainable
+    rng = np.random.default_rng(9)
+    base = [golden[f"train_feat_7_{i}"] for i in range(8)]
+    feats = [(base[i % 8] + rng.normal(0, 0.05, size=base[i % 8].shape)).astype(np.float32) for i in range(600)]
+    m = HiddenMarkovModelTrainable.from_data("7", feats, num_of_states=5, max_iterations=3, isMultiProcessingTraining=False, isTqdm=False)
+    means, covs, trans = O.init_parameters(feats[0], 5)
+    for it in range(3):
+        packs = [O.gaussian_pack(means[s], covs[s]) for s in range(5)]
+        tr = O.word_trellis(O.log_transitions(trans))
+        ems = [O.emission_scores(x, [p[0] for p in packs], [p[1] for p in packs], [p[2] for p in packs]) for x in feats]
+        _, _, paths = O.viterbi_batch(ems, tr)
+        r = O.mstep(feats, paths, 5, old_means=means)
+        if r["converged"]:
+            break
+        means, covs, trans = r["means"], r["covs"], r["trans"]
+    assert rel_close(m._means, means, rtol=1e-3, atol=1e-4)
+    assert rel_close(m._covariances, covs, rtol=1e-2, atol=1e-4)
+    assert np.allclose(m._transition_probs.to_dense(), trans, atol=2e-3)
+
+
+def test_kmeans_statistics_large_random(eng):
+    """Statistics kernels on 20k utterances with random (valid and invalid) alignments vs NumPy."""
+    from loe_speech_recognition import _trellis
+    rng = np.random.default_rng(2)
+    S, D, n = 5, 39, 20000
+    lens = rng.integers(9, 60, size=n)
+    off = np.concatenate(([0], np.cumsum(lens))).astype(np.int64)
+    F = int(off[-1])
+    x = rng.normal(0, 2, size=(F, D)).astype(np.float32)
+    path = np.zeros(F, dtype=np.int8)
+    for i in range(n):
+        p = np.sort(rng.integers(0, S, size=lens[i]))
+        if i % 50 == 0:
+            p = p[::-1].copy()                       # decreasing: only the first run is credited
+        path[off[i]:off[i + 1]] = p
+    tp = eng.pack_trellises([_trellis.build([np.zeros((S, S), np.float32)], [0], [0], "word")])
+    shift = rng.normal(size=(S, D)).astype(np.float32)
+    stats, counts, bucket = eng.kmeans_stats(eng._to_dev(x), eng._to_dev(path), eng._to_dev(off), n, F, tp, None, False, S,
+                                             eng._to_dev(shift))
+    stats = stats.cpu().numpy(); counts = counts.cpu().numpy()
+    # NumPy restatement of order_by_state + statistics
+    valid = np.zeros(F, dtype=bool)
+    ref_counts = np.zeros((S, S), dtype=np.int64)
+    for i in range(n):
+        p = path[off[i]:off[i + 1]].astype(int)
+        ok = np.concatenate(([True], np.cumprod(np.diff(p) >= 0).astype(bool)))
+        valid[off[i]:off[i + 1]] = ok
+        np.add.at(ref_counts, (p[:-1], p[1:]), 1)
+    assert np.array_equal(counts, ref_counts)
+    iu = np.triu_indices(D)
+    for s in range(S):
+        sel = valid & (path == s)
+        d = x[sel].astype(np.float64) - shift[s]
+        assert stats[s, 0] == sel.sum()
+        assert np.allclose(stats[s, 1:1 + D], d.sum(0), rtol=1e-10, atol=1e-8)
+        assert np.allclose(stats[s, 1 + D:], (d.T @ d)[iu], rtol=1e-10, atol=1e-8)
+    # bitwise reproducible
+    stats2, _, _ = eng.kmeans_stats(eng._to_dev(x), eng._to_dev(path), eng._to_dev(off), n, F, tp, None, False, S, eng._to_dev(shift))
+    assert np.array_equal(stats, stats2.cpu().numpy())
