@@ -15,13 +15,13 @@
 // = 75 KB resident in shared memory for the whole kernel, loaded once) and walks the frame
 // tiles g, g+G, ... (M = 128 frames).  The 10 CTAs of a column g walk the same frames at the
 // same pace, so the feature tile is fetched from HBM once and re-read from L2.
-//   warps 0-3  producers: coalesced load of the raw [128 x 39] tile (software-prefetched one
+//   warps 0-7  producers: coalesced load of the raw [128 x 39] tile (software-prefetched one
 //              tile ahead), hi/lo split, store in the canonical K-major no-swizzle UMMA layout
 //              (8 x 16 B core matrices; LBO = K-chunk stride, SBO = 128 B), fence.proxy.async,
 //              arrive on a_full[stage]
-//   warp  8    one thread issues 15 tcgen05.mma.kind::tf32 (M128 N240 K8) per tile and
+//   warp  12   one thread issues 15 tcgen05.mma.kind::tf32 (M128 N240 K8) per tile and
 //              tcgen05.commit's to a_empty[stage] and tmem_full[buf]
-//   warps 4-7  epilogue: tcgen05.ld the 128 x 240 fp32 accumulator (thread = frame row),
+//   warps 8-11 epilogue: tcgen05.ld the 128 x 240 fp32 accumulator (thread = frame row),
 //              square + sum each group of 40 columns, store 6 scores per frame
 // Accumulators are double buffered in TMEM (2 x 240 of the 512 columns), A in shared memory
 // (2 stages), so staging(i+1), MMA(i) and epilogue(i-1) overlap.
@@ -40,7 +40,7 @@ constexpr int kTileN = kStatesPerTile * kColsPerState;   // 240
 constexpr int kTmemCols = 512;
 constexpr int kBufStride = 256;         // TMEM column offset between the two accumulators
 constexpr int kDim = 39;
-constexpr int kProducerThreads = 128;
+constexpr int kProducerThreads = 256;      // 8 warps: 2 per SM sub-partition, so staging latencies overlap
 constexpr int kEpilogueThreads = 128;
 constexpr int kThreads = kProducerThreads + kEpilogueThreads + 32;
 
@@ -149,7 +149,7 @@ emission_tc_kernel(const float* __restrict__ feat, int64_t n_frames, const float
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {
+    if (warp == kProducerThreads / 32) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(kTmemCols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -165,36 +165,45 @@ emission_tc_kernel(const float* __restrict__ feat, int64_t n_frames, const float
     tc_fence_after();
     const uint32_t tmem_base = sm.tmem_base;
 
-    if (warp < 4) {
+    if (warp < kProducerThreads / 32) {
         // =========================== producers ===========================
-        float pre[kDim];                                   // raw tile, flat element tid + 128*i
+        constexpr int kTileElems = kTileM * kDim;                       // 4992
+        constexpr int kPre = (kTileElems + kProducerThreads - 1) / kProducerThreads;   // 20
+        float pre[kPre];                                   // raw tile, flat element tid + 256*i
         auto prefetch = [&](int m) {
             const int64_t f0 = (int64_t)m * kTileM;
             const int rows = (int)min((int64_t)kTileM, n_frames - f0);
-            const float* src = feat + f0 * kDim;
-            const int total = rows * kDim;
+            const float* __restrict__ src = feat + f0 * kDim + tid;
+            if (rows == kTileM) {                          // full tile: no per-element bounds
 #pragma unroll
-            for (int i = 0; i < kDim; ++i) {
-                const int e = tid + i * kProducerThreads;
-                pre[i] = (e < total) ? __ldg(src + e) : 0.f;
+                for (int i = 0; i < kPre - 1; ++i) pre[i] = __ldg(src + i * kProducerThreads);
+                pre[kPre - 1] = (tid + (kPre - 1) * kProducerThreads < kTileElems) ? __ldg(src + (kPre - 1) * kProducerThreads) : 0.f;
+            } else {
+                const int total = rows * kDim;
+#pragma unroll
+                for (int i = 0; i < kPre; ++i) pre[i] = (tid + i * kProducerThreads < total) ? __ldg(src + i * kProducerThreads) : 0.f;
             }
         };
         if (g < n_mtiles) prefetch(g);
+        const int row_id = tid & (kTileM - 1);
+        const int kc0 = (tid >> 7) * (kKChunks / 2);       // this thread's half of the K chunks
         int it = 0;
         for (int m = g; m < n_mtiles; m += G, ++it) {
             const int s = it & 1;
             const uint32_t k = (uint32_t)(it >> 1);
             // raw tile -> shared (flat, conflict free)
 #pragma unroll
-            for (int i = 0; i < kDim; ++i) sm.raw[tid + i * kProducerThreads] = pre[i];
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int i = 0; i < kPre; ++i)
+                if (i < kPre - 1 || tid + i * kProducerThreads < kTileElems) sm.raw[tid + i * kProducerThreads] = pre[i];
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             if (m + G < n_mtiles) prefetch(m + G);         // next tile's loads fly during the transform
             mbar_wait(&sm.a_empty[s], (k & 1) ^ 1);        // MMA finished reading this stage
-            const float* row = sm.raw + tid * kDim;        // stride 39 words: conflict free
-            uint8_t* ah = sm.a_hi[s] + tid * 16;
-            uint8_t* al = sm.a_lo[s] + tid * 16;
+            const float* row = sm.raw + row_id * kDim;     // stride 39 words: conflict free
+            uint8_t* ah = sm.a_hi[s] + row_id * 16;
+            uint8_t* al = sm.a_lo[s] + row_id * 16;
 #pragma unroll
-            for (int kc = 0; kc < kKChunks; ++kc) {
+            for (int kk = 0; kk < kKChunks / 2; ++kk) {
+                const int kc = kc0 + kk;
                 float v[4], h[4], l[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -208,9 +217,9 @@ emission_tc_kernel(const float* __restrict__ feat, int64_t n_frames, const float
             }
             fence_proxy_async();
             mbar_arrive(&sm.a_full[s]);
-            asm volatile("bar.sync 1, 128;" ::: "memory"); // everyone done with sm.raw before it is overwritten
+            asm volatile("bar.sync 1, 256;" ::: "memory"); // everyone done with sm.raw before it is overwritten
         }
-    } else if (warp == 8) {
+    } else if (warp == (kProducerThreads + kEpilogueThreads) / 32) {
         // =========================== MMA issuer ===========================
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTileN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
@@ -273,7 +282,7 @@ emission_tc_kernel(const float* __restrict__ feat, int64_t n_frames, const float
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == kProducerThreads / 32) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
     }
