@@ -91,8 +91,9 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
 //   round B, iterations [na, na+nb):  lanes 4q..4q+3 share filter 32 + q   (the 8 widest filters),
 //                                     combined with two xor shuffles
 // entry (it, lane) = weight mel_w[it*32+lane] applied to power bin mel_bin[it*32+lane] (0-weight padding).
+template <typename SampleT>
 __global__ void __launch_bounds__(kWarpsA * 32)
-mfcc_mel_kernel(const float* __restrict__ pcm, const int64_t* __restrict__ pcm_off,
+mfcc_mel_kernel(const SampleT* __restrict__ pcm, const int64_t* __restrict__ pcm_off,
                 const int64_t* __restrict__ frm_off, const int32_t* __restrict__ mel_bin,
                 const float* __restrict__ mel_w, int na, int nb,
                 float* __restrict__ mel_out, float* __restrict__ utt_max) {
@@ -138,7 +139,7 @@ mfcc_mel_kernel(const float* __restrict__ pcm, const int64_t* __restrict__ pcm_o
 
     const int64_t s0 = pcm_off[u];
     const int64_t n_samples = pcm_off[u + 1] - s0;
-    const float* __restrict__ x = pcm + s0;
+    const SampleT* __restrict__ x = pcm + s0;
     const int brev = (int)(__brev((unsigned)lane) >> 27);
     float vmax = 0.f;
 
@@ -152,17 +153,17 @@ mfcc_mel_kernel(const float* __restrict__ pcm, const int64_t* __restrict__ pcm_o
         float2 v[5];
         const int64_t base = (int64_t)kHop * t - kHalf;
         if (base >= 0 && base + kNfft <= n_samples) {          // interior frame: no bounds checks
-            const float* __restrict__ xb = x + base + 2 * lane;
+            const SampleT* __restrict__ xb = x + base + 2 * lane;
 #pragma unroll
             for (int n1 = 0; n1 < 5; ++n1)
-                v[n1] = make_float2(__ldg(xb + 64 * n1) * hw[2 * n1], __ldg(xb + 64 * n1 + 1) * hw[2 * n1 + 1]);
+                v[n1] = make_float2(__fmul_rn((float)__ldg(xb + 64 * n1), hw[2 * n1]), __fmul_rn((float)__ldg(xb + 64 * n1 + 1), hw[2 * n1 + 1]));
         } else {
 #pragma unroll
             for (int n1 = 0; n1 < 5; ++n1) {
                 const int64_t i0 = base + 2 * (32 * n1 + lane), i1 = i0 + 1;
-                const float a = (i0 >= 0 && i0 < n_samples) ? __ldg(x + i0) : 0.f;
-                const float b = (i1 >= 0 && i1 < n_samples) ? __ldg(x + i1) : 0.f;
-                v[n1] = make_float2(a * hw[2 * n1], b * hw[2 * n1 + 1]);
+                const float a = (i0 >= 0 && i0 < n_samples) ? (float)__ldg(x + i0) : 0.f;
+                const float b = (i1 >= 0 && i1 < n_samples) ? (float)__ldg(x + i1) : 0.f;
+                v[n1] = make_float2(__fmul_rn(a, hw[2 * n1]), __fmul_rn(b, hw[2 * n1 + 1]));   // never contracted: f32 and s16 inputs agree bit for bit
             }
         }
         // ---- radix-5 over n1 (forward transform), then twiddle W_160^(lane*k1)
@@ -307,7 +308,7 @@ mfcc_ceps_kernel(const float* __restrict__ mel, const float* __restrict__ utt_ma
 
 }  // namespace loe
 
-extern "C" int loe_mfcc_dev(const float* pcm_dev, const int64_t* pcm_off_dev, const int64_t* frm_off_dev,
+extern "C" int loe_mfcc_dev(const void* pcm_dev, int pcm_format, const int64_t* pcm_off_dev, const int64_t* frm_off_dev,
                             int n_utt, int64_t total_frames, int max_frames, int min_frames,
                             const int32_t* mel_bin_dev, const float* mel_w_dev, int mel_na, int mel_nb,
                             float* mel_ws_dev, float* utt_max_dev, float* feat_dev, void* stream) {
@@ -327,8 +328,13 @@ extern "C" int loe_mfcc_dev(const float* pcm_dev, const int64_t* pcm_off_dev, co
     LOE_CUDA(cudaMemsetAsync(utt_max_dev, 0, sizeof(float) * (size_t)n_utt, s));
     static_assert(sizeof(SmemA) <= 48 * 1024, "kernel A must fit the default dynamic shared memory limit");
     dim3 ga((unsigned)n_utt, (unsigned)((max_frames + kFramesPerBlockA - 1) / kFramesPerBlockA));
-    mfcc_mel_kernel<<<ga, kWarpsA * 32, sizeof(SmemA), s>>>(pcm_dev, pcm_off_dev, frm_off_dev, mel_bin_dev, mel_w_dev,
-                                                           mel_na, mel_nb, mel_ws_dev, utt_max_dev);
+    if (pcm_format == LOE_PCM_F32)
+        mfcc_mel_kernel<float><<<ga, kWarpsA * 32, sizeof(SmemA), s>>>((const float*)pcm_dev, pcm_off_dev, frm_off_dev, mel_bin_dev,
+                                                                      mel_w_dev, mel_na, mel_nb, mel_ws_dev, utt_max_dev);
+    else if (pcm_format == LOE_PCM_S16)
+        mfcc_mel_kernel<short><<<ga, kWarpsA * 32, sizeof(SmemA), s>>>((const short*)pcm_dev, pcm_off_dev, frm_off_dev, mel_bin_dev,
+                                                                      mel_w_dev, mel_na, mel_nb, mel_ws_dev, utt_max_dev);
+    else { set_error("unknown pcm_format %d", pcm_format); return LOE_ERR_VALUE; }
     LOE_LAUNCH_CHECK("mfcc_mel_kernel");
     dim3 gb((unsigned)n_utt, (unsigned)((max_frames + kTileB - 1) / kTileB));
     mfcc_ceps_kernel<<<gb, 256, 0, s>>>(mel_ws_dev, utt_max_dev, frm_off_dev, feat_dev);

@@ -204,7 +204,13 @@ class Engine:
             mel_ws = self.empty((total_frames, 40), torch.float32)
         if utt_max is None:
             utt_max = self.empty((n_utt,), torch.float32)
-        _native.check(self.lib.loe_mfcc_dev(pcm.data_ptr(), pcm_off.data_ptr(), frm_off.data_ptr(), n_utt, total_frames,
+        if pcm.dtype == torch.int16:
+            fmt = 1
+        elif pcm.dtype == torch.float32:
+            fmt = 0
+        else:
+            raise TypeError(f"PCM must be float32 or int16 on the device (got {pcm.dtype})")
+        _native.check(self.lib.loe_mfcc_dev(pcm.data_ptr(), fmt, pcm_off.data_ptr(), frm_off.data_ptr(), n_utt, total_frames,
                                             max_frames, min_frames, bins.data_ptr(), w.data_ptr(), na, nb,
                                             mel_ws.data_ptr(), utt_max.data_ptr(), out.data_ptr(), self._stream()))
         self.launches += 2
@@ -215,8 +221,10 @@ class Engine:
         pcm_off = np.concatenate(([0], np.cumsum(lens))).astype(np.int64)
         frames = 1 + lens // 160
         frm_off = np.concatenate(([0], np.cumsum(frames))).astype(np.int64)
-        flat = np.concatenate([np.asarray(s, dtype=np.float32) for s in signals]) if len(signals) > 1 \
-            else np.ascontiguousarray(signals[0], dtype=np.float32)
+        # int16 signals (raw WAV samples) stay int16 on the wire; anything else is shipped as float32
+        dt = np.int16 if all(s.dtype == np.int16 for s in signals) else np.float32
+        flat = np.concatenate([np.asarray(s, dtype=dt) for s in signals]) if len(signals) > 1 \
+            else np.ascontiguousarray(signals[0], dtype=dt)
         return self._to_dev(flat), self._to_dev(pcm_off), self._to_dev(frm_off), frm_off, frames
 
     def mfcc(self, signals: Sequence[np.ndarray], sample_rate=16000) -> Batch:

@@ -26,7 +26,7 @@ SIGNATURES = {
     "loe_abi_version": (c_int, []),
     "loe_last_error": (c_char_p, []),
     "loe_device_count": (c_int, []),
-    "loe_mfcc_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int,
+    "loe_mfcc_dev": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64, c_int, c_int,
                              c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "loe_emission_dev": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int,
                                  c_void_p, c_int, c_int, c_void_p]),

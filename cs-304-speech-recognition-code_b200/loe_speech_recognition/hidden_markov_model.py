@@ -476,7 +476,8 @@ class HiddenMarkovModelInference(_PackCache):
     def decode_pcm_flat(self, pcm_flat, sample_offsets: NDArray[np.int64], sample_rate: int = 16000,
                         precision: Optional[str] = None, n_chunks: Optional[int] = None) -> List[str]:
         """Batch ingestion form of :meth:`decode_pcm_batch`: ``pcm_flat`` is ONE host buffer (numpy
-        array or pinned torch tensor, float32, utterances back to back) and ``sample_offsets`` the
+        array or pinned torch tensor, utterances back to back; float32 as the reference holds them, or
+        the raw int16 WAV samples -- half the PCIe bytes, identical results) and ``sample_offsets`` the
         [n+1] sample offsets.  The batch is cut into chunks of whole utterances; the host->device copy
         of chunk c+1 runs on a copy stream while chunk c goes through MFCC, emission, Viterbi and
         labels on the compute stream, and only the word-id tables come back (added entry point)."""
@@ -487,10 +488,14 @@ class HiddenMarkovModelInference(_PackCache):
         n = len(off) - 1
         if n <= 0:
             return []
-        src = pcm_flat if isinstance(pcm_flat, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(pcm_flat, dtype=np.float32))
+        if isinstance(pcm_flat, torch.Tensor):
+            src = pcm_flat
+        else:
+            arr = np.asarray(pcm_flat)
+            src = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.int16 if arr.dtype == np.int16 else np.float32))
         frames = 1 + np.diff(off) // 160
         if n_chunks is None:
-            n_chunks = int(min(8, max(1, (int(off[-1]) * 4) // (64 << 20))))      # >= 64 MB per chunk
+            n_chunks = int(min(8, max(1, (int(off[-1]) * src.element_size()) // (64 << 20))))      # >= 64 MB per chunk
         cuts = np.searchsorted(off, np.linspace(0, int(off[-1]), n_chunks + 1)[1:-1]).tolist()
         bounds = sorted(set([0] + [min(max(int(c), 0), n) for c in cuts] + [n]))
         comp = torch.cuda.current_stream(eng.device)

@@ -46,6 +46,8 @@ typedef enum loe_status {
 #define LOE_N_FFT 320
 #define LOE_HOP 160
 #define LOE_N_BINS 161
+#define LOE_PCM_F32 0            /* float32 samples at int16 scale (what the reference passes)       */
+#define LOE_PCM_S16 1            /* int16 samples as stored in a WAV file: half the PCIe / HBM bytes  */
 #define LOE_MEL_NA_MAX 32        /* mel lane table: max iterations of round A / round B             */
 #define LOE_MEL_NB_MAX 16
 
@@ -66,7 +68,9 @@ int loe_device_count(void);
  * per-utterance maximum as reference and top_db=80, DCT-II ortho 13 ceps, Savitzky-Golay
  * delta / delta-delta of width 9, per-frame normalisation of the static block).
  *
- *   pcm_dev      [total_samples] float32 PCM at int16 scale, utterances back to back
+ *   pcm_dev      [total_samples] PCM, utterances back to back; pcm_format = LOE_PCM_F32 (float32 at
+ *                int16 scale, the dtype the reference feeds librosa, ti_digits.py:133) or LOE_PCM_S16
+ *                (raw int16 as read by scipy.io.wavfile; converted on load, bit-identical results)
  *   pcm_off_dev  [n_utt+1] int64 sample offsets
  *   frm_off_dev  [n_utt+1] int64 frame offsets, frames(u) = 1 + samples(u)/160
  *   max_frames   max_u frames(u)            min_frames  min_u frames(u) (must be >= 9)
@@ -80,7 +84,7 @@ int loe_device_count(void);
  *   feat_dev     [total_frames*39] float32 out, row-major (frame, coefficient): the
  *                transposed (T,39) layout MFCC.batch hands to the HMM code
  * -------------------------------------------------------------------------------------- */
-int loe_mfcc_dev(const float* pcm_dev, const int64_t* pcm_off_dev, const int64_t* frm_off_dev,
+int loe_mfcc_dev(const void* pcm_dev, int pcm_format, const int64_t* pcm_off_dev, const int64_t* frm_off_dev,
                  int n_utt, int64_t total_frames, int max_frames, int min_frames,
                  const int32_t* mel_bin_dev, const float* mel_w_dev, int mel_na, int mel_nb,
                  float* mel_ws_dev, float* utt_max_dev, float* feat_dev, void* stream);

@@ -31,7 +31,7 @@ def test_host_side_argument_checks_need_no_gpu(built_lib):
     import pytest
     lib = _native.load()
     # argument validation happens before any CUDA call
-    st = lib.loe_mfcc_dev(0, 0, 0, 1, 5, 5, 5, 0, 0, 11, 5, 0, 0, 0, 0)
+    st = lib.loe_mfcc_dev(0, 0, 0, 0, 1, 5, 5, 5, 0, 0, 11, 5, 0, 0, 0, 0)
     assert st == _native.LOE_ERR_VALUE
     with pytest.raises(ValueError):
         _native.check(st)

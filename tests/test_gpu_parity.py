@@ -335,6 +335,10 @@ def test_pcm_to_strings_pipeline(eng, golden):
     pinned = eng.torch.from_numpy(flat).pin_memory()
     assert inf.decode_pcm_flat(pinned, off) == got
     assert inf.decode_pcm_flat(flat[:0], off[:1]) == []
+    # raw int16 WAV samples on the wire: bit-identical features and strings
+    assert inf.decode_pcm_flat(flat.astype(np.int16), off, n_chunks=2) == got
+    f16 = MFCC.batch([u.astype(np.int16) for u in utts], 16000)
+    assert all(np.array_equal(a, b) for a, b in zip(f16, feats))
 
 
 def test_large_batch_properties(eng, golden):
