@@ -43,6 +43,9 @@ UNIT = "utt/s"
 LOOP_ORDER = ("1", "2", "3", "4", "5", "6", "7", "8", "9", "O", "S", "Z")   # sorted(os.listdir), hmm.py:431
 PENALTY = -100                                                              # project5_test_ndigits_with_sil.py:62
 FLOPS_PER_FRAME = 2 * 40 * 39 * 58                                          # 2(D+1)D S, S = 58
+# dram__bytes_read.sum + dram__bytes_write.sum per launch at the default workload (10 000 utterances, 3.84 M frames),
+# from the committed `ncu --set full` capture (profiles/r1e_kernels.txt); None = not captured
+NCU_TRAFFIC = {}
 
 
 def golden_params():
@@ -269,8 +272,10 @@ def impl_b200(args):
         return e0.elapsed_time(e1) / args.steps, out
 
     stage_ms = {}
-    stage_ms["mfcc"], _ = timed(lambda: eng.mfcc_device(pcm_dev, pcm_off_dev, frm_off_dev, n, F, max_t, min_t, 16000,
-                                                        out=feat, mel_ws=mel_ws, utt_max=utt_max))
+    stage_ms["mfcc_mel"], _ = timed(lambda: eng.mfcc_device(pcm_dev, pcm_off_dev, frm_off_dev, n, F, max_t, min_t, 16000,
+                                                            out=feat, mel_ws=mel_ws, utt_max=utt_max, phases=1))
+    stage_ms["mfcc_ceps"], _ = timed(lambda: eng.mfcc_device(pcm_dev, pcm_off_dev, frm_off_dev, n, F, max_t, min_t, 16000,
+                                                             out=feat, mel_ws=mel_ws, utt_max=utt_max, phases=2))
     score_buf = torch.empty((F, gp.n_states), dtype=torch.float32, device=dev)
     stage_ms["emission"], scores = timed(lambda: eng.emission(feat, gp, precision, out=score_buf))
     stage_ms["viterbi"], vit = timed(lambda: eng.viterbi(scores, frm_off_dev, n, max_t, F, tp, loop=True, penalty=pen,
@@ -321,20 +326,35 @@ def impl_b200(args):
     except Exception:
         pass
     bf16 = peaks.get("bf16_tflops", 1590.0)
-    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops burst / 2: TF32 dense is half the bf16 rate; TF32 is not in the file)" \
-        if peaks else "fallback 1590/2"
-    em_tflops = F * FLOPS_PER_FRAME / (stage_ms["emission"] * 1e-3) / 1e12
-    roofline = {"kernel": {"fp32": "emission_simt_kernel<float,39>", "fp64": "emission_simt_kernel<double,39>",
-                           "tc": "emission_tc_kernel"}[precision],
-                "bound": "tensor", "achieved": em_tflops, "peak": bf16 / 2, "unit": "TFLOP/s", "frac": em_tflops / (bf16 / 2),
-                "traffic": None, "peak_source": peak_src,
-                "algorithmic": f"{FLOPS_PER_FRAME} flop/frame x {F} frames per launch",
-                "ms_per_launch": stage_ms["emission"]}
     hbm = peaks.get("hbm_gbs", 6650.0)
-    other = {
-        "mfcc": {"bound": "hbm", "achieved_gbs": (4 * int(pcm_off[-1]) + 156 * F) / (stage_ms["mfcc"] * 1e-3) / 1e9, "peak_gbs": hbm},
-        "viterbi": {"bound": "hbm", "achieved_gbs": (4 * 58 * F + F) / (stage_ms["viterbi"] * 1e-3) / 1e9, "peak_gbs": hbm},
+    src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+    tf32_peak = bf16 / 2      # TF32 is not in MEASURED_PEAKS.json: dense TF32 = half the bf16 rate
+    n_samples = int(pcm_off[-1])
+    # algorithmic work per launch and DRAM traffic per launch from the committed ncu capture
+    # (profiles/r1e_kernels.txt: dram__bytes_read.sum + dram__bytes_write.sum at this workload size)
+    kernels = {
+        "mfcc_mel_kernel": {"bound": "hbm", "alg": 4 * n_samples + 160 * F, "ms": stage_ms["mfcc_mel"], "traffic": NCU_TRAFFIC.get("mfcc_mel")},
+        "mfcc_ceps_kernel": {"bound": "hbm", "alg": (160 + 156) * F, "ms": stage_ms["mfcc_ceps"], "traffic": NCU_TRAFFIC.get("mfcc_ceps")},
+        "emission_tc_kernel" if precision == "tc" else "emission_simt_kernel":
+            {"bound": "tensor", "alg": FLOPS_PER_FRAME * F, "ms": stage_ms["emission"], "traffic": NCU_TRAFFIC.get("emission_" + precision)},
+        "viterbi_warp_kernel": {"bound": "hbm", "alg": (4 * 58 + 1) * F, "ms": stage_ms["viterbi"], "traffic": NCU_TRAFFIC.get("viterbi")},
     }
+    all_roof = {}
+    for name, k in kernels.items():
+        if k["bound"] == "hbm":
+            ach, peak, unit = k["alg"] / (k["ms"] * 1e-3) / 1e9, hbm, "GB/s"
+        else:
+            ach, peak, unit = k["alg"] / (k["ms"] * 1e-3) / 1e12, tf32_peak, "TFLOP/s"
+        all_roof[name] = {"kernel": name, "bound": k["bound"], "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+                          "traffic": k["traffic"], "ms_per_launch": k["ms"],
+                          "algorithmic": (f"{k['alg']} bytes per launch" if k["bound"] == "hbm" else
+                                          f"{FLOPS_PER_FRAME} flop/frame x {F} frames per launch (counted once; 3 TF32 MMAs issued)")}
+    dominant = max(kernels, key=lambda kname: kernels[kname]["ms"])
+    roofline = dict(all_roof[dominant])
+    roofline["peak_source"] = src + ("; TF32 peak taken as bf16_tflops burst / 2" if roofline["bound"] == "tensor" else "")
+    if dominant == "mfcc_mel_kernel":
+        roofline["note"] = ("nominally HBM-bound (796 B/frame) but limited by fp32 issue: ~590 warp instructions per frame "
+                            "(radix-5 x 32-point shuffle FFT), see profiles/")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -351,8 +371,8 @@ def impl_b200(args):
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": roofline,
+        "roofline_all": all_roof,
         "stage_ms": stage_ms,
-        "other_kernels": other,
     }
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1

@@ -308,10 +308,10 @@ mfcc_ceps_kernel(const float* __restrict__ mel, const float* __restrict__ utt_ma
 
 }  // namespace loe
 
-extern "C" int loe_mfcc_dev(const void* pcm_dev, int pcm_format, const int64_t* pcm_off_dev, const int64_t* frm_off_dev,
-                            int n_utt, int64_t total_frames, int max_frames, int min_frames,
-                            const int32_t* mel_bin_dev, const float* mel_w_dev, int mel_na, int mel_nb,
-                            float* mel_ws_dev, float* utt_max_dev, float* feat_dev, void* stream) {
+static int mfcc_launch(const void* pcm_dev, int pcm_format, const int64_t* pcm_off_dev, const int64_t* frm_off_dev,
+                       int n_utt, int64_t total_frames, int max_frames, int min_frames,
+                       const int32_t* mel_bin_dev, const float* mel_w_dev, int mel_na, int mel_nb,
+                       float* mel_ws_dev, float* utt_max_dev, float* feat_dev, void* stream, int phases) {
     using namespace loe;
     if (n_utt <= 0 || total_frames <= 0) return LOE_OK;
     if (min_frames < 9) {
@@ -325,19 +325,39 @@ extern "C" int loe_mfcc_dev(const void* pcm_dev, int pcm_format, const int64_t* 
     int st = ensure_tables();
     if (st != LOE_OK) return st;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    LOE_CUDA(cudaMemsetAsync(utt_max_dev, 0, sizeof(float) * (size_t)n_utt, s));
-    static_assert(sizeof(SmemA) <= 48 * 1024, "kernel A must fit the default dynamic shared memory limit");
-    dim3 ga((unsigned)n_utt, (unsigned)((max_frames + kFramesPerBlockA - 1) / kFramesPerBlockA));
-    if (pcm_format == LOE_PCM_F32)
-        mfcc_mel_kernel<float><<<ga, kWarpsA * 32, sizeof(SmemA), s>>>((const float*)pcm_dev, pcm_off_dev, frm_off_dev, mel_bin_dev,
-                                                                      mel_w_dev, mel_na, mel_nb, mel_ws_dev, utt_max_dev);
-    else if (pcm_format == LOE_PCM_S16)
-        mfcc_mel_kernel<short><<<ga, kWarpsA * 32, sizeof(SmemA), s>>>((const short*)pcm_dev, pcm_off_dev, frm_off_dev, mel_bin_dev,
-                                                                      mel_w_dev, mel_na, mel_nb, mel_ws_dev, utt_max_dev);
-    else { set_error("unknown pcm_format %d", pcm_format); return LOE_ERR_VALUE; }
-    LOE_LAUNCH_CHECK("mfcc_mel_kernel");
-    dim3 gb((unsigned)n_utt, (unsigned)((max_frames + kTileB - 1) / kTileB));
-    mfcc_ceps_kernel<<<gb, 256, 0, s>>>(mel_ws_dev, utt_max_dev, frm_off_dev, feat_dev);
-    LOE_LAUNCH_CHECK("mfcc_ceps_kernel");
+    if (phases & 1) {
+        LOE_CUDA(cudaMemsetAsync(utt_max_dev, 0, sizeof(float) * (size_t)n_utt, s));
+        static_assert(sizeof(SmemA) <= 48 * 1024, "kernel A must fit the default dynamic shared memory limit");
+        dim3 ga((unsigned)n_utt, (unsigned)((max_frames + kFramesPerBlockA - 1) / kFramesPerBlockA));
+        if (pcm_format == LOE_PCM_F32)
+            mfcc_mel_kernel<float><<<ga, kWarpsA * 32, sizeof(SmemA), s>>>((const float*)pcm_dev, pcm_off_dev, frm_off_dev, mel_bin_dev,
+                                                                          mel_w_dev, mel_na, mel_nb, mel_ws_dev, utt_max_dev);
+        else if (pcm_format == LOE_PCM_S16)
+            mfcc_mel_kernel<short><<<ga, kWarpsA * 32, sizeof(SmemA), s>>>((const short*)pcm_dev, pcm_off_dev, frm_off_dev, mel_bin_dev,
+                                                                          mel_w_dev, mel_na, mel_nb, mel_ws_dev, utt_max_dev);
+        else { set_error("unknown pcm_format %d", pcm_format); return LOE_ERR_VALUE; }
+        LOE_LAUNCH_CHECK("mfcc_mel_kernel");
+    }
+    if (phases & 2) {
+        dim3 gb((unsigned)n_utt, (unsigned)((max_frames + kTileB - 1) / kTileB));
+        mfcc_ceps_kernel<<<gb, 256, 0, s>>>(mel_ws_dev, utt_max_dev, frm_off_dev, feat_dev);
+        LOE_LAUNCH_CHECK("mfcc_ceps_kernel");
+    }
     return LOE_OK;
+}
+
+extern "C" int loe_mfcc_dev(const void* pcm_dev, int pcm_format, const int64_t* pcm_off_dev, const int64_t* frm_off_dev,
+                            int n_utt, int64_t total_frames, int max_frames, int min_frames,
+                            const int32_t* mel_bin_dev, const float* mel_w_dev, int mel_na, int mel_nb,
+                            float* mel_ws_dev, float* utt_max_dev, float* feat_dev, void* stream) {
+    return mfcc_launch(pcm_dev, pcm_format, pcm_off_dev, frm_off_dev, n_utt, total_frames, max_frames, min_frames, mel_bin_dev,
+                       mel_w_dev, mel_na, mel_nb, mel_ws_dev, utt_max_dev, feat_dev, stream, 3);
+}
+
+extern "C" int loe_mfcc_phase_dev(const void* pcm_dev, int pcm_format, const int64_t* pcm_off_dev, const int64_t* frm_off_dev,
+                                  int n_utt, int64_t total_frames, int max_frames, int min_frames,
+                                  const int32_t* mel_bin_dev, const float* mel_w_dev, int mel_na, int mel_nb,
+                                  float* mel_ws_dev, float* utt_max_dev, float* feat_dev, void* stream, int phases) {
+    return mfcc_launch(pcm_dev, pcm_format, pcm_off_dev, frm_off_dev, n_utt, total_frames, max_frames, min_frames, mel_bin_dev,
+                       mel_w_dev, mel_na, mel_nb, mel_ws_dev, utt_max_dev, feat_dev, stream, phases);
 }

@@ -28,12 +28,52 @@ __all__ = [
     "ModelCollection",
 ]
 
-_OUT_OF_SCOPE = {"Segmentation", "DynamicTimeWarping", "TIDigits", "DataLoader", "plot_confusion_matrix_from_lists",
-                 "plot_line", "CSVReader", "CSVWriter", "SignalSeparation"}
+# name -> module of the reference that defines it (host-side I/O and tooling, not rebuilt here)
+_OUT_OF_SCOPE = {"Segmentation": "segmentation", "DynamicTimeWarping": "dynamic_time_wrapping", "TIDigits": "ti_digits",
+                 "DataLoader": "ti_digits", "plot_confusion_matrix_from_lists": "visualizer", "plot_line": "visualizer",
+                 "CSVReader": "csvnia", "CSVWriter": "csvnia", "SignalSeparation": "signal_separation"}
+
+
+def _configure_multiprocessing() -> None:
+    """The reference's scripts map ``predict`` over ``concurrent.futures.ProcessPoolExecutor()``
+    (scripts/project3_predict_simple.py:23-27, project5_test_*.py:33-41) after computing MFCCs in the
+    parent.  A CUDA context does not survive fork(), so the default start method is switched to
+    "spawn" (workers then create their own engine lazily).  Set LOE_B200_KEEP_START_METHOD=1 to opt out."""
+    import multiprocessing
+    import os
+    if os.environ.get("LOE_B200_KEEP_START_METHOD"):
+        return
+    try:
+        if multiprocessing.get_start_method(allow_none=True) is None:
+            multiprocessing.set_start_method("spawn")
+    except RuntimeError:
+        pass
+
+
+_configure_multiprocessing()
 
 
 def __getattr__(name):
+    """Names outside the accelerated path.  When LOE_REFERENCE_SRC points at the reference's
+    ``src/loe_speech_recognition`` directory, the original host-side module is loaded from there (so
+    the reference's scripts run unmodified with the hot path replaced); otherwise NotImplementedError."""
     if name in _OUT_OF_SCOPE:
+        import importlib.util
+        import os
+        import sys
+        src = os.environ.get("LOE_REFERENCE_SRC")
+        mod_name = _OUT_OF_SCOPE[name]
+        path = os.path.join(src, mod_name + ".py") if src else None
+        if path and os.path.exists(path):
+            full = f"{__name__}.{mod_name}"
+            mod = sys.modules.get(full)
+            if mod is None:
+                spec = importlib.util.spec_from_file_location(full, path)
+                mod = importlib.util.module_from_spec(spec)
+                sys.modules[full] = mod
+                spec.loader.exec_module(mod)
+            return getattr(mod, name)
         raise NotImplementedError(f"loe_speech_recognition.{name} is host-side I/O / tooling outside the accelerated "
-                                  "hot path and is not part of the B200 build (see DESIGN.md, 'Out of scope')")
+                                  "hot path and is not part of the B200 build (see DESIGN.md, 'Out of scope'); set "
+                                  "LOE_REFERENCE_SRC=<reference>/src/loe_speech_recognition to load the original module")
     raise AttributeError(name)

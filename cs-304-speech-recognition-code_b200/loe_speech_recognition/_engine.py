@@ -194,7 +194,7 @@ class Engine:
         return self._mel_cache[key]
 
     def mfcc_device(self, pcm, pcm_off, frm_off, n_utt, total_frames, max_frames, min_frames, sample_rate=16000,
-                    out=None, mel_ws=None, utt_max=None):
+                    out=None, mel_ws=None, utt_max=None, phases=3):
         """PCM (device) -> features [total_frames, 39] (device).  All tensors on this device."""
         torch = self.torch
         bins, w, na, nb = self._mel_tables(sample_rate)
@@ -210,10 +210,10 @@ class Engine:
             fmt = 0
         else:
             raise TypeError(f"PCM must be float32 or int16 on the device (got {pcm.dtype})")
-        _native.check(self.lib.loe_mfcc_dev(pcm.data_ptr(), fmt, pcm_off.data_ptr(), frm_off.data_ptr(), n_utt, total_frames,
-                                            max_frames, min_frames, bins.data_ptr(), w.data_ptr(), na, nb,
-                                            mel_ws.data_ptr(), utt_max.data_ptr(), out.data_ptr(), self._stream()))
-        self.launches += 2
+        _native.check(self.lib.loe_mfcc_phase_dev(pcm.data_ptr(), fmt, pcm_off.data_ptr(), frm_off.data_ptr(), n_utt, total_frames,
+                                                  max_frames, min_frames, bins.data_ptr(), w.data_ptr(), na, nb,
+                                                  mel_ws.data_ptr(), utt_max.data_ptr(), out.data_ptr(), self._stream(), phases))
+        self.launches += (phases & 1) + ((phases >> 1) & 1)
         return out
 
     def upload_pcm(self, signals: Sequence[np.ndarray]):

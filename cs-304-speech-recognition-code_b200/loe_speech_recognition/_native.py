@@ -28,6 +28,8 @@ SIGNATURES = {
     "loe_device_count": (c_int, []),
     "loe_mfcc_dev": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64, c_int, c_int,
                              c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "loe_mfcc_phase_dev": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64, c_int, c_int,
+                                   c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
     "loe_emission_dev": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int,
                                  c_void_p, c_int, c_int, c_void_p]),
     "loe_emission_tc_tiles": (c_int, [c_int]),

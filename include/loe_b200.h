@@ -89,6 +89,13 @@ int loe_mfcc_dev(const void* pcm_dev, int pcm_format, const int64_t* pcm_off_dev
                  const int32_t* mel_bin_dev, const float* mel_w_dev, int mel_na, int mel_nb,
                  float* mel_ws_dev, float* utt_max_dev, float* feat_dev, void* stream);
 
+/* The two kernels of loe_mfcc_dev separately (profiling / timing): phases bit 0 = PCM -> mel energies
+ * + utterance maxima, bit 1 = mel -> features.  loe_mfcc_dev == phases 3. */
+int loe_mfcc_phase_dev(const void* pcm_dev, int pcm_format, const int64_t* pcm_off_dev, const int64_t* frm_off_dev,
+                       int n_utt, int64_t total_frames, int max_frames, int min_frames,
+                       const int32_t* mel_bin_dev, const float* mel_w_dev, int mel_na, int mel_nb,
+                       float* mel_ws_dev, float* utt_max_dev, float* feat_dev, void* stream, int phases);
+
 /* --------------------------------------------------------------------------------------
  * Gaussian emission scoring.  Replaces MultivariateNormal.log_pdf
  * (hidden_markov_model.py:46-48 -> scipy multivariate_normal_frozen.logpdf) for every

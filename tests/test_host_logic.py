@@ -25,6 +25,24 @@ def test_public_names_and_out_of_scope():
     assert isinstance(HiddenMarkovModelInference()._log_transition_probability_between_words, np.float64)
 
 
+def test_spawn_start_method_and_reference_fallback(tmp_path):
+    """Importing the package makes ProcessPoolExecutor() spawn (CUDA does not survive fork), and
+    out-of-scope host modules can be borrowed from a reference checkout."""
+    pkg = os.path.join(ROOT, "cs-304-speech-recognition-code_b200")
+    code = ("import sys; sys.path.insert(0, %r); import multiprocessing, loe_speech_recognition as L; "
+            "print(multiprocessing.get_start_method())" % pkg)
+    assert subprocess.check_output([sys.executable, "-c", code], text=True).strip() == "spawn"
+    env = dict(os.environ, LOE_B200_KEEP_START_METHOD="1")
+    code2 = code.replace("get_start_method()", "get_start_method(allow_none=True)")
+    assert subprocess.check_output([sys.executable, "-c", code2], text=True, env=env).strip() == "None"
+    ref = "/root/reference/src/loe_speech_recognition"
+    if os.path.isdir(ref):
+        code3 = ("import sys; sys.path.insert(0, %r); import loe_speech_recognition as L; w = L.CSVWriter(['a', 'b']); "
+                 "w.add_line(['1', '2']); w.write(%r); print(type(w).__module__)" % (pkg, str(tmp_path / "o.csv")))
+        out = subprocess.check_output([sys.executable, "-c", code3], text=True, env=dict(os.environ, LOE_REFERENCE_SRC=ref))
+        assert out.strip() == "loe_speech_recognition.csvnia" and (tmp_path / "o.csv").exists()
+
+
 def test_transition_matrices_semantics():
     from loe_speech_recognition.transition_probability import LogTransitionProbabilities, TransitionProbabilities
     tp = TransitionProbabilities.from_num_of_states(5)
