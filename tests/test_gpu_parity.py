@@ -433,3 +433,61 @@ def test_kmeans_statistics_large_random(eng):
     # bitwise reproducible
     stats2, _, _ = eng.kmeans_stats(eng._to_dev(x), eng._to_dev(path), eng._to_dev(off), n, F, tp, None, False, S, eng._to_dev(shift))
     assert np.array_equal(stats, stats2.cpu().numpy())
+
+
+def test_long_utterance_fallback_paths(eng, golden):
+    """Utterances too long for the warp kernel's shared-memory back-pointers (CTA kernel, then its
+    global-workspace variant) must give the same bit-exact result."""
+    from oracle import hmm as O
+    inf = _loop_inference(golden)
+    gp, tp = inf._packs()
+    flat = [oracle_flat(golden, w) for w in LOOP_ORDER]
+    tr = O.loop_trellis([f[3] for f in flat])
+    base = np.concatenate([golden[f"loop_feat_{i}"] for i in range(10)])
+    for T in (3000, 12000):                      # 3000: CTA kernel, smem back-pointers; 12000: global workspace
+        x = np.ascontiguousarray(np.tile(base, (T // len(base) + 1, 1))[:T])
+        xd = eng._to_dev(x)
+        sc = eng.emission(xd, gp, "fp32")
+        off = eng._to_dev(np.array([0, T], dtype=np.int64))
+        path, _, _, bs = eng.viterbi(sc, off, 1, T, T, tp, loop=True, penalty=-100.0, penalty_f64=False, want_end_scores=False)
+        es, bi, opath = O.viterbi(sc.cpu().numpy(), tr, penalty=-100)
+        assert bs.cpu().numpy()[0] == es[bi]
+        assert np.array_equal(path.cpu().numpy(), opath)
+    assert not eng.lib.loe_viterbi_bp_fits(12000, 58)
+
+
+def test_config1_isolated_digits_200_utterances(eng):
+    """BASELINE.json configs[0]: 11 word HMMs x 5 states, 200 synthetic 1 s utterances.  Models are
+    trained by the GPU trainer; scores of the batched classifier are checked against the oracle run
+    on the same models, labels must be identical."""
+    from oracle import hmm as O
+    from loe_speech_recognition import HiddenMarkovModelTrainable, MFCC, ModelCollection, TI_DIGITS_LABELS
+    from loe_speech_recognition.synthetic import DIGITS, isolated_corpus, synth_isolated
+    train = isolated_corpus(seed=1, n_per_word=10, words=DIGITS, seconds=1.0)
+    models = {}
+    for w in TI_DIGITS_LABELS:
+        models[w] = HiddenMarkovModelTrainable.from_data(w, MFCC.batch(train[w], 16000), num_of_states=5, max_iterations=5,
+                                                         isMultiProcessingTraining=False, isTqdm=False)
+    mc = ModelCollection()
+    mc._models = [models[w] for w in TI_DIGITS_LABELS]
+    rng = np.random.default_rng(0)
+    truth = [DIGITS[int(i)] for i in rng.integers(0, 11, size=200)]
+    utts = [synth_isolated(rng, w, 1.0) for w in truth]
+    feats = MFCC.batch(utts, 16000)
+    assert all(f.shape == (101, 39) for f in feats)
+    got = mc.predict_batch(feats)
+    assert np.mean([a == b for a, b in zip(got, truth)]) >= 0.95
+    sc = mc.scores_batch(feats)
+    ref = np.zeros_like(sc)
+    for k, w in enumerate(TI_DIGITS_LABELS):
+        m = models[w]
+        packs = [O.gaussian_pack(m._means[s], m._covariances[s]) for s in range(5)]
+        tr = O.word_trellis(m._log_transition_probs.to_dense())
+        ems = [O.emission_scores(x, [p[0] for p in packs], [p[1] for p in packs], [p[2] for p in packs]) for x in feats]
+        ref[:, k] = O.viterbi_batch(ems, tr)[0][:, 0]
+    finite = np.isfinite(ref)
+    assert np.array_equal(finite, np.isfinite(sc))
+    # totals are sums of 101 per-frame scores of either sign (magnitudes up to 1e3): 1e-4 relative + 0.05 absolute
+    assert rel_close(sc[finite], ref[finite], rtol=1e-4, atol=0.05), np.abs(sc[finite] - ref[finite]).max()
+    labels = list(TI_DIGITS_LABELS)
+    assert got == [labels[int(i)] for i in np.argmax(ref, axis=1)]
