@@ -6,7 +6,7 @@
 Workload (config.workload): BASELINE.json configs[1] -- continuous 7-digit string decode over the
 digit-loop grammar with a silence word (12 word models, 58 states, 39-dim features), 10 000
 synthetic 16 kHz utterances per GPU.  One "step" = one pass of the hot path over that batch:
-MFCC -> Gaussian emission scoring -> loop-grammar Viterbi + backtrace -> word labels.
+MFCC -> Gaussian emission scoring -> loop-grammar Viterbi + backtrace + word labels.
 
   value  utterances/s with the PCM already resident in HBM (whole job, all ranks)
   e2e    same through the public API with HOST buffers: H2D of the pinned PCM, the four kernels,
@@ -218,9 +218,8 @@ def impl_b200(args):
     def step_device():
         eng.mfcc_device(pcm_dev, pcm_off_dev, frm_off_dev, n, F, max_t, min_t, 16000, out=feat, mel_ws=mel_ws, utt_max=utt_max)
         scores = eng.emission(feat, gp, precision)
-        path, _, _, best = eng.viterbi(scores, frm_off_dev, n, max_t, F, tp, loop=True, penalty=pen, penalty_f64=False,
-                                       want_end_scores=False)
-        words, count = eng.labels(path, frm_off_dev, n, tp, skip_label=skip, max_words=32)
+        path, _, _, best, words, count = eng.viterbi(scores, frm_off_dev, n, max_t, F, tp, loop=True, penalty=pen, penalty_f64=False,
+                                                     want_end_scores=False, labels=(skip, 32))
         return path, words, count
 
     def barrier():
@@ -278,8 +277,7 @@ def impl_b200(args):
     score_buf = torch.empty((F, gp.n_states), dtype=torch.float32, device=dev)
     stage_ms["emission"], scores = timed(lambda: eng.emission(feat, gp, precision, out=score_buf))
     stage_ms["viterbi"], vit = timed(lambda: eng.viterbi(scores, frm_off_dev, n, max_t, F, tp, loop=True, penalty=pen,
-                                                        want_end_scores=False))
-    stage_ms["labels"], _ = timed(lambda: eng.labels(vit[0], frm_off_dev, n, tp, skip_label=skip, max_words=32))
+                                                        want_end_scores=False, labels=(skip, 32)))
 
     # ---- end to end through the public API with host buffers
     for _ in range(max(1, min(args.warmup, 3))):

@@ -245,9 +245,15 @@ extern "C" int loe_viterbi_dev(const float* scores_dev, int ld, const int64_t* f
                                const uint8_t* flags_dev, int max_pos, const int32_t* utt_tr_dev,
                                int loop, double penalty, int penalty_f64,
                                int8_t* path_dev, float* end_scores_dev, int max_ends,
-                               int32_t* best_dev, float* best_score_dev, uint8_t* bp_ws_dev, void* stream) {
+                               int32_t* best_dev, float* best_score_dev, uint8_t* bp_ws_dev,
+                               const int32_t* word_dev, const int32_t* word_lo_dev, int skip_label,
+                               int8_t* words_dev, int max_words, int32_t* count_dev, void* stream) {
     using namespace loe;
     if (n_utt <= 0) return LOE_OK;
+    if (words_dev && (!word_dev || !word_lo_dev || !count_dev || max_words <= 0)) {
+        set_error("label decoding needs word, word_lo, count and max_words > 0");
+        return LOE_ERR_VALUE;
+    }
     if (max_pos > LOE_MAX_POS) {
         set_error("%d trellis positions: the reference's int8 path/tracer hold at most %d", max_pos, LOE_MAX_POS);
         return LOE_ERR_OVERFLOW;
@@ -275,11 +281,17 @@ extern "C" int loe_viterbi_dev(const float* scores_dev, int ld, const int64_t* f
     a.flags = flags_dev; a.utt_tr = utt_tr_dev; a.loop = loop; a.pen32 = (float)penalty; a.pen64 = penalty; a.pen_f64 = penalty_f64;
     a.path = path_dev; a.end_scores = end_scores_dev; a.max_ends = max_ends; a.best = best_dev; a.best_score = best_score_dev;
     a.bp_ws = bp_ws_dev; a.bp_in_smem = in_smem ? 1 : 0; a.max_frames = max_frames; a.max_pos = max_pos;
+    a.word = word_dev; a.word_lo = word_lo_dev; a.skip_label = skip_label; a.words = words_dev; a.max_words = max_words; a.count = count_dev;
     if (viterbi_warp_launch(a, n_utt, s)) return LOE_OK;      // one warp per utterance (the common case)
     LOE_CUDA(cudaGetLastError());
     const int threads = ((max_pos + 31) / 32) * 32;
     viterbi_kernel<<<(unsigned)n_utt, threads, smem, s>>>(a);
     LOE_LAUNCH_CHECK("viterbi_kernel");
+    if (words_dev) {
+        labels_kernel<<<(unsigned)((n_utt + 127) / 128), 128, 0, s>>>(path_dev, frm_off_dev, n_utt, tr_off_dev, word_dev, word_lo_dev,
+                                                                     utt_tr_dev, skip_label, words_dev, max_words, count_dev);
+        LOE_LAUNCH_CHECK("labels_kernel");
+    }
     return LOE_OK;
 }
 

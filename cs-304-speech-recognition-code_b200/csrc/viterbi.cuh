@@ -12,6 +12,8 @@ struct VitArgs {
     int loop; float pen32; double pen64; int pen_f64;
     int8_t* path; float* end_scores; int max_ends; int32_t* best; float* best_score;
     uint8_t* bp_ws; int bp_in_smem; int max_frames; int max_pos;
+    // optional fused label decoding (model_boundary.py:107-147); words == nullptr disables it
+    const int32_t* word; const int32_t* word_lo; int skip_label; int8_t* words; int max_words; int32_t* count;
 };
 
 // One-warp-per-utterance kernel (viterbi_warp.cu).  Returns false when the utterances are too long

@@ -28,7 +28,7 @@ __device__ __forceinline__ float fkey_inv(int k) { return __int_as_float(k ^ ((k
 
 struct WarpLayout {
     int n_rows;          // back-pointer rows of 32 words
-    int off_cross, off_path, off_ends, off_flags, total;
+    int off_cross, off_path, off_ends, off_flags, off_wlo, off_whi, off_wlab, total;
 };
 
 __host__ __device__ inline WarpLayout warp_layout(int max_frames, int max_pos, int spl) {
@@ -40,6 +40,9 @@ __host__ __device__ inline WarpLayout warp_layout(int max_frames, int max_pos, i
     L.off_path = o;  o += (max_frames + 3) & ~3;
     L.off_ends = o;  o += max_pos * 4;
     L.off_flags = o; o += (max_pos + 3) & ~3;
+    L.off_wlo = o;   o += (max_pos + 3) & ~3;
+    L.off_whi = o;   o += (max_pos + 3) & ~3;
+    L.off_wlab = o;  o += (max_pos + 3) & ~3;
     L.total = (o + 15) & ~15;
     return L;
 }
@@ -252,6 +255,48 @@ viterbi_warp_kernel(VitArgs a, int n_utt) {
     }
     __syncwarp();
     for (int t = lane; t < T; t += 32) a.path[f0 + t] = s_path[t];
+
+    // ---- fused label decoding (model_boundary.py:107-147).  The reference's running "current word
+    // range" is always the range of the word that holds the previous state, so whether a change point
+    // emits a word is a local test:  different word, or same word re-entered first-state-from-last-state.
+    if (a.words) {
+        uint8_t* s_wlo = base + L.off_wlo;
+        uint8_t* s_whi = base + L.off_whi;
+        uint8_t* s_wlab = base + L.off_wlab;
+        for (int p = lane; p < P; p += 32) {
+            const int lo = a.word_lo[p0 + p];
+            int hi = p;
+            while (hi + 1 < P && a.word_lo[p0 + hi + 1] == lo) ++hi;
+            s_wlo[p] = (uint8_t)lo; s_whi[p] = (uint8_t)hi; s_wlab[p] = (uint8_t)a.word[p0 + p];
+        }
+        __syncwarp();
+        int8_t* out = a.words + (int64_t)u * a.max_words;
+        int n = 0;
+        bool bad = false;
+        for (int tb = 0; tb < T; tb += 32) {
+            const int t = tb + lane;
+            bool emit = false; int lab = 0;
+            if (t < T) {
+                const int cur = s_path[t];
+                if (cur < 0 || cur >= P) bad = true;
+                else {
+                    lab = s_wlab[cur];
+                    if (t == 0) emit = true;
+                    else {
+                        const int prev = s_path[t - 1];
+                        if (prev >= 0 && prev < P && cur != prev)
+                            emit = (s_wlo[cur] != s_wlo[prev]) || (prev == s_whi[prev] && cur == s_wlo[cur]);
+                    }
+                }
+            }
+            emit = emit && lab != a.skip_label;
+            const unsigned m = __ballot_sync(FULL, emit);
+            if (emit) { const int k = n + __popc(m & ((1u << lane) - 1)); if (k < a.max_words) out[k] = (int8_t)lab; }
+            n += __popc(m);
+        }
+        bad = __any_sync(FULL, bad);
+        if (lane == 0) a.count[u] = bad ? -1 : n;
+    }
 }
 
 template <int SPL, bool LOOP, bool PENF64>

@@ -262,8 +262,16 @@ class Engine:
 
     # ------------------------------------------------------------------ Viterbi
     def viterbi(self, scores, batch_frm_off, n_utt, max_frames, total_frames, tp: TrellisPack, utt_tr=None,
-                loop=False, penalty=0.0, penalty_f64=False, want_end_scores=True):
+                loop=False, penalty=0.0, penalty_f64=False, want_end_scores=True, labels=None):
+        """``labels=(skip_label, max_words)`` additionally decodes the word sequence of every path in the
+        same launch; the return value then has two more entries (words int8 [n, max_words], count int32 [n])."""
         torch = self.torch
+        words = count = None
+        skip_label, max_words = -1, 0
+        if labels is not None:
+            skip_label, max_words = labels
+            words = self.empty((n_utt, max_words), torch.int8)
+            count = self.empty((n_utt,), torch.int32)
         path = self.empty((total_frames,), torch.int8)
         best = self.empty((n_utt,), torch.int32)
         best_score = self.empty((n_utt,), torch.float32)
@@ -276,8 +284,11 @@ class Engine:
             tp.tr_off.data_ptr(), tp.col.data_ptr(), tp.band.data_ptr(), tp.flags.data_ptr(), tp.max_pos,
             self._p(utt_tr), 1 if loop else 0, float(penalty), 1 if penalty_f64 else 0,
             path.data_ptr(), self._p(end_scores), tp.max_ends, best.data_ptr(), best_score.data_ptr(),
-            self._p(bp_ws), self._stream()))
+            self._p(bp_ws), tp.word.data_ptr(), tp.word_lo.data_ptr(), skip_label, self._p(words), max_words, self._p(count),
+            self._stream()))
         self.launches += 1
+        if labels is not None:
+            return path, end_scores, best, best_score, words, count
         return path, end_scores, best, best_score
 
     def labels(self, path, frm_off, n_utt, tp: TrellisPack, utt_tr=None, skip_label=-1, max_words=32):

@@ -38,7 +38,8 @@ SIGNATURES = {
     "loe_viterbi_dev": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
                                 c_int, c_double, c_int,
-                                c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "loe_labels_dev": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                c_void_p, c_int, c_void_p, c_void_p]),
     "loe_align_dev": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -416,15 +416,22 @@ class HiddenMarkovModelInference(_PackCache):
         off = batch.frm_off_host
         return best_score.cpu().numpy(), [path_h[off[i]:off[i + 1]] for i in range(batch.n_utt)]
 
-    def _decode_device(self, batch, precision: Optional[str] = None):
-        """features (device) -> (best_score [n], path [F]) on the device: two launches."""
+    def _decode_device(self, batch, precision: Optional[str] = None, max_words: Optional[int] = None):
+        """features (device) -> (best_score [n], path [F]) on the device: two launches.  With ``max_words``
+        the Viterbi launch also decodes the word sequence: (best_score, path, words, count)."""
         eng = _engine()
         gp, tp = self._packs()
         pen, f64 = _penalty_args(self._log_transition_probability_between_words)   # read per call: scripts poke it
         scores = eng.emission(batch.feat, gp, precision)
-        path, _, _, best_score = eng.viterbi(scores, batch.frm_off, batch.n_utt, batch.max_frames, batch.total_frames, tp,
-                                             loop=True, penalty=pen, penalty_f64=f64, want_end_scores=False)
-        return best_score, path
+        labels = None
+        if max_words is not None:
+            names = self._model_boundaries._labels
+            labels = (names.index("S") if "S" in names else -1, max_words)
+        out = eng.viterbi(scores, batch.frm_off, batch.n_utt, batch.max_frames, batch.total_frames, tp,
+                          loop=True, penalty=pen, penalty_f64=f64, want_end_scores=False, labels=labels)
+        if labels is not None:
+            return out[3], out[0], out[4], out[5]
+        return out[3], out[0]
 
     def _labels_device(self, path, batch, max_words: int = 32):
         """Launch the labels kernel (model_boundary.py:107-147): (words int8 [n, max_words], count int32 [n])
@@ -453,24 +460,22 @@ class HiddenMarkovModelInference(_PackCache):
                 out[i] = "".join(self._model_boundaries.get_labels(path_h[frm_off_host[i]:frm_off_host[i + 1]]))
         return out
 
-    def _strings_device(self, path, batch, max_words: int = 32) -> List[str]:
-        words, count = self._labels_device(path, batch, max_words)
+    def _strings_device(self, batch, precision: Optional[str] = None, max_words: int = 32) -> List[str]:
+        _, path, words, count = self._decode_device(batch, precision, max_words)
         return self._strings_host(words.cpu().numpy(), count.cpu().numpy(), lambda: path.cpu().numpy(), batch.frm_off_host)
 
     def predict_batch(self, signals: Sequence[NDArray[np.float32]], precision: Optional[str] = None) -> List[str]:
         """Digit strings of many (T, 39) feature matrices in one pass (added entry point)."""
         eng = _engine()
         batch = eng.upload_features(signals, self._multivariate_normals[0].dim_of_features)
-        _, path = self._decode_device(batch, precision)
-        return self._strings_device(path, batch)
+        return self._strings_device(batch, precision)
 
     def decode_pcm_batch(self, signals: Sequence[NDArray], sample_rate: int = 16000, precision: Optional[str] = None) -> List[str]:
         """Raw PCM -> digit strings, everything between the H2D copy of the samples and the D2H
         copy of the word ids on the device (MFCC -> emission -> Viterbi -> labels; added entry point)."""
         eng = _engine()
         batch = eng.mfcc(signals, sample_rate)
-        _, path = self._decode_device(batch, precision)
-        return self._strings_device(path, batch)
+        return self._strings_device(batch, precision)
 
 
     def decode_pcm_flat(self, pcm_flat, sample_offsets: NDArray[np.int64], sample_rate: int = 16000,
@@ -522,8 +527,7 @@ class HiddenMarkovModelInference(_PackCache):
                 t.record_stream(comp)
             feat = eng.mfcc_device(pcm, pcm_off, frm_off_dev, b - a, int(frm_off[-1]), int(fr.max()), int(fr.min()), sample_rate)
             batch = Batch(feat, frm_off_dev, frm_off, b - a, int(fr.max()))
-            _, path = self._decode_device(batch, precision)
-            words, count = self._labels_device(path, batch, max_words)
+            _, path, words, count = self._decode_device(batch, precision, max_words)
             if n_chunks > 1:
                 words_h[a:b].copy_(words, non_blocking=True)
                 count_h[a:b].copy_(count, non_blocking=True)

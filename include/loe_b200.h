@@ -146,6 +146,8 @@ int loe_emission_tc_dev(const float* feat_dev, int64_t n_frames, int dim, const 
  *   bp_ws_dev  workspace of total_frames*LOE_MAX_POS bytes, only used when the back-pointers
  *              of the longest utterance do not fit in shared memory (may be NULL otherwise;
  *              loe_viterbi_bp_fits tells)
+ *   word_dev / word_lo_dev / skip_label / words_dev / max_words / count_dev: optional fused
+ *              label decoding with the semantics of loe_labels_dev (words_dev == NULL: off)
  * -------------------------------------------------------------------------------------- */
 int loe_viterbi_bp_fits(int max_frames, int max_pos);
 int loe_viterbi_dev(const float* scores_dev, int ld, const int64_t* frm_off_dev, int n_utt, int max_frames,
@@ -153,7 +155,9 @@ int loe_viterbi_dev(const float* scores_dev, int ld, const int64_t* frm_off_dev,
                     const uint8_t* flags_dev, int max_pos, const int32_t* utt_tr_dev,
                     int loop, double penalty, int penalty_f64,
                     int8_t* path_dev, float* end_scores_dev, int max_ends,
-                    int32_t* best_dev, float* best_score_dev, uint8_t* bp_ws_dev, void* stream);
+                    int32_t* best_dev, float* best_score_dev, uint8_t* bp_ws_dev,
+                    const int32_t* word_dev, const int32_t* word_lo_dev, int skip_label,
+                    int8_t* words_dev, int max_words, int32_t* count_dev, void* stream);
 
 /* --------------------------------------------------------------------------------------
  * State path -> word sequence.  Replaces ModelBoundary.get_labels / append_to_labels

@@ -35,7 +35,7 @@ def test_host_side_argument_checks_need_no_gpu(built_lib):
     assert st == _native.LOE_ERR_VALUE
     with pytest.raises(ValueError):
         _native.check(st)
-    st = lib.loe_viterbi_dev(0, 58, 0, 1, 10, 0, 0, 0, 0, 200, 0, 1, -100.0, 0, 0, 0, 12, 0, 0, 0, 0)
+    st = lib.loe_viterbi_dev(0, 58, 0, 1, 10, 0, 0, 0, 0, 200, 0, 1, -100.0, 0, 0, 0, 12, 0, 0, 0, 0, 0, -1, 0, 0, 0, 0)
     assert st == _native.LOE_ERR_OVERFLOW
     with pytest.raises(OverflowError):
         _native.check(st)
