@@ -91,12 +91,14 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
 //   round B, iterations [na, na+nb):  lanes 4q..4q+3 share filter 32 + q   (the 8 widest filters),
 //                                     combined with two xor shuffles
 // entry (it, lane) = weight mel_w[it*32+lane] applied to power bin mel_bin[it*32+lane] (0-weight padding).
-template <typename SampleT>
+template <typename SampleT, int NA, int NB>
 __global__ void __launch_bounds__(kWarpsA * 32)
 mfcc_mel_kernel(const SampleT* __restrict__ pcm, const int64_t* __restrict__ pcm_off,
                 const int64_t* __restrict__ frm_off, const int32_t* __restrict__ mel_bin,
-                const float* __restrict__ mel_w, int na, int nb,
+                const float* __restrict__ mel_w, int na_rt, int nb_rt,
                 float* __restrict__ mel_out, float* __restrict__ utt_max) {
+    const int na = NA > 0 ? NA : na_rt;                  // NA, NB > 0: compile-time trip counts (loops unroll)
+    const int nb = NA > 0 ? NB : nb_rt;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmemA& sm = *reinterpret_cast<SmemA*>(smem_raw);
     const int u = blockIdx.x;
@@ -217,8 +219,15 @@ mfcc_mel_kernel(const SampleT* __restrict__ pcm, const int64_t* __restrict__ pcm
         __syncwarp();
         // ---- mel filterbank (lane-balanced table)
         float accA = 0.f, accB = 0.f;
-        for (int it = 0; it < na; ++it) accA = fmaf(sm.mel_w[it * 32 + lane], pw[sm.mel_bin[it * 32 + lane]], accA);
-        for (int it = na; it < na + nb; ++it) accB = fmaf(sm.mel_w[it * 32 + lane], pw[sm.mel_bin[it * 32 + lane]], accB);
+        if (NA > 0) {
+#pragma unroll
+            for (int it = 0; it < NA; ++it) accA = fmaf(sm.mel_w[it * 32 + lane], pw[sm.mel_bin[it * 32 + lane]], accA);
+#pragma unroll
+            for (int it = NA; it < NA + NB; ++it) accB = fmaf(sm.mel_w[it * 32 + lane], pw[sm.mel_bin[it * 32 + lane]], accB);
+        } else {
+            for (int it = 0; it < na; ++it) accA = fmaf(sm.mel_w[it * 32 + lane], pw[sm.mel_bin[it * 32 + lane]], accA);
+            for (int it = na; it < na + nb; ++it) accB = fmaf(sm.mel_w[it * 32 + lane], pw[sm.mel_bin[it * 32 + lane]], accB);
+        }
         accB += __shfl_xor_sync(FULL, accB, 1);
         accB += __shfl_xor_sync(FULL, accB, 2);
         float* mo = mel_out + (f0 + t) * kMels;
@@ -329,13 +338,14 @@ static int mfcc_launch(const void* pcm_dev, int pcm_format, const int64_t* pcm_o
         LOE_CUDA(cudaMemsetAsync(utt_max_dev, 0, sizeof(float) * (size_t)n_utt, s));
         static_assert(sizeof(SmemA) <= 48 * 1024, "kernel A must fit the default dynamic shared memory limit");
         dim3 ga((unsigned)n_utt, (unsigned)((max_frames + kFramesPerBlockA - 1) / kFramesPerBlockA));
-        if (pcm_format == LOE_PCM_F32)
-            mfcc_mel_kernel<float><<<ga, kWarpsA * 32, sizeof(SmemA), s>>>((const float*)pcm_dev, pcm_off_dev, frm_off_dev, mel_bin_dev,
-                                                                          mel_w_dev, mel_na, mel_nb, mel_ws_dev, utt_max_dev);
-        else if (pcm_format == LOE_PCM_S16)
-            mfcc_mel_kernel<short><<<ga, kWarpsA * 32, sizeof(SmemA), s>>>((const short*)pcm_dev, pcm_off_dev, frm_off_dev, mel_bin_dev,
-                                                                          mel_w_dev, mel_na, mel_nb, mel_ws_dev, utt_max_dev);
+        const bool k16 = (mel_na == 11 && mel_nb == 5);      // the 16 kHz table of every reference call site
+#define LOE_MEL_LAUNCH(T, A, B)                                                                                          \
+        mfcc_mel_kernel<T, A, B><<<ga, kWarpsA * 32, sizeof(SmemA), s>>>((const T*)pcm_dev, pcm_off_dev, frm_off_dev, mel_bin_dev, \
+                                                                        mel_w_dev, mel_na, mel_nb, mel_ws_dev, utt_max_dev)
+        if (pcm_format == LOE_PCM_F32) { if (k16) LOE_MEL_LAUNCH(float, 11, 5); else LOE_MEL_LAUNCH(float, 0, 0); }
+        else if (pcm_format == LOE_PCM_S16) { if (k16) LOE_MEL_LAUNCH(short, 11, 5); else LOE_MEL_LAUNCH(short, 0, 0); }
         else { set_error("unknown pcm_format %d", pcm_format); return LOE_ERR_VALUE; }
+#undef LOE_MEL_LAUNCH
         LOE_LAUNCH_CHECK("mfcc_mel_kernel");
     }
     if (phases & 2) {
