@@ -15,6 +15,7 @@ from .ti_digits import TI_DIGITS_LABELS, TI_DIGITS_LABEL_TYPE
 from .hidden_markov_model import (Signal, HiddenMarkovModel, HiddenMarkovModelTrainable, HiddenMarkovModelInference,
                                   HiddenMarkovModelTrainContinuous)
 from .model_collection import ModelCollection
+from .signal_separation import SignalSeparation
 
 __all__ = [
     "MFCC",
@@ -26,12 +27,13 @@ __all__ = [
     "HiddenMarkovModelTrainContinuous",
     "Signal",
     "ModelCollection",
+    "SignalSeparation",
 ]
 
 # name -> module of the reference that defines it (host-side I/O and tooling, not rebuilt here)
 _OUT_OF_SCOPE = {"Segmentation": "segmentation", "DynamicTimeWarping": "dynamic_time_wrapping", "TIDigits": "ti_digits",
                  "DataLoader": "ti_digits", "plot_confusion_matrix_from_lists": "visualizer", "plot_line": "visualizer",
-                 "CSVReader": "csvnia", "CSVWriter": "csvnia", "SignalSeparation": "signal_separation"}
+                 "CSVReader": "csvnia", "CSVWriter": "csvnia"}
 
 
 def _configure_multiprocessing() -> None:

@@ -302,6 +302,26 @@ class Engine:
         self.launches += 1
         return words, count
 
+    # ------------------------------------------------------------------ silence stripper
+    def silence(self, signals: Sequence[np.ndarray], frame_size: int, high: float, low: float, max_silence_frames: int):
+        """Host arrays (energies, noise mask, seg [n,4], max [n], energy offsets) for a batch of signals."""
+        torch = self.torch
+        pcm, pcm_off, _, _, _ = self.upload_pcm(signals)
+        lens = np.array([s.shape[0] for s in signals], dtype=np.int64)
+        efr = lens // frame_size + 1
+        eoff = np.concatenate(([0], np.cumsum(efr))).astype(np.int64)
+        n, tot = len(signals), int(eoff[-1])
+        energy = self.empty((tot,), torch.float32)
+        noise = self.empty((tot,), torch.uint8)
+        seg = self.empty((n, 4), torch.int32)
+        mx = self.empty((n,), torch.float32)
+        fmt = 1 if pcm.dtype == torch.int16 else 0
+        _native.check(self.lib.loe_silence_dev(pcm.data_ptr(), fmt, pcm_off.data_ptr(), n, frame_size, float(high), float(low),
+                                               int(max_silence_frames), self._to_dev(eoff).data_ptr(), energy.data_ptr(),
+                                               noise.data_ptr(), seg.data_ptr(), mx.data_ptr(), self._stream()))
+        self.launches += 1
+        return energy.cpu().numpy(), noise.cpu().numpy().astype(bool), seg.cpu().numpy(), mx.cpu().numpy(), eoff
+
     # ------------------------------------------------------------------ K-means statistics
     def kmeans_stats(self, feat, path, frm_off, n_utt, total_frames, tp: TrellisPack, utt_tr, remux: bool,
                      n_glob: int, shift):

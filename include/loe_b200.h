@@ -175,6 +175,24 @@ int loe_labels_dev(const int8_t* path_dev, const int64_t* frm_off_dev, int n_utt
                    int8_t* words_dev, int max_words, int32_t* count_dev, void* stream);
 
 /* --------------------------------------------------------------------------------------
+ * Energy-hysteresis silence stripper (the step before MFCC in the reference's silence-model training,
+ * scripts/project5_train_no_empty.py:18-31).  Replaces SignalSeparation._remove_empty / detect_speech
+ * (signal_separation.py:103-164) bit for bit (NumPy's float32 pairwise summation order for the frame
+ * energies, float64 thresholds = high/low * max|x|, the hysteresis state machine and its quirks).
+ *   efrm_off_dev [n_utt+1] int64: offsets into energy/noise; utterance u has samples/frame_size full
+ *                frames plus ONE trailing partial frame (possibly empty)
+ *   energy_dev [total] float32 out: mean |x| per frame (NaN for an empty trailing frame)
+ *   noise_dev  [total] uint8 out: 1 = frame the reference appends to its noise list
+ *   seg_dev    [n_utt*4] int32 out: {done, start, end, n_frames}: the stripped signal is frames
+ *                [start, end); done = 0 where the reference raises FailToProcess (speech never ended)
+ *   max_dev    [n_utt] float32 out: max |x|
+ * -------------------------------------------------------------------------------------- */
+int loe_silence_dev(const void* pcm_dev, int pcm_format, const int64_t* pcm_off_dev, int n_utt,
+                    int frame_size, double high, double low, int max_silence_frames,
+                    const int64_t* efrm_off_dev, float* energy_dev, uint8_t* noise_dev, int32_t* seg_dev,
+                    float* max_dev, void* stream);
+
+/* --------------------------------------------------------------------------------------
  * Segmental K-means sufficient statistics.  Replaces Signal.order_by_state,
  * SortedSignals.order_by_state / .transition_probabilities (signal.py:23-47, 68-91), the
  * accumulation half of HiddenMarkovModelTrainable._update_middleware_parameters
