@@ -171,6 +171,31 @@ class HiddenMarkovModel(_PackCache):
     def _model_folder_name_parser(folder_path: str) -> str:
         return str(folder_path.split("/")[-1])
 
+    # -- flat cache format (added) -----------------------------------------
+    # The reference's pickles embed scipy's private frozen-distribution classes, which couples a
+    # saved model to the scipy version that wrote it.  ``model.npz`` beside them holds only plain
+    # arrays (means, covariances, dense log-transitions); loading rebuilds the Gaussians with scipy.
+    def save_flat(self, parent_folder_path: str = "./cache") -> str:
+        folder = os.path.join(parent_folder_path, f"{self.label}")
+        os.makedirs(folder, exist_ok=True)
+        path = os.path.join(folder, "model.npz")
+        np.savez(path, label=np.array(self.label),
+                 means=np.stack([np.asarray(mn._core.mean, dtype=np.float64) for mn in self._multivariate_normals]),
+                 covariances=np.stack([np.asarray(mn._core.cov_object.covariance, dtype=np.float64) for mn in self._multivariate_normals]),
+                 log_transitions=self._log_transition_probs.to_dense())
+        return path
+
+    @classmethod
+    def from_flat(cls, model_folder_path: str) -> Self:
+        path = os.path.join(model_folder_path, "model.npz")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        z = np.load(path, allow_pickle=False)
+        model = cls(str(z["label"]))
+        model._multivariate_normals = [MultivariateNormal.from_means_covariances(m, c) for m, c in zip(z["means"], z["covariances"])]
+        model._log_transition_probs = LogTransitionProbabilities.from_dense(z["log_transitions"].astype(np.float32))
+        return model
+
 
 # ----------------------------------------------------------------------------------------
 # M-step from device statistics (shared by the isolated and the embedded trainer)

@@ -78,6 +78,22 @@ def test_reference_pickles_load_and_round_trip(tmp_path):
     assert pickle.loads(blob)._model_boundaries._labels == ["1", "S", "Z"]
 
 
+def test_flat_model_format_round_trip(tmp_path, golden):
+    """model.npz (plain arrays, no scipy pickles): same emission tables and transitions after reload."""
+    from loe_speech_recognition import HiddenMarkovModel
+    from loe_speech_recognition._engine import host_gauss_arrays
+    m = trained_word_model(golden, "4")
+    m.save_flat(str(tmp_path))
+    m2 = HiddenMarkovModel.from_flat(str(tmp_path / "4"))
+    assert m2.label == "4" and m2.num_of_states == 5
+    for a, b in zip(host_gauss_arrays(m._multivariate_normals), host_gauss_arrays(m2._multivariate_normals)):
+        assert np.array_equal(a, b)
+    assert np.array_equal(m2._log_transition_probs.to_dense(), m._log_transition_probs.to_dense())
+    assert isinstance(m2._log_transition_probs[(0, 0)], np.float32)
+    with pytest.raises(FileNotFoundError):
+        HiddenMarkovModel.from_flat(str(tmp_path / "nope"))
+
+
 def test_trellis_builder_matches_oracle(golden):
     from loe_speech_recognition import _trellis
     from loe_speech_recognition._native import POS_END, POS_INIT, POS_START
