@@ -491,3 +491,41 @@ def test_config1_isolated_digits_200_utterances(eng):
     assert rel_close(sc[finite], ref[finite], rtol=1e-4, atol=0.05), np.abs(sc[finite] - ref[finite]).max()
     labels = list(TI_DIGITS_LABELS)
     assert got == [labels[int(i)] for i in np.argmax(ref, axis=1)]
+
+
+@pytest.mark.parametrize("penalty", [-100, np.log(0.005)])
+def test_wide_trellis_four_positions_per_lane(eng, golden, penalty):
+    """65..128 positions run with 4 positions per lane (SPL = 4): a 25-word loop grammar (121 states),
+    and 20 independent words side by side (100 states), against the oracle on the kernel's own scores."""
+    from oracle import hmm as O
+    from loe_speech_recognition import HiddenMarkovModelInference, ModelCollection
+    from loe_speech_recognition.hidden_markov_model import _penalty_args
+    words = list(LOOP_ORDER) + list(LOOP_ORDER) + ["1"]
+    models = [trained_word_model(golden, w) for w in words]
+    inf = HiddenMarkovModelInference.from_models(models)
+    inf._log_transition_probability_between_words = penalty
+    gp, tp = inf._packs()
+    assert tp.max_pos == 121
+    tr = O.loop_trellis([golden[f"train_logA_{w}"] for w in words])
+    pen, f64 = _penalty_args(penalty)
+    feats = [golden[f"loop_feat_{i}"] for i in range(10)]
+    batch = eng.upload_features(feats, 39)
+    sc = eng.emission(batch.feat, gp, "fp32")
+    path, _, _, bs = eng.viterbi(sc, batch.frm_off, batch.n_utt, batch.max_frames, batch.total_frames, tp, loop=True,
+                                 penalty=pen, penalty_f64=f64, want_end_scores=False)
+    sc_h, path_h, off = sc.cpu().numpy(), path.cpu().numpy(), batch.frm_off_host
+    for i in range(10):
+        es, bi, opath = O.viterbi(sc_h[off[i]:off[i + 1]], tr, penalty=penalty)
+        assert bs.cpu().numpy()[i] == es[bi] and np.array_equal(path_h[off[i]:off[i + 1]], opath), i
+    if penalty == -100:
+        mc = ModelCollection()
+        mc._models = [trained_word_model(golden, w) for w in (list(LOOP_ORDER[:10]) * 2)]
+        got = mc.scores_batch(feats, "fp32")
+        gp2, tp2 = mc._packs()
+        assert tp2.max_pos == 100
+        sc2 = eng.emission(batch.feat, gp2, "fp32").cpu().numpy()
+        for k, m in enumerate(mc._models):
+            trw = O.word_trellis(m._log_transition_probs.to_dense())
+            for i in (0, 5):
+                es, _, _ = O.viterbi(sc2[off[i]:off[i + 1], 5 * k:5 * k + 5], trw)
+                assert got[i, k] == es[0] or (np.isinf(es[0]) and np.isinf(got[i, k]))
