@@ -64,7 +64,8 @@ def make_corpus(seed: int, n_utts: int, pool: int):
 
 # ------------------------------------------------------------------------------------------------
 def clocks_sampler_start(gpu_index: int):
-    path = tempfile.mktemp(suffix=".csv")
+    fd, path = tempfile.mkstemp(suffix=".csv")
+    os.close(fd)
     q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
     try:

@@ -78,8 +78,10 @@ constexpr int kMelItMax = LOE_MEL_NA_MAX + LOE_MEL_NB_MAX;
 struct __align__(16) SmemA {
     float mel_w[kMelItMax * 32];
     int mel_bin[kMelItMax * 32];
-    float2 z[kWarpsA][kHalf];           // per-warp complex spectrum of the packed sequence
-    float pw[kWarpsA][kBins + 3];       // per-warp power spectrum
+    float zre[kWarpsA][kHalf];          // per-warp complex spectrum of the packed sequence (split planes:
+    float zim[kWarpsA][kHalf];          // the stride-5 transposing store is then bank-conflict free)
+    float pw[kWarpsA][kBins + 3 + LOE_MEL_NA_MAX + 4 * LOE_MEL_NB_MAX];   // per-warp power spectrum (+ slack: zero-weight
+                                        // table entries may point past the last bin)
 };
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
@@ -147,8 +149,11 @@ mfcc_mel_kernel(const SampleT* __restrict__ pcm, const int64_t* __restrict__ pcm
 
     const float C1 = 0.30901699437494745f, C2 = -0.80901699437494745f;   // cos(2pi/5), cos(4pi/5)
     const float S1 = 0.95105651629515353f, S2 = 0.58778525229247314f;    // sin(2pi/5), sin(4pi/5)
-    float2* zw = sm.z[warp];
+    float* zre = sm.zre[warp];
+    float* zim = sm.zim[warp];
     float* pw = sm.pw[warp];
+    // filters own CONSECUTIVE bins: round A lane l reads bins binA + it, round B bins binB + 4*it
+    const int binA = sm.mel_bin[lane], binB = sm.mel_bin[na * 32 + lane];
 
     for (int t = t_begin + warp; t < t_end; t += kWarpsA) {
         // ---- load + window: z[n] = x[2n] + i x[2n+1], n = 32*n1 + lane
@@ -201,32 +206,33 @@ mfcc_mel_kernel(const SampleT* __restrict__ pcm, const int64_t* __restrict__ pcm
             }
         }
 #pragma unroll
-        for (int k1 = 0; k1 < 5; ++k1) zw[k1 + 5 * brev] = y[k1];
+        for (int k1 = 0; k1 < 5; ++k1) { zre[k1 + 5 * brev] = y[k1].x; zim[k1 + 5 * brev] = y[k1].y; }
         __syncwarp();
         // ---- real-input post-pass + power spectrum: bins k = lane + 32*i, i < 5 (k = 0..159), then k = 160
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
             const int k = lane + 32 * i;
-            const float2 A = zw[k];
-            const float2 Bc = zw[k == 0 ? 0 : kHalf - k];
+            const int kb = (k == 0) ? 0 : kHalf - k;
+            const float2 A = make_float2(zre[k], zim[k]);
+            const float2 Bc = make_float2(zre[kb], zim[kb]);
             const float2 E = make_float2(0.5f * (A.x + Bc.x), 0.5f * (A.y - Bc.y));
             const float2 O = make_float2(0.5f * (A.y + Bc.y), -0.5f * (A.x - Bc.x));
             const float xr = E.x + O.x * wp[i].x - O.y * wp[i].y;
             const float xi = E.y + O.x * wp[i].y + O.y * wp[i].x;
             pw[k] = xr * xr + xi * xi;
         }
-        if (lane == 0) { const float2 Z0 = zw[0]; const float xn = Z0.x - Z0.y; pw[kHalf] = xn * xn; }   // Nyquist bin
+        if (lane == 0) { const float xn = zre[0] - zim[0]; pw[kHalf] = xn * xn; }   // Nyquist bin
         __syncwarp();
         // ---- mel filterbank (lane-balanced table)
         float accA = 0.f, accB = 0.f;
         if (NA > 0) {
 #pragma unroll
-            for (int it = 0; it < NA; ++it) accA = fmaf(sm.mel_w[it * 32 + lane], pw[sm.mel_bin[it * 32 + lane]], accA);
+            for (int it = 0; it < NA; ++it) accA = fmaf(sm.mel_w[it * 32 + lane], pw[binA + it], accA);
 #pragma unroll
-            for (int it = NA; it < NA + NB; ++it) accB = fmaf(sm.mel_w[it * 32 + lane], pw[sm.mel_bin[it * 32 + lane]], accB);
+            for (int it = 0; it < NB; ++it) accB = fmaf(sm.mel_w[(NA + it) * 32 + lane], pw[binB + 4 * it], accB);
         } else {
-            for (int it = 0; it < na; ++it) accA = fmaf(sm.mel_w[it * 32 + lane], pw[sm.mel_bin[it * 32 + lane]], accA);
-            for (int it = na; it < na + nb; ++it) accB = fmaf(sm.mel_w[it * 32 + lane], pw[sm.mel_bin[it * 32 + lane]], accB);
+            for (int it = 0; it < na; ++it) accA = fmaf(sm.mel_w[it * 32 + lane], pw[binA + it], accA);
+            for (int it = 0; it < nb; ++it) accB = fmaf(sm.mel_w[(na + it) * 32 + lane], pw[binB + 4 * it], accB);
         }
         accB += __shfl_xor_sync(FULL, accB, 1);
         accB += __shfl_xor_sync(FULL, accB, 2);

@@ -458,15 +458,6 @@ class HiddenMarkovModelInference(_PackCache):
             return out[3], out[0], out[4], out[5]
         return out[3], out[0]
 
-    def _labels_device(self, path, batch, max_words: int = 32):
-        """Launch the labels kernel (model_boundary.py:107-147): (words int8 [n, max_words], count int32 [n])
-        on the device -- only this small id table crosses PCIe."""
-        eng = _engine()
-        _, tp = self._packs()
-        labels = self._model_boundaries._labels
-        skip = labels.index("S") if "S" in labels else -1
-        return eng.labels(path, batch.frm_off, batch.n_utt, tp, skip_label=skip, max_words=max_words)
-
     def _strings_host(self, words_h, count_h, path_getter, frm_off_host) -> List[str]:
         """Word-id table -> strings.  Utterances whose count overflowed the table or whose path held a
         negative state (T == 1) go through the host routine, which decides (and raises like the reference)."""

@@ -67,12 +67,22 @@ def mel_lane_tables(sample_rate: float):
         raise NotImplementedError(f"mel filters too wide for the kernel tables at sample_rate={sample_rate}")
     bins = np.zeros((na + nb, 32), dtype=np.int32)
     w = np.zeros((na + nb, 32), dtype=np.float32)
+    # every lane walks CONSECUTIVE bins (round A: first + it; round B: first + sub + 4*it), so the kernel
+    # only needs the first bin of each lane; padding entries keep the pattern with weight 0
     for m in range(32):
-        for j, k in enumerate(nz[m]):
-            bins[j, m], w[j, m] = k, dense[m, k]
+        first = int(nz[m][0]) if len(nz[m]) else 0
+        assert len(nz[m]) == 0 or np.array_equal(nz[m], np.arange(first, first + len(nz[m])))
+        for j in range(na):
+            bins[j, m] = first + j
+            if j < len(nz[m]):
+                w[j, m] = dense[m, first + j]
     for q, m in enumerate(range(32, N_MELS)):
-        for j, k in enumerate(nz[m]):
-            bins[na + j // 4, 4 * q + j % 4], w[na + j // 4, 4 * q + j % 4] = k, dense[m, k]
+        first = int(nz[m][0]) if len(nz[m]) else 0
+        assert len(nz[m]) == 0 or np.array_equal(nz[m], np.arange(first, first + len(nz[m])))
+        for j in range(4 * nb):
+            bins[na + j // 4, 4 * q + j % 4] = first + j
+            if j < len(nz[m]):
+                w[na + j // 4, 4 * q + j % 4] = dense[m, first + j]
     return np.ascontiguousarray(bins.reshape(-1)), np.ascontiguousarray(w.reshape(-1)), int(na), int(nb)
 
 

@@ -78,7 +78,9 @@ int loe_device_count(void);
  *                lane-balanced table.  Entry (it, lane) adds mel_w * power[mel_bin] to a partial sum:
  *                iterations [0, na): lane l accumulates filter l (filters 0..31);
  *                iterations [na, na+nb): lanes 4q..4q+3 share filter 32+q (non-zero j of that filter
- *                goes to lane 4q + j%4, iteration na + j/4).  Unused entries have weight 0.
+ *                goes to lane 4q + j%4, iteration na + j/4).  Unused entries have weight 0.  A lane's
+ *                bins must be consecutive (round A: bin(it) = bin(0) + it; round B: bin(it) = bin(0) + 4 it):
+ *                the kernel reads only mel_bin of each lane's first entry.
  *   mel_ws_dev   [total_frames*40] float32 workspace (mel energies)
  *   utt_max_dev  [n_utt] float32 workspace (per-utterance mel maximum)
  *   feat_dev     [total_frames*39] float32 out, row-major (frame, coefficient): the
