@@ -15,8 +15,9 @@
 // = 75 KB resident in shared memory for the whole kernel, loaded once) and walks the frame
 // tiles g, g+G, ... (M = 128 frames).  The 10 CTAs of a column g walk the same frames at the
 // same pace, so the feature tile is fetched from HBM once and re-read from L2.
-//   warps 0-7  producers: coalesced load of the raw [128 x 39] tile (software-prefetched one
-//              tile ahead), hi/lo split, store in the canonical K-major no-swizzle UMMA layout
+//   warps 0-7  producers: the raw [128 x 39] feature tile (19 968 contiguous bytes) arrives by
+//              cp.async.bulk (TMA engine, mbarrier complete_tx), two tiles in flight; the warps
+//              split it hi/lo and store it in the canonical K-major no-swizzle UMMA layout
 //              (8 x 16 B core matrices; LBO = K-chunk stride, SBO = 128 B), fence.proxy.async,
 //              arrive on a_full[stage]
 //   warp  12   one thread issues 15 tcgen05.mma.kind::tf32 (M128 N240 K8) per tile and
@@ -55,9 +56,9 @@ struct __align__(128) Smem {
     uint8_t b_lo[kBBytes];
     uint8_t a_hi[2][kABytes];
     uint8_t a_lo[2][kABytes];
-    float raw[kTileM * kDim + 4];
+    float raw[2][kTileM * kDim];       // raw feature tiles, filled by cp.async.bulk (TMA engine), 2 in flight
     float cst[8];
-    uint64_t a_full[2], a_empty[2], tmem_full[2], tmem_empty[2];
+    uint64_t raw_full[2], a_full[2], a_empty[2], tmem_full[2], tmem_empty[2];
     uint32_t tmem_base;
 };
 
@@ -79,6 +80,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "bra LAB_WAIT;\n"
         "DONE:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// one thread: arm the barrier with the byte count, then let the TMA engine copy a contiguous chunk
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -131,7 +138,7 @@ __device__ __forceinline__ float tf32_round(float x) {
 
 __global__ void __launch_bounds__(kThreads, 1)
 emission_tc_kernel(const float* __restrict__ feat, int64_t n_frames, const float* __restrict__ b_packed,
-                   const float* __restrict__ cst_pad, int n_states, float* __restrict__ out, int ld_out) {
+                   const float* __restrict__ cst_pad, int n_states, float* __restrict__ out, int ld_out, int use_bulk) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -142,6 +149,7 @@ emission_tc_kernel(const float* __restrict__ feat, int64_t n_frames, const float
     // ---- one-time setup: barriers, TMEM, resident B tile
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
+            mbar_init(&sm.raw_full[i], 1);
             mbar_init(&sm.a_full[i], kProducerThreads);
             mbar_init(&sm.a_empty[i], 1);
             mbar_init(&sm.tmem_full[i], 1);
@@ -167,38 +175,34 @@ emission_tc_kernel(const float* __restrict__ feat, int64_t n_frames, const float
 
     if (warp < kProducerThreads / 32) {
         // =========================== producers ===========================
-        constexpr int kTileElems = kTileM * kDim;                       // 4992
-        constexpr int kPre = (kTileElems + kProducerThreads - 1) / kProducerThreads;   // 20
-        float pre[kPre];                                   // raw tile, flat element tid + 256*i
-        auto prefetch = [&](int m) {
-            const int64_t f0 = (int64_t)m * kTileM;
-            const int rows = (int)min((int64_t)kTileM, n_frames - f0);
-            const float* __restrict__ src = feat + f0 * kDim + tid;
-            if (rows == kTileM) {                          // full tile: no per-element bounds
-#pragma unroll
-                for (int i = 0; i < kPre - 1; ++i) pre[i] = __ldg(src + i * kProducerThreads);
-                pre[kPre - 1] = (tid + (kPre - 1) * kProducerThreads < kTileElems) ? __ldg(src + (kPre - 1) * kProducerThreads) : 0.f;
-            } else {
-                const int total = rows * kDim;
-#pragma unroll
-                for (int i = 0; i < kPre; ++i) pre[i] = (tid + i * kProducerThreads < total) ? __ldg(src + i * kProducerThreads) : 0.f;
-            }
+        constexpr int kTileElems = kTileM * kDim;                       // 4992 floats = 19968 B, a multiple of 16
+        constexpr uint32_t kTileBytes = kTileElems * sizeof(float);
+        const int n_it = (g < n_mtiles) ? (n_mtiles - g + G - 1) / G : 0;
+        // bulk copies need a 16-byte aligned source (use_bulk) and a whole tile
+        auto tile_full = [&](int it) { return use_bulk && (int64_t)(g + it * G + 1) * kTileM <= n_frames; };
+        auto issue = [&](int it) {                       // thread 0 only: full tiles are contiguous and 16-byte aligned
+            bulk_load(sm.raw[it & 1], feat + (int64_t)(g + it * G) * kTileElems, kTileBytes, &sm.raw_full[it & 1]);
         };
-        if (g < n_mtiles) prefetch(g);
+        if (tid == 0) {
+            if (n_it > 0 && tile_full(0)) issue(0);
+            if (n_it > 1 && tile_full(1)) issue(1);
+        }
         const int row_id = tid & (kTileM - 1);
         const int kc0 = (tid >> 7) * (kKChunks / 2);       // this thread's half of the K chunks
-        int it = 0;
-        for (int m = g; m < n_mtiles; m += G, ++it) {
+        for (int it = 0; it < n_it; ++it) {
             const int s = it & 1;
             const uint32_t k = (uint32_t)(it >> 1);
-            // raw tile -> shared (flat, conflict free)
-#pragma unroll
-            for (int i = 0; i < kPre; ++i)
-                if (i < kPre - 1 || tid + i * kProducerThreads < kTileElems) sm.raw[tid + i * kProducerThreads] = pre[i];
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (m + G < n_mtiles) prefetch(m + G);         // next tile's loads fly during the transform
+            if (tile_full(it)) {
+                mbar_wait(&sm.raw_full[s], k & 1);         // TMA bytes have landed
+            } else {
+                // the batch's last, partial tile: plain loads, rows beyond the end read as zero
+                const int64_t f0 = (int64_t)(g + it * G) * kTileM;
+                const int total = (int)(n_frames - f0) * kDim;
+                for (int e = tid; e < kTileElems; e += kProducerThreads) sm.raw[s][e] = (e < total) ? __ldg(feat + f0 * kDim + e) : 0.f;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
             mbar_wait(&sm.a_empty[s], (k & 1) ^ 1);        // MMA finished reading this stage
-            const float* row = sm.raw + row_id * kDim;     // stride 39 words: conflict free
+            const float* row = sm.raw[s] + row_id * kDim;  // stride 39 words: conflict free
             uint8_t* ah = sm.a_hi[s] + row_id * 16;
             uint8_t* al = sm.a_lo[s] + row_id * 16;
 #pragma unroll
@@ -217,7 +221,8 @@ emission_tc_kernel(const float* __restrict__ feat, int64_t n_frames, const float
             }
             fence_proxy_async();
             mbar_arrive(&sm.a_full[s]);
-            asm volatile("bar.sync 1, 256;" ::: "memory"); // everyone done with sm.raw before it is overwritten
+            asm volatile("bar.sync 1, 256;" ::: "memory"); // everyone done with raw[s]: it may be refilled
+            if (tid == 0 && it + 2 < n_it && tile_full(it + 2)) issue(it + 2);
         }
     } else if (warp == (kProducerThreads + kEpilogueThreads) / 32) {
         // =========================== MMA issuer ===========================
@@ -315,7 +320,8 @@ extern "C" int loe_emission_tc_dev(const float* feat_dev, int64_t n_frames, int 
     if (G < 1) G = 1;
     if (G > n_mtiles) G = n_mtiles;
     dim3 grid((unsigned)n_tiles, (unsigned)G);
-    emission_tc_kernel<<<grid, kThreads, sizeof(Smem), s>>>(feat_dev, n_frames, b_packed_dev, cst_pad_dev, n_states, out_dev, ld_out);
+    const int use_bulk = (reinterpret_cast<uintptr_t>(feat_dev) & 15) == 0 ? 1 : 0;
+    emission_tc_kernel<<<grid, kThreads, sizeof(Smem), s>>>(feat_dev, n_frames, b_packed_dev, cst_pad_dev, n_states, out_dev, ld_out, use_bulk);
     LOE_LAUNCH_CHECK("emission_tc_kernel");
     return LOE_OK;
 }

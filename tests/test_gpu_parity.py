@@ -126,6 +126,13 @@ def test_emission_tc_many_tiles_and_ragged_sizes(eng, golden):
             ref = eng.emission(xd, gp, "fp64").cpu().numpy()
             got = eng.emission(xd, gp, "tc").cpu().numpy()
             assert emission_close(got, ref, lps), (n_states, n_frames, np.abs(got - ref).max())
+    # a feature buffer that is only 4-byte aligned takes the non-TMA loads; same values
+    gp = eng.pack_gaussians(normals)
+    x = eng._to_dev(base[:1000])
+    shifted = eng.torch.empty(1000 * 39 + 1, dtype=eng.torch.float32, device=eng.device)[1:].view(1000, 39)
+    shifted.copy_(x)
+    assert shifted.data_ptr() % 16 != 0
+    assert eng.torch.equal(eng.emission(shifted, gp, "tc"), eng.emission(x, gp, "tc"))
 
 
 # ------------------------------------------------------------------ a3 word Viterbi
