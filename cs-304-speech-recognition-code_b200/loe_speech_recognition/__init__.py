@@ -16,6 +16,7 @@ from .hidden_markov_model import (Signal, HiddenMarkovModel, HiddenMarkovModelTr
                                   HiddenMarkovModelTrainContinuous)
 from .model_collection import ModelCollection
 from .signal_separation import SignalSeparation
+from .dynamic_time_wrapping import DynamicTimeWarping
 
 __all__ = [
     "MFCC",
@@ -28,10 +29,11 @@ __all__ = [
     "Signal",
     "ModelCollection",
     "SignalSeparation",
+    "DynamicTimeWarping",
 ]
 
 # name -> module of the reference that defines it (host-side I/O and tooling, not rebuilt here)
-_OUT_OF_SCOPE = {"Segmentation": "segmentation", "DynamicTimeWarping": "dynamic_time_wrapping", "TIDigits": "ti_digits",
+_OUT_OF_SCOPE = {"Segmentation": "segmentation", "TIDigits": "ti_digits",
                  "DataLoader": "ti_digits", "plot_confusion_matrix_from_lists": "visualizer", "plot_line": "visualizer",
                  "CSVReader": "csvnia", "CSVWriter": "csvnia"}
 

@@ -316,11 +316,50 @@ class Engine:
         seg = self.empty((n, 4), torch.int32)
         mx = self.empty((n,), torch.float32)
         fmt = 1 if pcm.dtype == torch.int16 else 0
+        eoff_dev = self._to_dev(eoff)                 # must outlive the launch call
         _native.check(self.lib.loe_silence_dev(pcm.data_ptr(), fmt, pcm_off.data_ptr(), n, frame_size, float(high), float(low),
-                                               int(max_silence_frames), self._to_dev(eoff).data_ptr(), energy.data_ptr(),
+                                               int(max_silence_frames), eoff_dev.data_ptr(), energy.data_ptr(),
                                                noise.data_ptr(), seg.data_ptr(), mx.data_ptr(), self._stream()))
         self.launches += 1
         return energy.cpu().numpy(), noise.cpu().numpy().astype(bool), seg.cpu().numpy(), mx.cpu().numpy(), eoff
+
+    # ------------------------------------------------------------------ template DTW
+    def dtw(self, seq_feats: Sequence[np.ndarray], sample_feats: Sequence[np.ndarray], pruning: bool, pruning_factor: float,
+            want_matrices: bool = False):
+        """(best_idx int32 [n], best_dist float64 [n], dist float64 [n, W], cost, path) for samples vs templates;
+        cost / path (float64 / int8, sample 0 only) are returned when ``want_matrices``."""
+        torch = self.torch
+        lens = np.array([f.shape[0] for f in seq_feats], dtype=np.int32)
+        starts = np.concatenate(([0], np.cumsum(lens)[:-1])).astype(np.int32)
+        H, W = int(lens.sum()), len(lens)
+        D = int(seq_feats[0].shape[1])
+        row_start = np.zeros(H + 1, dtype=np.int32)
+        row_start[1:] = np.repeat(starts, lens)
+        boundary = np.zeros(H + 1, dtype=np.int32)
+        boundary[starts[1:]] = 1
+        seq = self._to_dev(np.concatenate([np.asarray(f, dtype=np.float32) for f in seq_feats]))
+        sl = np.array([f.shape[0] for f in sample_feats], dtype=np.int64)
+        soff = np.concatenate(([0], np.cumsum(sl))).astype(np.int64)
+        samp = self._to_dev(np.concatenate([np.asarray(f, dtype=np.float32) for f in sample_feats]))
+        n = len(sample_feats)
+        dist = self.empty((n, W), torch.float64)
+        bi = self.empty((n,), torch.int32)
+        bd = self.empty((n,), torch.float64)
+        cost = path = None
+        if want_matrices:
+            L0 = int(sl[0])
+            cost = self.empty((H + 1, L0 + 1), torch.float64)
+            path = self.empty((H + 1, L0 + 1), torch.int8)
+        # keep every table alive until the launch is enqueued (a temporary would be freed, and its block reused, first)
+        t_rs, t_b, t_st, t_ln, t_so = (self._to_dev(row_start), self._to_dev(boundary), self._to_dev(starts), self._to_dev(lens),
+                                       self._to_dev(soff))
+        _native.check(self.lib.loe_dtw_dev(seq.data_ptr(), H, D, t_rs.data_ptr(), t_b.data_ptr(),
+                                           t_st.data_ptr(), t_ln.data_ptr(), W, samp.data_ptr(),
+                                           t_so.data_ptr(), n, 1 if pruning else 0, float(pruning_factor),
+                                           dist.data_ptr(), bi.data_ptr(), bd.data_ptr(), self._p(cost), self._p(path), self._stream()))
+        self.launches += 1
+        return (bi.cpu().numpy(), bd.cpu().numpy(), dist.cpu().numpy(),
+                None if cost is None else cost.cpu().numpy(), None if path is None else path.cpu().numpy())
 
     # ------------------------------------------------------------------ K-means statistics
     def kmeans_stats(self, feat, path, frm_off, n_utt, total_frames, tp: TrellisPack, utt_tr, remux: bool,

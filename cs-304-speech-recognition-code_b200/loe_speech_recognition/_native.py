@@ -44,6 +44,8 @@ SIGNATURES = {
                                c_void_p, c_int, c_void_p, c_void_p]),
     "loe_silence_dev": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_double, c_double, c_int,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "loe_dtw_dev": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int,
+                            c_int, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "loe_align_dev": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "loe_kmeans_ws_doubles": (c_int64, [c_int64, c_int, c_int]),

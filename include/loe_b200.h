@@ -195,6 +195,24 @@ int loe_silence_dev(const void* pcm_dev, int pcm_format, const int64_t* pcm_off_
                     float* max_dev, void* stream);
 
 /* --------------------------------------------------------------------------------------
+ * Time-synchronous template DTW.  Replaces DynamicTimeWarping.search (dynamic_time_wrapping.py:66-116)
+ * for a batch of samples against one concatenated template set, bit for bit (float32 local distance in
+ * NumPy's summation order, float64 accumulated cost, beam pruning, and the reference's row-sharing /
+ * wrap-around / read-one-row-early quirks -- see csrc/dtw.cu).
+ *   seq_dev [n_rows*dim] template features back to back; word w owns frames [starts[w], starts[w]+lens[w])
+ *   row_start_dev [n_rows+1]: for cost row i >= 1 the start of the word that holds frame i-1;
+ *   row_is_boundary_dev [n_rows+1]: 1 where i == starts[w] for a word w > 0
+ *   samp_dev [total_sample_frames*dim], samp_off_dev [n_samples+1] int64
+ *   dist_dev [n_samples*n_words] float64 out; best_idx_dev / best_dist_dev [n_samples] out (first minimum)
+ *   cost_out_dev / path_out_dev: optional (n_rows+1) x (L+1) matrices of sample 0 (may be NULL)
+ * -------------------------------------------------------------------------------------- */
+int loe_dtw_dev(const float* seq_dev, int n_rows, int dim, const int32_t* row_start_dev,
+                const int32_t* row_is_boundary_dev, const int32_t* starts_dev, const int32_t* lens_dev,
+                int n_words, const float* samp_dev, const int64_t* samp_off_dev, int n_samples,
+                int pruning, double pruning_factor, double* dist_dev, int32_t* best_idx_dev,
+                double* best_dist_dev, double* cost_out_dev, int8_t* path_out_dev, void* stream);
+
+/* --------------------------------------------------------------------------------------
  * Segmental K-means sufficient statistics.  Replaces Signal.order_by_state,
  * SortedSignals.order_by_state / .transition_probabilities (signal.py:23-47, 68-91), the
  * accumulation half of HiddenMarkovModelTrainable._update_middleware_parameters
