@@ -44,8 +44,8 @@ LOOP_ORDER = ("1", "2", "3", "4", "5", "6", "7", "8", "9", "O", "S", "Z")   # so
 PENALTY = -100                                                              # project5_test_ndigits_with_sil.py:62
 FLOPS_PER_FRAME = 2 * 40 * 39 * 58                                          # 2(D+1)D S, S = 58
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at the default workload (10 000 utterances, 3.84 M frames),
-# from the committed `ncu --set full` capture (profiles/r1e_kernels.txt); None = not captured
-NCU_TRAFFIC = {"mfcc_mel": 3098607000, "mfcc_ceps": 1250796000, "emission_tc": 2056174000, "viterbi": 901821000}
+# from the committed `ncu --set full` capture (profiles/r1f_kernels.txt); None = not captured
+NCU_TRAFFIC = {"mfcc_mel": 3098969000, "mfcc_ceps": 1249852000, "emission_tc": 2368057000, "viterbi": 902000000}
 
 
 def golden_params():
@@ -330,7 +330,7 @@ def impl_b200(args):
     tf32_peak = bf16 / 2      # TF32 is not in MEASURED_PEAKS.json: dense TF32 = half the bf16 rate
     n_samples = int(pcm_off[-1])
     # algorithmic work per launch and DRAM traffic per launch from the committed ncu capture
-    # (profiles/r1e_kernels.txt: dram__bytes_read.sum + dram__bytes_write.sum at this workload size)
+    # (profiles/r1f_kernels.txt: dram__bytes_read.sum + dram__bytes_write.sum at this workload size)
     kernels = {
         "mfcc_mel_kernel": {"bound": "hbm", "alg": 4 * n_samples + 160 * F, "ms": stage_ms["mfcc_mel"], "traffic": NCU_TRAFFIC.get("mfcc_mel")},
         "mfcc_ceps_kernel": {"bound": "hbm", "alg": (160 + 156) * F, "ms": stage_ms["mfcc_ceps"], "traffic": NCU_TRAFFIC.get("mfcc_ceps")},
