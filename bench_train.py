@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--utts-per-word", type=int, default=9091)
     ap.add_argument("--pool", type=int, default=64)
     ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--mode", default="both", choices=["per-word", "batch", "both"])
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -49,7 +50,7 @@ def main():
     total_frames = 0
     t_iter, t_dev = [], []
     means_sum = 0.0
-    for w in DIGITS:
+    for w in (DIGITS if args.mode != "batch" else ()):
         b = eng.mfcc(corpus[w])
         first = b.feat[: int(b.frm_off_host[1])].cpu().numpy()
         # tile the pool on the device to this rank's shard
@@ -77,6 +78,31 @@ def main():
             if it > 0:
                 t_iter.append(t2 - t0); t_dev.append(t1 - t0)
         means_sum += float(np.abs(m._means).sum())
+    batch_line = None
+    if args.mode in ("batch", "both"):
+        # all 11 words in one device pass per iteration (HiddenMarkovModelTrainable.from_data_batch)
+        feats_by_word = {}
+        for w in DIGITS:
+            b = eng.mfcc(corpus[w])
+            flat = b.feat.cpu().numpy()
+            pool = [flat[b.frm_off_host[i]:b.frm_off_host[i + 1]] for i in range(len(corpus[w]))]
+            reps = (args.utts_per_word + args.pool - 1) // args.pool
+            feats_by_word[w] = (pool * reps)[:args.utts_per_word]          # from_data_batch shards by rank itself
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        models = HiddenMarkovModelTrainable.from_data_batch(feats_by_word, num_of_states=5, max_iterations=args.iters)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t1 = time.perf_counter()
+        models = HiddenMarkovModelTrainable.from_data_batch(feats_by_word, num_of_states=5, max_iterations=1)
+        torch.cuda.synchronize()
+        d1 = time.perf_counter() - t1
+        per_iter = (dt - d1) / max(1, args.iters - 1)       # upload + setup cancel out
+        chk = float(sum(np.abs(m._means).sum() for m in models.values()))
+        batch_line = {"ms_per_iteration_all_words": per_iter * 1e3, "ms_setup_and_first_iteration": d1 * 1e3,
+                      "utterances_per_s_per_iteration": args.utts_per_word * len(DIGITS) / per_iter, "means_checksum": chk}
+    if args.mode == "batch":
+        t_iter, t_dev = [0.0], [0.0]
     if world > 1:
         t = torch.tensor([np.mean(t_iter), np.mean(t_dev), means_sum], dtype=torch.float64, device=eng.device)
         mx = t.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
@@ -94,7 +120,8 @@ def main():
             "utterances_per_s_per_iteration": args.utts_per_word / it_s,
             "frames_per_s": total_frames / len(DIGITS) / it_s,
             "models_identical_across_ranks": identical, "means_checksum": means_sum,
-            "allreduce_payload_bytes": 8 * (5 * 820 + 25), "data": "synthetic (pool of %d per word, tiled)" % args.pool}))
+            "allreduce_payload_bytes": 8 * (5 * 820 + 25), "batched_trainer": batch_line,
+            "data": "synthetic (pool of %d per word, tiled)" % args.pool}))
     if world > 1:
         dist.destroy_process_group()
 

@@ -165,6 +165,28 @@ class Engine:
             gp.b_packed, gp.cst_pad = self._to_dev(b), self._to_dev(c)
         return gp
 
+    def pack_tc_words(self, words):
+        """Tensor-core images of several word models in ONE upload: ``words`` = [(means [S,D], U [S,D,D], cst [S])];
+        every word starts on a 6-state tile boundary so that a launch can address it by pointer offset.
+        Returns (b_packed, cst_pad, first tile of each word)."""
+        imgs, csts, first, t = [], [], [], 0
+        for means, us, cst in words:
+            b, c = pack_tc_image(means, us, cst)
+            imgs.append(b); csts.append(c); first.append(t)
+            t += len(c) // 6
+        return self._to_dev(np.concatenate(imgs)), self._to_dev(np.concatenate(csts)), first
+
+    def emission_tc_into(self, feat, b_packed, cst_pad, first_tile: int, n_states: int, out, col0: int):
+        """Tensor-core emission of one word (tiles from ``first_tile``) into columns [col0, col0+n_states) of ``out``."""
+        n_frames = int(feat.shape[0])
+        if n_frames == 0:
+            return
+        ld = int(out.shape[1])
+        _native.check(self.lib.loe_emission_tc_dev(feat.data_ptr(), n_frames, int(feat.shape[1]),
+                                                   b_packed.data_ptr() + first_tile * 19200 * 4, cst_pad.data_ptr() + first_tile * 6 * 4,
+                                                   n_states, out.data_ptr() + col0 * 4, ld, self._stream()))
+        self.launches += 1
+
     def pack_trellises(self, trellises: List[HostTrellis]) -> TrellisPack:
         off, col, band, flags, word, word_lo, max_pos, max_ends = stack(trellises)
         if max_pos > _native.LOE_MAX_POS:

@@ -263,6 +263,109 @@ class HiddenMarkovModelTrainable(HiddenMarkovModel):
         model._update_inference_weights()
         return model
 
+    @classmethod
+    def from_data_batch(cls, labeled_mfccs: Dict[str, List[NDArray[np.float32]]], num_of_states=5,
+                        max_iterations: int = 100) -> Dict[str, Self]:
+        """Train several word models at once (added entry point).  The result equals calling
+        :meth:`from_data` once per label (each word keeps its own convergence test and stops on its own),
+        but every iteration is ONE device pass over all words: per-word tensor-core emission launches into
+        one score matrix, one Viterbi launch with a trellis per word, one statistics pass for all states
+        and -- under torch.distributed -- one all-reduce; the Gaussians' whitening matrices are refreshed
+        with a batched float64 eigendecomposition instead of one scipy object per state, and the scipy
+        objects of the persistent format are built once at the end."""
+        from . import _dist
+        from ._engine import Batch
+
+        eng = _engine()
+        torch = eng.torch
+        labels = list(labeled_mfccs)
+        n_st = {l: int(num_of_states[l] if isinstance(num_of_states, dict) else num_of_states) for l in labels}
+        models = {}
+        for l in labels:
+            m = cls(l, isTqdm=False)
+            m._means, m._covariances, m._transition_probs = m._init_parameters(labeled_mfccs[l][0], n_st[l])
+            models[l] = m
+        D = int(labeled_mfccs[labels[0]][0].shape[1])
+        start = {}
+        G = 0
+        for l in labels:
+            start[l] = G
+            G += n_st[l]
+        # this rank's utterances, word by word (the frames of a word are contiguous on the device)
+        shards = {l: _dist.shard(list(labeled_mfccs[l])) for l in labels}
+        feats = [x for l in labels for x in shards[l]]
+        utt_word = np.array([i for i, l in enumerate(labels) for _ in shards[l]], dtype=np.int32)
+        batch = eng.upload_features(feats, D) if feats else None
+        utt_tr = eng._to_dev(utt_word) if feats else None
+        frame_range = {}
+        if feats:
+            cnt = np.cumsum([0] + [len(shards[l]) for l in labels])
+            for i, l in enumerate(labels):
+                frame_range[l] = (int(batch.frm_off_host[cnt[i]]), int(batch.frm_off_host[cnt[i + 1]]))
+            scores = eng.empty((batch.total_frames, G), torch.float32)
+        stride = 1 + D + D * (D + 1) // 2
+        active = set(labels)
+        whiten = {}
+
+        def refresh(which):
+            """(U, cst) of the listed words from their covariances: scipy's _PSD in batched form."""
+            cov = np.concatenate([models[l]._covariances.astype(np.float64) for l in which])
+            if not np.all(np.isfinite(cov)):
+                raise ValueError("array must not contain infs or NaNs")
+            lam, vec = np.linalg.eigh(cov)
+            eps = 1e6 * np.finfo(np.float64).eps * np.max(np.abs(lam), axis=1)
+            if np.any(lam.min(axis=1) < -eps):
+                raise ValueError("The input matrix must be symmetric positive semidefinite.")
+            if np.any(lam <= eps[:, None]):
+                raise np.linalg.LinAlgError("When `allow_singular is False`, the input matrix must be symmetric positive definite.")
+            U = vec * np.sqrt(1.0 / lam)[:, None, :]
+            cst = -0.5 * (D * np.log(2 * np.pi) + np.sum(np.log(lam), axis=1))
+            o = 0
+            for l in which:
+                whiten[l] = (U[o:o + n_st[l]], cst[o:o + n_st[l]])
+                o += n_st[l]
+
+        refresh(labels)
+        for it in range(max_iterations):
+            if not active:
+                break
+            if feats:
+                b_packed, cst_pad, first = eng.pack_tc_words([(models[l]._means.astype(np.float64), *whiten[l]) for l in labels])
+                with np.errstate(divide="ignore", invalid="ignore"):       # log 0 = -inf is the reference's encoding
+                    trellises = [_trellis.build([np.log(models[l]._transition_probs.to_dense())], [start[l]], [i], "word")
+                                 for i, l in enumerate(labels)]
+                tp = eng.pack_trellises(trellises)
+                for i, l in enumerate(labels):
+                    if l in active:
+                        a, b = frame_range[l]
+                        eng.emission_tc_into(batch.feat[a:b], b_packed, cst_pad, first[i], n_st[l], scores[a:b], start[l])
+                path, _, _, _ = eng.viterbi(scores, batch.frm_off, batch.n_utt, batch.max_frames, batch.total_frames, tp,
+                                            utt_tr=utt_tr, want_end_scores=False)
+                shift = eng._to_dev(np.concatenate([models[l]._means for l in labels]).astype(np.float32))
+                stats, counts, _ = eng.kmeans_stats(batch.feat, path, batch.frm_off, batch.n_utt, batch.total_frames, tp,
+                                                    utt_tr, False, G, shift)
+            else:
+                stats = torch.zeros((G, stride), dtype=torch.float64, device=eng.device)
+                counts = torch.zeros((G, G), dtype=torch.int32, device=eng.device)
+            stats, counts = _dist.allreduce_stats(stats, counts)
+            stats_h, counts_h = stats.cpu().numpy(), counts.cpu().numpy().astype(np.int64)
+            updated = []
+            for l in labels:
+                if l not in active:
+                    continue
+                a, n = start[l], n_st[l]
+                try:
+                    models[l]._update_from_statistics(stats_h[a:a + n], counts_h[a:a + n, a:a + n],
+                                                      shift=models[l]._means.astype(np.float64))
+                    updated.append(l)
+                except cls.HMMTrainConverge:
+                    active.discard(l)
+            if updated:
+                refresh(updated)
+        for l in labels:
+            models[l]._update_inference_weights()
+        return models
+
     def _update_inference_weights(self) -> None:
         self._log_transition_probs = LogTransitionProbabilities.from_transition_probability(self._transition_probs)
         self._multivariate_normals = self.get_multivariate_normals(self._means, self._covariances)

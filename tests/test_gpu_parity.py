@@ -536,3 +536,26 @@ def test_wide_trellis_four_positions_per_lane(eng, golden, penalty):
             for i in (0, 5):
                 es, _, _ = O.viterbi(sc2[off[i]:off[i + 1], 5 * k:5 * k + 5], trw)
                 assert got[i, k] == es[0] or (np.isinf(es[0]) and np.isinf(got[i, k]))
+
+
+def test_batched_training_equals_per_word_training(eng, golden):
+    """from_data_batch (all words in one device pass per iteration, batched eigendecomposition) must give
+    the models from_data gives word by word."""
+    from loe_speech_recognition import HiddenMarkovModelTrainable
+    labeled = {w: [golden[f"train_feat_{w}_{i}"] for i in range(64) if f"train_feat_{w}_{i}" in golden.files] for w in WORDS}
+    got = HiddenMarkovModelTrainable.from_data_batch(labeled, num_of_states=dict(N_STATES), max_iterations=4)
+    for w in WORDS:
+        ref = HiddenMarkovModelTrainable.from_data(w, labeled[w], num_of_states=N_STATES[w], max_iterations=4,
+                                                   isMultiProcessingTraining=False, isTqdm=False)
+        assert rel_close(got[w]._means, ref._means, rtol=1e-5, atol=1e-6), w
+        assert rel_close(got[w]._covariances, ref._covariances, rtol=1e-4, atol=1e-6), w
+        a, b = got[w]._log_transition_probs.to_dense(), ref._log_transition_probs.to_dense()
+        assert np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(a[~np.isnan(a)], b[~np.isnan(b)]), w
+        assert rel_close(got[w]._means, golden[f"train_means_{w}"], rtol=1e-4, atol=1e-5), w
+        assert got[w].num_of_states == N_STATES[w] and len(got[w]._multivariate_normals) == N_STATES[w]
+    # identical frames: the best path jumps 0 -> 2 at once, state 1 is never visited -> HMMTrainMeanFail (both entry points)
+    flat = np.tile(golden["train_feat_1_0"][:1], (12, 1))
+    with pytest.raises(HiddenMarkovModelTrainable.HMMTrainMeanFail):
+        HiddenMarkovModelTrainable.from_data_batch({"1": [flat]}, num_of_states=3, max_iterations=3)
+    with pytest.raises(HiddenMarkovModelTrainable.HMMTrainMeanFail):
+        HiddenMarkovModelTrainable.from_data("1", [flat], num_of_states=3, max_iterations=3, isTqdm=False)
