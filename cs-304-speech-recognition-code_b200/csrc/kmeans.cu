@@ -11,10 +11,10 @@
 //                bucket (global state id of the word model it is credited to, 0xFFFF = none) and
 //                adds integer transition counts with atomics (integer => order independent).
 // accum_kernel:  grid = (bucket, chunk of frames).  A CTA scans the bucket ids of its chunk,
-//                compacts the matching frames in order, and every thread owns <= 4 entries of
-//                the packed statistics vector  [N | sum x | upper triangle of sum x x^T]  (float64,
-//                data shifted by shift_g for conditioning) which it updates from a shared-memory
-//                copy of the frame.  No floating-point atomics: partials per chunk, then
+//                compacts the matching frames in order and accumulates the outer products of the
+//                shifted, augmented frames [x - shift_g, 1] in 4 x 4 register tiles (float64); the
+//                packed statistics vector is [N | sum x | upper triangle of sum x x^T].
+//                No floating-point atomics: partials per chunk, then
 // reduce_kernel: sums the chunk partials in a fixed order => bitwise reproducible statistics.
 // Algorithmic HBM bytes: 4*D + 2 per frame (features once + bucket id; re-scans of the id array hit L2).
 #include "common.cuh"
@@ -22,7 +22,6 @@
 namespace loe {
 
 constexpr int kAccThreads = 256;
-constexpr int kAccBatch = 16;
 constexpr int kMaxDimK = 40;               // D + 1 (constant-one column) must fit
 
 // ------------------------------------------------------------------------------------------
@@ -80,6 +79,17 @@ __global__ void align_kernel(const int8_t* __restrict__ path, const int64_t* __r
 }
 
 // ------------------------------------------------------------------------------------------
+// Outer-product accumulation, register tiled.  The augmented frame y = [x - shift, 1] has K = D + 1 <= 40
+// entries; sum y y^T is cut into 4 x 4 tiles of a 10 x 10 tile grid and only the 55 tiles on or above the
+// diagonal are computed.  The CTA's 256 threads form 4 groups of 64; group q takes frames q, q+4, ... of a
+// batch and thread t < 55 of a group owns one tile (16 float64 accumulators): 4 + 4 shared-memory loads
+// feed 16 FMAs.  Groups are summed in a fixed order at the end, chunks by reduce_kernel: reproducible.
+constexpr int kAccGroups = 4;
+constexpr int kAccGroupThreads = kAccThreads / kAccGroups;      // 64
+constexpr int kTilesPerDim = kMaxDimK / 4;                       // 10
+constexpr int kTiles = kTilesPerDim * (kTilesPerDim + 1) / 2;    // 55
+constexpr int kAccFrames = 32;                                   // frames staged per batch
+
 __global__ void __launch_bounds__(kAccThreads)
 accum_kernel(const float* __restrict__ feat, const uint16_t* __restrict__ bucket, int64_t total_frames, int dim,
              int64_t chunk, const float* __restrict__ shift, double* __restrict__ part) {
@@ -87,30 +97,29 @@ accum_kernel(const float* __restrict__ feat, const uint16_t* __restrict__ bucket
     const int c = blockIdx.y;
     const int n_chunks = gridDim.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int K = dim + 1;                                   // augmented with a constant 1
+    const int grp = tid / kAccGroupThreads, tg = tid % kAccGroupThreads;
     const int stride = 1 + dim + dim * (dim + 1) / 2;
 
-    __shared__ double s_x[kAccBatch][kMaxDimK];
+    __shared__ __align__(16) double s_x[kAccFrames][kMaxDimK];
     __shared__ float s_shift[kMaxDimK];
     __shared__ int64_t s_list[kAccThreads];
     __shared__ int s_wcount[kAccThreads / 32];
+    __shared__ double s_sum[kMaxDimK][kMaxDimK + 1];
 
-    // entry -> (i, j) with the convention x[dim] == 1:  e = 0 -> (dim, dim);  1..dim -> (e-1, dim)
-    int ei[4], ej[4];
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int e = tid + q * kAccThreads;
-        int i = dim, j = dim;
-        if (e >= 1 && e <= dim) { i = e - 1; j = dim; }
-        else if (e > dim && e < stride) {
-            int r = e - 1 - dim, row = 0;
-            while (r >= dim - row) { r -= dim - row; ++row; }
-            i = row; j = row + r;
-        }
-        ei[q] = i; ej[q] = j;
+    // tile of this thread: t -> (ti, tj), ti <= tj, row-major over the upper triangle
+    int ti = 0, tj = 0;
+    const bool has_tile = tg < kTiles;
+    if (has_tile) {
+        int r = tg;
+        while (r >= kTilesPerDim - ti) { r -= kTilesPerDim - ti; ++ti; }
+        tj = ti + r;
     }
-    if (tid < K) s_shift[tid] = (tid < dim) ? shift[(size_t)g * dim + tid] : 0.f;
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+    if (tid < kMaxDimK) s_shift[tid] = (tid < dim) ? shift[(size_t)g * dim + tid] : 0.f;
     __syncthreads();
 
     const int64_t f_begin = (int64_t)c * chunk;
@@ -126,29 +135,57 @@ accum_kernel(const float* __restrict__ feat, const uint16_t* __restrict__ bucket
         for (int w = 0; w < kAccThreads / 32; ++w) { if (w < warp) off += s_wcount[w]; n_match += s_wcount[w]; }
         if (match) s_list[off + __popc(bal & ((1u << lane) - 1))] = f;
         __syncthreads();
-        for (int b0 = 0; b0 < n_match; b0 += kAccBatch) {
-            const int nb = min(kAccBatch, n_match - b0);
-            for (int i = tid; i < nb * K; i += kAccThreads) {
-                const int r = i / K, k = i - r * K;
-                s_x[r][k] = (k < dim) ? ((double)feat[s_list[b0 + r] * dim + k] - (double)s_shift[k]) : 1.0;
+        for (int b0 = 0; b0 < n_match; b0 += kAccFrames) {
+            const int nb = min(kAccFrames, n_match - b0);
+            // stage y = [x - shift, 1, 0...] of nb frames (float64)
+            for (int i = tid; i < nb * kMaxDimK; i += kAccThreads) {
+                const int r = i / kMaxDimK, k = i - r * kMaxDimK;
+                double v = 0.0;
+                if (k < dim) v = (double)feat[s_list[b0 + r] * dim + k] - (double)s_shift[k];
+                else if (k == dim) v = 1.0;
+                s_x[r][k] = v;
             }
             __syncthreads();
+            if (has_tile) {
+                for (int r = grp; r < nb; r += kAccGroups) {
+                    const double2 i01 = *reinterpret_cast<const double2*>(&s_x[r][4 * ti]);
+                    const double2 i23 = *reinterpret_cast<const double2*>(&s_x[r][4 * ti + 2]);
+                    const double2 j01 = *reinterpret_cast<const double2*>(&s_x[r][4 * tj]);
+                    const double2 j23 = *reinterpret_cast<const double2*>(&s_x[r][4 * tj + 2]);
+                    const double xi[4] = {i01.x, i01.y, i23.x, i23.y};
+                    const double xj[4] = {j01.x, j01.y, j23.x, j23.y};
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                if (tid + q * kAccThreads < stride) {
-                    double a = acc[q];
-                    for (int r = 0; r < nb; ++r) a = fma(s_x[r][ei[q]], s_x[r][ej[q]], a);
-                    acc[q] = a;
+                    for (int a = 0; a < 4; ++a)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) acc[a][b] = fma(xi[a], xj[b], acc[a][b]);
                 }
             }
             __syncthreads();
         }
     }
-    double* dst = part + ((size_t)g * n_chunks + c) * stride;
+    // groups -> one K x K matrix in shared memory (fixed order), then the packed vector
+    for (int q = 0; q < kAccGroups; ++q) {
+        if (grp == q && has_tile) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int e = tid + q * kAccThreads;
-        if (e < stride) dst[e] = acc[q];
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    double* dstp = &s_sum[4 * ti + a][4 * tj + b];
+                    *dstp = (q == 0) ? acc[a][b] : (*dstp + acc[a][b]);
+                }
+        }
+        __syncthreads();
+    }
+    double* dst = part + ((size_t)g * n_chunks + c) * stride;
+    for (int e = tid; e < stride; e += kAccThreads) {
+        int i = dim, j = dim;                              // e = 0: N = sum 1*1
+        if (e >= 1 && e <= dim) { i = e - 1; j = dim; }    // sum (x_i - shift_i) * 1
+        else if (e > dim) {
+            int r = e - 1 - dim, row = 0;
+            while (r >= dim - row) { r -= dim - row; ++row; }
+            i = row; j = row + r;
+        }
+        dst[e] = s_sum[i][j];
     }
 }
 
@@ -198,7 +235,6 @@ extern "C" int loe_kmeans_dev(const float* feat_dev, const uint16_t* bucket_dev,
     if (n_glob <= 0) return LOE_OK;
     if (dim + 1 > kMaxDimK) { set_error("kmeans kernel supports dim <= %d (got %d)", kMaxDimK - 1, dim); return LOE_ERR_UNSUPPORTED; }
     const int stride = 1 + dim + dim * (dim + 1) / 2;
-    if (stride > 4 * kAccThreads) { set_error("statistics vector too long"); return LOE_ERR_UNSUPPORTED; }
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     int64_t chunk; int n_chunks;
     kmeans_chunking(total_frames, &chunk, &n_chunks);

@@ -166,15 +166,23 @@ class Engine:
         return gp
 
     def pack_tc_words(self, words):
-        """Tensor-core images of several word models in ONE upload: ``words`` = [(means [S,D], U [S,D,D], cst [S])];
-        every word starts on a 6-state tile boundary so that a launch can address it by pointer offset.
-        Returns (b_packed, cst_pad, first tile of each word)."""
-        imgs, csts, first, t = [], [], [], 0
-        for means, us, cst in words:
-            b, c = pack_tc_image(means, us, cst)
-            imgs.append(b); csts.append(c); first.append(t)
-            t += len(c) // 6
-        return self._to_dev(np.concatenate(imgs)), self._to_dev(np.concatenate(csts)), first
+        """Tensor-core images of several word models in ONE host pass and ONE upload: ``words`` =
+        [(means [S,D], U [S,D,D], cst [S])]; every word starts on a 6-state tile boundary so that a launch
+        can address it by pointer offset.  Returns (b_packed, cst_pad, first tile of each word)."""
+        D = words[0][0].shape[1]
+        first, slots, t = [], [], 0
+        for means, _, _ in words:
+            n_t = (means.shape[0] + 5) // 6
+            first.append(t)
+            slots.append(np.arange(means.shape[0]) + 6 * t)
+            t += n_t
+        slots = np.concatenate(slots)
+        means_p = np.zeros((6 * t, D)); us_p = np.zeros((6 * t, D, D)); cst_p = np.zeros(6 * t)
+        means_p[slots] = np.concatenate([w[0] for w in words])
+        us_p[slots] = np.concatenate([w[1] for w in words])
+        cst_p[slots] = np.concatenate([w[2] for w in words])
+        b, c = pack_tc_image(means_p, us_p, cst_p)        # zero states give zero columns, like the padding
+        return self._to_dev(b), self._to_dev(c), first
 
     def emission_tc_into(self, feat, b_packed, cst_pad, first_tile: int, n_states: int, out, col0: int):
         """Tensor-core emission of one word (tiles from ``first_tile``) into columns [col0, col0+n_states) of ``out``."""

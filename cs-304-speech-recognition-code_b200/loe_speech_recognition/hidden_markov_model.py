@@ -212,6 +212,20 @@ def _unpack_stats(stats: np.ndarray, dim: int):
     return n, s1, s2
 
 
+def _batched_eigh(cov: np.ndarray):
+    """float64 symmetric eigendecomposition of [n, D, D] matrices (lower triangle, like scipy's _PSD); LAPACK
+    releases the GIL, so the batch is spread over a few host threads."""
+    n = cov.shape[0]
+    if n < 16:
+        return np.linalg.eigh(cov)
+    import concurrent.futures as cf
+    k = min(8, os.cpu_count() or 1, n // 8)
+    parts = np.array_split(np.arange(n), k)
+    with cf.ThreadPoolExecutor(max_workers=k) as ex:
+        res = list(ex.map(lambda idx: np.linalg.eigh(cov[idx]), parts))
+    return np.concatenate([r[0] for r in res]), np.concatenate([r[1] for r in res])
+
+
 @dataclass
 class HiddenMarkovModelTrainable(HiddenMarkovModel):
     class HMMTrainMeanFail(Exception):
@@ -312,7 +326,7 @@ class HiddenMarkovModelTrainable(HiddenMarkovModel):
             cov = np.concatenate([models[l]._covariances.astype(np.float64) for l in which])
             if not np.all(np.isfinite(cov)):
                 raise ValueError("array must not contain infs or NaNs")
-            lam, vec = np.linalg.eigh(cov)
+            lam, vec = _batched_eigh(cov)
             eps = 1e6 * np.finfo(np.float64).eps * np.max(np.abs(lam), axis=1)
             if np.any(lam.min(axis=1) < -eps):
                 raise ValueError("The input matrix must be symmetric positive semidefinite.")
