@@ -90,11 +90,37 @@ constexpr int kTilesPerDim = kMaxDimK / 4;                       // 10
 constexpr int kTiles = kTilesPerDim * (kTilesPerDim + 1) / 2;    // 55
 constexpr int kAccFrames = 32;                                   // frames staged per batch
 
+constexpr int kIdsPerThread = 8;
+constexpr int kScanSpan = kAccThreads * kIdsPerThread;           // 2048 frames per scan round
+
+// min / max bucket id present in every chunk: lets the (bucket, chunk) CTAs that have nothing to do exit
+// at once (frames are grouped by word, so a chunk usually holds the states of one or two words)
+__global__ void chunk_range_kernel(const uint16_t* __restrict__ bucket, int64_t total_frames, int64_t chunk,
+                                   int* __restrict__ range) {
+    __shared__ int s_lo[32], s_hi[32];
+    const int c = blockIdx.x;
+    const int64_t f_begin = (int64_t)c * chunk, f_end = min(total_frames, f_begin + chunk);
+    int lo = 0x7fffffff, hi = -1;
+    for (int64_t f = f_begin + threadIdx.x; f < f_end; f += blockDim.x) {
+        const int b = bucket[f];
+        if (b != 0xFFFF) { lo = min(lo, b); hi = max(hi, b); }
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) { lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+    if ((threadIdx.x & 31) == 0) { s_lo[threadIdx.x >> 5] = lo; s_hi[threadIdx.x >> 5] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { lo = min(lo, s_lo[w]); hi = max(hi, s_hi[w]); }
+        range[2 * c] = lo; range[2 * c + 1] = hi;
+    }
+}
+
 __global__ void __launch_bounds__(kAccThreads)
 accum_kernel(const float* __restrict__ feat, const uint16_t* __restrict__ bucket, int64_t total_frames, int dim,
-             int64_t chunk, const float* __restrict__ shift, double* __restrict__ part) {
+             int64_t chunk, const float* __restrict__ shift, const int* __restrict__ range, double* __restrict__ part) {
     const int g = blockIdx.x;
     const int c = blockIdx.y;
+    if (g < range[2 * c] || g > range[2 * c + 1]) return;          // partials were zeroed by the launcher
     const int n_chunks = gridDim.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int grp = tid / kAccGroupThreads, tg = tid % kAccGroupThreads;
@@ -102,7 +128,7 @@ accum_kernel(const float* __restrict__ feat, const uint16_t* __restrict__ bucket
 
     __shared__ __align__(16) double s_x[kAccFrames][kMaxDimK];
     __shared__ float s_shift[kMaxDimK];
-    __shared__ int64_t s_list[kAccThreads];
+    __shared__ int s_list[kScanSpan];                             // matching frames of the round, relative to `base`
     __shared__ int s_wcount[kAccThreads / 32];
     __shared__ double s_sum[kMaxDimK][kMaxDimK + 1];
 
@@ -124,16 +150,35 @@ accum_kernel(const float* __restrict__ feat, const uint16_t* __restrict__ bucket
 
     const int64_t f_begin = (int64_t)c * chunk;
     const int64_t f_end = min(total_frames, f_begin + chunk);
-    for (int64_t base = f_begin; base < f_end; base += kAccThreads) {
-        const int64_t f = base + tid;
-        const bool match = f < f_end && bucket[f] == (uint16_t)g;
-        const unsigned bal = __ballot_sync(0xffffffffu, match);
-        if (lane == 0) s_wcount[warp] = __popc(bal);
+    for (int64_t base = f_begin; base < f_end; base += kScanSpan) {
+        // ---- scan 8 consecutive ids per thread, compact the matches in frame order
+        const int64_t f0 = base + (int64_t)tid * kIdsPerThread;
+        unsigned flags = 0;
+        if (f0 + kIdsPerThread <= f_end && ((reinterpret_cast<uintptr_t>(bucket + f0) & 15) == 0)) {
+            const uint4 v = *reinterpret_cast<const uint4*>(bucket + f0);
+            const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if ((w[q] & 0xFFFFu) == (unsigned)g) flags |= 1u << (2 * q);
+                if ((w[q] >> 16) == (unsigned)g) flags |= 1u << (2 * q + 1);
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < kIdsPerThread; ++q)
+                if (f0 + q < f_end && bucket[f0 + q] == (uint16_t)g) flags |= 1u << q;
+        }
+        const int cnt = __popc(flags);
+        int incl = cnt;                                           // inclusive warp prefix sum
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        if (lane == 31) s_wcount[warp] = incl;
         __syncthreads();
-        int off = 0, n_match = 0;
+        int off = incl - cnt, n_match = 0;
 #pragma unroll
         for (int w = 0; w < kAccThreads / 32; ++w) { if (w < warp) off += s_wcount[w]; n_match += s_wcount[w]; }
-        if (match) s_list[off + __popc(bal & ((1u << lane) - 1))] = f;
+#pragma unroll
+        for (int q = 0; q < kIdsPerThread; ++q)
+            if (flags & (1u << q)) s_list[off++] = tid * kIdsPerThread + q;
         __syncthreads();
         for (int b0 = 0; b0 < n_match; b0 += kAccFrames) {
             const int nb = min(kAccFrames, n_match - b0);
@@ -141,7 +186,7 @@ accum_kernel(const float* __restrict__ feat, const uint16_t* __restrict__ bucket
             for (int i = tid; i < nb * kMaxDimK; i += kAccThreads) {
                 const int r = i / kMaxDimK, k = i - r * kMaxDimK;
                 double v = 0.0;
-                if (k < dim) v = (double)feat[s_list[b0 + r] * dim + k] - (double)s_shift[k];
+                if (k < dim) v = (double)feat[(base + s_list[b0 + r]) * dim + k] - (double)s_shift[k];
                 else if (k == dim) v = 1.0;
                 s_x[r][k] = v;
             }
@@ -200,8 +245,8 @@ __global__ void reduce_kernel(const double* __restrict__ part, int n_chunks, int
 }
 
 static void kmeans_chunking(int64_t total_frames, int64_t* chunk, int* n_chunks) {
-    int64_t ch = 16384;
-    while ((total_frames + ch - 1) / ch > 128) ch *= 2;
+    int64_t ch = 8192;
+    while ((total_frames + ch - 1) / ch > 512) ch *= 2;
     *chunk = ch;
     *n_chunks = (int)((total_frames + ch - 1) / ch);
     if (*n_chunks < 1) *n_chunks = 1;
@@ -226,7 +271,7 @@ extern "C" int loe_align_dev(const int8_t* path_dev, const int64_t* frm_off_dev,
 extern "C" int64_t loe_kmeans_ws_doubles(int64_t total_frames, int n_glob, int dim) {
     int64_t chunk; int n_chunks;
     loe::kmeans_chunking(total_frames, &chunk, &n_chunks);
-    return (int64_t)n_glob * n_chunks * (1 + dim + dim * (dim + 1) / 2);
+    return (int64_t)n_glob * n_chunks * (1 + dim + dim * (dim + 1) / 2) + n_chunks;    // + per-chunk bucket ranges
 }
 
 extern "C" int loe_kmeans_dev(const float* feat_dev, const uint16_t* bucket_dev, int64_t total_frames, int dim,
@@ -238,8 +283,13 @@ extern "C" int loe_kmeans_dev(const float* feat_dev, const uint16_t* bucket_dev,
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     int64_t chunk; int n_chunks;
     kmeans_chunking(total_frames, &chunk, &n_chunks);
+    const size_t n_part = (size_t)n_glob * n_chunks * stride;
+    int* range = reinterpret_cast<int*>(part_ws_dev + n_part);
+    LOE_CUDA(cudaMemsetAsync(part_ws_dev, 0, sizeof(double) * n_part, s));       // skipped CTAs leave zeros
+    chunk_range_kernel<<<(unsigned)n_chunks, 256, 0, s>>>(bucket_dev, total_frames, chunk, range);
+    LOE_LAUNCH_CHECK("chunk_range_kernel");
     dim3 grid((unsigned)n_glob, (unsigned)n_chunks);
-    accum_kernel<<<grid, kAccThreads, 0, s>>>(feat_dev, bucket_dev, total_frames, dim, chunk, shift_dev, part_ws_dev);
+    accum_kernel<<<grid, kAccThreads, 0, s>>>(feat_dev, bucket_dev, total_frames, dim, chunk, shift_dev, range, part_ws_dev);
     LOE_LAUNCH_CHECK("accum_kernel");
     reduce_kernel<<<(unsigned)n_glob, 256, 0, s>>>(part_ws_dev, n_chunks, stride, stats_dev);
     LOE_LAUNCH_CHECK("reduce_kernel");
