@@ -13,8 +13,10 @@
 //
 // Decomposition: B-stationary.  CTA (n, g) owns one tile of 6 states (N = 240 columns; W hi/lo
 // = 75 KB resident in shared memory for the whole kernel, loaded once) and walks the frame
-// tiles g, g+G, ... (M = 128 frames).  The 10 CTAs of a column g walk the same frames at the
-// same pace, so the feature tile is fetched from HBM once and re-read from L2.
+// tiles g, g+G, ... (M = 128 frames).  The CTAs of the different state tiles walk the same frames
+// at about the same pace, so a feature tile is fetched from HBM once and re-read from L2.  The SMs
+// are divided over the state tiles in proportion to their MMA cost: the last tile may hold fewer
+// states, is issued with a narrower N and gets fewer CTAs, so that every SM is busy to the end.
 //   warps 0-7  producers: the raw [128 x 39] feature tile (19 968 contiguous bytes) arrives by
 //              cp.async.bulk (TMA engine, mbarrier complete_tx), two tiles in flight; the warps
 //              split it hi/lo and store it in the canonical K-major no-swizzle UMMA layout
@@ -138,12 +140,20 @@ __device__ __forceinline__ float tf32_round(float x) {
 
 __global__ void __launch_bounds__(kThreads, 1)
 emission_tc_kernel(const float* __restrict__ feat, int64_t n_frames, const float* __restrict__ b_packed,
-                   const float* __restrict__ cst_pad, int n_states, float* __restrict__ out, int ld_out, int use_bulk) {
+                   const float* __restrict__ cst_pad, int n_states, float* __restrict__ out, int ld_out, int use_bulk,
+                   int g_full, int g_last) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int n_tile = blockIdx.x;
-    const int g = blockIdx.y, G = gridDim.y;
+    // CTA -> (state tile, frame-tile group).  Full tiles get g_full CTAs each, the last (possibly narrower,
+    // hence cheaper) tile gets g_last, so that all SMs finish together.
+    const int n_tiles = (n_states + kStatesPerTile - 1) / kStatesPerTile;
+    const int cta = blockIdx.x;
+    const int n_tile = min(cta / g_full, n_tiles - 1);
+    const int G = (n_tile == n_tiles - 1) ? g_last : g_full;
+    const int g = cta - n_tile * g_full;
+    const int valid = min(kStatesPerTile, n_states - n_tile * kStatesPerTile);       // states of this tile
+    const int n_cols = ((valid * kColsPerState + 15) / 16) * 16;                      // MMA N: multiple of 16
     const int n_mtiles = (int)((n_frames + kTileM - 1) / kTileM);
 
     // ---- one-time setup: barriers, TMEM, resident B tile
@@ -227,7 +237,7 @@ emission_tc_kernel(const float* __restrict__ feat, int64_t n_frames, const float
     } else if (warp == (kProducerThreads + kEpilogueThreads) / 32) {
         // =========================== MMA issuer ===========================
         if (lane == 0) {
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTileN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n_cols >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
             const uint32_t b_hi = smem_u32(sm.b_hi), b_lo = smem_u32(sm.b_lo);
             int it = 0;
             for (int m = g; m < n_mtiles; m += G, ++it) {
@@ -265,6 +275,7 @@ emission_tc_kernel(const float* __restrict__ feat, int64_t n_frames, const float
             float score[kStatesPerTile];
 #pragma unroll
             for (int j = 0; j < kStatesPerTile; ++j) {
+                if (j >= valid) { score[j] = 0.f; continue; }      // warp-uniform: the narrow last tile reads less
                 float v[40];
                 tmem_ld32(taddr + j * kColsPerState, v);
                 tmem_ld8(taddr + j * kColsPerState + 32, v + 32);
@@ -316,12 +327,28 @@ extern "C" int loe_emission_tc_dev(const float* feat_dev, int64_t n_frames, int 
     }
     const int n_tiles = (n_states + kStatesPerTile - 1) / kStatesPerTile;
     const int n_mtiles = (int)((n_frames + kTileM - 1) / kTileM);
-    int G = sm_count[dev] / n_tiles;
-    if (G < 1) G = 1;
-    if (G > n_mtiles) G = n_mtiles;
-    dim3 grid((unsigned)n_tiles, (unsigned)G);
+    // distribute the SMs over the state tiles in proportion to their MMA cost (N columns)
+    const int valid_last = n_states - (n_tiles - 1) * kStatesPerTile;
+    const double cost_last = (double)(((valid_last * kColsPerState + 15) / 16) * 16) / kTileN;
+    const int sms = sm_count[dev];
+    int g_full = 1, g_last = 1;
+    if (n_tiles == 1) {
+        g_last = sms;
+    } else if (sms >= n_tiles) {
+        // minimise max(1/g_full, cost_last/g_last) subject to (n_tiles-1)*g_full + g_last <= sms
+        double best = 1e30;
+        for (int gf = 1; (n_tiles - 1) * gf < sms; ++gf) {
+            const int gl = sms - (n_tiles - 1) * gf;
+            const double t = (1.0 / gf > cost_last / gl) ? 1.0 / gf : cost_last / gl;
+            if (t < best) { best = t; g_full = gf; g_last = gl; }
+        }
+    }
+    if (g_full > n_mtiles) g_full = n_mtiles;
+    if (g_last > n_mtiles) g_last = n_mtiles;
+    const unsigned grid = (unsigned)((n_tiles - 1) * g_full + g_last);
     const int use_bulk = (reinterpret_cast<uintptr_t>(feat_dev) & 15) == 0 ? 1 : 0;
-    emission_tc_kernel<<<grid, kThreads, sizeof(Smem), s>>>(feat_dev, n_frames, b_packed_dev, cst_pad_dev, n_states, out_dev, ld_out, use_bulk);
+    emission_tc_kernel<<<grid, kThreads, sizeof(Smem), s>>>(feat_dev, n_frames, b_packed_dev, cst_pad_dev, n_states, out_dev, ld_out,
+                                                            use_bulk, g_full, g_last);
     LOE_LAUNCH_CHECK("emission_tc_kernel");
     return LOE_OK;
 }
