@@ -461,6 +461,19 @@ def test_long_utterance_fallback_paths(eng, golden):
         assert bs.cpu().numpy()[0] == es[bi]
         assert np.array_equal(path.cpu().numpy(), opath)
     assert not eng.lib.loe_viterbi_bp_fits(12000, 58)
+    # label decoding on the fallback path (separate labels kernel) and the stand-alone labels entry point
+    inf._log_transition_probability_between_words = -100
+    long_feat = np.ascontiguousarray(np.tile(base, (2, 1))[:5000])
+    got = inf.predict_batch([long_feat, golden["loop_feat_0"]])
+    _, paths = inf.viterbi_batch([long_feat, golden["loop_feat_0"]])
+    assert got == ["".join(inf._model_boundaries.get_labels(p)) for p in paths]
+    assert len(got[0]) > 32                          # more words than the id table holds: host routine takes over
+    batch = eng.upload_features([golden["loop_feat_0"], golden["loop_feat_1"]], 39)
+    _, path = inf._decode_device(batch)
+    words, count = eng.labels(path, batch.frm_off, 2, tp, skip_label=LOOP_ORDER.index("S"), max_words=32)
+    for i in range(2):
+        ids = words.cpu().numpy()[i, :int(count[i])]
+        assert "".join(LOOP_ORDER[k] for k in ids) == str(golden["loop_strings_int"][i])
 
 
 def test_config1_isolated_digits_200_utterances(eng):
