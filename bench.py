@@ -9,8 +9,8 @@ synthetic 16 kHz utterances per GPU.  One "step" = one pass of the hot path over
 MFCC -> Gaussian emission scoring -> loop-grammar Viterbi + backtrace + word labels.
 
   value  utterances/s with the PCM already resident in HBM (whole job, all ranks)
-  e2e    same through the public API with HOST buffers: H2D of the pinned PCM, the four kernels,
-         D2H of the word ids, string assembly -- every step
+  e2e    same through the C-ABI host call (loe_decoder_decode_host) with HOST buffers: H2D of the
+         pinned PCM, the four kernels, D2H of the word ids, string assembly -- every step
   roofline      dominant kernel (emission scoring), timed live with CUDA events
   cpu_baseline  the reference's CPU path (oracle/ref_port.py: per-(frame,state) scipy calls, process
                 pool over utterances like the reference's scripts) on a bounded sample, rank 0, N=1
@@ -311,6 +311,22 @@ def impl_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e16_s = float(t.item())
     assert strings16 == strings
+    # the same batch through the torch-free C entry point (loe_decoder_decode_host): host pointers in, word ids out
+    host_np, host16_np = pinned.numpy(), pinned16.numpy()
+    c_abi = {}
+    for tag, buf in (("f32", host_np), ("s16", host16_np)):
+        for _ in range(2):
+            strings_c = inf.decode_pcm_host(buf, pcm_off, 16000, device=dev.index or 0)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            strings_c = inf.decode_pcm_host(buf, pcm_off, 16000, device=dev.index or 0)
+        sec = (time.perf_counter() - t0) / args.steps
+        t = torch.tensor([sec], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        c_abi[tag] = float(t.item())
+        assert strings_c == strings
     h2d = int(pinned.numel() * 4 + pcm_off.nbytes + frm_off.nbytes)
     d2h = int(n * 32 + n * 4)
 
@@ -334,7 +350,7 @@ def impl_b200(args):
     kernels = {
         "mfcc_mel_kernel": {"bound": "hbm", "alg": 4 * n_samples + 160 * F, "ms": stage_ms["mfcc_mel"], "traffic": NCU_TRAFFIC.get("mfcc_mel")},
         "mfcc_ceps_kernel": {"bound": "hbm", "alg": (160 + 156) * F, "ms": stage_ms["mfcc_ceps"], "traffic": NCU_TRAFFIC.get("mfcc_ceps")},
-        "emission_tc_kernel" if precision == "tc" else "emission_simt_kernel":
+        {"tc": "emission_tc_kernel", "h16": "emission_h16_kernel"}.get(precision, "emission_simt_kernel"):
             {"bound": "tensor", "alg": FLOPS_PER_FRAME * F, "ms": stage_ms["emission"], "traffic": NCU_TRAFFIC.get("emission_" + precision)},
         "viterbi_warp_kernel": {"bound": "hbm", "alg": (4 * 58 + 1) * F, "ms": stage_ms["viterbi"], "traffic": NCU_TRAFFIC.get("viterbi")},
     }
@@ -343,30 +359,37 @@ def impl_b200(args):
         if k["bound"] == "hbm":
             ach, peak, unit = k["alg"] / (k["ms"] * 1e-3) / 1e9, hbm, "GB/s"
         else:
-            ach, peak, unit = k["alg"] / (k["ms"] * 1e-3) / 1e12, tf32_peak, "TFLOP/s"
+            ach, peak, unit = k["alg"] / (k["ms"] * 1e-3) / 1e12, (bf16 if precision == "h16" else tf32_peak), "TFLOP/s"
         all_roof[name] = {"kernel": name, "bound": k["bound"], "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
                           "traffic": k["traffic"], "ms_per_launch": k["ms"],
                           "algorithmic": (f"{k['alg']} bytes per launch" if k["bound"] == "hbm" else
-                                          f"{FLOPS_PER_FRAME} flop/frame x {F} frames per launch (counted once; 3 TF32 MMAs issued)")}
+                                          f"{FLOPS_PER_FRAME} flop/frame x {F} frames per launch (counted once; 3 split-operand products issued)")}
     dominant = max(kernels, key=lambda kname: kernels[kname]["ms"])
     roofline = dict(all_roof[dominant])
-    roofline["peak_source"] = src + ("; TF32 peak taken as bf16_tflops burst / 2" if roofline["bound"] == "tensor" else "")
+    if roofline["bound"] == "tensor":
+        src += ("; kind::f16 MMAs run at the measured bf16 rate" if precision == "h16" else "; TF32 peak taken as bf16_tflops burst / 2")
+    roofline["peak_source"] = src
     if dominant == "mfcc_mel_kernel":
         roofline["note"] = ("nominally HBM-bound (796 B/frame) but limited by fp32 issue: ~590 warp instructions per frame "
                             "(radix-5 x 32-point shuffle FFT), see profiles/")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": {"fp32": "f32", "fp64": "f64", "tc": "tf32x3"}[precision], "data": "synthetic",
+        "dtype": {"fp32": "f32", "fp64": "f64", "tc": "tf32x3", "h16": "f16x3"}[precision], "data": "synthetic",
         "config": {**workload_config(n, min(args.pool, n), "gpu"), "frames_per_gpu": F, "emission": precision},
         "frames_per_s": world * F / (ms * 1e-3),
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_s * 1e3, "api": "HiddenMarkovModelInference.decode_pcm_flat (pinned host PCM in, digit strings out)",
+        "e2e": {"value": world * n / c_abi["f32"], "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": c_abi["f32"] * 1e3,
+                "api": "loe_decoder_decode_host (C ABI, include/loe_b200.h) called through HiddenMarkovModelInference.decode_pcm_host: "
+                       "pinned host float32 PCM in, digit strings out; numpy + ctypes only, streams / workspace / chunk overlap "
+                       "inside the C library",
                 "string_accuracy_vs_truth": acc},
-        "e2e_int16_pcm": {"value": world * n / e2e16_s, "unit": UNIT, "ms_per_step": e2e16_s * 1e3,
+        "e2e_int16_pcm": {"value": world * n / c_abi["s16"], "unit": UNIT, "ms_per_step": c_abi["s16"] * 1e3,
                           "h2d_bytes_per_step": int(pinned16.numel() * 2 + pcm_off.nbytes + frm_off.nbytes),
-                          "note": "same API call fed the raw int16 WAV samples instead of the reference's float32 copy; "
-                                  "identical strings"},
+                          "note": "same call fed the raw int16 WAV samples instead of the reference's float32 copy; identical strings"},
+        "e2e_python_api": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_s * 1e3, "int16_value": world * n / e2e16_s,
+                           "int16_ms_per_step": e2e16_s * 1e3,
+                           "api": "HiddenMarkovModelInference.decode_pcm_flat (torch tensors / streams as plumbing); identical strings"},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": roofline,
@@ -395,7 +418,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--utts", type=int, default=10000, help="utterances per GPU")
     ap.add_argument("--pool", type=int, default=500, help="distinct synthetic utterances (tiled to --utts)")
-    ap.add_argument("--precision", default=os.environ.get("LOE_B200_EMISSION", "tc"), choices=["fp32", "fp64", "tc"])
+    ap.add_argument("--precision", default=os.environ.get("LOE_B200_EMISSION", "tc"), choices=["fp32", "fp64", "tc", "h16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -1,0 +1,235 @@
+// Host-buffer decode entry point: a self-contained C pipeline (no torch, no Python) that takes raw PCM in
+// HOST memory and returns the decoded word ids, i.e. the whole of
+//   MFCC.batch -> HiddenMarkovModelInference.predict  (mfcc.py:71-84, hidden_markov_model.py:458-461)
+// for a batch of utterances.  The decoder object owns the device copies of the model tables, a
+// workspace that grows on demand and two streams: the batch is cut into chunks of whole utterances and
+// the host->device copy of chunk c+1 (copy stream) overlaps MFCC, emission scoring and Viterbi of
+// chunk c (compute stream); only the word-id tables (and optionally paths / scores) travel back.
+#include "common.cuh"
+#include <vector>
+#include <algorithm>
+#include <new>
+#include <string.h>
+
+
+namespace loe {
+
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return LOE_OK;
+        if (p) { LOE_CUDA(cudaFree(p)); p = nullptr; cap = 0; }
+        const size_t want = bytes + bytes / 8 + 256;
+        LOE_CUDA(cudaMalloc(&p, want));
+        cap = want;
+        return LOE_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct Decoder {
+    int device = 0;
+    cudaStream_t copy = nullptr, comp = nullptr;
+    cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    // model
+    int mel_na = 0, mel_nb = 0, n_states = 0, n_pos = 0, n_ends = 0;
+    int32_t* d_mel_bin = nullptr; float* d_mel_w = nullptr; float* d_b = nullptr; float* d_cst = nullptr;
+    int32_t* d_tr_off = nullptr; int32_t* d_col = nullptr; float* d_band = nullptr; uint8_t* d_flags = nullptr;
+    int32_t* d_word = nullptr; int32_t* d_word_lo = nullptr;
+    // workspace
+    DevBuf pcm[2], off[2], mel, feat, scores, path, umax, words, count, best, best_score, bp;
+    int64_t* h_off[2] = {nullptr, nullptr}; size_t h_off_cap[2] = {0, 0};      // pinned staging: [pcm_off | frm_off]
+    bool used[2] = {false, false};
+    char* h_out = nullptr; size_t h_out_cap = 0;                                // pinned staging of the results
+};
+
+template <typename T>
+static int upload(T** dst, const T* src, size_t n) {
+    LOE_CUDA(cudaMalloc((void**)dst, sizeof(T) * std::max<size_t>(n, 1)));
+    if (n) LOE_CUDA(cudaMemcpy(*dst, src, sizeof(T) * n, cudaMemcpyHostToDevice));
+    return LOE_OK;
+}
+
+static void destroy(Decoder* d) {
+    if (!d) return;
+    cudaSetDevice(d->device);
+    if (d->comp) cudaStreamSynchronize(d->comp);
+    if (d->copy) cudaStreamSynchronize(d->copy);
+    for (int i = 0; i < 2; ++i) {
+        d->pcm[i].release(); d->off[i].release();
+        if (d->h_off[i]) cudaFreeHost(d->h_off[i]);
+        if (d->ev_copy[i]) cudaEventDestroy(d->ev_copy[i]);
+        if (d->ev_done[i]) cudaEventDestroy(d->ev_done[i]);
+    }
+    if (d->h_out) cudaFreeHost(d->h_out);
+    DevBuf* bufs[] = {&d->mel, &d->feat, &d->scores, &d->path, &d->umax, &d->words, &d->count, &d->best, &d->best_score, &d->bp};
+    for (DevBuf* b : bufs) b->release();
+    void* tabs[] = {d->d_mel_bin, d->d_mel_w, d->d_b, d->d_cst, d->d_tr_off, d->d_col, d->d_band, d->d_flags, d->d_word, d->d_word_lo};
+    for (void* t : tabs) if (t) cudaFree(t);
+    if (d->copy) cudaStreamDestroy(d->copy);
+    if (d->comp) cudaStreamDestroy(d->comp);
+    delete d;
+}
+
+}  // namespace loe
+
+extern "C" int loe_decoder_create(int device, const int32_t* mel_bin_host, const float* mel_w_host, int mel_na, int mel_nb,
+                                  const float* b_packed_host, const float* cst_pad_host, int n_states,
+                                  int n_pos, const int32_t* col_host, const float* band_host, const uint8_t* flags_host,
+                                  const int32_t* word_host, const int32_t* word_lo_host, void** out) {
+    using namespace loe;
+    if (!out) { set_error("out is NULL"); return LOE_ERR_VALUE; }
+    *out = nullptr;
+    if (n_pos <= 0 || n_pos > LOE_MAX_POS) { set_error("%d trellis positions (1..%d supported)", n_pos, LOE_MAX_POS); return n_pos > LOE_MAX_POS ? LOE_ERR_OVERFLOW : LOE_ERR_VALUE; }
+    if (n_states <= 0 || mel_na < 0 || mel_nb < 0 || mel_na > LOE_MEL_NA_MAX || mel_nb > LOE_MEL_NB_MAX) { set_error("bad model sizes"); return LOE_ERR_VALUE; }
+    LOE_CUDA(cudaSetDevice(device));
+    Decoder* d = new (std::nothrow) Decoder();
+    if (!d) { set_error("out of host memory"); return LOE_ERR_CUDA; }
+    d->device = device; d->mel_na = mel_na; d->mel_nb = mel_nb; d->n_states = n_states; d->n_pos = n_pos;
+    for (int p = 0; p < n_pos; ++p) d->n_ends += (flags_host[p] & LOE_POS_END) ? 1 : 0;
+    int st = LOE_OK;
+    const int n_tiles = loe_emission_tc_tiles(n_states);
+    const int32_t tr_off[2] = {0, n_pos};
+    auto fail = [&](int code) { destroy(d); return code; };
+#define LOE_TRY(x) if ((st = (x)) != LOE_OK) return fail(st)
+    LOE_TRY(check_cuda(cudaStreamCreateWithFlags(&d->copy, cudaStreamNonBlocking), "stream"));
+    LOE_TRY(check_cuda(cudaStreamCreateWithFlags(&d->comp, cudaStreamNonBlocking), "stream"));
+    for (int i = 0; i < 2; ++i) {
+        LOE_TRY(check_cuda(cudaEventCreateWithFlags(&d->ev_copy[i], cudaEventDisableTiming), "event"));
+        LOE_TRY(check_cuda(cudaEventCreateWithFlags(&d->ev_done[i], cudaEventDisableTiming), "event"));
+    }
+    LOE_TRY(upload(&d->d_mel_bin, mel_bin_host, (size_t)(mel_na + mel_nb) * 32));
+    LOE_TRY(upload(&d->d_mel_w, mel_w_host, (size_t)(mel_na + mel_nb) * 32));
+    LOE_TRY(upload(&d->d_b, b_packed_host, (size_t)n_tiles * 19200));
+    LOE_TRY(upload(&d->d_cst, cst_pad_host, (size_t)n_tiles * 6));
+    LOE_TRY(upload(&d->d_tr_off, tr_off, 2));
+    LOE_TRY(upload(&d->d_col, col_host, (size_t)n_pos));
+    LOE_TRY(upload(&d->d_band, band_host, (size_t)n_pos * 3));
+    LOE_TRY(upload(&d->d_flags, flags_host, (size_t)n_pos));
+    LOE_TRY(upload(&d->d_word, word_host, (size_t)n_pos));
+    LOE_TRY(upload(&d->d_word_lo, word_lo_host, (size_t)n_pos));
+#undef LOE_TRY
+    *out = d;
+    return LOE_OK;
+}
+
+extern "C" void loe_decoder_destroy(void* dec) { loe::destroy(reinterpret_cast<loe::Decoder*>(dec)); }
+
+extern "C" int loe_decoder_decode_host(void* dec, const void* pcm_host, int pcm_format, const int64_t* sample_off_host, int n_utt,
+                                       double penalty, int penalty_f64, int skip_label, int max_words, int n_chunks,
+                                       int8_t* words_host, int32_t* count_host, float* best_score_host, int8_t* path_host) {
+    using namespace loe;
+    Decoder* d = reinterpret_cast<Decoder*>(dec);
+    if (!d) { set_error("decoder is NULL"); return LOE_ERR_VALUE; }
+    if (n_utt <= 0) return LOE_OK;
+    if (pcm_format != LOE_PCM_F32 && pcm_format != LOE_PCM_S16) { set_error("unknown pcm_format %d", pcm_format); return LOE_ERR_VALUE; }
+    if (max_words <= 0 || !words_host || !count_host) { set_error("words / count buffers required"); return LOE_ERR_VALUE; }
+    LOE_CUDA(cudaSetDevice(d->device));
+    const size_t bps = pcm_format == LOE_PCM_F32 ? 4 : 2;
+    const int64_t total_samples = sample_off_host[n_utt] - sample_off_host[0];
+    if (n_chunks <= 0) n_chunks = (int)std::min<int64_t>(8, std::max<int64_t>(1, (int64_t)(total_samples * bps) / (64ll << 20)));
+    // chunk boundaries: whole utterances, about equal numbers of samples
+    std::vector<int> bounds{0};
+    for (int c = 1; c < n_chunks; ++c) {
+        const int64_t target = sample_off_host[0] + total_samples * c / n_chunks;
+        int u = (int)(std::lower_bound(sample_off_host, sample_off_host + n_utt + 1, target) - sample_off_host);
+        u = std::min(std::max(u, bounds.back()), n_utt);
+        if (u > bounds.back()) bounds.push_back(u);
+    }
+    if (bounds.back() != n_utt) bounds.push_back(n_utt);
+    // results land in pinned staging (a device->host copy into pageable memory would block the host
+    // until the chunk's kernels finish and with it the next chunk's upload), then move to the caller's arrays
+    int64_t total_frames = 0;
+    for (int i = 0; i < n_utt; ++i) total_frames += 1 + (sample_off_host[i + 1] - sample_off_host[i]) / LOE_HOP;
+    const size_t o_words = 0, o_count = o_words + (((size_t)n_utt * max_words + 15) & ~(size_t)15),
+                 o_score = o_count + (size_t)n_utt * 4, o_path = o_score + (size_t)n_utt * 4,
+                 out_bytes = o_path + (path_host ? (size_t)total_frames : 0);
+    if (d->h_out_cap < out_bytes) {
+        if (d->h_out) LOE_CUDA(cudaFreeHost(d->h_out));
+        d->h_out = nullptr; d->h_out_cap = 0;
+        LOE_CUDA(cudaHostAlloc((void**)&d->h_out, out_bytes + out_bytes / 4, cudaHostAllocDefault));
+        d->h_out_cap = out_bytes + out_bytes / 4;
+    }
+    int64_t frames_done = 0;
+    for (size_t c = 0; c + 1 < bounds.size(); ++c) {
+        const int a = bounds[c], b = bounds[c + 1], n = b - a, set = (int)(c & 1);
+        const int64_t s0 = sample_off_host[a], ns = sample_off_host[b] - s0;
+        // staging of this set is free once its previous copy has completed
+        // (host) and its device buffers once the kernels of the chunk that used them are done (copy stream waits)
+        if (d->used[set]) { LOE_CUDA(cudaEventSynchronize(d->ev_copy[set])); LOE_CUDA(cudaStreamWaitEvent(d->copy, d->ev_done[set], 0)); }
+        const size_t off_elems = 2 * (size_t)(n + 1);
+        if (d->h_off_cap[set] < off_elems) {
+            if (d->h_off[set]) LOE_CUDA(cudaFreeHost(d->h_off[set]));
+            d->h_off[set] = nullptr; d->h_off_cap[set] = 0;
+            LOE_CUDA(cudaHostAlloc((void**)&d->h_off[set], sizeof(int64_t) * (off_elems + off_elems / 4 + 16), cudaHostAllocDefault));
+            d->h_off_cap[set] = off_elems + off_elems / 4 + 16;
+        }
+        int64_t* pcm_off = d->h_off[set];
+        int64_t* frm_off = pcm_off + (n + 1);
+        int max_frames = 0, min_frames = 1 << 30;
+        frm_off[0] = 0;
+        for (int i = 0; i <= n; ++i) pcm_off[i] = sample_off_host[a + i] - s0;
+        for (int i = 0; i < n; ++i) {
+            const int fr = (int)(1 + (pcm_off[i + 1] - pcm_off[i]) / LOE_HOP);
+            frm_off[i + 1] = frm_off[i] + fr;
+            max_frames = std::max(max_frames, fr); min_frames = std::min(min_frames, fr);
+        }
+        const int64_t F = frm_off[n];
+        int st;
+        if ((st = d->pcm[set].ensure((size_t)ns * bps)) != LOE_OK) return st;
+        if ((st = d->off[set].ensure(sizeof(int64_t) * off_elems)) != LOE_OK) return st;
+        LOE_CUDA(cudaMemcpyAsync(d->pcm[set].p, (const char*)pcm_host + (size_t)(s0 - sample_off_host[0]) * bps, (size_t)ns * bps,
+                                 cudaMemcpyHostToDevice, d->copy));
+        LOE_CUDA(cudaMemcpyAsync(d->off[set].p, pcm_off, sizeof(int64_t) * off_elems, cudaMemcpyHostToDevice, d->copy));
+        LOE_CUDA(cudaEventRecord(d->ev_copy[set], d->copy));
+        d->used[set] = true;
+        // compute buffers are shared by all chunks: growing them must wait for the chunks in flight
+        const bool bp_needed = !loe_viterbi_bp_fits(max_frames, d->n_pos);
+        const size_t need[] = {(size_t)F * 40 * 4, (size_t)F * 39 * 4, (size_t)F * d->n_states * 4, (size_t)F, (size_t)n * 4,
+                               (size_t)n * max_words, (size_t)n * 4, (size_t)n * 4, (size_t)n * 4, bp_needed ? (size_t)F * LOE_MAX_POS : 0};
+        DevBuf* bufs[] = {&d->mel, &d->feat, &d->scores, &d->path, &d->umax, &d->words, &d->count, &d->best, &d->best_score, &d->bp};
+        bool grow = false;
+        for (int i = 0; i < 10; ++i) grow |= need[i] > bufs[i]->cap;
+        if (grow) {
+            LOE_CUDA(cudaStreamSynchronize(d->comp));
+            for (int i = 0; i < 10; ++i) if ((st = bufs[i]->ensure(need[i])) != LOE_OK) return st;
+        }
+        LOE_CUDA(cudaStreamWaitEvent(d->comp, d->ev_copy[set], 0));
+        const int64_t* d_pcm_off = (const int64_t*)d->off[set].p;
+        const int64_t* d_frm_off = d_pcm_off + (n + 1);
+        if ((st = loe_mfcc_dev(d->pcm[set].p, pcm_format, d_pcm_off, d_frm_off, n, F, max_frames, min_frames, d->d_mel_bin, d->d_mel_w,
+                               d->mel_na, d->mel_nb, (float*)d->mel.p, (float*)d->umax.p, (float*)d->feat.p, d->comp)) != LOE_OK) return st;
+        if ((st = loe_emission_tc_dev((const float*)d->feat.p, F, 39, d->d_b, d->d_cst, d->n_states, (float*)d->scores.p, d->n_states,
+                                      d->comp)) != LOE_OK) return st;
+        if ((st = loe_viterbi_dev((const float*)d->scores.p, d->n_states, d_frm_off, n, max_frames, d->d_tr_off, d->d_col, d->d_band,
+                                  d->d_flags, d->n_pos, nullptr, 1, penalty, penalty_f64, (int8_t*)d->path.p, nullptr, d->n_ends,
+                                  (int32_t*)d->best.p, (float*)d->best_score.p, bp_needed ? (uint8_t*)d->bp.p : nullptr,
+                                  d->d_word, d->d_word_lo, skip_label, (int8_t*)d->words.p, max_words, (int32_t*)d->count.p, d->comp)) != LOE_OK)
+            return st;
+        LOE_CUDA(cudaMemcpyAsync(d->h_out + o_words + (size_t)a * max_words, d->words.p, (size_t)n * max_words, cudaMemcpyDeviceToHost, d->comp));
+        LOE_CUDA(cudaMemcpyAsync(d->h_out + o_count + (size_t)a * 4, d->count.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, d->comp));
+        if (best_score_host) LOE_CUDA(cudaMemcpyAsync(d->h_out + o_score + (size_t)a * 4, d->best_score.p, sizeof(float) * n, cudaMemcpyDeviceToHost, d->comp));
+        if (path_host) LOE_CUDA(cudaMemcpyAsync(d->h_out + o_path + frames_done, d->path.p, (size_t)F, cudaMemcpyDeviceToHost, d->comp));
+        LOE_CUDA(cudaEventRecord(d->ev_done[set], d->comp));
+        frames_done += F;
+    }
+    LOE_CUDA(cudaStreamSynchronize(d->comp));
+    memcpy(words_host, d->h_out + o_words, (size_t)n_utt * max_words);
+    memcpy(count_host, d->h_out + o_count, (size_t)n_utt * 4);
+    if (best_score_host) memcpy(best_score_host, d->h_out + o_score, (size_t)n_utt * 4);
+    if (path_host) memcpy(path_host, d->h_out + o_path, (size_t)total_frames);
+    return LOE_OK;
+}
+
+extern "C" int loe_host_alloc(void** ptr_out, size_t bytes) {
+    using namespace loe;
+    if (!ptr_out) { set_error("ptr_out is NULL"); return LOE_ERR_VALUE; }
+    LOE_CUDA(cudaHostAlloc(ptr_out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return LOE_OK;
+}
+
+extern "C" int loe_host_free(void* ptr) {
+    using namespace loe;
+    if (ptr) LOE_CUDA(cudaFreeHost(ptr));
+    return LOE_OK;
+}

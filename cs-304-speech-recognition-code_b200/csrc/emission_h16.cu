@@ -1,0 +1,365 @@
+// Gaussian emission scoring on the 5th-generation tensor cores, 3xFP16 variant of emission_tc.cu.
+//
+// Same contraction and the same split-operand idea as the 3xTF32 kernel
+//     y[f, (s, j)] = sum_k [x_f, 1][k] * W_s[k, j],   score[f, s] = cst_s - 0.5 * sum_j y^2
+// but the operands are split into two binary16 parts (x = hi + lo, 11 + 11 significant bits: the
+// same 22 bits a TF32 pair carries) and the products hi*hi + lo*hi + hi*lo run as kind::f16 MMAs,
+// which the tensor pipe executes at twice the TF32 rate.  The 15 (A chunk, B chunk) products of
+// 8 halfs each are paired into 8 MMAs of K = 16 through the descriptors' leading byte offset
+// (one zero A chunk and one duplicated B chunk make the pairing come out even), against 15 TF32 MMAs.
+//
+// Range: binary16 tops out at 65504.  The B image is checked on the host when it is packed (the
+// caller falls back to the TF32 image otherwise); every feature row whose largest magnitude reaches
+// 2^15 is scaled by an exact power of two before the split and the squared norm is scaled back in
+// the epilogue, so the A operand cannot overflow.  Residuals below 2^-24 flush to the binary16
+// subnormal grid: an absolute error of 3e-8 on values below 0.125, the same size as the TF32 pair's
+// relative error there.
+//
+// Decomposition, warp roles and pipelines are those of emission_tc.cu: B-stationary CTAs per state
+// tile, raw feature tiles by cp.async.bulk (two in flight), 8 producer warps, 4 epilogue warps, one
+// MMA-issuing thread, two accumulators in TMEM.
+#include <cuda_fp16.h>
+#include "tcgen05.cuh"
+
+namespace loe {
+namespace h16 {
+using namespace loe::tc;
+
+constexpr int kTileM = 128;
+constexpr int kDim = 39;
+constexpr int kK = 40;                  // 39 features + the constant 1 of the bias row
+constexpr int kChunksPerPart = kK / 8;  // 16-byte chunks (8 halfs) of one hi or lo part: 5
+constexpr int kAChunks = 2 * kChunksPerPart + 1;   // hi 0-4, lo 5-9, zero 10
+constexpr int kBChunks = 2 * kChunksPerPart + 1;   // hi 0-4, lo 5-9, copy of hi chunk 4 at 10
+constexpr int kColsPerState = 40;
+constexpr int kStatesPerTile = 6;
+constexpr int kTileN = kStatesPerTile * kColsPerState;   // 240
+constexpr int kTmemCols = 512;
+constexpr int kBufStride = 256;
+constexpr int kProducerGroups = 2;           // groups of 128 threads (thread = feature row) taking the tiles in turn
+constexpr int kProducerThreads = kProducerGroups * 128;
+constexpr int kEpilogueThreads = 128;
+constexpr int kThreads = kProducerThreads + kEpilogueThreads + 32;
+constexpr int kALbo = kTileM * 16;      // 2048 B between K-adjacent A chunks
+constexpr int kBLbo = kTileN * 16;      // 3840 B between K-adjacent B chunks
+constexpr int kABytes = kAChunks * kALbo;   // 22528
+constexpr int kBBytes = kBChunks * kBLbo;   // 42240
+constexpr int kNumMma = 8;
+constexpr int kRawBufs = 4;
+
+struct __align__(128) Smem {
+    uint8_t b[kBBytes];
+    uint8_t a[2][kABytes];
+    float raw[kRawBufs][kTileM * kDim];  // raw feature tiles, filled by cp.async.bulk: two in flight per producer group
+    float inv2[4][kTileM];              // 4^e of the rows scaled by 2^-e (1 for ordinary rows); slot = tile & 3: the
+                                        // producers run at most 3 tiles ahead of the epilogue
+    float out_stage[4][32 * kStatesPerTile];   // per epilogue warp: 32 rows x 6 scores on their way to global memory
+    float cst[8];
+    uint64_t raw_full[kRawBufs], a_full[2], a_empty[2], tmem_full[2], tmem_empty[2];
+    uint32_t tmem_base;
+};
+
+// the 8 MMAs: (first A chunk, second A chunk, first B chunk, second B chunk)
+__host__ __device__ constexpr int pair_chunk(int mma, int which) {
+    constexpr int t[kNumMma][4] = {
+        {0, 1, 0, 1}, {2, 3, 2, 3},          // hi * hi
+        {5, 6, 0, 1}, {7, 8, 2, 3},          // lo * hi
+        {0, 1, 5, 6}, {2, 3, 7, 8},          // hi * lo
+        {4, 9, 4, 10},                       // hi4 * hi4 + lo4 * hi4 (copy)
+        {4, 10, 9, 10},                      // hi4 * lo4 + zero * (anything)
+    };
+    return t[mma][which];
+}
+
+// hi/lo split of 8 consecutive values into one 16-byte chunk each (packed conversions: F2FP converts two
+// values per instruction, the scalar F2F runs on the slow conversion pipe)
+__device__ __forceinline__ void split_store(const float* x, uint8_t* a_row, int kc) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const __half2 hh = __floats2half2_rn(x[2 * q], x[2 * q + 1]);
+        const float2 hf = __half22float2(hh);
+        const __half2 ll = __floats2half2_rn(x[2 * q] - hf.x, x[2 * q + 1] - hf.y);
+        h[q] = *reinterpret_cast<const uint32_t*>(&hh);
+        l[q] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    *reinterpret_cast<uint4*>(a_row + kc * kALbo) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(a_row + (kChunksPerPart + kc) * kALbo) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// One thread stages one feature row (39 values + the constant 1 of the bias row).  Returns 4^e of the
+// power-of-two scale 2^-e applied to the row: 1 unless its largest magnitude reaches 2^15.
+__device__ __forceinline__ float stage_row(const float* __restrict__ row, uint8_t* __restrict__ a_row) {
+    float v[kK];
+    float mx = 0.0f;
+#pragma unroll
+    for (int c = 0; c < kDim; ++c) {
+        v[c] = row[c];
+        mx = fmaxf(mx, fabsf(v[c]));
+    }
+    v[kDim] = 1.0f;
+    float inv2 = 1.0f;
+    if (!(mx < 32768.0f)) {                        // rare; also taken for NaN
+        const int e = (int)((__float_as_uint(mx) >> 23) & 0xffu) - 127 - 14;       // 1 .. 114
+        const float scale = __uint_as_float((uint32_t)(127 - e) << 23);
+        inv2 = (2 * e < 128) ? __uint_as_float((uint32_t)(127 + 2 * e) << 23) : CUDART_INF_F;
+#pragma unroll
+        for (int c = 0; c < kK; ++c) v[c] *= scale;
+    }
+#pragma unroll
+    for (int kc = 0; kc < kChunksPerPart; ++kc) split_store(v + kc * 8, a_row, kc);
+    return inv2;
+}
+
+__device__ __forceinline__ unsigned long long pack_f2(float x, float y) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+    return r;
+}
+__device__ __forceinline__ float2 unpack_f2(unsigned long long v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+// acc += x * x on both fp32 lanes of a 64-bit register pair (FFMA2)
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long x, unsigned long long acc) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(r) : "l"(x), "l"(acc));
+    return r;
+}
+
+// sum of squares of the first 39 of 40 accumulator columns
+__device__ __forceinline__ float sumsq39(const float* v) {
+    // packed fp32x2 FMAs (two lanes per instruction), two independent chains of pairs
+    unsigned long long a = 0ull, b = 0ull;
+#pragma unroll
+    for (int c = 0; c < 36; c += 4) {
+        a = ffma2(pack_f2(v[c], v[c + 1]), a);
+        b = ffma2(pack_f2(v[c + 2], v[c + 3]), b);
+    }
+    a = ffma2(pack_f2(v[36], v[37]), a);
+    const float2 fa = unpack_f2(a), fb = unpack_f2(b);
+    return fmaf(v[38], v[38], (fa.x + fa.y) + (fb.x + fb.y));
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+emission_h16_kernel(const float* __restrict__ feat, int64_t n_frames, const uint8_t* __restrict__ b_packed,
+                   const float* __restrict__ cst_pad, int n_states, float* __restrict__ out, int ld_out, int use_bulk,
+                   int g_full, int g_last) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // CTA -> (state tile, frame-tile group).  Full tiles get g_full CTAs each, the last (possibly narrower,
+    // hence cheaper) tile gets g_last, so that all SMs finish together.
+    const int n_tiles = (n_states + kStatesPerTile - 1) / kStatesPerTile;
+    const int cta = blockIdx.x;
+    const int n_tile = min(cta / g_full, n_tiles - 1);
+    const int G = (n_tile == n_tiles - 1) ? g_last : g_full;
+    const int g = cta - n_tile * g_full;
+    const int valid = min(kStatesPerTile, n_states - n_tile * kStatesPerTile);       // states of this tile
+    const int n_cols = ((valid * kColsPerState + 15) / 16) * 16;                      // MMA N: multiple of 16
+    const int n_mtiles = (int)((n_frames + kTileM - 1) / kTileM);
+    // 8-byte stores of score pairs need an even row pitch, an 8-byte aligned matrix and an even number of states
+    // in this tile (else the odd last state would be lost): otherwise scalar stores
+    const bool pair_stores = ((ld_out & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 7) == 0) && ((valid & 1) == 0);
+
+    // ---- one-time setup: barriers, TMEM, resident B tile
+    if (tid == 0) {
+        for (int i = 0; i < kRawBufs; ++i) mbar_init(&sm.raw_full[i], 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&sm.a_full[i], kTileM);
+            mbar_init(&sm.a_empty[i], 1);
+            mbar_init(&sm.tmem_full[i], 1);
+            mbar_init(&sm.tmem_empty[i], kEpilogueThreads);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kProducerThreads / 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(b_packed + (size_t)n_tile * kBBytes);
+        uint4* dst = reinterpret_cast<uint4*>(sm.b);
+        for (int i = tid; i < kBBytes / 16; i += kThreads) dst[i] = __ldg(src + i);
+        if (tid < kStatesPerTile) sm.cst[tid] = cst_pad[n_tile * kStatesPerTile + tid];
+        // the zero chunk of both A stages is written once
+        for (int i = tid; i < 2 * kTileM; i += kThreads)
+            *reinterpret_cast<uint4*>(sm.a[i / kTileM] + (kAChunks - 1) * kALbo + (i % kTileM) * 16) = make_uint4(0, 0, 0, 0);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = sm.tmem_base;
+
+    if (warp < kProducerThreads / 32) {
+        // =========================== producers ===========================
+        constexpr int kTileElems = kTileM * kDim;                       // 4992 floats = 19968 B, a multiple of 16
+        constexpr uint32_t kTileBytes = kTileElems * sizeof(float);
+        const int n_it = (g < n_mtiles) ? (n_mtiles - g + G - 1) / G : 0;
+        // bulk copies need a 16-byte aligned source (use_bulk) and a whole tile
+        auto tile_full = [&](int it) { return use_bulk && (int64_t)(g + it * G + 1) * kTileM <= n_frames; };
+        // kProducerGroups groups of 128 threads (thread = feature row) take the tiles in turn; tile it is staged into
+        // stage it & 1 of A.  The raw tiles go round four buffers (it & 3): four bulk copies are in flight.
+        const int row_id = tid & (kTileM - 1);
+        const int p = tid >> 7;
+        auto issue = [&](int it) {                       // one thread: full tiles are contiguous and 16-byte aligned
+            bulk_load(sm.raw[it & 3], feat + (int64_t)(g + it * G) * kTileElems, kTileBytes, &sm.raw_full[it & 3]);
+        };
+        if (row_id == 0)
+            for (int it = p; it < kRawBufs && it < n_it; it += kProducerGroups)
+                if (tile_full(it)) issue(it);
+        for (int it = p; it < n_it; it += kProducerGroups) {
+            const int st = it & 1;
+            const uint32_t k = (uint32_t)(it >> 1);
+            float* raw = sm.raw[it & 3];
+            if (tile_full(it)) {
+                mbar_wait(&sm.raw_full[it & 3], (uint32_t)(it >> 2) & 1);         // TMA bytes have landed
+            } else {
+                // the batch's last, partial tile: plain loads, rows beyond the end read as zero
+                const int64_t f0 = (int64_t)(g + it * G) * kTileM;
+                const int total = (int)(n_frames - f0) * kDim;
+                for (int e = row_id; e < kTileElems; e += kTileM) raw[e] = (e < total) ? __ldg(feat + f0 * kDim + e) : 0.f;
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + p) : "memory");
+            }
+            mbar_wait(&sm.a_empty[st], (k & 1) ^ 1);       // MMA finished reading this stage
+            sm.inv2[it & 3][row_id] = stage_row(raw + row_id * kDim /* stride 39 words: conflict free */,
+                                                sm.a[st] + row_id * 16);
+            fence_proxy_async();
+            mbar_arrive(&sm.a_full[st]);
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + p) : "memory");   // the group is done with this raw buffer: refill it
+            if (row_id == 0 && it + 4 < n_it && tile_full(it + 4)) issue(it + 4);
+        }
+    } else if (warp == (kProducerThreads + kEpilogueThreads) / 32) {
+        // =========================== MMA issuer ===========================
+        if (lane == 0) {
+            // c_format F32 (bit 4), a/b format F16 (0), N >> 3 at bit 17, M >> 4 at bit 24
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(n_cols >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+            const uint32_t b_base = smem_u32(sm.b);
+            uint64_t b_desc[kNumMma];
+#pragma unroll
+            for (int i = 0; i < kNumMma; ++i)
+                b_desc[i] = make_desc(b_base + pair_chunk(i, 2) * kBLbo, (pair_chunk(i, 3) - pair_chunk(i, 2)) * kBLbo);
+            int it = 0;
+            for (int m = g; m < n_mtiles; m += G, ++it) {
+                const int s = it & 1;
+                const uint32_t k = (uint32_t)(it >> 1);
+                mbar_wait(&sm.a_full[s], k & 1);
+                mbar_wait(&sm.tmem_empty[s], (k & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d = tmem_base + (uint32_t)(s * kBufStride);
+                const uint32_t a_base = smem_u32(sm.a[s]);
+#pragma unroll
+                for (int i = 0; i < kNumMma; ++i)
+                    mma_f16(d, make_desc(a_base + pair_chunk(i, 0) * kALbo, (pair_chunk(i, 1) - pair_chunk(i, 0)) * kALbo), b_desc[i], idesc,
+                            i ? 1u : 0u);
+                mma_commit(&sm.a_empty[s]);
+                mma_commit(&sm.tmem_full[s]);
+            }
+        }
+    } else {
+        // =========================== epilogue ===========================
+        // One warp per TMEM lane quarter (thread = frame row).  The stores of a tile are deferred until the first
+        // TMEM loads of the next tile have been issued.
+        const int q = warp & 3;                             // TMEM lane quarter this warp may touch
+        const int r = q * 32 + lane;
+        float2* stage = reinterpret_cast<float2*>(sm.out_stage[q]);
+        auto store_tile = [&](int m_prev) {
+            if (pair_stores) {
+                // a row's 6 scores are 24 contiguous bytes of the score matrix: three neighbouring lanes write one
+                // row (8 bytes each) -- a third of the sector requests of lane-per-row scalar stores
+                const int64_t f0 = (int64_t)m_prev * kTileM + q * 32;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const int idx = i * 32 + lane, row = idx / 3, h = idx - row * 3;
+                    const int st0 = n_tile * kStatesPerTile + 2 * h;
+                    if (f0 + row < n_frames && st0 + 1 < n_states)
+                        *reinterpret_cast<float2*>(out + (f0 + row) * ld_out + st0) = stage[idx];
+                }
+            } else {
+                const int64_t f = (int64_t)m_prev * kTileM + r;
+                if (f < n_frames) {
+                    float* o = out + f * ld_out + n_tile * kStatesPerTile;
+                    const float* mine = reinterpret_cast<const float*>(stage) + lane * kStatesPerTile;
+#pragma unroll
+                    for (int j = 0; j < kStatesPerTile; ++j)
+                        if (j < valid) o[j] = mine[j];
+                }
+            }
+            __syncwarp();                                   // the staging buffer may be rewritten
+        };
+        int it = 0, m_prev = -1;
+        for (int m = g; m < n_mtiles; m += G, ++it) {
+            const int s = it & 1;
+            const uint32_t k = (uint32_t)(it >> 1);
+            mbar_wait(&sm.tmem_full[s], k & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * kBufStride);
+            // software pipeline over the states: the TMEM load of state j+1 is in flight while state j is reduced
+            float va[40], vb[40];
+            tmem_ld32(taddr, va);
+            tmem_ld8(taddr + 32, va + 32);
+            if (m_prev >= 0) store_tile(m_prev);            // previous tile's scores: shared memory -> global
+            float score[kStatesPerTile];
+            const float mhalf = -0.5f * sm.inv2[it & 3][r];          // exact: inv2 is a power of two (1 for ordinary rows)
+#pragma unroll
+            for (int j = 0; j < kStatesPerTile; ++j) {
+                if (j >= valid) { score[j] = 0.f; continue; }      // warp-uniform: the narrow last tile reads less
+                float* cur = (j & 1) ? vb : va;
+                float* nxt = (j & 1) ? va : vb;
+                tmem_ld_wait();
+                if (j + 1 < valid) {
+                    tmem_ld32(taddr + (j + 1) * kColsPerState, nxt);
+                    tmem_ld8(taddr + (j + 1) * kColsPerState + 32, nxt + 32);
+                }
+                score[j] = fmaf(mhalf, sumsq39(cur), sm.cst[j]);
+            }
+            tc_fence_before();
+            mbar_arrive(&sm.tmem_empty[s]);
+#pragma unroll
+            for (int h = 0; h < 3; ++h) stage[lane * 3 + h] = make_float2(score[2 * h], score[2 * h + 1]);
+            __syncwarp();
+            m_prev = m;
+        }
+        if (m_prev >= 0) store_tile(m_prev);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kProducerThreads / 32) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+    }
+}
+
+}  // namespace h16
+}  // namespace loe
+
+extern "C" int loe_emission_h16_tile_bytes(void) { return loe::h16::kBBytes; }
+
+extern "C" int loe_emission_h16_dev(const float* feat_dev, int64_t n_frames, int dim, const void* b_packed_dev,
+                                    const float* cst_pad_dev, int n_states, float* out_dev, int ld_out, void* stream) {
+    using namespace loe;
+    using namespace loe::h16;
+    if (n_frames <= 0 || n_states <= 0) return LOE_OK;
+    if (dim != kDim) { set_error("tensor-core emission path is built for dim == 39 (got %d)", dim); return LOE_ERR_UNSUPPORTED; }
+    if (ld_out < n_states) { set_error("ld_out (%d) < n_states (%d)", ld_out, n_states); return LOE_ERR_VALUE; }
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    static int sm_count[64] = {0};
+    int dev = 0;
+    LOE_CUDA(cudaGetDevice(&dev));
+    if (dev >= 64) dev = 63;
+    if (sm_count[dev] == 0) {
+        LOE_CUDA(cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
+        LOE_CUDA(cudaFuncSetAttribute(emission_h16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+    }
+    int g_full = 1, g_last = 1;
+    split_sms(n_states, n_frames, sm_count[dev], &g_full, &g_last);
+    const int n_tiles = (n_states + kStatesPerTile - 1) / kStatesPerTile;
+    const unsigned grid = (unsigned)((n_tiles - 1) * g_full + g_last);
+    const int use_bulk = (reinterpret_cast<uintptr_t>(feat_dev) & 15) == 0 ? 1 : 0;
+    emission_h16_kernel<<<grid, kThreads, sizeof(Smem), s>>>(feat_dev, n_frames, static_cast<const uint8_t*>(b_packed_dev), cst_pad_dev,
+                                                             n_states, out_dev, ld_out, use_bulk, g_full, g_last);
+    LOE_LAUNCH_CHECK("emission_h16_kernel");
+    return LOE_OK;
+}

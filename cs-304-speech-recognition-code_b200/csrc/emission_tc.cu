@@ -28,7 +28,7 @@
 //              square + sum each group of 40 columns, store 6 scores per frame
 // Accumulators are double buffered in TMEM (2 x 240 of the 512 columns), A in shared memory
 // (2 stages), so staging(i+1), MMA(i) and epilogue(i-1) overlap.
-#include "common.cuh"
+#include "tcgen05.cuh"
 
 namespace loe {
 namespace tc {
@@ -63,76 +63,6 @@ struct __align__(128) Smem {
     uint64_t raw_full[2], a_full[2], a_empty[2], tmem_full[2], tmem_empty[2];
     uint32_t tmem_base;
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-// one thread: arm the barrier with the byte count, then let the TMA engine copy a contiguous chunk
-__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);            // start address, 16-byte units
-    d |= (uint64_t)(lbo_bytes >> 4) << 16;              // leading (K) byte offset
-    d |= (uint64_t)(kSbo >> 4) << 32;                   // stride (M/N) byte offset
-    d |= (uint64_t)1 << 46;                             // descriptor version (Blackwell)
-    return d;                                           // layout_type = 0: no swizzle
-}
-
-__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n"
-        "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
-}
-__device__ __forceinline__ void mma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-    uint32_t* r = reinterpret_cast<uint32_t*>(v);
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
-    uint32_t* r = reinterpret_cast<uint32_t*>(v);
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ float tf32_round(float x) {
     return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
@@ -325,26 +255,9 @@ extern "C" int loe_emission_tc_dev(const float* feat_dev, int64_t n_frames, int 
         LOE_CUDA(cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
         LOE_CUDA(cudaFuncSetAttribute(emission_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
     }
-    const int n_tiles = (n_states + kStatesPerTile - 1) / kStatesPerTile;
-    const int n_mtiles = (int)((n_frames + kTileM - 1) / kTileM);
-    // distribute the SMs over the state tiles in proportion to their MMA cost (N columns)
-    const int valid_last = n_states - (n_tiles - 1) * kStatesPerTile;
-    const double cost_last = (double)(((valid_last * kColsPerState + 15) / 16) * 16) / kTileN;
-    const int sms = sm_count[dev];
     int g_full = 1, g_last = 1;
-    if (n_tiles == 1) {
-        g_last = sms;
-    } else if (sms >= n_tiles) {
-        // minimise max(1/g_full, cost_last/g_last) subject to (n_tiles-1)*g_full + g_last <= sms
-        double best = 1e30;
-        for (int gf = 1; (n_tiles - 1) * gf < sms; ++gf) {
-            const int gl = sms - (n_tiles - 1) * gf;
-            const double t = (1.0 / gf > cost_last / gl) ? 1.0 / gf : cost_last / gl;
-            if (t < best) { best = t; g_full = gf; g_last = gl; }
-        }
-    }
-    if (g_full > n_mtiles) g_full = n_mtiles;
-    if (g_last > n_mtiles) g_last = n_mtiles;
+    split_sms(n_states, n_frames, sm_count[dev], &g_full, &g_last);
+    const int n_tiles = (n_states + kStatesPerTile - 1) / kStatesPerTile;
     const unsigned grid = (unsigned)((n_tiles - 1) * g_full + g_last);
     const int use_bulk = (reinterpret_cast<uintptr_t>(feat_dev) & 15) == 0 ? 1 : 0;
     emission_tc_kernel<<<grid, kThreads, sizeof(Smem), s>>>(feat_dev, n_frames, b_packed_dev, cst_pad_dev, n_states, out_dev, ld_out,

@@ -20,12 +20,13 @@ from ._trellis import HostTrellis, stack
 _ENGINE = None
 _ENGINE_PID = None
 
-PRECISIONS = {"fp32": 0, "fp64": 1, "tc": 2}
+PRECISIONS = {"fp32": 0, "fp64": 1, "tc": 2, "h16": 3}
 
 
 def default_precision() -> str:
-    """"auto" = the tcgen05 3xTF32 kernel when the model is 39-dimensional, the float32 SIMT kernel
-    otherwise.  LOE_B200_EMISSION=fp32|fp64|tc overrides (fp64 reproduces scipy bit for bit almost
+    """"auto" = for 39-dimensional models the tcgen05 3xFP16 kernel ("h16"; the 3xTF32 kernel "tc" when a
+    model's whitening matrix leaves the binary16 range), the float32 SIMT kernel otherwise.
+    LOE_B200_EMISSION=fp32|fp64|tc|h16 overrides (fp64 reproduces scipy bit for bit almost
     everywhere and is the mode to use when chasing a path difference)."""
     return os.environ.get("LOE_B200_EMISSION", "auto")
 
@@ -45,8 +46,9 @@ class GaussPack:
     mean64: "torch.Tensor"
     u64: "torch.Tensor"
     cst64: "torch.Tensor"
-    b_packed: "torch.Tensor" = None     # tensor-core image (dim == 39 only)
+    b_packed: "torch.Tensor" = None     # tensor-core image, 3xTF32 (dim == 39 only)
     cst_pad: "torch.Tensor" = None
+    b_h16: "torch.Tensor" = None        # tensor-core image, 3xFP16 (dim == 39 and |W| < 32768 only)
 
 
 @dataclass
@@ -112,6 +114,31 @@ def pack_tc_image(means: np.ndarray, us: np.ndarray, cst: np.ndarray):
     return np.ascontiguousarray(out.reshape(-1)), cst_pad
 
 
+H16_MAX = 32768.0
+
+
+def pack_h16_image(means: np.ndarray, us: np.ndarray, cst: np.ndarray):
+    """Host pre-pack of the 3xFP16 tensor-core operand (layout documented at loe_emission_h16_dev), or
+    None when an entry of W_s = [U_s ; -mean_s.U_s] leaves the binary16 range."""
+    S, D = means.shape
+    spt, cols, K = 6, 40, 40
+    n_tiles = (S + spt - 1) // spt
+    W = np.zeros((n_tiles * spt, K, cols), dtype=np.float64)
+    W[:S, :D, :D] = us
+    W[:S, D, :D] = -np.einsum("si,sij->sj", means, us)
+    if not np.all(np.abs(W) < H16_MAX):          # also rejects NaN / inf
+        return None
+    hi = W.astype(np.float16)
+    lo = (W - hi.astype(np.float64)).astype(np.float16)
+    out = np.empty((n_tiles, 11, spt * cols, 8), dtype=np.float16)
+    for base, part in ((0, hi), (5, lo)):
+        # part [tile, state_local, k, j] -> [tile, kc, n = state_local*40 + j, q]
+        p = part.reshape(n_tiles, spt, K // 8, 8, cols)            # [t, sl, kc, q, j]
+        out[:, base:base + 5] = p.transpose(0, 2, 1, 4, 3).reshape(n_tiles, K // 8, spt * cols, 8)
+    out[:, 10] = out[:, 4]
+    return np.ascontiguousarray(out.reshape(-1))
+
+
 class Engine:
     def __init__(self, device: Optional[int] = None):
         import torch
@@ -163,6 +190,9 @@ class Engine:
         if gp.dim == 39:
             b, c = pack_tc_image(means, us, cst)
             gp.b_packed, gp.cst_pad = self._to_dev(b), self._to_dev(c)
+            h = pack_h16_image(means, us, cst)
+            if h is not None:
+                gp.b_h16 = self._to_dev(h)
         return gp
 
     def pack_tc_words(self, words):
@@ -268,7 +298,9 @@ class Engine:
         torch = self.torch
         precision = precision or default_precision()
         if precision == "auto":
-            precision = "tc" if gp.b_packed is not None else "fp32"
+            precision = "h16" if gp.b_h16 is not None else "tc" if gp.b_packed is not None else "fp32"
+        if precision == "h16" and gp.b_h16 is None and gp.b_packed is not None:
+            precision = "tc"                     # whitening matrix outside the binary16 range
         n_frames, dim = int(feat.shape[0]), int(feat.shape[1])
         if dim != gp.dim:
             raise AssertionError(f"feature dimension {dim} != model dimension {gp.dim}")
@@ -277,6 +309,13 @@ class Engine:
         if out is None:
             out = self.empty((n_frames, ld), torch.float32)
         code = PRECISIONS[precision]
+        if code == 3:
+            if gp.b_h16 is None:
+                raise NotImplementedError("the tensor-core emission kernel is built for 39-dimensional features")
+            _native.check(self.lib.loe_emission_h16_dev(feat.data_ptr(), n_frames, dim, gp.b_h16.data_ptr(),
+                                                        gp.cst_pad.data_ptr(), gp.n_states, out.data_ptr(), ld, self._stream()))
+            self.launches += 1
+            return out
         if code == 2:
             if gp.b_packed is None:
                 raise NotImplementedError("the tensor-core emission kernel is built for 39-dimensional features")

@@ -34,6 +34,8 @@ SIGNATURES = {
                                  c_void_p, c_int, c_int, c_void_p]),
     "loe_emission_tc_tiles": (c_int, [c_int]),
     "loe_emission_tc_dev": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]),
+    "loe_emission_h16_tile_bytes": (c_int, []),
+    "loe_emission_h16_dev": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "loe_viterbi_bp_fits": (c_int, [c_int, c_int]),
     "loe_viterbi_dev": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
@@ -50,6 +52,13 @@ SIGNATURES = {
                               c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "loe_kmeans_ws_doubles": (c_int64, [c_int64, c_int, c_int]),
     "loe_kmeans_dev": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "loe_decoder_create": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int,
+                                   c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "loe_decoder_decode_host": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_double, c_int, c_int, c_int, c_int,
+                                        c_void_p, c_void_p, c_void_p, c_void_p]),
+    "loe_decoder_destroy": (None, [c_void_p]),
+    "loe_host_alloc": (c_int, [c_void_p, ctypes.c_size_t]),
+    "loe_host_free": (c_int, [c_void_p]),
 }
 
 _lib = None

@@ -71,7 +71,7 @@ class MultivariateNormal:
 class _PackCache:
     """Mixin: drops device handles when pickled (ProcessPoolExecutor ships models to workers)."""
 
-    _PACK_ATTRS = ("_pack_cache",)
+    _PACK_ATTRS = ("_pack_cache", "_native_decoder")
 
     def __getstate__(self):
         state = dict(self.__dict__)
@@ -79,11 +79,11 @@ class _PackCache:
             state.pop(k, None)
         return state
 
-    def _cached(self, key, builder):
-        cache = self.__dict__.get("_pack_cache")
+    def _cached(self, key, builder, slot: str = "_pack_cache"):
+        cache = self.__dict__.get(slot)
         if cache is None or cache[0] != key or cache[2] != os.getpid():
             cache = (key, builder(), os.getpid())
-            self.__dict__["_pack_cache"] = cache
+            self.__dict__[slot] = cache
         return cache[1]
 
 
@@ -675,6 +675,42 @@ class HiddenMarkovModelInference(_PackCache):
             return np.concatenate([p.cpu().numpy() for _, _, p, _, _, _ in keep])
         frm_all = np.concatenate(([0], np.cumsum(frames))).astype(np.int64)
         return self._strings_host(wh, ch, full_path, frm_all)
+
+    # -- torch-free route: the C host-buffer decoder (include/loe_b200.h, loe_decoder_*) ----------
+    def native_decoder(self, sample_rate: float = 16000, device: int = 0):
+        """The :class:`_decoder.NativeDecoder` of this model (device tables, streams and workspace owned by
+        the C library; rebuilt when a script replaces the Gaussians / transitions)."""
+        from ._decoder import NativeDecoder
+        from ._engine import host_gauss_arrays
+
+        def build():
+            mb = self._model_boundaries
+            dense = self._log_transition_probs.to_dense()
+            lows, sizes = mb.lower_boundaries, mb.sizes
+            blocks = [dense[a:a + n, a:a + n] for a, n in zip(lows, sizes)]
+            tr = _trellis.build(blocks, lows, list(range(len(sizes))), "loop")
+            return NativeDecoder(*host_gauss_arrays(self._multivariate_normals), tr, sample_rate, device)
+        key = ("native", float(sample_rate), int(device)) + tuple(_model_key(self._multivariate_normals, self._log_transition_probs))
+        return self._cached(key, build, slot="_native_decoder")
+
+    def decode_pcm_host(self, pcm_flat, sample_offsets, sample_rate: float = 16000, n_chunks: int = 0,
+                        device: int = 0) -> List[str]:
+        """:meth:`decode_pcm_flat` through ``loe_decoder_decode_host``: numpy in, strings out, no torch on
+        the way (``pcm_flat`` float32 or int16; a :class:`_decoder.PinnedBuffer` array makes the copies
+        asynchronous).  Same results as every other decode entry point."""
+        dec = self.native_decoder(sample_rate, device)
+        pen, f64 = _penalty_args(self._log_transition_probability_between_words)
+        names = self._model_boundaries._labels
+        skip = names.index("S") if "S" in names else -1
+        off = np.asarray(sample_offsets, dtype=np.int64)
+        words, count, _, _ = dec.decode(pcm_flat, off, pen, f64, skip, 32, n_chunks)
+        if len(off) <= 1:
+            return []
+
+        def full_path():
+            return dec.decode(pcm_flat, off, pen, f64, skip, 32, n_chunks, want_path=True)[3]
+        frm_all = np.concatenate(([0], np.cumsum(1 + np.diff(off) // 160))).astype(np.int64)
+        return self._strings_host(words, count, full_path, frm_all)
 
 
 # ----------------------------------------------------------------------------------------

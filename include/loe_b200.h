@@ -23,6 +23,7 @@
 #ifndef LOE_B200_H
 #define LOE_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -123,6 +124,19 @@ int loe_emission_dev(const float* feat_dev, int64_t n_frames, int dim,
 int loe_emission_tc_tiles(int n_states);
 int loe_emission_tc_dev(const float* feat_dev, int64_t n_frames, int dim, const float* b_packed_dev,
                         const float* cst_pad_dev, int n_states, float* out_dev, int ld_out, void* stream);
+
+/* 3xFP16 variant of loe_emission_tc_dev (csrc/emission_h16.cu): the operands are split into two
+ * binary16 parts (the same 22 significant bits as the TF32 pair) and run as kind::f16 MMAs, 8 per
+ * 128-frame tile against 15 -- about twice the throughput at the same measured accuracy.
+ * b_packed_dev: per tile of 6 states loe_emission_h16_tile_bytes() (= 42240) bytes of binary16,
+ *   [chunk c (11)][n = state_local*40 + j (240)][q (8)] with W_s[k][j], k = 8*(c % 5) + q:
+ *   chunks 0-4 = fp16(W), chunks 5-9 = fp16(W - fp16(W)), chunk 10 = a copy of chunk 4.
+ * Domain: every |W| must be below 32768 (the host packer checks and the caller uses the TF32 image
+ * otherwise); feature rows of any magnitude are accepted (rows reaching 2^15 are rescaled by an exact
+ * power of two inside the kernel).  cst_pad_dev as for loe_emission_tc_dev. */
+int loe_emission_h16_tile_bytes(void);
+int loe_emission_h16_dev(const float* feat_dev, int64_t n_frames, int dim, const void* b_packed_dev,
+                         const float* cst_pad_dev, int n_states, float* out_dev, int ld_out, void* stream);
 
 /* --------------------------------------------------------------------------------------
  * Viterbi + backtrace, one CTA per utterance.  Replaces HiddenMarkovModel._viterbi /
@@ -241,6 +255,38 @@ int loe_align_dev(const int8_t* path_dev, const int64_t* frm_off_dev, int n_utt,
 int64_t loe_kmeans_ws_doubles(int64_t total_frames, int n_glob, int dim);
 int loe_kmeans_dev(const float* feat_dev, const uint16_t* bucket_dev, int64_t total_frames, int dim,
                    int n_glob, const float* shift_dev, double* part_ws_dev, double* stats_dev, void* stream);
+
+/* --------------------------------------------------------------------------------------
+ * Host-buffer decoder: the whole hot path behind ONE call that takes HOST memory and needs no
+ * torch / Python on the caller's side.  Replaces, for a batch of utterances,
+ *     [HiddenMarkovModelInference.predict(MFCC(sig, sr).feature_vector) for sig in signals]
+ * (mfcc.py:24-44 + hidden_markov_model.py:458-581 + model_boundary.py:107-147).
+ *
+ * loe_decoder_create uploads the model tables once (mel lane tables as loe_mfcc_dev reads them,
+ * the tensor-core Gaussian image as loe_emission_tc_dev reads it, ONE loop-grammar trellis as
+ * loe_viterbi_dev reads it; all pointers are HOST pointers) and owns two streams plus a device
+ * workspace that grows on demand and is reused by later calls.
+ *
+ * loe_decoder_decode_host: pcm_host holds the utterances back to back (float32 or int16, see
+ * pcm_format), utterance i = samples [sample_off[i], sample_off[i+1]).  The batch is cut into
+ * n_chunks chunks of whole utterances (n_chunks <= 0: about 64 MB each, at most 8); the copy of
+ * chunk c+1 overlaps the kernels of chunk c (pinned pcm_host makes that copy asynchronous; pageable
+ * memory works, without the overlap).  Outputs (HOST): words [n_utt*max_words] int8 word ids,
+ * count [n_utt] int32 (count > max_words or < 0: decode that utterance's path on the host, as
+ * loe_labels_dev documents), optional best_score [n_utt] float32 and path [total_frames] int8.
+ * The call returns after the results have landed.  One call at a time per decoder.
+ * -------------------------------------------------------------------------------------- */
+int loe_decoder_create(int device, const int32_t* mel_bin_host, const float* mel_w_host, int mel_na, int mel_nb,
+                       const float* b_packed_host, const float* cst_pad_host, int n_states,
+                       int n_pos, const int32_t* col_host, const float* band_host, const uint8_t* flags_host,
+                       const int32_t* word_host, const int32_t* word_lo_host, void** decoder_out);
+int loe_decoder_decode_host(void* decoder, const void* pcm_host, int pcm_format, const int64_t* sample_off_host, int n_utt,
+                            double penalty, int penalty_f64, int skip_label, int max_words, int n_chunks,
+                            int8_t* words_host, int32_t* count_host, float* best_score_host, int8_t* path_host);
+void loe_decoder_destroy(void* decoder);
+/* page-locked host buffers for pcm_host (cudaHostAlloc / cudaFreeHost) */
+int loe_host_alloc(void** ptr_out, size_t bytes);
+int loe_host_free(void* ptr);
 
 #ifdef __cplusplus
 }

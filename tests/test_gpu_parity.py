@@ -54,7 +54,7 @@ def test_mfcc_ragged_batch_and_errors(eng):
 
 
 # ------------------------------------------------------------------ a2 emission
-@pytest.mark.parametrize("precision,rtol", [("fp32", 1e-4), ("fp64", 1e-6), ("tc", 1e-4)])
+@pytest.mark.parametrize("precision,rtol", [("fp32", 1e-4), ("fp64", 1e-6), ("tc", 1e-4), ("h16", 1e-4)])
 def test_emission_matches_scipy(eng, golden, precision, rtol):
     from oracle import hmm as O
     x = np.concatenate([golden[f"iso_feat_{i}"] for i in range(6)])
@@ -105,7 +105,7 @@ def test_emission_ill_conditioned(eng):
     gp = eng.pack_gaussians([mn])
     pk = O.gaussian_pack(mean, cov)
     ref = O.emission_scores(x, *[np.array([v]) for v in pk])
-    for precision in ("fp32", "fp64", "tc"):
+    for precision in ("fp32", "fp64", "tc", "h16"):
         got = eng.emission(eng._to_dev(x), gp, precision).cpu().numpy()
         assert emission_close(got, ref, [pk[2]]), (precision, np.abs(got / ref - 1).max())
 
@@ -124,8 +124,9 @@ def test_emission_tc_many_tiles_and_ragged_sizes(eng, golden):
             x = base[rng.integers(0, len(base), size=n_frames)]
             xd = eng._to_dev(x)
             ref = eng.emission(xd, gp, "fp64").cpu().numpy()
-            got = eng.emission(xd, gp, "tc").cpu().numpy()
-            assert emission_close(got, ref, lps), (n_states, n_frames, np.abs(got - ref).max())
+            for kind in ("tc", "h16"):
+                got = eng.emission(xd, gp, kind).cpu().numpy()
+                assert emission_close(got, ref, lps), (kind, n_states, n_frames, np.abs(got - ref).max())
     # a feature buffer that is only 4-byte aligned takes the non-TMA loads; same values
     gp = eng.pack_gaussians(normals)
     x = eng._to_dev(base[:1000])
@@ -133,6 +134,44 @@ def test_emission_tc_many_tiles_and_ragged_sizes(eng, golden):
     shifted.copy_(x)
     assert shifted.data_ptr() % 16 != 0
     assert eng.torch.equal(eng.emission(shifted, gp, "tc"), eng.emission(x, gp, "tc"))
+    assert eng.torch.equal(eng.emission(shifted, gp, "h16"), eng.emission(x, gp, "h16"))
+
+
+def test_emission_h16_range_handling(eng, golden):
+    """binary16 tops out at 65504: feature rows of any magnitude are rescaled inside the kernel, a model
+    whose whitening matrix leaves the range gets no FP16 image and runs on the TF32 kernel."""
+    from loe_speech_recognition._engine import pack_h16_image
+    rng = np.random.default_rng(11)
+    inf = _loop_inference(golden)
+    normals = inf._multivariate_normals[:12]
+    gp = eng.pack_gaussians(normals)
+    assert gp.b_h16 is not None
+    lps = [mn._core.cov_object._log_pdet for mn in normals]
+    x = np.concatenate([golden[f"loop_feat_{i}"] for i in range(3)])[:600].copy()
+    big = rng.integers(0, len(x), size=60)
+    x[big] *= np.float32(10.0) ** rng.integers(3, 9, size=60)[:, None].astype(np.float32)     # rows up to ~1e9
+    xd = eng._to_dev(x)
+    ref = eng.emission(xd, gp, "fp64").cpu().numpy()
+    got = eng.emission(xd, gp, "h16").cpu().numpy()
+    assert np.all(np.isfinite(got))
+    np.testing.assert_allclose(got, ref, rtol=2e-4)      # huge rows: 1e-4 of |score| plus the float32 input cancellation
+    # ordinary rows are untouched by the presence of huge ones
+    small = np.setdiff1d(np.arange(len(x)), big)
+    assert emission_close(got[small], ref[small], lps)
+    # NaN rows stay NaN, rows after them are unaffected
+    x2 = x[:256].copy(); x2[5, 7] = np.nan
+    g2 = eng.emission(eng._to_dev(x2), gp, "h16").cpu().numpy()
+    assert np.all(np.isnan(g2[5])) and np.all(np.isfinite(np.delete(g2, 5, axis=0)))
+    # out-of-range model: no FP16 image, "h16" and "auto" run the TF32 kernel
+    means = np.stack([np.asarray(mn._core.mean, dtype=np.float64) for mn in normals])
+    us = np.stack([np.asarray(mn._core.cov_object._LP, dtype=np.float64) for mn in normals])
+    cst = np.zeros(len(normals))
+    assert pack_h16_image(means, us * 1e4, cst) is None
+    assert pack_h16_image(means, us, cst) is not None
+    gp_big = eng.pack_gauss_arrays(means, us * 1e4, cst)
+    assert gp_big.b_h16 is None
+    xs = eng._to_dev(x[small][:200] * np.float32(1e-4))
+    assert eng.torch.equal(eng.emission(xs, gp_big, "h16"), eng.emission(xs, gp_big, "tc"))
 
 
 # ------------------------------------------------------------------ a3 word Viterbi
@@ -163,7 +202,7 @@ def test_isolated_predict_end_to_end(eng, golden):
     mc = ModelCollection()
     mc._models = [models[w] for w in order]
     feats = [golden[f"iso_feat_{i}"] for i in range(22)]
-    for precision in ("fp32", "fp64", "tc"):
+    for precision in ("fp32", "fp64", "tc", "h16"):
         sc = mc.scores_batch(feats, precision)
         assert rel_close(sc, golden["iso_scores"], rtol=1e-4)
         assert mc.predict_batch(feats, precision) == [str(s) for s in golden["iso_labels"]]
@@ -216,7 +255,7 @@ def test_loop_decode_strings(eng, golden, name):
     feats = [golden[f"loop_feat_{i}"] for i in range(10)]
     want = [str(s) for s in golden[f"loop_strings_{name}"]]
     assert inf.predict_batch(feats, "fp64") == want
-    for precision in ("fp32", "tc"):
+    for precision in ("fp32", "tc", "h16"):
         got32 = inf.predict_batch(feats, precision)
         scores, paths = inf.viterbi_batch(feats, precision)
         assert rel_close(scores, golden[f"loop_scores_{name}"], rtol=1e-4)
@@ -572,3 +611,75 @@ def test_batched_training_equals_per_word_training(eng, golden):
         HiddenMarkovModelTrainable.from_data_batch({"1": [flat]}, num_of_states=3, max_iterations=3)
     with pytest.raises(HiddenMarkovModelTrainable.HMMTrainMeanFail):
         HiddenMarkovModelTrainable.from_data("1", [flat], num_of_states=3, max_iterations=3, isTqdm=False)
+
+
+@pytest.mark.gpu
+def test_host_buffer_decoder_matches_flat_decode(eng, golden):
+    """loe_decoder_decode_host (C pipeline, host buffers, no torch on the way) == decode_pcm_flat,
+    for float32 and int16 PCM, one chunk and several, pinned and pageable; scores and paths too."""
+    from loe_speech_recognition import MFCC
+    from loe_speech_recognition._decoder import PinnedBuffer
+    from loe_speech_recognition.hidden_markov_model import _penalty_args
+    from loe_speech_recognition.synthetic import string_corpus
+    inf = _loop_inference(golden)
+    utts, _ = string_corpus(seed=31, n_utts=24, n_digits=5)
+    utts.append(utts[0][:1700])                                   # 11 frames: close to the shortest allowed
+    off = np.concatenate(([0], np.cumsum([len(u) for u in utts]))).astype(np.int64)
+    flat = np.concatenate(utts).astype(np.float32)
+    for penalty in (np.log(0.005), -100):
+        inf._log_transition_probability_between_words = penalty
+        want = inf.decode_pcm_flat(flat, off)
+        assert inf.decode_pcm_host(flat, off) == want
+        assert inf.decode_pcm_host(flat, off, n_chunks=5) == want
+        assert inf.decode_pcm_host(flat.astype(np.int16), off, n_chunks=3) == inf.decode_pcm_flat(flat.astype(np.int16), off)
+    pin = PinnedBuffer(flat.shape[0], np.float32)
+    pin.array[:] = flat
+    assert inf.decode_pcm_host(pin.array, off, n_chunks=4) == want
+    sc, paths = inf.viterbi_batch(MFCC.batch(utts, 16000))
+    pen, f64 = _penalty_args(inf._log_transition_probability_between_words)
+    _, _, score, path = inf.native_decoder().decode(pin.array, off, pen, f64, -1, 32, 3, want_scores=True, want_path=True)
+    np.testing.assert_array_equal(score, sc)
+    np.testing.assert_array_equal(path, np.concatenate(paths))
+    pin.close()
+    assert inf.decode_pcm_host(flat[:0], off[:1]) == []
+    with pytest.raises(ValueError):
+        inf.decode_pcm_host(flat[:100], np.array([0, 100]))       # 1 frame < 9: the reference's savgol error
+    # a second model gets its own decoder; replacing the penalty needs no rebuild
+    assert inf.native_decoder() is inf.native_decoder()
+
+
+@pytest.mark.gpu
+def test_c_program_decodes_like_python(eng, golden, tmp_path):
+    """examples/decode_host.c, compiled with gcc against include/loe_b200.h and libloe_b200.so, decodes a
+    batch without Python in the process and prints the same word ids and scores."""
+    import os
+    import shutil
+    import subprocess
+    from loe_speech_recognition import _native
+    from loe_speech_recognition._decoder import write_blob
+    from loe_speech_recognition.hidden_markov_model import _penalty_args
+    from loe_speech_recognition.synthetic import string_corpus
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc on this box")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "decode_host")
+    lib_dir = os.path.dirname(_native.LIB_PATH)
+    subprocess.run(["gcc", "-O2", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "decode_host.c"),
+                    "-L", lib_dir, "-lloe_b200", f"-Wl,-rpath,{lib_dir}", "-o", exe], check=True)
+    inf = _loop_inference(golden)
+    utts, _ = string_corpus(seed=41, n_utts=12, n_digits=4)
+    off = np.concatenate(([0], np.cumsum([len(u) for u in utts]))).astype(np.int64)
+    flat = np.concatenate(utts).astype(np.int16)
+    pen, f64 = _penalty_args(inf._log_transition_probability_between_words)
+    dec = inf.native_decoder()
+    words, count, score, _ = dec.decode(flat, off, pen, f64, -1, 32, 3, want_scores=True)
+    blob = str(tmp_path / "batch.blob")
+    write_blob(blob, dec, flat, off, pen, f64, -1, 32, 3)
+    env = dict(os.environ)
+    out = subprocess.run([exe, blob], check=True, capture_output=True, text=True, env=env, timeout=120).stdout.strip().splitlines()
+    assert len(out) == len(utts)
+    for i, line in enumerate(out):
+        tok = line.split()
+        assert int(tok[0]) == count[i]
+        assert np.float32(tok[1]) == score[i]
+        assert [int(t) for t in tok[2:]] == words[i, :count[i]].tolist()
