@@ -25,13 +25,15 @@ constexpr int kFeat = 39;
 
 struct MfccTables {
     float hann[kNfft];                  // periodic Hann
-    float tw160_re[5 * 32], tw160_im[5 * 32];   // W_160^(lane*k1)
-    float w32_re[16], w32_im[16];       // W_32^m
+    float w160_re[kHalf], w160_im[kHalf];   // W_160^j
     float w320_re[kBins], w320_im[kBins];   // W_320^k
     float dct[kCeps * kMels];           // ortho DCT-II rows
 };
 
 __device__ MfccTables g_mfcc_tables;
+// kernel B reads these as FMA operands straight from the constant bank
+__constant__ float c_dct[kCeps * kMels];        // ortho DCT-II rows
+__constant__ float c_sg1[9], c_sg2[9];          // Savitzky-Golay first / second derivative taps, width 9
 static bool g_tables_ready[64] = {false};
 
 static int ensure_tables() {
@@ -41,16 +43,10 @@ static int ensure_tables() {
     static MfccTables h;
     const double PI = 3.14159265358979323846;
     for (int n = 0; n < kNfft; ++n) h.hann[n] = (float)(0.5 - 0.5 * cos(2.0 * PI * n / kNfft));
-    for (int k1 = 0; k1 < 5; ++k1)
-        for (int l = 0; l < 32; ++l) {
-            double a = -2.0 * PI * (double)(l * k1) / kHalf;
-            h.tw160_re[k1 * 32 + l] = (float)cos(a);
-            h.tw160_im[k1 * 32 + l] = (float)sin(a);
-        }
-    for (int m = 0; m < 16; ++m) {
-        double a = -2.0 * PI * m / 32.0;
-        h.w32_re[m] = (float)cos(a);
-        h.w32_im[m] = (float)sin(a);
+    for (int j = 0; j < kHalf; ++j) {
+        double a = -2.0 * PI * (double)j / kHalf;
+        h.w160_re[j] = (float)cos(a);
+        h.w160_im[j] = (float)sin(a);
     }
     for (int k = 0; k < kBins; ++k) {
         double a = -2.0 * PI * k / kNfft;
@@ -64,6 +60,14 @@ static int ensure_tables() {
             h.dct[k * kMels + n] = (float)v;
         }
     LOE_CUDA(cudaMemcpyToSymbol(g_mfcc_tables, &h, sizeof(h)));
+    LOE_CUDA(cudaMemcpyToSymbol(c_dct, h.dct, sizeof(h.dct)));
+    float sg1[9], sg2[9];
+    for (int q = -4; q <= 4; ++q) {
+        sg1[q + 4] = (float)q * (1.0f / 60.0f);
+        sg2[q + 4] = (float)(3 * q * q - 20) * (1.0f / 462.0f);
+    }
+    LOE_CUDA(cudaMemcpyToSymbol(c_sg1, sg1, sizeof(sg1)));
+    LOE_CUDA(cudaMemcpyToSymbol(c_sg2, sg2, sizeof(sg2)));
     if (dev < 64) g_tables_ready[dev] = true;
     return LOE_OK;
 }
@@ -71,22 +75,101 @@ static int ensure_tables() {
 // ------------------------------------------------------------------------------------------
 // Kernel A
 // ------------------------------------------------------------------------------------------
-constexpr int kWarpsA = 8;
-constexpr int kFramesPerBlockA = 64;
+// 320-point real FFT = 160-point complex FFT of z[n] = x[2n] + i x[2n+1] plus a real-input post-pass.
+// The 160-point transform is split 10 x 16 with every sub-transform held in the registers of ONE thread
+// (no shuffles; the only exchange is one pass through shared memory):
+//   n = 16 n1 + n2, k = k1 + 10 k2
+//   step 1, thread (frame, n2):  B[k1][n2] = W_160^(n2 k1) * sum_n1 z[16 n1 + n2] W_10^(n1 k1)      (10-point, 2 x 5 prime-factor)
+//   step 2, thread (frame, a):   Z[k1 + 10 k2] = sum_n2 B[k1][n2] W_16^(n2 k2) for k1 = a and k1 = 10 - a  (two radix-4 x 4 FFTs)
+// The post-pass pairs bin k = a + 10 k2 with 160 - k = (10 - a) + 10 (15 - k2): both live in the same thread.
+// a = 0 pairs with "k1 = 10", i.e. Z[10 + 10 k2]: step 1 stores an eleventh slot B[0][n2] W_16^n2, whose
+// transform is the k1 = 0 output rotated by one; a = 5 pairs with itself.  Six threads per frame run the same
+// code (a = 0 and a = 5 compute each of their pairs twice).
+// A warp works on batches of 10 frames: step 1 in 5 passes of 2 frames, step 2 in 2 passes of 5 frames
+// (30 lanes), then the mel filterbank one frame at a time with a filter per lane.
+constexpr int kWarpsA = 4;
+constexpr int kBatchA = 10;                 // frames per warp batch
+constexpr int kChunkA = 160;                // frames per CTA
+constexpr int kSlotPitch = 17;              // complex entries per slot (16 used): step 2's slot reads spread over the banks
+constexpr int kSlots = 11;
+constexpr int kFramePitch = 390;            // floats per frame: 11 x 17 x 2 = 374, padded to 6 mod 32 so that the
+                                            // power-spectrum stores of 5 frames x 6 lanes hit 30 different banks
 constexpr int kMelItMax = LOE_MEL_NA_MAX + LOE_MEL_NB_MAX;
+static_assert(kSlots * kSlotPitch * 2 <= kFramePitch, "frame area too small");
+static_assert(kBins + 3 + LOE_MEL_NA_MAX + 4 * LOE_MEL_NB_MAX <= kFramePitch, "power spectrum + table slack must fit the frame area");
 
 struct __align__(16) SmemA {
+    float area[kWarpsA][kBatchA * kFramePitch];     // per warp: step-1 slots, then the power spectra of the same frames
+    float2 wpost[6 * kSlotPitch];                   // W_320^(a + 10 k2) at [a * 17 + k2]
     float mel_w[kMelItMax * 32];
-    int mel_bin[kMelItMax * 32];
-    float zre[kWarpsA][kHalf];          // per-warp complex spectrum of the packed sequence (split planes:
-    float zim[kWarpsA][kHalf];          // the stride-5 transposing store is then bank-conflict free)
-    float pw[kWarpsA][kBins + 3 + LOE_MEL_NA_MAX + 4 * LOE_MEL_NB_MAX];   // per-warp power spectrum (+ slack: zero-weight
-                                        // table entries may point past the last bin)
 };
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+
+// forward 5-point DFT
+__device__ __forceinline__ void dft5(float2 v0, float2 v1, float2 v2, float2 v3, float2 v4, float2* y) {
+    const float C1 = 0.30901699437494745f, C2 = -0.80901699437494745f;   // cos(2pi/5), cos(4pi/5)
+    const float S1 = 0.95105651629515353f, S2 = 0.58778525229247314f;    // sin(2pi/5), sin(4pi/5)
+    const float2 t1 = cadd(v1, v4), t2 = cadd(v2, v3), t3 = csub(v1, v4), t4 = csub(v2, v3);
+    y[0] = make_float2(v0.x + t1.x + t2.x, v0.y + t1.y + t2.y);
+    const float2 m1 = make_float2(v0.x + C1 * t1.x + C2 * t2.x, v0.y + C1 * t1.y + C2 * t2.y);
+    const float2 m2 = make_float2(v0.x + C2 * t1.x + C1 * t2.x, v0.y + C2 * t1.y + C1 * t2.y);
+    const float2 q1 = make_float2(S1 * t3.x + S2 * t4.x, S1 * t3.y + S2 * t4.y);
+    const float2 q2 = make_float2(S2 * t3.x - S1 * t4.x, S2 * t3.y - S1 * t4.y);
+    y[1] = make_float2(m1.x + q1.y, m1.y - q1.x);
+    y[4] = make_float2(m1.x - q1.y, m1.y + q1.x);
+    y[2] = make_float2(m2.x + q2.y, m2.y - q2.x);
+    y[3] = make_float2(m2.x - q2.y, m2.y + q2.x);
+}
+
+// forward 10-point DFT, prime-factor (Good-Thomas) 2 x 5: no twiddles between the two stages.
+//   input n = (5 na + 2 nb) mod 10, output k = (5 ka + 6 kb) mod 10
+__device__ __forceinline__ void dft10(const float2* v, float2* out) {
+    float2 c0[5], c1[5];
+    dft5(v[0], v[2], v[4], v[6], v[8], c0);
+    dft5(v[5], v[7], v[9], v[1], v[3], c1);
+    out[0] = cadd(c0[0], c1[0]); out[5] = csub(c0[0], c1[0]);
+    out[6] = cadd(c0[1], c1[1]); out[1] = csub(c0[1], c1[1]);
+    out[2] = cadd(c0[2], c1[2]); out[7] = csub(c0[2], c1[2]);
+    out[8] = cadd(c0[3], c1[3]); out[3] = csub(c0[3], c1[3]);
+    out[4] = cadd(c0[4], c1[4]); out[9] = csub(c0[4], c1[4]);
+}
+
+__device__ __forceinline__ void dft4(float2 u0, float2 u1, float2 u2, float2 u3, float2& y0, float2& y1, float2& y2, float2& y3) {
+    const float2 s0 = cadd(u0, u2), s1 = csub(u0, u2), s2 = cadd(u1, u3), s3 = csub(u1, u3);
+    y0 = cadd(s0, s2);
+    y1 = make_float2(s1.x + s3.y, s1.y - s3.x);     // s1 - i s3
+    y2 = csub(s0, s2);
+    y3 = make_float2(s1.x - s3.y, s1.y + s3.x);     // s1 + i s3
+}
+
+// forward 16-point FFT in place, natural order in and out: n = 4a + b, k = c + 4d
+__device__ __forceinline__ void fft16(float2* v) {
+    const float CA = 0.92387953251128674f, SA = 0.38268343236508977f, R = 0.70710678118654752f;
+    float2 t[4][4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) dft4(v[b], v[4 + b], v[8 + b], v[12 + b], t[b][0], t[b][1], t[b][2], t[b][3]);
+    // twiddles W_16^(b c)
+    t[1][1] = cmul(t[1][1], make_float2(CA, -SA));                       // W^1
+    t[1][2] = make_float2(R * (t[1][2].x + t[1][2].y), R * (t[1][2].y - t[1][2].x));   // W^2 = (1 - i) / sqrt 2
+    t[1][3] = cmul(t[1][3], make_float2(SA, -CA));                       // W^3
+    t[2][1] = make_float2(R * (t[2][1].x + t[2][1].y), R * (t[2][1].y - t[2][1].x));   // W^2
+    t[2][2] = make_float2(t[2][2].y, -t[2][2].x);                        // W^4 = -i
+    t[2][3] = make_float2(R * (t[2][3].y - t[2][3].x), -R * (t[2][3].x + t[2][3].y));  // W^6 = (-1 - i) / sqrt 2
+    t[3][1] = cmul(t[3][1], make_float2(SA, -CA));                       // W^3
+    t[3][2] = make_float2(R * (t[3][2].y - t[3][2].x), -R * (t[3][2].x + t[3][2].y));  // W^6
+    t[3][3] = cmul(t[3][3], make_float2(-CA, SA));                       // W^9
+#pragma unroll
+    for (int c = 0; c < 4; ++c) dft4(t[0][c], t[1][c], t[2][c], t[3][c], v[c], v[c + 4], v[c + 8], v[c + 12]);
+}
+
+template <typename SampleT> struct Pair;
+template <> struct Pair<float> { using type = float2; };
+template <> struct Pair<short> { using type = short2; };
 
 // Mel filterbank as a lane-balanced table (host-built, see mfcc.py:mel_lane_tables):
 //   round A, iterations [0, na):      lane l accumulates filter l          (filters 0..31)
@@ -94,7 +177,7 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
 //                                     combined with two xor shuffles
 // entry (it, lane) = weight mel_w[it*32+lane] applied to power bin mel_bin[it*32+lane] (0-weight padding).
 template <typename SampleT, int NA, int NB>
-__global__ void __launch_bounds__(kWarpsA * 32)
+__global__ void __launch_bounds__(kWarpsA * 32, 3)
 mfcc_mel_kernel(const SampleT* __restrict__ pcm, const int64_t* __restrict__ pcm_off,
                 const int64_t* __restrict__ frm_off, const int32_t* __restrict__ mel_bin,
                 const float* __restrict__ mel_w, int na_rt, int nb_rt,
@@ -106,140 +189,141 @@ mfcc_mel_kernel(const SampleT* __restrict__ pcm, const int64_t* __restrict__ pcm
     const int u = blockIdx.x;
     const int64_t f0 = frm_off[u];
     const int T = (int)(frm_off[u + 1] - f0);
-    const int t_begin = blockIdx.y * kFramesPerBlockA;
+    const int t_begin = blockIdx.y * kChunkA;
     if (t_begin >= T) return;
-    const int t_end = min(T, t_begin + kFramesPerBlockA);
+    const int t_end = min(T, t_begin + kChunkA);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr unsigned FULL = 0xffffffffu;
 
-    for (int i = tid; i < (na + nb) * 32; i += blockDim.x) { sm.mel_w[i] = mel_w[i]; sm.mel_bin[i] = mel_bin[i]; }
-    // per-lane constants, fixed for every frame: window taps, 5x32 twiddles, shuffle-FFT twiddles,
-    // real-input post-pass twiddles
-    float hw[10];
-    float2 tw[5], ws[4], wp[5];
-#pragma unroll
-    for (int n1 = 0; n1 < 5; ++n1) {
-        const int n = 2 * (32 * n1 + lane);
-        hw[2 * n1] = g_mfcc_tables.hann[n];
-        hw[2 * n1 + 1] = g_mfcc_tables.hann[n + 1];
-        tw[n1] = make_float2(g_mfcc_tables.tw160_re[n1 * 32 + lane], g_mfcc_tables.tw160_im[n1 * 32 + lane]);
-        const int k = lane + 32 * n1;
-        wp[n1] = make_float2(g_mfcc_tables.w320_re[k], g_mfcc_tables.w320_im[k]);
+    for (int i = tid; i < (na + nb) * 32; i += kWarpsA * 32) sm.mel_w[i] = mel_w[i];
+    for (int i = tid; i < 6 * 16; i += kWarpsA * 32) {
+        const int k = (i >> 4) + 10 * (i & 15);                  // a + 10 k2 <= 155
+        sm.wpost[(i >> 4) * kSlotPitch + (i & 15)] = make_float2(g_mfcc_tables.w320_re[k], g_mfcc_tables.w320_im[k]);
     }
-    // stage h = 16, 8, 4, 2: lanes with bit h set multiply by W_{2h}^(lane & (h-1)), the others by 1;
-    // sg = -1 for the upper lane of a butterfly (o - y), +1 for the lower (y + o)
-    float sg[5];
+    // the frame areas start out finite: zero-weight filterbank entries may read slack words no step writes
+    for (int i = tid; i < kWarpsA * kBatchA * kFramePitch; i += kWarpsA * 32) (&sm.area[0][0])[i] = 0.f;
+
+    // per-lane constants of step 1 (thread = (frame parity, n2)): window taps and W_160^(n2 k1)
+    const int n2 = lane & 15, fl = lane >> 4;
+    float hw[20];
+    float2 tw[10];
 #pragma unroll
-    for (int st = 0; st < 5; ++st) {
-        const int h = 16 >> st;
-        const bool upper = (lane & h) != 0;
-        sg[st] = upper ? -1.f : 1.f;
-        if (st < 4) {
-            const int j = (lane & (h - 1)) * (16 / h);
-            ws[st] = upper ? make_float2(g_mfcc_tables.w32_re[j], g_mfcc_tables.w32_im[j]) : make_float2(1.f, 0.f);
-        }
+    for (int n1 = 0; n1 < 10; ++n1) {
+        hw[2 * n1] = g_mfcc_tables.hann[32 * n1 + 2 * n2];
+        hw[2 * n1 + 1] = g_mfcc_tables.hann[32 * n1 + 2 * n2 + 1];
+        tw[n1] = make_float2(g_mfcc_tables.w160_re[n2 * n1], g_mfcc_tables.w160_im[n2 * n1]);     // tw[0] = 1 is not used
     }
+    const float2 w16 = make_float2(g_mfcc_tables.w160_re[10 * n2], g_mfcc_tables.w160_im[10 * n2]);   // W_16^n2
+    // step 2 (thread = (frame of five, a))
+    const int a = lane % 6, fl5 = lane / 6;
+    const int binA = mel_bin[lane], binB = mel_bin[na * 32 + lane];    // filters own CONSECUTIVE bins
     __syncthreads();
 
     const int64_t s0 = pcm_off[u];
     const int64_t n_samples = pcm_off[u + 1] - s0;
     const SampleT* __restrict__ x = pcm + s0;
-    const int brev = (int)(__brev((unsigned)lane) >> 27);
+    // two samples per load when the utterance starts on an even sample (the pair is then naturally aligned)
+    const bool pair_ok = ((s0 & 1) == 0) && ((reinterpret_cast<uintptr_t>(pcm) & (2 * sizeof(SampleT) - 1)) == 0);
+    using PairT = typename Pair<SampleT>::type;
+    float* area = sm.area[warp];
     float vmax = 0.f;
 
-    const float C1 = 0.30901699437494745f, C2 = -0.80901699437494745f;   // cos(2pi/5), cos(4pi/5)
-    const float S1 = 0.95105651629515353f, S2 = 0.58778525229247314f;    // sin(2pi/5), sin(4pi/5)
-    float* zre = sm.zre[warp];
-    float* zim = sm.zim[warp];
-    float* pw = sm.pw[warp];
-    // filters own CONSECUTIVE bins: round A lane l reads bins binA + it, round B bins binB + 4*it
-    const int binA = sm.mel_bin[lane], binB = sm.mel_bin[na * 32 + lane];
-
-    for (int t = t_begin + warp; t < t_end; t += kWarpsA) {
-        // ---- load + window: z[n] = x[2n] + i x[2n+1], n = 32*n1 + lane
-        float2 v[5];
-        const int64_t base = (int64_t)kHop * t - kHalf;
-        if (base >= 0 && base + kNfft <= n_samples) {          // interior frame: no bounds checks
-            const SampleT* __restrict__ xb = x + base + 2 * lane;
+    for (int tb = t_begin + warp * kBatchA; tb < t_end; tb += kWarpsA * kBatchA) {
+        // ---------------- step 1: load, window, 10-point DFTs, twiddle, store the 11 slots
+#pragma unroll 1
+        for (int p = 0; p < kBatchA / 2; ++p) {
+            const int fb = 2 * p + fl, t = tb + fb;
+            if (t < t_end) {
+                float2 v[10];
+                const int64_t base = (int64_t)kHop * t - kHalf;
+                if (base >= 0 && base + kNfft <= n_samples) {          // interior frame: no bounds checks
+                    const SampleT* __restrict__ xb = x + base + 2 * n2;
+                    if (pair_ok) {
 #pragma unroll
-            for (int n1 = 0; n1 < 5; ++n1)
-                v[n1] = make_float2(__fmul_rn((float)__ldg(xb + 64 * n1), hw[2 * n1]), __fmul_rn((float)__ldg(xb + 64 * n1 + 1), hw[2 * n1 + 1]));
-        } else {
+                        for (int n1 = 0; n1 < 10; ++n1) {
+                            const PairT s = __ldg(reinterpret_cast<const PairT*>(xb + 32 * n1));
+                            v[n1] = make_float2(__fmul_rn((float)s.x, hw[2 * n1]), __fmul_rn((float)s.y, hw[2 * n1 + 1]));
+                        }
+                    } else {
 #pragma unroll
-            for (int n1 = 0; n1 < 5; ++n1) {
-                const int64_t i0 = base + 2 * (32 * n1 + lane), i1 = i0 + 1;
-                const float a = (i0 >= 0 && i0 < n_samples) ? (float)__ldg(x + i0) : 0.f;
-                const float b = (i1 >= 0 && i1 < n_samples) ? (float)__ldg(x + i1) : 0.f;
-                v[n1] = make_float2(__fmul_rn(a, hw[2 * n1]), __fmul_rn(b, hw[2 * n1 + 1]));   // never contracted: f32 and s16 inputs agree bit for bit
+                        for (int n1 = 0; n1 < 10; ++n1)
+                            v[n1] = make_float2(__fmul_rn((float)__ldg(xb + 32 * n1), hw[2 * n1]),
+                                                __fmul_rn((float)__ldg(xb + 32 * n1 + 1), hw[2 * n1 + 1]));
+                    }
+                } else {
+#pragma unroll
+                    for (int n1 = 0; n1 < 10; ++n1) {
+                        const int64_t i0 = base + 32 * n1 + 2 * n2, i1 = i0 + 1;
+                        const float sa = (i0 >= 0 && i0 < n_samples) ? (float)__ldg(x + i0) : 0.f;
+                        const float sb = (i1 >= 0 && i1 < n_samples) ? (float)__ldg(x + i1) : 0.f;
+                        v[n1] = make_float2(__fmul_rn(sa, hw[2 * n1]), __fmul_rn(sb, hw[2 * n1 + 1]));   // never contracted: f32 and s16 inputs agree bit for bit
+                    }
+                }
+                float2 y[10];
+                dft10(v, y);
+                float2* slot = reinterpret_cast<float2*>(area + fb * kFramePitch) + n2;
+                slot[0] = y[0];
+                slot[10 * kSlotPitch] = cmul(y[0], w16);
+#pragma unroll
+                for (int k1 = 1; k1 < 10; ++k1) slot[k1 * kSlotPitch] = cmul(y[k1], tw[k1]);
             }
         }
-        // ---- radix-5 over n1 (forward transform), then twiddle W_160^(lane*k1)
-        float2 y[5];
-        {
-            float2 t1 = make_float2(v[1].x + v[4].x, v[1].y + v[4].y);
-            float2 t2 = make_float2(v[2].x + v[3].x, v[2].y + v[3].y);
-            float2 t3 = make_float2(v[1].x - v[4].x, v[1].y - v[4].y);
-            float2 t4 = make_float2(v[2].x - v[3].x, v[2].y - v[3].y);
-            y[0] = make_float2(v[0].x + t1.x + t2.x, v[0].y + t1.y + t2.y);
-            float2 m1 = make_float2(v[0].x + C1 * t1.x + C2 * t2.x, v[0].y + C1 * t1.y + C2 * t2.y);
-            float2 m2 = make_float2(v[0].x + C2 * t1.x + C1 * t2.x, v[0].y + C2 * t1.y + C1 * t2.y);
-            float2 q1 = make_float2(S1 * t3.x + S2 * t4.x, S1 * t3.y + S2 * t4.y);
-            float2 q2 = make_float2(S2 * t3.x - S1 * t4.x, S2 * t3.y - S1 * t4.y);
-            y[1] = make_float2(m1.x + q1.y, m1.y - q1.x);
-            y[4] = make_float2(m1.x - q1.y, m1.y + q1.x);
-            y[2] = make_float2(m2.x + q2.y, m2.y - q2.x);
-            y[3] = make_float2(m2.x - q2.y, m2.y + q2.x);
-        }
+        __syncwarp();
+        // ---------------- step 2: two 16-point FFTs per thread, real-input post-pass, power spectrum
+#pragma unroll 1
+        for (int p = 0; p < 2; ++p) {
+            const int fb = 5 * p + fl5;
+            const bool active = lane < 30 && tb + fb < t_end;
+            float* fa = area + fb * kFramePitch;
+            float2 za[16], zb[16];
+            if (active) {
+                const float2* sa = reinterpret_cast<const float2*>(fa) + a * kSlotPitch;
+                const float2* sb = reinterpret_cast<const float2*>(fa) + (10 - a) * kSlotPitch;
 #pragma unroll
-        for (int k1 = 1; k1 < 5; ++k1) y[k1] = cmul(y[k1], tw[k1]);
-        // ---- 32-point DIF FFT across lanes for each k1 (output in bit-reversed lane order):
-        //      every lane computes (sg*y + o) * w with its own sg, w -- no divergence
+                for (int i = 0; i < 16; ++i) { za[i] = sa[i]; zb[i] = sb[i]; }
+            }
+            __syncwarp();                                   // the slots of these frames are in registers: their areas take the power spectra
+            if (active) {
+                fft16(za);
+                fft16(zb);
+                const float2* wp = sm.wpost + a * kSlotPitch;
 #pragma unroll
-        for (int st = 0; st < 5; ++st) {
-            const int h = 16 >> st;
-#pragma unroll
-            for (int k1 = 0; k1 < 5; ++k1) {
-                const float ox = __shfl_xor_sync(FULL, y[k1].x, h);
-                const float oy = __shfl_xor_sync(FULL, y[k1].y, h);
-                const float2 a = make_float2(fmaf(sg[st], y[k1].x, ox), fmaf(sg[st], y[k1].y, oy));
-                y[k1] = (st < 4) ? cmul(a, ws[st < 4 ? st : 0]) : a;
+                for (int k2 = 0; k2 < 16; ++k2) {
+                    // X[k] = (e + w o) / 2, X[160 - k] = conj(e - w o) / 2 with A = Z[k], B = Z[160 - k]
+                    const float2 A = za[k2], B = zb[15 - k2];
+                    const float2 e = make_float2(A.x + B.x, A.y - B.y);
+                    const float2 o = make_float2(A.y + B.y, B.x - A.x);
+                    const float2 wo = cmul(wp[k2], o);
+                    const float2 xp = cadd(e, wo), xm = csub(e, wo);
+                    const int k = a + 10 * k2;
+                    fa[k] = 0.25f * (xp.x * xp.x + xp.y * xp.y);
+                    fa[kNfft / 2 - k] = 0.25f * (xm.x * xm.x + xm.y * xm.y);
+                }
             }
         }
-#pragma unroll
-        for (int k1 = 0; k1 < 5; ++k1) { zre[k1 + 5 * brev] = y[k1].x; zim[k1 + 5 * brev] = y[k1].y; }
         __syncwarp();
-        // ---- real-input post-pass + power spectrum: bins k = lane + 32*i, i < 5 (k = 0..159), then k = 160
+        // ---------------- mel filterbank (lane-balanced table), one frame at a time
+        const int nf = min(kBatchA, t_end - tb);
+#pragma unroll 1
+        for (int fb = 0; fb < nf; ++fb) {
+            const float* pw = area + fb * kFramePitch;
+            float accA = 0.f, accB = 0.f;
+            if (NA > 0) {
 #pragma unroll
-        for (int i = 0; i < 5; ++i) {
-            const int k = lane + 32 * i;
-            const int kb = (k == 0) ? 0 : kHalf - k;
-            const float2 A = make_float2(zre[k], zim[k]);
-            const float2 Bc = make_float2(zre[kb], zim[kb]);
-            const float2 E = make_float2(0.5f * (A.x + Bc.x), 0.5f * (A.y - Bc.y));
-            const float2 O = make_float2(0.5f * (A.y + Bc.y), -0.5f * (A.x - Bc.x));
-            const float xr = E.x + O.x * wp[i].x - O.y * wp[i].y;
-            const float xi = E.y + O.x * wp[i].y + O.y * wp[i].x;
-            pw[k] = xr * xr + xi * xi;
+                for (int it = 0; it < NA; ++it) accA = fmaf(sm.mel_w[it * 32 + lane], pw[binA + it], accA);
+#pragma unroll
+                for (int it = 0; it < NB; ++it) accB = fmaf(sm.mel_w[(NA + it) * 32 + lane], pw[binB + 4 * it], accB);
+            } else {
+                for (int it = 0; it < na; ++it) accA = fmaf(sm.mel_w[it * 32 + lane], pw[binA + it], accA);
+                for (int it = 0; it < nb; ++it) accB = fmaf(sm.mel_w[(na + it) * 32 + lane], pw[binB + 4 * it], accB);
+            }
+            accB += __shfl_xor_sync(FULL, accB, 1);
+            accB += __shfl_xor_sync(FULL, accB, 2);
+            float* mo = mel_out + (f0 + tb + fb) * kMels;
+            mo[lane] = accA;
+            if ((lane & 3) == 0) mo[32 + (lane >> 2)] = accB;
+            vmax = fmaxf(vmax, fmaxf(accA, accB));
         }
-        if (lane == 0) { const float xn = zre[0] - zim[0]; pw[kHalf] = xn * xn; }   // Nyquist bin
-        __syncwarp();
-        // ---- mel filterbank (lane-balanced table)
-        float accA = 0.f, accB = 0.f;
-        if (NA > 0) {
-#pragma unroll
-            for (int it = 0; it < NA; ++it) accA = fmaf(sm.mel_w[it * 32 + lane], pw[binA + it], accA);
-#pragma unroll
-            for (int it = 0; it < NB; ++it) accB = fmaf(sm.mel_w[(NA + it) * 32 + lane], pw[binB + 4 * it], accB);
-        } else {
-            for (int it = 0; it < na; ++it) accA = fmaf(sm.mel_w[it * 32 + lane], pw[binA + it], accA);
-            for (int it = 0; it < nb; ++it) accB = fmaf(sm.mel_w[(na + it) * 32 + lane], pw[binB + 4 * it], accB);
-        }
-        accB += __shfl_xor_sync(FULL, accB, 1);
-        accB += __shfl_xor_sync(FULL, accB, 2);
-        float* mo = mel_out + (f0 + t) * kMels;
-        mo[lane] = accA;
-        if ((lane & 3) == 0) mo[32 + (lane >> 2)] = accB;
-        vmax = fmaxf(vmax, fmaxf(accA, accB));
         __syncwarp();
     }
 #pragma unroll
@@ -250,16 +334,23 @@ mfcc_mel_kernel(const SampleT* __restrict__ pcm, const int64_t* __restrict__ pcm
 // ------------------------------------------------------------------------------------------
 // Kernel B
 // ------------------------------------------------------------------------------------------
-constexpr int kTileB = 64;
-constexpr int kHaloB = kTileB + 8;
+// One thread per frame.  A CTA takes 120 output frames of one utterance plus the 8 halo frames the width-9
+// delta filters reach: 128 rows of mel energies are converted to dB while they are copied (coalesced) into
+// shared memory; each thread then pulls its row into registers and runs the 13 x 40 DCT against the constant
+// bank (the coefficient is an immediate-like operand of the FMA: no load instruction), normalises the static
+// block in registers, and the deltas read the cepstra of the neighbouring rows from shared memory.
+constexpr int kTileB = 120;
+constexpr int kRowsB = kTileB + 8;      // = threads per CTA
+constexpr int kMelPitch = kMels + 1;    // odd pitches: row-per-lane accesses are bank-conflict free
+constexpr int kCepPitch = kCeps;
+constexpr int kOutPitch = kFeat;
 
-__global__ void __launch_bounds__(256)
+
+__global__ void __launch_bounds__(kRowsB)
 mfcc_ceps_kernel(const float* __restrict__ mel, const float* __restrict__ utt_max,
                  const int64_t* __restrict__ frm_off, float* __restrict__ feat) {
-    __shared__ float s_lm[kHaloB][kMels + 1];
-    __shared__ float s_c[kHaloB][kCeps + 1];
-    __shared__ float s_dct[kCeps][kMels + 1];
-    __shared__ float s_out[kTileB * kFeat];
+    __shared__ float s_lm[kRowsB * kMelPitch];  // dB mel rows; reused for the output tile (kTileB * 39 floats)
+    __shared__ float s_c[kRowsB * kCepPitch];
     const int u = blockIdx.x;
     const int64_t f0 = frm_off[u];
     const int T = (int)(frm_off[u + 1] - f0);
@@ -269,56 +360,66 @@ mfcc_ceps_kernel(const float* __restrict__ mel, const float* __restrict__ utt_ma
     const int tid = threadIdx.x;
     const int g0 = max(0, min(t0 - 4, T - 9));
     const int g1 = min(T - 1, max(t1 + 3, 8));
-    const int ng = g1 - g0 + 1;
+    const int ng = g1 - g0 + 1;                 // <= kRowsB
 
-    for (int i = tid; i < kCeps * kMels; i += blockDim.x) s_dct[i / kMels][i % kMels] = g_mfcc_tables.dct[i];
     const float ref_db = 10.0f * log10f(fmaxf(1e-10f, utt_max[u]));
-    for (int i = tid; i < ng * kMels; i += blockDim.x) {
+    const float* __restrict__ src = mel + (f0 + g0) * kMels;
+    for (int i = tid; i < ng * kMels; i += kRowsB) {
         const int j = i / kMels, m = i - j * kMels;
-        const float v = mel[(f0 + g0 + j) * kMels + m];
-        float db = 10.0f * log10f(fmaxf(1e-10f, v)) - ref_db;
-        s_lm[j][m] = fmaxf(db, -80.0f);
+        const float db = 10.0f * log10f(fmaxf(1e-10f, __ldg(src + i))) - ref_db;
+        s_lm[j * kMelPitch + m] = fmaxf(db, -80.0f);
     }
     __syncthreads();
-    for (int i = tid; i < ng * kCeps; i += blockDim.x) {
-        const int j = i / kCeps, k = i - j * kCeps;
-        float acc = 0.f;
-#pragma unroll 8
-        for (int m = 0; m < kMels; ++m) acc = fmaf(s_dct[k][m], s_lm[j][m], acc);
-        s_c[j][k] = acc;
-    }
-    __syncthreads();
-    const int nt = t1 - t0;
-    for (int i = tid; i < nt * kCeps; i += blockDim.x) {
-        const int j = i / kCeps, k = i - j * kCeps;
-        const int t = t0 + j;
-        const int c = min(max(t, 4), T - 5) - g0;
-        float d1 = 0.f, d2 = 0.f;
+    float c[kCeps];
+    if (tid < ng) {
+        float lm[kMels];
 #pragma unroll
-        for (int q = -4; q <= 4; ++q) {
-            const float cv = s_c[c + q][k];
-            d1 = fmaf((float)q * (1.0f / 60.0f), cv, d1);
-            d2 = fmaf((float)(3 * q * q - 20) * (1.0f / 462.0f), cv, d2);
+        for (int m = 0; m < kMels; ++m) lm[m] = s_lm[tid * kMelPitch + m];
+#pragma unroll
+        for (int k = 0; k < kCeps; ++k) {
+            float acc = 0.f;
+#pragma unroll
+            for (int m = 0; m < kMels; ++m) acc = fmaf(c_dct[k * kMels + m], lm[m], acc);
+            c[k] = acc;
+            s_c[tid * kCepPitch + k] = acc;
         }
-        s_out[j * kFeat + kCeps + k] = d1;
-        s_out[j * kFeat + 2 * kCeps + k] = d2;
     }
-    for (int j = tid; j < nt; j += blockDim.x) {
-        const int r = t0 + j - g0;
+    __syncthreads();                            // cepstra visible; every read of s_lm is done
+    float* s_out = s_lm;
+    const int r = tid - (t0 - g0);              // output frame handled by this thread: t0 + r
+    if (r >= 0 && r < t1 - t0) {
         float mean = 0.f;
 #pragma unroll
-        for (int k = 0; k < kCeps; ++k) mean += s_c[r][k];
+        for (int k = 0; k < kCeps; ++k) mean += c[k];
         mean *= (1.0f / kCeps);
         float var = 0.f;
 #pragma unroll
-        for (int k = 0; k < kCeps; ++k) { const float d = s_c[r][k] - mean; var = fmaf(d, d, var); }
+        for (int k = 0; k < kCeps; ++k) { const float d = c[k] - mean; var = fmaf(d, d, var); }
         const float inv = 1.0f / (sqrtf(var * (1.0f / kCeps)) + 1e-8f);
+        float* o = s_out + r * kOutPitch;
 #pragma unroll
-        for (int k = 0; k < kCeps; ++k) s_out[j * kFeat + k] = (s_c[r][k] - mean) * inv;
+        for (int k = 0; k < kCeps; ++k) o[k] = (c[k] - mean) * inv;
+        const int cc = min(max(t0 + r, 4), T - 5) - g0;      // centre row of the delta window
+        float d1[kCeps], d2[kCeps];
+#pragma unroll
+        for (int k = 0; k < kCeps; ++k) { d1[k] = 0.f; d2[k] = 0.f; }
+#pragma unroll
+        for (int q = -4; q <= 4; ++q) {
+            const float* row = s_c + (cc + q) * kCepPitch;
+#pragma unroll
+            for (int k = 0; k < kCeps; ++k) {
+                const float cv = row[k];
+                d1[k] = fmaf(c_sg1[q + 4], cv, d1[k]);
+                d2[k] = fmaf(c_sg2[q + 4], cv, d2[k]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kCeps; ++k) { o[kCeps + k] = d1[k]; o[2 * kCeps + k] = d2[k]; }
     }
     __syncthreads();
+    const int nt = t1 - t0;
     float* __restrict__ dst = feat + (f0 + t0) * kFeat;
-    for (int i = tid; i < nt * kFeat; i += blockDim.x) dst[i] = s_out[i];
+    for (int i = tid; i < nt * kFeat; i += kRowsB) dst[i] = s_out[i];
 }
 
 }  // namespace loe
@@ -342,21 +443,22 @@ static int mfcc_launch(const void* pcm_dev, int pcm_format, const int64_t* pcm_o
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     if (phases & 1) {
         LOE_CUDA(cudaMemsetAsync(utt_max_dev, 0, sizeof(float) * (size_t)n_utt, s));
-        static_assert(sizeof(SmemA) <= 48 * 1024, "kernel A must fit the default dynamic shared memory limit");
-        dim3 ga((unsigned)n_utt, (unsigned)((max_frames + kFramesPerBlockA - 1) / kFramesPerBlockA));
+        dim3 ga((unsigned)n_utt, (unsigned)((max_frames + kChunkA - 1) / kChunkA));
         const bool k16 = (mel_na == 11 && mel_nb == 5);      // the 16 kHz table of every reference call site
+        // the kernel's shared memory (slots of 4 warps x 10 frames) exceeds the 48 KB default: opt in, once per device
 #define LOE_MEL_LAUNCH(T, A, B)                                                                                          \
+        LOE_CUDA(cudaFuncSetAttribute(mfcc_mel_kernel<T, A, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemA))); \
         mfcc_mel_kernel<T, A, B><<<ga, kWarpsA * 32, sizeof(SmemA), s>>>((const T*)pcm_dev, pcm_off_dev, frm_off_dev, mel_bin_dev, \
                                                                         mel_w_dev, mel_na, mel_nb, mel_ws_dev, utt_max_dev)
-        if (pcm_format == LOE_PCM_F32) { if (k16) LOE_MEL_LAUNCH(float, 11, 5); else LOE_MEL_LAUNCH(float, 0, 0); }
-        else if (pcm_format == LOE_PCM_S16) { if (k16) LOE_MEL_LAUNCH(short, 11, 5); else LOE_MEL_LAUNCH(short, 0, 0); }
+        if (pcm_format == LOE_PCM_F32) { if (k16) { LOE_MEL_LAUNCH(float, 11, 5); } else { LOE_MEL_LAUNCH(float, 0, 0); } }
+        else if (pcm_format == LOE_PCM_S16) { if (k16) { LOE_MEL_LAUNCH(short, 11, 5); } else { LOE_MEL_LAUNCH(short, 0, 0); } }
         else { set_error("unknown pcm_format %d", pcm_format); return LOE_ERR_VALUE; }
 #undef LOE_MEL_LAUNCH
         LOE_LAUNCH_CHECK("mfcc_mel_kernel");
     }
     if (phases & 2) {
         dim3 gb((unsigned)n_utt, (unsigned)((max_frames + kTileB - 1) / kTileB));
-        mfcc_ceps_kernel<<<gb, 256, 0, s>>>(mel_ws_dev, utt_max_dev, frm_off_dev, feat_dev);
+        mfcc_ceps_kernel<<<gb, kRowsB, 0, s>>>(mel_ws_dev, utt_max_dev, frm_off_dev, feat_dev);
         LOE_LAUNCH_CHECK("mfcc_ceps_kernel");
     }
     return LOE_OK;
