@@ -45,7 +45,7 @@ PENALTY = -100                                                              # pr
 FLOPS_PER_FRAME = 2 * 40 * 39 * 58                                          # 2(D+1)D S, S = 58
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at the default workload (10 000 utterances, 3.84 M frames),
 # from the committed `ncu --set full` capture (profiles/r1f_kernels.txt); None = not captured
-NCU_TRAFFIC = {"mfcc_mel": 3098969000, "mfcc_ceps": 1249852000, "emission_tc": 2368057000, "viterbi": 902000000}
+NCU_TRAFFIC = {"mfcc_mel": 3098969000, "mfcc_ceps": 1249852000, "emission_tc": 2368057000, "emission_h16": 2136338000, "viterbi": 902000000}
 
 
 def golden_params():
@@ -195,6 +195,8 @@ def impl_b200(args):
     inf = HiddenMarkovModelInference.from_models(models)
     inf._log_transition_probability_between_words = PENALTY
     precision = args.precision
+    if precision == "auto":                 # what the package picks for this model (3xFP16 when its range allows, else 3xTF32)
+        precision = "h16" if inf._packs()[0].b_h16 is not None else "tc"
 
     utts, truth = make_corpus(100 + rank, args.utts, args.pool)
     n = len(utts)
@@ -418,7 +420,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--utts", type=int, default=10000, help="utterances per GPU")
     ap.add_argument("--pool", type=int, default=500, help="distinct synthetic utterances (tiled to --utts)")
-    ap.add_argument("--precision", default=os.environ.get("LOE_B200_EMISSION", "tc"), choices=["fp32", "fp64", "tc", "h16"])
+    ap.add_argument("--precision", default=os.environ.get("LOE_B200_EMISSION", "auto"), choices=["auto", "fp32", "fp64", "tc", "h16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

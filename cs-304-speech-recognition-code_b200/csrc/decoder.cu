@@ -34,6 +34,7 @@ struct Decoder {
     // model
     int mel_na = 0, mel_nb = 0, n_states = 0, n_pos = 0, n_ends = 0;
     int32_t* d_mel_bin = nullptr; float* d_mel_w = nullptr; float* d_b = nullptr; float* d_cst = nullptr;
+    void* d_b_h16 = nullptr;            // optional 3xFP16 image (loe_decoder_set_h16): then the FP16 tensor-core kernel scores
     int32_t* d_tr_off = nullptr; int32_t* d_col = nullptr; float* d_band = nullptr; uint8_t* d_flags = nullptr;
     int32_t* d_word = nullptr; int32_t* d_word_lo = nullptr;
     // workspace
@@ -64,7 +65,7 @@ static void destroy(Decoder* d) {
     if (d->h_out) cudaFreeHost(d->h_out);
     DevBuf* bufs[] = {&d->mel, &d->feat, &d->scores, &d->path, &d->umax, &d->words, &d->count, &d->best, &d->best_score, &d->bp};
     for (DevBuf* b : bufs) b->release();
-    void* tabs[] = {d->d_mel_bin, d->d_mel_w, d->d_b, d->d_cst, d->d_tr_off, d->d_col, d->d_band, d->d_flags, d->d_word, d->d_word_lo};
+    void* tabs[] = {d->d_b_h16, d->d_mel_bin, d->d_mel_w, d->d_b, d->d_cst, d->d_tr_off, d->d_col, d->d_band, d->d_flags, d->d_word, d->d_word_lo};
     for (void* t : tabs) if (t) cudaFree(t);
     if (d->copy) cudaStreamDestroy(d->copy);
     if (d->comp) cudaStreamDestroy(d->comp);
@@ -110,6 +111,19 @@ extern "C" int loe_decoder_create(int device, const int32_t* mel_bin_host, const
     LOE_TRY(upload(&d->d_word_lo, word_lo_host, (size_t)n_pos));
 #undef LOE_TRY
     *out = d;
+    return LOE_OK;
+}
+
+extern "C" int loe_decoder_set_h16(void* dec, const void* b_h16_host) {
+    using namespace loe;
+    Decoder* d = reinterpret_cast<Decoder*>(dec);
+    if (!d) { set_error("decoder is NULL"); return LOE_ERR_VALUE; }
+    LOE_CUDA(cudaSetDevice(d->device));
+    if (d->d_b_h16) { cudaFree(d->d_b_h16); d->d_b_h16 = nullptr; }
+    if (!b_h16_host) return LOE_OK;
+    const size_t bytes = (size_t)loe_emission_tc_tiles(d->n_states) * (size_t)loe_emission_h16_tile_bytes();
+    LOE_CUDA(cudaMalloc(&d->d_b_h16, bytes));
+    LOE_CUDA(cudaMemcpy(d->d_b_h16, b_h16_host, bytes, cudaMemcpyHostToDevice));
     return LOE_OK;
 }
 
@@ -199,8 +213,11 @@ extern "C" int loe_decoder_decode_host(void* dec, const void* pcm_host, int pcm_
         const int64_t* d_frm_off = d_pcm_off + (n + 1);
         if ((st = loe_mfcc_dev(d->pcm[set].p, pcm_format, d_pcm_off, d_frm_off, n, F, max_frames, min_frames, d->d_mel_bin, d->d_mel_w,
                                d->mel_na, d->mel_nb, (float*)d->mel.p, (float*)d->umax.p, (float*)d->feat.p, d->comp)) != LOE_OK) return st;
-        if ((st = loe_emission_tc_dev((const float*)d->feat.p, F, 39, d->d_b, d->d_cst, d->n_states, (float*)d->scores.p, d->n_states,
-                                      d->comp)) != LOE_OK) return st;
+        st = d->d_b_h16 ? loe_emission_h16_dev((const float*)d->feat.p, F, 39, d->d_b_h16, d->d_cst, d->n_states, (float*)d->scores.p,
+                                               d->n_states, d->comp)
+                        : loe_emission_tc_dev((const float*)d->feat.p, F, 39, d->d_b, d->d_cst, d->n_states, (float*)d->scores.p,
+                                              d->n_states, d->comp);
+        if (st != LOE_OK) return st;
         if ((st = loe_viterbi_dev((const float*)d->scores.p, d->n_states, d_frm_off, n, max_frames, d->d_tr_off, d->d_col, d->d_band,
                                   d->d_flags, d->n_pos, nullptr, 1, penalty, penalty_f64, (int8_t*)d->path.p, nullptr, d->n_ends,
                                   (int32_t*)d->best.p, (float*)d->best_score.p, bp_needed ? (uint8_t*)d->bp.p : nullptr,

@@ -89,7 +89,7 @@ static int ensure_tables() {
 // (30 lanes), then the mel filterbank one frame at a time with a filter per lane.
 constexpr int kWarpsA = 4;
 constexpr int kBatchA = 10;                 // frames per warp batch
-constexpr int kChunkA = 160;                // frames per CTA
+constexpr int kMinChunkA = 160;             // frames per CTA: at least this many (a multiple of the 40 frames one round of the 4 warps takes)
 constexpr int kSlotPitch = 17;              // complex entries per slot (16 used): step 2's slot reads spread over the banks
 constexpr int kSlots = 11;
 constexpr int kFramePitch = 390;            // floats per frame: 11 x 17 x 2 = 374, padded to 6 mod 32 so that the
@@ -180,7 +180,7 @@ template <typename SampleT, int NA, int NB>
 __global__ void __launch_bounds__(kWarpsA * 32, 3)
 mfcc_mel_kernel(const SampleT* __restrict__ pcm, const int64_t* __restrict__ pcm_off,
                 const int64_t* __restrict__ frm_off, const int32_t* __restrict__ mel_bin,
-                const float* __restrict__ mel_w, int na_rt, int nb_rt,
+                const float* __restrict__ mel_w, int na_rt, int nb_rt, int chunk,
                 float* __restrict__ mel_out, float* __restrict__ utt_max) {
     const int na = NA > 0 ? NA : na_rt;                  // NA, NB > 0: compile-time trip counts (loops unroll)
     const int nb = NA > 0 ? NB : nb_rt;
@@ -189,9 +189,9 @@ mfcc_mel_kernel(const SampleT* __restrict__ pcm, const int64_t* __restrict__ pcm
     const int u = blockIdx.x;
     const int64_t f0 = frm_off[u];
     const int T = (int)(frm_off[u + 1] - f0);
-    const int t_begin = blockIdx.y * kChunkA;
+    const int t_begin = blockIdx.y * chunk;
     if (t_begin >= T) return;
-    const int t_end = min(T, t_begin + kChunkA);
+    const int t_end = min(T, t_begin + chunk);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr unsigned FULL = 0xffffffffu;
 
@@ -215,7 +215,7 @@ mfcc_mel_kernel(const SampleT* __restrict__ pcm, const int64_t* __restrict__ pcm
     }
     const float2 w16 = make_float2(g_mfcc_tables.w160_re[10 * n2], g_mfcc_tables.w160_im[10 * n2]);   // W_16^n2
     // step 2 (thread = (frame of five, a))
-    const int a = lane % 6, fl5 = lane / 6;
+    const int a = lane / 5, fl5 = lane % 5;     // a-major: the slot reads of a half-warp then spread over all banks
     const int binA = mel_bin[lane], binB = mel_bin[na * 32 + lane];    // filters own CONSECUTIVE bins
     __syncthreads();
 
@@ -228,37 +228,62 @@ mfcc_mel_kernel(const SampleT* __restrict__ pcm, const int64_t* __restrict__ pcm
     float* area = sm.area[warp];
     float vmax = 0.f;
 
+    // raw samples of one step-1 item (frame t, this lane's n2): z[16 n1 + n2] = (x[32 n1 + 2 n2], x[32 n1 + 2 n2 + 1]),
+    // zero outside the utterance (centre padding)
+    auto fetch = [&](int t, float2* dst) {
+        const int64_t base = (int64_t)kHop * t - kHalf;
+        if (base >= 0 && base + kNfft <= n_samples) {          // interior frame: no bounds checks
+            const SampleT* __restrict__ xb = x + base + 2 * n2;
+            if (pair_ok) {
+#pragma unroll
+                for (int n1 = 0; n1 < 10; ++n1) {
+                    const PairT s = __ldg(reinterpret_cast<const PairT*>(xb + 32 * n1));
+                    dst[n1] = make_float2((float)s.x, (float)s.y);
+                }
+            } else {
+#pragma unroll
+                for (int n1 = 0; n1 < 10; ++n1) dst[n1] = make_float2((float)__ldg(xb + 32 * n1), (float)__ldg(xb + 32 * n1 + 1));
+            }
+        } else {
+#pragma unroll
+            for (int n1 = 0; n1 < 10; ++n1) {
+                const int64_t i0 = base + 32 * n1 + 2 * n2, i1 = i0 + 1;
+                dst[n1] = make_float2((i0 >= 0 && i0 < n_samples) ? (float)__ldg(x + i0) : 0.f,
+                                      (i1 >= 0 && i1 < n_samples) ? (float)__ldg(x + i1) : 0.f);
+            }
+        }
+    };
+    // the samples of the next step-1 item are requested one pass ahead (across batches too), so that the loads
+    // are in flight while the current item is transformed
+    float2 vn[10];
+#pragma unroll
+    for (int n1 = 0; n1 < 10; ++n1) vn[n1] = make_float2(0.f, 0.f);
+    if (t_begin + warp * kBatchA + fl < t_end) fetch(t_begin + warp * kBatchA + fl, vn);
+
     for (int tb = t_begin + warp * kBatchA; tb < t_end; tb += kWarpsA * kBatchA) {
-        // ---------------- step 1: load, window, 10-point DFTs, twiddle, store the 11 slots
+        // pull the samples of this warp's next batch into L2 (11 hops = 1760 + 160 samples, one 128-byte line per lane
+        // and round): the register prefetch below then only has to cover an L2 hit
+        {
+            const int tbn = tb + kWarpsA * kBatchA;
+            if (tbn < t_end) {
+                const int64_t lo = max((int64_t)0, (int64_t)kHop * tbn - kHalf);
+                const int64_t hi = min(n_samples, (int64_t)kHop * (tbn + kBatchA) + kHalf);
+                constexpr int kPerLine = 128 / (int)sizeof(SampleT);
+                for (int64_t i = lo + (int64_t)lane * kPerLine; i < hi; i += 32 * kPerLine)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(x + i));
+            }
+        }
+        // ---------------- step 1: window, 10-point DFTs, twiddle, store the 11 slots
 #pragma unroll 1
         for (int p = 0; p < kBatchA / 2; ++p) {
             const int fb = 2 * p + fl, t = tb + fb;
+            float2 v[10];
+#pragma unroll
+            for (int n1 = 0; n1 < 10; ++n1)           // never contracted: f32 and s16 inputs agree bit for bit
+                v[n1] = make_float2(__fmul_rn(vn[n1].x, hw[2 * n1]), __fmul_rn(vn[n1].y, hw[2 * n1 + 1]));
+            const int tn = (p < kBatchA / 2 - 1) ? t + 2 : tb + kWarpsA * kBatchA + fl;
+            if (tn < t_end) fetch(tn, vn);
             if (t < t_end) {
-                float2 v[10];
-                const int64_t base = (int64_t)kHop * t - kHalf;
-                if (base >= 0 && base + kNfft <= n_samples) {          // interior frame: no bounds checks
-                    const SampleT* __restrict__ xb = x + base + 2 * n2;
-                    if (pair_ok) {
-#pragma unroll
-                        for (int n1 = 0; n1 < 10; ++n1) {
-                            const PairT s = __ldg(reinterpret_cast<const PairT*>(xb + 32 * n1));
-                            v[n1] = make_float2(__fmul_rn((float)s.x, hw[2 * n1]), __fmul_rn((float)s.y, hw[2 * n1 + 1]));
-                        }
-                    } else {
-#pragma unroll
-                        for (int n1 = 0; n1 < 10; ++n1)
-                            v[n1] = make_float2(__fmul_rn((float)__ldg(xb + 32 * n1), hw[2 * n1]),
-                                                __fmul_rn((float)__ldg(xb + 32 * n1 + 1), hw[2 * n1 + 1]));
-                    }
-                } else {
-#pragma unroll
-                    for (int n1 = 0; n1 < 10; ++n1) {
-                        const int64_t i0 = base + 32 * n1 + 2 * n2, i1 = i0 + 1;
-                        const float sa = (i0 >= 0 && i0 < n_samples) ? (float)__ldg(x + i0) : 0.f;
-                        const float sb = (i1 >= 0 && i1 < n_samples) ? (float)__ldg(x + i1) : 0.f;
-                        v[n1] = make_float2(__fmul_rn(sa, hw[2 * n1]), __fmul_rn(sb, hw[2 * n1 + 1]));   // never contracted: f32 and s16 inputs agree bit for bit
-                    }
-                }
                 float2 y[10];
                 dft10(v, y);
                 float2* slot = reinterpret_cast<float2*>(area + fb * kFramePitch) + n2;
@@ -443,13 +468,21 @@ static int mfcc_launch(const void* pcm_dev, int pcm_format, const int64_t* pcm_o
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     if (phases & 1) {
         LOE_CUDA(cudaMemsetAsync(utt_max_dev, 0, sizeof(float) * (size_t)n_utt, s));
-        dim3 ga((unsigned)n_utt, (unsigned)((max_frames + kChunkA - 1) / kChunkA));
+        // frames per CTA: as many as possible (the per-CTA set-up -- constants, zeroed shared memory, first loads -- is
+        // paid once) while the batch still fills the machine a few times over: about 12 CTAs per SM in flight or queued
+        int sms = 0, dev = 0;
+        LOE_CUDA(cudaGetDevice(&dev));
+        LOE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        int64_t chunk64 = total_frames / (12 * (int64_t)sms);
+        chunk64 = ((chunk64 + 39) / 40) * 40;
+        const int chunk = (int)(chunk64 < kMinChunkA ? kMinChunkA : chunk64 > (1 << 20) ? (1 << 20) : chunk64);
+        dim3 ga((unsigned)n_utt, (unsigned)((max_frames + chunk - 1) / chunk));
         const bool k16 = (mel_na == 11 && mel_nb == 5);      // the 16 kHz table of every reference call site
         // the kernel's shared memory (slots of 4 warps x 10 frames) exceeds the 48 KB default: opt in, once per device
 #define LOE_MEL_LAUNCH(T, A, B)                                                                                          \
         LOE_CUDA(cudaFuncSetAttribute(mfcc_mel_kernel<T, A, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemA))); \
         mfcc_mel_kernel<T, A, B><<<ga, kWarpsA * 32, sizeof(SmemA), s>>>((const T*)pcm_dev, pcm_off_dev, frm_off_dev, mel_bin_dev, \
-                                                                        mel_w_dev, mel_na, mel_nb, mel_ws_dev, utt_max_dev)
+                                                                        mel_w_dev, mel_na, mel_nb, chunk, mel_ws_dev, utt_max_dev)
         if (pcm_format == LOE_PCM_F32) { if (k16) { LOE_MEL_LAUNCH(float, 11, 5); } else { LOE_MEL_LAUNCH(float, 0, 0); } }
         else if (pcm_format == LOE_PCM_S16) { if (k16) { LOE_MEL_LAUNCH(short, 11, 5); } else { LOE_MEL_LAUNCH(short, 0, 0); } }
         else { set_error("unknown pcm_format %d", pcm_format); return LOE_ERR_VALUE; }

@@ -55,7 +55,7 @@ class NativeDecoder:
 
     def __init__(self, means: np.ndarray, us: np.ndarray, cst: np.ndarray, trellis, sample_rate: float = 16000,
                  device: int = 0):
-        from ._engine import pack_tc_image
+        from ._engine import default_precision, pack_h16_image, pack_tc_image
         from .mfcc import mel_lane_tables
 
         if means.shape[1] != 39:
@@ -73,6 +73,12 @@ class NativeDecoder:
             int(device), _ptr(bins), _ptr(w), na, nb, _ptr(b_packed), _ptr(cst_pad), int(means.shape[0]),
             int(col.shape[0]), _ptr(col), _ptr(band), _ptr(flags), _ptr(word), _ptr(word_lo), ctypes.byref(handle)))
         self._h = handle
+        # same emission policy as the engine ("auto": 3xFP16 when the whitening matrices fit binary16)
+        b_h16 = pack_h16_image(means, us, cst) if default_precision() in ("auto", "h16") else None
+        if b_h16 is not None:
+            b_h16 = np.ascontiguousarray(b_h16)
+            _native.check(self._lib.loe_decoder_set_h16(self._h, _ptr(b_h16)))
+        self.emission = "h16" if b_h16 is not None else "tc"
         self.sample_rate = sample_rate
         self.tables = (bins, w, na, nb, b_packed, cst_pad, int(means.shape[0]), col, band, flags, word, word_lo)
 

@@ -56,6 +56,7 @@ SIGNATURES = {
                                    c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "loe_decoder_decode_host": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_double, c_int, c_int, c_int, c_int,
                                         c_void_p, c_void_p, c_void_p, c_void_p]),
+    "loe_decoder_set_h16": (c_int, [c_void_p, c_void_p]),
     "loe_decoder_destroy": (None, [c_void_p]),
     "loe_host_alloc": (c_int, [c_void_p, ctypes.c_size_t]),
     "loe_host_free": (c_int, [c_void_p]),

@@ -283,6 +283,11 @@ int loe_decoder_create(int device, const int32_t* mel_bin_host, const float* mel
 int loe_decoder_decode_host(void* decoder, const void* pcm_host, int pcm_format, const int64_t* sample_off_host, int n_utt,
                             double penalty, int penalty_f64, int skip_label, int max_words, int n_chunks,
                             int8_t* words_host, int32_t* count_host, float* best_score_host, int8_t* path_host);
+/* Optional: the 3xFP16 Gaussian image of the same model (HOST pointer, layout of loe_emission_h16_dev,
+ * ceil(n_states / 6) * loe_emission_h16_tile_bytes() bytes).  When set, decode scores with
+ * loe_emission_h16_dev instead of loe_emission_tc_dev -- the choice the Python package makes for models
+ * whose whitening matrices fit the binary16 range.  NULL removes it again. */
+int loe_decoder_set_h16(void* decoder, const void* b_h16_host);
 void loe_decoder_destroy(void* decoder);
 /* page-locked host buffers for pcm_host (cudaHostAlloc / cudaFreeHost) */
 int loe_host_alloc(void** ptr_out, size_t bytes);
