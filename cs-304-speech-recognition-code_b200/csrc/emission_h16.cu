@@ -44,6 +44,8 @@ constexpr int kALbo = kTileM * 16;      // 2048 B between K-adjacent A chunks
 constexpr int kBLbo = kTileN * 16;      // 3840 B between K-adjacent B chunks
 constexpr int kABytes = kAChunks * kALbo;   // 22528
 constexpr int kBBytes = kBChunks * kBLbo;   // 42240
+constexpr int kProducerRegs = 104;
+constexpr int kEpilogueRegs = 176;
 constexpr int kNumMma = 8;
 constexpr int kRawBufs = 4;
 
@@ -142,6 +144,9 @@ __device__ __forceinline__ float sumsq39(const float* v) {
     return fmaf(v[38], v[38], (fa.x + fa.y) + (fb.x + fb.y));
 }
 
+// The CTA is launched with 128 registers per thread (13 warps are allocated like 16: 16 x 32 x 128 is the whole
+// file).  The two producer warpgroups hand 24 registers per thread back (setmaxnreg.dec) and the epilogue
+// warpgroup takes them (setmaxnreg.inc) for its 120-column accumulator slice.
 __global__ void __launch_bounds__(kThreads, 1)
 emission_h16_kernel(const float* __restrict__ feat, int64_t n_frames, const uint8_t* __restrict__ b_packed,
                    const float* __restrict__ cst_pad, int n_states, float* __restrict__ out, int ld_out, int use_bulk,
@@ -195,6 +200,7 @@ emission_h16_kernel(const float* __restrict__ feat, int64_t n_frames, const uint
 
     if (warp < kProducerThreads / 32) {
         // =========================== producers ===========================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProducerRegs));
         constexpr int kTileElems = kTileM * kDim;                       // 4992 floats = 19968 B, a multiple of 16
         constexpr uint32_t kTileBytes = kTileElems * sizeof(float);
         const int n_it = (g < n_mtiles) ? (n_mtiles - g + G - 1) / G : 0;
@@ -262,6 +268,7 @@ emission_h16_kernel(const float* __restrict__ feat, int64_t n_frames, const uint
         // =========================== epilogue ===========================
         // One warp per TMEM lane quarter (thread = frame row).  The stores of a tile are deferred until the first
         // TMEM loads of the next tile have been issued.
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kEpilogueRegs));
         const int q = warp & 3;                             // TMEM lane quarter this warp may touch
         const int r = q * 32 + lane;
         float2* stage = reinterpret_cast<float2*>(sm.out_stage[q]);
@@ -296,27 +303,32 @@ emission_h16_kernel(const float* __restrict__ feat, int64_t n_frames, const uint
             mbar_wait(&sm.tmem_full[s], k & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * kBufStride);
-            // software pipeline over the states: the TMEM load of state j+1 is in flight while state j is reduced
-            float va[40], vb[40];
-            tmem_ld32(taddr, va);
-            tmem_ld8(taddr + 32, va + 32);
-            if (m_prev >= 0) store_tile(m_prev);            // previous tile's scores: shared memory -> global
+            // Two rounds of three states (120 accumulator columns each): what a round costs is the issue -> wait::ld
+            // round trip (a couple of hundred cycles with four warps draining), not the bytes, so a tile is drained
+            // in two waits instead of six and its accumulator is handed back to the MMA warp as soon as the second
+            // round sits in registers, before any of its arithmetic.
+            float v[3 * kColsPerState];
+            auto load3 = [&](uint32_t t) {
+                tmem_ld64(t, v);
+                tmem_ld32(t + 64, v + 64);
+                tmem_ld16(t + 96, v + 96);
+                tmem_ld8(t + 112, v + 112);
+            };
             float score[kStatesPerTile];
+            load3(taddr);
+            if (m_prev >= 0) store_tile(m_prev);            // previous tile's scores: shared memory -> global
             const float mhalf = -0.5f * sm.inv2[it & 3][r];          // exact: inv2 is a power of two (1 for ordinary rows)
+            tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < kStatesPerTile; ++j) {
-                if (j >= valid) { score[j] = 0.f; continue; }      // warp-uniform: the narrow last tile reads less
-                float* cur = (j & 1) ? vb : va;
-                float* nxt = (j & 1) ? va : vb;
+            for (int j = 0; j < 3; ++j) score[j] = (j < valid) ? fmaf(mhalf, sumsq39(v + j * kColsPerState), sm.cst[j]) : 0.f;
+            if (valid > 3) {                                 // warp-uniform: the narrow last tile may end here
+                load3(taddr + 3 * kColsPerState);
                 tmem_ld_wait();
-                if (j + 1 < valid) {
-                    tmem_ld32(taddr + (j + 1) * kColsPerState, nxt);
-                    tmem_ld8(taddr + (j + 1) * kColsPerState + 32, nxt + 32);
-                }
-                score[j] = fmaf(mhalf, sumsq39(cur), sm.cst[j]);
             }
             tc_fence_before();
             mbar_arrive(&sm.tmem_empty[s]);
+#pragma unroll
+            for (int j = 3; j < kStatesPerTile; ++j) score[j] = (j < valid) ? fmaf(mhalf, sumsq39(v + (j - 3) * kColsPerState), sm.cst[j]) : 0.f;
 #pragma unroll
             for (int h = 0; h < 3; ++h) stage[lane * 3 + h] = make_float2(score[2 * h], score[2 * h + 1]);
             __syncwarp();

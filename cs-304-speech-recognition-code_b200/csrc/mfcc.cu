@@ -89,7 +89,7 @@ static int ensure_tables() {
 // (30 lanes), then the mel filterbank one frame at a time with a filter per lane.
 constexpr int kWarpsA = 4;
 constexpr int kBatchA = 10;                 // frames per warp batch
-constexpr int kMinChunkA = 160;             // frames per CTA: at least this many (a multiple of the 40 frames one round of the 4 warps takes)
+constexpr int kMinChunkA = 160;             // frames per CTA: at least this many
 constexpr int kSlotPitch = 17;              // complex entries per slot (16 used): step 2's slot reads spread over the banks
 constexpr int kSlots = 11;
 constexpr int kFramePitch = 390;            // floats per frame: 11 x 17 x 2 = 374, padded to 6 mod 32 so that the
@@ -474,7 +474,7 @@ static int mfcc_launch(const void* pcm_dev, int pcm_format, const int64_t* pcm_o
         LOE_CUDA(cudaGetDevice(&dev));
         LOE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         int64_t chunk64 = total_frames / (12 * (int64_t)sms);
-        chunk64 = ((chunk64 + 39) / 40) * 40;
+        chunk64 = ((chunk64 + kWarpsA * kBatchA - 1) / (kWarpsA * kBatchA)) * (kWarpsA * kBatchA);   // whole rounds of the CTA's warps
         const int chunk = (int)(chunk64 < kMinChunkA ? kMinChunkA : chunk64 > (1 << 20) ? (1 << 20) : chunk64);
         dim3 ga((unsigned)n_utt, (unsigned)((max_frames + chunk - 1) / chunk));
         const bool k16 = (mel_na == 11 && mel_nb == 5);      // the 16 kHz table of every reference call site

@@ -79,6 +79,7 @@ class NativeDecoder:
             b_h16 = np.ascontiguousarray(b_h16)
             _native.check(self._lib.loe_decoder_set_h16(self._h, _ptr(b_h16)))
         self.emission = "h16" if b_h16 is not None else "tc"
+        self.b_h16 = b_h16
         self.sample_rate = sample_rate
         self.tables = (bins, w, na, nb, b_packed, cst_pad, int(means.shape[0]), col, band, flags, word, word_lo)
 
@@ -130,10 +131,11 @@ def write_blob(path: str, decoder: NativeDecoder, pcm_flat: np.ndarray, sample_o
     pcm = np.ascontiguousarray(pcm_flat)
     if pcm.dtype != np.int16:
         pcm = pcm.astype(np.float32)
+    b_h16 = decoder.b_h16 if decoder.b_h16 is not None else np.zeros(0, dtype=np.float16)
     head = np.array([na, nb, n_states, col.shape[0], off.shape[0] - 1, max_words, 1 if pcm.dtype == np.int16 else 0,
-                     1 if penalty_f64 else 0, skip_label, n_chunks, pcm.shape[0], 0], dtype=np.int64)
+                     1 if penalty_f64 else 0, skip_label, n_chunks, pcm.shape[0], b_h16.nbytes], dtype=np.int64)
     with open(path, "wb") as f:
         f.write(head.tobytes())
         f.write(np.array([penalty], dtype=np.float64).tobytes())
-        for a in (bins, w, b_packed, cst_pad, col, band, flags, word, word_lo, off, pcm):
+        for a in (bins, w, b_packed, cst_pad, col, band, flags, word, word_lo, b_h16, off, pcm):
             f.write(np.ascontiguousarray(a).tobytes())

@@ -39,6 +39,8 @@ int main(int argc, char** argv) {
     uint8_t* flags = slurp(f, (size_t)n_pos);
     int32_t* word = slurp(f, (size_t)n_pos * 4);
     int32_t* word_lo = slurp(f, (size_t)n_pos * 4);
+    const size_t h16_bytes = (size_t)h[11];     /* 3xFP16 Gaussian image, when the model's range allows it (else 0) */
+    void* b_h16 = h16_bytes ? slurp(f, h16_bytes) : NULL;
     int64_t* off = slurp(f, (size_t)(n_utt + 1) * 8);
     const size_t pcm_bytes = (size_t)n_samples * (pcm_format == LOE_PCM_S16 ? 2 : 4);
     void* pcm = NULL;
@@ -49,6 +51,8 @@ int main(int argc, char** argv) {
     void* dec = NULL;
     if (loe_decoder_create(0, mel_bin, mel_w, mel_na, mel_nb, b_packed, cst_pad, n_states, n_pos, col, band, flags, word, word_lo,
                            &dec) != LOE_OK) { fprintf(stderr, "create: %s\n", loe_last_error()); return 1; }
+    if (b_h16 && h16_bytes == (size_t)n_tiles * (size_t)loe_emission_h16_tile_bytes() &&
+        loe_decoder_set_h16(dec, b_h16) != LOE_OK) { fprintf(stderr, "set_h16: %s\n", loe_last_error()); return 1; }
     int8_t* words = malloc((size_t)n_utt * max_words);
     int32_t* count = malloc((size_t)n_utt * 4);
     float* score = malloc((size_t)n_utt * 4);

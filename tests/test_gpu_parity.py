@@ -53,6 +53,31 @@ def test_mfcc_ragged_batch_and_errors(eng):
     assert np.all(np.isfinite(z))
 
 
+def test_mfcc_independent_of_batch_composition(eng):
+    """The mel kernel sizes its frame chunks from the batch and picks two-sample loads from the parity of an
+    utterance's first sample: the features of an utterance must not depend on either -- bitwise -- nor on whether
+    the PCM arrives as float32 or int16, and the big batch must still agree with the oracle."""
+    from loe_speech_recognition import MFCC
+    from oracle import mfcc as OM
+    rng = np.random.default_rng(11)
+    t = np.arange(70000)
+    base = []
+    for L in (1441, 16000, 23457, 46401, 64000, 69999, 30000, 52000):       # odd lengths shift later utterances to odd starts
+        f = rng.uniform(200, 4000, 3)
+        sig = sum(3000 * np.sin(2 * np.pi * fi * t[:L] / 16000 + rng.uniform(0, 6)) for fi in f) + rng.normal(0, 30, L)
+        base.append(np.round(sig).astype(np.int16))
+    alone = [MFCC.batch([b.astype(np.float32)], 16000)[0] for b in base]
+    for b, a in zip(base[:3], alone[:3]):
+        ref = OM.mfcc_feature_vector(b.astype(np.float32)).T
+        assert rel_close(a, ref, rtol=1e-4, atol=1e-4 * np.abs(ref[:, :13]).max())
+    big = [base[i % len(base)] for i in range(1200)]                            # ~330 k frames: chunks longer than the minimum
+    assert sum(1 + len(b) // 160 for b in big) > 12 * 148 * 160
+    for dtype in (np.float32, np.int16):
+        got = MFCC.batch([b.astype(dtype) for b in big], 16000)
+        for i, g in enumerate(got):
+            assert np.array_equal(g, alone[i % len(base)]), (dtype, i)
+
+
 # ------------------------------------------------------------------ a2 emission
 @pytest.mark.parametrize("precision,rtol", [("fp32", 1e-4), ("fp64", 1e-6), ("tc", 1e-4), ("h16", 1e-4)])
 def test_emission_matches_scipy(eng, golden, precision, rtol):
