@@ -48,15 +48,16 @@ constexpr int kProducerRegs = 104;
 constexpr int kEpilogueRegs = 176;
 constexpr int kNumMma = 8;
 constexpr int kRawBufs = 4;
+constexpr int kHalves = 2;              // 6-state column tiles per CTA: a staged feature tile is multiplied with both
 
 struct __align__(128) Smem {
-    uint8_t b[kBBytes];
+    uint8_t b[kHalves][kBBytes];
     uint8_t a[2][kABytes];
     float raw[kRawBufs][kTileM * kDim];  // raw feature tiles, filled by cp.async.bulk: two in flight per producer group
     float inv2[4][kTileM];              // 4^e of the rows scaled by 2^-e (1 for ordinary rows); slot = tile & 3: the
                                         // producers run at most 3 tiles ahead of the epilogue
     float out_stage[4][32 * kStatesPerTile];   // per epilogue warp: 32 rows x 6 scores on their way to global memory
-    float cst[8];
+    float cst[kHalves * kStatesPerTile];
     uint64_t raw_full[kRawBufs], a_full[2], a_empty[2], tmem_full[2], tmem_empty[2];
     uint32_t tmem_base;
 };
@@ -154,19 +155,20 @@ emission_h16_kernel(const float* __restrict__ feat, int64_t n_frames, const uint
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    // CTA -> (state tile, frame-tile group).  Full tiles get g_full CTAs each, the last (possibly narrower,
-    // hence cheaper) tile gets g_last, so that all SMs finish together.
+    // CTA -> (column supertile = kHalves state tiles of 6, frame-tile group).  Full supertiles get g_full CTAs each,
+    // the last (possibly narrower, hence cheaper) one gets g_last, so that all SMs finish together.
     const int n_tiles = (n_states + kStatesPerTile - 1) / kStatesPerTile;
+    const int n_super = (n_tiles + kHalves - 1) / kHalves;
     const int cta = blockIdx.x;
-    const int n_tile = min(cta / g_full, n_tiles - 1);
-    const int G = (n_tile == n_tiles - 1) ? g_last : g_full;
-    const int g = cta - n_tile * g_full;
-    const int valid = min(kStatesPerTile, n_states - n_tile * kStatesPerTile);       // states of this tile
-    const int n_cols = ((valid * kColsPerState + 15) / 16) * 16;                      // MMA N: multiple of 16
+    const int sup = min(cta / g_full, n_super - 1);
+    const int G = (sup == n_super - 1) ? g_last : g_full;
+    const int g = cta - sup * g_full;
+    const int H = min(kHalves, n_tiles - sup * kHalves);                               // state tiles of this CTA
     const int n_mtiles = (int)((n_frames + kTileM - 1) / kTileM);
-    // 8-byte stores of score pairs need an even row pitch, an 8-byte aligned matrix and an even number of states
-    // in this tile (else the odd last state would be lost): otherwise scalar stores
-    const bool pair_stores = ((ld_out & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 7) == 0) && ((valid & 1) == 0);
+    auto valid_of = [&](int h) { return min(kStatesPerTile, n_states - (sup * kHalves + h) * kStatesPerTile); };
+    // 8-byte stores of score pairs need an even row pitch and an 8-byte aligned matrix (and an even number of states
+    // in the tile, else the odd last state would be lost): otherwise scalar stores
+    const bool pair_ok = ((ld_out & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 7) == 0);
 
     // ---- one-time setup: barriers, TMEM, resident B tile
     if (tid == 0) {
@@ -184,10 +186,10 @@ emission_h16_kernel(const float* __restrict__ feat, int64_t n_frames, const uint
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     {
-        const uint4* src = reinterpret_cast<const uint4*>(b_packed + (size_t)n_tile * kBBytes);
-        uint4* dst = reinterpret_cast<uint4*>(sm.b);
-        for (int i = tid; i < kBBytes / 16; i += kThreads) dst[i] = __ldg(src + i);
-        if (tid < kStatesPerTile) sm.cst[tid] = cst_pad[n_tile * kStatesPerTile + tid];
+        const uint4* src = reinterpret_cast<const uint4*>(b_packed + (size_t)sup * kHalves * kBBytes);
+        uint4* dst = reinterpret_cast<uint4*>(&sm.b[0][0]);
+        for (int i = tid; i < H * (kBBytes / 16); i += kThreads) dst[i] = __ldg(src + i);
+        if (tid < H * kStatesPerTile) sm.cst[tid] = cst_pad[sup * kHalves * kStatesPerTile + tid];
         // the zero chunk of both A stages is written once
         for (int i = tid; i < 2 * kTileM; i += kThreads)
             *reinterpret_cast<uint4*>(sm.a[i / kTileM] + (kAChunks - 1) * kALbo + (i % kTileM) * 16) = make_uint4(0, 0, 0, 0);
@@ -240,28 +242,39 @@ emission_h16_kernel(const float* __restrict__ feat, int64_t n_frames, const uint
     } else if (warp == (kProducerThreads + kEpilogueThreads) / 32) {
         // =========================== MMA issuer ===========================
         if (lane == 0) {
-            // c_format F32 (bit 4), a/b format F16 (0), N >> 3 at bit 17, M >> 4 at bit 24
-            const uint32_t idesc = (1u << 4) | ((uint32_t)(n_cols >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-            const uint32_t b_base = smem_u32(sm.b);
-            uint64_t b_desc[kNumMma];
+            // c_format F32 (bit 4), a/b format F16 (0), N >> 3 at bit 17, M >> 4 at bit 24; MMA N: multiple of 16
+            uint32_t idesc[kHalves];
+            uint64_t b_desc[kHalves][kNumMma];
 #pragma unroll
-            for (int i = 0; i < kNumMma; ++i)
-                b_desc[i] = make_desc(b_base + pair_chunk(i, 2) * kBLbo, (pair_chunk(i, 3) - pair_chunk(i, 2)) * kBLbo);
-            int it = 0;
-            for (int m = g; m < n_mtiles; m += G, ++it) {
-                const int s = it & 1;
-                const uint32_t k = (uint32_t)(it >> 1);
-                mbar_wait(&sm.a_full[s], k & 1);
-                mbar_wait(&sm.tmem_empty[s], (k & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t d = tmem_base + (uint32_t)(s * kBufStride);
-                const uint32_t a_base = smem_u32(sm.a[s]);
+            for (int h = 0; h < kHalves; ++h) {
+                const int n_cols = ((max(valid_of(h), 1) * kColsPerState + 15) / 16) * 16;
+                idesc[h] = (1u << 4) | ((uint32_t)(n_cols >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+                const uint32_t b_base = smem_u32(sm.b[h]);
 #pragma unroll
                 for (int i = 0; i < kNumMma; ++i)
-                    mma_f16(d, make_desc(a_base + pair_chunk(i, 0) * kALbo, (pair_chunk(i, 1) - pair_chunk(i, 0)) * kALbo), b_desc[i], idesc,
-                            i ? 1u : 0u);
-                mma_commit(&sm.a_empty[s]);
-                mma_commit(&sm.tmem_full[s]);
+                    b_desc[h][i] = make_desc(b_base + pair_chunk(i, 2) * kBLbo, (pair_chunk(i, 3) - pair_chunk(i, 2)) * kBLbo);
+            }
+            // j counts (feature tile, half) pairs: accumulator j & 1, A stage = tile & 1
+            int it = 0, j = 0;
+            for (int m = g; m < n_mtiles; m += G, ++it) {
+                const int st = it & 1;
+                mbar_wait(&sm.a_full[st], (uint32_t)(it >> 1) & 1);
+                const uint32_t a_base = smem_u32(sm.a[st]);
+#pragma unroll
+                for (int h = 0; h < kHalves; ++h) {
+                    if (h >= H) break;
+                    const int s = j & 1;
+                    mbar_wait(&sm.tmem_empty[s], ((uint32_t)(j >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t d = tmem_base + (uint32_t)(s * kBufStride);
+#pragma unroll
+                    for (int i = 0; i < kNumMma; ++i)
+                        mma_f16(d, make_desc(a_base + pair_chunk(i, 0) * kALbo, (pair_chunk(i, 1) - pair_chunk(i, 0)) * kALbo),
+                                b_desc[h][i], idesc[h], i ? 1u : 0u);
+                    if (h == H - 1) mma_commit(&sm.a_empty[st]);     // the stage is free once this tile's last product has run
+                    mma_commit(&sm.tmem_full[s]);
+                    ++j;
+                }
             }
         }
     } else {
@@ -272,69 +285,80 @@ emission_h16_kernel(const float* __restrict__ feat, int64_t n_frames, const uint
         const int q = warp & 3;                             // TMEM lane quarter this warp may touch
         const int r = q * 32 + lane;
         float2* stage = reinterpret_cast<float2*>(sm.out_stage[q]);
-        auto store_tile = [&](int m_prev) {
-            if (pair_stores) {
+        auto store_tile = [&](int m_prev, int h_prev) {
+            const int st_base = (sup * kHalves + h_prev) * kStatesPerTile;
+            const int valid = valid_of(h_prev);
+            if (pair_ok && (valid & 1) == 0) {
                 // a row's 6 scores are 24 contiguous bytes of the score matrix: three neighbouring lanes write one
                 // row (8 bytes each) -- a third of the sector requests of lane-per-row scalar stores
                 const int64_t f0 = (int64_t)m_prev * kTileM + q * 32;
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
-                    const int idx = i * 32 + lane, row = idx / 3, h = idx - row * 3;
-                    const int st0 = n_tile * kStatesPerTile + 2 * h;
+                    const int idx = i * 32 + lane, row = idx / 3, c = idx - row * 3;
+                    const int st0 = st_base + 2 * c;
                     if (f0 + row < n_frames && st0 + 1 < n_states)
                         *reinterpret_cast<float2*>(out + (f0 + row) * ld_out + st0) = stage[idx];
                 }
             } else {
                 const int64_t f = (int64_t)m_prev * kTileM + r;
                 if (f < n_frames) {
-                    float* o = out + f * ld_out + n_tile * kStatesPerTile;
+                    float* o = out + f * ld_out + st_base;
                     const float* mine = reinterpret_cast<const float*>(stage) + lane * kStatesPerTile;
 #pragma unroll
-                    for (int j = 0; j < kStatesPerTile; ++j)
-                        if (j < valid) o[j] = mine[j];
+                    for (int jj = 0; jj < kStatesPerTile; ++jj)
+                        if (jj < valid) o[jj] = mine[jj];
                 }
             }
             __syncwarp();                                   // the staging buffer may be rewritten
         };
-        int it = 0, m_prev = -1;
+        // j counts (feature tile, half) pairs like the MMA warp does: accumulator j & 1
+        int it = 0, j = 0, m_prev = -1, h_prev = 0;
         for (int m = g; m < n_mtiles; m += G, ++it) {
-            const int s = it & 1;
-            const uint32_t k = (uint32_t)(it >> 1);
-            mbar_wait(&sm.tmem_full[s], k & 1);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * kBufStride);
-            // Two rounds of three states (120 accumulator columns each): what a round costs is the issue -> wait::ld
-            // round trip (a couple of hundred cycles with four warps draining), not the bytes, so a tile is drained
-            // in two waits instead of six and its accumulator is handed back to the MMA warp as soon as the second
-            // round sits in registers, before any of its arithmetic.
-            float v[3 * kColsPerState];
-            auto load3 = [&](uint32_t t) {
-                tmem_ld64(t, v);
-                tmem_ld32(t + 64, v + 64);
-                tmem_ld16(t + 96, v + 96);
-                tmem_ld8(t + 112, v + 112);
-            };
-            float score[kStatesPerTile];
-            load3(taddr);
-            if (m_prev >= 0) store_tile(m_prev);            // previous tile's scores: shared memory -> global
-            const float mhalf = -0.5f * sm.inv2[it & 3][r];          // exact: inv2 is a power of two (1 for ordinary rows)
-            tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 3; ++j) score[j] = (j < valid) ? fmaf(mhalf, sumsq39(v + j * kColsPerState), sm.cst[j]) : 0.f;
-            if (valid > 3) {                                 // warp-uniform: the narrow last tile may end here
-                load3(taddr + 3 * kColsPerState);
+            for (int h = 0; h < kHalves; ++h) {
+                if (h >= H) break;
+                const int s = j & 1;
+                const int valid = valid_of(h);
+                mbar_wait(&sm.tmem_full[s], (uint32_t)(j >> 1) & 1);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * kBufStride);
+                // Two rounds of three states (120 accumulator columns each): what a round costs is the issue -> wait::ld
+                // round trip (a couple of hundred cycles with four warps draining), not the bytes, so an accumulator is
+                // drained in two waits instead of six and handed back to the MMA warp as soon as the second round sits
+                // in registers, before any of its arithmetic.
+                float v[3 * kColsPerState];
+                auto load3 = [&](uint32_t t) {
+                    tmem_ld64(t, v);
+                    tmem_ld32(t + 64, v + 64);
+                    tmem_ld16(t + 96, v + 96);
+                    tmem_ld8(t + 112, v + 112);
+                };
+                float score[kStatesPerTile];
+                const float* cst = sm.cst + h * kStatesPerTile;
+                load3(taddr);
+                if (m_prev >= 0) store_tile(m_prev, h_prev);     // previous scores: shared memory -> global
+                const float mhalf = -0.5f * sm.inv2[it & 3][r];  // exact: inv2 is a power of two (1 for ordinary rows)
                 tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < 3; ++c) score[c] = (c < valid) ? fmaf(mhalf, sumsq39(v + c * kColsPerState), cst[c]) : 0.f;
+                if (valid > 3) {                                 // warp-uniform: a narrow last tile may end here
+                    load3(taddr + 3 * kColsPerState);
+                    tmem_ld_wait();
+                }
+                tc_fence_before();
+                mbar_arrive(&sm.tmem_empty[s]);
+#pragma unroll
+                for (int c = 3; c < kStatesPerTile; ++c)
+                    score[c] = (c < valid) ? fmaf(mhalf, sumsq39(v + (c - 3) * kColsPerState), cst[c]) : 0.f;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) stage[lane * 3 + c] = make_float2(score[2 * c], score[2 * c + 1]);
+                __syncwarp();
+                m_prev = m;
+                h_prev = h;
+                ++j;
             }
-            tc_fence_before();
-            mbar_arrive(&sm.tmem_empty[s]);
-#pragma unroll
-            for (int j = 3; j < kStatesPerTile; ++j) score[j] = (j < valid) ? fmaf(mhalf, sumsq39(v + (j - 3) * kColsPerState), sm.cst[j]) : 0.f;
-#pragma unroll
-            for (int h = 0; h < 3; ++h) stage[lane * 3 + h] = make_float2(score[2 * h], score[2 * h + 1]);
-            __syncwarp();
-            m_prev = m;
         }
-        if (m_prev >= 0) store_tile(m_prev);
+        if (m_prev >= 0) store_tile(m_prev, h_prev);
     }
     tc_fence_before();
     __syncthreads();
@@ -343,6 +367,8 @@ emission_h16_kernel(const float* __restrict__ feat, int64_t n_frames, const uint
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
     }
 }
+
+static_assert(sizeof(Smem) <= 227 * 1024, "shared memory of the emission kernel");
 
 }  // namespace h16
 }  // namespace loe
@@ -365,10 +391,31 @@ extern "C" int loe_emission_h16_dev(const float* feat_dev, int64_t n_frames, int
         LOE_CUDA(cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
         LOE_CUDA(cudaFuncSetAttribute(emission_h16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
     }
-    int g_full = 1, g_last = 1;
-    split_sms(n_states, n_frames, sm_count[dev], &g_full, &g_last);
+    // divide the SMs over the column supertiles in proportion to their MMA cost (the last one may be narrower)
     const int n_tiles = (n_states + kStatesPerTile - 1) / kStatesPerTile;
-    const unsigned grid = (unsigned)((n_tiles - 1) * g_full + g_last);
+    const int n_super = (n_tiles + kHalves - 1) / kHalves;
+    const int n_mtiles = (int)((n_frames + kTileM - 1) / kTileM);
+    double cost_last = 0.0;
+    for (int t = (n_super - 1) * kHalves; t < n_tiles; ++t) {
+        const int valid = n_states - t * kStatesPerTile < kStatesPerTile ? n_states - t * kStatesPerTile : kStatesPerTile;
+        cost_last += (double)(((valid * kColsPerState + 15) / 16) * 16) / (double)(kHalves * kTileN);
+    }
+    int g_full = 1, g_last = 1;
+    const int sms = sm_count[dev];
+    if (n_super == 1) {
+        g_last = sms;
+    } else if (sms >= n_super) {
+        // minimise max(1 / g_full, cost_last / g_last) subject to (n_super - 1) * g_full + g_last <= sms
+        double best = 1e30;
+        for (int gf = 1; (n_super - 1) * gf < sms; ++gf) {
+            const int gl = sms - (n_super - 1) * gf;
+            const double t = (1.0 / gf > cost_last / gl) ? 1.0 / gf : cost_last / gl;
+            if (t < best) { best = t; g_full = gf; g_last = gl; }
+        }
+    }
+    if (g_full > n_mtiles) g_full = n_mtiles;
+    if (g_last > n_mtiles) g_last = n_mtiles;
+    const unsigned grid = (unsigned)((n_super - 1) * g_full + g_last);
     const int use_bulk = (reinterpret_cast<uintptr_t>(feat_dev) & 15) == 0 ? 1 : 0;
     emission_h16_kernel<<<grid, kThreads, sizeof(Smem), s>>>(feat_dev, n_frames, static_cast<const uint8_t*>(b_packed_dev), cst_pad_dev,
                                                              n_states, out_dev, ld_out, use_bulk, g_full, g_last);
