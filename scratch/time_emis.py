@@ -4,11 +4,12 @@ F, S = 3836960, 58
 dev = torch.device("cuda", 0)
 feat = torch.randn(F, 39, device=dev)
 n_tiles = (S + 5) // 6
-b = (torch.randn(n_tiles * 42240 // 2, device=dev) * 0.1).half()
 cst = torch.zeros(n_tiles * 6, device=dev)
 out = torch.empty(F, S, device=dev)
 for path in sorted(glob.glob(os.path.join(os.path.dirname(__file__), "libs", "*.so"))):
     lib = ctypes.CDLL(path)
+    lib.loe_emission_h16_tile_bytes.restype = c_int
+    b = (torch.randn(n_tiles * lib.loe_emission_h16_tile_bytes() // 2, device=dev) * 0.1).half()
     fn = lib.loe_emission_h16_dev
     fn.restype = c_int
     fn.argtypes = [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]

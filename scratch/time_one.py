@@ -4,7 +4,7 @@ F, S = 3836960, 58
 dev = torch.device("cuda", 0)
 feat = torch.randn(F, 39, device=dev)
 n_tiles = (S + 5) // 6
-b = (torch.randn(n_tiles * 42240 // 2, device=dev) * 0.1).half()
+b = (torch.randn(n_tiles * 57600 // 2, device=dev) * 0.1).half()
 cst = torch.zeros(n_tiles * 6, device=dev)
 out = torch.empty(F, S, device=dev)
 lib = ctypes.CDLL(sys.argv[1])
