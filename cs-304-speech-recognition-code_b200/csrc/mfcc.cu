@@ -387,11 +387,13 @@ mfcc_ceps_kernel(const float* __restrict__ mel, const float* __restrict__ utt_ma
     const int g1 = min(T - 1, max(t1 + 3, 8));
     const int ng = g1 - g0 + 1;                 // <= kRowsB
 
-    const float ref_db = 10.0f * log10f(fmaxf(1e-10f, utt_max[u]));
+    // 10 log10(x) = kDbPerLog2 * log2(x); MUFU.LG2 (__log2f, 2 ulp) instead of the 20-instruction log10f
+    constexpr float kDbPerLog2 = 3.0102999566398120f;
+    const float ref_db = kDbPerLog2 * __log2f(fmaxf(1e-10f, utt_max[u]));
     const float* __restrict__ src = mel + (f0 + g0) * kMels;
     for (int i = tid; i < ng * kMels; i += kRowsB) {
         const int j = i / kMels, m = i - j * kMels;
-        const float db = 10.0f * log10f(fmaxf(1e-10f, __ldg(src + i))) - ref_db;
+        const float db = fmaf(kDbPerLog2, __log2f(fmaxf(1e-10f, __ldg(src + i))), -ref_db);
         s_lm[j * kMelPitch + m] = fmaxf(db, -80.0f);
     }
     __syncthreads();
