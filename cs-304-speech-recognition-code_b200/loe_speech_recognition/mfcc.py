@@ -54,35 +54,75 @@ def mel_filterbank(sample_rate: float) -> NDArray[np.float32]:
     return w
 
 
+def _distinct_bank_starts(first, last, span, lanes_per_filter):
+    """Window starts w[f] <= first[f] with w[f] + span > last[f] such that the addresses the 32 lanes read in one
+    iteration -- w[f] + j, j < lanes_per_filter -- fall into 32 different shared-memory banks (residues mod 32),
+    or None.  Depth-first search with the natural start tried first; 32 / lanes_per_filter filters."""
+    n = len(first)
+    cands = [[w for w in range(first[f], last[f] - span, -1) if w >= 0] for f in range(n)]
+    order = sorted(range(n), key=lambda f: len(cands[f]))          # most constrained filters first
+    chosen = [None] * n
+    budget = [200000]
+
+    def place(i, used):
+        if i == n:
+            return True
+        f = order[i]
+        for w in cands[f]:
+            budget[0] -= 1
+            if budget[0] < 0:
+                return False
+            rs = {(w + j) % 32 for j in range(lanes_per_filter)}
+            if rs & used:
+                continue
+            chosen[f] = w
+            if place(i + 1, used | rs):
+                return True
+        return False
+
+    return chosen if place(0, set()) else None
+
+
 def mel_lane_tables(sample_rate: float):
     """The filterbank in the lane-balanced layout loe_mfcc_dev reads (include/loe_b200.h):
     (bin int32 [(na+nb)*32], weight float32 [(na+nb)*32], na, nb).  Round A: lane l owns filter l
-    (filters 0..31), one non-zero per iteration.  Round B: lanes 4q..4q+3 share filter 32+q (the
-    widest filters), non-zero j goes to lane 4q + j%4, iteration j//4."""
+    (filters 0..31), one bin per iteration.  Round B: lanes 4q..4q+3 share filter 32+q (the
+    widest filters), lane 4q + j takes every fourth bin starting at its window start + j.
+
+    Every lane walks CONSECUTIVE bins (round A: start + it; round B: start + j + 4*it), so the kernel only
+    needs the first bin of each lane; entries outside the filter's support carry weight 0.  A filter narrower
+    than the na (4 nb) bins of its window leaves room to slide the window: the starts are chosen such that
+    the 32 addresses of one iteration hit 32 different shared-memory banks (the natural starts, 3, 4, 6, ...,
+    69 at 16 kHz, collide two-way in every iteration)."""
     dense = mel_filterbank(sample_rate)
     nz = [np.nonzero(dense[m])[0] for m in range(N_MELS)]
     na = max((len(nz[m]) for m in range(32)), default=0)
     nb = max(((len(nz[m]) + 3) // 4 for m in range(32, N_MELS)), default=0)
     if na > _native.LOE_MEL_NA_MAX or nb > _native.LOE_MEL_NB_MAX:
         raise NotImplementedError(f"mel filters too wide for the kernel tables at sample_rate={sample_rate}")
+    first = [int(nz[m][0]) if len(nz[m]) else 0 for m in range(N_MELS)]
+    last = [int(nz[m][-1]) if len(nz[m]) else 0 for m in range(N_MELS)]
+    for m in range(N_MELS):
+        assert len(nz[m]) == 0 or np.array_equal(nz[m], np.arange(first[m], last[m] + 1))
+    start_a = _distinct_bank_starts(first[:32], last[:32], na, 1) or first[:32]
+    start_b = _distinct_bank_starts(first[32:], last[32:], 4 * nb, 4) or first[32:]
     bins = np.zeros((na + nb, 32), dtype=np.int32)
     w = np.zeros((na + nb, 32), dtype=np.float32)
-    # every lane walks CONSECUTIVE bins (round A: first + it; round B: first + sub + 4*it), so the kernel
-    # only needs the first bin of each lane; padding entries keep the pattern with weight 0
+    n_bins = dense.shape[1]
     for m in range(32):
-        first = int(nz[m][0]) if len(nz[m]) else 0
-        assert len(nz[m]) == 0 or np.array_equal(nz[m], np.arange(first, first + len(nz[m])))
         for j in range(na):
-            bins[j, m] = first + j
-            if j < len(nz[m]):
-                w[j, m] = dense[m, first + j]
+            k = start_a[m] + j
+            bins[j, m] = k
+            if k < n_bins:
+                w[j, m] = dense[m, k]
     for q, m in enumerate(range(32, N_MELS)):
-        first = int(nz[m][0]) if len(nz[m]) else 0
-        assert len(nz[m]) == 0 or np.array_equal(nz[m], np.arange(first, first + len(nz[m])))
         for j in range(4 * nb):
-            bins[na + j // 4, 4 * q + j % 4] = first + j
-            if j < len(nz[m]):
-                w[na + j // 4, 4 * q + j % 4] = dense[m, first + j]
+            k = start_b[q] + j
+            bins[na + j // 4, 4 * q + j % 4] = k
+            if k < n_bins:
+                w[na + j // 4, 4 * q + j % 4] = dense[m, k]
+    # nothing of a filter's support may fall outside its window
+    assert np.isclose(w[:na].sum(), dense[:32].sum(), rtol=1e-6) and np.isclose(w[na:].sum(), dense[32:].sum(), rtol=1e-6)
     return np.ascontiguousarray(bins.reshape(-1)), np.ascontiguousarray(w.reshape(-1)), int(na), int(nb)
 
 
