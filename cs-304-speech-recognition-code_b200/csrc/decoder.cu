@@ -8,11 +8,115 @@
 #include "common.cuh"
 #include <vector>
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <new>
+#include <thread>
+#include <stdlib.h>
 #include <string.h>
+#include <immintrin.h>
 
 
 namespace loe {
+
+// ------------------------------------------------------------------------------------------------
+// Lossless narrowing of float32 PCM on the host.  The reference hands the decoder float32 copies of int16 WAV
+// samples (ti_digits.py:85-139), so half of the PCIe bytes are zeros in disguise.  Worker threads convert a chunk
+// to int16 in pinned staging while the previous chunk is on the wire and VERIFY every sample (convert back,
+// compare): a chunk with a single sample that is not an int16 value travels as float32 like before.  The MFCC
+// kernel produces bit-identical features from either format (tests: f32 vs s16), so results do not depend on it.
+// ------------------------------------------------------------------------------------------------
+static bool narrow_range_sse2(const float* src, int16_t* dst, int64_t n) {
+    __m128i bad = _mm_setzero_si128();
+    int64_t i = 0;
+    for (; i + 8 <= n; i += 8) {
+        const __m128 a = _mm_loadu_ps(src + i), b = _mm_loadu_ps(src + i + 4);
+        const __m128i p = _mm_packs_epi32(_mm_cvttps_epi32(a), _mm_cvttps_epi32(b));       // saturating
+        const __m128 ra = _mm_cvtepi32_ps(_mm_srai_epi32(_mm_unpacklo_epi16(p, p), 16));
+        const __m128 rb = _mm_cvtepi32_ps(_mm_srai_epi32(_mm_unpackhi_epi16(p, p), 16));
+        bad = _mm_or_si128(bad, _mm_castps_si128(_mm_or_ps(_mm_cmpneq_ps(ra, a), _mm_cmpneq_ps(rb, b))));   // NaN != anything
+        _mm_storeu_si128(reinterpret_cast<__m128i*>(dst + i), p);
+    }
+    bool ok = _mm_movemask_epi8(bad) == 0;
+    for (; i < n; ++i) {
+        const float v = src[i];
+        const bool in = v >= -32768.0f && v <= 32767.0f;
+        const int16_t t = in ? (int16_t)(int32_t)v : (int16_t)0;
+        ok = ok && in && (float)t == v;
+        dst[i] = t;
+    }
+    return ok;
+}
+
+__attribute__((target("avx2"))) static bool narrow_range_avx2(const float* src, int16_t* dst, int64_t n) {
+    __m256i bad = _mm256_setzero_si256();
+    int64_t i = 0;
+    // the int16 copy is written once and read by the DMA engine only: streaming stores (no read-for-ownership of
+    // the destination lines) when the destination is 32-byte aligned
+    const bool stream = (reinterpret_cast<uintptr_t>(dst) & 31) == 0;
+    for (; i + 16 <= n; i += 16) {
+        const __m256 a = _mm256_loadu_ps(src + i), b = _mm256_loadu_ps(src + i + 8);
+        // packs works per 128-bit lane: [a0-3 b0-3 | a4-7 b4-7] -> permute the 64-bit quarters back into order
+        const __m256i p = _mm256_permute4x64_epi64(_mm256_packs_epi32(_mm256_cvttps_epi32(a), _mm256_cvttps_epi32(b)), 0xD8);
+        const __m256 ra = _mm256_cvtepi32_ps(_mm256_cvtepi16_epi32(_mm256_castsi256_si128(p)));
+        const __m256 rb = _mm256_cvtepi32_ps(_mm256_cvtepi16_epi32(_mm256_extracti128_si256(p, 1)));
+        bad = _mm256_or_si256(bad, _mm256_castps_si256(_mm256_or_ps(_mm256_cmp_ps(ra, a, _CMP_NEQ_UQ), _mm256_cmp_ps(rb, b, _CMP_NEQ_UQ))));
+        if (stream) _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i), p);
+        else _mm256_storeu_si256(reinterpret_cast<__m256i*>(dst + i), p);
+    }
+    if (stream) _mm_sfence();
+    const bool ok = _mm256_testz_si256(bad, bad) != 0;
+    return narrow_range_sse2(src + i, dst + i, n - i) && ok;
+}
+
+static bool narrow_range(const float* src, int16_t* dst, int64_t n) {
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    return avx2 ? narrow_range_avx2(src, dst, n) : narrow_range_sse2(src, dst, n);
+}
+
+// persistent worker threads: run(f) calls f(worker index) on every worker and returns when all are done
+class Pool {
+public:
+    explicit Pool(int n) : n_(n) {
+        for (int i = 0; i < n; ++i) th_.emplace_back([this, i] { loop(i); });
+    }
+    ~Pool() {
+        { std::lock_guard<std::mutex> l(m_); stop_ = true; ++gen_; }
+        cv_.notify_all();
+        for (auto& t : th_) t.join();
+    }
+    int size() const { return n_; }
+    void run(const std::function<void(int)>& f) {
+        std::unique_lock<std::mutex> l(m_);
+        job_ = &f; pending_ = n_; ++gen_;
+        cv_.notify_all();
+        done_.wait(l, [this] { return pending_ == 0; });
+        job_ = nullptr;
+    }
+private:
+    void loop(int i) {
+        int seen = 0;
+        for (;;) {
+            const std::function<void(int)>* job;
+            {
+                std::unique_lock<std::mutex> l(m_);
+                cv_.wait(l, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (stop_) return;
+                job = job_;
+            }
+            (*job)(i);
+            { std::lock_guard<std::mutex> l(m_); if (--pending_ == 0) done_.notify_one(); }
+        }
+    }
+    int n_; std::vector<std::thread> th_; std::mutex m_; std::condition_variable cv_, done_;
+    const std::function<void(int)>* job_ = nullptr; int pending_ = 0, gen_ = 0; bool stop_ = false;
+};
+
+constexpr double kNarrowMinGBps = 65.0;
 
 struct DevBuf {
     void* p = nullptr; size_t cap = 0;
@@ -42,6 +146,12 @@ struct Decoder {
     int64_t* h_off[2] = {nullptr, nullptr}; size_t h_off_cap[2] = {0, 0};      // pinned staging: [pcm_off | frm_off]
     bool used[2] = {false, false};
     char* h_out = nullptr; size_t h_out_cap = 0;                                // pinned staging of the results
+    // host-side narrowing of float32 PCM (see above): worker pool, pinned int16 staging per buffer set, and the
+    // running verdict: -1 = not measured yet, 0 = off (conversion slower than the float32 copy it saves), 1 = on
+    Pool* pool = nullptr;
+    int16_t* h_stage[2] = {nullptr, nullptr}; size_t h_stage_cap[2] = {0, 0};
+    int narrow = -1;
+    double narrow_gbps = 0.0;                                                   // measured conversion rate, float32 bytes
 };
 
 template <typename T>
@@ -63,6 +173,8 @@ static void destroy(Decoder* d) {
         if (d->ev_done[i]) cudaEventDestroy(d->ev_done[i]);
     }
     if (d->h_out) cudaFreeHost(d->h_out);
+    for (int i = 0; i < 2; ++i) if (d->h_stage[i]) cudaFreeHost(d->h_stage[i]);
+    delete d->pool;
     DevBuf* bufs[] = {&d->mel, &d->feat, &d->scores, &d->path, &d->umax, &d->words, &d->count, &d->best, &d->best_score, &d->bp};
     for (DevBuf* b : bufs) b->release();
     void* tabs[] = {d->d_b_h16, d->d_mel_bin, d->d_mel_w, d->d_b, d->d_cst, d->d_tr_off, d->d_col, d->d_band, d->d_flags, d->d_word, d->d_word_lo};
@@ -164,6 +276,11 @@ extern "C" int loe_decoder_decode_host(void* dec, const void* pcm_host, int pcm_
         LOE_CUDA(cudaHostAlloc((void**)&d->h_out, out_bytes + out_bytes / 4, cudaHostAllocDefault));
         d->h_out_cap = out_bytes + out_bytes / 4;
     }
+    // worker threads of the float32 -> int16 narrowing: LOE_B200_NARROW_THREADS (0 = never narrow), default = the
+    // machine's hardware threads, at most 32
+    int narrow_threads = (int)std::min<unsigned>(32u, std::max<unsigned>(1u, std::thread::hardware_concurrency()));
+    if (const char* e = getenv("LOE_B200_NARROW_THREADS")) narrow_threads = std::max(0, std::min(256, atoi(e)));
+    if (d->pool && d->pool->size() != narrow_threads) { delete d->pool; d->pool = nullptr; }
     int64_t frames_done = 0;
     for (size_t c = 0; c + 1 < bounds.size(); ++c) {
         const int a = bounds[c], b = bounds[c + 1], n = b - a, set = (int)(c & 1);
@@ -190,10 +307,44 @@ extern "C" int loe_decoder_decode_host(void* dec, const void* pcm_host, int pcm_
         }
         const int64_t F = frm_off[n];
         int st;
-        if ((st = d->pcm[set].ensure((size_t)ns * bps)) != LOE_OK) return st;
+        // float32 PCM: try to send the chunk as int16 (exact or not at all); the conversion of this chunk overlaps the
+        // copy and the kernels of the previous one
+        const char* src = (const char*)pcm_host + (size_t)(s0 - sample_off_host[0]) * bps;
+        int chunk_format = pcm_format;
+        size_t chunk_bps = bps;
+        if (pcm_format == LOE_PCM_F32 && d->narrow != 0 && narrow_threads > 0 && ns > 0) {
+            if (!d->pool) d->pool = new (std::nothrow) Pool(narrow_threads);
+            if (d->pool) {
+                if (d->h_stage_cap[set] < (size_t)ns) {
+                    if (d->h_stage[set]) LOE_CUDA(cudaFreeHost(d->h_stage[set]));
+                    d->h_stage[set] = nullptr; d->h_stage_cap[set] = 0;
+                    const size_t want = (size_t)ns + (size_t)ns / 8 + 64;
+                    LOE_CUDA(cudaHostAlloc((void**)&d->h_stage[set], want * sizeof(int16_t), cudaHostAllocDefault));
+                    d->h_stage_cap[set] = want;
+                }
+                const float* fsrc = reinterpret_cast<const float*>(src);
+                int16_t* fdst = d->h_stage[set];
+                std::atomic<int> exact(1);
+                const int W = d->pool->size();
+                const auto t0 = std::chrono::steady_clock::now();
+                d->pool->run([&](int w) {
+                    const int64_t i0 = (ns * w / W) & ~(int64_t)15, i1 = (w == W - 1) ? ns : ((ns * (w + 1) / W) & ~(int64_t)15);
+                    if (i1 > i0 && !narrow_range(fsrc + i0, fdst + i0, i1 - i0)) exact.store(0);
+                });
+                const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+                if (d->narrow < 0 && (ns >= (1 << 20) || getenv("LOE_B200_NARROW_MIN_GBPS"))) {
+                    // worth it only if converting is faster than the float32 copy it replaces (PCIe 5 x16: ~52 GB/s)
+                    d->narrow_gbps = (double)ns * 4.0 / sec * 1e-9;
+                    double min_gbps = kNarrowMinGBps;
+                    if (const char* e = getenv("LOE_B200_NARROW_MIN_GBPS")) min_gbps = atof(e);
+                    d->narrow = d->narrow_gbps > min_gbps ? 1 : 0;
+                }
+                if (exact.load()) { src = reinterpret_cast<const char*>(fdst); chunk_format = LOE_PCM_S16; chunk_bps = 2; }
+            }
+        }
+        if ((st = d->pcm[set].ensure((size_t)ns * chunk_bps)) != LOE_OK) return st;
         if ((st = d->off[set].ensure(sizeof(int64_t) * off_elems)) != LOE_OK) return st;
-        LOE_CUDA(cudaMemcpyAsync(d->pcm[set].p, (const char*)pcm_host + (size_t)(s0 - sample_off_host[0]) * bps, (size_t)ns * bps,
-                                 cudaMemcpyHostToDevice, d->copy));
+        LOE_CUDA(cudaMemcpyAsync(d->pcm[set].p, src, (size_t)ns * chunk_bps, cudaMemcpyHostToDevice, d->copy));
         LOE_CUDA(cudaMemcpyAsync(d->off[set].p, pcm_off, sizeof(int64_t) * off_elems, cudaMemcpyHostToDevice, d->copy));
         LOE_CUDA(cudaEventRecord(d->ev_copy[set], d->copy));
         d->used[set] = true;
@@ -211,7 +362,7 @@ extern "C" int loe_decoder_decode_host(void* dec, const void* pcm_host, int pcm_
         LOE_CUDA(cudaStreamWaitEvent(d->comp, d->ev_copy[set], 0));
         const int64_t* d_pcm_off = (const int64_t*)d->off[set].p;
         const int64_t* d_frm_off = d_pcm_off + (n + 1);
-        if ((st = loe_mfcc_dev(d->pcm[set].p, pcm_format, d_pcm_off, d_frm_off, n, F, max_frames, min_frames, d->d_mel_bin, d->d_mel_w,
+        if ((st = loe_mfcc_dev(d->pcm[set].p, chunk_format, d_pcm_off, d_frm_off, n, F, max_frames, min_frames, d->d_mel_bin, d->d_mel_w,
                                d->mel_na, d->mel_nb, (float*)d->mel.p, (float*)d->umax.p, (float*)d->feat.p, d->comp)) != LOE_OK) return st;
         st = d->d_b_h16 ? loe_emission_h16_dev((const float*)d->feat.p, F, 39, d->d_b_h16, d->d_cst, d->n_states, (float*)d->scores.p,
                                                d->n_states, d->comp)
@@ -236,6 +387,17 @@ extern "C" int loe_decoder_decode_host(void* dec, const void* pcm_host, int pcm_
     if (best_score_host) memcpy(best_score_host, d->h_out + o_score, (size_t)n_utt * 4);
     if (path_host) memcpy(path_host, d->h_out + o_path, (size_t)total_frames);
     return LOE_OK;
+}
+
+extern "C" int loe_pcm_narrow_host(const float* src_host, int16_t* dst_host, int64_t n_samples) {
+    if (n_samples <= 0) return 1;
+    if (!src_host || !dst_host) return 0;
+    return loe::narrow_range(src_host, dst_host, n_samples) ? 1 : 0;
+}
+
+extern "C" double loe_decoder_narrow_rate(void* dec) {
+    loe::Decoder* d = reinterpret_cast<loe::Decoder*>(dec);
+    return d ? (d->narrow == 0 ? -d->narrow_gbps : d->narrow_gbps) : 0.0;
 }
 
 extern "C" int loe_host_alloc(void** ptr_out, size_t bytes) {

@@ -83,6 +83,11 @@ class NativeDecoder:
         self.sample_rate = sample_rate
         self.tables = (bins, w, na, nb, b_packed, cst_pad, int(means.shape[0]), col, band, flags, word, word_lo)
 
+    def narrow_rate(self) -> float:
+        """GB/s (float32 bytes) the library measured for its host-side float32 -> int16 narrowing: > 0 in use,
+        < 0 measured and switched off, 0 not measured / disabled (include/loe_b200.h)."""
+        return float(self._lib.loe_decoder_narrow_rate(self._h))
+
     def close(self) -> None:
         if getattr(self, "_h", None) is not None:
             self._lib.loe_decoder_destroy(self._h)

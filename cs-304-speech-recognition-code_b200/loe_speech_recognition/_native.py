@@ -58,6 +58,8 @@ SIGNATURES = {
                                         c_void_p, c_void_p, c_void_p, c_void_p]),
     "loe_decoder_set_h16": (c_int, [c_void_p, c_void_p]),
     "loe_decoder_destroy": (None, [c_void_p]),
+    "loe_pcm_narrow_host": (c_int, [c_void_p, c_void_p, c_int64]),
+    "loe_decoder_narrow_rate": (c_double, [c_void_p]),
     "loe_host_alloc": (c_int, [c_void_p, ctypes.c_size_t]),
     "loe_host_free": (c_int, [c_void_p]),
 }

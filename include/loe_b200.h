@@ -289,6 +289,18 @@ int loe_decoder_decode_host(void* decoder, const void* pcm_host, int pcm_format,
  * whose whitening matrices fit the binary16 range.  NULL removes it again. */
 int loe_decoder_set_h16(void* decoder, const void* b_h16_host);
 void loe_decoder_destroy(void* decoder);
+/* float32 PCM that holds int16 values (the reference converts WAV samples to float32 on the host,
+ * ti_digits.py:85-139) is narrowed back to int16 by worker threads inside loe_decoder_decode_host before it
+ * crosses PCIe: every sample is verified (converted back and compared), a chunk with one inexact sample
+ * travels as float32, and the features are bit-identical either way.  LOE_B200_NARROW_THREADS sets the
+ * number of threads (default: hardware threads, at most 32; 0 = off); the decoder switches it off by itself
+ * when the conversion turns out slower than the copy it saves.
+ * loe_pcm_narrow_host: the same conversion as a stand-alone call (single thread): writes dst_host[i] =
+ * (int16) src_host[i] and returns 1 if every sample was exact, 0 otherwise (dst contents then unspecified).
+ * loe_decoder_narrow_rate: GB/s of float32 input the decoder measured for it (negative: measured and
+ * switched off, 0: not measured yet). */
+int loe_pcm_narrow_host(const float* src_host, int16_t* dst_host, int64_t n_samples);
+double loe_decoder_narrow_rate(void* decoder);
 /* page-locked host buffers for pcm_host (cudaHostAlloc / cudaFreeHost) */
 int loe_host_alloc(void** ptr_out, size_t bytes);
 int loe_host_free(void* ptr);

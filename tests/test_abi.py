@@ -42,3 +42,29 @@ def test_host_side_argument_checks_need_no_gpu(built_lib):
     assert lib.loe_emission_dev(0, 10, 7, 0, 0, 0, 3, 0, 3, 0, 0) == _native.LOE_ERR_UNSUPPORTED
     assert lib.loe_viterbi_bp_fits(460, 58) == 1 and lib.loe_viterbi_bp_fits(100000, 128) == 0
     assert lib.loe_kmeans_ws_doubles(1000, 5, 39) == 5 * 820 + 1
+
+
+def test_pcm_narrowing_is_exact_or_refused(built_lib):
+    """loe_pcm_narrow_host (host code, no GPU): float32 PCM that holds int16 values converts exactly at every
+    length / alignment; a single fractional, out-of-range or non-finite sample makes the call report failure."""
+    import numpy as np
+    from loe_speech_recognition import _native
+    lib = _native.load()
+    rng = np.random.default_rng(5)
+    for n in (0, 1, 7, 8, 15, 16, 17, 31, 33, 1000, 100003):
+        a = rng.integers(-32768, 32768, n).astype(np.float32)
+        for shift in (0, 1, 16):
+            out = np.full(n + 32, 77, np.int16)
+            assert lib.loe_pcm_narrow_host(a.ctypes.data, out.ctypes.data + 2 * shift, n) == 1
+            assert np.array_equal(out[shift:shift + n], a.astype(np.int16))
+            assert np.all(out[:shift] == 77) and np.all(out[shift + n:] == 77)
+        if n:
+            out = np.empty(n, np.int16)
+            for bad in (0.5, -0.25, 32768.0, -32769.0, np.nan, np.inf, -np.inf, 1e20):
+                b = a.copy()
+                b[rng.integers(0, n)] = bad
+                assert lib.loe_pcm_narrow_host(b.ctypes.data, out.ctypes.data, n) == 0, (n, bad)
+    edge = np.array([-32768.0, 32767.0, 0.0, -0.0, 1.0, -1.0], np.float32)
+    out = np.empty(edge.size, np.int16)
+    assert lib.loe_pcm_narrow_host(edge.ctypes.data, out.ctypes.data, edge.size) == 1
+    assert out.tolist() == [-32768, 32767, 0, 0, 1, -1]

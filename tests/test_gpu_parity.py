@@ -674,6 +674,43 @@ def test_host_buffer_decoder_matches_flat_decode(eng, golden):
 
 
 @pytest.mark.gpu
+def test_host_narrowing_of_float_pcm_is_lossless(eng, golden, monkeypatch):
+    """loe_decoder_decode_host narrows float32 PCM that holds int16 values to int16 on the host (verified per
+    sample, per chunk) when that beats the copy it saves; forced on here: same strings, scores and paths as the
+    float32 path, also when one chunk holds an inexact sample and travels as float32."""
+    from loe_speech_recognition._decoder import NativeDecoder
+    from loe_speech_recognition.hidden_markov_model import _penalty_args
+    from loe_speech_recognition.synthetic import string_corpus
+    inf = _loop_inference(golden)
+    utts, _ = string_corpus(seed=57, n_utts=18, n_digits=4)
+    off = np.concatenate(([0], np.cumsum([len(u) for u in utts]))).astype(np.int64)
+    flat = np.round(np.concatenate(utts)).astype(np.float32)
+    pen, f64 = _penalty_args(inf._log_transition_probability_between_words)
+    monkeypatch.setenv("LOE_B200_NARROW_THREADS", "0")
+    inf.__dict__.pop("_native_decoder", None)
+    w0, c0, s0, p0 = inf.native_decoder().decode(flat, off, pen, f64, -1, 32, 3, want_scores=True, want_path=True)
+    assert inf.native_decoder().narrow_rate() == 0.0
+    monkeypatch.setenv("LOE_B200_NARROW_THREADS", "4")
+    monkeypatch.setenv("LOE_B200_NARROW_MIN_GBPS", "0")
+    inf.__dict__.pop("_native_decoder", None)
+    dec = inf.native_decoder()
+    w1, c1, s1, p1 = dec.decode(flat, off, pen, f64, -1, 32, 3, want_scores=True, want_path=True)
+    assert dec.narrow_rate() > 0.0
+    for a, b in ((w0, w1), (c0, c1), (s0, s1), (p0, p1)):
+        np.testing.assert_array_equal(a, b)
+    bent = flat.copy()
+    bent[int(off[9]) + 1234] += 0.25                                # the middle chunk can no longer be narrowed
+    inf.__dict__.pop("_native_decoder", None)
+    monkeypatch.setenv("LOE_B200_NARROW_THREADS", "0")
+    w2, c2, s2, p2 = inf.native_decoder().decode(bent, off, pen, f64, -1, 32, 3, want_scores=True, want_path=True)
+    monkeypatch.setenv("LOE_B200_NARROW_THREADS", "4")
+    inf.__dict__.pop("_native_decoder", None)
+    w3, c3, s3, p3 = inf.native_decoder().decode(bent, off, pen, f64, -1, 32, 3, want_scores=True, want_path=True)
+    for a, b in ((w2, w3), (c2, c3), (s2, s3), (p2, p3)):
+        np.testing.assert_array_equal(a, b)
+    inf.__dict__.pop("_native_decoder", None)
+
+
 def test_c_program_decodes_like_python(eng, golden, tmp_path):
     """examples/decode_host.c, compiled with gcc against include/loe_b200.h and libloe_b200.so, decodes a
     batch without Python in the process and prints the same word ids and scores."""
