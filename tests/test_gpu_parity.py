@@ -78,6 +78,37 @@ def test_mfcc_independent_of_batch_composition(eng):
             assert np.array_equal(g, alone[i % len(base)]), (dtype, i)
 
 
+def test_kernels_stay_inside_their_buffers(eng, golden):
+    """Guard bands around every output of the decode path (mel workspace, utterance maxima, features, scores)
+    keep their sentinel: ragged utterances, a partial last emission tile, float32 and int16 PCM."""
+    torch = eng.torch
+    from loe_speech_recognition.synthetic import string_corpus
+    utts, _ = string_corpus(seed=77, n_utts=9, n_digits=3)
+    utts = [u[: len(u) - 53 * i] for i, u in enumerate(utts)] + [utts[0][:1441]]
+    inf = _loop_inference(golden)
+    gp, _ = inf._packs()
+    G = 4096
+    for dtype in (np.float32, np.int16):
+        pcm, pcm_off, frm_off_dev, frm_off, frames = eng.upload_pcm([np.round(u).astype(dtype) for u in utts])
+        n, F = len(utts), int(frm_off[-1])
+
+        def banded(rows, cols):
+            size = rows * max(cols, 1)
+            t = torch.full((G + size + G,), -12345.0, dtype=torch.float32, device=eng.device)
+            return t, (t[G:G + size].view(rows, cols) if cols else t[G:G + size])
+        mel_all, mel = banded(F, 40)
+        um_all, um = banded(n, 0)
+        feat_all, feat = banded(F, 39)
+        sc_all, sc = banded(F, gp.n_states)
+        eng.mfcc_device(pcm, pcm_off, frm_off_dev, n, F, int(frames.max()), int(frames.min()), 16000, out=feat, mel_ws=mel, utt_max=um)
+        for prec in ("h16", "tc", "fp32"):
+            eng.emission(feat, gp, prec, out=sc)
+            torch.cuda.synchronize()
+            for whole, inner in ((mel_all, F * 40), (um_all, n), (feat_all, F * 39), (sc_all, F * gp.n_states)):
+                assert bool((whole[:G] == -12345.0).all()) and bool((whole[G + inner:] == -12345.0).all()), (dtype, prec)
+        assert bool(torch.isfinite(feat).all()) and bool(torch.isfinite(sc).all()) and bool((feat != -12345.0).any())
+
+
 # ------------------------------------------------------------------ a2 emission
 @pytest.mark.parametrize("precision,rtol", [("fp32", 1e-4), ("fp64", 1e-6), ("tc", 1e-4), ("h16", 1e-4)])
 def test_emission_matches_scipy(eng, golden, precision, rtol):
