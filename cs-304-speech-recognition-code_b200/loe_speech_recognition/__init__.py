@@ -6,22 +6,31 @@ Same class names and signatures as the reference package (src/loe_speech_recogni
 __init__.py:11-30) for everything on that path; the computation runs in hand-written sm_100a
 CUDA kernels behind a C ABI (include/loe_b200.h).  There is no CPU fallback.
 
-Out of scope for this build: the TIDIGITS corpus walker, the
-energy-based silence stripper, the live microphone segmenter, template DTW, CSV and plot
-helpers.  Accessing those names raises NotImplementedError with this explanation.
+Host-side helpers around the path (corpus walker, '|'-separated result tables, result plots; SURVEY.md §8
+f1 / f4) are plain Python mirrors of the reference's modules.  Out of scope: the live microphone
+segmenter (``Segmentation``, needs sounddevice and audio hardware); accessing it raises NotImplementedError
+unless LOE_REFERENCE_SRC points at a reference checkout.
 """
 from .mfcc import MFCC
-from .ti_digits import TI_DIGITS_LABELS, TI_DIGITS_LABEL_TYPE
+from .ti_digits import TIDigits, DataLoader, TI_DIGITS_LABELS, TI_DIGITS_LABEL_TYPE
 from .hidden_markov_model import (Signal, HiddenMarkovModel, HiddenMarkovModelTrainable, HiddenMarkovModelInference,
                                   HiddenMarkovModelTrainContinuous)
 from .model_collection import ModelCollection
 from .signal_separation import SignalSeparation
 from .dynamic_time_wrapping import DynamicTimeWarping
+from .visualizer import plot_confusion_matrix_from_lists, plot_line
+from .csvnia import CSVReader, CSVWriter
 
 __all__ = [
     "MFCC",
+    "TIDigits",
+    "DataLoader",
     "TI_DIGITS_LABELS",
     "TI_DIGITS_LABEL_TYPE",
+    "plot_confusion_matrix_from_lists",
+    "plot_line",
+    "CSVReader",
+    "CSVWriter",
     "HiddenMarkovModel",
     "HiddenMarkovModelTrainable",
     "HiddenMarkovModelInference",
@@ -33,9 +42,7 @@ __all__ = [
 ]
 
 # name -> module of the reference that defines it (host-side I/O and tooling, not rebuilt here)
-_OUT_OF_SCOPE = {"Segmentation": "segmentation", "TIDigits": "ti_digits",
-                 "DataLoader": "ti_digits", "plot_confusion_matrix_from_lists": "visualizer", "plot_line": "visualizer",
-                 "CSVReader": "csvnia", "CSVWriter": "csvnia"}
+_OUT_OF_SCOPE = {"Segmentation": "segmentation"}
 
 
 def _configure_multiprocessing() -> None:
