@@ -8,7 +8,9 @@ pinned version; ``numpy==2.2.1`` in ``requirements.txt`` implies >= 0.10.2),
 which is neither vendored under ``/root/reference`` nor installable here, and
 the reference has no test or golden vector for it.  This file restates the
 published librosa >= 0.10 algorithm for exactly the calls the reference makes,
-built from the same scipy primitives librosa itself calls:
+built from the same scipy primitives librosa itself calls (cross-checked stage by stage against the
+librosa-compatible paths of transformers.audio_utils and torchaudio in
+tests/test_oracle_golden.py::test_mfcc_oracle_against_independent_librosa_restatements):
 
   melspectrogram(y, sr, n_mels=40, n_fft=320, hop_length=160,
                  fmin=133.33, fmax=6855.4976)          mfcc.py:31-34

@@ -123,3 +123,44 @@ def test_mfcc_oracle_regression(golden_mfcc):
     assert np.allclose(d1[:, 0], d1[:, 4], atol=1e-5) and np.allclose(d2[:, -1], d2[:, -5], atol=1e-5)
     T = 1 + 16000 // 160
     assert golden_mfcc["feat0"].shape == (39, T)
+
+
+def test_mfcc_oracle_against_independent_librosa_restatements():
+    """The MFCC oracle is "parity unpinned" (librosa is absent and un-pinned upstream).  Second opinions that ARE
+    installed: transformers.audio_utils and torchaudio both ship restatements of the same librosa recipe
+    (slaney mel scale + slaney area normalisation, centred periodic-Hann STFT, power_to_db, ortho DCT-II).  The
+    oracle's stages must agree with them on a seeded signal -- this pins the recipe's conventions (filter edges
+    and normalisation, window periodicity, zero centre padding, dB reference / floor, DCT scaling), not librosa's
+    last-ulp arithmetic."""
+    import pytest
+    from oracle import mfcc as OM
+    AU = pytest.importorskip("transformers.audio_utils")
+    rng = np.random.default_rng(4)
+    t = np.arange(16000)
+    y = (3000 * np.sin(2 * np.pi * 440 * t / 16000) + 1500 * np.sin(2 * np.pi * 2300 * t / 16000) + rng.normal(0, 30, t.size)).astype(np.float32)
+    # mel filterbank
+    fb = AU.mel_filter_bank(num_frequency_bins=161, num_mel_filters=40, min_frequency=OM.FMIN, max_frequency=OM.FMAX,
+                            sampling_rate=16000, norm="slaney", mel_scale="slaney")
+    mine = OM.mel_basis(16000)
+    assert fb.T.shape == mine.shape and np.abs(fb.T - mine).max() < 1e-7 * np.abs(mine).max()
+    # |STFT|^2 -> mel -> dB
+    win = AU.window_function(OM.N_FFT, "hann", periodic=True)
+    S = AU.spectrogram(y, win, frame_length=OM.N_FFT, hop_length=OM.HOP, fft_length=OM.N_FFT, power=2.0, center=True,
+                       pad_mode="constant", mel_filters=fb, mel_floor=0.0)
+    mel = np.einsum("ft,mf->mt", OM.stft_power(y), mine)
+    assert S.shape == mel.shape == (40, 101) and np.abs(S - mel).max() < 1e-5 * np.abs(mel).max()
+    db = AU.power_to_db(S, reference=S.max(), min_value=1e-10, db_range=80.0)
+    lm = OM.power_to_db(mel)
+    assert np.abs(db - lm).max() < 1e-3 and lm.max() == 0.0 and lm.min() >= -80.0
+    # DCT-II (ortho), 13 cepstra: torchaudio's matrix
+    torchaudio = pytest.importorskip("torchaudio")
+    dct = torchaudio.functional.create_dct(OM.N_MFCC, OM.N_MELS, norm="ortho").numpy().T          # (13, 40)
+    import scipy.fft
+    ceps = scipy.fft.dct(lm, axis=-2, type=2, norm="ortho")[:OM.N_MFCC]
+    assert np.abs(dct @ lm - ceps).max() < 1e-3
+    # and torchaudio's own mel spectrogram with the librosa-compatible switches
+    import torch
+    ms = torchaudio.transforms.MelSpectrogram(sample_rate=16000, n_fft=OM.N_FFT, win_length=OM.N_FFT, hop_length=OM.HOP,
+                                              f_min=OM.FMIN, f_max=OM.FMAX, n_mels=OM.N_MELS, power=2.0, center=True,
+                                              pad_mode="constant", norm="slaney", mel_scale="slaney")(torch.from_numpy(y)).numpy()
+    assert ms.shape == mel.shape and np.abs(ms - mel).max() < 1e-4 * np.abs(mel).max()
