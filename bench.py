@@ -45,7 +45,7 @@ PENALTY = -100                                                              # pr
 FLOPS_PER_FRAME = 2 * 40 * 39 * 58                                          # 2(D+1)D S, S = 58
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at the default workload (10 000 utterances, 3.84 M frames),
 # from the committed `ncu --set full` capture (profiles/r1f_kernels.txt); None = not captured
-NCU_TRAFFIC = {"mfcc_mel": 3052987000, "mfcc_ceps": 1213186000, "emission_tc": 2368057000, "emission_h16": 2215323000, "viterbi": 902897000}
+NCU_TRAFFIC = {"mfcc_mel": 3054942000, "mfcc_ceps": 1212502000, "emission_tc": 2368057000, "emission_h16": 2092383000, "viterbi": 899417000}
 
 
 def golden_params():
@@ -348,7 +348,7 @@ def impl_b200(args):
     tf32_peak = bf16 / 2      # TF32 is not in MEASURED_PEAKS.json: dense TF32 = half the bf16 rate
     n_samples = int(pcm_off[-1])
     # algorithmic work per launch and DRAM traffic per launch from the committed ncu capture
-    # (profiles/r1h_kernels.txt, emission_tc: r1f; dram__bytes_read.sum + dram__bytes_write.sum at this workload size)
+    # (profiles/r1j_kernels.txt, emission_tc: r1f; dram__bytes_read.sum + dram__bytes_write.sum at this workload size)
     kernels = {
         "mfcc_mel_kernel": {"bound": "hbm", "alg": 4 * n_samples + 160 * F, "ms": stage_ms["mfcc_mel"], "traffic": NCU_TRAFFIC.get("mfcc_mel")},
         "mfcc_ceps_kernel": {"bound": "hbm", "alg": (160 + 156) * F, "ms": stage_ms["mfcc_ceps"], "traffic": NCU_TRAFFIC.get("mfcc_ceps")},
