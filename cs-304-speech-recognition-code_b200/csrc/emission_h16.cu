@@ -30,7 +30,7 @@ constexpr int kDim = 39;
 constexpr int kK = 40;                  // 39 features + the constant 1 of the bias row
 constexpr int kChunksPerPart = kK / 8;  // 16-byte chunks (8 halfs) of one hi or lo part: 5
 constexpr int kAChunks = 2 * kChunksPerPart + 1;   // hi 0-4, lo 5-9, zero 10
-constexpr int kBChunks = 2 * kChunksPerPart + 1;   // hi 0-4, lo 5-9, copy of hi chunk 4 at 10
+constexpr int kBChunks = 3 * kChunksPerPart;       // hi 0-4, lo 5-9, second copy of hi at 10-14
 constexpr int kColsPerState = 40;
 constexpr int kStatesPerTile = 6;
 constexpr int kTileN = kStatesPerTile * kColsPerState;   // 240
@@ -43,12 +43,19 @@ constexpr int kThreads = kProducerThreads + kEpilogueThreads + 32;
 constexpr int kALbo = kTileM * 16;      // 2048 B between K-adjacent A chunks
 constexpr int kBLbo = kTileN * 16;      // 3840 B between K-adjacent B chunks
 constexpr int kABytes = kAChunks * kALbo;   // 22528
-constexpr int kBBytes = kBChunks * kBLbo;   // 42240
-constexpr int kProducerRegs = 104;
-constexpr int kEpilogueRegs = 176;
+constexpr int kBBytes = kBChunks * kBLbo;   // 57600
+constexpr int kProducerRegs = 88;
+constexpr int kEpilogueRegs = 208;
 constexpr int kNumMma = 8;
-constexpr int kRawBufs = 4;
-constexpr int kHalves = 2;              // 6-state column tiles per CTA: a staged feature tile is multiplied with both
+#ifndef LOE_H16_RAW_BUFS
+#define LOE_H16_RAW_BUFS 2
+#endif
+constexpr int kRawBufs = LOE_H16_RAW_BUFS;     // a power of two, a multiple of the producer groups
+static_assert((kRawBufs & (kRawBufs - 1)) == 0 && kRawBufs >= 2, "raw buffer ring");
+#ifndef LOE_H16_HALVES
+#define LOE_H16_HALVES 2
+#endif
+constexpr int kHalves = LOE_H16_HALVES;              // 6-state column tiles per CTA: a staged feature tile is multiplied with both
 
 struct __align__(128) Smem {
     uint8_t b[kHalves][kBBytes];
@@ -62,17 +69,28 @@ struct __align__(128) Smem {
     uint32_t tmem_base;
 };
 
-// the 8 MMAs: (first A chunk, second A chunk, first B chunk, second B chunk)
+// W_s is lower triangular (feature k feeds the columns j <= k; the bias row 39 feeds all), and the accumulator
+// columns are ordered [left block: state x 24 columns j < 24][right block: state x 16 columns j >= 24]: the K chunks
+// 0-2 (features 0-23) cannot reach the right block, so their MMAs are issued with N = 144 instead of 240.  The 15
+// (A chunk, B chunk) products pair up into 8 MMAs of K = 16:
+//   (first A chunk, second A chunk, first B chunk, second B chunk, N), widest first -- the first MMA overwrites all
+//   240 columns, the others accumulate
+constexpr int kLeftCols = 24, kRightCols = kColsPerState - kLeftCols;       // per state
+constexpr int kLeftN = kStatesPerTile * kLeftCols;                         // 144
 __host__ __device__ constexpr int pair_chunk(int mma, int which) {
-    constexpr int t[kNumMma][4] = {
-        {0, 1, 0, 1}, {2, 3, 2, 3},          // hi * hi
-        {5, 6, 0, 1}, {7, 8, 2, 3},          // lo * hi
-        {0, 1, 5, 6}, {2, 3, 7, 8},          // hi * lo
-        {4, 9, 4, 10},                       // hi4 * hi4 + lo4 * hi4 (copy)
-        {4, 10, 9, 10},                      // hi4 * lo4 + zero * (anything)
+    constexpr int t[kNumMma][5] = {
+        {4, 9, 4, 14, kTileN},         // hi4 * hi4 + lo4 * hi4
+        {4, 10, 9, 14, kTileN},        // hi4 * lo4 + zero * (anything finite)
+        {3, 8, 3, 13, kTileN},         // hi3 * hi3 + lo3 * hi3
+        {2, 3, 7, 8, kTileN},          // hi2 * lo2 + hi3 * lo3
+        {2, 7, 2, 12, kLeftN},         // hi2 * hi2 + lo2 * hi2
+        {1, 6, 1, 11, kLeftN},         // hi1 * hi1 + lo1 * hi1
+        {0, 1, 5, 6, kLeftN},          // hi0 * lo0 + hi1 * lo1
+        {0, 5, 0, 10, kLeftN},         // hi0 * hi0 + lo0 * hi0
     };
     return t[mma][which];
 }
+static_assert(kLeftN % 16 == 0 && kTileN % 16 == 0 && kLeftCols % 8 == 0, "MMA N granularity / chunk alignment of the blocks");
 
 // hi/lo split of 8 consecutive values into one 16-byte chunk each (packed conversions: F2FP converts two
 // values per instruction, the scalar F2F runs on the slow conversion pipe)
@@ -146,7 +164,7 @@ __device__ __forceinline__ float sumsq39(const float* v) {
 }
 
 // The CTA is launched with 128 registers per thread (13 warps are allocated like 16: 16 x 32 x 128 is the whole
-// file).  The two producer warpgroups hand 24 registers per thread back (setmaxnreg.dec) and the epilogue
+// file).  The two producer warpgroups hand 40 registers per thread back (setmaxnreg.dec) and the epilogue
 // warpgroup takes them (setmaxnreg.inc) for its 120-column accumulator slice.
 __global__ void __launch_bounds__(kThreads, 1)
 emission_h16_kernel(const float* __restrict__ feat, int64_t n_frames, const uint8_t* __restrict__ b_packed,
@@ -213,7 +231,7 @@ emission_h16_kernel(const float* __restrict__ feat, int64_t n_frames, const uint
         const int row_id = tid & (kTileM - 1);
         const int p = tid >> 7;
         auto issue = [&](int it) {                       // one thread: full tiles are contiguous and 16-byte aligned
-            bulk_load(sm.raw[it & 3], feat + (int64_t)(g + it * G) * kTileElems, kTileBytes, &sm.raw_full[it & 3]);
+            bulk_load(sm.raw[it & (kRawBufs - 1)], feat + (int64_t)(g + it * G) * kTileElems, kTileBytes, &sm.raw_full[it & (kRawBufs - 1)]);
         };
         if (row_id == 0)
             for (int it = p; it < kRawBufs && it < n_it; it += kProducerGroups)
@@ -221,9 +239,9 @@ emission_h16_kernel(const float* __restrict__ feat, int64_t n_frames, const uint
         for (int it = p; it < n_it; it += kProducerGroups) {
             const int st = it & 1;
             const uint32_t k = (uint32_t)(it >> 1);
-            float* raw = sm.raw[it & 3];
+            float* raw = sm.raw[it & (kRawBufs - 1)];
             if (tile_full(it)) {
-                mbar_wait(&sm.raw_full[it & 3], (uint32_t)(it >> 2) & 1);         // TMA bytes have landed
+                mbar_wait(&sm.raw_full[it & (kRawBufs - 1)], (uint32_t)(it / kRawBufs) & 1);         // TMA bytes have landed
             } else {
                 // the batch's last, partial tile: plain loads, rows beyond the end read as zero
                 const int64_t f0 = (int64_t)(g + it * G) * kTileM;
@@ -237,18 +255,19 @@ emission_h16_kernel(const float* __restrict__ feat, int64_t n_frames, const uint
             fence_proxy_async();
             mbar_arrive(&sm.a_full[st]);
             asm volatile("bar.sync %0, 128;" ::"r"(1 + p) : "memory");   // the group is done with this raw buffer: refill it
-            if (row_id == 0 && it + 4 < n_it && tile_full(it + 4)) issue(it + 4);
+            if (row_id == 0 && it + kRawBufs < n_it && tile_full(it + kRawBufs)) issue(it + kRawBufs);
         }
     } else if (warp == (kProducerThreads + kEpilogueThreads) / 32) {
         // =========================== MMA issuer ===========================
         if (lane == 0) {
-            // c_format F32 (bit 4), a/b format F16 (0), N >> 3 at bit 17, M >> 4 at bit 24; MMA N: multiple of 16
-            uint32_t idesc[kHalves];
+            // c_format F32 (bit 4), a/b format F16 (0), N >> 3 at bit 17, M >> 4 at bit 24
+            uint32_t idesc[kNumMma];
             uint64_t b_desc[kHalves][kNumMma];
 #pragma unroll
+            for (int i = 0; i < kNumMma; ++i)
+                idesc[i] = (1u << 4) | ((uint32_t)(pair_chunk(i, 4) >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+#pragma unroll
             for (int h = 0; h < kHalves; ++h) {
-                const int n_cols = ((max(valid_of(h), 1) * kColsPerState + 15) / 16) * 16;
-                idesc[h] = (1u << 4) | ((uint32_t)(n_cols >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
                 const uint32_t b_base = smem_u32(sm.b[h]);
 #pragma unroll
                 for (int i = 0; i < kNumMma; ++i)
@@ -270,7 +289,7 @@ emission_h16_kernel(const float* __restrict__ feat, int64_t n_frames, const uint
 #pragma unroll
                     for (int i = 0; i < kNumMma; ++i)
                         mma_f16(d, make_desc(a_base + pair_chunk(i, 0) * kALbo, (pair_chunk(i, 1) - pair_chunk(i, 0)) * kALbo),
-                                b_desc[h][i], idesc[h], i ? 1u : 0u);
+                                b_desc[h][i], idesc[i], i ? 1u : 0u);
                     if (h == H - 1) mma_commit(&sm.a_empty[st]);     // the stage is free once this tile's last product has run
                     mma_commit(&sm.tmem_full[s]);
                     ++j;
@@ -326,30 +345,42 @@ emission_h16_kernel(const float* __restrict__ feat, int64_t n_frames, const uint
                 // round trip (a couple of hundred cycles with four warps draining), not the bytes, so an accumulator is
                 // drained in two waits instead of six and handed back to the MMA warp as soon as the second round sits
                 // in registers, before any of its arithmetic.
-                float v[3 * kColsPerState];
-                auto load3 = [&](uint32_t t) {
+                // Accumulator columns: left blocks (24 columns each) of states 0-5 at 0..143, right blocks (16 columns each)
+                // at 144..239.  Round 1 = columns 0..119 = the left blocks of states 0-4; round 2 = the left block of
+                // state 5 and all right blocks.  The padding column of every state is an exact zero: all 40 are summed.
+                float v[kTileN / 2];
+                auto load_half = [&](uint32_t t) {
                     tmem_ld64(t, v);
                     tmem_ld32(t + 64, v + 64);
                     tmem_ld16(t + 96, v + 96);
                     tmem_ld8(t + 112, v + 112);
                 };
-                float score[kStatesPerTile];
+                auto sumsq = [&](const float* x, int n, unsigned long long acc) {       // n even, compile-time
+#pragma unroll
+                    for (int c = 0; c < n; c += 2) acc = ffma2(pack_f2(x[c], x[c + 1]), acc);
+                    return acc;
+                };
                 const float* cst = sm.cst + h * kStatesPerTile;
-                load3(taddr);
+                unsigned long long acc[kStatesPerTile];
+                load_half(taddr);
                 if (m_prev >= 0) store_tile(m_prev, h_prev);     // previous scores: shared memory -> global
                 const float mhalf = -0.5f * sm.inv2[it & 3][r];  // exact: inv2 is a power of two (1 for ordinary rows)
                 tmem_ld_wait();
 #pragma unroll
-                for (int c = 0; c < 3; ++c) score[c] = (c < valid) ? fmaf(mhalf, sumsq39(v + c * kColsPerState), cst[c]) : 0.f;
-                if (valid > 3) {                                 // warp-uniform: a narrow last tile may end here
-                    load3(taddr + 3 * kColsPerState);
-                    tmem_ld_wait();
-                }
+                for (int c = 0; c < 5; ++c) acc[c] = sumsq(v + c * kLeftCols, kLeftCols, 0ull);
+                load_half(taddr + kTileN / 2);
+                tmem_ld_wait();
                 tc_fence_before();
                 mbar_arrive(&sm.tmem_empty[s]);
+                acc[5] = sumsq(v, kLeftCols, 0ull);
 #pragma unroll
-                for (int c = 3; c < kStatesPerTile; ++c)
-                    score[c] = (c < valid) ? fmaf(mhalf, sumsq39(v + (c - 3) * kColsPerState), cst[c]) : 0.f;
+                for (int c = 0; c < kStatesPerTile; ++c) acc[c] = sumsq(v + kLeftCols + c * kRightCols, kRightCols, acc[c]);
+                float score[kStatesPerTile];
+#pragma unroll
+                for (int c = 0; c < kStatesPerTile; ++c) {
+                    const float2 f = unpack_f2(acc[c]);
+                    score[c] = (c < valid) ? fmaf(mhalf, f.x + f.y, cst[c]) : 0.f;
+                }
 #pragma unroll
                 for (int c = 0; c < 3; ++c) stage[lane * 3 + c] = make_float2(score[2 * c], score[2 * c + 1]);
                 __syncwarp();

@@ -117,25 +117,38 @@ def pack_tc_image(means: np.ndarray, us: np.ndarray, cst: np.ndarray):
 H16_MAX = 32768.0
 
 
+H16_LEFT_COLS = 24        # accumulator columns j < 24 of every state form the "left" block (csrc/emission_h16.cu)
+
+
 def pack_h16_image(means: np.ndarray, us: np.ndarray, cst: np.ndarray):
     """Host pre-pack of the 3xFP16 tensor-core operand (layout documented at loe_emission_h16_dev), or
-    None when an entry of W_s = [U_s ; -mean_s.U_s] leaves the binary16 range."""
+    None when an entry of the operand leaves the binary16 range.
+
+    The kernel only needs |U_s^T (x - mean_s)|, so the whitening matrix may be replaced by any W with
+    W W^T = U_s U_s^T.  U_s^T = Q R gives W = R^T, LOWER TRIANGULAR: feature k only reaches the columns
+    j <= k.  With the accumulator columns ordered [left block: state x columns 0-23][right block: state x
+    columns 24-39], the K chunks of the features 0-23 cannot reach the right block and their MMAs are issued
+    with N = 144 instead of 240 -- 80 % of the dense MMA work.  Row 39 is the bias -mean_s . W (dense),
+    column 39 an exact zero."""
     S, D = means.shape
     spt, cols, K = 6, 40, 40
     n_tiles = (S + spt - 1) // spt
     W = np.zeros((n_tiles * spt, K, cols), dtype=np.float64)
-    W[:S, :D, :D] = us
-    W[:S, D, :D] = -np.einsum("si,sij->sj", means, us)
+    for s in range(S):
+        r = np.linalg.qr(np.asarray(us[s], dtype=np.float64).T, mode="r")      # upper triangular, |R d| = |U^T d|
+        W[s, :D, :D] = np.tril(r.T)
+        W[s, D, :D] = -means[s] @ W[s, :D, :D]
     if not np.all(np.abs(W) < H16_MAX):          # also rejects NaN / inf
         return None
     hi = W.astype(np.float16)
     lo = (W - hi.astype(np.float64)).astype(np.float16)
-    out = np.empty((n_tiles, 11, spt * cols, 8), dtype=np.float16)
-    for base, part in ((0, hi), (5, lo)):
-        # part [tile, state_local, k, j] -> [tile, kc, n = state_local*40 + j, q]
-        p = part.reshape(n_tiles, spt, K // 8, 8, cols)            # [t, sl, kc, q, j]
-        out[:, base:base + 5] = p.transpose(0, 2, 1, 4, 3).reshape(n_tiles, K // 8, spt * cols, 8)
-    out[:, 10] = out[:, 4]
+    L = H16_LEFT_COLS
+    out = np.empty((n_tiles, 15, spt * cols, 8), dtype=np.float16)
+    for base, part in ((0, hi), (5, lo), (10, hi)):
+        p = part.reshape(n_tiles, spt, K // 8, 8, cols)                 # [t, sl, kc, q, j]
+        left = p[..., :L].transpose(0, 2, 1, 4, 3).reshape(n_tiles, K // 8, spt * L, 8)              # n = sl * 24 + j
+        right = p[..., L:].transpose(0, 2, 1, 4, 3).reshape(n_tiles, K // 8, spt * (cols - L), 8)    # n = 144 + sl * 16 + (j - 24)
+        out[:, base:base + 5] = np.concatenate((left, right), axis=2)
     return np.ascontiguousarray(out.reshape(-1))
 
 
