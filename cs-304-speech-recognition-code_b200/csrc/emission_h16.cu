@@ -70,27 +70,35 @@ struct __align__(128) Smem {
 };
 
 // W_s is lower triangular (feature k feeds the columns j <= k; the bias row 39 feeds all), and the accumulator
-// columns are ordered [left block: state x 24 columns j < 24][right block: state x 16 columns j >= 24]: the K chunks
-// 0-2 (features 0-23) cannot reach the right block, so their MMAs are issued with N = 144 instead of 240.  The 15
-// (A chunk, B chunk) products pair up into 8 MMAs of K = 16:
+// columns are ordered in three blocks, [state x columns 0-15][state x columns 16-31][state x columns 32-39]
+// (96 + 96 + 48 columns): the K chunks 0-1 (features 0-15) only reach the first block, chunks 2-3 the first two,
+// so their MMAs are issued with N = 96 / 192 instead of 240 -- 70 % of the dense MMA work.  The 15 (A chunk,
+// B chunk) products pair up into 8 MMAs of K = 16:
 //   (first A chunk, second A chunk, first B chunk, second B chunk, N), widest first -- the first MMA overwrites all
 //   240 columns, the others accumulate
-constexpr int kLeftCols = 24, kRightCols = kColsPerState - kLeftCols;       // per state
-constexpr int kLeftN = kStatesPerTile * kLeftCols;                         // 144
+constexpr int kBlocks = 3;
+__host__ __device__ constexpr int block_width(int b) { return b == 0 ? 16 : b == 1 ? 16 : 8; }           // columns per state
+__host__ __device__ constexpr int block_start(int b) { return b == 0 ? 0 : kStatesPerTile * block_width(0) + (b == 1 ? 0 : kStatesPerTile * block_width(1)); }
+constexpr int kN1 = block_start(1), kN2 = block_start(2);                  // 96, 192
 __host__ __device__ constexpr int pair_chunk(int mma, int which) {
     constexpr int t[kNumMma][5] = {
         {4, 9, 4, 14, kTileN},         // hi4 * hi4 + lo4 * hi4
         {4, 10, 9, 14, kTileN},        // hi4 * lo4 + zero * (anything finite)
-        {3, 8, 3, 13, kTileN},         // hi3 * hi3 + lo3 * hi3
-        {2, 3, 7, 8, kTileN},          // hi2 * lo2 + hi3 * lo3
-        {2, 7, 2, 12, kLeftN},         // hi2 * hi2 + lo2 * hi2
-        {1, 6, 1, 11, kLeftN},         // hi1 * hi1 + lo1 * hi1
-        {0, 1, 5, 6, kLeftN},          // hi0 * lo0 + hi1 * lo1
-        {0, 5, 0, 10, kLeftN},         // hi0 * hi0 + lo0 * hi0
+        {3, 8, 3, 13, kN2},            // hi3 * hi3 + lo3 * hi3
+        {2, 3, 7, 8, kN2},             // hi2 * lo2 + hi3 * lo3
+        {2, 7, 2, 12, kN2},            // hi2 * hi2 + lo2 * hi2
+        {1, 6, 1, 11, kN1},            // hi1 * hi1 + lo1 * hi1
+        {0, 1, 5, 6, kN1},             // hi0 * lo0 + hi1 * lo1
+        {0, 5, 0, 10, kN1},            // hi0 * hi0 + lo0 * hi0
     };
     return t[mma][which];
 }
-static_assert(kLeftN % 16 == 0 && kTileN % 16 == 0 && kLeftCols % 8 == 0, "MMA N granularity / chunk alignment of the blocks");
+// state that owns accumulator column n
+__host__ __device__ constexpr int state_of(int n) {
+    return n < kN1 ? n / block_width(0) : n < kN2 ? (n - kN1) / block_width(1) : (n - kN2) / block_width(2);
+}
+static_assert(kN1 % 16 == 0 && kN2 % 16 == 0 && kTileN % 16 == 0, "MMA N granularity");
+static_assert(block_width(0) + block_width(1) + block_width(2) == kColsPerState, "blocks cover a state's columns");
 
 // hi/lo split of 8 consecutive values into one 16-byte chunk each (packed conversions: F2FP converts two
 // values per instruction, the scalar F2F runs on the slow conversion pipe)
@@ -345,9 +353,9 @@ emission_h16_kernel(const float* __restrict__ feat, int64_t n_frames, const uint
                 // round trip (a couple of hundred cycles with four warps draining), not the bytes, so an accumulator is
                 // drained in two waits instead of six and handed back to the MMA warp as soon as the second round sits
                 // in registers, before any of its arithmetic.
-                // Accumulator columns: left blocks (24 columns each) of states 0-5 at 0..143, right blocks (16 columns each)
-                // at 144..239.  Round 1 = columns 0..119 = the left blocks of states 0-4; round 2 = the left block of
-                // state 5 and all right blocks.  The padding column of every state is an exact zero: all 40 are summed.
+                // Two rounds of 120 accumulator columns; column n belongs to state_of(n) (pieces of 16 / 16 / 8 columns, so
+                // a pair of neighbouring columns never straddles two states).  The padding column of every state is an
+                // exact zero: all 40 are summed.
                 float v[kTileN / 2];
                 auto load_half = [&](uint32_t t) {
                     tmem_ld64(t, v);
@@ -355,26 +363,23 @@ emission_h16_kernel(const float* __restrict__ feat, int64_t n_frames, const uint
                     tmem_ld16(t + 96, v + 96);
                     tmem_ld8(t + 112, v + 112);
                 };
-                auto sumsq = [&](const float* x, int n, unsigned long long acc) {       // n even, compile-time
-#pragma unroll
-                    for (int c = 0; c < n; c += 2) acc = ffma2(pack_f2(x[c], x[c + 1]), acc);
-                    return acc;
-                };
                 const float* cst = sm.cst + h * kStatesPerTile;
                 unsigned long long acc[kStatesPerTile];
+#pragma unroll
+                for (int c = 0; c < kStatesPerTile; ++c) acc[c] = 0ull;
                 load_half(taddr);
                 if (m_prev >= 0) store_tile(m_prev, h_prev);     // previous scores: shared memory -> global
                 const float mhalf = -0.5f * sm.inv2[it & 3][r];  // exact: inv2 is a power of two (1 for ordinary rows)
                 tmem_ld_wait();
 #pragma unroll
-                for (int c = 0; c < 5; ++c) acc[c] = sumsq(v + c * kLeftCols, kLeftCols, 0ull);
+                for (int n = 0; n < kTileN / 2; n += 2) acc[state_of(n)] = ffma2(pack_f2(v[n], v[n + 1]), acc[state_of(n)]);
                 load_half(taddr + kTileN / 2);
                 tmem_ld_wait();
                 tc_fence_before();
                 mbar_arrive(&sm.tmem_empty[s]);
-                acc[5] = sumsq(v, kLeftCols, 0ull);
 #pragma unroll
-                for (int c = 0; c < kStatesPerTile; ++c) acc[c] = sumsq(v + kLeftCols + c * kRightCols, kRightCols, acc[c]);
+                for (int n = 0; n < kTileN / 2; n += 2)
+                    acc[state_of(kTileN / 2 + n)] = ffma2(pack_f2(v[n], v[n + 1]), acc[state_of(kTileN / 2 + n)]);
                 float score[kStatesPerTile];
 #pragma unroll
                 for (int c = 0; c < kStatesPerTile; ++c) {

@@ -117,7 +117,7 @@ def pack_tc_image(means: np.ndarray, us: np.ndarray, cst: np.ndarray):
 H16_MAX = 32768.0
 
 
-H16_LEFT_COLS = 24        # accumulator columns j < 24 of every state form the "left" block (csrc/emission_h16.cu)
+H16_BLOCK_WIDTHS = (16, 16, 8)    # accumulator column blocks per state (csrc/emission_h16.cu: block_width)
 
 
 def pack_h16_image(means: np.ndarray, us: np.ndarray, cst: np.ndarray):
@@ -126,10 +126,10 @@ def pack_h16_image(means: np.ndarray, us: np.ndarray, cst: np.ndarray):
 
     The kernel only needs |U_s^T (x - mean_s)|, so the whitening matrix may be replaced by any W with
     W W^T = U_s U_s^T.  U_s^T = Q R gives W = R^T, LOWER TRIANGULAR: feature k only reaches the columns
-    j <= k.  With the accumulator columns ordered [left block: state x columns 0-23][right block: state x
-    columns 24-39], the K chunks of the features 0-23 cannot reach the right block and their MMAs are issued
-    with N = 144 instead of 240 -- 80 % of the dense MMA work.  Row 39 is the bias -mean_s . W (dense),
-    column 39 an exact zero."""
+    j <= k.  With the accumulator columns ordered in three blocks, [state x columns 0-15][state x columns
+    16-31][state x columns 32-39], the K chunks of the features 0-15 only reach the first block and those of
+    the features 16-31 the first two: their MMAs are issued with N = 96 / 192 instead of 240 -- 70 % of the
+    dense MMA work.  Row 39 is the bias -mean_s . W (dense), column 39 an exact zero."""
     S, D = means.shape
     spt, cols, K = 6, 40, 40
     n_tiles = (S + spt - 1) // spt
@@ -142,13 +142,14 @@ def pack_h16_image(means: np.ndarray, us: np.ndarray, cst: np.ndarray):
         return None
     hi = W.astype(np.float16)
     lo = (W - hi.astype(np.float64)).astype(np.float16)
-    L = H16_LEFT_COLS
     out = np.empty((n_tiles, 15, spt * cols, 8), dtype=np.float16)
     for base, part in ((0, hi), (5, lo), (10, hi)):
         p = part.reshape(n_tiles, spt, K // 8, 8, cols)                 # [t, sl, kc, q, j]
-        left = p[..., :L].transpose(0, 2, 1, 4, 3).reshape(n_tiles, K // 8, spt * L, 8)              # n = sl * 24 + j
-        right = p[..., L:].transpose(0, 2, 1, 4, 3).reshape(n_tiles, K // 8, spt * (cols - L), 8)    # n = 144 + sl * 16 + (j - 24)
-        out[:, base:base + 5] = np.concatenate((left, right), axis=2)
+        blocks, j0 = [], 0
+        for w in H16_BLOCK_WIDTHS:                                      # block b: n = start_b + sl * w + (j - j0)
+            blocks.append(p[..., j0:j0 + w].transpose(0, 2, 1, 4, 3).reshape(n_tiles, K // 8, spt * w, 8))
+            j0 += w
+        out[:, base:base + 5] = np.concatenate(blocks, axis=2)
     return np.ascontiguousarray(out.reshape(-1))
 
 
