@@ -70,35 +70,28 @@ struct __align__(128) Smem {
 };
 
 // W_s is lower triangular (feature k feeds the columns j <= k; the bias row 39 feeds all), and the accumulator
-// columns are ordered in three blocks, [state x columns 0-15][state x columns 16-31][state x columns 32-39]
-// (96 + 96 + 48 columns): the K chunks 0-1 (features 0-15) only reach the first block, chunks 2-3 the first two,
-// so their MMAs are issued with N = 96 / 192 instead of 240 -- 70 % of the dense MMA work.  The 15 (A chunk,
-// B chunk) products pair up into 8 MMAs of K = 16:
-//   (first A chunk, second A chunk, first B chunk, second B chunk, N), widest first -- the first MMA overwrites all
-//   240 columns, the others accumulate
-constexpr int kBlocks = 3;
-__host__ __device__ constexpr int block_width(int b) { return b == 0 ? 16 : b == 1 ? 16 : 8; }           // columns per state
-__host__ __device__ constexpr int block_start(int b) { return b == 0 ? 0 : kStatesPerTile * block_width(0) + (b == 1 ? 0 : kStatesPerTile * block_width(1)); }
-constexpr int kN1 = block_start(1), kN2 = block_start(2);                  // 96, 192
+// columns are ordered in five blocks of 48, [column block b = j / 8][state][j % 8]: the K chunk c (features 8c ..
+// 8c + 7) only reaches the blocks 0 .. c, so its MMAs are issued with N = 48 (c + 1) instead of 240 -- 65 % of the
+// dense MMA work.  The 15 (A chunk, B chunk) products pair up into 8 MMAs of K = 16:
+//   (first A chunk, second A chunk, first B chunk, second B chunk, column blocks), widest first -- the first MMA
+//   overwrites all 240 columns, the others accumulate
+constexpr int kBlockCols = kStatesPerTile * 8;      // 48 accumulator columns per column block
 __host__ __device__ constexpr int pair_chunk(int mma, int which) {
     constexpr int t[kNumMma][5] = {
-        {4, 9, 4, 14, kTileN},         // hi4 * hi4 + lo4 * hi4
-        {4, 10, 9, 14, kTileN},        // hi4 * lo4 + zero * (anything finite)
-        {3, 8, 3, 13, kN2},            // hi3 * hi3 + lo3 * hi3
-        {2, 3, 7, 8, kN2},             // hi2 * lo2 + hi3 * lo3
-        {2, 7, 2, 12, kN2},            // hi2 * hi2 + lo2 * hi2
-        {1, 6, 1, 11, kN1},            // hi1 * hi1 + lo1 * hi1
-        {0, 1, 5, 6, kN1},             // hi0 * lo0 + hi1 * lo1
-        {0, 5, 0, 10, kN1},            // hi0 * hi0 + lo0 * hi0
+        {4, 9, 4, 14, 5},          // hi4 * hi4 + lo4 * hi4
+        {4, 10, 9, 14, 5},         // hi4 * lo4 + zero * (anything finite)
+        {3, 8, 3, 13, 4},          // hi3 * hi3 + lo3 * hi3
+        {2, 3, 7, 8, 4},           // hi2 * lo2 + hi3 * lo3
+        {2, 7, 2, 12, 3},          // hi2 * hi2 + lo2 * hi2
+        {1, 6, 1, 11, 2},          // hi1 * hi1 + lo1 * hi1
+        {0, 1, 5, 6, 2},           // hi0 * lo0 + hi1 * lo1
+        {0, 5, 0, 10, 1},          // hi0 * hi0 + lo0 * hi0
     };
     return t[mma][which];
 }
-// state that owns accumulator column n
-__host__ __device__ constexpr int state_of(int n) {
-    return n < kN1 ? n / block_width(0) : n < kN2 ? (n - kN1) / block_width(1) : (n - kN2) / block_width(2);
-}
-static_assert(kN1 % 16 == 0 && kN2 % 16 == 0 && kTileN % 16 == 0, "MMA N granularity");
-static_assert(block_width(0) + block_width(1) + block_width(2) == kColsPerState, "blocks cover a state's columns");
+// state that owns accumulator column n (a pair of neighbouring columns never straddles two states)
+__host__ __device__ constexpr int state_of(int n) { return (n % kBlockCols) / 8; }
+static_assert(kBlockCols % 16 == 0 && 5 * kBlockCols == kTileN, "MMA N granularity / blocks cover the tile");
 
 // hi/lo split of 8 consecutive values into one 16-byte chunk each (packed conversions: F2FP converts two
 // values per instruction, the scalar F2F runs on the slow conversion pipe)
@@ -273,7 +266,7 @@ emission_h16_kernel(const float* __restrict__ feat, int64_t n_frames, const uint
             uint64_t b_desc[kHalves][kNumMma];
 #pragma unroll
             for (int i = 0; i < kNumMma; ++i)
-                idesc[i] = (1u << 4) | ((uint32_t)(pair_chunk(i, 4) >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+                idesc[i] = (1u << 4) | ((uint32_t)((pair_chunk(i, 4) * kBlockCols) >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
 #pragma unroll
             for (int h = 0; h < kHalves; ++h) {
                 const uint32_t b_base = smem_u32(sm.b[h]);
@@ -353,8 +346,8 @@ emission_h16_kernel(const float* __restrict__ feat, int64_t n_frames, const uint
                 // round trip (a couple of hundred cycles with four warps draining), not the bytes, so an accumulator is
                 // drained in two waits instead of six and handed back to the MMA warp as soon as the second round sits
                 // in registers, before any of its arithmetic.
-                // Two rounds of 120 accumulator columns; column n belongs to state_of(n) (pieces of 16 / 16 / 8 columns, so
-                // a pair of neighbouring columns never straddles two states).  The padding column of every state is an
+                // Two rounds of 120 accumulator columns; column n belongs to state_of(n) (pieces of 8 columns, so a pair of
+                // neighbouring columns never straddles two states).  The padding column of every state is an
                 // exact zero: all 40 are summed.
                 float v[kTileN / 2];
                 auto load_half = [&](uint32_t t) {

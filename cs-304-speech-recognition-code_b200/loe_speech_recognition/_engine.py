@@ -117,7 +117,7 @@ def pack_tc_image(means: np.ndarray, us: np.ndarray, cst: np.ndarray):
 H16_MAX = 32768.0
 
 
-H16_BLOCK_WIDTHS = (16, 16, 8)    # accumulator column blocks per state (csrc/emission_h16.cu: block_width)
+H16_BLOCK_WIDTHS = (8, 8, 8, 8, 8)    # accumulator column blocks per state (csrc/emission_h16.cu)
 
 
 def pack_h16_image(means: np.ndarray, us: np.ndarray, cst: np.ndarray):
@@ -126,10 +126,9 @@ def pack_h16_image(means: np.ndarray, us: np.ndarray, cst: np.ndarray):
 
     The kernel only needs |U_s^T (x - mean_s)|, so the whitening matrix may be replaced by any W with
     W W^T = U_s U_s^T.  U_s^T = Q R gives W = R^T, LOWER TRIANGULAR: feature k only reaches the columns
-    j <= k.  With the accumulator columns ordered in three blocks, [state x columns 0-15][state x columns
-    16-31][state x columns 32-39], the K chunks of the features 0-15 only reach the first block and those of
-    the features 16-31 the first two: their MMAs are issued with N = 96 / 192 instead of 240 -- 70 % of the
-    dense MMA work.  Row 39 is the bias -mean_s . W (dense), column 39 an exact zero."""
+    j <= k.  With the accumulator columns ordered [column block j // 8][state][j % 8], the K chunk c of 8
+    features only reaches the first 48 (c + 1) columns and its MMAs are issued with that N instead of 240 --
+    65 % of the dense MMA work.  Row 39 is the bias -mean_s . W (dense), column 39 an exact zero."""
     S, D = means.shape
     spt, cols, K = 6, 40, 40
     n_tiles = (S + spt - 1) // spt

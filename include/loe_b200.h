@@ -127,17 +127,14 @@ int loe_emission_tc_dev(const float* feat_dev, int64_t n_frames, int dim, const 
 
 /* 3xFP16 variant of loe_emission_tc_dev (csrc/emission_h16.cu): the operands are split into two
  * binary16 parts (the same 22 significant bits as the TF32 pair) and run as kind::f16 MMAs, 8 per
- * 128-frame tile against 15, six of them over 96 or 192 of the 240 columns -- more than twice the throughput at the
+ * 128-frame tile against 15, six of them over 48 to 192 of the 240 columns -- more than twice the throughput at the
  * same measured accuracy.
  * b_packed_dev: per tile of 6 states loe_emission_h16_tile_bytes() (= 57600) bytes of binary16,
- *   [chunk c (15)][n (240)][q (8)] with W_s[k][j], k = 8*(c % 5) + q, and the accumulator column n in three
- *   blocks: n = state_local*16 + j (j < 16), n = 96 + state_local*16 + (j - 16) (16 <= j < 32),
- *   n = 192 + state_local*8 + (j - 32) (j >= 32);
+ *   [chunk c (15)][n = (j/8)*48 + state_local*8 + j%8 (240)][q (8)] with W_s[k][j], k = 8*(c % 5) + q:
  *   chunks 0-4 = fp16(W), chunks 5-9 = fp16(W - fp16(W)), chunks 10-14 = chunks 0-4 again.
  *   W_s = [ R_s^T ; -mean_s . R_s^T ] with U_s^T = Q R_s (any W with W W^T = U_s U_s^T scores alike):
- *   W_s MUST be lower triangular in its first 39 rows (W_s[k][j] = 0 for j > k) -- the kernel does not multiply
- *   the features 0-15 with the columns >= 16 nor the features 16-31 with the columns >= 32 -- and column 39 and
- *   states >= n_states zero.
+ *   W_s MUST be lower triangular in its first 39 rows (W_s[k][j] = 0 for j > k) -- the kernel multiplies the
+ *   features 8c .. 8c+7 with the columns j < 8 (c + 1) only -- and column 39 and states >= n_states zero.
  * Domain: every |W| must be below 32768 (the host packer checks and the caller uses the TF32 image
  * otherwise); feature rows of any magnitude are accepted (rows reaching 2^15 are rescaled by an exact
  * power of two inside the kernel).  cst_pad_dev as for loe_emission_tc_dev. */
