@@ -19,6 +19,7 @@ LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libloe_b200.so")
 SOURCES = ["common.cu", "mfcc.cu", "emission.cu", "emission_tc.cu", "viterbi.cu", "viterbi_warp.cu", "kmeans.cu", "vad.cu", "dtw.cu", "decoder.cu", "emission_h16.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+SPILL_SENSITIVE = {"emission_h16.cu"}
 
 
 def _nvcc() -> str:
@@ -46,7 +47,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         obj = os.path.join(LIB_DIR, src.replace(".cu", ".o"))
         cmd = [_nvcc(), *ARCH, "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--use_fast_math=false"]
         cmd = [c for c in cmd if c != "--use_fast_math=false"]
-        if verbose:
+        if verbose or src in SPILL_SENSITIVE:
             cmd += ["-Xptxas", "-v"]
         cmd += ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -57,6 +58,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if p.returncode != 0 or verbose:
             sys.stderr.write(f"--- nvcc {src}\n{out}\n")
         failed |= p.returncode != 0
+        if p.returncode == 0 and src in SPILL_SENSITIVE:
+            # the warp-specialised tensor-core kernels lose ~30 % when ptxas spills inside their role loops (the
+            # setmaxnreg split leaves no slack): make a regression visible at build time
+            import re
+            for m in re.finditer(r"Function properties for (\S+)\s*\n\s*(\d+) bytes stack frame, (\d+) bytes spill stores", out):
+                if int(m.group(3)) > 0:
+                    sys.stderr.write(f"WARNING: {src}: {m.group(1)} spills {m.group(3)} bytes -- rebalance kProducerRegs / kEpilogueRegs\n")
     if failed:
         raise RuntimeError("nvcc failed")
     cmd = [_nvcc(), *ARCH, "-shared", "-o", LIB, *objs, "-lcudart"]
