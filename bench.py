@@ -45,7 +45,7 @@ PENALTY = -100                                                              # pr
 FLOPS_PER_FRAME = 2 * 40 * 39 * 58                                          # 2(D+1)D S, S = 58
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at the default workload (10 000 utterances, 3.84 M frames),
 # from the committed `ncu --set full` capture (profiles/r1f_kernels.txt); None = not captured
-NCU_TRAFFIC = {"mfcc_mel": 3054942000, "mfcc_ceps": 1212502000, "emission_tc": 2368057000, "emission_h16": 2092383000, "viterbi": 899417000}
+NCU_TRAFFIC = {"mfcc_mel": 3054661000, "mfcc_ceps": 1213004000, "emission_tc": 2368057000, "emission_h16": 2164706000, "viterbi": 900178000}
 
 
 def golden_params():
@@ -348,7 +348,7 @@ def impl_b200(args):
     tf32_peak = bf16 / 2      # TF32 is not in MEASURED_PEAKS.json: dense TF32 = half the bf16 rate
     n_samples = int(pcm_off[-1])
     # algorithmic work per launch and DRAM traffic per launch from the committed ncu capture
-    # (profiles/r1j_kernels.txt, emission_tc: r1f; dram__bytes_read.sum + dram__bytes_write.sum at this workload size)
+    # (profiles/r1k_kernels.txt, emission_tc: r1f; dram__bytes_read.sum + dram__bytes_write.sum at this workload size)
     kernels = {
         "mfcc_mel_kernel": {"bound": "hbm", "alg": 4 * n_samples + 160 * F, "ms": stage_ms["mfcc_mel"], "traffic": NCU_TRAFFIC.get("mfcc_mel")},
         "mfcc_ceps_kernel": {"bound": "hbm", "alg": (160 + 156) * F, "ms": stage_ms["mfcc_ceps"], "traffic": NCU_TRAFFIC.get("mfcc_ceps")},
@@ -372,15 +372,16 @@ def impl_b200(args):
         src += ("; kind::f16 MMAs run at the measured bf16 rate" if precision == "h16" else "; TF32 peak taken as bf16_tflops burst / 2")
     roofline["peak_source"] = src
     if precision == "h16":
-        # what the tensor pipe is actually issued: 8 MMAs of K = 16 per 128-frame tile and 6-state column tile (the
-        # 3-way operand split, K 40 -> 15 chunks of 8 paired into 8 x 16, 40 columns per state)
-        n_cols = sum(((min(6, 58 - 6 * t) * 40 + 15) // 16) * 16 for t in range(10))
-        issued = n_cols * 8 * 16 * 2 * F
+        # what the tensor pipe is actually issued: 8 MMAs of K = 16 per 128-frame tile and 6-state column tile (3-way
+        # operand split, 15 chunk products paired into 8), each over the 48 (c + 1) columns its K chunk can reach in the
+        # lower-triangular image: N = 240 + 240 + 192 + 192 + 144 + 96 + 96 + 48 = 1248 of the dense 8 x 240
+        n_tiles = (58 + 5) // 6
+        issued = n_tiles * 1248 * 16 * 2 * F
         sustained = peaks.get("bf16_tflops_sustained") or bf16
         note = {"issued_tflops": issued / (stage_ms["emission"] * 1e-3) / 1e12, "sustained_bf16_tflops": sustained,
                 "issued_over_useful": issued / (FLOPS_PER_FRAME * F),
-                "note": "the kernel runs power-capped (ncu: 1.6 GHz SM clock); counting the MMAs as issued it sits at the box's "
-                        "sustained dense rate, the gap to `achieved` is the 3-way operand split and K/N padding"}
+                "note": "the kernel runs power-capped (ncu: 1.6 GHz SM clock); `achieved` counts the useful flops once, the "
+                        "tensor pipe is issued 2.2x that (3-way operand split, triangular image at 65 % of dense, padding)"}
         all_roof["emission_h16_kernel"]["issued"] = note
         if dominant == "emission_h16_kernel":
             roofline["issued"] = note
