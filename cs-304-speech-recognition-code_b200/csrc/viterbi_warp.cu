@@ -13,6 +13,7 @@
 // so a 460-frame, 58-state utterance needs 7.4 KB of shared memory instead of 26.7 KB and four
 // utterances share a CTA.
 #include "viterbi.cuh"
+#include <type_traits>
 
 namespace loe {
 
@@ -131,76 +132,84 @@ viterbi_warp_kernel(VitArgs a, int n_utt) {
             for (int i = 0; i < SPL; ++i)
                 enext[k][i] = (act[i] && 1 + jb + kPre + k < T) ? __ldg(src[i] + (int64_t)k * a.ld) : 0.f;
         const int slot_base = (FPW > kPre) ? (jb & (FPW - 1)) : 0;     // position of this block inside a bp word
-#pragma unroll
-        for (int k = 0; k < kPre; ++k) {
+        // One frame of the recursion.  FAST = the block lies strictly before the utterance's last frame: no bounds test per
+        // frame and the partial back-pointer / cross-word words are only flushed at their static positions.
+        auto frame = [&](auto fast_tag, const int k) {
+            constexpr bool FAST = decltype(fast_tag)::value;
             const int j = jb + k;
-            if (j < T - 1) {
-                // ---- cross-word candidate: fl(pen + max END d); argmax = lowest END position reaching it
-                float cross32 = neg_inf(); double cross64 = -CUDART_INF; int cross_arg = 0;
-                if (LOOP) {
-                    const float m = end_max();
-                    int pos = 0x7fffffff;
-                    if (PENF64) {
-                        cross64 = __dadd_rn(a.pen64, (double)m);
+            if (!FAST && !(j < T - 1)) return;
+            // ---- cross-word candidate: fl(pen + max END d); argmax = lowest END position reaching it
+            float cross32 = neg_inf(); double cross64 = -CUDART_INF; int cross_arg = 0;
+            if (LOOP) {
+                const float m = end_max();
+                int pos = 0x7fffffff;
+                if (PENF64) {
+                    cross64 = __dadd_rn(a.pen64, (double)m);
 #pragma unroll
-                        for (int i = 0; i < SPL; ++i) {
-                            const unsigned eq = __ballot_sync(FULL, is_end[i] && __dadd_rn(a.pen64, (double)d[i]) == cross64);
-                            if (eq) pos = min(pos, (__ffs(eq) - 1) * SPL + i);
-                        }
-                    } else {
-                        cross32 = __fadd_rn(a.pen32, m);
-#pragma unroll
-                        for (int i = 0; i < SPL; ++i) {
-                            const unsigned eq = __ballot_sync(FULL, is_end[i] && __fadd_rn(a.pen32, d[i]) == cross32);
-                            if (eq) pos = min(pos, (__ffs(eq) - 1) * SPL + i);
-                        }
+                    for (int i = 0; i < SPL; ++i) {
+                        const unsigned eq = __ballot_sync(FULL, is_end[i] && __dadd_rn(a.pen64, (double)d[i]) == cross64);
+                        if (eq) pos = min(pos, (__ffs(eq) - 1) * SPL + i);
                     }
-                    cross_arg = (pos == 0x7fffffff) ? 0 : pos;
-                    cbits |= (uint32_t)cross_arg << (8 * (k & 3));
-                    if ((k & 3) == 3 || j == T - 2) { s_cross[j >> 2] = cbits; cbits = 0; }
-                }
-                // ---- predecessors held by the lane below
-                float up1 = __shfl_up_sync(FULL, d[SPL - 1], 1);
-                float up2 = (SPL >= 2) ? __shfl_up_sync(FULL, d[SPL >= 2 ? SPL - 2 : 0], 1) : __shfl_up_sync(FULL, d[0], 2);
-                if (lane == 0) { up1 = neg_inf(); up2 = neg_inf(); }
-                if (SPL == 1 && lane == 1) up2 = neg_inf();
-                float nd[SPL];
+                } else {
+                    cross32 = __fadd_rn(a.pen32, m);
 #pragma unroll
-                for (int i = 0; i < SPL; ++i) {
-                    const float p1 = (i >= 1) ? d[i >= 1 ? i - 1 : 0] : up1;
-                    const float p2 = (i >= 2) ? d[i >= 2 ? i - 2 : 0] : (i == 1 ? up1 : up2);
-                    const float e = ecur[k][i];
-                    float best = __fadd_rn(b2[i], p2); unsigned code = 2;
-                    const float c1 = __fadd_rn(b1[i], p1);
-                    if (c1 > best) { best = c1; code = 1; }
-                    const float c0 = __fadd_rn(b0[i], d[i]);
-                    if (c0 > best) { best = c0; code = 0; }
-                    if (best == neg_inf()) code = 3;
-                    float val = __fadd_rn(best, e);
-                    if (LOOP) {
-                        // word start: b1 = b2 = -inf, so best == c0 (its self loop); the cross-word
-                        // candidate wins unless the self loop is strictly larger
-                        if (PENF64) {
-                            const bool use_cross = is_start[i] && !((double)c0 > cross64);
-                            const float vx = __double2float_rn(__dadd_rn(cross64, (double)e));
-                            val = use_cross ? vx : val;
-                            code = use_cross ? 3u : code;
-                        } else {
-                            const bool use_cross = is_start[i] && !(c0 > cross32);
-                            const float vx = __fadd_rn(cross32, e);
-                            val = use_cross ? vx : val;
-                            code = use_cross ? 3u : code;
-                        }
+                    for (int i = 0; i < SPL; ++i) {
+                        const unsigned eq = __ballot_sync(FULL, is_end[i] && __fadd_rn(a.pen32, d[i]) == cross32);
+                        if (eq) pos = min(pos, (__ffs(eq) - 1) * SPL + i);
                     }
-                    nd[i] = act[i] ? val : neg_inf();
-                    const int slot = (FPW > kPre) ? (slot_base + k) : (k & (FPW - 1));
-                    bits |= code << (2 * (slot * SPL + i));
                 }
-#pragma unroll
-                for (int i = 0; i < SPL; ++i) d[i] = nd[i];
-                const bool row_done = (FPW > kPre) ? (((slot_base + k) & (FPW - 1)) == FPW - 1) : ((k & (FPW - 1)) == FPW - 1);
-                if (row_done || j == T - 2) { s_bp[(j / FPW) * 32 + lane] = bits; bits = 0; }
+                cross_arg = (pos == 0x7fffffff) ? 0 : pos;
+                cbits |= (uint32_t)cross_arg << (8 * (k & 3));
+                if ((k & 3) == 3 || (!FAST && j == T - 2)) { s_cross[j >> 2] = cbits; cbits = 0; }
             }
+            // ---- predecessors held by the lane below
+            float up1 = __shfl_up_sync(FULL, d[SPL - 1], 1);
+            float up2 = (SPL >= 2) ? __shfl_up_sync(FULL, d[SPL >= 2 ? SPL - 2 : 0], 1) : __shfl_up_sync(FULL, d[0], 2);
+            if (lane == 0) { up1 = neg_inf(); up2 = neg_inf(); }
+            if (SPL == 1 && lane == 1) up2 = neg_inf();
+            float nd[SPL];
+#pragma unroll
+            for (int i = 0; i < SPL; ++i) {
+                const float p1 = (i >= 1) ? d[i >= 1 ? i - 1 : 0] : up1;
+                const float p2 = (i >= 2) ? d[i >= 2 ? i - 2 : 0] : (i == 1 ? up1 : up2);
+                const float e = ecur[k][i];
+                float best = __fadd_rn(b2[i], p2); unsigned code = 2;
+                const float c1 = __fadd_rn(b1[i], p1);
+                if (c1 > best) { best = c1; code = 1; }
+                const float c0 = __fadd_rn(b0[i], d[i]);
+                if (c0 > best) { best = c0; code = 0; }
+                if (best == neg_inf()) code = 3;
+                float val = __fadd_rn(best, e);
+                if (LOOP) {
+                    // word start: b1 = b2 = -inf, so best == c0 (its self loop); the cross-word
+                    // candidate wins unless the self loop is strictly larger
+                    if (PENF64) {
+                        const bool use_cross = is_start[i] && !((double)c0 > cross64);
+                        const float vx = __double2float_rn(__dadd_rn(cross64, (double)e));
+                        val = use_cross ? vx : val;
+                        code = use_cross ? 3u : code;
+                    } else {
+                        const bool use_cross = is_start[i] && !(c0 > cross32);
+                        const float vx = __fadd_rn(cross32, e);
+                        val = use_cross ? vx : val;
+                        code = use_cross ? 3u : code;
+                    }
+                }
+                nd[i] = act[i] ? val : neg_inf();
+                const int slot = (FPW > kPre) ? (slot_base + k) : (k & (FPW - 1));
+                bits |= code << (2 * (slot * SPL + i));
+            }
+#pragma unroll
+            for (int i = 0; i < SPL; ++i) d[i] = nd[i];
+            const bool row_done = (FPW > kPre) ? (((slot_base + k) & (FPW - 1)) == FPW - 1) : ((k & (FPW - 1)) == FPW - 1);
+            if (row_done || (!FAST && j == T - 2)) { s_bp[(j / FPW) * 32 + lane] = bits; bits = 0; }
+        };
+        if (jb + kPre < T - 1) {
+#pragma unroll
+            for (int k = 0; k < kPre; ++k) frame(std::true_type{}, k);
+        } else {
+#pragma unroll
+            for (int k = 0; k < kPre; ++k) frame(std::false_type{}, k);
         }
 #pragma unroll
         for (int k = 0; k < kPre; ++k)
