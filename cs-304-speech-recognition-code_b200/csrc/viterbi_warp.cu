@@ -147,14 +147,14 @@ viterbi_warp_kernel(VitArgs a, int n_utt) {
                     cross64 = __dadd_rn(a.pen64, (double)m);
 #pragma unroll
                     for (int i = 0; i < SPL; ++i) {
-                        const unsigned eq = __ballot_sync(FULL, is_end[i] && __dadd_rn(a.pen64, (double)d[i]) == cross64);
+                        const unsigned eq = __ballot_sync(FULL, __dadd_rn(a.pen64, (double)d[i]) == cross64) & end_mask[i];
                         if (eq) pos = min(pos, (__ffs(eq) - 1) * SPL + i);
                     }
                 } else {
                     cross32 = __fadd_rn(a.pen32, m);
 #pragma unroll
                     for (int i = 0; i < SPL; ++i) {
-                        const unsigned eq = __ballot_sync(FULL, is_end[i] && __fadd_rn(a.pen32, d[i]) == cross32);
+                        const unsigned eq = __ballot_sync(FULL, __fadd_rn(a.pen32, d[i]) == cross32) & end_mask[i];
                         if (eq) pos = min(pos, (__ffs(eq) - 1) * SPL + i);
                     }
                 }
@@ -195,7 +195,7 @@ viterbi_warp_kernel(VitArgs a, int n_utt) {
                         code = use_cross ? 3u : code;
                     }
                 }
-                nd[i] = act[i] ? val : neg_inf();
+                nd[i] = val;                 // positions beyond the trellis have -inf bands and stay at -inf by themselves
                 const int slot = (FPW > kPre) ? (slot_base + k) : (k & (FPW - 1));
                 bits |= code << (2 * (slot * SPL + i));
             }
