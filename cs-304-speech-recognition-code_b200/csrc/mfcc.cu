@@ -107,15 +107,40 @@ struct __align__(16) SmemA {
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// complex add / subtract / element-wise multiply as ONE packed instruction (add / sub / mul .f32x2: both halves
+// IEEE round-to-nearest, i.e. the same results as two scalar operations, half the issue slots)
+__device__ __forceinline__ unsigned long long pack2(float2 a) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+    return r;
+}
+__device__ __forceinline__ float2 unpack2(unsigned long long v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pack2(a)), "l"(pack2(b)));
+    return unpack2(r);
+}
+__device__ __forceinline__ float2 csub(float2 a, float2 b) {
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pack2(a)), "l"(pack2(b)));
+    return unpack2(r);
+}
+__device__ __forceinline__ float2 emul(float2 a, float2 b) {            // (a.x * b.x, a.y * b.y), never contracted
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pack2(a)), "l"(pack2(b)));
+    return unpack2(r);
+}
 
 // forward 5-point DFT
 __device__ __forceinline__ void dft5(float2 v0, float2 v1, float2 v2, float2 v3, float2 v4, float2* y) {
     const float C1 = 0.30901699437494745f, C2 = -0.80901699437494745f;   // cos(2pi/5), cos(4pi/5)
     const float S1 = 0.95105651629515353f, S2 = 0.58778525229247314f;    // sin(2pi/5), sin(4pi/5)
     const float2 t1 = cadd(v1, v4), t2 = cadd(v2, v3), t3 = csub(v1, v4), t4 = csub(v2, v3);
-    y[0] = make_float2(v0.x + t1.x + t2.x, v0.y + t1.y + t2.y);
+    y[0] = cadd(cadd(v0, t1), t2);
     const float2 m1 = make_float2(v0.x + C1 * t1.x + C2 * t2.x, v0.y + C1 * t1.y + C2 * t2.y);
     const float2 m2 = make_float2(v0.x + C2 * t1.x + C1 * t2.x, v0.y + C2 * t1.y + C1 * t2.y);
     const float2 q1 = make_float2(S1 * t3.x + S2 * t4.x, S1 * t3.y + S2 * t4.y);
@@ -285,7 +310,7 @@ mfcc_mel_kernel(const SampleT* __restrict__ pcm, const int64_t* __restrict__ pcm
             float2 v[10];
 #pragma unroll
             for (int n1 = 0; n1 < 10; ++n1)           // never contracted: f32 and s16 inputs agree bit for bit
-                v[n1] = make_float2(__fmul_rn(vn[n1].x, hw[2 * n1]), __fmul_rn(vn[n1].y, hw[2 * n1 + 1]));
+                v[n1] = emul(vn[n1], make_float2(hw[2 * n1], hw[2 * n1 + 1]));
             const int tn = (p < kBatchA / 2 - 1) ? t + 2 : tb + kWarpsA * kBatchA + fl;
             if (tn < t_end) fetch(tn, vn);
             if (t < t_end) {
