@@ -420,11 +420,17 @@ mfcc_ceps_kernel(const float* __restrict__ mel, const float* __restrict__ utt_ma
     // 10 log10(x) = kDbPerLog2 * log2(x); MUFU.LG2 (__log2f, 2 ulp) instead of the 20-instruction log10f
     constexpr float kDbPerLog2 = 3.0102999566398120f;
     const float ref_db = kDbPerLog2 * __log2f(fmaxf(1e-10f, utt_max[u]));
-    const float* __restrict__ src = mel + (f0 + g0) * kMels;
-    for (int i = tid; i < ng * kMels; i += kRowsB) {
-        const int j = i / kMels, m = i - j * kMels;
-        const float db = fmaf(kDbPerLog2, __log2f(fmaxf(1e-10f, __ldg(src + i))), -ref_db);
-        s_lm[j * kMelPitch + m] = fmaxf(db, -80.0f);
+    // mel rows are 160 bytes: four energies per 16-byte load (one row / column split per load instead of per value)
+    const float4* __restrict__ src4 = reinterpret_cast<const float4*>(mel + (f0 + g0) * kMels);
+    static_assert(kMels % 4 == 0, "vector loads of the mel rows");
+    for (int i = tid; i < ng * (kMels / 4); i += kRowsB) {
+        const int j = i / (kMels / 4), m = 4 * (i - j * (kMels / 4));
+        const float4 e = __ldg(src4 + i);
+        float* o = s_lm + j * kMelPitch + m;
+        o[0] = fmaxf(fmaf(kDbPerLog2, __log2f(fmaxf(1e-10f, e.x)), -ref_db), -80.0f);
+        o[1] = fmaxf(fmaf(kDbPerLog2, __log2f(fmaxf(1e-10f, e.y)), -ref_db), -80.0f);
+        o[2] = fmaxf(fmaf(kDbPerLog2, __log2f(fmaxf(1e-10f, e.z)), -ref_db), -80.0f);
+        o[3] = fmaxf(fmaf(kDbPerLog2, __log2f(fmaxf(1e-10f, e.w)), -ref_db), -80.0f);
     }
     __syncthreads();
     float c[kCeps];
