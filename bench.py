@@ -45,7 +45,7 @@ PENALTY = -100                                                              # pr
 FLOPS_PER_FRAME = 2 * 40 * 39 * 58                                          # 2(D+1)D S, S = 58
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at the default workload (10 000 utterances, 3.84 M frames),
 # from the committed `ncu --set full` capture (profiles/r1f_kernels.txt); None = not captured
-NCU_TRAFFIC = {"mfcc_mel": 3054661000, "mfcc_ceps": 1213004000, "emission_tc": 2368057000, "emission_h16": 2164706000, "viterbi": 900178000}
+NCU_TRAFFIC = {"mfcc_mel": 3054381000, "mfcc_ceps": 1212527000, "emission_tc": 2368057000, "emission_h16": 2076703000, "viterbi": 899512000}
 
 
 def golden_params():
@@ -348,7 +348,7 @@ def impl_b200(args):
     tf32_peak = bf16 / 2      # TF32 is not in MEASURED_PEAKS.json: dense TF32 = half the bf16 rate
     n_samples = int(pcm_off[-1])
     # algorithmic work per launch and DRAM traffic per launch from the committed ncu capture
-    # (profiles/r1k_kernels.txt, emission_tc: r1f; dram__bytes_read.sum + dram__bytes_write.sum at this workload size)
+    # (profiles/r1l_kernels.txt, emission_tc: r1f; dram__bytes_read.sum + dram__bytes_write.sum at this workload size)
     kernels = {
         "mfcc_mel_kernel": {"bound": "hbm", "alg": 4 * n_samples + 160 * F, "ms": stage_ms["mfcc_mel"], "traffic": NCU_TRAFFIC.get("mfcc_mel")},
         "mfcc_ceps_kernel": {"bound": "hbm", "alg": (160 + 156) * F, "ms": stage_ms["mfcc_ceps"], "traffic": NCU_TRAFFIC.get("mfcc_ceps")},
@@ -386,8 +386,8 @@ def impl_b200(args):
         if dominant == "emission_h16_kernel":
             roofline["issued"] = note
     if dominant == "mfcc_mel_kernel":
-        roofline["note"] = ("nominally HBM-bound (796 B/frame) but limited by instruction issue and shared-memory wavefronts: ~350 warp "
-                            "instructions and ~76 wavefronts per frame (thread-level 10 x 16 FFT), see profiles/")
+        roofline["note"] = ("nominally HBM-bound (796 B/frame) but limited by instruction issue and shared-memory wavefronts: ~320 warp "
+                            "instructions and ~60 wavefronts per frame (thread-level 10 x 16 FFT), see profiles/")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
