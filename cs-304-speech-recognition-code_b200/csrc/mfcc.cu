@@ -506,6 +506,10 @@ static int mfcc_launch(const void* pcm_dev, int pcm_format, const int64_t* pcm_o
         set_error("mel table iteration counts out of range (na=%d, nb=%d)", mel_na, mel_nb);
         return LOE_ERR_VALUE;
     }
+    if ((reinterpret_cast<uintptr_t>(mel_ws_dev) & 15) != 0) {
+        set_error("mel_ws_dev must be 16-byte aligned (the cepstrum kernel reads it with 16-byte loads)");
+        return LOE_ERR_VALUE;
+    }
     int st = ensure_tables();
     if (st != LOE_OK) return st;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);

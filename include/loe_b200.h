@@ -82,7 +82,7 @@ int loe_device_count(void);
  *                goes to lane 4q + j%4, iteration na + j/4).  Unused entries have weight 0.  A lane's
  *                bins must be consecutive (round A: bin(it) = bin(0) + it; round B: bin(it) = bin(0) + 4 it):
  *                the kernel reads only mel_bin of each lane's first entry.
- *   mel_ws_dev   [total_frames*40] float32 workspace (mel energies)
+ *   mel_ws_dev   [total_frames*40] float32 workspace (mel energies), 16-byte aligned
  *   utt_max_dev  [n_utt] float32 workspace (per-utterance mel maximum)
  *   feat_dev     [total_frames*39] float32 out, row-major (frame, coefficient): the
  *                transposed (T,39) layout MFCC.batch hands to the HMM code

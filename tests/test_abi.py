@@ -39,6 +39,7 @@ def test_host_side_argument_checks_need_no_gpu(built_lib):
     assert st == _native.LOE_ERR_OVERFLOW
     with pytest.raises(OverflowError):
         _native.check(st)
+    assert lib.loe_mfcc_dev(0, 0, 0, 0, 1, 20, 20, 20, 0, 0, 11, 5, 4, 0, 0, 0) == _native.LOE_ERR_VALUE    # mel workspace not 16-byte aligned
     assert lib.loe_emission_dev(0, 10, 7, 0, 0, 0, 3, 0, 3, 0, 0) == _native.LOE_ERR_UNSUPPORTED
     assert lib.loe_viterbi_bp_fits(460, 58) == 1 and lib.loe_viterbi_bp_fits(100000, 128) == 0
     assert lib.loe_kmeans_ws_doubles(1000, 5, 39) == 5 * 820 + 1
