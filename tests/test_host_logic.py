@@ -294,3 +294,66 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_h16_image_is_triangular_and_scores_like_the_whitening_matrix():
+    """pack_h16_image (host, no GPU): the 3xFP16 operand of loe_emission_h16_dev replaces U_s by the
+    lower-triangular R_s^T of U_s^T = Q R_s.  Rebuilt from the image (hi + lo parts, layout of include/loe_b200.h):
+    the same |W^T (x - mean)|^2 as U_s to ~1e-7, feature chunk c empty beyond column 8 (c + 1) (what lets the
+    kernel issue narrower MMAs), column 39 and the padding states zero, the second hi copy identical."""
+    from loe_speech_recognition._engine import pack_h16_image
+    rng = np.random.default_rng(0)
+    S, D = 8, 39
+    means = rng.normal(size=(S, D))
+    us = np.stack([np.linalg.qr(rng.normal(size=(D, D)))[0] @ np.diag(rng.uniform(0.5, 30, D)) for _ in range(S)])
+    flat = pack_h16_image(means, us, np.zeros(S))
+    assert flat.dtype == np.float16 and flat.size == 2 * 15 * 240 * 8
+    img = flat.reshape(2, 15, 240, 8).astype(np.float64)
+    assert np.array_equal(img[:, 0:5], img[:, 10:15])
+    x = rng.normal(size=(7, D))
+    xa = np.concatenate([x, np.ones((7, 1))], axis=1)
+    for s in range(12):
+        t, sl = divmod(s, 6)
+        W = np.zeros((40, 40))
+        for c in range(5):
+            for j in range(40):
+                n = (j // 8) * 48 + sl * 8 + j % 8
+                W[8 * c:8 * c + 8, j] = img[t, c, n] + img[t, 5 + c, n]
+        if s >= S:
+            assert not W.any()                                        # padding states of the last tile
+            continue
+        assert not np.triu(W[:39, :39], 1).any() and not W[:, 39].any()
+        for c in range(4):
+            assert not W[8 * c:8 * c + 8, 8 * (c + 1):].any()
+        ref = (((x - means[s]) @ us[s]) ** 2).sum(axis=1)
+        got = ((xa @ W) ** 2).sum(axis=1)
+        assert np.abs(got - ref).max() <= 2e-7 * ref.max()
+    assert pack_h16_image(means, us * 1e4, np.zeros(S)) is None       # outside the binary16 range: TF32 image instead
+    bad = us.copy()
+    bad[3, 5, 7] = np.nan
+    assert pack_h16_image(means, bad, np.zeros(S)) is None
+
+
+def test_mel_lane_tables_exact_and_bank_conflict_free():
+    """mel_lane_tables (host): the lane-balanced filterbank the MFCC kernel reads reproduces the dense slaney
+    filterbank exactly, every lane walks consecutive bins, and at 16 kHz the window starts are slid so that the 32
+    power-spectrum reads of each iteration fall into 32 different shared-memory banks."""
+    from loe_speech_recognition.mfcc import mel_filterbank, mel_lane_tables
+    for sr in (16000, 8000, 22050):
+        bins, w, na, nb = mel_lane_tables(sr)
+        B, Wt = bins.reshape(na + nb, 32), w.reshape(na + nb, 32)
+        dense = mel_filterbank(sr)
+        rec = np.zeros_like(dense)
+        for it in range(na + nb):
+            for lane in range(32):
+                m = lane if it < na else 32 + lane // 4
+                if Wt[it, lane] != 0:
+                    rec[m, B[it, lane]] += Wt[it, lane]
+        assert np.array_equal(rec, dense)
+        assert np.array_equal(B[:na], B[0][None, :] + np.arange(na)[:, None])
+        assert np.array_equal(B[na:], B[na][None, :] + 4 * np.arange(nb)[:, None])
+        assert B.min() >= 0 and B.max() < 161 + 3 + 32 + 64               # inside the kernel's frame area slack
+        if sr == 16000:
+            assert (na, nb) == (11, 5)
+            for it in range(na + nb):
+                assert len(set(int(b) % 32 for b in B[it])) == 32
