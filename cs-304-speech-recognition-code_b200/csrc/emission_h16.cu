@@ -6,7 +6,11 @@
 // same 22 bits a TF32 pair carries) and the products hi*hi + lo*hi + hi*lo run as kind::f16 MMAs,
 // which the tensor pipe executes at twice the TF32 rate.  The 15 (A chunk, B chunk) products of
 // 8 halfs each are paired into 8 MMAs of K = 16 through the descriptors' leading byte offset
-// (one zero A chunk and one duplicated B chunk make the pairing come out even), against 15 TF32 MMAs.
+// (one zero A chunk and a second copy of the hi B chunks make the pairing come out even), against 15 TF32 MMAs.
+//
+// W_s is not scipy's U_s itself but the lower-triangular R_s^T of U_s^T = Q R_s (the host packs it; same
+// |W^T (x - mean)|): with the accumulator columns ordered [column block][state][8] the MMAs of feature chunk c
+// only run over the 48 (c + 1) columns that chunk can reach -- 65 % of the dense MMA work (see pair_chunk).
 //
 // Range: binary16 tops out at 65504.  The B image is checked on the host when it is packed (the
 // caller falls back to the TF32 image otherwise); every feature row whose largest magnitude reaches
@@ -15,9 +19,12 @@
 // subnormal grid: an absolute error of 3e-8 on values below 0.125, the same size as the TF32 pair's
 // relative error there.
 //
-// Decomposition, warp roles and pipelines are those of emission_tc.cu: B-stationary CTAs per state
-// tile, raw feature tiles by cp.async.bulk (two in flight), 8 producer warps, 4 epilogue warps, one
-// MMA-issuing thread, two accumulators in TMEM.
+// Decomposition: B-stationary CTAs, each with the images of kHalves = 2 six-state column tiles resident; a staged
+// 128-frame feature tile is multiplied with both (16 MMAs).  Warp roles: 8 producer warps in two groups (raw feature
+// tiles by cp.async.bulk, one in flight per group; hi / lo split into the A stages), one MMA-issuing thread, 4 epilogue
+// warps (two accumulators of 240 columns in TMEM, each drained in two 120-column rounds).  The register file is
+// split with setmaxnreg: 88 per producer thread, 208 per epilogue thread -- the spill-free point; this kernel loses
+// 10-30 % as soon as ptxas spills inside a role loop (build.py warns).
 #include <cuda_fp16.h>
 #include "tcgen05.cuh"
 
