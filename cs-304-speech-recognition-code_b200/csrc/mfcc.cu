@@ -1,9 +1,9 @@
 // MFCC front end for sm_100a.  Replaces mfcc.py:24-84 of the reference (librosa pipeline).
 //
-// Kernel A (mel):   PCM -> Hann window -> 320-point real FFT (one warp per frame: radix-5 in
-//                   registers x 32-point shuffle FFT across lanes, real-input post-pass in
-//                   shared memory) -> |.|^2 -> sparse slaney filterbank -> mel energies
-//                   [frames, 40] + per-utterance maximum (atomicMax on the float bits).
+// Kernel A (mel):   PCM -> Hann window -> 320-point real FFT (160-point complex FFT split 10 x 16 with every
+//                   sub-transform in the registers of one thread, one pass through shared memory, real-input
+//                   post-pass in registers; details at the kernel) -> |.|^2 -> sparse slaney filterbank -> mel
+//                   energies [frames, 40] + per-utterance maximum (atomicMax on the float bits).
 // Kernel B (ceps):  mel -> dB relative to the utterance maximum, floor at -80 dB -> DCT-II
 //                   (ortho) 13 ceps -> Savitzky-Golay delta / delta-delta (width 9, edge
 //                   frames take the value of the nearest full window) -> per-frame
