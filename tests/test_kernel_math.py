@@ -1,0 +1,113 @@
+"""CPU: the index arithmetic the hand-written kernels rely on, restated in NumPy / checked on the source tables.
+
+* the 10 x 16 decomposition of the 160-point complex FFT and the in-thread real-input post-pass of
+  csrc/mfcc.cu (mfcc_mel_kernel): prime-factor 10-point DFT, twiddles, the rotated eleventh slot that lets the
+  a = 0 thread pair bin k with 160 - k like every other thread;
+* the pairing table of csrc/emission_h16.cu (pair_chunk): the 8 MMAs of K = 16 cover the 15 split-operand chunk
+  products exactly once, and no MMA is issued narrower than its chunks reach in the lower-triangular image.
+"""
+import os
+import re
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "cs-304-speech-recognition-code_b200", "csrc")
+
+
+def _w(n, e):
+    return np.exp(-2j * np.pi * e / n)
+
+
+def _dft5(v):
+    c1, c2, s1, s2 = np.cos(2 * np.pi / 5), np.cos(4 * np.pi / 5), np.sin(2 * np.pi / 5), np.sin(4 * np.pi / 5)
+    t1, t2, t3, t4 = v[1] + v[4], v[2] + v[3], v[1] - v[4], v[2] - v[3]
+    m1, m2 = v[0] + c1 * t1 + c2 * t2, v[0] + c2 * t1 + c1 * t2
+    q1, q2 = s1 * t3 + s2 * t4, s2 * t3 - s1 * t4
+    return [v[0] + t1 + t2, m1 - 1j * q1, m2 - 1j * q2, m2 + 1j * q2, m1 + 1j * q1]
+
+
+def _dft10(v):
+    """Good-Thomas 2 x 5: input n = (5 na + 2 nb) mod 10, output k = (5 ka + 6 kb) mod 10 -- no twiddles."""
+    c0 = _dft5([v[(2 * nb) % 10] for nb in range(5)])
+    c1 = _dft5([v[(5 + 2 * nb) % 10] for nb in range(5)])
+    out = [None] * 10
+    for kb in range(5):
+        out[(6 * kb) % 10] = c0[kb] + c1[kb]
+        out[(5 + 6 * kb) % 10] = c0[kb] - c1[kb]
+    return out
+
+
+def _dft4(u):
+    s0, s1, s2, s3 = u[0] + u[2], u[0] - u[2], u[1] + u[3], u[1] - u[3]
+    return [s0 + s2, s1 - 1j * s3, s0 - s2, s1 + 1j * s3]
+
+
+def _fft16(v):
+    t = [[y * _w(16, b * c) for c, y in enumerate(_dft4([v[4 * a + b] for a in range(4)]))] for b in range(4)]
+    out = [None] * 16
+    for c in range(4):
+        for d, y in enumerate(_dft4([t[b][c] for b in range(4)])):
+            out[c + 4 * d] = y
+    return out
+
+
+def test_mel_kernel_fft_decomposition():
+    rng = np.random.default_rng(0)
+    x = rng.normal(0, 3000, 320)
+    xw = x * (0.5 - 0.5 * np.cos(2 * np.pi * np.arange(320) / 320))            # periodic Hann
+    ref = np.abs(np.fft.rfft(xw)) ** 2
+    z = xw[0::2] + 1j * xw[1::2]
+    # step 1, thread n2: 10-point DFT over n1 of z[16 n1 + n2], twiddle W_160^(n2 k1); slot 10 = slot 0 * W_16^n2
+    slots = np.zeros((11, 16), complex)
+    for n2 in range(16):
+        a = _dft10([z[16 * n1 + n2] for n1 in range(10)])
+        assert np.allclose(a, np.fft.fft(z[n2::16]))
+        for k1 in range(10):
+            slots[k1, n2] = a[k1] * _w(160, n2 * k1)
+        slots[10, n2] = slots[0, n2] * _w(16, n2)
+    assert np.allclose(_fft16(np.arange(16) * (1 + 0.5j)), np.fft.fft(np.arange(16) * (1 + 0.5j)))
+    # step 2, thread a: FFTs of slots a and 10 - a; bin k = a + 10 k2 pairs with 160 - k = (10 - a) + 10 (15 - k2)
+    zfull = np.fft.fft(z)
+    power = np.full(161, np.nan)
+    for a in range(6):
+        za, zb = _fft16(slots[a]), _fft16(slots[10 - a])
+        for k2 in range(16):
+            k = a + 10 * k2
+            A, B = za[k2], zb[15 - k2]
+            assert np.allclose(A, zfull[k % 160]) and np.allclose(B, zfull[(160 - k) % 160])
+            e = complex(A.real + B.real, A.imag - B.imag)
+            o = complex(A.imag + B.imag, B.real - A.real)
+            t = _w(320, k) * o
+            power[k], power[160 - k] = 0.25 * abs(e + t) ** 2, 0.25 * abs(e - t) ** 2
+    assert not np.isnan(power).any()
+    assert np.abs(power - ref).max() <= 1e-12 * ref.max()
+
+
+def test_emission_h16_pairing_table():
+    src = open(os.path.join(CSRC, "emission_h16.cu")).read()
+    body = src[src.index("constexpr int t[kNumMma][5] = {"):]
+    body = body[:body.index("};")]
+    rows = [tuple(int(v) for v in m) for m in re.findall(r"\{(\d+), (\d+), (\d+), (\d+), (\d+)\}", body)]
+    assert len(rows) == 8
+
+    def a_part(c):      # A chunks: hi 0-4, lo 5-9, zero 10
+        return ("hi", c) if c < 5 else ("lo", c - 5) if c < 10 else ("zero", None)
+
+    def b_part(c):      # B chunks: hi 0-4, lo 5-9, second copy of hi 10-14
+        return ("hi", c) if c < 5 else ("lo", c - 5) if c < 10 else ("hi", c - 10)
+
+    products = []
+    for a0, a1, b0, b1, blocks in rows:
+        assert 1 <= blocks <= 5
+        for ac, bc in ((a0, b0), (a1, b1)):
+            (pa, ca), (pb, cb) = a_part(ac), b_part(bc)
+            if pa == "zero":
+                continue                                    # zero x anything finite
+            assert ca == cb                                 # same K chunk on both sides
+            assert blocks >= ca + 1                         # the MMA covers every column that chunk reaches (j <= 8 c + 7)
+            products.append((pa, pb, ca))
+    want = [(pa, pb, c) for c in range(5) for pa, pb in (("hi", "hi"), ("lo", "hi"), ("hi", "lo"))]
+    assert sorted(products) == sorted(want)                 # hi*hi + lo*hi + hi*lo of every chunk, once each
+    assert rows[0][4] == 5                                  # the first MMA (accumulate = 0) overwrites all 240 columns
+    assert sum(r[4] for r in rows) * 48 == 1248             # 65 % of the dense 8 x 240
