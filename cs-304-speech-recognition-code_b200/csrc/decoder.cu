@@ -18,6 +18,8 @@
 #include <stdlib.h>
 #include <string.h>
 #include <immintrin.h>
+#include <pthread.h>
+#include <sched.h>
 
 
 namespace loe {
@@ -80,8 +82,15 @@ static bool narrow_range(const float* src, int16_t* dst, int64_t n) {
 // persistent worker threads: run(f) calls f(worker index) on every worker and returns when all are done
 class Pool {
 public:
-    explicit Pool(int n) : n_(n) {
+    // cpus: the CPUs the workers may run on (empty: wherever the process may)
+    Pool(int n, const std::vector<int>& cpus) : n_(n) {
         for (int i = 0; i < n; ++i) th_.emplace_back([this, i] { loop(i); });
+        if (!cpus.empty()) {
+            cpu_set_t set;
+            CPU_ZERO(&set);
+            for (int c : cpus) if (c >= 0 && c < CPU_SETSIZE) CPU_SET(c, &set);
+            for (auto& t : th_) pthread_setaffinity_np(t.native_handle(), sizeof(set), &set);   // best effort
+        }
     }
     ~Pool() {
         { std::lock_guard<std::mutex> l(m_); stop_ = true; ++gen_; }
@@ -116,7 +125,56 @@ private:
     const std::function<void(int)>* job_ = nullptr; int pending_ = 0, gen_ = 0; bool stop_ = false;
 };
 
-constexpr double kNarrowMinGBps = 65.0;
+// ------------------------------------------------------------------------------------------------
+// When to narrow.  The host thread narrows chunk c+1 while the copy engine moves chunk c, so a chunk period is
+// max(narrow time, int16 copy time) with narrowing and the float32 copy time without: narrowing pays exactly when
+// the conversion rate (float32 bytes/s) beats the wire rate of the host->device copies.  Both are MEASURED by this
+// decoder, under whatever the other ranks of the box are doing at the same time: conversion times per chunk on the
+// host clock, copy times per chunk with CUDA events on the copy stream.  The verdict is taken once kNarrowVotes
+// chunks of >= 1 M samples have been seen, from the MEDIANS, with a 10 % margin in favour of the plain copy
+// (mode LOE_NARROW_AUTO); loe_decoder_set_narrow / LOE_B200_NARROW = on|off make it an explicit choice.
+// ------------------------------------------------------------------------------------------------
+constexpr int kNarrowVotes = 6;
+constexpr double kNarrowMargin = 1.10;
+
+// CPUs next to the GPU: /sys/bus/pci/devices/<bus id>/local_cpulist ("0-15,32-47"), intersected with the CPUs this
+// process may use.  Empty when the file is unreadable (containers) -- the workers then float.
+static std::vector<int> local_cpus(int device) {
+    std::vector<int> out;
+    char bus[32] = "";
+    if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) return out;
+    for (char* c = bus; *c; ++c) *c = (char)tolower(*c);
+    char path[128];
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/local_cpulist", bus);
+    FILE* f = fopen(path, "r");
+    if (!f) return out;
+    char line[4096] = "";
+    if (!fgets(line, sizeof(line), f)) line[0] = 0;
+    fclose(f);
+    cpu_set_t allowed;
+    CPU_ZERO(&allowed);
+    const bool have_allowed = sched_getaffinity(0, sizeof(allowed), &allowed) == 0;
+    for (char* tok = strtok(line, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+        int a = 0, b = 0;
+        const int k = sscanf(tok, "%d-%d", &a, &b);
+        if (k < 1) continue;
+        if (k == 1) b = a;
+        for (int c = a; c <= b && c < CPU_SETSIZE; ++c)
+            if (!have_allowed || CPU_ISSET(c, &allowed)) out.push_back(c);
+    }
+    return out;
+}
+
+static int env_int(const char* name, int fallback) {
+    const char* e = getenv(name);
+    return (e && *e) ? atoi(e) : fallback;
+}
+
+static double median(std::vector<double> v) {
+    if (v.empty()) return 0.0;
+    std::sort(v.begin(), v.end());
+    return v[v.size() / 2];
+}
 
 struct DevBuf {
     void* p = nullptr; size_t cap = 0;
@@ -135,6 +193,8 @@ struct Decoder {
     int device = 0;
     cudaStream_t copy = nullptr, comp = nullptr;
     cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    cudaEvent_t ev_copy_begin[2] = {nullptr, nullptr};                          // timing pair of a chunk's PCM copy
+    size_t copy_bytes[2] = {0, 0};
     // model
     int mel_na = 0, mel_nb = 0, n_states = 0, n_pos = 0, n_ends = 0;
     int32_t* d_mel_bin = nullptr; float* d_mel_w = nullptr; float* d_b = nullptr; float* d_cst = nullptr;
@@ -150,8 +210,14 @@ struct Decoder {
     // running verdict: -1 = not measured yet, 0 = off (conversion slower than the float32 copy it saves), 1 = on
     Pool* pool = nullptr;
     int16_t* h_stage[2] = {nullptr, nullptr}; size_t h_stage_cap[2] = {0, 0};
-    int narrow = -1;
-    double narrow_gbps = 0.0;                                                   // measured conversion rate, float32 bytes
+    int narrow_mode = LOE_NARROW_AUTO;                                          // explicit choice, or auto
+    int narrow = -1;                                                            // auto verdict: -1 undecided (narrowing while measuring)
+    int narrow_threads = 0;                                                     // workers in use (0 until the pool exists)
+    int pinned_cpus = 0;                                                        // CPUs the workers are bound to (0: floating)
+    std::vector<double> narrow_samples, copy_samples;                           // GB/s per chunk: float32 bytes converted / wire bytes copied
+    double narrow_gbps = 0.0, copy_gbps = 0.0;                                  // medians of the above
+    // last call
+    int64_t last_wire_bytes = 0, last_pcm_bytes = 0; int last_chunks = 0, last_chunks_narrowed = 0;
 };
 
 template <typename T>
@@ -171,6 +237,7 @@ static void destroy(Decoder* d) {
         if (d->h_off[i]) cudaFreeHost(d->h_off[i]);
         if (d->ev_copy[i]) cudaEventDestroy(d->ev_copy[i]);
         if (d->ev_done[i]) cudaEventDestroy(d->ev_done[i]);
+        if (d->ev_copy_begin[i]) cudaEventDestroy(d->ev_copy_begin[i]);
     }
     if (d->h_out) cudaFreeHost(d->h_out);
     for (int i = 0; i < 2; ++i) if (d->h_stage[i]) cudaFreeHost(d->h_stage[i]);
@@ -199,6 +266,10 @@ extern "C" int loe_decoder_create(int device, const int32_t* mel_bin_host, const
     Decoder* d = new (std::nothrow) Decoder();
     if (!d) { set_error("out of host memory"); return LOE_ERR_CUDA; }
     d->device = device; d->mel_na = mel_na; d->mel_nb = mel_nb; d->n_states = n_states; d->n_pos = n_pos;
+    if (const char* e = getenv("LOE_B200_NARROW")) {
+        if (!strcmp(e, "on") || !strcmp(e, "1")) d->narrow_mode = LOE_NARROW_ON;
+        else if (!strcmp(e, "off") || !strcmp(e, "0")) d->narrow_mode = LOE_NARROW_OFF;
+    }
     for (int p = 0; p < n_pos; ++p) d->n_ends += (flags_host[p] & LOE_POS_END) ? 1 : 0;
     int st = LOE_OK;
     const int n_tiles = loe_emission_tc_tiles(n_states);
@@ -208,7 +279,8 @@ extern "C" int loe_decoder_create(int device, const int32_t* mel_bin_host, const
     LOE_TRY(check_cuda(cudaStreamCreateWithFlags(&d->copy, cudaStreamNonBlocking), "stream"));
     LOE_TRY(check_cuda(cudaStreamCreateWithFlags(&d->comp, cudaStreamNonBlocking), "stream"));
     for (int i = 0; i < 2; ++i) {
-        LOE_TRY(check_cuda(cudaEventCreateWithFlags(&d->ev_copy[i], cudaEventDisableTiming), "event"));
+        LOE_TRY(check_cuda(cudaEventCreate(&d->ev_copy[i]), "event"));
+        LOE_TRY(check_cuda(cudaEventCreate(&d->ev_copy_begin[i]), "event"));
         LOE_TRY(check_cuda(cudaEventCreateWithFlags(&d->ev_done[i], cudaEventDisableTiming), "event"));
     }
     LOE_TRY(upload(&d->d_mel_bin, mel_bin_host, (size_t)(mel_na + mel_nb) * 32));
@@ -253,7 +325,9 @@ extern "C" int loe_decoder_decode_host(void* dec, const void* pcm_host, int pcm_
     LOE_CUDA(cudaSetDevice(d->device));
     const size_t bps = pcm_format == LOE_PCM_F32 ? 4 : 2;
     const int64_t total_samples = sample_off_host[n_utt] - sample_off_host[0];
-    if (n_chunks <= 0) n_chunks = (int)std::min<int64_t>(8, std::max<int64_t>(1, (int64_t)(total_samples * bps) / (64ll << 20)));
+    // default: chunks of about 64 MB (the first chunk's copy and the last chunk's kernels are the part of the call
+    // that nothing overlaps), at most 64
+    if (n_chunks <= 0) n_chunks = (int)std::min<int64_t>(64, std::max<int64_t>(1, (int64_t)(total_samples * bps) / (64ll << 20)));
     // chunk boundaries: whole utterances, about equal numbers of samples
     std::vector<int> bounds{0};
     for (int c = 1; c < n_chunks; ++c) {
@@ -276,11 +350,34 @@ extern "C" int loe_decoder_decode_host(void* dec, const void* pcm_host, int pcm_
         LOE_CUDA(cudaHostAlloc((void**)&d->h_out, out_bytes + out_bytes / 4, cudaHostAllocDefault));
         d->h_out_cap = out_bytes + out_bytes / 4;
     }
-    // worker threads of the float32 -> int16 narrowing: LOE_B200_NARROW_THREADS (0 = never narrow), default = the
-    // machine's hardware threads, at most 32
-    int narrow_threads = (int)std::min<unsigned>(32u, std::max<unsigned>(1u, std::thread::hardware_concurrency()));
-    if (const char* e = getenv("LOE_B200_NARROW_THREADS")) narrow_threads = std::max(0, std::min(256, atoi(e)));
-    if (d->pool && d->pool->size() != narrow_threads) { delete d->pool; d->pool = nullptr; }
+    // worker threads of the float32 -> int16 narrowing: this rank's share of the machine -- hardware threads divided
+    // by the ranks on the box (LOCAL_WORLD_SIZE, as torchrun exports it), at most 32 -- bound to the CPUs next to the
+    // GPU when the kernel tells which those are.  LOE_B200_NARROW_THREADS overrides the count (0 = never narrow),
+    // LOE_B200_NARROW_PIN=0 leaves the workers floating.
+    const bool narrowing_possible = pcm_format == LOE_PCM_F32 && d->narrow_mode != LOE_NARROW_OFF &&
+                                    !(d->narrow_mode == LOE_NARROW_AUTO && d->narrow == 0);
+    int narrow_threads = 0;
+    if (narrowing_possible) {
+        const int hw = (int)std::max<unsigned>(1u, std::thread::hardware_concurrency());
+        const int ranks = std::max(1, env_int("LOCAL_WORLD_SIZE", 1));
+        narrow_threads = std::max(1, std::min(32, hw / ranks));
+        if (const char* e = getenv("LOE_B200_NARROW_THREADS")) narrow_threads = std::max(0, std::min(256, atoi(e)));
+        if (d->pool && d->pool->size() != narrow_threads) { delete d->pool; d->pool = nullptr; }
+        if (!d->pool && narrow_threads > 0) {
+            std::vector<int> cpus;
+            if (env_int("LOE_B200_NARROW_PIN", 1) != 0) cpus = local_cpus(d->device);
+            if ((int)cpus.size() < narrow_threads) cpus.clear();        // fewer local CPUs than workers: let them float
+            d->pool = new (std::nothrow) Pool(narrow_threads, cpus);
+            d->pinned_cpus = d->pool ? (int)cpus.size() : 0;
+        }
+        d->narrow_threads = d->pool ? narrow_threads : 0;
+    }
+    d->last_wire_bytes = 0; d->last_pcm_bytes = (int64_t)total_samples * (int64_t)bps; d->last_chunks = 0; d->last_chunks_narrowed = 0;
+    // conversion and copy rates are sampled on every chunk of at least min_samples samples (reported by
+    // loe_decoder_stats); the automatic verdict is taken from them while it is still open
+    const int64_t min_samples = env_int("LOE_B200_NARROW_MIN_SAMPLES", 1 << 20);
+    const bool deciding = pcm_format == LOE_PCM_F32 && d->narrow_mode == LOE_NARROW_AUTO && d->narrow < 0;
+    auto keep = [](std::vector<double>& v, double x) { if (v.size() >= 256) v.erase(v.begin(), v.begin() + 128); v.push_back(x); };
     int64_t frames_done = 0;
     for (size_t c = 0; c + 1 < bounds.size(); ++c) {
         const int a = bounds[c], b = bounds[c + 1], n = b - a, set = (int)(c & 1);
@@ -312,41 +409,42 @@ extern "C" int loe_decoder_decode_host(void* dec, const void* pcm_host, int pcm_
         const char* src = (const char*)pcm_host + (size_t)(s0 - sample_off_host[0]) * bps;
         int chunk_format = pcm_format;
         size_t chunk_bps = bps;
-        if (pcm_format == LOE_PCM_F32 && d->narrow != 0 && narrow_threads > 0 && ns > 0) {
-            if (!d->pool) d->pool = new (std::nothrow) Pool(narrow_threads);
-            if (d->pool) {
-                if (d->h_stage_cap[set] < (size_t)ns) {
-                    if (d->h_stage[set]) LOE_CUDA(cudaFreeHost(d->h_stage[set]));
-                    d->h_stage[set] = nullptr; d->h_stage_cap[set] = 0;
-                    const size_t want = (size_t)ns + (size_t)ns / 8 + 64;
-                    LOE_CUDA(cudaHostAlloc((void**)&d->h_stage[set], want * sizeof(int16_t), cudaHostAllocDefault));
-                    d->h_stage_cap[set] = want;
-                }
-                const float* fsrc = reinterpret_cast<const float*>(src);
-                int16_t* fdst = d->h_stage[set];
-                std::atomic<int> exact(1);
-                const int W = d->pool->size();
-                const auto t0 = std::chrono::steady_clock::now();
-                d->pool->run([&](int w) {
-                    const int64_t i0 = (ns * w / W) & ~(int64_t)15, i1 = (w == W - 1) ? ns : ((ns * (w + 1) / W) & ~(int64_t)15);
-                    if (i1 > i0 && !narrow_range(fsrc + i0, fdst + i0, i1 - i0)) exact.store(0);
-                });
-                const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-                if (d->narrow < 0 && (ns >= (1 << 20) || getenv("LOE_B200_NARROW_MIN_GBPS"))) {
-                    // worth it only if converting is faster than the float32 copy it replaces (PCIe 5 x16: ~52 GB/s)
-                    d->narrow_gbps = (double)ns * 4.0 / sec * 1e-9;
-                    double min_gbps = kNarrowMinGBps;
-                    if (const char* e = getenv("LOE_B200_NARROW_MIN_GBPS")) min_gbps = atof(e);
-                    d->narrow = d->narrow_gbps > min_gbps ? 1 : 0;
-                }
-                if (exact.load()) { src = reinterpret_cast<const char*>(fdst); chunk_format = LOE_PCM_S16; chunk_bps = 2; }
+        if (narrowing_possible && d->pool && ns > 0) {
+            if (d->h_stage_cap[set] < (size_t)ns) {
+                if (d->h_stage[set]) LOE_CUDA(cudaFreeHost(d->h_stage[set]));
+                d->h_stage[set] = nullptr; d->h_stage_cap[set] = 0;
+                const size_t want = (size_t)ns + (size_t)ns / 8 + 64;
+                LOE_CUDA(cudaHostAlloc((void**)&d->h_stage[set], want * sizeof(int16_t), cudaHostAllocDefault));
+                d->h_stage_cap[set] = want;
             }
+            const float* fsrc = reinterpret_cast<const float*>(src);
+            int16_t* fdst = d->h_stage[set];
+            std::atomic<int> exact(1);
+            const int W = d->pool->size();
+            const auto t0 = std::chrono::steady_clock::now();
+            d->pool->run([&](int w) {
+                const int64_t i0 = (ns * w / W) & ~(int64_t)15, i1 = (w == W - 1) ? ns : ((ns * (w + 1) / W) & ~(int64_t)15);
+                if (i1 > i0 && !narrow_range(fsrc + i0, fdst + i0, i1 - i0)) exact.store(0);
+            });
+            const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            if (ns >= min_samples && sec > 0) keep(d->narrow_samples, (double)ns * 4.0 / sec * 1e-9);
+            if (exact.load()) { src = reinterpret_cast<const char*>(fdst); chunk_format = LOE_PCM_S16; chunk_bps = 2; d->last_chunks_narrowed++; }
         }
         if ((st = d->pcm[set].ensure((size_t)ns * chunk_bps)) != LOE_OK) return st;
         if ((st = d->off[set].ensure(sizeof(int64_t) * off_elems)) != LOE_OK) return st;
-        LOE_CUDA(cudaMemcpyAsync(d->pcm[set].p, src, (size_t)ns * chunk_bps, cudaMemcpyHostToDevice, d->copy));
         LOE_CUDA(cudaMemcpyAsync(d->off[set].p, pcm_off, sizeof(int64_t) * off_elems, cudaMemcpyHostToDevice, d->copy));
+        if (d->copy_bytes[set]) {                  // the previous copy of this set has completed (synchronised above)
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, d->ev_copy_begin[set], d->ev_copy[set]) == cudaSuccess && ms > 0.f)
+                keep(d->copy_samples, (double)d->copy_bytes[set] / (ms * 1e-3) * 1e-9);
+            d->copy_bytes[set] = 0;
+        }
+        LOE_CUDA(cudaEventRecord(d->ev_copy_begin[set], d->copy));
+        LOE_CUDA(cudaMemcpyAsync(d->pcm[set].p, src, (size_t)ns * chunk_bps, cudaMemcpyHostToDevice, d->copy));
         LOE_CUDA(cudaEventRecord(d->ev_copy[set], d->copy));
+        if (ns >= min_samples) d->copy_bytes[set] = (size_t)ns * chunk_bps;
+        d->last_wire_bytes += (int64_t)((size_t)ns * chunk_bps + sizeof(int64_t) * off_elems);
+        d->last_chunks++;
         d->used[set] = true;
         // compute buffers are shared by all chunks: growing them must wait for the chunks in flight
         const bool bp_needed = !loe_viterbi_bp_fits(max_frames, d->n_pos);
@@ -382,6 +480,18 @@ extern "C" int loe_decoder_decode_host(void* dec, const void* pcm_host, int pcm_
         frames_done += F;
     }
     LOE_CUDA(cudaStreamSynchronize(d->comp));
+    for (int set = 0; set < 2; ++set) {
+        if (!d->copy_bytes[set]) continue;
+        float ms = 0.f;
+        if (cudaEventSynchronize(d->ev_copy[set]) == cudaSuccess &&
+            cudaEventElapsedTime(&ms, d->ev_copy_begin[set], d->ev_copy[set]) == cudaSuccess && ms > 0.f)
+            keep(d->copy_samples, (double)d->copy_bytes[set] / (ms * 1e-3) * 1e-9);
+        d->copy_bytes[set] = 0;
+    }
+    d->narrow_gbps = median(d->narrow_samples);
+    d->copy_gbps = median(d->copy_samples);
+    if (deciding && (int)d->narrow_samples.size() >= kNarrowVotes && (int)d->copy_samples.size() >= kNarrowVotes)
+        d->narrow = d->narrow_gbps > kNarrowMargin * d->copy_gbps ? 1 : 0;
     memcpy(words_host, d->h_out + o_words, (size_t)n_utt * max_words);
     memcpy(count_host, d->h_out + o_count, (size_t)n_utt * 4);
     if (best_score_host) memcpy(best_score_host, d->h_out + o_score, (size_t)n_utt * 4);
@@ -397,7 +507,31 @@ extern "C" int loe_pcm_narrow_host(const float* src_host, int16_t* dst_host, int
 
 extern "C" double loe_decoder_narrow_rate(void* dec) {
     loe::Decoder* d = reinterpret_cast<loe::Decoder*>(dec);
-    return d ? (d->narrow == 0 ? -d->narrow_gbps : d->narrow_gbps) : 0.0;
+    if (!d) return 0.0;
+    const bool off = d->narrow_mode == LOE_NARROW_OFF || (d->narrow_mode == LOE_NARROW_AUTO && d->narrow == 0);
+    return off ? -d->narrow_gbps : d->narrow_gbps;
+}
+
+extern "C" int loe_decoder_set_narrow(void* dec, int mode) {
+    using namespace loe;
+    Decoder* d = reinterpret_cast<Decoder*>(dec);
+    if (!d) { set_error("decoder is NULL"); return LOE_ERR_VALUE; }
+    if (mode != LOE_NARROW_AUTO && mode != LOE_NARROW_OFF && mode != LOE_NARROW_ON) { set_error("unknown narrow mode %d", mode); return LOE_ERR_VALUE; }
+    d->narrow_mode = mode;
+    if (mode == LOE_NARROW_AUTO) { d->narrow = -1; d->narrow_samples.clear(); d->copy_samples.clear(); d->narrow_gbps = d->copy_gbps = 0.0; }
+    return LOE_OK;
+}
+
+extern "C" int loe_decoder_stats(void* dec, double* out, int n) {
+    using namespace loe;
+    Decoder* d = reinterpret_cast<Decoder*>(dec);
+    if (!d || !out) { set_error("decoder / out is NULL"); return LOE_ERR_VALUE; }
+    const int on = d->narrow_mode == LOE_NARROW_ON ? 1 : d->narrow_mode == LOE_NARROW_OFF ? 0 : d->narrow;   // -1: still measuring
+    const double v[LOE_DECODER_STATS] = {(double)d->narrow_mode, (double)on, d->narrow_gbps, d->copy_gbps, (double)d->narrow_threads,
+                                         (double)d->pinned_cpus, (double)d->last_pcm_bytes, (double)d->last_wire_bytes,
+                                         (double)d->last_chunks, (double)d->last_chunks_narrowed};
+    for (int i = 0; i < n && i < LOE_DECODER_STATS; ++i) out[i] = v[i];
+    return LOE_OK;
 }
 
 extern "C" int loe_host_alloc(void** ptr_out, size_t bytes) {

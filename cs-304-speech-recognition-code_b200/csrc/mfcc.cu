@@ -12,6 +12,8 @@
 // utterance (mfcc.py:35).  Algorithmic HBM bytes per frame: 640 (PCM) + 156 (features).
 #include "common.cuh"
 #include <math.h>
+#include <atomic>
+#include <mutex>
 
 namespace loe {
 
@@ -34,12 +36,18 @@ __device__ MfccTables g_mfcc_tables;
 // kernel B reads these as FMA operands straight from the constant bank
 __constant__ float c_dct[kCeps * kMels];        // ortho DCT-II rows
 __constant__ float c_sg1[9], c_sg2[9];          // Savitzky-Golay first / second derivative taps, width 9
-static bool g_tables_ready[64] = {false};
+static std::atomic<bool> g_tables_ready[64];
+static std::mutex g_tables_mutex;
 
+// One-time upload of the constant tables per device.  The copies go through the legacy default stream from pageable
+// memory while the kernels run on the caller's (possibly non-blocking) stream, which is not ordered after it: the
+// device is synchronised once after the uploads, and the whole initialisation is serialised between host threads.
 static int ensure_tables() {
     int dev = 0;
     LOE_CUDA(cudaGetDevice(&dev));
-    if (dev < 64 && g_tables_ready[dev]) return LOE_OK;
+    if (dev < 64 && g_tables_ready[dev].load(std::memory_order_acquire)) return LOE_OK;
+    std::lock_guard<std::mutex> lock(g_tables_mutex);
+    if (dev < 64 && g_tables_ready[dev].load(std::memory_order_acquire)) return LOE_OK;
     static MfccTables h;
     const double PI = 3.14159265358979323846;
     for (int n = 0; n < kNfft; ++n) h.hann[n] = (float)(0.5 - 0.5 * cos(2.0 * PI * n / kNfft));
@@ -68,7 +76,8 @@ static int ensure_tables() {
     }
     LOE_CUDA(cudaMemcpyToSymbol(c_sg1, sg1, sizeof(sg1)));
     LOE_CUDA(cudaMemcpyToSymbol(c_sg2, sg2, sizeof(sg2)));
-    if (dev < 64) g_tables_ready[dev] = true;
+    LOE_CUDA(cudaDeviceSynchronize());
+    if (dev < 64) g_tables_ready[dev].store(true, std::memory_order_release);
     return LOE_OK;
 }
 

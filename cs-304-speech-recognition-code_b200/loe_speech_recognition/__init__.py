@@ -45,25 +45,6 @@ __all__ = [
 _OUT_OF_SCOPE = {"Segmentation": "segmentation"}
 
 
-def _configure_multiprocessing() -> None:
-    """The reference's scripts map ``predict`` over ``concurrent.futures.ProcessPoolExecutor()``
-    (scripts/project3_predict_simple.py:23-27, project5_test_*.py:33-41) after computing MFCCs in the
-    parent.  A CUDA context does not survive fork(), so the default start method is switched to
-    "spawn" (workers then create their own engine lazily).  Set LOE_B200_KEEP_START_METHOD=1 to opt out."""
-    import multiprocessing
-    import os
-    if os.environ.get("LOE_B200_KEEP_START_METHOD"):
-        return
-    try:
-        if multiprocessing.get_start_method(allow_none=True) is None:
-            multiprocessing.set_start_method("spawn")
-    except RuntimeError:
-        pass
-
-
-_configure_multiprocessing()
-
-
 def __getattr__(name):
     """Names outside the accelerated path.  When LOE_REFERENCE_SRC points at the reference's
     ``src/loe_speech_recognition`` directory, the original host-side module is loaded from there (so

@@ -88,6 +88,21 @@ class NativeDecoder:
         < 0 measured and switched off, 0 not measured / disabled (include/loe_b200.h)."""
         return float(self._lib.loe_decoder_narrow_rate(self._h))
 
+    def set_narrow(self, mode) -> None:
+        """``"on"`` / ``"off"``: narrow float32 PCM to int16 on the host (or never); ``"auto"``: let the decoder decide
+        from its own per-chunk measurements (include/loe_b200.h, loe_decoder_set_narrow)."""
+        code = {"auto": -1, "off": 0, "on": 1, -1: -1, 0: 0, 1: 1, True: 1, False: 0}[mode]
+        _native.check(self._lib.loe_decoder_set_narrow(self._h, code))
+
+    def stats(self) -> dict:
+        """What the last ``decode`` call did on the ingestion side (loe_decoder_stats)."""
+        v = np.zeros(10, dtype=np.float64)
+        _native.check(self._lib.loe_decoder_stats(self._h, _ptr(v), 10))
+        return {"narrow_mode": {-1: "auto", 0: "off", 1: "on"}[int(v[0])],
+                "narrow_on": {1: True, 0: False}.get(int(v[1])),          # None: still sampling
+                "narrow_gbps": float(v[2]), "copy_gbps": float(v[3]), "narrow_threads": int(v[4]), "pinned_cpus": int(v[5]),
+                "pcm_bytes": int(v[6]), "wire_bytes": int(v[7]), "chunks": int(v[8]), "chunks_narrowed": int(v[9])}
+
     def close(self) -> None:
         if getattr(self, "_h", None) is not None:
             self._lib.loe_decoder_destroy(self._h)

@@ -463,10 +463,31 @@ class Engine:
         return stats, counts, bucket
 
 
+def _prefer_spawn() -> None:
+    """The reference's scripts map ``predict`` over ``concurrent.futures.ProcessPoolExecutor()``
+    (scripts/project3_predict_simple.py:23-27, project5_test_*.py:33-41) after computing MFCCs in the
+    parent.  A CUDA context does not survive fork(), so from the moment THIS process owns one, pools
+    created with the default context must spawn (workers then create their own engine lazily).  Done when
+    the engine is created -- never at import -- and only if the application has not chosen a start method
+    itself; LOE_B200_KEEP_START_METHOD=1 opts out."""
+    import multiprocessing
+    if os.environ.get("LOE_B200_KEEP_START_METHOD"):
+        return
+    try:
+        if multiprocessing.get_start_method(allow_none=True) is None:
+            multiprocessing.set_start_method("spawn")
+    except RuntimeError:
+        pass
+
+
 def get_engine() -> Engine:
     """The engine of this process (created on first use; never inherited across fork)."""
     global _ENGINE, _ENGINE_PID
     if _ENGINE is None or _ENGINE_PID != os.getpid():
+        if _ENGINE is not None:
+            raise RuntimeError("loe_speech_recognition: this process was forked from one that already owns a CUDA "
+                               "context; use the 'spawn' start method (multiprocessing.get_context('spawn'))")
         _ENGINE = Engine()
         _ENGINE_PID = os.getpid()
+        _prefer_spawn()
     return _ENGINE

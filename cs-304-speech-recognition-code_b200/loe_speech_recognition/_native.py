@@ -60,6 +60,8 @@ SIGNATURES = {
     "loe_decoder_destroy": (None, [c_void_p]),
     "loe_pcm_narrow_host": (c_int, [c_void_p, c_void_p, c_int64]),
     "loe_decoder_narrow_rate": (c_double, [c_void_p]),
+    "loe_decoder_set_narrow": (c_int, [c_void_p, c_int]),
+    "loe_decoder_stats": (c_int, [c_void_p, c_void_p, c_int]),
     "loe_host_alloc": (c_int, [c_void_p, ctypes.c_size_t]),
     "loe_host_free": (c_int, [c_void_p]),
 }

@@ -20,6 +20,7 @@ from __future__ import annotations
 import logging
 import os
 import pickle
+import zlib
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Self, Sequence, Tuple
 
@@ -57,12 +58,13 @@ class MultivariateNormal:
         return mn
 
     def log_pdf(self, x: NDArray) -> float:
-        """Single-frame log-density through the emission kernel (np.float32, like :46-48)."""
+        """Single-frame log-density through the float64 emission kernel, rounded to np.float32 like :46-48
+        (scipy evaluates in float64; one frame costs nothing, so the exact mode is used here)."""
         assert x.shape[0] == self.dim_of_features
         eng = _engine()
         gp = eng.pack_gaussians([self])
         feat = eng._to_dev(np.asarray(x, dtype=np.float32)[None, :])
-        return eng.emission(feat, gp).cpu().numpy()[0, 0]
+        return eng.emission(feat, gp, "fp64").cpu().numpy()[0, 0]
 
 
 # ----------------------------------------------------------------------------------------
@@ -88,8 +90,16 @@ class _PackCache:
 
 
 def _model_key(normals, ltp):
-    return (id(normals), len(normals), id(ltp), tuple(id(n._core) for n in normals),
-            len(ltp._core), id(ltp._core))
+    """Identity of a model for the device-pack cache: object ids plus a content fingerprint (CRC of the means,
+    the whitening matrices and the transition table), so that in-place edits and recycled addresses are seen."""
+    crc = 0
+    for n in normals:
+        crc = zlib.crc32(np.ascontiguousarray(n._core.mean).view(np.uint8), crc)
+        crc = zlib.crc32(np.ascontiguousarray(n._core.cov_object._LP).view(np.uint8), crc)
+    if ltp._core:
+        crc = zlib.crc32(np.fromiter(ltp._core.values(), dtype=np.float64, count=len(ltp._core)).view(np.uint8), crc)
+        crc = zlib.crc32(np.array(list(ltp._core.keys()), dtype=np.int32).view(np.uint8), crc)
+    return (id(normals), len(normals), id(ltp), len(ltp._core), id(ltp._core), crc)
 
 
 @dataclass

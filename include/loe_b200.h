@@ -273,7 +273,7 @@ int loe_kmeans_dev(const float* feat_dev, const uint16_t* bucket_dev, int64_t to
  *
  * loe_decoder_decode_host: pcm_host holds the utterances back to back (float32 or int16, see
  * pcm_format), utterance i = samples [sample_off[i], sample_off[i+1]).  The batch is cut into
- * n_chunks chunks of whole utterances (n_chunks <= 0: about 64 MB each, at most 8); the copy of
+ * n_chunks chunks of whole utterances (n_chunks <= 0: about 64 MB each, at most 64); the copy of
  * chunk c+1 overlaps the kernels of chunk c (pinned pcm_host makes that copy asynchronous; pageable
  * memory works, without the overlap).  Outputs (HOST): words [n_utt*max_words] int8 word ids,
  * count [n_utt] int32 (count > max_words or < 0: decode that utterance's path on the host, as
@@ -294,15 +294,31 @@ int loe_decoder_decode_host(void* decoder, const void* pcm_host, int pcm_format,
 int loe_decoder_set_h16(void* decoder, const void* b_h16_host);
 void loe_decoder_destroy(void* decoder);
 /* float32 PCM that holds int16 values (the reference converts WAV samples to float32 on the host,
- * ti_digits.py:85-139) is narrowed back to int16 by worker threads inside loe_decoder_decode_host before it
+ * ti_digits.py:85-139) can be narrowed back to int16 by worker threads inside loe_decoder_decode_host before it
  * crosses PCIe: every sample is verified (converted back and compared), a chunk with one inexact sample
- * travels as float32, and the features are bit-identical either way.  LOE_B200_NARROW_THREADS sets the
- * number of threads (default: hardware threads, at most 32; 0 = off); the decoder switches it off by itself
- * when the conversion turns out slower than the copy it saves.
+ * travels as float32, and the features are bit-identical either way.
+ *   workers: hardware threads / LOCAL_WORLD_SIZE (the ranks sharing the box, as torchrun exports it), at most 32,
+ *            bound to the CPUs next to the GPU (sysfs local_cpulist) when readable; LOE_B200_NARROW_THREADS
+ *            overrides the count (0 = never narrow), LOE_B200_NARROW_PIN=0 leaves them floating.
+ *   loe_decoder_set_narrow(mode): LOE_NARROW_ON / LOE_NARROW_OFF make it the caller's explicit choice (also
+ *            LOE_B200_NARROW=on|off in the environment when the decoder is created).  LOE_NARROW_AUTO (default):
+ *            the decoder narrows while it samples, per chunk, its conversion rate (host clock) and the wire rate
+ *            of its host->device copies (CUDA events); after 6 chunks of >= 2^20 samples each it keeps narrowing
+ *            iff median conversion GB/s (float32 bytes) > 1.1 x median copy GB/s -- the condition under which a
+ *            pipelined chunk period gets shorter -- and the verdict then stands for the decoder's lifetime.
+ *   loe_decoder_stats: out[0..LOE_DECODER_STATS) = {mode, narrowing on (1) / off (0) / still sampling (-1),
+ *            median conversion GB/s (float32 bytes), median copy GB/s (wire bytes), worker threads, CPUs the workers
+ *            are bound to (0 = floating), PCM bytes of the last call as the caller holds them, bytes that crossed
+ *            PCIe host->device in the last call, chunks of the last call, chunks of it that travelled as int16}.
  * loe_pcm_narrow_host: the same conversion as a stand-alone call (single thread): writes dst_host[i] =
  * (int16) src_host[i] and returns 1 if every sample was exact, 0 otherwise (dst contents then unspecified).
- * loe_decoder_narrow_rate: GB/s of float32 input the decoder measured for it (negative: measured and
- * switched off, 0: not measured yet). */
+ * loe_decoder_narrow_rate: median conversion GB/s measured so far (negative: narrowing is off, 0: no sample yet). */
+#define LOE_NARROW_AUTO (-1)
+#define LOE_NARROW_OFF 0
+#define LOE_NARROW_ON 1
+#define LOE_DECODER_STATS 10
+int loe_decoder_set_narrow(void* decoder, int mode);
+int loe_decoder_stats(void* decoder, double* out, int n);
 int loe_pcm_narrow_host(const float* src_host, int16_t* dst_host, int64_t n_samples);
 double loe_decoder_narrow_rate(void* decoder);
 /* page-locked host buffers for pcm_host (cudaHostAlloc / cudaFreeHost) */

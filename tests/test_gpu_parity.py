@@ -265,8 +265,22 @@ def test_isolated_predict_end_to_end(eng, golden):
         for k, w in enumerate(order[:3]):
             s, paths = models[w].predict_batch(feats, precision)
             assert rel_close(s, golden["iso_scores"][:, k], rtol=1e-4)
-            same = [np.array_equal(p, golden[f"iso_paths_{i}"][k]) for i, p in enumerate(paths)]
-            assert np.mean(same) >= (1.0 if precision == "fp64" else 0.9)
+            # every path equals the reference's, or is a near-tie by the oracle's own arithmetic (both state sequences
+            # re-scored on the oracle's scores, |delta| <= 1e-4 |score|); the float64 kernel gets no excuse at all
+            from oracle import hmm as O
+            from oracle.adjudicate import adjudicate
+            means, Us, lps, logA = oracle_flat(golden, w)
+            tr = O.word_trellis(logA)
+            excused = 0
+            for i, p in enumerate(paths):
+                want = golden[f"iso_paths_{i}"][k]
+                if np.array_equal(p, want):
+                    continue
+                assert precision != "fp64", (w, i)
+                ok, rel = adjudicate(O.emission_scores(feats[i], means, Us, lps), tr, None, p, len(means) - 1, want, len(means) - 1)
+                assert ok, (precision, w, i, rel)
+                excused += 1
+            print(f"isolated {w} {precision}: {len(paths) - excused}/{len(paths)} paths identical, {excused} margin-excused")
     score, path = models["1"].predict(feats[0])
     assert isinstance(score, np.float32) and path.dtype == np.int8 and path.shape == (feats[0].shape[0],)
     assert mc.predict(feats[0]) == str(golden["iso_labels"][0])
@@ -310,15 +324,25 @@ def test_loop_decode_strings(eng, golden, name):
     inf._log_transition_probability_between_words = PENALTIES[name]
     feats = [golden[f"loop_feat_{i}"] for i in range(10)]
     want = [str(s) for s in golden[f"loop_strings_{name}"]]
+    from oracle.adjudicate import OracleLoopDecoder, compare_loop_decodes
     assert inf.predict_batch(feats, "fp64") == want
+    od = OracleLoopDecoder({w: (golden[f"train_means_{w}"], golden[f"train_covs_{w}"], golden[f"train_logA_{w}"]) for w in LOOP_ORDER},
+                           LOOP_ORDER)
+    ems = od.emissions(feats)
     for precision in ("fp32", "tc", "h16"):
         got32 = inf.predict_batch(feats, precision)
         scores, paths = inf.viterbi_batch(feats, precision)
         assert rel_close(scores, golden[f"loop_scores_{name}"], rtol=1e-4)
-        # float32 / 3xTF32 emission: any differing path must be a near-tie (margin test)
+        # float32 / 3xTF32 / 3xFP16 emission: a differing path must be a near-tie under the ORACLE's arithmetic -- both
+        # state sequences re-scored on the oracle's scores (margin test); the oracle decode itself is
+        # pinned to the reference's golden paths
+        v = compare_loop_decodes(ems, od.trellis, PENALTIES[name], od.sizes, LOOP_ORDER, paths, got32)
+        print(f"loop {name} {precision}:", v.summary())
+        assert not v.failed, (name, precision, v.failed)
+        assert v.identical_paths + v.excused == len(feats)
+        assert v.identical_strings >= len(feats) - v.excused
         for i, (g, w) in enumerate(zip(got32, want)):
-            if g != w:
-                assert abs(scores[i] - golden[f"loop_scores_{name}"][i]) <= 1e-4 * abs(scores[i])
+            assert g == w or not np.array_equal(paths[i], golden[f"loop_path_{name}_{i}"]), (name, precision, i)
     assert inf.predict(feats[0]) == want[0]
 
 
@@ -427,8 +451,15 @@ def test_pcm_to_strings_pipeline(eng, golden):
     got = inf.decode_pcm_batch(utts)
     feats = MFCC.batch(utts, 16000)
     assert got == inf.predict_batch(feats)
-    want = [str(s) for s in golden["loop_strings_int"]][:6]
-    assert sum(g == w for g, w in zip(got, want)) >= 5
+    # vs the oracle pipeline on the same PCM: identical state paths, or a near-tie by the oracle's arithmetic
+    from oracle.adjudicate import OracleLoopDecoder
+    od = OracleLoopDecoder({w: (golden[f"train_means_{w}"], golden[f"train_covs_{w}"], golden[f"train_logA_{w}"]) for w in LOOP_ORDER},
+                           LOOP_ORDER)
+    _, paths = inf.viterbi_batch(feats)
+    v = od.compare(utts, -100, paths, got)
+    print("pcm -> strings pipeline:", v.summary())
+    assert not v.failed, v.failed
+    assert v.identical_strings >= len(utts) - v.excused
     # flat host buffer, chunked copy/compute overlap: same strings for any chunking
     flat = np.concatenate(utts)
     off = np.concatenate(([0], np.cumsum([len(u) for u in utts]))).astype(np.int64)
@@ -463,14 +494,54 @@ def test_large_batch_properties(eng, golden):
     tr = O.loop_trellis([f[3] for f in flat])
     idx = list(range(0, 2000, 10))
     ems = [O.emission_scores(feat_h[off[i]:off[i + 1]], means, Us, lps) for i in idx]
-    _, _, opaths = O.viterbi_batch(ems, tr, penalty=-100)
-    same = [np.array_equal(op, path_h[off[i]:off[i + 1]]) for i, op in zip(idx, opaths)]
-    assert np.mean(same) >= 0.97, np.mean(same)
-    # exact given the kernel's own scores
+    from oracle.adjudicate import compare_loop_decodes
+    sizes = [len(f[0]) for f in flat]
     gp, tp = inf._packs()
-    sc = eng.emission(b.feat, gp, "fp32").cpu().numpy()
-    _, _, opaths2 = O.viterbi_batch([sc[off[i]:off[i + 1]] for i in idx], tr, penalty=-100)
-    assert all(np.array_equal(op, path_h[off[i]:off[i + 1]]) for i, op in zip(idx, opaths2))
+    for precision in ("fp32", "h16"):
+        _, p_dev = inf._decode_device(b, precision)
+        p_h = p_dev.cpu().numpy()
+        # oracle emission + oracle Viterbi on the kernel's own features: identical paths or adjudicated near-ties
+        v = compare_loop_decodes(ems, tr, -100, sizes, LOOP_ORDER, [p_h[off[i]:off[i + 1]] for i in idx])
+        print(f"large batch {precision}:", v.summary())
+        assert not v.failed, (precision, v.failed[:5])
+        assert v.excused <= 10, v.summary()
+        # exact given the kernel's own scores
+        sc = eng.emission(b.feat, gp, precision).cpu().numpy()
+        _, _, opaths2 = O.viterbi_batch([sc[off[i]:off[i + 1]] for i in idx], tr, penalty=-100)
+        assert all(np.array_equal(op, p_h[off[i]:off[i + 1]]) for i, op in zip(idx, opaths2)), precision
+
+
+def test_benchmarked_path_h16_1000_utterances_vs_oracle(eng, golden):
+    """The configuration bench.py times -- config-2 strings, 3xFP16 tensor-core emission, through the C-ABI host-buffer
+    decoder (loe_decoder_decode_host) -- at 1 000 distinct utterances against the full oracle pipeline (oracle MFCC ->
+    oracle emission -> oracle Viterbi, hidden_markov_model.py:481-581).  Every utterance must give the oracle's state
+    path, or pass the margin test: both state sequences re-scored with the oracle's arithmetic within 1e-4 |score|.
+    The counts are printed; a mismatch that is not a near-tie fails the test."""
+    from oracle.adjudicate import OracleLoopDecoder
+    from loe_speech_recognition.hidden_markov_model import _penalty_args
+    from loe_speech_recognition.synthetic import string_corpus
+    inf = _loop_inference(golden)
+    inf._log_transition_probability_between_words = -100
+    utts, _ = string_corpus(seed=4242, n_utts=1000, n_digits=7)
+    off = np.concatenate(([0], np.cumsum([len(u) for u in utts]))).astype(np.int64)
+    flat = np.concatenate(utts).astype(np.float32)
+    dec = inf.native_decoder()
+    assert dec.emission == "h16"
+    strings = inf.decode_pcm_host(flat, off)
+    pen, f64 = _penalty_args(-100)
+    _, _, score, path = dec.decode(flat, off, pen, f64, LOOP_ORDER.index("S"), 32, 0, want_scores=True, want_path=True)
+    frm = np.concatenate(([0], np.cumsum(1 + np.diff(off) // 160)))
+    paths = [path[frm[i]:frm[i + 1]] for i in range(len(utts))]
+    od = OracleLoopDecoder({w: (golden[f"train_means_{w}"], golden[f"train_covs_{w}"], golden[f"train_logA_{w}"]) for w in LOOP_ORDER},
+                           LOOP_ORDER)
+    v = od.compare(utts, -100, paths, strings)
+    print("h16 / C-ABI decode of 1000 config-2 utterances vs oracle:", v.summary())
+    assert not v.failed, v.failed[:5]
+    assert v.identical_paths + v.excused == len(utts)
+    assert v.identical_strings >= len(utts) - v.excused
+    assert v.excused <= 50, v.summary()                    # near-ties are rare; a flood of them would be a precision bug
+    # the same batch through the torch-backed entry points gives the same strings
+    assert inf.decode_pcm_flat(flat, off, precision="h16") == strings
 
 
 def test_training_at_scale_matches_oracle(eng, golden):
@@ -722,11 +793,22 @@ def test_host_narrowing_of_float_pcm_is_lossless(eng, golden, monkeypatch):
     w0, c0, s0, p0 = inf.native_decoder().decode(flat, off, pen, f64, -1, 32, 3, want_scores=True, want_path=True)
     assert inf.native_decoder().narrow_rate() == 0.0
     monkeypatch.setenv("LOE_B200_NARROW_THREADS", "4")
-    monkeypatch.setenv("LOE_B200_NARROW_MIN_GBPS", "0")
+    monkeypatch.setenv("LOE_B200_NARROW_MIN_SAMPLES", "1000")
     inf.__dict__.pop("_native_decoder", None)
     dec = inf.native_decoder()
+    dec.set_narrow("on")
     w1, c1, s1, p1 = dec.decode(flat, off, pen, f64, -1, 32, 3, want_scores=True, want_path=True)
     assert dec.narrow_rate() > 0.0
+    st = dec.stats()
+    assert st["narrow_on"] is True and st["narrow_threads"] == 4 and st["chunks"] == 3 and st["chunks_narrowed"] == 3
+    assert st["pcm_bytes"] == flat.nbytes and st["wire_bytes"] == flat.nbytes // 2 + 2 * 8 * (len(off) - 1 + 3)
+    assert st["copy_gbps"] > 0.0
+    dec.set_narrow("off")
+    w1b, c1b, s1b, p1b = dec.decode(flat, off, pen, f64, -1, 32, 3, want_scores=True, want_path=True)
+    assert dec.stats()["chunks_narrowed"] == 0 and dec.stats()["wire_bytes"] > flat.nbytes and dec.narrow_rate() < 0.0
+    for a, b in ((w1, w1b), (c1, c1b), (s1, s1b), (p1, p1b)):
+        np.testing.assert_array_equal(a, b)
+    dec.set_narrow("on")
     for a, b in ((w0, w1), (c0, c1), (s0, s1), (p0, p1)):
         np.testing.assert_array_equal(a, b)
     bent = flat.copy()
@@ -735,8 +817,10 @@ def test_host_narrowing_of_float_pcm_is_lossless(eng, golden, monkeypatch):
     monkeypatch.setenv("LOE_B200_NARROW_THREADS", "0")
     w2, c2, s2, p2 = inf.native_decoder().decode(bent, off, pen, f64, -1, 32, 3, want_scores=True, want_path=True)
     monkeypatch.setenv("LOE_B200_NARROW_THREADS", "4")
+    monkeypatch.setenv("LOE_B200_NARROW", "on")
     inf.__dict__.pop("_native_decoder", None)
     w3, c3, s3, p3 = inf.native_decoder().decode(bent, off, pen, f64, -1, 32, 3, want_scores=True, want_path=True)
+    assert inf.native_decoder().stats()["chunks_narrowed"] == 2
     for a, b in ((w2, w3), (c2, c3), (s2, s3), (p2, p3)):
         np.testing.assert_array_equal(a, b)
     inf.__dict__.pop("_native_decoder", None)
