@@ -11,7 +11,9 @@ MFCC -> Gaussian emission scoring -> loop-grammar Viterbi + backtrace + word lab
   value  utterances/s with the PCM already resident in HBM (whole job, all ranks)
   e2e    same through the C-ABI host call (loe_decoder_decode_host) with HOST buffers: H2D of the
          pinned PCM, the four kernels, D2H of the word ids, string assembly -- every step
-  roofline      dominant kernel (emission scoring), timed live with CUDA events
+  roofline      the kernel with the largest live CUDA-event time of the step (roofline_all: every kernel)
+  parity        untimed gate: every distinct utterance of the batch decoded through the C ABI is compared with the
+                oracle pipeline; differing state paths must pass the both-paths margin test (oracle/adjudicate.py)
   cpu_baseline  the reference's CPU path (oracle/ref_port.py: per-(frame,state) scipy calls, process
                 pool over utterances like the reference's scripts) on a bounded sample, rank 0, N=1
 
@@ -43,9 +45,16 @@ UNIT = "utt/s"
 LOOP_ORDER = ("1", "2", "3", "4", "5", "6", "7", "8", "9", "O", "S", "Z")   # sorted(os.listdir), hmm.py:431
 PENALTY = -100                                                              # project5_test_ndigits_with_sil.py:62
 FLOPS_PER_FRAME = 2 * 40 * 39 * 58                                          # 2(D+1)D S, S = 58
-# dram__bytes_read.sum + dram__bytes_write.sum per launch at the default workload (10 000 utterances, 3.84 M frames),
-# from the committed `ncu --set full` capture (profiles/r1f_kernels.txt); None = not captured
-NCU_TRAFFIC = {"mfcc_mel": 3054381000, "mfcc_ceps": 1212527000, "emission_tc": 2368057000, "emission_h16": 2076703000, "viterbi": 899512000}
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch at the default workload, from the committed `ncu --set full`
+    captures: profiles/ncu_traffic.json maps kernel -> {"bytes", "capture"}.  Not a measurement of THIS run (ncu cannot run
+    inside a timed bench): every roofline entry names the capture its traffic figure came from, or carries null."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:
+        return {}
 
 
 def golden_params():
@@ -230,7 +239,9 @@ def impl_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- correctness gate: device path vs per-utterance public API on a few utterances
+    # ---- correctness gate (untimed): device path vs per-utterance public API on a few utterances, and -- rank 0 -- EVERY
+    #      distinct utterance of the batch through the C-ABI decoder against the oracle pipeline (oracle MFCC -> emission ->
+    #      Viterbi); a differing state path must pass the margin test (both sequences re-scored by the oracle, 1e-4 |score|)
     path, words, count = step_device()
     torch.cuda.synchronize()
     labels = inf._model_boundaries._labels
@@ -238,6 +249,22 @@ def impl_b200(args):
     from loe_speech_recognition import MFCC
     want = [inf.predict(x) for x in MFCC.batch(utts[:4], 16000)]
     assert got == want, (got, want)
+    parity = None
+    if rank == 0 and not args.no_parity_gate:
+        from oracle.adjudicate import OracleLoopDecoder
+        n_gate = min(args.pool, n)
+        g_off = pcm_off[:n_gate + 1]
+        g_flat = np.concatenate(utts[:n_gate]).astype(np.float32)
+        dec = inf.native_decoder(16000, dev.index or 0)
+        g_strings = inf.decode_pcm_host(g_flat, g_off, 16000, device=dev.index or 0)
+        _, _, _, g_path = dec.decode(g_flat, g_off, pen, False, skip, 32, 0, want_path=True)
+        g_paths = [g_path[frm_off[i]:frm_off[i + 1]] for i in range(n_gate)]
+        od = OracleLoopDecoder(params, LOOP_ORDER)
+        verdict = od.compare(utts[:n_gate], PENALTY, g_paths, g_strings)
+        parity = {**verdict.summary(), "emission": dec.emission, "api": "loe_decoder_decode_host",
+                  "rule": "state path identical to the oracle's, or both state sequences re-scored with the oracle's arithmetic "
+                          "within 1e-4 |score| (oracle/adjudicate.py)"}
+        assert not verdict.failed, verdict.failed[:5]
 
     # ---- device-resident throughput
     for _ in range(args.warmup):
@@ -315,9 +342,10 @@ def impl_b200(args):
     assert strings16 == strings
     # the same batch through the torch-free C entry point (loe_decoder_decode_host): host pointers in, word ids out
     host_np, host16_np = pinned.numpy(), pinned16.numpy()
-    c_abi = {}
+    c_abi, c_stats = {}, {}
+    dec = inf.native_decoder(16000, dev.index or 0)
     for tag, buf in (("f32", host_np), ("s16", host16_np)):
-        for _ in range(2):
+        for _ in range(3):                     # the first calls also settle the decoder's narrowing verdict (6 chunks)
             strings_c = inf.decode_pcm_host(buf, pcm_off, 16000, device=dev.index or 0)
         barrier()
         t0 = time.perf_counter()
@@ -328,8 +356,31 @@ def impl_b200(args):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         c_abi[tag] = float(t.item())
+        c_stats[tag] = dec.stats()
         assert strings_c == strings
-    h2d = int(pinned.numel() * 4 + pcm_off.nbytes + frm_off.nbytes)
+    # what the box can do at best: every rank streams the same float32 bytes from the same pinned buffer with bare
+    # cudaMemcpyAsync calls, one per chunk, nothing else running (max over ranks).  e2e is stated as a fraction of it.
+    n_ch = max(1, c_stats["f32"]["chunks"])
+    sink = torch.empty_like(pcm_dev)
+    edges = np.linspace(0, pinned.numel(), n_ch + 1).astype(np.int64)
+
+    def bare_copy():
+        for a, b in zip(edges[:-1], edges[1:]):
+            sink[a:b].copy_(pinned[a:b], non_blocking=True)
+    for _ in range(2):
+        bare_copy()
+    barrier()
+    ce0, ce1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ce0.record()
+    for _ in range(args.steps):
+        bare_copy()
+    ce1.record()
+    barrier()
+    t = torch.tensor([ce0.elapsed_time(ce1) / args.steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ceiling_ms = float(t.item())
+    del sink
     d2h = int(n * 32 + n * 4)
 
     if rank != 0:
@@ -349,13 +400,17 @@ def impl_b200(args):
     n_samples = int(pcm_off[-1])
     # algorithmic work per launch and DRAM traffic per launch from the committed ncu capture
     # (profiles/r1l_kernels.txt, emission_tc: r1f; dram__bytes_read.sum + dram__bytes_write.sum at this workload size)
+    traffic = ncu_traffic() if (n == 10000 and args.pool == 500) else {}     # the captures are of the default workload
     kernels = {
-        "mfcc_mel_kernel": {"bound": "hbm", "alg": 4 * n_samples + 160 * F, "ms": stage_ms["mfcc_mel"], "traffic": NCU_TRAFFIC.get("mfcc_mel")},
-        "mfcc_ceps_kernel": {"bound": "hbm", "alg": (160 + 156) * F, "ms": stage_ms["mfcc_ceps"], "traffic": NCU_TRAFFIC.get("mfcc_ceps")},
+        "mfcc_mel_kernel": {"bound": "hbm", "alg": 4 * n_samples + 160 * F, "ms": stage_ms["mfcc_mel"]},
+        "mfcc_ceps_kernel": {"bound": "hbm", "alg": (160 + 156) * F, "ms": stage_ms["mfcc_ceps"]},
         {"tc": "emission_tc_kernel", "h16": "emission_h16_kernel"}.get(precision, "emission_simt_kernel"):
-            {"bound": "tensor", "alg": FLOPS_PER_FRAME * F, "ms": stage_ms["emission"], "traffic": NCU_TRAFFIC.get("emission_" + precision)},
-        "viterbi_warp_kernel": {"bound": "hbm", "alg": (4 * 58 + 1) * F, "ms": stage_ms["viterbi"], "traffic": NCU_TRAFFIC.get("viterbi")},
+            {"bound": "tensor", "alg": FLOPS_PER_FRAME * F, "ms": stage_ms["emission"]},
+        "viterbi_warp_kernel": {"bound": "hbm", "alg": (4 * 58 + 1) * F, "ms": stage_ms["viterbi"]},
     }
+    for name, k in kernels.items():
+        k["traffic"] = traffic.get(name, {}).get("bytes")
+        k["traffic_source"] = traffic.get(name, {}).get("capture")
     all_roof = {}
     for name, k in kernels.items():
         if k["bound"] == "hbm":
@@ -363,7 +418,7 @@ def impl_b200(args):
         else:
             ach, peak, unit = k["alg"] / (k["ms"] * 1e-3) / 1e12, (bf16 if precision == "h16" else tf32_peak), "TFLOP/s"
         all_roof[name] = {"kernel": name, "bound": k["bound"], "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
-                          "traffic": k["traffic"], "ms_per_launch": k["ms"],
+                          "traffic": k["traffic"], "traffic_source": k["traffic_source"], "ms_per_launch": k["ms"],
                           "algorithmic": (f"{k['alg']} bytes per launch" if k["bound"] == "hbm" else
                                           f"{FLOPS_PER_FRAME} flop/frame x {F} frames per launch (counted once; 3 split-operand products issued)")}
     dominant = max(kernels, key=lambda kname: kernels[kname]["ms"])
@@ -394,19 +449,29 @@ def impl_b200(args):
         "dtype": {"fp32": "f32", "fp64": "f64", "tc": "tf32x3", "h16": "f16x3"}[precision], "data": "synthetic",
         "config": {**workload_config(n, min(args.pool, n), "gpu"), "frames_per_gpu": F, "emission": precision},
         "frames_per_s": world * F / (ms * 1e-3),
-        "e2e": {"value": world * n / c_abi["f32"], "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+        "e2e": {"value": world * n / c_abi["f32"], "unit": UNIT, "h2d_bytes_per_step": c_stats["f32"]["wire_bytes"], "d2h_bytes_per_step": d2h,
                 "ms_per_step": c_abi["f32"] * 1e3,
+                "host_pcm_bytes_per_step": c_stats["f32"]["pcm_bytes"],
+                "narrow_on": c_stats["f32"]["narrow_on"], "narrow_mode": c_stats["f32"]["narrow_mode"],
+                "narrow_gbps": c_stats["f32"]["narrow_gbps"], "copy_gbps": c_stats["f32"]["copy_gbps"],
+                "narrow_threads": c_stats["f32"]["narrow_threads"], "narrow_pinned_cpus": c_stats["f32"]["pinned_cpus"],
+                "chunks": c_stats["f32"]["chunks"], "host_cpus": os.cpu_count(),
+                "h2d_ceiling": {"ms_per_step": ceiling_ms, "gbps_per_gpu": pinned.numel() * 4 / (ceiling_ms * 1e-3) / 1e9,
+                                "what": f"{world} rank(s) x bare pinned cudaMemcpyAsync of the same float32 PCM, one call per chunk "
+                                        f"({n_ch} chunks), CUDA events, max over ranks"},
+                "frac_of_h2d_ceiling": ceiling_ms / (c_abi["f32"] * 1e3),
                 "api": "loe_decoder_decode_host (C ABI, include/loe_b200.h) called through HiddenMarkovModelInference.decode_pcm_host: "
                        "pinned host float32 PCM in, digit strings out; numpy + ctypes only, streams / workspace / chunk overlap "
                        "inside the C library",
                 "string_accuracy_vs_truth": acc},
         "e2e_int16_pcm": {"value": world * n / c_abi["s16"], "unit": UNIT, "ms_per_step": c_abi["s16"] * 1e3,
-                          "h2d_bytes_per_step": int(pinned16.numel() * 2 + pcm_off.nbytes + frm_off.nbytes),
+                          "h2d_bytes_per_step": c_stats["s16"]["wire_bytes"],
                           "note": "same call fed the raw int16 WAV samples instead of the reference's float32 copy; identical strings"},
         "e2e_python_api": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_s * 1e3, "int16_value": world * n / e2e16_s,
                            "int16_ms_per_step": e2e16_s * 1e3,
                            "api": "HiddenMarkovModelInference.decode_pcm_flat (torch tensors / streams as plumbing); identical strings"},
         "gpu_launches": launches,
+        "parity": parity,
         "clocks": clocks,
         "roofline": roofline,
         "roofline_all": all_roof,
@@ -436,6 +501,7 @@ def main():
     ap.add_argument("--pool", type=int, default=500, help="distinct synthetic utterances (tiled to --utts)")
     ap.add_argument("--precision", default=os.environ.get("LOE_B200_EMISSION", "auto"), choices=["auto", "fp32", "fp64", "tc", "h16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-gate", action="store_true", help="skip the oracle comparison of every distinct utterance (rank 0, untimed)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
