@@ -148,3 +148,60 @@ def mfcc_feature_vector(y, sr=16000, n_mfcc=N_MFCC):
 def mfcc_batch(signals, sr=16000):
     """Equivalent of ``MFCC.batch``: list of (T, 39) transposed views."""
     return [mfcc_feature_vector(s, sr).T for s in signals]
+
+
+# --------------------------------------------------------------------------------------
+# Parameterised front end (BASELINE.json configs[3] "spec" set; SURVEY.md §8c last row)
+# --------------------------------------------------------------------------------------
+# PARITY UNPINNED BY CONSTRUCTION: the live reference has exactly one parameter set (mfcc.py:31-34) and never
+# calls pre-emphasis, a Hamming window, a 512-point FFT or cepstral mean normalisation.  What follows is the
+# same librosa-shaped pipeline as above with those stages made parameters; with REFERENCE_CONFIG it reduces to
+# mfcc_feature_vector (tests/test_oracle_golden.py::test_parameterised_mfcc_reduces_to_reference).
+REFERENCE_CONFIG = dict(n_fft=320, win_length=320, hop_length=160, window="hann", n_mels=40, fmin=FMIN, fmax=FMAX,
+                        preemphasis=0.0, log="db", n_mfcc=13, norm="frame")
+# 25 ms / 10 ms frames at 16 kHz, 512-point FFT, Hamming, pre-emphasis 0.97, natural log, CMN
+SPEC_CONFIG = dict(n_fft=512, win_length=400, hop_length=160, window="hamming", n_mels=40, fmin=FMIN, fmax=FMAX,
+                   preemphasis=0.97, log="ln", n_mfcc=13, norm="cmn")
+
+
+def preemphasis(y, coef):
+    """y[n] - coef * y[n-1] with y[-1] := y[0] (the first sample keeps (1 - coef) of its value), float32 arithmetic."""
+    y = np.asarray(y, dtype=np.float32)
+    if coef == 0.0:
+        return y
+    prev = np.concatenate((y[:1], y[:-1]))
+    return (y - np.float32(coef) * prev).astype(np.float32)
+
+
+def mfcc_feature_vector_ex(y, sr=16000, cfg=None):
+    """(3 * n_mfcc, T) float32 features of one signal under ``cfg`` (a dict like REFERENCE_CONFIG)."""
+    c = dict(REFERENCE_CONFIG)
+    c.update(cfg or {})
+    if not isinstance(y, np.ndarray):
+        raise TypeError("Input signal must be a numpy array.")
+    if y.ndim != 1:
+        raise ValueError("Input signal must be 1-dimensional.")
+    y = preemphasis(y.astype(np.float32), c["preemphasis"])
+    power = stft_power(y, n_fft=c["n_fft"], hop=c["hop_length"], window=c["window"], win_length=c["win_length"])
+    basis = mel_basis(sr, n_fft=c["n_fft"], n_mels=c["n_mels"], fmin=c["fmin"], fmax=c["fmax"])
+    mel = np.einsum("ft,mf->mt", power, basis, optimize=True)
+    if c["log"] == "db":
+        lm = power_to_db(mel)
+    elif c["log"] == "ln":
+        lm = np.log(np.maximum(1e-10, mel))
+    else:
+        raise ValueError(c["log"])
+    ceps = scipy.fft.dct(lm, axis=-2, type=2, norm="ortho")[: c["n_mfcc"], :]
+    d1 = delta(ceps, 1)
+    d2 = delta(ceps, 2)
+    if c["norm"] == "frame":
+        static = normalize_mfccs(ceps)
+    elif c["norm"] == "cmn":                 # cepstral mean normalisation: per coefficient, over the utterance's frames
+        static = ceps - np.mean(ceps, axis=1, keepdims=True)
+    elif c["norm"] == "cmvn":
+        static = (ceps - np.mean(ceps, axis=1, keepdims=True)) / (np.std(ceps, axis=1, keepdims=True) + 1e-8)
+    elif c["norm"] == "none":
+        static = ceps
+    else:
+        raise ValueError(c["norm"])
+    return np.concatenate((static, d1, d2), axis=0).astype(np.float32)

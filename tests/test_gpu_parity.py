@@ -806,11 +806,12 @@ def test_host_narrowing_of_float_pcm_is_lossless(eng, golden, monkeypatch):
     dec.set_narrow("off")
     w1b, c1b, s1b, p1b = dec.decode(flat, off, pen, f64, -1, 32, 3, want_scores=True, want_path=True)
     assert dec.stats()["chunks_narrowed"] == 0 and dec.stats()["wire_bytes"] > flat.nbytes and dec.narrow_rate() < 0.0
-    valid = np.arange(32)[None, :] < c1[:, None]             # ids past an utterance's count are unspecified
-    for a, b in ((np.where(valid, w1, 0), np.where(valid, w1b, 0)), (c1, c1b), (s1, s1b), (p1, p1b)):
+    def ids(w, c):                                           # ids past an utterance's count are unspecified
+        return np.where(np.arange(32)[None, :] < c[:, None], w, 0)
+    for a, b in ((ids(w1, c1), ids(w1b, c1b)), (c1, c1b), (s1, s1b), (p1, p1b)):
         np.testing.assert_array_equal(a, b)
     dec.set_narrow("on")
-    for a, b in ((w0, w1), (c0, c1), (s0, s1), (p0, p1)):
+    for a, b in ((ids(w0, c0), ids(w1, c1)), (c0, c1), (s0, s1), (p0, p1)):
         np.testing.assert_array_equal(a, b)
     bent = flat.copy()
     bent[int(off[9]) + 1234] += 0.25                                # the middle chunk can no longer be narrowed
@@ -822,7 +823,7 @@ def test_host_narrowing_of_float_pcm_is_lossless(eng, golden, monkeypatch):
     inf.__dict__.pop("_native_decoder", None)
     w3, c3, s3, p3 = inf.native_decoder().decode(bent, off, pen, f64, -1, 32, 3, want_scores=True, want_path=True)
     assert inf.native_decoder().stats()["chunks_narrowed"] == 2
-    for a, b in ((w2, w3), (c2, c3), (s2, s3), (p2, p3)):
+    for a, b in ((ids(w2, c2), ids(w3, c3)), (c2, c3), (s2, s3), (p2, p3)):
         np.testing.assert_array_equal(a, b)
     inf.__dict__.pop("_native_decoder", None)
 
