@@ -1,0 +1,336 @@
+// Parameterised MFCC front end for sm_100a (BASELINE.json configs[3], "spec" parameter set: 25 ms / 10 ms frames,
+// 512-point FFT, Hamming window, pre-emphasis 0.97, 40 mel bands, natural log, 13 cepstra + delta + delta-delta, CMN).
+//
+// The reference has ONE parameter set (mfcc.py:31-34: n_fft 320, hop 160, Hann, dB, per-frame normalisation), served by
+// the specialised kernels of mfcc.cu.  This file is the same librosa-shaped pipeline (mfcc.py:24-44) with the stages
+// the north star names made parameters: any power-of-two FFT size up to 1024, any window (host table, so Hamming /
+// Hann / a short window centred in a longer FFT), pre-emphasis, dB or natural log, and the normalisation of the static
+// block (none / per frame as the reference does / cepstral mean / mean and variance over the utterance).
+//
+//   mel_ex_kernel    PCM -> pre-emphasis -> window -> N-point real FFT (N/2-point complex Stockham radix-4 FFT of one
+//                    frame per warp in shared memory + real-input post-pass) -> |.|^2 -> triangular filterbank
+//                    -> mel energies [frames, n_mels] (+ per-utterance maximum for the dB mode)
+//   ceps_ex_kernel   mel -> log -> DCT-II -> cepstra [frames, n_ceps]            (thread per frame)
+//   cmn_ex_kernel    per-utterance mean (and 1/std) of every cepstral coefficient, fixed summation order (CTA per utterance)
+//   feat_ex_kernel   normalised static block + Savitzky-Golay delta / delta-delta (width 9) -> features [frames, 3 n_ceps]
+//
+// Algorithmic HBM bytes per frame: 4 * hop (PCM) + 12 * n_ceps (features).
+#include "common.cuh"
+#include <math.h>
+
+namespace loe {
+
+constexpr int kWarpsE = 4;
+constexpr int kMaxMelsE = 64;
+constexpr int kMaxCepsE = 16;
+
+__device__ __forceinline__ float2 cmulE(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ float sample_f32(const float* x, int64_t i) { return __ldg(x + i); }
+__device__ __forceinline__ float sample_f32(const short* x, int64_t i) { return (float)__ldg(x + i); }
+
+// Shared memory of mel_ex_kernel<LOG2N>: per warp two ping-pong buffers of M = N/2 complex points (the second one
+// also takes the power spectrum), CTA-wide the twiddles W_M^j (j < M), W_N^k (k <= M) and the window.
+template <int LOG2N>
+struct SmemE {
+    static constexpr int N = 1 << LOG2N, M = N / 2;
+    float2 buf[kWarpsE][2][M];
+    float2 wm[M];
+    float2 wn[M + 1];
+    float win[N];
+};
+
+template <typename SampleT, int LOG2N>
+__global__ void __launch_bounds__(kWarpsE * 32)
+mel_ex_kernel(const SampleT* __restrict__ pcm, const int64_t* __restrict__ pcm_off, const int64_t* __restrict__ frm_off,
+              const float* __restrict__ window, int hop, float preemph,
+              const int32_t* __restrict__ mel_start, const int32_t* __restrict__ mel_len, const float* __restrict__ mel_w,
+              int mel_pitch, int n_mels, int chunk, float* __restrict__ mel_out, float* __restrict__ utt_max) {
+    using S = SmemE<LOG2N>;
+    constexpr int N = S::N, M = S::M;
+    extern __shared__ __align__(16) unsigned char smem_raw_e[];
+    S& sm = *reinterpret_cast<S*>(smem_raw_e);
+    const int u = blockIdx.x;
+    const int64_t f0 = frm_off[u];
+    const int T = (int)(frm_off[u + 1] - f0);
+    const int t_begin = blockIdx.y * chunk;
+    if (t_begin >= T) return;
+    const int t_end = min(T, t_begin + chunk);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int j = tid; j < M; j += kWarpsE * 32) {
+        float s, c;
+        sincospif(-2.0f * (float)j / (float)M, &s, &c);
+        sm.wm[j] = make_float2(c, s);
+    }
+    for (int k = tid; k <= M; k += kWarpsE * 32) {
+        float s, c;
+        sincospif(-2.0f * (float)k / (float)N, &s, &c);
+        sm.wn[k] = make_float2(c, s);
+    }
+    for (int i = tid; i < N; i += kWarpsE * 32) sm.win[i] = window[i];
+    __syncthreads();
+
+    const int64_t s0 = pcm_off[u];
+    const int64_t n_samples = pcm_off[u + 1] - s0;
+    const SampleT* __restrict__ x = pcm + s0;
+    float2* a = sm.buf[warp][0];
+    float2* b = sm.buf[warp][1];
+    float vmax = 0.f;
+    // emphasised sample i of the utterance (zero outside: centre padding); y[0] keeps (1 - preemph) x[0]
+    auto emph = [&](int64_t i) -> float {
+        if (i < 0 || i >= n_samples) return 0.f;
+        const float cur = sample_f32(x, i);
+        if (preemph == 0.f) return cur;
+        const float prev = sample_f32(x, i > 0 ? i - 1 : 0);
+        return __fsub_rn(cur, __fmul_rn(preemph, prev));         // never contracted: float32 and int16 PCM agree bit for bit
+    };
+    for (int t = t_begin + warp; t < t_end; t += kWarpsE) {
+        const int64_t base = (int64_t)hop * t - N / 2;
+        // z[n] = (w[2n] y[2n], w[2n+1] y[2n+1])
+        for (int n = lane; n < M; n += 32)
+            a[n] = make_float2(sm.win[2 * n] * emph(base + 2 * n), sm.win[2 * n + 1] * emph(base + 2 * n + 1));
+        __syncwarp();
+        // Stockham autosort FFT of M points: radix-4 passes (sub-transform size Ns = 1, 4, 16, ...), one radix-2 pass at
+        // the end when log2 M is odd.  Pass: v[r] = in[j + r M/R] W^(r (j mod Ns) M / (Ns R)); out[expand(j) + r Ns] = DFT_R(v)[r]
+        float2* in = a;
+        float2* out = b;
+        int Ns = 1;
+#pragma unroll 1
+        for (; Ns * 4 <= M; Ns *= 4) {
+            const int tw_step = M / (Ns * 4);
+            for (int j = lane; j < M / 4; j += 32) {
+                const int k = j & (Ns - 1);
+                float2 v0 = in[j], v1 = in[j + M / 4], v2 = in[j + M / 2], v3 = in[j + 3 * M / 4];
+                if (Ns > 1) {
+                    v1 = cmulE(v1, sm.wm[k * tw_step]);
+                    v2 = cmulE(v2, sm.wm[2 * k * tw_step]);
+                    v3 = cmulE(v3, sm.wm[3 * k * tw_step]);
+                }
+                const float2 s0_ = make_float2(v0.x + v2.x, v0.y + v2.y), s1_ = make_float2(v0.x - v2.x, v0.y - v2.y);
+                const float2 s2_ = make_float2(v1.x + v3.x, v1.y + v3.y), s3_ = make_float2(v1.x - v3.x, v1.y - v3.y);
+                const int j0 = ((j - k) << 2) + k;
+                out[j0] = make_float2(s0_.x + s2_.x, s0_.y + s2_.y);
+                out[j0 + Ns] = make_float2(s1_.x + s3_.y, s1_.y - s3_.x);          // s1 - i s3
+                out[j0 + 2 * Ns] = make_float2(s0_.x - s2_.x, s0_.y - s2_.y);
+                out[j0 + 3 * Ns] = make_float2(s1_.x - s3_.y, s1_.y + s3_.x);      // s1 + i s3
+            }
+            __syncwarp();
+            float2* tmp = in; in = out; out = tmp;
+        }
+        if (Ns < M) {                                   // one radix-2 pass left (Ns == M / 2)
+            for (int j = lane; j < M / 2; j += 32) {
+                const float2 v0 = in[j], v1 = cmulE(in[j + M / 2], sm.wm[j]);          // k = j, step = M / (2 Ns) = 1
+                out[j] = make_float2(v0.x + v1.x, v0.y + v1.y);
+                out[j + Ns] = make_float2(v0.x - v1.x, v0.y - v1.y);
+            }
+            __syncwarp();
+            float2* tmp = in; in = out; out = tmp;
+        }
+        // real-input post-pass: X[k] = (E + W_N^k O) / 2 with E = Z[k] + conj Z[M-k], O = -i (Z[k] - conj Z[M-k]);
+        // power spectrum into the other buffer (M + 1 floats)
+        float* pw = reinterpret_cast<float*>(out);
+        for (int k = lane; k <= M; k += 32) {
+            const float2 A = in[k & (M - 1)], B = in[(M - k) & (M - 1)];
+            const float2 e = make_float2(A.x + B.x, A.y - B.y);
+            const float2 o = make_float2(A.y + B.y, B.x - A.x);
+            const float2 wo = cmulE(sm.wn[k], o);
+            const float xr = e.x + wo.x, xi = e.y + wo.y;
+            pw[k] = 0.25f * (xr * xr + xi * xi);
+        }
+        __syncwarp();
+        // triangular filters: lane takes filters lane, lane + 32, ...
+        float* mo = mel_out + (f0 + t) * n_mels;
+        for (int m = lane; m < n_mels; m += 32) {
+            const int st = mel_start[m], len = mel_len[m];
+            const float* w = mel_w + (size_t)m * mel_pitch;
+            float acc = 0.f;
+            for (int i = 0; i < len; ++i) acc = fmaf(__ldg(w + i), pw[st + i], acc);
+            mo[m] = acc;
+            vmax = fmaxf(vmax, acc);
+        }
+        __syncwarp();
+    }
+    if (utt_max) {
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+        if (lane == 0) atomicMax(reinterpret_cast<int*>(utt_max + u), __float_as_int(vmax));        // mel >= 0
+    }
+}
+
+// thread per frame: log, DCT-II (coefficient table in shared memory)
+__global__ void __launch_bounds__(128)
+ceps_ex_kernel(const float* __restrict__ mel, const float* __restrict__ utt_max, const int64_t* __restrict__ frm_off, int n_utt,
+               int64_t total_frames, const float* __restrict__ dct, int n_mels, int n_ceps, int log_mode, float* __restrict__ ceps) {
+    __shared__ float s_dct[kMaxCepsE * kMaxMelsE];
+    for (int i = threadIdx.x; i < n_ceps * n_mels; i += blockDim.x) s_dct[i] = dct[i];
+    __syncthreads();
+    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= total_frames) return;
+    float ref_db = 0.f;
+    if (log_mode == LOE_LOG_DB) {
+        int lo = 0, hi = n_utt;                    // utterance of this frame: last u with frm_off[u] <= f
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (frm_off[mid] <= f) lo = mid; else hi = mid; }
+        ref_db = 10.0f * log10f(fmaxf(1e-10f, utt_max[lo]));
+    }
+    float lm[kMaxMelsE];
+    const float* row = mel + f * n_mels;
+#pragma unroll 1
+    for (int m = 0; m < n_mels; ++m) {
+        const float e = fmaxf(1e-10f, __ldg(row + m));
+        lm[m] = log_mode == LOE_LOG_DB ? fmaxf(10.0f * log10f(e) - ref_db, -80.0f) : logf(e);
+    }
+    float* o = ceps + f * n_ceps;
+    for (int k = 0; k < n_ceps; ++k) {
+        float acc = 0.f;
+        for (int m = 0; m < n_mels; ++m) acc = fmaf(s_dct[k * n_mels + m], lm[m], acc);
+        o[k] = acc;
+    }
+}
+
+// CTA per utterance: mean and 1 / (std + 1e-8) of every coefficient over the utterance's frames.  Thread t sums the
+// frames t, t + 128, ... in float64, the partials are combined in a fixed tree: bitwise reproducible.
+__global__ void __launch_bounds__(128)
+cmn_ex_kernel(const float* __restrict__ ceps, const int64_t* __restrict__ frm_off, int n_ceps, float* __restrict__ stat) {
+    __shared__ double s_sum[128], s_sq[128];
+    const int u = blockIdx.x;
+    const int64_t f0 = frm_off[u];
+    const int T = (int)(frm_off[u + 1] - f0);
+    for (int k = 0; k < n_ceps; ++k) {
+        double a = 0.0, q = 0.0;
+        for (int t = threadIdx.x; t < T; t += 128) { const double v = ceps[(f0 + t) * n_ceps + k]; a += v; q += v * v; }
+        s_sum[threadIdx.x] = a; s_sq[threadIdx.x] = q;
+        __syncthreads();
+        for (int o = 64; o >= 1; o >>= 1) {
+            if (threadIdx.x < o) { s_sum[threadIdx.x] += s_sum[threadIdx.x + o]; s_sq[threadIdx.x] += s_sq[threadIdx.x + o]; }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            const double mean = s_sum[0] / T;
+            const double var = fmax(0.0, s_sq[0] / T - mean * mean);
+            stat[(size_t)u * 2 * n_ceps + k] = (float)mean;
+            stat[(size_t)u * 2 * n_ceps + n_ceps + k] = (float)(1.0 / (sqrt(var) + 1e-8));
+        }
+        __syncthreads();
+    }
+}
+
+// thread per frame: normalised static block, Savitzky-Golay delta / delta-delta of width 9 over the raw cepstra (edge
+// frames take the value of the nearest full window: scipy savgol_filter mode="interp" with polyorder == deriv)
+__global__ void __launch_bounds__(128)
+feat_ex_kernel(const float* __restrict__ ceps, const float* __restrict__ stat, const int64_t* __restrict__ frm_off, int n_utt,
+               int64_t total_frames, int n_ceps, int norm_mode, float* __restrict__ feat) {
+    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= total_frames) return;
+    int lo = 0, hi = n_utt;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (frm_off[mid] <= f) lo = mid; else hi = mid; }
+    const int64_t f0 = frm_off[lo];
+    const int T = (int)(frm_off[lo + 1] - f0);
+    const int t = (int)(f - f0);
+    const float* c = ceps + f * n_ceps;
+    float* o = feat + f * 3 * n_ceps;
+    if (norm_mode == LOE_NORM_FRAME) {
+        float mean = 0.f;
+        for (int k = 0; k < n_ceps; ++k) mean += c[k];
+        mean /= (float)n_ceps;
+        float var = 0.f;
+        for (int k = 0; k < n_ceps; ++k) { const float d = c[k] - mean; var = fmaf(d, d, var); }
+        const float inv = 1.0f / (sqrtf(var / (float)n_ceps) + 1e-8f);
+        for (int k = 0; k < n_ceps; ++k) o[k] = (c[k] - mean) * inv;
+    } else if (norm_mode == LOE_NORM_CMN || norm_mode == LOE_NORM_CMVN) {
+        const float* st = stat + (size_t)lo * 2 * n_ceps;
+        for (int k = 0; k < n_ceps; ++k) {
+            const float d = c[k] - st[k];
+            o[k] = norm_mode == LOE_NORM_CMVN ? d * st[n_ceps + k] : d;
+        }
+    } else {
+        for (int k = 0; k < n_ceps; ++k) o[k] = c[k];
+    }
+    const int cc = min(max(t, 4), T - 5);
+    for (int k = 0; k < n_ceps; ++k) {
+        float d1 = 0.f, d2 = 0.f;
+#pragma unroll
+        for (int q = -4; q <= 4; ++q) {
+            const float cv = __ldg(ceps + (f0 + cc + q) * n_ceps + k);
+            d1 = fmaf((float)q * (1.0f / 60.0f), cv, d1);
+            d2 = fmaf((float)(3 * q * q - 20) * (1.0f / 462.0f), cv, d2);
+        }
+        o[n_ceps + k] = d1;
+        o[2 * n_ceps + k] = d2;
+    }
+}
+
+template <typename SampleT, int LOG2N>
+static int launch_mel_ex(const void* pcm_dev, const int64_t* pcm_off_dev, const int64_t* frm_off_dev, int n_utt, int max_frames,
+                         int chunk, const loe_mfcc_config* cfg, const float* window_dev, const int32_t* mel_start_dev,
+                         const int32_t* mel_len_dev, const float* mel_w_dev, int mel_pitch, float* mel_ws_dev, float* utt_max_dev,
+                         cudaStream_t s) {
+    using S = SmemE<LOG2N>;
+    LOE_CUDA(cudaFuncSetAttribute(mel_ex_kernel<SampleT, LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S)));
+    dim3 grid((unsigned)n_utt, (unsigned)((max_frames + chunk - 1) / chunk));
+    mel_ex_kernel<SampleT, LOG2N><<<grid, kWarpsE * 32, sizeof(S), s>>>(
+        (const SampleT*)pcm_dev, pcm_off_dev, frm_off_dev, window_dev, cfg->hop, cfg->preemph, mel_start_dev, mel_len_dev, mel_w_dev,
+        mel_pitch, cfg->n_mels, chunk, mel_ws_dev, cfg->log_mode == LOE_LOG_DB ? utt_max_dev : nullptr);
+    LOE_LAUNCH_CHECK("mel_ex_kernel");
+    return LOE_OK;
+}
+
+}  // namespace loe
+
+extern "C" int loe_mfcc_ex_dev(const void* pcm_dev, int pcm_format, const int64_t* pcm_off_dev, const int64_t* frm_off_dev,
+                               int n_utt, int64_t total_frames, int max_frames, int min_frames, const loe_mfcc_config* cfg,
+                               const float* window_dev, const int32_t* mel_start_dev, const int32_t* mel_len_dev,
+                               const float* mel_w_dev, int mel_pitch, const float* dct_dev, float* mel_ws_dev, float* ceps_ws_dev,
+                               float* utt_stat_dev, float* feat_dev, void* stream) {
+    using namespace loe;
+    if (n_utt <= 0 || total_frames <= 0) return LOE_OK;
+    if (!cfg) { set_error("cfg is NULL"); return LOE_ERR_VALUE; }
+    if (min_frames < 9) {
+        set_error("MFCC needs at least 9 frames per utterance for the width-9 delta filter (got %d)", min_frames);
+        return LOE_ERR_VALUE;
+    }
+    int log2n = 0;
+    while ((1 << log2n) < cfg->n_fft) ++log2n;
+    if ((1 << log2n) != cfg->n_fft || log2n < 6 || log2n > 10) {
+        set_error("n_fft = %d: the parameterised front end takes a power of two in 64..1024 (320 is served by loe_mfcc_dev)", cfg->n_fft);
+        return LOE_ERR_UNSUPPORTED;
+    }
+    if (cfg->hop <= 0 || cfg->n_mels <= 0 || cfg->n_mels > kMaxMelsE || cfg->n_ceps <= 0 || cfg->n_ceps > kMaxCepsE ||
+        cfg->n_ceps > cfg->n_mels || mel_pitch <= 0) {
+        set_error("bad front-end sizes (hop %d, n_mels %d <= %d, n_ceps %d <= %d)", cfg->hop, cfg->n_mels, kMaxMelsE, cfg->n_ceps, kMaxCepsE);
+        return LOE_ERR_VALUE;
+    }
+    if (cfg->log_mode != LOE_LOG_DB && cfg->log_mode != LOE_LOG_LN) { set_error("unknown log_mode %d", cfg->log_mode); return LOE_ERR_VALUE; }
+    if (cfg->norm_mode < LOE_NORM_NONE || cfg->norm_mode > LOE_NORM_CMVN) { set_error("unknown norm_mode %d", cfg->norm_mode); return LOE_ERR_VALUE; }
+    if (pcm_format != LOE_PCM_F32 && pcm_format != LOE_PCM_S16) { set_error("unknown pcm_format %d", pcm_format); return LOE_ERR_VALUE; }
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (cfg->log_mode == LOE_LOG_DB) LOE_CUDA(cudaMemsetAsync(utt_stat_dev, 0, sizeof(float) * (size_t)n_utt, s));
+    int sms = 0, dev = 0;
+    LOE_CUDA(cudaGetDevice(&dev));
+    LOE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    // frames per CTA: the per-CTA table set-up (twiddles, window) is paid once per chunk; keep ~8 CTAs per SM in flight or queued
+    int64_t chunk64 = total_frames / (8 * (int64_t)sms);
+    chunk64 = ((chunk64 + kWarpsE - 1) / kWarpsE) * kWarpsE;
+    const int chunk = (int)(chunk64 < 64 ? 64 : chunk64 > (1 << 20) ? (1 << 20) : chunk64);
+    int st = LOE_OK;
+#define LOE_EX(L)                                                                                                                    \
+    case L:                                                                                                                          \
+        st = pcm_format == LOE_PCM_F32                                                                                               \
+                 ? launch_mel_ex<float, L>(pcm_dev, pcm_off_dev, frm_off_dev, n_utt, max_frames, chunk, cfg, window_dev, mel_start_dev, \
+                                           mel_len_dev, mel_w_dev, mel_pitch, mel_ws_dev, utt_stat_dev, s)                            \
+                 : launch_mel_ex<short, L>(pcm_dev, pcm_off_dev, frm_off_dev, n_utt, max_frames, chunk, cfg, window_dev, mel_start_dev, \
+                                           mel_len_dev, mel_w_dev, mel_pitch, mel_ws_dev, utt_stat_dev, s);                           \
+        break
+    switch (log2n) { LOE_EX(6); LOE_EX(7); LOE_EX(8); LOE_EX(9); LOE_EX(10); }
+#undef LOE_EX
+    if (st != LOE_OK) return st;
+    const unsigned blocks = (unsigned)((total_frames + 127) / 128);
+    ceps_ex_kernel<<<blocks, 128, 0, s>>>(mel_ws_dev, utt_stat_dev, frm_off_dev, n_utt, total_frames, dct_dev, cfg->n_mels, cfg->n_ceps,
+                                          cfg->log_mode, ceps_ws_dev);
+    LOE_LAUNCH_CHECK("ceps_ex_kernel");
+    if (cfg->norm_mode == LOE_NORM_CMN || cfg->norm_mode == LOE_NORM_CMVN) {
+        cmn_ex_kernel<<<(unsigned)n_utt, 128, 0, s>>>(ceps_ws_dev, frm_off_dev, cfg->n_ceps, utt_stat_dev);
+        LOE_LAUNCH_CHECK("cmn_ex_kernel");
+    }
+    feat_ex_kernel<<<blocks, 128, 0, s>>>(ceps_ws_dev, utt_stat_dev, frm_off_dev, n_utt, total_frames, cfg->n_ceps, cfg->norm_mode, feat_dev);
+    LOE_LAUNCH_CHECK("feat_ex_kernel");
+    return LOE_OK;
+}

@@ -11,7 +11,7 @@ f1 / f4) are plain Python mirrors of the reference's modules.  Out of scope: the
 segmenter (``Segmentation``, needs sounddevice and audio hardware); accessing it raises NotImplementedError
 unless LOE_REFERENCE_SRC points at a reference checkout.
 """
-from .mfcc import MFCC
+from .mfcc import MFCC, MFCCConfig
 from .ti_digits import TIDigits, DataLoader, TI_DIGITS_LABELS, TI_DIGITS_LABEL_TYPE
 from .hidden_markov_model import (Signal, HiddenMarkovModel, HiddenMarkovModelTrainable, HiddenMarkovModelInference,
                                   HiddenMarkovModelTrainContinuous)
@@ -23,6 +23,7 @@ from .csvnia import CSVReader, CSVWriter
 
 __all__ = [
     "MFCC",
+    "MFCCConfig",
     "TIDigits",
     "DataLoader",
     "TI_DIGITS_LABELS",

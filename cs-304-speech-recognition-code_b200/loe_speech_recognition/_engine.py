@@ -289,10 +289,44 @@ class Engine:
         self.launches += (phases & 1) + ((phases >> 1) & 1)
         return out
 
-    def upload_pcm(self, signals: Sequence[np.ndarray]):
+    def _ex_tables(self, sample_rate, config):
+        key = (float(sample_rate), config)
+        if key not in self._mel_cache:
+            start, length, w = config.mel_tables(sample_rate)
+            self._mel_cache[key] = (self._to_dev(config.window_table()), self._to_dev(start), self._to_dev(length), self._to_dev(w),
+                                    int(w.shape[1]), self._to_dev(config.dct_table()))
+        return self._mel_cache[key]
+
+    def mfcc_ex_device(self, pcm, pcm_off, frm_off, n_utt, total_frames, max_frames, min_frames, sample_rate, config,
+                       out=None, mel_ws=None, ceps_ws=None, utt_stat=None):
+        """PCM (device) -> features [total_frames, 3 n_mfcc] (device) under an MFCCConfig (loe_mfcc_ex_dev)."""
+        import ctypes
+        torch = self.torch
+        win, start, length, w, pitch, dct = self._ex_tables(sample_rate, config)
+        nc = int(config.n_mfcc)
+        out = self.empty((total_frames, 3 * nc), torch.float32) if out is None else out
+        mel_ws = self.empty((total_frames, config.n_mels), torch.float32) if mel_ws is None else mel_ws
+        ceps_ws = self.empty((total_frames, nc), torch.float32) if ceps_ws is None else ceps_ws
+        utt_stat = self.empty((n_utt, 2 * nc), torch.float32) if utt_stat is None else utt_stat
+        if pcm.dtype == torch.int16:
+            fmt = 1
+        elif pcm.dtype == torch.float32:
+            fmt = 0
+        else:
+            raise TypeError(f"PCM must be float32 or int16 on the device (got {pcm.dtype})")
+        cfg = _native.MfccConfigStruct(int(config.n_fft), int(config.hop_length), int(config.n_mels), nc,
+                                       _native.LOG_MODES[config.log], _native.NORM_MODES[config.norm], float(config.preemphasis), 0.0)
+        _native.check(self.lib.loe_mfcc_ex_dev(pcm.data_ptr(), fmt, pcm_off.data_ptr(), frm_off.data_ptr(), n_utt, total_frames,
+                                               max_frames, min_frames, ctypes.addressof(cfg), win.data_ptr(), start.data_ptr(),
+                                               length.data_ptr(), w.data_ptr(), pitch, dct.data_ptr(), mel_ws.data_ptr(),
+                                               ceps_ws.data_ptr(), utt_stat.data_ptr(), out.data_ptr(), self._stream()))
+        self.launches += 3 + (1 if config.norm in ("cmn", "cmvn") else 0)
+        return out
+
+    def upload_pcm(self, signals: Sequence[np.ndarray], hop: int = 160):
         lens = np.array([s.shape[0] for s in signals], dtype=np.int64)
         pcm_off = np.concatenate(([0], np.cumsum(lens))).astype(np.int64)
-        frames = 1 + lens // 160
+        frames = 1 + lens // hop
         frm_off = np.concatenate(([0], np.cumsum(frames))).astype(np.int64)
         # int16 signals (raw WAV samples) stay int16 on the wire; anything else is shipped as float32
         dt = np.int16 if all(s.dtype == np.int16 for s in signals) else np.float32
@@ -300,7 +334,12 @@ class Engine:
             else np.ascontiguousarray(signals[0], dtype=dt)
         return self._to_dev(flat), self._to_dev(pcm_off), self._to_dev(frm_off), frm_off, frames
 
-    def mfcc(self, signals: Sequence[np.ndarray], sample_rate=16000) -> Batch:
+    def mfcc(self, signals: Sequence[np.ndarray], sample_rate=16000, config=None) -> Batch:
+        if config is not None and not config.is_reference:
+            pcm, pcm_off, frm_off_dev, frm_off, frames = self.upload_pcm(signals, int(config.hop_length))
+            feat = self.mfcc_ex_device(pcm, pcm_off, frm_off_dev, len(signals), int(frm_off[-1]), int(frames.max()),
+                                       int(frames.min()), sample_rate, config)
+            return Batch(feat, frm_off_dev, frm_off, len(signals), int(frames.max()))
         pcm, pcm_off, frm_off_dev, frm_off, frames = self.upload_pcm(signals)
         feat = self.mfcc_device(pcm, pcm_off, frm_off_dev, len(signals), int(frm_off[-1]), int(frames.max()),
                                 int(frames.min()), sample_rate)

@@ -30,6 +30,8 @@ SIGNATURES = {
                              c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "loe_mfcc_phase_dev": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64, c_int, c_int,
                                    c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
+    "loe_mfcc_ex_dev": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p,
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "loe_emission_dev": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int,
                                  c_void_p, c_int, c_int, c_void_p]),
     "loe_emission_tc_tiles": (c_int, [c_int]),
@@ -65,6 +67,17 @@ SIGNATURES = {
     "loe_host_alloc": (c_int, [c_void_p, ctypes.c_size_t]),
     "loe_host_free": (c_int, [c_void_p]),
 }
+
+
+
+class MfccConfigStruct(ctypes.Structure):
+    """loe_mfcc_config (include/loe_b200.h)."""
+    _fields_ = [("n_fft", ctypes.c_int32), ("hop", ctypes.c_int32), ("n_mels", ctypes.c_int32), ("n_ceps", ctypes.c_int32),
+                ("log_mode", ctypes.c_int32), ("norm_mode", ctypes.c_int32), ("preemph", ctypes.c_float), ("reserved", ctypes.c_float)]
+
+
+LOG_MODES = {"db": 0, "ln": 1}
+NORM_MODES = {"none": 0, "frame": 1, "cmn": 2, "cmvn": 3}
 
 _lib = None
 

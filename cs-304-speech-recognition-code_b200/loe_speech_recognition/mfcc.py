@@ -126,6 +126,80 @@ def mel_lane_tables(sample_rate: float):
     return np.ascontiguousarray(bins.reshape(-1)), np.ascontiguousarray(w.reshape(-1)), int(na), int(nb)
 
 
+@dataclass(frozen=True)
+class MFCCConfig:
+    """Front-end parameters (added; the reference hard-wires REFERENCE, mfcc.py:31-34).  ``MFCC.batch(..., config=)``
+    runs any other set through ``loe_mfcc_ex_dev`` (csrc/mfcc_ex.cu): power-of-two FFT sizes up to 1024, a window
+    shorter than the FFT (centred, zero-padded, as librosa pads it), pre-emphasis, dB or natural log, and the
+    normalisation of the static block.  ``MFCCConfig.spec()`` is BASELINE.json configs[3]."""
+    n_fft: int = N_FFT
+    win_length: int = N_FFT
+    hop_length: int = HOP
+    window: str = "hann"                 # "hann" | "hamming" (periodic, scipy.signal.get_window(fftbins=True))
+    n_mels: int = N_MELS
+    fmin: float = FMIN
+    fmax: float = FMAX
+    preemphasis: float = 0.0
+    log: str = "db"                      # "db": power_to_db(ref=np.max), top_db 80 | "ln": natural log
+    n_mfcc: int = 13
+    norm: str = "frame"                  # "frame" (mfcc.py:62-66) | "cmn" | "cmvn" | "none"
+
+    @classmethod
+    def spec(cls) -> "MFCCConfig":
+        """25 ms / 10 ms frames at 16 kHz, 512-point FFT, Hamming, pre-emphasis 0.97, 40 mel, 13 ceps + deltas, CMN."""
+        return cls(n_fft=512, win_length=400, window="hamming", preemphasis=0.97, log="ln", norm="cmn")
+
+    @property
+    def is_reference(self) -> bool:
+        return self == MFCCConfig()
+
+    def window_table(self) -> NDArray[np.float32]:
+        n = np.arange(self.win_length, dtype=np.float64)
+        if self.window == "hann":
+            w = 0.5 - 0.5 * np.cos(2.0 * np.pi * n / self.win_length)
+        elif self.window == "hamming":
+            w = 0.54 - 0.46 * np.cos(2.0 * np.pi * n / self.win_length)
+        else:
+            raise ValueError(f"unknown window {self.window!r}")
+        if self.win_length > self.n_fft:
+            raise ValueError("win_length must not exceed n_fft")
+        lpad = (self.n_fft - self.win_length) // 2
+        out = np.zeros(self.n_fft, dtype=np.float32)
+        out[lpad:lpad + self.win_length] = w
+        return out
+
+    def mel_tables(self, sample_rate: float):
+        """(start int32 [n_mels], length int32 [n_mels], weights float32 [n_mels, pitch]) of the slaney filterbank."""
+        n_bins = 1 + self.n_fft // 2
+        freqs = np.arange(n_bins, dtype=np.float64) * (float(sample_rate) / self.n_fft)
+        edges = _slaney_mel_to_hz(np.linspace(_slaney_hz_to_mel(self.fmin), _slaney_hz_to_mel(self.fmax), self.n_mels + 2))
+        width = np.diff(edges)
+        dense = np.zeros((self.n_mels, n_bins), dtype=np.float32)
+        for m in range(self.n_mels):
+            rise = (freqs - edges[m]) / width[m]
+            fall = (edges[m + 2] - freqs) / width[m + 1]
+            dense[m] = np.maximum(0.0, np.minimum(rise, fall))
+        dense *= (2.0 / (edges[2:] - edges[:-2]))[:, None].astype(np.float32)
+        start = np.zeros(self.n_mels, dtype=np.int32)
+        length = np.zeros(self.n_mels, dtype=np.int32)
+        for m in range(self.n_mels):
+            nz = np.nonzero(dense[m])[0]
+            if len(nz):
+                start[m], length[m] = nz[0], nz[-1] - nz[0] + 1
+        pitch = max(1, int(length.max()))
+        w = np.zeros((self.n_mels, pitch), dtype=np.float32)
+        for m in range(self.n_mels):
+            w[m, :length[m]] = dense[m, start[m]:start[m] + length[m]]
+        return start, length, w
+
+    def dct_table(self) -> NDArray[np.float32]:
+        k = np.arange(self.n_mfcc, dtype=np.float64)[:, None]
+        n = np.arange(self.n_mels, dtype=np.float64)[None, :]
+        d = np.sqrt(2.0 / self.n_mels) * np.cos(np.pi * (2 * n + 1) * k / (2.0 * self.n_mels))
+        d[0] /= np.sqrt(2.0)
+        return d.astype(np.float32)
+
+
 @dataclass
 class MFCC:
     # Input
@@ -157,8 +231,9 @@ class MFCC:
         return (mfccs - mean) / (std + 1e-8)
 
     @classmethod
-    def batch(cls, signals: List[NDArray], sample_rate: int) -> List[NDArray[np.float32]]:
-        """List of (T, 39) float32 feature matrices (row = frame), one kernel pass for all signals."""
+    def batch(cls, signals: List[NDArray], sample_rate: int, config: "MFCCConfig | None" = None) -> List[NDArray[np.float32]]:
+        """List of (T, 39) float32 feature matrices (row = frame), one kernel pass for all signals.
+        ``config`` (added, default = the reference's parameter set) selects another front end, see MFCCConfig."""
         from ._engine import get_engine
 
         for s in signals:
@@ -166,7 +241,7 @@ class MFCC:
         if len(signals) == 0:
             return []
         eng = get_engine()
-        b = eng.mfcc(signals, sample_rate)
+        b = eng.mfcc(signals, sample_rate, config)
         flat = b.feat.cpu().numpy()
         off = b.frm_off_host
         return [flat[off[i]:off[i + 1]] for i in range(len(signals))]

@@ -100,6 +100,46 @@ int loe_mfcc_phase_dev(const void* pcm_dev, int pcm_format, const int64_t* pcm_o
                        float* mel_ws_dev, float* utt_max_dev, float* feat_dev, void* stream, int phases);
 
 /* --------------------------------------------------------------------------------------
+ * Parameterised MFCC front end (csrc/mfcc_ex.cu).  The reference hard-wires one parameter set (mfcc.py:31-34), which
+ * loe_mfcc_dev serves; this entry point is the same pipeline (mfcc.py:24-44) with the stages made parameters, for
+ * BASELINE.json configs[3] (25 ms / 10 ms frames, 512-point FFT, Hamming, pre-emphasis 0.97, 40 mel, 13 ceps + deltas,
+ * cepstral mean normalisation).  No live reference call site: parity is against the restated oracle only.
+ *
+ *   frames(u) = 1 + samples(u) / hop, frame t covers samples [hop t - n_fft/2, hop t + n_fft/2), zeros outside
+ *   y[i] = x[i] - preemph * x[i-1]  (x[-1] := x[0]);  window_dev [n_fft] (a shorter window zero-padded to n_fft, centred)
+ *   filter m = sum_i mel_w_dev[m * mel_pitch + i] * power[mel_start_dev[m] + i], i < mel_len_dev[m]
+ *   log_mode LOE_LOG_DB: 10 log10(max(1e-10, mel)) - 10 log10(max over the utterance), floored at -80 (power_to_db
+ *            ref=np.max);  LOE_LOG_LN: ln(max(1e-10, mel))
+ *   dct_dev [n_ceps * n_mels] (row k = coefficient k);  deltas: Savitzky-Golay width 9 on the raw cepstra
+ *   norm_mode (static block only): NONE, FRAME ((c - mean_k c) / (std_k c + 1e-8) inside each frame, mfcc.py:62-66),
+ *            CMN (c - mean over the utterance's frames), CMVN (CMN / (std over the frames + 1e-8))
+ *   workspaces: mel_ws_dev [total_frames * n_mels], ceps_ws_dev [total_frames * n_ceps],
+ *               utt_stat_dev [n_utt * 2 * n_ceps]  (float32)
+ *   feat_dev [total_frames * 3 * n_ceps] out, row-major (frame, coefficient)
+ * -------------------------------------------------------------------------------------- */
+#define LOE_LOG_DB 0
+#define LOE_LOG_LN 1
+#define LOE_NORM_NONE 0
+#define LOE_NORM_FRAME 1
+#define LOE_NORM_CMN 2
+#define LOE_NORM_CMVN 3
+typedef struct loe_mfcc_config {
+    int32_t n_fft;       /* power of two, 64 .. 1024 */
+    int32_t hop;
+    int32_t n_mels;      /* <= 64 */
+    int32_t n_ceps;      /* <= 16 */
+    int32_t log_mode;    /* LOE_LOG_* */
+    int32_t norm_mode;   /* LOE_NORM_* */
+    float preemph;       /* 0 = none */
+    float reserved;
+} loe_mfcc_config;
+int loe_mfcc_ex_dev(const void* pcm_dev, int pcm_format, const int64_t* pcm_off_dev, const int64_t* frm_off_dev,
+                    int n_utt, int64_t total_frames, int max_frames, int min_frames, const loe_mfcc_config* cfg,
+                    const float* window_dev, const int32_t* mel_start_dev, const int32_t* mel_len_dev,
+                    const float* mel_w_dev, int mel_pitch, const float* dct_dev, float* mel_ws_dev, float* ceps_ws_dev,
+                    float* utt_stat_dev, float* feat_dev, void* stream);
+
+/* --------------------------------------------------------------------------------------
  * Gaussian emission scoring.  Replaces MultivariateNormal.log_pdf
  * (hidden_markov_model.py:46-48 -> scipy multivariate_normal_frozen.logpdf) for every
  * (frame, state) pair at once:

@@ -109,6 +109,45 @@ def test_kernels_stay_inside_their_buffers(eng, golden):
         assert bool(torch.isfinite(feat).all()) and bool(torch.isfinite(sc).all()) and bool((feat != -12345.0).any())
 
 
+def test_parameterised_mfcc_matches_oracle(eng):
+    """g2 / BASELINE configs[3]: the parameterised front end (loe_mfcc_ex_dev) against the restated oracle
+    (parity unpinned by construction -- no live reference call site) for the "spec" set and variations of every
+    parameter; float32 and int16 PCM bit-identical; ragged batch; errors."""
+    from dataclasses import asdict, replace
+    from loe_speech_recognition import MFCC, MFCCConfig
+    from oracle import mfcc as OM
+    rng = np.random.default_rng(21)
+    t = np.arange(70000)
+    sigs = []
+    for L in (1600, 1441, 16000, 23457, 64000, 5000, 30001):
+        f = rng.uniform(200, 4000, 3)
+        sig = sum(3000 * np.sin(2 * np.pi * fi * t[:L] / 16000 + rng.uniform(0, 6)) for fi in f) + rng.normal(0, 30, L)
+        sigs.append(np.round(sig).astype(np.int16))
+    spec = MFCCConfig.spec()
+    configs = [spec, replace(spec, log="db", norm="frame"), replace(spec, norm="cmvn"), replace(spec, norm="none", preemphasis=0.0),
+               MFCCConfig(n_fft=256, win_length=256, hop_length=128), MFCCConfig(n_fft=1024, win_length=800, hop_length=320, window="hamming"),
+               MFCCConfig(n_fft=512, win_length=512, hop_length=160), MFCCConfig(n_fft=64, win_length=64, hop_length=32, n_mels=20, fmax=7000.0)]
+    for cfg in configs:
+        got = MFCC.batch([s.astype(np.float32) for s in sigs], 16000, config=cfg)
+        got16 = MFCC.batch(sigs, 16000, config=cfg)
+        for s, g, g16 in zip(sigs, got, got16):
+            ref = OM.mfcc_feature_vector_ex(s.astype(np.float32), 16000, asdict(cfg)).T
+            assert g.shape == ref.shape and g.dtype == np.float32, (cfg, g.shape, ref.shape)
+            atol = 1e-4 * max(np.abs(ref[:, :13]).max(), 1.0)
+            assert rel_close(g, ref, rtol=1e-4, atol=atol), (cfg, len(s), np.abs(g - ref).max())
+            assert np.array_equal(g, g16), cfg
+    # the reference's own parameter set through config= takes the specialised kernels
+    a = MFCC.batch([sigs[2].astype(np.float32)], 16000, config=MFCCConfig())[0]
+    assert np.array_equal(a, MFCC.batch([sigs[2].astype(np.float32)], 16000)[0])
+    with pytest.raises(NotImplementedError):
+        MFCC.batch([sigs[2].astype(np.float32)], 16000, config=MFCCConfig(n_fft=400, win_length=400))
+    with pytest.raises(ValueError):
+        MFCC.batch([np.zeros(1000, np.float32)], 16000, config=spec)          # 7 frames < 9
+    # bitwise reproducible (fixed-order CMN sums)
+    b1 = MFCC.batch(sigs, 16000, config=spec); b2 = MFCC.batch(sigs, 16000, config=spec)
+    assert all(np.array_equal(x, y) for x, y in zip(b1, b2))
+
+
 # ------------------------------------------------------------------ a2 emission
 @pytest.mark.parametrize("precision,rtol", [("fp32", 1e-4), ("fp64", 1e-6), ("tc", 1e-4), ("h16", 1e-4)])
 def test_emission_matches_scipy(eng, golden, precision, rtol):

@@ -111,3 +111,54 @@ def test_emission_h16_pairing_table():
     assert sorted(products) == sorted(want)                 # hi*hi + lo*hi + hi*lo of every chunk, once each
     assert rows[0][4] == 5                                  # the first MMA (accumulate = 0) overwrites all 240 columns
     assert sum(r[4] for r in rows) * 48 == 1248             # 65 % of the dense 8 x 240
+
+
+def _stockham_real_power(x, N):
+    """NumPy walk through mel_ex_kernel's FFT (csrc/mfcc_ex.cu): z[n] = x[2n] + i x[2n+1], Stockham autosort passes of
+    radix 4 (sub-transform size Ns = 1, 4, ...) plus one radix-2 pass when log2(N/2) is odd, with the kernel's index
+    arithmetic (j0 = ((j - k) << 2) + k, twiddle index r k M / (4 Ns)), then the real-input post-pass."""
+    M = N // 2
+    wm = np.exp(-2j * np.pi * np.arange(M) / M)
+    wn = np.exp(-2j * np.pi * np.arange(M + 1) / N)
+    a = x[0::2] + 1j * x[1::2]
+    Ns = 1
+    while Ns * 4 <= M:
+        out = np.zeros(M, dtype=complex)
+        step = M // (Ns * 4)
+        for j in range(M // 4):
+            k = j & (Ns - 1)
+            v0, v1, v2, v3 = a[j], a[j + M // 4], a[j + M // 2], a[j + 3 * M // 4]
+            if Ns > 1:
+                v1 *= wm[k * step]; v2 *= wm[2 * k * step]; v3 *= wm[3 * k * step]
+            s0, s1, s2, s3 = v0 + v2, v0 - v2, v1 + v3, v1 - v3
+            j0 = ((j - k) << 2) + k
+            out[j0] = s0 + s2
+            out[j0 + Ns] = s1 - 1j * s3
+            out[j0 + 2 * Ns] = s0 - s2
+            out[j0 + 3 * Ns] = s1 + 1j * s3
+        a = out
+        Ns *= 4
+    if Ns < M:
+        out = np.zeros(M, dtype=complex)
+        for j in range(M // 2):
+            v0, v1 = a[j], a[j + M // 2] * wm[j]
+            out[j] = v0 + v1
+            out[j + Ns] = v0 - v1
+        a = out
+    pw = np.zeros(M + 1)
+    for k in range(M + 1):
+        A, B = a[k & (M - 1)], a[(M - k) & (M - 1)]
+        e = complex(A.real + B.real, A.imag - B.imag)
+        o = complex(A.imag + B.imag, B.real - A.real)
+        xk = e + wn[k] * o
+        pw[k] = 0.25 * abs(xk) ** 2
+    return pw
+
+
+def test_parameterised_fft_index_arithmetic():
+    rng = np.random.default_rng(0)
+    for N in (64, 128, 256, 512, 1024):
+        x = rng.normal(size=N)
+        ref = np.abs(np.fft.rfft(x)) ** 2
+        got = _stockham_real_power(x, N)
+        assert np.allclose(got, ref, rtol=1e-10, atol=1e-10), N

@@ -164,3 +164,21 @@ def test_mfcc_oracle_against_independent_librosa_restatements():
                                               f_min=OM.FMIN, f_max=OM.FMAX, n_mels=OM.N_MELS, power=2.0, center=True,
                                               pad_mode="constant", norm="slaney", mel_scale="slaney")(torch.from_numpy(y)).numpy()
     assert ms.shape == mel.shape and np.abs(ms - mel).max() < 1e-4 * np.abs(mel).max()
+
+
+def test_parameterised_mfcc_reduces_to_reference():
+    """oracle.mfcc.mfcc_feature_vector_ex (the configs[3] front end, parity unpinned by construction) with the
+    reference's parameter set IS the pinned-as-far-as-possible restatement; the "spec" set changes what it should."""
+    from oracle import mfcc as OM
+    rng = np.random.default_rng(4)
+    y = np.round(rng.normal(0, 2000, size=24000)).astype(np.float32)
+    assert np.array_equal(OM.mfcc_feature_vector_ex(y, 16000, OM.REFERENCE_CONFIG), OM.mfcc_feature_vector(y).astype(np.float32))
+    spec = OM.mfcc_feature_vector_ex(y, 16000, OM.SPEC_CONFIG)
+    assert spec.shape == (39, 151) and spec.dtype == np.float32
+    assert np.abs(spec[:13].mean(axis=1)).max() < 1e-4                       # CMN: zero mean over time per coefficient
+    e = OM.preemphasis(y, 0.97)
+    assert e[0] == np.float32(y[0] - np.float32(0.97) * y[0]) and e[5] == np.float32(y[5] - np.float32(0.97) * y[4])
+    # a 400-sample Hamming window centred in a 512-point FFT: frame t only sees samples [160 t - 200, 160 t + 200)
+    y2 = y.copy(); y2[160 * 50 + 201:160 * 50 + 250] += 500.0
+    p1 = OM.stft_power(y, 512, 160, "hamming", 400); p2 = OM.stft_power(y2, 512, 160, "hamming", 400)
+    assert np.array_equal(p1[:, 50], p2[:, 50]) and not np.array_equal(p1[:, 51], p2[:, 51])
