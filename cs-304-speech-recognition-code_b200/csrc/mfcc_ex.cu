@@ -17,6 +17,7 @@
 // Algorithmic HBM bytes per frame: 4 * hop (PCM) + 12 * n_ceps (features).
 #include "common.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace loe {
 
@@ -44,7 +45,7 @@ __global__ void __launch_bounds__(kWarpsE * 32)
 mel_ex_kernel(const SampleT* __restrict__ pcm, const int64_t* __restrict__ pcm_off, const int64_t* __restrict__ frm_off,
               const float* __restrict__ window, int hop, float preemph,
               const int32_t* __restrict__ mel_start, const int32_t* __restrict__ mel_len, const float* __restrict__ mel_w,
-              int mel_pitch, int n_mels, int chunk, float* __restrict__ mel_out, float* __restrict__ utt_max) {
+              int mel_pitch, int n_mels, int chunk, float* __restrict__ mel_out, float* __restrict__ utt_max, int knock) {
     using S = SmemE<LOG2N>;
     constexpr int N = S::N, M = S::M;
     extern __shared__ __align__(16) unsigned char smem_raw_e[];
@@ -86,6 +87,7 @@ mel_ex_kernel(const SampleT* __restrict__ pcm, const int64_t* __restrict__ pcm_o
     for (int t = t_begin + warp; t < t_end; t += kWarpsE) {
         const int64_t base = (int64_t)hop * t - N / 2;
         // z[n] = (w[2n] y[2n], w[2n+1] y[2n+1])
+        if (!(knock & 1))
         for (int n = lane; n < M; n += 32)
             a[n] = make_float2(sm.win[2 * n] * emph(base + 2 * n), sm.win[2 * n + 1] * emph(base + 2 * n + 1));
         __syncwarp();
@@ -96,6 +98,7 @@ mel_ex_kernel(const SampleT* __restrict__ pcm, const int64_t* __restrict__ pcm_o
         int Ns = 1;
 #pragma unroll 1
         for (; Ns * 4 <= M; Ns *= 4) {
+            if (knock & 2) continue;
             const int tw_step = M / (Ns * 4);
             for (int j = lane; j < M / 4; j += 32) {
                 const int k = j & (Ns - 1);
@@ -128,6 +131,7 @@ mel_ex_kernel(const SampleT* __restrict__ pcm, const int64_t* __restrict__ pcm_o
         // real-input post-pass: X[k] = (E + W_N^k O) / 2 with E = Z[k] + conj Z[M-k], O = -i (Z[k] - conj Z[M-k]);
         // power spectrum into the other buffer (M + 1 floats)
         float* pw = reinterpret_cast<float*>(out);
+        if (!(knock & 4))
         for (int k = lane; k <= M; k += 32) {
             const float2 A = in[k & (M - 1)], B = in[(M - k) & (M - 1)];
             const float2 e = make_float2(A.x + B.x, A.y - B.y);
@@ -139,6 +143,7 @@ mel_ex_kernel(const SampleT* __restrict__ pcm, const int64_t* __restrict__ pcm_o
         __syncwarp();
         // triangular filters: lane takes filters lane, lane + 32, ...
         float* mo = mel_out + (f0 + t) * n_mels;
+        if (!(knock & 8))
         for (int m = lane; m < n_mels; m += 32) {
             const int st = mel_start[m], len = mel_len[m];
             const float* w = mel_w + (size_t)m * mel_pitch;
@@ -268,7 +273,7 @@ static int launch_mel_ex(const void* pcm_dev, const int64_t* pcm_off_dev, const 
     dim3 grid((unsigned)n_utt, (unsigned)((max_frames + chunk - 1) / chunk));
     mel_ex_kernel<SampleT, LOG2N><<<grid, kWarpsE * 32, sizeof(S), s>>>(
         (const SampleT*)pcm_dev, pcm_off_dev, frm_off_dev, window_dev, cfg->hop, cfg->preemph, mel_start_dev, mel_len_dev, mel_w_dev,
-        mel_pitch, cfg->n_mels, chunk, mel_ws_dev, cfg->log_mode == LOE_LOG_DB ? utt_max_dev : nullptr);
+        mel_pitch, cfg->n_mels, chunk, mel_ws_dev, cfg->log_mode == LOE_LOG_DB ? utt_max_dev : nullptr, getenv("LOE_MEL_EX_KNOCK") ? atoi(getenv("LOE_MEL_EX_KNOCK")) : 0);
     LOE_LAUNCH_CHECK("mel_ex_kernel");
     return LOE_OK;
 }

@@ -52,6 +52,22 @@ class GaussPack:
 
 
 @dataclass
+class GmmPack:
+    """Flat device copy of a DiagGMM (gmm.py): per-component arrays for the SIMT kernels, the tensor-core image if its
+    entries fit the binary16 pair."""
+    n_states: int
+    n_mix: int
+    mean32: "torch.Tensor"
+    iv32: "torch.Tensor"
+    cst32: "torch.Tensor"
+    mean64: "torch.Tensor"
+    iv64: "torch.Tensor"
+    cst64: "torch.Tensor"
+    b_img: "torch.Tensor" = None
+    shift_scale: "torch.Tensor" = None
+
+
+@dataclass
 class TrellisPack:
     tr_off: "torch.Tensor"
     col: "torch.Tensor"
@@ -378,6 +394,50 @@ class Engine:
         mean, u, cst = (gp.mean64, gp.u64, gp.cst64) if code == 1 else (gp.mean32, gp.u32, gp.cst32)
         _native.check(self.lib.loe_emission_dev(feat.data_ptr(), n_frames, dim, mean.data_ptr(), u.data_ptr(), cst.data_ptr(),
                                                 gp.n_states, out.data_ptr(), ld, code, self._stream()))
+        self.launches += 1
+        return out
+
+    # ------------------------------------------------------------------ diagonal GMM emission
+    def pack_gmm(self, weights, means, variances) -> GmmPack:
+        from .gmm import LOG_2PI, pack_gmm_image
+        S, M, D = means.shape
+        with np.errstate(divide="ignore"):
+            cst = np.log(weights) - 0.5 * (D * LOG_2PI + np.sum(np.log(variances), axis=-1))
+        m = np.ascontiguousarray(means.reshape(S * M, D)); iv = np.ascontiguousarray((1.0 / variances).reshape(S * M, D))
+        c = np.ascontiguousarray(cst.reshape(S * M))
+        gp = GmmPack(S, M, self._to_dev(m.astype(np.float32)), self._to_dev(iv.astype(np.float32)), self._to_dev(c.astype(np.float32)),
+                     self._to_dev(m), self._to_dev(iv), self._to_dev(c))
+        img = pack_gmm_image(weights, means, variances) if D == 39 else None
+        if img is not None:
+            gp.b_img, gp.shift_scale = self._to_dev(img[0]), self._to_dev(img[1])
+        return gp
+
+    def emission_gmm(self, feat, gp: GmmPack, precision: Optional[str] = None, out=None):
+        """[F, S] state log-likelihoods of a diagonal GMM.  precision "auto" / None: the tcgen05 kernel when the model has
+        a tensor-core image, else float32 SIMT; "tc", "fp32", "fp64" force a path."""
+        torch = self.torch
+        precision = precision or "auto"
+        if precision == "auto":
+            precision = "tc" if gp.b_img is not None else "fp32"
+        n_frames, dim = int(feat.shape[0]), int(feat.shape[1])
+        if dim != 39:
+            raise AssertionError(f"feature dimension {dim} != model dimension 39")
+        if out is None:
+            out = self.empty((n_frames, gp.n_states), torch.float32)
+        ld = int(out.shape[1])
+        if precision == "tc":
+            if gp.b_img is None:
+                raise NotImplementedError("this mixture model has no tensor-core image (entries outside the binary16 pair's range)")
+            _native.check(self.lib.loe_emission_gmm_tc_dev(feat.data_ptr(), n_frames, dim, gp.b_img.data_ptr(), gp.shift_scale.data_ptr(),
+                                                           gp.mean32.data_ptr(), gp.iv32.data_ptr(), gp.cst32.data_ptr(), gp.n_states,
+                                                           gp.n_mix, out.data_ptr(), ld, self._stream()))
+        elif precision in ("fp32", "fp64"):
+            mean, iv, cst = (gp.mean64, gp.iv64, gp.cst64) if precision == "fp64" else (gp.mean32, gp.iv32, gp.cst32)
+            _native.check(self.lib.loe_emission_gmm_dev(feat.data_ptr(), n_frames, dim, mean.data_ptr(), iv.data_ptr(), cst.data_ptr(),
+                                                        gp.n_states, gp.n_mix, out.data_ptr(), ld, 1 if precision == "fp64" else 0,
+                                                        self._stream()))
+        else:
+            raise ValueError(f"unknown precision {precision!r}")
         self.launches += 1
         return out
 

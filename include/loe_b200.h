@@ -183,6 +183,36 @@ int loe_emission_h16_dev(const float* feat_dev, int64_t n_frames, int dim, const
                          const float* cst_pad_dev, int n_states, float* out_dev, int ld_out, void* stream);
 
 /* --------------------------------------------------------------------------------------
+ * Diagonal-covariance Gaussian-mixture emission scoring (csrc/emission_gmm.cu; BASELINE.json north_star kernel (2),
+ * configs[0] extension set and configs[4]).  The live reference scores one full-covariance Gaussian per state
+ * (hidden_markov_model.py:20-48); the semantics of the mixture follow its abandoned deprecated/gaussian_mixture_model.py:157-162:
+ *     out[f*ld_out + s] = log sum_m exp( cst[s,m] - 0.5 * sum_k (x_fk - mean[s,m,k])^2 * inv_var[s,m,k] )
+ *     cst[s,m] = log w[s,m] - 0.5 * (D log 2pi + sum_k log var[s,m,k])
+ * No live reference call site: parity is against the restated oracle (oracle/gmm.py) only.
+ *
+ * loe_emission_gmm_dev: SIMT.  mean_dev / inv_var_dev [n_states*n_mix*dim], cst_dev [n_states*n_mix]; precision 0 =
+ *   float32 arrays, 1 = float64 arrays (the exact mode).  dim == 39, n_mix <= 16.
+ * loe_emission_gmm_tc_dev: the same result as ONE dense contraction on the tcgen05 tensor cores,
+ *     y[f, n] = [z^2 (39), 1, z (39), 0] . B[:, n],  z = (x - shift) * iscale,  n = state_local * MP + mixture
+ *   (MP = n_mix padded to a power of two; a column tile holds 240 / MP states), 3 x binary16 split operands with fp32
+ *   accumulation in TMEM, log-sum-exp over the mixtures in the epilogue thread of the frame.
+ *   b_packed_dev: per tile loe_emission_gmm_tile_bytes() (= 76800) bytes of binary16, [chunk c (20)][n (240)][q (8)]:
+ *     chunks 0-9 = fp16(B[8c + q][n]), chunks 10-19 = fp16(B - fp16(B)) of rows 8(c-10) + q;
+ *     B[k < 39] = -t_k^2 / (2 var_k), B[39] = cst - 0.5 sum (mean - shift)^2 / var, B[40 + k] = t_k (mean_k - shift_k) / var_k,
+ *     B[79] = 0; unused columns zero.
+ *   shift_scale_dev [tiles * 80] float32: per tile shift[40] then iscale[40] = 1 / t (t_k powers of two).
+ *   mean32_dev / inv_var32_dev / cst32_dev: the float32 arrays of loe_emission_gmm_dev -- frame rows with |z| >= 128 or
+ *     non-finite values are evaluated from them by plain float32 arithmetic inside the same kernel.
+ * -------------------------------------------------------------------------------------- */
+int loe_emission_gmm_tile_bytes(void);
+int loe_emission_gmm_tiles(int n_states, int n_mix);
+int loe_emission_gmm_dev(const float* feat_dev, int64_t n_frames, int dim, const void* mean_dev, const void* inv_var_dev,
+                         const void* cst_dev, int n_states, int n_mix, float* out_dev, int ld_out, int precision, void* stream);
+int loe_emission_gmm_tc_dev(const float* feat_dev, int64_t n_frames, int dim, const void* b_packed_dev,
+                            const float* shift_scale_dev, const float* mean32_dev, const float* inv_var32_dev,
+                            const float* cst32_dev, int n_states, int n_mix, float* out_dev, int ld_out, void* stream);
+
+/* --------------------------------------------------------------------------------------
  * Viterbi + backtrace, one CTA per utterance.  Replaces HiddenMarkovModel._viterbi /
  * _viterbi_static (hidden_markov_model.py:80-91, 160-208), HiddenMarkovModelInference.
  * _viterbi / _viterbi_static (:463-581) and the forced alignment of

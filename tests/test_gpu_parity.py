@@ -128,9 +128,10 @@ def test_parameterised_mfcc_matches_oracle(eng):
                MFCCConfig(n_fft=256, win_length=256, hop_length=128), MFCCConfig(n_fft=1024, win_length=800, hop_length=320, window="hamming"),
                MFCCConfig(n_fft=512, win_length=512, hop_length=160), MFCCConfig(n_fft=64, win_length=64, hop_length=32, n_mels=20, fmax=7000.0)]
     for cfg in configs:
-        got = MFCC.batch([s.astype(np.float32) for s in sigs], 16000, config=cfg)
-        got16 = MFCC.batch(sigs, 16000, config=cfg)
-        for s, g, g16 in zip(sigs, got, got16):
+        use = [s for s in sigs if 1 + len(s) // cfg.hop_length >= 9]
+        got = MFCC.batch([s.astype(np.float32) for s in use], 16000, config=cfg)
+        got16 = MFCC.batch(use, 16000, config=cfg)
+        for s, g, g16 in zip(use, got, got16):
             ref = OM.mfcc_feature_vector_ex(s.astype(np.float32), 16000, asdict(cfg)).T
             assert g.shape == ref.shape and g.dtype == np.float32, (cfg, g.shape, ref.shape)
             atol = 1e-4 * max(np.abs(ref[:, :13]).max(), 1.0)
