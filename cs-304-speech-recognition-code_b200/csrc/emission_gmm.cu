@@ -94,6 +94,7 @@ __device__ __forceinline__ float score_state(const T* x, const T* __restrict__ m
                                              const T* __restrict__ cst, int s, int n_mix) {
     T best = -CUDART_INF;
     T vals[16];
+    bool nan_seen = false;
     for (int m = 0; m < n_mix; ++m) {
         const T* mu = mean + (size_t)(s * n_mix + m) * kDim;
         const T* iv = inv_var + (size_t)(s * n_mix + m) * kDim;
@@ -101,9 +102,11 @@ __device__ __forceinline__ float score_state(const T* x, const T* __restrict__ m
 #pragma unroll
         for (int k = 0; k < kDim; ++k) { const T d = x[k] - mu[k]; q = fma(d * d, iv[k], q); }
         vals[m] = cst[s * n_mix + m] - (T)0.5 * q;
+        nan_seen |= vals[m] != vals[m];
         best = vals[m] > best ? vals[m] : best;
     }
-    if (!(best > -CUDART_INF)) return (float)best;              // all components -inf (or NaN): no exp of inf - inf
+    if (nan_seen) return CUDART_NAN_F;                          // NaN in, NaN out (like the oracle's logsumexp)
+    if (!(best > -CUDART_INF)) return (float)best;              // all components -inf: no exp of inf - inf
     T sum = 0;
     for (int m = 0; m < n_mix; ++m) sum += exp(vals[m] - best);
     return (float)(best + log(sum));

@@ -254,6 +254,18 @@ class Engine:
                                                    n_states, out.data_ptr() + col0 * 4, ld, self._stream()))
         self.launches += 1
 
+    def emission_h16_into(self, feat, b_h16, cst_pad, first_tile: int, n_states: int, out, col0: int):
+        """3xFP16 tensor-core emission of one word (image tiles from ``first_tile``) into columns [col0, col0+n_states) of ``out``."""
+        n_frames = int(feat.shape[0])
+        if n_frames == 0:
+            return
+        ld = int(out.shape[1])
+        tile_bytes = int(self.lib.loe_emission_h16_tile_bytes())
+        _native.check(self.lib.loe_emission_h16_dev(feat.data_ptr(), n_frames, int(feat.shape[1]),
+                                                    b_h16.data_ptr() + first_tile * tile_bytes, cst_pad.data_ptr() + first_tile * 6 * 4,
+                                                    n_states, out.data_ptr() + col0 * 4, ld, self._stream()))
+        self.launches += 1
+
     def pack_trellises(self, trellises: List[HostTrellis]) -> TrellisPack:
         off, col, band, flags, word, word_lo, max_pos, max_ends = stack(trellises)
         if max_pos > _native.LOE_MAX_POS:

@@ -20,6 +20,7 @@ LOE_MAX_POS = 128
 LOE_MEL_NA_MAX = 32
 LOE_MEL_NB_MAX = 16
 POS_INIT, POS_START, POS_END = 1, 2, 4
+LOE_MSTEP_UPDATED, LOE_MSTEP_CONVERGED, LOE_MSTEP_MEAN_FAIL, LOE_MSTEP_SUSPECT = 1, 2, 4, 8
 
 # every symbol include/loe_b200.h declares: name -> (restype, argtypes)
 SIGNATURES = {
@@ -59,6 +60,8 @@ SIGNATURES = {
                               c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "loe_kmeans_ws_doubles": (c_int64, [c_int64, c_int, c_int]),
     "loe_kmeans_dev": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "loe_mstep_dev": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "loe_decoder_create": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int,
                                    c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "loe_decoder_decode_host": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_double, c_int, c_int, c_int, c_int,

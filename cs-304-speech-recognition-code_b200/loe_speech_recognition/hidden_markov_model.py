@@ -289,14 +289,193 @@ class HiddenMarkovModelTrainable(HiddenMarkovModel):
 
     @classmethod
     def from_data_batch(cls, labeled_mfccs: Dict[str, List[NDArray[np.float32]]], num_of_states=5,
-                        max_iterations: int = 100) -> Dict[str, Self]:
+                        max_iterations: int = 100, device_mstep: Optional[bool] = None, return_info: bool = False):
         """Train several word models at once (added entry point).  The result equals calling
         :meth:`from_data` once per label (each word keeps its own convergence test and stops on its own),
-        but every iteration is ONE device pass over all words: per-word tensor-core emission launches into
-        one score matrix, one Viterbi launch with a trellis per word, one statistics pass for all states
-        and -- under torch.distributed -- one all-reduce; the Gaussians' whitening matrices are refreshed
-        with a batched float64 eigendecomposition instead of one scipy object per state, and the scipy
-        objects of the persistent format are built once at the end."""
+        but every iteration is ONE device pass over all words and nothing but a status word per model
+        leaves the device: per-word 3xFP16 tensor-core emission launches into one score matrix, one
+        Viterbi launch with a trellis per word, one statistics pass for all states, -- under
+        torch.distributed -- one all-reduce, and the M-step itself (``loe_mstep_dev``: means, the
+        reference's means-only convergence test, covariances, transition probabilities, and the
+        whitening data written straight into the tensor-core image).  The scipy objects of the
+        persistent format are built once at the end from the float32 parameters, which are bit-identical
+        to the host M-step's.  ``device_mstep=False`` (or LOE_B200_HOST_MSTEP=1) keeps the round-1 host M-step."""
+        if device_mstep is None:
+            device_mstep = not os.environ.get("LOE_B200_HOST_MSTEP")
+        D = int(next(iter(labeled_mfccs.values()))[0].shape[1])
+        if device_mstep and D == 39:
+            return cls._from_data_batch_device(labeled_mfccs, num_of_states, max_iterations, return_info)
+        models = cls._from_data_batch_host(labeled_mfccs, num_of_states, max_iterations)
+        return (models, {"iterations": None, "mstep": "host"}) if return_info else models
+
+    @classmethod
+    def _from_data_batch_device(cls, labeled_mfccs, num_of_states, max_iterations: int, return_info: bool):
+        from . import _dist, _native
+        from ._engine import pack_h16_image
+
+        eng = _engine()
+        torch = eng.torch
+        labels = list(labeled_mfccs)
+        n_st = {l: int(num_of_states[l] if isinstance(num_of_states, dict) else num_of_states) for l in labels}
+        W, D = len(labels), 39
+        sizes = np.array([n_st[l] for l in labels], dtype=np.int32)
+        first = np.concatenate(([0], np.cumsum(sizes)[:-1])).astype(np.int32)
+        G = int(sizes.sum())
+        tiles = (sizes + 5) // 6
+        tile0 = np.concatenate(([0], np.cumsum(tiles)[:-1])).astype(np.int32)
+        n_tiles = int(tiles.sum())
+        tile_halves = eng.lib.loe_emission_h16_tile_bytes() // 2
+
+        # initial parameters exactly as from_data: uniform segmentation of each word's FIRST utterance (:359-389)
+        means0 = np.zeros((G, D), np.float32)
+        cov0 = np.zeros((G, D, D), np.float32)
+        band0 = np.full((G, 3), -np.inf, np.float32)
+        trans0 = {}
+        for i, l in enumerate(labels):
+            m, c, t = cls._init_parameters(labeled_mfccs[l][0], n_st[l])
+            means0[first[i]:first[i] + sizes[i]] = m
+            cov0[first[i]:first[i] + sizes[i]] = c
+            trans0[l] = t
+            with np.errstate(divide="ignore", invalid="ignore"):
+                band0[first[i]:first[i] + sizes[i]] = _trellis.build([np.log(t.to_dense())], [0], [0], "word").band
+
+        # this rank's utterances, word by word (the frames of a word are contiguous on the device)
+        shards = {l: _dist.shard(list(labeled_mfccs[l])) for l in labels}
+        feats = [x for l in labels for x in shards[l]]
+        utt_word = np.array([i for i, l in enumerate(labels) for _ in shards[l]], dtype=np.int32)
+        batch = eng.upload_features(feats, D) if feats else None
+        utt_tr = eng._to_dev(utt_word) if feats else None
+        frame_range = {}
+        if feats:
+            cnt = np.cumsum([0] + [len(shards[l]) for l in labels])
+            for i, l in enumerate(labels):
+                frame_range[l] = (int(batch.frm_off_host[cnt[i]]), int(batch.frm_off_host[cnt[i + 1]]))
+            scores = eng.empty((batch.total_frames, G), torch.float32)
+        stride = 1 + D + D * (D + 1) // 2
+
+        # device-resident model: float32 means / covariances, trellis bands, 3xFP16 image, active set
+        def host_image(idx):
+            """3xFP16 image tiles + constants of word ``idx`` from its float32 covariances, scipy's way (eigh + _PSD checks)."""
+            a, n = int(first[idx]), int(sizes[idx])
+            cov = cov_h[a:a + n].astype(np.float64)
+            if not np.all(np.isfinite(cov)):
+                raise ValueError("array must not contain infs or NaNs")
+            lam, vec = np.linalg.eigh(cov)
+            eps = 1e6 * np.finfo(np.float64).eps * np.max(np.abs(lam), axis=1)
+            if np.any(lam.min(axis=1) < -eps):
+                raise ValueError("The input matrix must be symmetric positive semidefinite.")
+            if np.any(lam <= eps[:, None]):
+                raise np.linalg.LinAlgError("When `allow_singular is False`, the input matrix must be symmetric positive definite.")
+            U = vec * np.sqrt(1.0 / lam)[:, None, :]
+            cst = -0.5 * (D * np.log(2 * np.pi) + np.sum(np.log(lam), axis=1))
+            img = pack_h16_image(means_h[a:a + n].astype(np.float64), U, cst)
+            if img is None:
+                raise NotImplementedError("whitening matrix outside the binary16 range: train this model with from_data(…) under "
+                                          "LOE_B200_EMISSION=tc / LOE_B200_HOST_MSTEP=1")
+            cp = np.zeros(int(tiles[idx]) * 6, np.float32)
+            cp[:n] = cst.astype(np.float32)
+            return img, cp
+
+        means_h, cov_h = means0, cov0
+        img0 = np.zeros(n_tiles * tile_halves, np.float16)
+        cst0 = np.zeros(n_tiles * 6, np.float32)
+        for i in range(W):
+            im, cp = host_image(i)
+            img0[tile0[i] * tile_halves:(tile0[i] + tiles[i]) * tile_halves] = im
+            cst0[tile0[i] * 6:(tile0[i] + tiles[i]) * 6] = cp
+        means_d, cov_d, b_h16, cst_pad = eng._to_dev(means0), eng._to_dev(cov0), eng._to_dev(img0), eng._to_dev(cst0)
+        trellises = [_trellis.build([np.zeros((int(n), int(n)), np.float32)], [int(a)], [i], "word") for i, (a, n) in enumerate(zip(first, sizes))]
+        tp = eng.pack_trellises(trellises)
+        tp.band.copy_(eng._to_dev(band0))
+        state_word = eng._to_dev(np.repeat(np.arange(W, dtype=np.int32), sizes))
+        word_first, word_n, word_tile = eng._to_dev(first), eng._to_dev(sizes), eng._to_dev(tile0)
+        active = torch.ones(W, dtype=torch.int32, device=eng.device)
+        updated = torch.zeros(W, dtype=torch.int32, device=eng.device)
+        status = torch.zeros(W, dtype=torch.int32, device=eng.device)
+        counts_applied = torch.zeros((G, G), dtype=torch.int32, device=eng.device)
+        applied_any = torch.zeros(W, dtype=torch.int32, device=eng.device)
+        status_host = [torch.empty(W, dtype=torch.int32).pin_memory() for _ in range(2)]
+        events = [None, None]
+        maybe_active = np.ones(W, dtype=bool)          # host view of the active set, one iteration behind the device
+        iterations = 0
+        stream = torch.cuda.current_stream(eng.device)
+
+        def digest(slot):
+            """Host reaction to the status words of an iteration (read one iteration late: the device froze converged
+            words itself, the E-step of a word that was already done is wasted work, never a different result)."""
+            events[slot].synchronize()
+            st = status_host[slot].numpy()
+            if np.any(st & _native.LOE_MSTEP_MEAN_FAIL):
+                raise cls.HMMTrainMeanFail
+            bad = np.nonzero(st & _native.LOE_MSTEP_SUSPECT)[0]
+            if bad.size:
+                nonlocal means_h, cov_h
+                means_h, cov_h = means_d.cpu().numpy(), cov_d.cpu().numpy()
+                for i in bad.tolist():                 # scipy's own verdict: raises what the reference raises, or repairs the image
+                    im, cp = host_image(i)             # (the device parked the word: its parameters are those of the flagged update)
+                    b_h16[int(tile0[i]) * tile_halves:int(tile0[i] + tiles[i]) * tile_halves].copy_(eng._to_dev(im))
+                    cst_pad[int(tile0[i]) * 6:int(tile0[i] + tiles[i]) * 6].copy_(eng._to_dev(cp))
+                    active[i] = 1
+            maybe_active[(st & (_native.LOE_MSTEP_CONVERGED)) != 0] = False
+
+        for it in range(max_iterations):
+            if not maybe_active.any():
+                break
+            iterations += 1
+            if feats:
+                for i, l in enumerate(labels):
+                    if maybe_active[i]:
+                        a, b = frame_range[l]
+                        eng.emission_h16_into(batch.feat[a:b], b_h16, cst_pad, int(tile0[i]), int(sizes[i]), scores[a:b], int(first[i]))
+                path, _, _, _ = eng.viterbi(scores, batch.frm_off, batch.n_utt, batch.max_frames, batch.total_frames, tp,
+                                            utt_tr=utt_tr, want_end_scores=False)
+                stats, counts, _ = eng.kmeans_stats(batch.feat, path, batch.frm_off, batch.n_utt, batch.total_frames, tp,
+                                                    utt_tr, False, G, means_d)
+            else:
+                stats = torch.zeros((G, stride), dtype=torch.float64, device=eng.device)
+                counts = torch.zeros((G, G), dtype=torch.int32, device=eng.device)
+            stats, counts = _dist.allreduce_stats(stats, counts)
+            _native.check(eng.lib.loe_mstep_dev(stats.data_ptr(), counts.data_ptr(), G, W, state_word.data_ptr(), word_first.data_ptr(),
+                                                word_n.data_ptr(), word_tile.data_ptr(), means_d.data_ptr(), cov_d.data_ptr(),
+                                                counts_applied.data_ptr(), tp.band.data_ptr(), b_h16.data_ptr(), cst_pad.data_ptr(),
+                                                active.data_ptr(), updated.data_ptr(), status.data_ptr(), D, eng._stream()))
+            eng.launches += 2
+            applied_any += updated
+            slot = it & 1
+            status_host[slot].copy_(status, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            events[slot] = ev
+            if it >= 1:
+                digest((it - 1) & 1)
+        if iterations:
+            digest((iterations - 1) & 1)
+
+        # persistent form: float32 parameters back to the host once, scipy objects built like _update_inference_weights
+        means_h, cov_h = means_d.cpu().numpy(), cov_d.cpu().numpy()
+        counts_h, applied_h = counts_applied.cpu().numpy().astype(np.int64), applied_any.cpu().numpy()
+        models = {}
+        for i, l in enumerate(labels):
+            a, n = int(first[i]), int(sizes[i])
+            m = cls(l, isTqdm=False)
+            m._means, m._covariances = means_h[a:a + n].copy(), cov_h[a:a + n].copy()
+            if applied_h[i]:
+                c = counts_h[a:a + n, a:a + n]
+                with np.errstate(all="ignore"):
+                    probs = (c / np.sum(c, axis=1, keepdims=True)).astype(np.float32)
+                m._transition_probs = TransitionProbabilities.from_transition_probability(probs)
+            else:
+                m._transition_probs = trans0[l]
+            m._update_inference_weights()
+            models[l] = m
+        info = {"iterations": iterations, "mstep": "device", "n_states": G, "frames_this_rank": int(batch.total_frames) if feats else 0}
+        return (models, info) if return_info else models
+
+    @classmethod
+    def _from_data_batch_host(cls, labeled_mfccs: Dict[str, List[NDArray[np.float32]]], num_of_states=5,
+                              max_iterations: int = 100) -> Dict[str, Self]:
+        """Round-1 form of :meth:`from_data_batch`: device E-step, host M-step (batched float64 eigendecomposition, image
+        packing and upload every iteration).  Kept as the cross-check of the device M-step and for dimensions other than 39."""
         from . import _dist
         from ._engine import Batch
 

@@ -331,6 +331,36 @@ int loe_kmeans_dev(const float* feat_dev, const uint16_t* bucket_dev, int64_t to
                    int n_glob, const float* shift_dev, double* part_ws_dev, double* stats_dev, void* stream);
 
 /* --------------------------------------------------------------------------------------
+ * Segmental K-means M-step on the device (csrc/mstep.cu).  Replaces, for every word model of a batched training run,
+ * HiddenMarkovModelTrainable._update_middleware_parameters (hidden_markov_model.py:320-350: means, the means-only
+ * convergence test np.allclose(new, old) BEFORE covariances / transitions are touched, np.cov (N-1) + 1e-3 I, transition
+ * counts / row sum) and _update_inference_weights (:283-292: log-transitions, the Gaussians' whitening data), from the
+ * statistics of loe_kmeans_dev (shifted by the current means) and the counts of loe_align_dev.  Word w owns the global
+ * states [word_first[w], word_first[w] + word_n[w]) and the 6-state image tiles from word_tile[w].
+ *   means32_dev [n_glob*39] in/out (float32 model means: shift of the statistics on entry, new means where updated)
+ *   cov32_dev [n_glob*39*39], counts_applied_dev [n_glob*n_glob]: written for updated words only (a converged word keeps
+ *       the previous values, like the reference)
+ *   band_dev [n_glob*3]: log-transition into state g from g, g-1, g-2 (the per-word trellises of loe_viterbi_dev)
+ *   b_h16_dev / cst_pad_dev: the 3xFP16 image of loe_emission_h16_dev, rewritten in place for updated words
+ *   active_dev [n_words] in/out: 1 = training, 0 = converged (frozen), -1 = failed (empty state), -2 = parked (suspect
+ *       covariance: no image was written; the caller repairs the image and sets the word back to 1)
+ *   updated_dev [n_words] scratch;  status_dev [n_words] out: LOE_MSTEP_* bits of THIS call
+ * The float32 means / covariances / transition probabilities equal the host M-step's bit for bit given the same
+ * statistics; the whitening matrix is the inverse Cholesky factor of the (reversed) covariance instead of scipy's
+ * eigenvector form (same quadratic form).  LOE_MSTEP_SUSPECT: the covariance is not finite, fails a pivot test or its
+ * whitening matrix leaves the binary16 range -- the caller then applies scipy's own test on the host.
+ * -------------------------------------------------------------------------------------- */
+#define LOE_MSTEP_UPDATED 1
+#define LOE_MSTEP_CONVERGED 2
+#define LOE_MSTEP_MEAN_FAIL 4
+#define LOE_MSTEP_SUSPECT 8
+int loe_mstep_dev(const double* stats_dev, const int32_t* counts_dev, int n_glob, int n_words,
+                  const int32_t* state_word_dev, const int32_t* word_first_dev, const int32_t* word_n_dev,
+                  const int32_t* word_tile_dev, float* means32_dev, float* cov32_dev, int32_t* counts_applied_dev,
+                  float* band_dev, void* b_h16_dev, float* cst_pad_dev, int32_t* active_dev, int32_t* updated_dev,
+                  int32_t* status_dev, int dim, void* stream);
+
+/* --------------------------------------------------------------------------------------
  * Host-buffer decoder: the whole hot path behind ONE call that takes HOST memory and needs no
  * torch / Python on the caller's side.  Replaces, for a batch of utterances,
  *     [HiddenMarkovModelInference.predict(MFCC(sig, sr).feature_vector) for sig in signals]

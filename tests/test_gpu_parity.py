@@ -780,6 +780,108 @@ def test_batched_training_equals_per_word_training(eng, golden):
         HiddenMarkovModelTrainable.from_data("1", [flat], num_of_states=3, max_iterations=3, isTqdm=False)
 
 
+def test_device_mstep_equals_host_mstep(eng, golden):
+    """loe_mstep_dev against the host M-step (hidden_markov_model.py:320-350 restated in _update_from_statistics) on the
+    statistics of a real E-step: float32 means / covariances / transition probabilities bit-identical, convergence flags
+    equal, and the whitening data it writes into the 3xFP16 image scores like scipy's (same quadratic form)."""
+    from loe_speech_recognition import HiddenMarkovModelTrainable
+    labeled = {w: [golden[f"train_feat_{w}_{i}"] for i in range(64) if f"train_feat_{w}_{i}" in golden.files] for w in WORDS}
+    dev, info = HiddenMarkovModelTrainable.from_data_batch(labeled, num_of_states=dict(N_STATES), max_iterations=4, return_info=True)
+    host = HiddenMarkovModelTrainable.from_data_batch(labeled, num_of_states=dict(N_STATES), max_iterations=4, device_mstep=False)
+    assert info["mstep"] == "device" and 1 <= info["iterations"] <= 4
+    for w in WORDS:
+        assert np.array_equal(dev[w]._means, host[w]._means), w
+        assert np.array_equal(dev[w]._covariances, host[w]._covariances), w
+        a, b = dev[w]._log_transition_probs.to_dense(), host[w]._log_transition_probs.to_dense()
+        assert np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(a[~np.isnan(a)], b[~np.isnan(b)]), w
+        assert rel_close(dev[w]._means, golden[f"train_means_{w}"], rtol=1e-4, atol=1e-5), w
+        assert rel_close(dev[w]._covariances, golden[f"train_covs_{w}"], rtol=1e-3, atol=1e-5), w
+    # run to convergence: both stop on the same iteration for every word (the means-only test runs on the device)
+    dev2, info2 = HiddenMarkovModelTrainable.from_data_batch(labeled, num_of_states=dict(N_STATES), max_iterations=40, return_info=True)
+    host2 = HiddenMarkovModelTrainable.from_data_batch(labeled, num_of_states=dict(N_STATES), max_iterations=40, device_mstep=False)
+    assert info2["iterations"] < 40
+    for w in WORDS:
+        assert np.array_equal(dev2[w]._means, host2[w]._means) and np.array_equal(dev2[w]._covariances, host2[w]._covariances), w
+    with pytest.raises(HiddenMarkovModelTrainable.HMMTrainMeanFail):
+        flat = np.tile(golden["train_feat_1_0"][:1], (12, 1))
+        HiddenMarkovModelTrainable.from_data_batch({"1": [flat]}, num_of_states=3, max_iterations=3)
+
+
+def test_device_mstep_kernel_against_numpy(eng):
+    """The M-step kernels alone on synthetic statistics: exact float32 parameters, NaN rows for states that never leave,
+    converged words untouched, an empty state reported, a non-finite covariance parked as suspect, and the image a word
+    gets scores frames like the float64 kernel on the same (mean, covariance)."""
+    import ctypes
+    from loe_speech_recognition import _native, _trellis
+    from loe_speech_recognition.hidden_markov_model import HiddenMarkovModelTrainable as T, MultivariateNormal
+    torch = eng.torch
+    rng = np.random.default_rng(12)
+    D, sizes = 39, np.array([5, 3, 5, 5], np.int32)
+    W, G = len(sizes), int(sizes.sum())
+    first = np.concatenate(([0], np.cumsum(sizes)[:-1])).astype(np.int32)
+    tile0 = np.arange(W, dtype=np.int32)
+    stride = 1 + D + D * (D + 1) // 2
+    iu = np.triu_indices(D)
+    old = rng.normal(0, 2, size=(G, D)).astype(np.float32)
+    stats = np.zeros((G, stride)); counts = np.zeros((G, G), np.int32)
+    for g in range(G):
+        n = int(rng.integers(60, 400))
+        x = rng.normal(0, 1.5, size=(n, D)) @ np.diag(rng.uniform(0.3, 2.0, D)) + rng.normal(0, 0.1, D)
+        stats[g, 0] = n; stats[g, 1:1 + D] = x.sum(0); stats[g, 1 + D:] = (x.T @ x)[iu]
+    for i, (a, n) in enumerate(zip(first, sizes)):
+        for s in range(n):
+            counts[a + s, a + s] = rng.integers(5, 50)
+            if s + 1 < n:
+                counts[a + s, a + s + 1] = rng.integers(1, 20)
+    stats[first[2]:first[2] + 5, 1:1 + D] *= 1e-7                 # word 2: means move by less than the allclose bar -> converged
+    stats[first[3] + 1, 0] = 0.0                                   # word 3: an empty state -> mean fail
+    means_d = eng._to_dev(old.copy()); cov_d = torch.full((G, D, D), 7.0, dtype=torch.float32, device=eng.device)
+    tile_halves = eng.lib.loe_emission_h16_tile_bytes() // 2
+    b_h16 = torch.zeros(W * tile_halves, dtype=torch.float16, device=eng.device); cst_pad = torch.zeros(W * 6, dtype=torch.float32, device=eng.device)
+    band = torch.full((G, 3), 9.0, dtype=torch.float32, device=eng.device)
+    active = torch.ones(W, dtype=torch.int32, device=eng.device); updated = torch.zeros_like(active); status = torch.zeros_like(active)
+    applied = torch.zeros((G, G), dtype=torch.int32, device=eng.device)
+    tabs = [eng._to_dev(np.repeat(np.arange(W, dtype=np.int32), sizes)), eng._to_dev(first), eng._to_dev(sizes), eng._to_dev(tile0)]
+    sd, cd = eng._to_dev(stats), eng._to_dev(counts)
+    _native.check(eng.lib.loe_mstep_dev(sd.data_ptr(), cd.data_ptr(), G, W, *[t.data_ptr() for t in tabs], means_d.data_ptr(), cov_d.data_ptr(),
+                                        applied.data_ptr(), band.data_ptr(), b_h16.data_ptr(), cst_pad.data_ptr(), active.data_ptr(),
+                                        updated.data_ptr(), status.data_ptr(), D, eng._stream()))
+    st = status.cpu().numpy(); act = active.cpu().numpy()
+    assert st.tolist() == [_native.LOE_MSTEP_UPDATED, _native.LOE_MSTEP_UPDATED, _native.LOE_MSTEP_CONVERGED, _native.LOE_MSTEP_MEAN_FAIL]
+    assert act.tolist() == [1, 1, 0, -1]
+    got_means, got_cov, got_band = means_d.cpu().numpy(), cov_d.cpu().numpy(), band.cpu().numpy()
+    for i in (0, 1):
+        a, n = int(first[i]), int(sizes[i])
+        m = T(str(i)); m._means = old[a:a + n].copy(); m._covariances = None
+        m._update_from_statistics(stats[a:a + n], counts[a:a + n, a:a + n].astype(np.int64), shift=old[a:a + n].astype(np.float64))
+        assert np.array_equal(got_means[a:a + n], m._means) and np.array_equal(got_cov[a:a + n], m._covariances), i
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ref_band = _trellis.build([np.log(m._transition_probs.to_dense())], [0], [0], "word").band
+        assert np.array_equal(np.isnan(got_band[a:a + n]), np.isnan(ref_band))
+        ok = ~np.isnan(ref_band)
+        assert np.allclose(got_band[a:a + n][ok], ref_band[ok], rtol=2e-7, atol=0) or np.array_equal(got_band[a:a + n][ok], ref_band[ok])
+        assert np.array_equal(applied.cpu().numpy()[a:a + n], counts[a:a + n])
+        # the image scores like scipy on the same parameters
+        normals = [MultivariateNormal.from_means_covariances(mm, cc) for mm, cc in zip(m._means, m._covariances)]
+        gp = eng.pack_gaussians(normals)
+        x = eng._to_dev((m._means[rng.integers(0, n, 300)] + rng.normal(0, 1.5, size=(300, D))).astype(np.float32))
+        ref = eng.emission(x, gp, "fp64").cpu().numpy()
+        out = torch.empty((300, n), dtype=torch.float32, device=eng.device)
+        eng.emission_h16_into(x, b_h16, cst_pad, int(tile0[i]), n, out, 0)
+        lps = [mn._core.cov_object._log_pdet for mn in normals]
+        assert emission_close(out.cpu().numpy(), ref, lps), (i, np.abs(out.cpu().numpy() - ref).max())
+    for i in (2, 3):                                               # converged / failed words keep everything
+        a, n = int(first[i]), int(sizes[i])
+        assert np.array_equal(got_means[a:a + n], old[a:a + n]) and np.all(got_cov[a:a + n] == 7.0) and np.all(got_band[a:a + n] == 9.0)
+    # a non-finite covariance (one frame: N - 1 = 0) is parked for the host
+    stats2 = stats.copy(); stats2[first[0] + 2, 0] = 1.0
+    active.fill_(1); active[3] = 0
+    _native.check(eng.lib.loe_mstep_dev(eng._to_dev(stats2).data_ptr(), cd.data_ptr(), G, W, *[t.data_ptr() for t in tabs], means_d.data_ptr(),
+                                        cov_d.data_ptr(), applied.data_ptr(), band.data_ptr(), b_h16.data_ptr(), cst_pad.data_ptr(),
+                                        active.data_ptr(), updated.data_ptr(), status.data_ptr(), D, eng._stream()))
+    assert status.cpu().numpy()[0] & _native.LOE_MSTEP_SUSPECT and active.cpu().numpy()[0] == -2
+
+
 @pytest.mark.gpu
 def test_host_buffer_decoder_matches_flat_decode(eng, golden):
     """loe_decoder_decode_host (C pipeline, host buffers, no torch on the way) == decode_pcm_flat,

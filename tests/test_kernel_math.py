@@ -162,3 +162,23 @@ def test_parameterised_fft_index_arithmetic():
         ref = np.abs(np.fft.rfft(x)) ** 2
         got = _stockham_real_power(x, N)
         assert np.allclose(got, ref, rtol=1e-10, atol=1e-10), N
+
+
+def test_reversed_cholesky_gives_the_lower_triangular_whitening_matrix():
+    """csrc/mstep.cu: M = chol(J cov J) (J = exchange matrix), W[k][j] = M^-1[38 - j][38 - k].  W must be LOWER triangular
+    (what the 3xFP16 emission image needs) with W W^T = cov^-1, and log|cov| = 2 sum log diag(M)."""
+    rng = np.random.default_rng(1)
+    D = 39
+    q, _ = np.linalg.qr(rng.normal(size=(D, D)))
+    cov = (q * np.logspace(-3, 2, D)) @ q.T
+    cov = (cov + cov.T) / 2
+    J = np.eye(D)[::-1]
+    M = np.linalg.cholesky(J @ cov @ J)
+    Minv = np.linalg.inv(M)
+    W = np.array([[Minv[D - 1 - j, D - 1 - k] for j in range(D)] for k in range(D)])
+    assert np.allclose(np.triu(W, 1), 0.0)
+    assert np.allclose(W @ W.T, np.linalg.inv(cov), rtol=1e-8, atol=1e-8 * np.abs(np.linalg.inv(cov)).max())
+    assert np.isclose(2 * np.log(np.diag(M)).sum(), np.linalg.slogdet(cov)[1])
+    x = rng.normal(size=(5, D)); mu = rng.normal(size=D)
+    ref = np.einsum("ti,ij,tj->t", x - mu, np.linalg.inv(cov), x - mu)
+    assert np.allclose(np.sum(((x - mu) @ W) ** 2, axis=1), ref, rtol=1e-9)
