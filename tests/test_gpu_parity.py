@@ -833,7 +833,7 @@ def test_device_mstep_kernel_against_numpy(eng):
             counts[a + s, a + s] = rng.integers(5, 50)
             if s + 1 < n:
                 counts[a + s, a + s + 1] = rng.integers(1, 20)
-    stats[first[2]:first[2] + 5, 1:1 + D] *= 1e-7                 # word 2: means move by less than the allclose bar -> converged
+    stats[first[2]:first[2] + 5, 1:1 + D] *= 1e-9                 # word 2: means move by less than the allclose bar -> converged
     stats[first[3] + 1, 0] = 0.0                                   # word 3: an empty state -> mean fail
     means_d = eng._to_dev(old.copy()); cov_d = torch.full((G, D, D), 7.0, dtype=torch.float32, device=eng.device)
     tile_halves = eng.lib.loe_emission_h16_tile_bytes() // 2
