@@ -18,6 +18,7 @@
 // reduce_kernel: sums the chunk partials in a fixed order => bitwise reproducible statistics.
 // Algorithmic HBM bytes: 4*D + 2 per frame (features once + bucket id; re-scans of the id array hit L2).
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace loe {
 
@@ -244,6 +245,221 @@ __global__ void reduce_kernel(const double* __restrict__ part, int n_chunks, int
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Sorted path (dim == 39, n_glob <= 1024): the default.
+//   1. counting sort of the frames by bucket, stable in frame order, per chunk of 2048 frames:
+//        bucket_hist_kernel -> bucket_scan_kernel (exclusive offsets per (bucket, chunk), bases, work list)
+//        -> bucket_scatter_kernel (frame index lists, one contiguous list per bucket)
+//   2. accum2_kernel: one CTA per work item = up to 2048 consecutive list entries of ONE bucket.  The augmented frames
+//      y = [x - shift, 1] are gathered through the list into shared memory (float64, 128 per batch) and sum y y^T is
+//      accumulated in 8 x 8 float64 register tiles: the 15 tiles on or above the diagonal of the 5 x 5 tile grid belong
+//      to 15 threads of a group of 16, 16 groups take the frames of a batch in turn.  8 + 8 shared-memory doubles feed
+//      64 FMAs (the 4 x 4 tiles of the scanning kernel: 4 + 4 for 16), which balances the shared-memory wavefronts with
+//      the FP64 pipe -- the pipe that bounds this kernel: 820 FMAs per frame.
+//   3. reduce2_kernel: partials of a bucket summed in work-list order.
+// Everything is in a fixed order: statistics are bitwise reproducible, and independent of how other buckets' frames are
+// interleaved with a bucket's own.
+// ------------------------------------------------------------------------------------------
+constexpr int kSortChunk = 2048;                 // frames per histogram / scatter CTA
+constexpr int kSortThreads = 256;
+constexpr int kSortMaxGlob = 1024;
+constexpr int kSplit = 2048;                     // list entries per work item
+constexpr int kA2Frames = 112;                   // frames per staged batch (44.8 KB of float64 rows: under the 48 KB static limit)
+constexpr int kA2Groups = 16;
+constexpr int kA2BlockPitch = 10;                // doubles per 8-wide block of a staged row (2 of padding: conflict-free 16-byte reads)
+constexpr int kA2RowPitch = 5 * kA2BlockPitch;   // 50 doubles
+
+__global__ void __launch_bounds__(kSortThreads)
+bucket_hist_kernel(const uint16_t* __restrict__ bucket, int64_t total_frames, int n_glob, int* __restrict__ chunk_hist) {
+    extern __shared__ int s_hist[];
+    const int c = blockIdx.x;
+    for (int i = threadIdx.x; i < n_glob; i += kSortThreads) s_hist[i] = 0;
+    __syncthreads();
+    const int64_t f_begin = (int64_t)c * kSortChunk, f_end = min(total_frames, f_begin + kSortChunk);
+    for (int64_t f = f_begin + threadIdx.x; f < f_end; f += kSortThreads) {
+        const int b = bucket[f];
+        if (b < n_glob) atomicAdd(&s_hist[b], 1);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_glob; i += kSortThreads) chunk_hist[(size_t)c * n_glob + i] = s_hist[i];
+}
+
+// one CTA: per-bucket exclusive offsets over the chunks (in place), bucket bases, and the work list
+__global__ void __launch_bounds__(1024)
+bucket_scan_kernel(int* __restrict__ chunk_hist, int n_chunks, int n_glob, int* __restrict__ base, int* __restrict__ work,
+                   int* __restrict__ work_range, int n_work_max) {
+    __shared__ int s_total[kSortMaxGlob];
+    const int g = threadIdx.x;
+    if (g < n_glob) {
+        int run = 0;
+        for (int c = 0; c < n_chunks; ++c) {
+            const int t = chunk_hist[(size_t)c * n_glob + g];
+            chunk_hist[(size_t)c * n_glob + g] = run;
+            run += t;
+        }
+        s_total[g] = run;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int b = 0, nw = 0;
+        for (int q = 0; q < n_glob; ++q) {
+            base[q] = b;
+            work_range[q] = nw;
+            for (int o = 0; o < s_total[q] && nw < n_work_max; o += kSplit) {
+                work[3 * nw] = q; work[3 * nw + 1] = b + o; work[3 * nw + 2] = b + min(s_total[q], o + kSplit);
+                ++nw;
+            }
+            b += s_total[q];
+        }
+        work_range[n_glob] = nw;
+    }
+}
+
+__global__ void __launch_bounds__(kSortThreads)
+bucket_scatter_kernel(const uint16_t* __restrict__ bucket, int64_t total_frames, int n_glob, const int* __restrict__ chunk_off,
+                      const int* __restrict__ base, int* __restrict__ idx) {
+    extern __shared__ int s_sc[];
+    int* run_off = s_sc;                          // [n_glob] next free list slot of every bucket
+    int* wc = s_sc + n_glob;                      // [8][n_glob] matches per warp in the current round
+    const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < n_glob; i += kSortThreads) run_off[i] = base[i] + chunk_off[(size_t)c * n_glob + i];
+    for (int i = tid; i < 8 * n_glob; i += kSortThreads) wc[i] = 0;
+    __syncthreads();
+    const int64_t f_begin = (int64_t)c * kSortChunk;
+    for (int r = 0; r < kSortChunk / kSortThreads; ++r) {
+        const int64_t f = f_begin + r * kSortThreads + tid;
+        const int b = (f < total_frames) ? (int)bucket[f] : 0xFFFF;
+        const bool valid = b < n_glob;
+        const unsigned mask = __match_any_sync(0xffffffffu, b);
+        const int rank = __popc(mask & ((1u << lane) - 1u));
+        const bool leader = valid && rank == 0;
+        if (leader) wc[warp * n_glob + b] = __popc(mask);
+        __syncthreads();
+        if (valid) {
+            int pos = run_off[b] + rank;
+            for (int w = 0; w < warp; ++w) pos += wc[w * n_glob + b];
+            idx[pos] = (int)(f - 0);              // frame index (total_frames < 2^31 is checked by the launcher)
+        }
+        __syncthreads();
+        if (leader) { atomicAdd(&run_off[b], __popc(mask)); wc[warp * n_glob + b] = 0; }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256, 1)
+accum2_kernel(const float* __restrict__ feat, const int* __restrict__ idx, const int* __restrict__ work, const int* __restrict__ work_range,
+              int n_glob, const float* __restrict__ shift, double* __restrict__ part) {
+    constexpr int D = 39;
+    const int item = blockIdx.x;
+    if (item >= work_range[n_glob]) return;
+    const int g = work[3 * item], begin = work[3 * item + 1], end = work[3 * item + 2];
+    const int tid = threadIdx.x;
+    const int grp = tid >> 4, tile = tid & 15;
+    __shared__ __align__(16) double s_y[kA2Frames * kA2RowPitch];      // reused for the final sum
+    __shared__ double s_shift[40];
+    // tile -> (bi, bj), bi <= bj, row-major over the upper triangle of the 5 x 5 grid
+    int bi = 0, bj = 0;
+    const bool has_tile = tile < 15;
+    if (has_tile) { int r = tile; while (r >= 5 - bi) { r -= 5 - bi; ++bi; } bj = bi + r; }
+    double acc[8][8];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) acc[a][b] = 0.0;
+    if (tid < 40) s_shift[tid] = (tid < D) ? (double)shift[(size_t)g * D + tid] : 0.0;
+    __syncthreads();
+    for (int b0 = begin; b0 < end; b0 += kA2Frames) {
+        const int nb = min(kA2Frames, end - b0);
+        for (int i = tid; i < nb * 40; i += 256) {
+            const int r = i / 40, k = i - r * 40;
+            double v = 0.0;
+            if (k < D) v = (double)__ldg(feat + (size_t)idx[b0 + r] * D + k) - s_shift[k];
+            else if (k == D) v = 1.0;
+            s_y[r * kA2RowPitch + (k >> 3) * kA2BlockPitch + (k & 7)] = v;
+        }
+        __syncthreads();
+        if (has_tile) {
+            for (int r = grp; r < nb; r += kA2Groups) {
+                const double* row = s_y + r * kA2RowPitch;
+                double xi[8], xj[8];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const double2 u = *reinterpret_cast<const double2*>(row + bi * kA2BlockPitch + 2 * q);
+                    const double2 v = *reinterpret_cast<const double2*>(row + bj * kA2BlockPitch + 2 * q);
+                    xi[2 * q] = u.x; xi[2 * q + 1] = u.y; xj[2 * q] = v.x; xj[2 * q + 1] = v.y;
+                }
+#pragma unroll
+                for (int a = 0; a < 8; ++a)
+#pragma unroll
+                    for (int b = 0; b < 8; ++b) acc[a][b] = fma(xi[a], xj[b], acc[a][b]);
+            }
+        }
+        __syncthreads();
+    }
+    // groups -> one 40 x 40 matrix in shared memory, fixed order
+    double* s_sum = s_y;                          // [40][41]
+    for (int q = 0; q < kA2Groups; ++q) {
+        if (grp == q && has_tile) {
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    double* d = &s_sum[(8 * bi + a) * 41 + 8 * bj + b];
+                    *d = (q == 0) ? acc[a][b] : (*d + acc[a][b]);
+                }
+        }
+        __syncthreads();
+    }
+    constexpr int stride = 1 + D + D * (D + 1) / 2;
+    double* dst = part + (size_t)item * stride;
+    for (int e = tid; e < stride; e += 256) {
+        int i = D, j = D;                                  // e = 0: N = sum 1 * 1
+        if (e >= 1 && e <= D) { i = e - 1; j = D; }        // sum (x_i - shift_i) * 1
+        else if (e > D) {
+            int r = e - 1 - D, row = 0;
+            while (r >= D - row) { r -= D - row; ++row; }
+            i = row; j = row + r;
+        }
+        dst[e] = s_sum[i * 41 + j];
+    }
+}
+
+__global__ void reduce2_kernel(const double* __restrict__ part, const int* __restrict__ work_range, int stride, double* __restrict__ stats) {
+    const int g = blockIdx.x;
+    const int w0 = work_range[g], w1 = work_range[g + 1];
+    for (int e = threadIdx.x; e < stride; e += blockDim.x) {
+        double a = 0.0;
+        for (int w = w0; w < w1; ++w) a += part[(size_t)w * stride + e];
+        stats[(size_t)g * stride + e] = a;
+    }
+}
+
+// workspace layout of the sorted path, in doubles: [part: n_work_max * stride][ints: chunk_hist | base | work | work_range | idx]
+struct SortedLayout {
+    int n_chunks, n_work_max;
+    size_t part_doubles, int_count, total_doubles;
+    size_t o_hist, o_base, o_work, o_range, o_idx;      // offsets in ints
+};
+static SortedLayout sorted_layout(int64_t total_frames, int n_glob, int dim) {
+    SortedLayout L;
+    const int stride = 1 + dim + dim * (dim + 1) / 2;
+    L.n_chunks = (int)((total_frames + kSortChunk - 1) / kSortChunk);
+    if (L.n_chunks < 1) L.n_chunks = 1;
+    L.n_work_max = (int)((total_frames + kSplit - 1) / kSplit) + n_glob;
+    L.part_doubles = (size_t)L.n_work_max * stride;
+    L.o_hist = 0;
+    L.o_base = L.o_hist + (size_t)L.n_chunks * n_glob;
+    L.o_work = L.o_base + (size_t)n_glob;
+    L.o_range = L.o_work + 3 * (size_t)L.n_work_max;
+    L.o_idx = L.o_range + (size_t)n_glob + 1;
+    L.int_count = L.o_idx + (size_t)total_frames;
+    L.total_doubles = L.part_doubles + (L.int_count + 1) / 2;
+    return L;
+}
+static bool sorted_path_ok(int64_t total_frames, int n_glob, int dim) {
+    return dim == 39 && n_glob <= kSortMaxGlob && total_frames < (int64_t)0x7fffffff && !getenv("LOE_B200_KMEANS_SCAN");
+}
+
 static void kmeans_chunking(int64_t total_frames, int64_t* chunk, int* n_chunks) {
     int64_t ch = 8192;
     while ((total_frames + ch - 1) / ch > 512) ch *= 2;
@@ -271,7 +487,9 @@ extern "C" int loe_align_dev(const int8_t* path_dev, const int64_t* frm_off_dev,
 extern "C" int64_t loe_kmeans_ws_doubles(int64_t total_frames, int n_glob, int dim) {
     int64_t chunk; int n_chunks;
     loe::kmeans_chunking(total_frames, &chunk, &n_chunks);
-    return (int64_t)n_glob * n_chunks * (1 + dim + dim * (dim + 1) / 2) + n_chunks;    // + per-chunk bucket ranges
+    const int64_t scan = (int64_t)n_glob * n_chunks * (1 + dim + dim * (dim + 1) / 2) + n_chunks;    // + per-chunk bucket ranges
+    const int64_t sorted = loe::sorted_path_ok(total_frames, n_glob, dim) ? (int64_t)loe::sorted_layout(total_frames, n_glob, dim).total_doubles : 0;
+    return scan > sorted ? scan : sorted;
 }
 
 extern "C" int loe_kmeans_dev(const float* feat_dev, const uint16_t* bucket_dev, int64_t total_frames, int dim,
@@ -281,6 +499,31 @@ extern "C" int loe_kmeans_dev(const float* feat_dev, const uint16_t* bucket_dev,
     if (dim + 1 > kMaxDimK) { set_error("kmeans kernel supports dim <= %d (got %d)", kMaxDimK - 1, dim); return LOE_ERR_UNSUPPORTED; }
     const int stride = 1 + dim + dim * (dim + 1) / 2;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (total_frames <= 0) { LOE_CUDA(cudaMemsetAsync(stats_dev, 0, sizeof(double) * (size_t)n_glob * stride, s)); return LOE_OK; }
+    if (sorted_path_ok(total_frames, n_glob, dim)) {
+        const SortedLayout L = sorted_layout(total_frames, n_glob, dim);
+        int* ints = reinterpret_cast<int*>(part_ws_dev + L.part_doubles);
+        int* hist = ints + L.o_hist; int* base = ints + L.o_base; int* work = ints + L.o_work; int* range = ints + L.o_range; int* idx = ints + L.o_idx;
+        static bool attr_done[64] = {false};
+        int dev = 0;
+        LOE_CUDA(cudaGetDevice(&dev));
+        const size_t scatter_smem = sizeof(int) * 9 * (size_t)n_glob;
+        if (dev < 64 && !attr_done[dev]) {
+            LOE_CUDA(cudaFuncSetAttribute(bucket_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(int) * 9 * kSortMaxGlob)));
+            attr_done[dev] = true;
+        }
+        bucket_hist_kernel<<<(unsigned)L.n_chunks, kSortThreads, sizeof(int) * (size_t)n_glob, s>>>(bucket_dev, total_frames, n_glob, hist);
+        LOE_LAUNCH_CHECK("bucket_hist_kernel");
+        bucket_scan_kernel<<<1, 1024, 0, s>>>(hist, L.n_chunks, n_glob, base, work, range, L.n_work_max);
+        LOE_LAUNCH_CHECK("bucket_scan_kernel");
+        bucket_scatter_kernel<<<(unsigned)L.n_chunks, kSortThreads, scatter_smem, s>>>(bucket_dev, total_frames, n_glob, hist, base, idx);
+        LOE_LAUNCH_CHECK("bucket_scatter_kernel");
+        accum2_kernel<<<(unsigned)L.n_work_max, 256, 0, s>>>(feat_dev, idx, work, range, n_glob, shift_dev, part_ws_dev);
+        LOE_LAUNCH_CHECK("accum2_kernel");
+        reduce2_kernel<<<(unsigned)n_glob, 256, 0, s>>>(part_ws_dev, range, stride, stats_dev);
+        LOE_LAUNCH_CHECK("reduce2_kernel");
+        return LOE_OK;
+    }
     int64_t chunk; int n_chunks;
     kmeans_chunking(total_frames, &chunk, &n_chunks);
     const size_t n_part = (size_t)n_glob * n_chunks * stride;
