@@ -170,6 +170,69 @@ def workload_config(n_utts, pool, where):
 
 
 # ------------------------------------------------------------------------------------------------
+def train_block(args, eng, world, rank, dist):
+    """BASELINE.json configs[2]: segmental K-means training of the 11 digit HMMs (5 states) on 100 k synthetic single-digit
+    utterances, STRONG scaling: the utterances are sharded over the ranks, one all-reduce of the packed float64 statistics
+    per iteration, the M-step on every rank's device.  Times are CUDA events on the launching stream (start of one
+    iteration to the start of the next, median over the iterations), max over ranks."""
+    import torch
+    from loe_speech_recognition import HiddenMarkovModelTrainable
+    from loe_speech_recognition.synthetic import DIGITS, isolated_corpus
+    pool = 64
+    corpus = isolated_corpus(seed=3, n_per_word=pool, words=DIGITS)
+    per_word = (args.train_utts + len(DIGITS) - 1) // len(DIGITS)
+    feats_by_word = {}
+    for w in DIGITS:
+        b = eng.mfcc(corpus[w])
+        flat = b.feat.cpu().numpy()
+        utts = [flat[b.frm_off_host[i]:b.frm_off_host[i + 1]] for i in range(len(corpus[w]))]
+        feats_by_word[w] = (utts * ((per_word + pool - 1) // pool))[:per_word]     # from_data_batch shards by rank itself
+    n_utts = per_word * len(DIGITS)
+    n_frames = sum(x.shape[0] for xs in feats_by_word.values() for x in xs)
+    HiddenMarkovModelTrainable.from_data_batch(feats_by_word, num_of_states=5, max_iterations=2)            # warm-up
+    launches0 = eng.launches
+    models, info = HiddenMarkovModelTrainable.from_data_batch(feats_by_word, num_of_states=5, max_iterations=args.train_iters, return_info=True)
+    launches = eng.launches - launches0
+    chk = float(sum(np.abs(m._means.astype(np.float64)).sum() + np.abs(m._covariances.astype(np.float64)).sum() for m in models.values()))
+    vals = torch.tensor([info["ms_per_iteration"], chk, -chk] + [info["phase_ms"][k] for k in ("emission", "viterbi", "align_stats", "allreduce", "mstep")],
+                        dtype=torch.float64, device=eng.device)
+    if dist is not None:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+    ms, chk_max, chk_min = float(vals[0]), float(vals[1]), -float(vals[2])
+    phases = {k: float(vals[3 + i]) for i, k in enumerate(("emission", "viterbi", "align_stats", "allreduce", "mstep"))}
+    if rank != 0:
+        return None
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    frames_rank = info["frames_this_rank"]
+    stats_bytes = (4 * 39 + 2 + 1) * frames_rank                   # features + bucket ids + path, per rank and iteration (SURVEY §8d)
+    return {
+        "workload": "BASELINE.json configs[2]: segmental K-means, 11 digit HMMs x 5 states, full-covariance Gaussians, D=39, "
+                    f"{n_utts} synthetic single-digit utterances ({n_frames} frames; pool of {pool} per word, tiled)",
+        "scaling": "strong", "n_gpus": world, "utterances_total": n_utts, "frames_total": n_frames, "frames_per_rank": frames_rank,
+        "iterations_run": info["iterations"], "ms_per_iteration": ms, "utterances_per_s": n_utts / (ms * 1e-3),
+        "frames_per_s": n_frames / (ms * 1e-3), "phase_ms_median": phases,
+        "mstep": info["mstep"], "emission": "h16 (3xFP16 tcgen05), one launch per word model",
+        "allreduce": {"bytes": info["allreduce_bytes"], "ms": phases["allreduce"], "collective": "one NCCL all-reduce of the packed float64 "
+                      "statistics + counts per iteration" if world > 1 else "none (1 rank)"},
+        "models_identical_across_ranks": bool(chk_max == chk_min), "parameters_checksum": chk_max,
+        "gpu_launches": launches,
+        "roofline": {"kernel": "align_kernel + bucket sort + accum2_kernel + reduce2_kernel (the statistics phase)", "bound": "hbm",
+                     "achieved": stats_bytes / (phases["align_stats"] * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                     "frac": stats_bytes / (phases["align_stats"] * 1e-3) / 1e9 / hbm, "traffic": None,
+                     "algorithmic": f"{stats_bytes} bytes per rank and iteration ((4 x 39 + 2 + 1) B per frame)",
+                     "fp64_gflops": 2 * 820 * frames_rank / (phases["align_stats"] * 1e-3) / 1e9,
+                     "note": "sum [x,1][x,1]^T is 820 float64 FMAs per frame: the FP64 pipe (64 FMA/clk/SM, ~36 TFLOP/s at 1.9 GHz), "
+                             "not HBM, bounds this phase; float64 keeps the statistics exact enough for models that are identical "
+                             "across 1..8 ranks"},
+    }
+
+
+# ------------------------------------------------------------------------------------------------
 def impl_b200(args):
     import torch
     import torch.distributed as dist
@@ -383,6 +446,17 @@ def impl_b200(args):
     del sink
     d2h = int(n * 32 + n * 4)
 
+    train = None if args.no_train else train_block(args, eng, world, rank, dist if world > 1 else None)
+    sweep = None
+    if rank == 0 and world == 1 and not args.no_sweep:
+        import bench_mfcc
+        del pcm_dev, feat, mel_ws, score_buf
+        torch.cuda.empty_cache()
+        sweep = {name: bench_mfcc.run_sweep(eng, args.sweep_utts, min(args.sweep_utts, 100000), "f32", name) for name in ("reference", "spec")}
+        for v in sweep.values():
+            v["note"] = (f"bounded sample of BASELINE.json configs[3] ({args.sweep_utts} of the 1 M utterances, 1-4 s each, generated on the "
+                         "device); bench_mfcc.py runs the full sweep")
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -471,6 +545,8 @@ def impl_b200(args):
                            "int16_ms_per_step": e2e16_s * 1e3,
                            "api": "HiddenMarkovModelInference.decode_pcm_flat (torch tensors / streams as plumbing); identical strings"},
         "gpu_launches": launches,
+        "train": train,
+        "mfcc_sweep": sweep,
         "parity": parity,
         "clocks": clocks,
         "roofline": roofline,
@@ -501,6 +577,11 @@ def main():
     ap.add_argument("--pool", type=int, default=500, help="distinct synthetic utterances (tiled to --utts)")
     ap.add_argument("--precision", default=os.environ.get("LOE_B200_EMISSION", "auto"), choices=["auto", "fp32", "fp64", "tc", "h16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the segmental K-means block (BASELINE.json configs[2])")
+    ap.add_argument("--train-utts", type=int, default=100001, help="training utterances in total (sharded over the ranks)")
+    ap.add_argument("--train-iters", type=int, default=8)
+    ap.add_argument("--no-sweep", action="store_true", help="skip the MFCC sweep block (BASELINE.json configs[3])")
+    ap.add_argument("--sweep-utts", type=int, default=200000)
     ap.add_argument("--no-parity-gate", action="store_true", help="skip the oracle comparison of every distinct utterance (rank 0, untimed)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

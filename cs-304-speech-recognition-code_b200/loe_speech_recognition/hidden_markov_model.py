@@ -418,29 +418,44 @@ class HiddenMarkovModelTrainable(HiddenMarkovModel):
                     active[i] = 1
             maybe_active[(st & (_native.LOE_MSTEP_CONVERGED)) != 0] = False
 
+        marks = []                                     # CUDA events between the phases of every iteration (return_info only)
+
+        def mark():
+            if return_info:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(stream)
+                marks.append(e)
+
         for it in range(max_iterations):
             if not maybe_active.any():
                 break
             iterations += 1
+            mark()
             if feats:
                 for i, l in enumerate(labels):
                     if maybe_active[i]:
                         a, b = frame_range[l]
                         eng.emission_h16_into(batch.feat[a:b], b_h16, cst_pad, int(tile0[i]), int(sizes[i]), scores[a:b], int(first[i]))
+                mark()
                 path, _, _, _ = eng.viterbi(scores, batch.frm_off, batch.n_utt, batch.max_frames, batch.total_frames, tp,
                                             utt_tr=utt_tr, want_end_scores=False)
+                mark()
                 stats, counts, _ = eng.kmeans_stats(batch.feat, path, batch.frm_off, batch.n_utt, batch.total_frames, tp,
                                                     utt_tr, False, G, means_d)
+                mark()
             else:
                 stats = torch.zeros((G, stride), dtype=torch.float64, device=eng.device)
                 counts = torch.zeros((G, G), dtype=torch.int32, device=eng.device)
+                mark(); mark(); mark()
             stats, counts = _dist.allreduce_stats(stats, counts)
+            mark()
             _native.check(eng.lib.loe_mstep_dev(stats.data_ptr(), counts.data_ptr(), G, W, state_word.data_ptr(), word_first.data_ptr(),
                                                 word_n.data_ptr(), word_tile.data_ptr(), means_d.data_ptr(), cov_d.data_ptr(),
                                                 counts_applied.data_ptr(), tp.band.data_ptr(), b_h16.data_ptr(), cst_pad.data_ptr(),
                                                 active.data_ptr(), updated.data_ptr(), status.data_ptr(), D, eng._stream()))
             eng.launches += 2
             applied_any += updated
+            mark()
             slot = it & 1
             status_host[slot].copy_(status, non_blocking=True)
             ev = torch.cuda.Event()
@@ -468,7 +483,17 @@ class HiddenMarkovModelTrainable(HiddenMarkovModel):
                 m._transition_probs = trans0[l]
             m._update_inference_weights()
             models[l] = m
-        info = {"iterations": iterations, "mstep": "device", "n_states": G, "frames_this_rank": int(batch.total_frames) if feats else 0}
+        info = {"iterations": iterations, "mstep": "device", "n_states": G, "frames_this_rank": int(batch.total_frames) if feats else 0,
+                "allreduce_bytes": 8 * (G * stride + G * G)}
+        if return_info and iterations:
+            torch.cuda.synchronize(eng.device)
+            ph = np.array([[marks[6 * k + j].elapsed_time(marks[6 * k + j + 1]) for j in range(5)] for k in range(iterations)])
+            total = np.array([marks[6 * k].elapsed_time(marks[6 * (k + 1)]) for k in range(iterations - 1)])
+            info["phase_ms"] = {n: float(np.median(ph[:, j])) for j, n in enumerate(("emission", "viterbi", "align_stats", "allreduce", "mstep"))}
+            info["phase_ms_first_iteration"] = {n: float(ph[0, j]) for j, n in enumerate(("emission", "viterbi", "align_stats", "allreduce", "mstep"))}
+            # start-to-start time of consecutive iterations on the device: kernels + host gaps (status check, launches)
+            info["ms_per_iteration"] = float(np.median(total)) if len(total) else float(ph[0].sum())
+            info["ms_per_iteration_all"] = [float(v) for v in total]
         return (models, info) if return_info else models
 
     @classmethod
