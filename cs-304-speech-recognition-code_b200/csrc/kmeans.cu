@@ -248,7 +248,7 @@ __global__ void reduce_kernel(const double* __restrict__ part, int n_chunks, int
 // ------------------------------------------------------------------------------------------
 // Sorted path (dim == 39, n_glob <= 1024): the default.
 //   1. counting sort of the frames by bucket, stable in frame order, per chunk of 2048 frames:
-//        bucket_hist_kernel -> bucket_scan_kernel (exclusive offsets per (bucket, chunk), bases, work list)
+//        bucket_hist_kernel -> bucket_scan_kernel (exclusive offsets per (bucket, chunk)) -> bucket_plan_kernel (bases, work list)
 //        -> bucket_scatter_kernel (frame index lists, one contiguous list per bucket)
 //   2. accum2_kernel: one CTA per work item = up to 2048 consecutive list entries of ONE bucket.  The augmented frames
 //      y = [x - shift, 1] are gathered through the list into shared memory (float64, 128 per batch) and sum y y^T is
@@ -281,37 +281,52 @@ bucket_hist_kernel(const uint16_t* __restrict__ bucket, int64_t total_frames, in
         if (b < n_glob) atomicAdd(&s_hist[b], 1);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < n_glob; i += kSortThreads) chunk_hist[(size_t)c * n_glob + i] = s_hist[i];
+    for (int i = threadIdx.x; i < n_glob; i += kSortThreads) chunk_hist[(size_t)i * gridDim.x + c] = s_hist[i];       // [bucket][chunk]
 }
 
-// one CTA: per-bucket exclusive offsets over the chunks (in place), bucket bases, and the work list
+// warp per bucket: exclusive offsets over the chunks (in place, coalesced: the histogram is stored [bucket][chunk]) and the
+// bucket's total
 __global__ void __launch_bounds__(1024)
-bucket_scan_kernel(int* __restrict__ chunk_hist, int n_chunks, int n_glob, int* __restrict__ base, int* __restrict__ work,
-                   int* __restrict__ work_range, int n_work_max) {
-    __shared__ int s_total[kSortMaxGlob];
-    const int g = threadIdx.x;
-    if (g < n_glob) {
-        int run = 0;
-        for (int c = 0; c < n_chunks; ++c) {
-            const int t = chunk_hist[(size_t)c * n_glob + g];
-            chunk_hist[(size_t)c * n_glob + g] = run;
-            run += t;
-        }
-        s_total[g] = run;
+bucket_scan_kernel(int* __restrict__ chunk_hist, int n_chunks, int n_glob, int* __restrict__ total) {
+    const int g = blockIdx.x * 32 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (g >= n_glob) return;
+    int* h = chunk_hist + (size_t)g * n_chunks;
+    int carry = 0;
+    for (int c0 = 0; c0 < n_chunks; c0 += 32) {
+        const int c = c0 + lane;
+        const int v = (c < n_chunks) ? h[c] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (c < n_chunks) h[c] = carry + incl - v;
+        carry += __shfl_sync(0xffffffffu, incl, 31);
     }
-    __syncthreads();
+    if (lane == 0) total[g] = carry;
+}
+
+// one CTA: bucket bases (exclusive scan of the totals) and the work list -- up to kSplit consecutive list entries of one
+// bucket per item, in bucket order
+__global__ void __launch_bounds__(1024)
+bucket_plan_kernel(const int* __restrict__ total, int n_glob, int* __restrict__ base, int* __restrict__ work,
+                   int* __restrict__ work_range, int n_work_max) {
+    __shared__ int s_base[kSortMaxGlob + 1], s_w0[kSortMaxGlob + 1];
     if (threadIdx.x == 0) {
         int b = 0, nw = 0;
         for (int q = 0; q < n_glob; ++q) {
-            base[q] = b;
-            work_range[q] = nw;
-            for (int o = 0; o < s_total[q] && nw < n_work_max; o += kSplit) {
-                work[3 * nw] = q; work[3 * nw + 1] = b + o; work[3 * nw + 2] = b + min(s_total[q], o + kSplit);
-                ++nw;
-            }
-            b += s_total[q];
+            s_base[q] = b; s_w0[q] = nw;
+            b += total[q];
+            nw += (total[q] + kSplit - 1) / kSplit;
         }
-        work_range[n_glob] = nw;
+        s_base[n_glob] = b; s_w0[n_glob] = min(nw, n_work_max);
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q <= n_glob; q += blockDim.x) work_range[q] = min(s_w0[q], n_work_max);
+    for (int q = threadIdx.x; q < n_glob; q += blockDim.x) {
+        base[q] = s_base[q];
+        const int n = total[q];
+        for (int o = 0, w = s_w0[q]; o < n && w < n_work_max; o += kSplit, ++w) {
+            work[3 * w] = q; work[3 * w + 1] = s_base[q] + o; work[3 * w + 2] = s_base[q] + min(n, o + kSplit);
+        }
     }
 }
 
@@ -322,7 +337,7 @@ bucket_scatter_kernel(const uint16_t* __restrict__ bucket, int64_t total_frames,
     int* run_off = s_sc;                          // [n_glob] next free list slot of every bucket
     int* wc = s_sc + n_glob;                      // [8][n_glob] matches per warp in the current round
     const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < n_glob; i += kSortThreads) run_off[i] = base[i] + chunk_off[(size_t)c * n_glob + i];
+    for (int i = tid; i < n_glob; i += kSortThreads) run_off[i] = base[i] + chunk_off[(size_t)i * gridDim.x + c];
     for (int i = tid; i < 8 * n_glob; i += kSortThreads) wc[i] = 0;
     __syncthreads();
     const int64_t f_begin = (int64_t)c * kSortChunk;
@@ -367,17 +382,30 @@ accum2_kernel(const float* __restrict__ feat, const int* __restrict__ idx, const
 #pragma unroll
         for (int b = 0; b < 8; ++b) acc[a][b] = 0.0;
     if (tid < 40) s_shift[tid] = (tid < D) ? (double)shift[(size_t)g * D + tid] : 0.0;
+    // The raw features of the NEXT batch are gathered into registers (kA2Pre independent loads per thread in flight) while
+    // the current batch is multiplied: the gather through the frame list has HBM latency and one CTA per SM cannot hide it
+    // any other way.  Element e = tid + 256 j of a batch is (row e / 40, column e % 40).
+    constexpr int kA2Pre = (kA2Frames * 40 + 255) / 256;
+    float pre[kA2Pre];
+    auto prefetch = [&](int b0) {
+        const int nb = min(kA2Frames, end - b0);
+#pragma unroll
+        for (int j = 0; j < kA2Pre; ++j) {
+            const int e = tid + 256 * j, r = e / 40, k = e - r * 40;
+            pre[j] = (r < nb && k < D) ? __ldg(feat + (size_t)__ldg(idx + b0 + r) * D + k) : 0.f;
+        }
+    };
+    prefetch(begin);
     __syncthreads();
     for (int b0 = begin; b0 < end; b0 += kA2Frames) {
         const int nb = min(kA2Frames, end - b0);
-        for (int i = tid; i < nb * 40; i += 256) {
-            const int r = i / 40, k = i - r * 40;
-            double v = 0.0;
-            if (k < D) v = (double)__ldg(feat + (size_t)idx[b0 + r] * D + k) - s_shift[k];
-            else if (k == D) v = 1.0;
-            s_y[r * kA2RowPitch + (k >> 3) * kA2BlockPitch + (k & 7)] = v;
+#pragma unroll
+        for (int j = 0; j < kA2Pre; ++j) {
+            const int e = tid + 256 * j, r = e / 40, k = e - r * 40;
+            if (r < nb) s_y[r * kA2RowPitch + (k >> 3) * kA2BlockPitch + (k & 7)] = (k < D) ? (double)pre[j] - s_shift[k] : 1.0;
         }
         __syncthreads();
+        if (b0 + kA2Frames < end) prefetch(b0 + kA2Frames);
         if (has_tile) {
             for (int r = grp; r < nb; r += kA2Groups) {
                 const double* row = s_y + r * kA2RowPitch;
@@ -434,11 +462,11 @@ __global__ void reduce2_kernel(const double* __restrict__ part, const int* __res
     }
 }
 
-// workspace layout of the sorted path, in doubles: [part: n_work_max * stride][ints: chunk_hist | base | work | work_range | idx]
+// workspace layout of the sorted path, in doubles: [part: n_work_max * stride][ints: chunk_hist | total | base | work | work_range | idx]
 struct SortedLayout {
     int n_chunks, n_work_max;
     size_t part_doubles, int_count, total_doubles;
-    size_t o_hist, o_base, o_work, o_range, o_idx;      // offsets in ints
+    size_t o_hist, o_total, o_base, o_work, o_range, o_idx;      // offsets in ints
 };
 static SortedLayout sorted_layout(int64_t total_frames, int n_glob, int dim) {
     SortedLayout L;
@@ -448,7 +476,8 @@ static SortedLayout sorted_layout(int64_t total_frames, int n_glob, int dim) {
     L.n_work_max = (int)((total_frames + kSplit - 1) / kSplit) + n_glob;
     L.part_doubles = (size_t)L.n_work_max * stride;
     L.o_hist = 0;
-    L.o_base = L.o_hist + (size_t)L.n_chunks * n_glob;
+    L.o_total = L.o_hist + (size_t)L.n_chunks * n_glob;
+    L.o_base = L.o_total + (size_t)n_glob;
     L.o_work = L.o_base + (size_t)n_glob;
     L.o_range = L.o_work + 3 * (size_t)L.n_work_max;
     L.o_idx = L.o_range + (size_t)n_glob + 1;
@@ -503,7 +532,7 @@ extern "C" int loe_kmeans_dev(const float* feat_dev, const uint16_t* bucket_dev,
     if (sorted_path_ok(total_frames, n_glob, dim)) {
         const SortedLayout L = sorted_layout(total_frames, n_glob, dim);
         int* ints = reinterpret_cast<int*>(part_ws_dev + L.part_doubles);
-        int* hist = ints + L.o_hist; int* base = ints + L.o_base; int* work = ints + L.o_work; int* range = ints + L.o_range; int* idx = ints + L.o_idx;
+        int* hist = ints + L.o_hist; int* total = ints + L.o_total; int* base = ints + L.o_base; int* work = ints + L.o_work; int* range = ints + L.o_range; int* idx = ints + L.o_idx;
         static bool attr_done[64] = {false};
         int dev = 0;
         LOE_CUDA(cudaGetDevice(&dev));
@@ -514,8 +543,10 @@ extern "C" int loe_kmeans_dev(const float* feat_dev, const uint16_t* bucket_dev,
         }
         bucket_hist_kernel<<<(unsigned)L.n_chunks, kSortThreads, sizeof(int) * (size_t)n_glob, s>>>(bucket_dev, total_frames, n_glob, hist);
         LOE_LAUNCH_CHECK("bucket_hist_kernel");
-        bucket_scan_kernel<<<1, 1024, 0, s>>>(hist, L.n_chunks, n_glob, base, work, range, L.n_work_max);
+        bucket_scan_kernel<<<(unsigned)((n_glob + 31) / 32), 1024, 0, s>>>(hist, L.n_chunks, n_glob, total);
         LOE_LAUNCH_CHECK("bucket_scan_kernel");
+        bucket_plan_kernel<<<1, 1024, 0, s>>>(total, n_glob, base, work, range, L.n_work_max);
+        LOE_LAUNCH_CHECK("bucket_plan_kernel");
         bucket_scatter_kernel<<<(unsigned)L.n_chunks, kSortThreads, scatter_smem, s>>>(bucket_dev, total_frames, n_glob, hist, base, idx);
         LOE_LAUNCH_CHECK("bucket_scatter_kernel");
         accum2_kernel<<<(unsigned)L.n_work_max, 256, 0, s>>>(feat_dev, idx, work, range, n_glob, shift_dev, part_ws_dev);

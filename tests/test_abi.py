@@ -43,7 +43,7 @@ def test_host_side_argument_checks_need_no_gpu(built_lib):
     assert lib.loe_emission_dev(0, 10, 7, 0, 0, 0, 3, 0, 3, 0, 0) == _native.LOE_ERR_UNSUPPORTED
     assert lib.loe_viterbi_bp_fits(460, 58) == 1 and lib.loe_viterbi_bp_fits(100000, 128) == 0
     # sorted path: (1 work item per 2048 list entries + one per bucket) partials of 820 doubles + the integer tables
-    assert lib.loe_kmeans_ws_doubles(1000, 5, 39) == 6 * 820 + (1 * 5 + 5 + 3 * 6 + 6 + 1000 + 1) // 2
+    assert lib.loe_kmeans_ws_doubles(1000, 5, 39) == 6 * 820 + (1 * 5 + 5 + 5 + 3 * 6 + 6 + 1000 + 1) // 2
     assert lib.loe_kmeans_ws_doubles(1000, 5, 13) == 5 * (1 + 13 + 91) + 1              # other dimensions: the scanning path
 
 
