@@ -251,11 +251,14 @@ __global__ void reduce_kernel(const double* __restrict__ part, int n_chunks, int
 //        bucket_hist_kernel -> bucket_scan_kernel (exclusive offsets per (bucket, chunk)) -> bucket_plan_kernel (bases, work list)
 //        -> bucket_scatter_kernel (frame index lists, one contiguous list per bucket)
 //   2. accum2_kernel: one CTA per work item = up to 2048 consecutive list entries of ONE bucket.  The augmented frames
-//      y = [x - shift, 1] are gathered through the list into shared memory (float64, 128 per batch) and sum y y^T is
-//      accumulated in 8 x 8 float64 register tiles: the 15 tiles on or above the diagonal of the 5 x 5 tile grid belong
-//      to 15 threads of a group of 16, 16 groups take the frames of a batch in turn.  8 + 8 shared-memory doubles feed
-//      64 FMAs (the 4 x 4 tiles of the scanning kernel: 4 + 4 for 16), which balances the shared-memory wavefronts with
-//      the FP64 pipe -- the pipe that bounds this kernel: 820 FMAs per frame.
+//      y = [x - shift, 1] are gathered through the list into shared memory (float64, 64 per batch; the next batch's raw
+//      features are prefetched into registers meanwhile) and sum y y^T = Y^T Y is a contraction over the frames on the FP64
+//      TENSOR cores: mma.sync m8n8k4 (DMMA), 15 tiles of 8 x 8 on or above the diagonal of the 5 x 5 tile grid, 4 frames per
+//      instruction, all 15 accumulator tiles in the registers of every warp; 5 shared-memory loads feed 15 DMMAs (3 840
+//      FMAs).  The FP64 pipe bounds this kernel (960 FMAs per frame at 64 per clock and SM); with scalar DFMAs in 8 x 8
+//      register tiles (the first version of this path) instruction issue and latency did: 15 % pipe utilisation (ncu).
+//      float64 is kept because the models must come out identical whatever the number of ranks the frames are sharded
+//      over -- split-precision products on the tcgen05 pipe give 2^-21 per product, not enough for that.
 //   3. reduce2_kernel: partials of a bucket summed in work-list order.
 // Everything is in a fixed order: statistics are bitwise reproducible, and independent of how other buckets' frames are
 // interleaved with a bucket's own.
@@ -264,10 +267,8 @@ constexpr int kSortChunk = 2048;                 // frames per histogram / scatt
 constexpr int kSortThreads = 256;
 constexpr int kSortMaxGlob = 1024;
 constexpr int kSplit = 2048;                     // list entries per work item
-constexpr int kA2Frames = 112;                   // frames per staged batch (44.8 KB of float64 rows: under the 48 KB static limit)
-constexpr int kA2Groups = 16;
-constexpr int kA2BlockPitch = 10;                // doubles per 8-wide block of a staged row (2 of padding: conflict-free 16-byte reads)
-constexpr int kA2RowPitch = 5 * kA2BlockPitch;   // 50 doubles
+constexpr int kA2Frames = 64;                    // frames per staged batch (22.5 KB of float64 rows: two CTAs per SM)
+constexpr int kA2RowPitch = 44;                  // doubles per staged row (40 used): conflict-free fragment loads
 
 __global__ void __launch_bounds__(kSortThreads)
 bucket_hist_kernel(const uint16_t* __restrict__ bucket, int64_t total_frames, int n_glob, int* __restrict__ chunk_hist) {
@@ -361,30 +362,30 @@ bucket_scatter_kernel(const uint16_t* __restrict__ bucket, int64_t total_frames,
     }
 }
 
-__global__ void __launch_bounds__(256, 1)
+// D (8 x 8, fp64) += A (8 x 4) B (4 x 8) on the FP64 tensor cores.  Lane l holds A[l >> 2][l & 3], B[l & 3][l >> 2] and
+// D[l >> 2][2 (l & 3) + {0, 1}].
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(256, 2)
 accum2_kernel(const float* __restrict__ feat, const int* __restrict__ idx, const int* __restrict__ work, const int* __restrict__ work_range,
               int n_glob, const float* __restrict__ shift, double* __restrict__ part) {
     constexpr int D = 39;
     const int item = blockIdx.x;
     if (item >= work_range[n_glob]) return;
     const int g = work[3 * item], begin = work[3 * item + 1], end = work[3 * item + 2];
-    const int tid = threadIdx.x;
-    const int grp = tid >> 4, tile = tid & 15;
-    __shared__ __align__(16) double s_y[kA2Frames * kA2RowPitch];      // reused for the final sum
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ __align__(16) double s_y[kA2Frames * kA2RowPitch];      // staged rows [frame][44]; reused for the final sum
     __shared__ double s_shift[40];
-    // tile -> (bi, bj), bi <= bj, row-major over the upper triangle of the 5 x 5 grid
-    int bi = 0, bj = 0;
-    const bool has_tile = tile < 15;
-    if (has_tile) { int r = tile; while (r >= 5 - bi) { r -= 5 - bi; ++bi; } bj = bi + r; }
-    double acc[8][8];
+    // sum y y^T as 15 tiles of 8 x 8 (upper triangle of the 5 x 5 tile grid), all of them in the registers of every warp:
+    // tile t = (bi, bj), lane holds rows 8 bi + (lane >> 2), columns 8 bj + 2 (lane & 3) + {0, 1}
+    double c[15][2];
 #pragma unroll
-    for (int a = 0; a < 8; ++a)
-#pragma unroll
-        for (int b = 0; b < 8; ++b) acc[a][b] = 0.0;
+    for (int t = 0; t < 15; ++t) { c[t][0] = 0.0; c[t][1] = 0.0; }
     if (tid < 40) s_shift[tid] = (tid < D) ? (double)shift[(size_t)g * D + tid] : 0.0;
     // The raw features of the NEXT batch are gathered into registers (kA2Pre independent loads per thread in flight) while
-    // the current batch is multiplied: the gather through the frame list has HBM latency and one CTA per SM cannot hide it
-    // any other way.  Element e = tid + 256 j of a batch is (row e / 40, column e % 40).
+    // the current batch is multiplied.  Element e = tid + 256 j of a batch is (row e / 40, column e % 40).
     constexpr int kA2Pre = (kA2Frames * 40 + 255) / 256;
     float pre[kA2Pre];
     auto prefetch = [&](int b0) {
@@ -399,42 +400,44 @@ accum2_kernel(const float* __restrict__ feat, const int* __restrict__ idx, const
     __syncthreads();
     for (int b0 = begin; b0 < end; b0 += kA2Frames) {
         const int nb = min(kA2Frames, end - b0);
+        // rows beyond the batch are ZERO (also their constant-one column): the 4-frame steps below need no tail handling
 #pragma unroll
         for (int j = 0; j < kA2Pre; ++j) {
             const int e = tid + 256 * j, r = e / 40, k = e - r * 40;
-            if (r < nb) s_y[r * kA2RowPitch + (k >> 3) * kA2BlockPitch + (k & 7)] = (k < D) ? (double)pre[j] - s_shift[k] : 1.0;
+            if (r < kA2Frames) s_y[r * kA2RowPitch + k] = (r < nb) ? ((k < D) ? (double)pre[j] - s_shift[k] : 1.0) : 0.0;
         }
         __syncthreads();
         if (b0 + kA2Frames < end) prefetch(b0 + kA2Frames);
-        if (has_tile) {
-            for (int r = grp; r < nb; r += kA2Groups) {
-                const double* row = s_y + r * kA2RowPitch;
-                double xi[8], xj[8];
+        const int n_steps = (nb + 3) >> 2;
+        for (int st = warp; st < n_steps; st += 8) {
+            // one load per 8-wide block serves as the A fragment of the tiles in that block row and as the B fragment of
+            // the tiles in that block column (pitch 44: the 16 lanes of a half-warp hit 32 different banks)
+            const double* p = s_y + (4 * st + (lane & 3)) * kA2RowPitch + (lane >> 2);
+            double f[5];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const double2 u = *reinterpret_cast<const double2*>(row + bi * kA2BlockPitch + 2 * q);
-                    const double2 v = *reinterpret_cast<const double2*>(row + bj * kA2BlockPitch + 2 * q);
-                    xi[2 * q] = u.x; xi[2 * q + 1] = u.y; xj[2 * q] = v.x; xj[2 * q + 1] = v.y;
-                }
+            for (int b = 0; b < 5; ++b) f[b] = p[8 * b];
+            int t = 0;
 #pragma unroll
-                for (int a = 0; a < 8; ++a)
+            for (int bi = 0; bi < 5; ++bi)
 #pragma unroll
-                    for (int b = 0; b < 8; ++b) acc[a][b] = fma(xi[a], xj[b], acc[a][b]);
-            }
+                for (int bj = bi; bj < 5; ++bj, ++t) dmma884(c[t][0], c[t][1], f[bi], f[bj]);
         }
         __syncthreads();
     }
-    // groups -> one 40 x 40 matrix in shared memory, fixed order
+    // warps -> one 40 x 40 matrix in shared memory, fixed order
     double* s_sum = s_y;                          // [40][41]
-    for (int q = 0; q < kA2Groups; ++q) {
-        if (grp == q && has_tile) {
+    for (int q = 0; q < 8; ++q) {
+        if (warp == q) {
+            int t = 0;
 #pragma unroll
-            for (int a = 0; a < 8; ++a)
+            for (int bi = 0; bi < 5; ++bi)
 #pragma unroll
-                for (int b = 0; b < 8; ++b) {
-                    double* d = &s_sum[(8 * bi + a) * 41 + 8 * bj + b];
-                    *d = (q == 0) ? acc[a][b] : (*d + acc[a][b]);
-                }
+                for (int bj = bi; bj < 5; ++bj, ++t)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        double* d = &s_sum[(8 * bi + (lane >> 2)) * 41 + 8 * bj + 2 * (lane & 3) + h];
+                        *d = (q == 0) ? c[t][h] : (*d + c[t][h]);
+                    }
         }
         __syncthreads();
     }

@@ -1,0 +1,155 @@
+"""Workspace for running the reference's own driver scripts UNMODIFIED (``scripts/*.py`` are the
+acceptance harness).
+
+The scripts (project3_train.py, project5_test_ndigits_with_sil.py, project6_train.py) read ``./ConvertedTIDigits``,
+``./.cache/<model>`` and write ``./runtime.log``, ``./plots/*.csv`` and ``./.cache/<model>``, all relative to the working
+directory, and import ``loe_speech_recognition`` from PYTHONPATH.  ``build_workspace`` lays down a synthetic corpus tree
+and the seed models; ``run_script`` executes one script file with a chosen PYTHONPATH -- the drop-in package (GPU) or the
+reference's ``src`` plus stub modules for its absent third-party imports (CPU, authoring container only).
+
+Script files are taken from /root/reference/scripts when that exists, else from oracle/_ref/scripts (a git-ignored
+staging copy that travels to the GPU box, made by oracle/stage_reference_scripts.py).  They are never modified.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "cs-304-speech-recognition-code_b200")
+SCRIPTS = ("project3_train.py", "project5_test_ndigits_with_sil.py", "project6_train.py")
+MODEL_ORDER = ("1", "2", "3", "4", "5", "6", "7", "8", "9", "O", "S", "Z")
+
+
+def scripts_dir():
+    for d in ("/root/reference/scripts", os.path.join(ROOT, "oracle", "_ref", "scripts")):
+        if all(os.path.exists(os.path.join(d, s)) for s in SCRIPTS):
+            return d
+    return None
+
+
+def write_seed_models(folder: str, golden) -> None:
+    """Reference-format model folders (<label>/{log_trans_probs,multivariate_normals}.pickle) of the 12 word models the
+    unmodified reference trained for tests/golden/golden_hmm.npz.  Written by whichever ``loe_speech_recognition`` is
+    importable in the calling process (the pickles embed that module path, and both packages read each other's files)."""
+    from loe_speech_recognition.hidden_markov_model import HiddenMarkovModel, HiddenMarkovModelTrainable
+    from loe_speech_recognition.transition_probability import LogTransitionProbabilities
+    for w in MODEL_ORDER:
+        m = HiddenMarkovModel(w)
+        m._multivariate_normals = HiddenMarkovModelTrainable.get_multivariate_normals(golden[f"train_means_{w}"], golden[f"train_covs_{w}"])
+        ltp = LogTransitionProbabilities()
+        dense = golden[f"train_logA_{w}"]
+        ltp.num_of_states = int(dense.shape[0])
+        for i in range(dense.shape[0]):
+            for j in range(dense.shape[1]):
+                ltp._core[(i, j)] = dense[i, j]
+        m._log_transition_probs = ltp
+        m.save(folder)
+
+
+def build_corpus(root: str, seed: int = 7, n_train_iso: int = 6, n_test_iso: int = 2) -> dict:
+    """``root/ConvertedTIDigits/Adults/TIDIGITS/{TRAIN,TEST}/<speaker>/<digits><production letter>.WAV`` -- int16 PCM from
+    the seeded synthetic generator (file naming: ti_digits.py:125-129).  Returns {split: {label: n_files}}."""
+    sys.path.insert(0, PKG)
+    from scipy.io import wavfile
+    # the generator module is plain NumPy and has no package-relative imports: load it by path so that this also works in
+    # a process that has the REFERENCE package imported under the same name
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_loe_synth", os.path.join(PKG, "loe_speech_recognition", "synthetic.py"))
+    synth = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(synth)
+    rng = np.random.default_rng(seed)
+    plan = {"TRAIN": {"iso": n_train_iso, "strings": {2: 3, 3: 1, 4: 2, 5: 1, 6: 1, 7: 2}},
+            "TEST": {"iso": n_test_iso, "strings": {2: 1, 4: 1, 7: 1}}}
+    made = {}
+    for split, p in plan.items():
+        d = os.path.join(root, "ConvertedTIDigits", "Adults", "TIDIGITS", split, "SYN", "AA")
+        os.makedirs(d, exist_ok=True)
+        made[split] = {}
+        for w in synth.DIGITS:
+            for k in range(p["iso"]):
+                pcm = synth.synth_string(rng, [w])                  # S + digit + S, like a TIDIGITS isolated-digit file
+                wavfile.write(os.path.join(d, f"{w}{chr(65 + k)}.WAV"), 16000, pcm.astype(np.int16))
+            made[split][w] = p["iso"]
+        for n, count in p["strings"].items():
+            for _ in range(count):
+                while True:
+                    ds = [synth.DIGITS[int(i)] for i in rng.integers(0, len(synth.DIGITS), size=n)]
+                    lab = "".join(ds)
+                    if lab not in made[split]:
+                        break
+                wavfile.write(os.path.join(d, f"{lab}A.WAV"), 16000, synth.synth_string(rng, ds).astype(np.int16))
+                made[split][lab] = 1
+    os.makedirs(os.path.join(root, "plots"), exist_ok=True)
+    return made
+
+
+def write_stubs(folder: str) -> str:
+    """Stub modules for the reference's third-party imports that are absent in the authoring container.  ``librosa`` is
+    NOT a no-op: it forwards the calls mfcc.py:31-40 makes to the restated oracle (oracle/mfcc.py), so the reference arm
+    runs the reference's own HMM code on the oracle's features."""
+    os.makedirs(os.path.join(folder, "librosa"), exist_ok=True)
+    os.makedirs(os.path.join(folder, "matplotlib"), exist_ok=True)
+    open(os.path.join(folder, "librosa", "__init__.py"), "w").write(f'''
+import sys
+sys.path.insert(0, {ROOT!r})
+import numpy as np
+import scipy.fft
+from oracle import mfcc as _OM
+
+def power_to_db(S, ref=1.0, **kw):
+    assert ref is np.max
+    return _OM.power_to_db(S)
+
+class feature:
+    @staticmethod
+    def melspectrogram(y=None, sr=16000, n_mels=40, n_fft=320, hop_length=160, fmin=133.33, fmax=6855.4976):
+        assert (n_mels, n_fft, hop_length) == (40, 320, 160)
+        return np.einsum("ft,mf->mt", _OM.stft_power(y), _OM.mel_basis(sr, fmin=fmin, fmax=fmax), optimize=True)
+
+    @staticmethod
+    def mfcc(S=None, sr=16000, n_mfcc=13):
+        return scipy.fft.dct(S, axis=-2, type=2, norm="ortho")[:n_mfcc, :]
+
+    @staticmethod
+    def delta(m, order=1):
+        return _OM.delta(m, order)
+''')
+    permissive = '''
+class _Any:
+    def __call__(self, *a, **k): return _Any()
+    def __getattr__(self, n):
+        if n.startswith("__"): raise AttributeError(n)
+        return _Any()
+def __getattr__(n):
+    if n.startswith("__"): raise AttributeError(n)
+    return _Any()
+'''
+    for name in ("sounddevice.py", "uniplot.py", "soundfile.py", os.path.join("matplotlib", "__init__.py"), os.path.join("matplotlib", "pyplot.py")):
+        open(os.path.join(folder, name), "w").write(permissive)
+    return folder
+
+
+def run_script(name: str, cwd: str, pythonpath, timeout: int = 3000, extra_env=None) -> subprocess.CompletedProcess:
+    sd = scripts_dir()
+    assert sd is not None, "reference scripts not found"
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.pathsep.join(list(pythonpath))
+    env.pop("LOE_REFERENCE_SRC", None)
+    if extra_env:
+        env.update(extra_env)
+    return subprocess.run([sys.executable, os.path.join(sd, name)], cwd=cwd, env=env, capture_output=True, text=True, timeout=timeout)
+
+
+def read_csv(path: str):
+    return [line.rstrip("\n") for line in open(path)]
+
+
+def copy_tree(src: str, dst: str) -> None:
+    if os.path.isdir(dst):
+        shutil.rmtree(dst)
+    shutil.copytree(src, dst)
