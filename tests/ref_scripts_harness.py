@@ -63,7 +63,7 @@ def build_corpus(root: str, seed: int = 7, n_train_iso: int = 6, n_test_iso: int
     synth = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(synth)
     rng = np.random.default_rng(seed)
-    plan = {"TRAIN": {"iso": n_train_iso, "strings": {2: 3, 3: 1, 4: 2, 5: 1, 6: 1, 7: 2}},
+    plan = {"TRAIN": {"iso": n_train_iso, "strings": {2: 4, 3: 3, 4: 3, 5: 3, 6: 3, 7: 4}},
             "TEST": {"iso": n_test_iso, "strings": {2: 1, 4: 1, 7: 1}}}
     made = {}
     for split, p in plan.items():
@@ -153,3 +153,17 @@ def copy_tree(src: str, dst: str) -> None:
     if os.path.isdir(dst):
         shutil.rmtree(dst)
     shutil.copytree(src, dst)
+
+
+def last_exception(stderr: str):
+    """Name of the exception a script died with (last 'Xxx: message' / 'pkg.Xxx' line of the traceback), or None."""
+    import re
+    names = re.findall(r"^([A-Za-z_][\w.]*(?:Error|Exception|Fail|Converge|Interrupt))\b", stderr, flags=re.M)
+    return names[-1].split(".")[-1] if names else None
+
+
+def iterations_done(stderr: str):
+    """Last 'n/200' the embedded trainer's progress bar printed (tqdm writes to stderr), or None."""
+    import re
+    hits = re.findall(r"Training Iteration:\s+\d+%\|[^|]*\|\s*(\d+)/(\d+)", stderr)
+    return int(hits[-1][0]) if hits else None
