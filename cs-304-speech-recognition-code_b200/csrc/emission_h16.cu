@@ -174,10 +174,10 @@ __device__ __forceinline__ float sumsq39(const float* v) {
 // The CTA is launched with 128 registers per thread (13 warps are allocated like 16: 16 x 32 x 128 is the whole
 // file).  The two producer warpgroups hand 40 registers per thread back (setmaxnreg.dec) and the epilogue
 // warpgroup takes them (setmaxnreg.inc) for its 120-column accumulator slice.
-__global__ void __launch_bounds__(kThreads, 1)
-emission_h16_kernel(const float* __restrict__ feat, int64_t n_frames, const uint8_t* __restrict__ b_packed,
-                   const float* __restrict__ cst_pad, int n_states, float* __restrict__ out, int ld_out, int use_bulk,
-                   int g_full, int g_last) {
+__device__ __forceinline__ void
+emission_h16_body(const float* __restrict__ feat, int64_t n_frames, const uint8_t* __restrict__ b_packed,
+                  const float* __restrict__ cst_pad, int n_states, float* __restrict__ out, int ld_out, int use_bulk,
+                  int g_full, int g_last, int cta) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -185,7 +185,6 @@ emission_h16_kernel(const float* __restrict__ feat, int64_t n_frames, const uint
     // the last (possibly narrower, hence cheaper) one gets g_last, so that all SMs finish together.
     const int n_tiles = (n_states + kStatesPerTile - 1) / kStatesPerTile;
     const int n_super = (n_tiles + kHalves - 1) / kHalves;
-    const int cta = blockIdx.x;
     const int sup = min(cta / g_full, n_super - 1);
     const int G = (sup == n_super - 1) ? g_last : g_full;
     const int g = cta - sup * g_full;
@@ -404,12 +403,70 @@ emission_h16_kernel(const float* __restrict__ feat, int64_t n_frames, const uint
     }
 }
 
+__global__ void __launch_bounds__(kThreads, 1)
+emission_h16_kernel(const float* __restrict__ feat, int64_t n_frames, const uint8_t* __restrict__ b_packed,
+                   const float* __restrict__ cst_pad, int n_states, float* __restrict__ out, int ld_out, int use_bulk,
+                   int g_full, int g_last) {
+    emission_h16_body(feat, n_frames, b_packed, cst_pad, n_states, out, ld_out, use_bulk, g_full, g_last, (int)blockIdx.x);
+}
+
+// Several models in ONE launch (batched training: one word model per segment, hidden_markov_model.py:294-318 runs them one
+// after the other).  Segment i scores the frames [seg_begin[i], seg_end[i]) with the n_states[i] <= 12 states whose image
+// starts at tile seg_tile[i] into the columns from seg_col[i]; it owns ctas_per_seg consecutive CTAs.  A segment whose
+// active flag is not 1 is skipped by its CTAs (the device-side M-step freezes converged models, mstep.cu).
+__global__ void __launch_bounds__(kThreads, 1)
+emission_h16_multi_kernel(const float* __restrict__ feat, const uint8_t* __restrict__ b_packed, const float* __restrict__ cst_pad,
+                          const int64_t* __restrict__ seg_begin, const int64_t* __restrict__ seg_end, const int32_t* __restrict__ seg_tile,
+                          const int32_t* __restrict__ seg_states, const int32_t* __restrict__ seg_col, const int32_t* __restrict__ active,
+                          float* __restrict__ out, int ld_out, int ctas_per_seg) {
+    const int seg = blockIdx.x / ctas_per_seg, g = blockIdx.x % ctas_per_seg;
+    if (active && active[seg] != 1) return;
+    const int64_t begin = seg_begin[seg], n = seg_end[seg] - begin;
+    const int n_mtiles = (int)((n + kTileM - 1) / kTileM);
+    if (n <= 0 || g >= n_mtiles) return;
+    const float* f = feat + begin * kDim;
+    const int use_bulk = (reinterpret_cast<uintptr_t>(f) & 15) == 0 ? 1 : 0;
+    emission_h16_body(f, n, b_packed + (size_t)seg_tile[seg] * kBBytes, cst_pad + seg_tile[seg] * kStatesPerTile, seg_states[seg],
+                      out + begin * ld_out + seg_col[seg], ld_out, use_bulk, 1, min(ctas_per_seg, n_mtiles), g);
+}
+
 static_assert(sizeof(Smem) <= 227 * 1024, "shared memory of the emission kernel");
 
 }  // namespace h16
 }  // namespace loe
 
 extern "C" int loe_emission_h16_tile_bytes(void) { return loe::h16::kBBytes; }
+
+extern "C" int loe_emission_h16_multi_dev(const float* feat_dev, int dim, const void* b_packed_dev, const float* cst_pad_dev, int n_seg,
+                                          const int64_t* seg_begin_dev, const int64_t* seg_end_dev, const int32_t* seg_tile_dev,
+                                          const int32_t* seg_states_dev, const int32_t* seg_col_dev, const int32_t* active_dev,
+                                          int max_states, float* out_dev, int ld_out, void* stream) {
+    using namespace loe;
+    using namespace loe::h16;
+    if (n_seg <= 0) return LOE_OK;
+    if (dim != kDim) { set_error("tensor-core emission path is built for dim == 39 (got %d)", dim); return LOE_ERR_UNSUPPORTED; }
+    if (max_states > kHalves * kStatesPerTile) {
+        set_error("a segment of the multi-model launch holds at most %d states (got %d)", kHalves * kStatesPerTile, max_states);
+        return LOE_ERR_UNSUPPORTED;
+    }
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    int dev = 0, sms = 0;
+    LOE_CUDA(cudaGetDevice(&dev));
+    LOE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    static bool attr_done[64] = {false};
+    if (dev < 64 && !attr_done[dev]) {
+        LOE_CUDA(cudaFuncSetAttribute(emission_h16_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+        attr_done[dev] = true;
+    }
+    // two waves of CTAs over the machine, shared evenly by the segments (their frame counts are similar in training)
+    int per_seg = (2 * sms + n_seg - 1) / n_seg;
+    if (per_seg < 1) per_seg = 1;
+    emission_h16_multi_kernel<<<(unsigned)(n_seg * per_seg), kThreads, sizeof(Smem), s>>>(
+        feat_dev, static_cast<const uint8_t*>(b_packed_dev), cst_pad_dev, seg_begin_dev, seg_end_dev, seg_tile_dev, seg_states_dev,
+        seg_col_dev, active_dev, out_dev, ld_out, per_seg);
+    LOE_LAUNCH_CHECK("emission_h16_multi_kernel");
+    return LOE_OK;
+}
 
 extern "C" int loe_emission_h16_dev(const float* feat_dev, int64_t n_frames, int dim, const void* b_packed_dev,
                                     const float* cst_pad_dev, int n_states, float* out_dev, int ld_out, void* stream) {

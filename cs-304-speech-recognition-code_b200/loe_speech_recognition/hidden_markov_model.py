@@ -394,6 +394,10 @@ class HiddenMarkovModelTrainable(HiddenMarkovModel):
         status = torch.zeros(W, dtype=torch.int32, device=eng.device)
         counts_applied = torch.zeros((G, G), dtype=torch.int32, device=eng.device)
         applied_any = torch.zeros(W, dtype=torch.int32, device=eng.device)
+        multi_ok = bool(feats) and int(sizes.max()) <= 12 and not os.environ.get("LOE_B200_EMISSION_PER_WORD")
+        if multi_ok:
+            seg_begin = eng._to_dev(np.array([frame_range[l][0] for l in labels], dtype=np.int64))
+            seg_end = eng._to_dev(np.array([frame_range[l][1] for l in labels], dtype=np.int64))
         status_host = [torch.empty(W, dtype=torch.int32).pin_memory() for _ in range(2)]
         events = [None, None]
         maybe_active = np.ones(W, dtype=bool)          # host view of the active set, one iteration behind the device
@@ -432,10 +436,17 @@ class HiddenMarkovModelTrainable(HiddenMarkovModel):
             iterations += 1
             mark()
             if feats:
-                for i, l in enumerate(labels):
-                    if maybe_active[i]:
-                        a, b = frame_range[l]
-                        eng.emission_h16_into(batch.feat[a:b], b_h16, cst_pad, int(tile0[i]), int(sizes[i]), scores[a:b], int(first[i]))
+                if multi_ok:            # all word models in one launch; converged ones are skipped on the device
+                    _native.check(eng.lib.loe_emission_h16_multi_dev(batch.feat.data_ptr(), D, b_h16.data_ptr(), cst_pad.data_ptr(), W,
+                                                                     seg_begin.data_ptr(), seg_end.data_ptr(), word_tile.data_ptr(),
+                                                                     word_n.data_ptr(), word_first.data_ptr(), active.data_ptr(),
+                                                                     int(sizes.max()), scores.data_ptr(), G, eng._stream()))
+                    eng.launches += 1
+                else:
+                    for i, l in enumerate(labels):
+                        if maybe_active[i]:
+                            a, b = frame_range[l]
+                            eng.emission_h16_into(batch.feat[a:b], b_h16, cst_pad, int(tile0[i]), int(sizes[i]), scores[a:b], int(first[i]))
                 mark()
                 path, _, _, _ = eng.viterbi(scores, batch.frm_off, batch.n_utt, batch.max_frames, batch.total_frames, tp,
                                             utt_tr=utt_tr, want_end_scores=False)

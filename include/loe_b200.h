@@ -181,6 +181,15 @@ int loe_emission_tc_dev(const float* feat_dev, int64_t n_frames, int dim, const 
 int loe_emission_h16_tile_bytes(void);
 int loe_emission_h16_dev(const float* feat_dev, int64_t n_frames, int dim, const void* b_packed_dev,
                          const float* cst_pad_dev, int n_states, float* out_dev, int ld_out, void* stream);
+/* Several models in ONE launch (batched training, where the reference trains its word models one after the other,
+ * hidden_markov_model.py:294-318): segment i scores the frames [seg_begin[i], seg_end[i]) of feat_dev with the
+ * seg_states[i] (<= 12 = max_states bound) states whose image starts at tile seg_tile[i] of b_packed_dev / cst_pad_dev,
+ * into the columns from seg_col[i] of out_dev.  active_dev (may be NULL): segments whose flag is not 1 are skipped on the
+ * device (the M-step freezes converged models there, loe_mstep_dev).  All seg_* arrays are device arrays. */
+int loe_emission_h16_multi_dev(const float* feat_dev, int dim, const void* b_packed_dev, const float* cst_pad_dev, int n_seg,
+                               const int64_t* seg_begin_dev, const int64_t* seg_end_dev, const int32_t* seg_tile_dev,
+                               const int32_t* seg_states_dev, const int32_t* seg_col_dev, const int32_t* active_dev,
+                               int max_states, float* out_dev, int ld_out, void* stream);
 
 /* --------------------------------------------------------------------------------------
  * Diagonal-covariance Gaussian-mixture emission scoring (csrc/emission_gmm.cu; BASELINE.json north_star kernel (2),
