@@ -458,8 +458,9 @@ extern "C" int loe_emission_h16_multi_dev(const float* feat_dev, int dim, const 
         LOE_CUDA(cudaFuncSetAttribute(emission_h16_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
         attr_done[dev] = true;
     }
-    // two waves of CTAs over the machine, shared evenly by the segments (their frame counts are similar in training)
-    int per_seg = (2 * sms + n_seg - 1) / n_seg;
+    // one CTA per SM (the kernel's shared memory allows no more), shared evenly by the segments (their frame counts are
+    // similar in training); more segments than SMs simply queue
+    int per_seg = sms / n_seg;
     if (per_seg < 1) per_seg = 1;
     emission_h16_multi_kernel<<<(unsigned)(n_seg * per_seg), kThreads, sizeof(Smem), s>>>(
         feat_dev, static_cast<const uint8_t*>(b_packed_dev), cst_pad_dev, seg_begin_dev, seg_end_dev, seg_tile_dev, seg_states_dev,
