@@ -290,9 +290,17 @@ def impl_b200(args):
     skip = inf._model_boundaries._labels.index("S")
     pen = float(PENALTY)
 
+    # 3xFP16 emission: the cepstrum kernel writes the emission kernel's A operand (pre-split binary16 image) instead of the
+    # float32 feature matrix -- the same hand-off loe_decoder_decode_host uses
+    image = eng.image_buffers(F) if precision == "h16" else None
+
     def step_device():
-        eng.mfcc_device(pcm_dev, pcm_off_dev, frm_off_dev, n, F, max_t, min_t, 16000, out=feat, mel_ws=mel_ws, utt_max=utt_max)
-        scores = eng.emission(feat, gp, precision)
+        if image is not None:
+            eng.mfcc_device(pcm_dev, pcm_off_dev, frm_off_dev, n, F, max_t, min_t, 16000, mel_ws=mel_ws, utt_max=utt_max, image=image, want_feat=False)
+            scores = eng.emission_image(image, F, gp)
+        else:
+            eng.mfcc_device(pcm_dev, pcm_off_dev, frm_off_dev, n, F, max_t, min_t, 16000, out=feat, mel_ws=mel_ws, utt_max=utt_max)
+            scores = eng.emission(feat, gp, precision)
         path, _, _, best, words, count = eng.viterbi(scores, frm_off_dev, n, max_t, F, tp, loop=True, penalty=pen, penalty_f64=False,
                                                      want_end_scores=False, labels=(skip, 32))
         return path, words, count
@@ -366,9 +374,13 @@ def impl_b200(args):
     stage_ms["mfcc_mel"], _ = timed(lambda: eng.mfcc_device(pcm_dev, pcm_off_dev, frm_off_dev, n, F, max_t, min_t, 16000,
                                                             out=feat, mel_ws=mel_ws, utt_max=utt_max, phases=1))
     stage_ms["mfcc_ceps"], _ = timed(lambda: eng.mfcc_device(pcm_dev, pcm_off_dev, frm_off_dev, n, F, max_t, min_t, 16000,
-                                                             out=feat, mel_ws=mel_ws, utt_max=utt_max, phases=2))
+                                                             out=feat, mel_ws=mel_ws, utt_max=utt_max, phases=2, image=image,
+                                                             want_feat=image is None))
     score_buf = torch.empty((F, gp.n_states), dtype=torch.float32, device=dev)
-    stage_ms["emission"], scores = timed(lambda: eng.emission(feat, gp, precision, out=score_buf))
+    if image is not None:
+        stage_ms["emission"], scores = timed(lambda: eng.emission_image(image, F, gp, out=score_buf))
+    else:
+        stage_ms["emission"], scores = timed(lambda: eng.emission(feat, gp, precision, out=score_buf))
     stage_ms["viterbi"], vit = timed(lambda: eng.viterbi(scores, frm_off_dev, n, max_t, F, tp, loop=True, penalty=pen,
                                                         want_end_scores=False, labels=(skip, 32)))
 
@@ -477,6 +489,8 @@ def impl_b200(args):
     traffic = ncu_traffic() if (n == 10000 and args.pool == 500) else {}     # the captures are of the default workload
     kernels = {
         "mfcc_mel_kernel": {"bound": "hbm", "alg": 4 * n_samples + 160 * F, "ms": stage_ms["mfcc_mel"]},
+        # mel energies in; out: the float32 features (156 B / frame) or, on the 3xFP16 path, the pre-split operand image
+        # (160 B / frame) + 4 B row scale -- counted as the 156 B of features either way
         "mfcc_ceps_kernel": {"bound": "hbm", "alg": (160 + 156) * F, "ms": stage_ms["mfcc_ceps"]},
         {"tc": "emission_tc_kernel", "h16": "emission_h16_kernel"}.get(precision, "emission_simt_kernel"):
             {"bound": "tensor", "alg": FLOPS_PER_FRAME * F, "ms": stage_ms["emission"]},

@@ -131,11 +131,14 @@ private:
 // the conversion rate (float32 bytes/s) beats the wire rate of the host->device copies.  Both are MEASURED by this
 // decoder, under whatever the other ranks of the box are doing at the same time: conversion times per chunk on the
 // host clock, copy times per chunk with CUDA events on the copy stream.  The verdict is taken once kNarrowVotes
-// chunks of >= 1 M samples have been seen, from the MEDIANS, with a 10 % margin in favour of the plain copy
-// (mode LOE_NARROW_AUTO); loe_decoder_set_narrow / LOE_B200_NARROW = on|off make it an explicit choice.
+// chunks of >= 1 M samples have been seen, from the MEDIANS of the last (at most 64) samples: on only if the conversion
+// beats the copy by 25 %, and off again -- for good -- when a later call finds the win below 5 % (mode LOE_NARROW_AUTO);
+// loe_decoder_set_narrow / LOE_B200_NARROW = on|off make it an explicit choice.
 // ------------------------------------------------------------------------------------------------
 constexpr int kNarrowVotes = 6;
-constexpr double kNarrowMargin = 1.10;
+constexpr double kNarrowOnMargin = 1.25;       // switch on (stay undecided -> on) only with a clear win ...
+constexpr double kNarrowOffMargin = 1.05;      // ... and off again as soon as the win is gone: the verdict is re-examined on every
+                                               // call from the medians of the last samples, so one lucky first call cannot latch it
 
 // CPUs next to the GPU: /sys/bus/pci/devices/<bus id>/local_cpulist ("0-15,32-47"), intersected with the CPUs this
 // process may use.  Empty when the file is unreadable (containers) -- the workers then float.
@@ -202,7 +205,7 @@ struct Decoder {
     int32_t* d_tr_off = nullptr; int32_t* d_col = nullptr; float* d_band = nullptr; uint8_t* d_flags = nullptr;
     int32_t* d_word = nullptr; int32_t* d_word_lo = nullptr;
     // workspace
-    DevBuf pcm[2], off[2], mel, feat, scores, path, umax, words, count, best, best_score, bp;
+    DevBuf pcm[2], off[2], mel, feat, scores, path, umax, words, count, best, best_score, bp, aimg, inv2;
     int64_t* h_off[2] = {nullptr, nullptr}; size_t h_off_cap[2] = {0, 0};      // pinned staging: [pcm_off | frm_off]
     bool used[2] = {false, false};
     char* h_out = nullptr; size_t h_out_cap = 0;                                // pinned staging of the results
@@ -242,7 +245,7 @@ static void destroy(Decoder* d) {
     if (d->h_out) cudaFreeHost(d->h_out);
     for (int i = 0; i < 2; ++i) if (d->h_stage[i]) cudaFreeHost(d->h_stage[i]);
     delete d->pool;
-    DevBuf* bufs[] = {&d->mel, &d->feat, &d->scores, &d->path, &d->umax, &d->words, &d->count, &d->best, &d->best_score, &d->bp};
+    DevBuf* bufs[] = {&d->mel, &d->feat, &d->scores, &d->path, &d->umax, &d->words, &d->count, &d->best, &d->best_score, &d->bp, &d->aimg, &d->inv2};
     for (DevBuf* b : bufs) b->release();
     void* tabs[] = {d->d_b_h16, d->d_mel_bin, d->d_mel_w, d->d_b, d->d_cst, d->d_tr_off, d->d_col, d->d_band, d->d_flags, d->d_word, d->d_word_lo};
     for (void* t : tabs) if (t) cudaFree(t);
@@ -377,7 +380,7 @@ extern "C" int loe_decoder_decode_host(void* dec, const void* pcm_host, int pcm_
     // loe_decoder_stats); the automatic verdict is taken from them while it is still open
     const int64_t min_samples = env_int("LOE_B200_NARROW_MIN_SAMPLES", 1 << 20);
     const bool deciding = pcm_format == LOE_PCM_F32 && d->narrow_mode == LOE_NARROW_AUTO && d->narrow < 0;
-    auto keep = [](std::vector<double>& v, double x) { if (v.size() >= 256) v.erase(v.begin(), v.begin() + 128); v.push_back(x); };
+    auto keep = [](std::vector<double>& v, double x) { if (v.size() >= 64) v.erase(v.begin(), v.begin() + 32); v.push_back(x); };
     int64_t frames_done = 0;
     for (size_t c = 0; c + 1 < bounds.size(); ++c) {
         const int a = bounds[c], b = bounds[c + 1], n = b - a, set = (int)(c & 1);
@@ -448,24 +451,34 @@ extern "C" int loe_decoder_decode_host(void* dec, const void* pcm_host, int pcm_
         d->used[set] = true;
         // compute buffers are shared by all chunks: growing them must wait for the chunks in flight
         const bool bp_needed = !loe_viterbi_bp_fits(max_frames, d->n_pos);
-        const size_t need[] = {(size_t)F * 40 * 4, (size_t)F * 39 * 4, (size_t)F * d->n_states * 4, (size_t)F, (size_t)n * 4,
-                               (size_t)n * max_words, (size_t)n * 4, (size_t)n * 4, (size_t)n * 4, bp_needed ? (size_t)F * LOE_MAX_POS : 0};
-        DevBuf* bufs[] = {&d->mel, &d->feat, &d->scores, &d->path, &d->umax, &d->words, &d->count, &d->best, &d->best_score, &d->bp};
+        // with the 3xFP16 image the cepstrum kernel writes the emission kernel's A operand directly (no float32 feature
+        // matrix at all): see loe_mfcc_img_dev / loe_emission_h16_img_dev
+        const bool img = d->d_b_h16 != nullptr;
+        const size_t need[] = {(size_t)F * 40 * 4, img ? 0 : (size_t)F * 39 * 4, (size_t)F * d->n_states * 4, (size_t)F, (size_t)n * 4,
+                               (size_t)n * max_words, (size_t)n * 4, (size_t)n * 4, (size_t)n * 4, bp_needed ? (size_t)F * LOE_MAX_POS : 0,
+                               img ? (size_t)loe_emission_h16_img_bytes(F) : 0, img ? (size_t)((F + 127) / 128) * 128 * 4 : 0};
+        DevBuf* bufs[] = {&d->mel, &d->feat, &d->scores, &d->path, &d->umax, &d->words, &d->count, &d->best, &d->best_score, &d->bp,
+                          &d->aimg, &d->inv2};
         bool grow = false;
-        for (int i = 0; i < 10; ++i) grow |= need[i] > bufs[i]->cap;
+        for (int i = 0; i < 12; ++i) grow |= need[i] > bufs[i]->cap;
         if (grow) {
             LOE_CUDA(cudaStreamSynchronize(d->comp));
-            for (int i = 0; i < 10; ++i) if ((st = bufs[i]->ensure(need[i])) != LOE_OK) return st;
+            for (int i = 0; i < 12; ++i) if ((st = bufs[i]->ensure(need[i])) != LOE_OK) return st;
         }
         LOE_CUDA(cudaStreamWaitEvent(d->comp, d->ev_copy[set], 0));
         const int64_t* d_pcm_off = (const int64_t*)d->off[set].p;
         const int64_t* d_frm_off = d_pcm_off + (n + 1);
-        if ((st = loe_mfcc_dev(d->pcm[set].p, chunk_format, d_pcm_off, d_frm_off, n, F, max_frames, min_frames, d->d_mel_bin, d->d_mel_w,
-                               d->mel_na, d->mel_nb, (float*)d->mel.p, (float*)d->umax.p, (float*)d->feat.p, d->comp)) != LOE_OK) return st;
-        st = d->d_b_h16 ? loe_emission_h16_dev((const float*)d->feat.p, F, 39, d->d_b_h16, d->d_cst, d->n_states, (float*)d->scores.p,
-                                               d->n_states, d->comp)
-                        : loe_emission_tc_dev((const float*)d->feat.p, F, 39, d->d_b, d->d_cst, d->n_states, (float*)d->scores.p,
-                                              d->n_states, d->comp);
+        if (img) {
+            if ((st = loe_mfcc_img_dev(d->pcm[set].p, chunk_format, d_pcm_off, d_frm_off, n, F, max_frames, min_frames, d->d_mel_bin, d->d_mel_w,
+                                       d->mel_na, d->mel_nb, (float*)d->mel.p, (float*)d->umax.p, nullptr, d->aimg.p, (float*)d->inv2.p,
+                                       d->comp, 3)) != LOE_OK) return st;
+            st = loe_emission_h16_img_dev(d->aimg.p, (const float*)d->inv2.p, F, d->d_b_h16, d->d_cst, d->n_states, (float*)d->scores.p,
+                                          d->n_states, d->comp);
+        } else {
+            if ((st = loe_mfcc_dev(d->pcm[set].p, chunk_format, d_pcm_off, d_frm_off, n, F, max_frames, min_frames, d->d_mel_bin, d->d_mel_w,
+                                   d->mel_na, d->mel_nb, (float*)d->mel.p, (float*)d->umax.p, (float*)d->feat.p, d->comp)) != LOE_OK) return st;
+            st = loe_emission_tc_dev((const float*)d->feat.p, F, 39, d->d_b, d->d_cst, d->n_states, (float*)d->scores.p, d->n_states, d->comp);
+        }
         if (st != LOE_OK) return st;
         if ((st = loe_viterbi_dev((const float*)d->scores.p, d->n_states, d_frm_off, n, max_frames, d->d_tr_off, d->d_col, d->d_band,
                                   d->d_flags, d->n_pos, nullptr, 1, penalty, penalty_f64, (int8_t*)d->path.p, nullptr, d->n_ends,
@@ -490,8 +503,12 @@ extern "C" int loe_decoder_decode_host(void* dec, const void* pcm_host, int pcm_
     }
     d->narrow_gbps = median(d->narrow_samples);
     d->copy_gbps = median(d->copy_samples);
-    if (deciding && (int)d->narrow_samples.size() >= kNarrowVotes && (int)d->copy_samples.size() >= kNarrowVotes)
-        d->narrow = d->narrow_gbps > kNarrowMargin * d->copy_gbps ? 1 : 0;
+    if (pcm_format == LOE_PCM_F32 && d->narrow_mode == LOE_NARROW_AUTO && d->narrow != 0 &&
+        (int)d->narrow_samples.size() >= kNarrowVotes && (int)d->copy_samples.size() >= kNarrowVotes) {
+        if (d->narrow < 0) d->narrow = d->narrow_gbps > kNarrowOnMargin * d->copy_gbps ? 1 : 0;
+        else if (d->narrow_gbps < kNarrowOffMargin * d->copy_gbps) d->narrow = 0;        // once off it stays off (no more samples)
+    }
+    (void)deciding;
     memcpy(words_host, d->h_out + o_words, (size_t)n_utt * max_words);
     memcpy(count_host, d->h_out + o_count, (size_t)n_utt * 4);
     if (best_score_host) memcpy(best_score_host, d->h_out + o_score, (size_t)n_utt * 4);

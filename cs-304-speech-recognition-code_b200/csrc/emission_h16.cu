@@ -27,6 +27,7 @@
 // 10-30 % as soon as ptxas spills inside a role loop (build.py warns).
 #include <cuda_fp16.h>
 #include "tcgen05.cuh"
+#include "h16_stage.cuh"
 
 namespace loe {
 namespace h16 {
@@ -54,6 +55,7 @@ constexpr int kBBytes = kBChunks * kBLbo;   // 57600
 constexpr int kProducerRegs = 88;
 constexpr int kEpilogueRegs = 208;
 constexpr int kNumMma = 8;
+static_assert(kALbo == kStageLbo && kChunksPerPart == kStageChunksPerPart && kK == kStageK, "h16_stage.cuh describes this kernel's A operand");
 #ifndef LOE_H16_RAW_BUFS
 #define LOE_H16_RAW_BUFS 2
 #endif
@@ -100,46 +102,6 @@ __host__ __device__ constexpr int pair_chunk(int mma, int which) {
 __host__ __device__ constexpr int state_of(int n) { return (n % kBlockCols) / 8; }
 static_assert(kBlockCols % 16 == 0 && 5 * kBlockCols == kTileN, "MMA N granularity / blocks cover the tile");
 
-// hi/lo split of 8 consecutive values into one 16-byte chunk each (packed conversions: F2FP converts two
-// values per instruction, the scalar F2F runs on the slow conversion pipe)
-__device__ __forceinline__ void split_store(const float* x, uint8_t* a_row, int kc) {
-    uint32_t h[4], l[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const __half2 hh = __floats2half2_rn(x[2 * q], x[2 * q + 1]);
-        const float2 hf = __half22float2(hh);
-        const __half2 ll = __floats2half2_rn(x[2 * q] - hf.x, x[2 * q + 1] - hf.y);
-        h[q] = *reinterpret_cast<const uint32_t*>(&hh);
-        l[q] = *reinterpret_cast<const uint32_t*>(&ll);
-    }
-    *reinterpret_cast<uint4*>(a_row + kc * kALbo) = make_uint4(h[0], h[1], h[2], h[3]);
-    *reinterpret_cast<uint4*>(a_row + (kChunksPerPart + kc) * kALbo) = make_uint4(l[0], l[1], l[2], l[3]);
-}
-
-// One thread stages one feature row (39 values + the constant 1 of the bias row).  Returns 4^e of the
-// power-of-two scale 2^-e applied to the row: 1 unless its largest magnitude reaches 2^15.
-__device__ __forceinline__ float stage_row(const float* __restrict__ row, uint8_t* __restrict__ a_row) {
-    float v[kK];
-    float mx = 0.0f;
-#pragma unroll
-    for (int c = 0; c < kDim; ++c) {
-        v[c] = row[c];
-        mx = fmaxf(mx, fabsf(v[c]));
-    }
-    v[kDim] = 1.0f;
-    float inv2 = 1.0f;
-    if (!(mx < 32768.0f)) {                        // rare; also taken for NaN
-        const int e = (int)((__float_as_uint(mx) >> 23) & 0xffu) - 127 - 14;       // 1 .. 114
-        const float scale = __uint_as_float((uint32_t)(127 - e) << 23);
-        inv2 = (2 * e < 128) ? __uint_as_float((uint32_t)(127 + 2 * e) << 23) : CUDART_INF_F;
-#pragma unroll
-        for (int c = 0; c < kK; ++c) v[c] *= scale;
-    }
-#pragma unroll
-    for (int kc = 0; kc < kChunksPerPart; ++kc) split_store(v + kc * 8, a_row, kc);
-    return inv2;
-}
-
 __device__ __forceinline__ unsigned long long pack_f2(float x, float y) {
     unsigned long long r;
     asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
@@ -174,8 +136,12 @@ __device__ __forceinline__ float sumsq39(const float* v) {
 // The CTA is launched with 128 registers per thread (13 warps are allocated like 16: 16 x 32 x 128 is the whole
 // file).  The two producer warpgroups hand 40 registers per thread back (setmaxnreg.dec) and the epilogue
 // warpgroup takes them (setmaxnreg.inc) for its 120-column accumulator slice.
+// IMG = true: ``feat`` is not the feature matrix but the pre-split A image the cepstrum kernel wrote (h16_stage.cuh: per
+// 128-frame tile 20 480 bytes = hi chunks 0-4, lo chunks 5-9 in the layout of an A stage) and ``inv2_g`` the row scales: the
+// producer warps have nothing to do but ONE thread that bulk-copies tile after tile straight into the A stages.
+template <bool IMG>
 __device__ __forceinline__ void
-emission_h16_body(const float* __restrict__ feat, int64_t n_frames, const uint8_t* __restrict__ b_packed,
+emission_h16_body(const float* __restrict__ feat, const float* __restrict__ inv2_g, int64_t n_frames, const uint8_t* __restrict__ b_packed,
                   const float* __restrict__ cst_pad, int n_states, float* __restrict__ out, int ld_out, int use_bulk,
                   int g_full, int g_last, int cta) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -199,7 +165,7 @@ emission_h16_body(const float* __restrict__ feat, int64_t n_frames, const uint8_
     if (tid == 0) {
         for (int i = 0; i < kRawBufs; ++i) mbar_init(&sm.raw_full[i], 1);
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&sm.a_full[i], kTileM);
+            mbar_init(&sm.a_full[i], IMG ? 1 : kTileM);
             mbar_init(&sm.a_empty[i], 1);
             mbar_init(&sm.tmem_full[i], 1);
             mbar_init(&sm.tmem_empty[i], kEpilogueThreads);
@@ -228,9 +194,20 @@ emission_h16_body(const float* __restrict__ feat, int64_t n_frames, const uint8_
     if (warp < kProducerThreads / 32) {
         // =========================== producers ===========================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProducerRegs));
+        const int n_it = (g < n_mtiles) ? (n_mtiles - g + G - 1) / G : 0;
+        if constexpr (IMG) {
+            // the image is tile-major and padded to whole tiles: one bulk copy per tile, stage it & 1
+            if (tid == 0) {
+                const uint8_t* img = reinterpret_cast<const uint8_t*>(feat);
+                for (int it = 0; it < n_it; ++it) {
+                    const int st = it & 1;
+                    mbar_wait(&sm.a_empty[st], (((uint32_t)(it >> 1)) & 1) ^ 1);       // MMA finished reading this stage
+                    bulk_load(sm.a[st], img + (size_t)(g + it * G) * kImgTileBytes, kImgTileBytes, &sm.a_full[st]);
+                }
+            }
+        } else {
         constexpr int kTileElems = kTileM * kDim;                       // 4992 floats = 19968 B, a multiple of 16
         constexpr uint32_t kTileBytes = kTileElems * sizeof(float);
-        const int n_it = (g < n_mtiles) ? (n_mtiles - g + G - 1) / G : 0;
         // bulk copies need a 16-byte aligned source (use_bulk) and a whole tile
         auto tile_full = [&](int it) { return use_bulk && (int64_t)(g + it * G + 1) * kTileM <= n_frames; };
         // kProducerGroups groups of 128 threads (thread = feature row) take the tiles in turn; tile it is staged into
@@ -263,6 +240,7 @@ emission_h16_body(const float* __restrict__ feat, int64_t n_frames, const uint8_
             mbar_arrive(&sm.a_full[st]);
             asm volatile("bar.sync %0, 128;" ::"r"(1 + p) : "memory");   // the group is done with this raw buffer: refill it
             if (row_id == 0 && it + kRawBufs < n_it && tile_full(it + kRawBufs)) issue(it + kRawBufs);
+        }
         }
     } else if (warp == (kProducerThreads + kEpilogueThreads) / 32) {
         // =========================== MMA issuer ===========================
@@ -368,7 +346,8 @@ emission_h16_body(const float* __restrict__ feat, int64_t n_frames, const uint8_
                 for (int c = 0; c < kStatesPerTile; ++c) acc[c] = 0ull;
                 load_half(taddr);
                 if (m_prev >= 0) store_tile(m_prev, h_prev);     // previous scores: shared memory -> global
-                const float mhalf = -0.5f * sm.inv2[it & 3][r];  // exact: inv2 is a power of two (1 for ordinary rows)
+                // exact: inv2 is a power of two (1 for ordinary rows)
+                const float mhalf = -0.5f * (IMG ? __ldg(inv2_g + (size_t)m * kTileM + r) : sm.inv2[it & 3][r]);
                 tmem_ld_wait();
 #pragma unroll
                 for (int n = 0; n < kTileN / 2; n += 2) acc[state_of(n)] = ffma2(pack_f2(v[n], v[n + 1]), acc[state_of(n)]);
@@ -407,7 +386,14 @@ __global__ void __launch_bounds__(kThreads, 1)
 emission_h16_kernel(const float* __restrict__ feat, int64_t n_frames, const uint8_t* __restrict__ b_packed,
                    const float* __restrict__ cst_pad, int n_states, float* __restrict__ out, int ld_out, int use_bulk,
                    int g_full, int g_last) {
-    emission_h16_body(feat, n_frames, b_packed, cst_pad, n_states, out, ld_out, use_bulk, g_full, g_last, (int)blockIdx.x);
+    emission_h16_body<false>(feat, nullptr, n_frames, b_packed, cst_pad, n_states, out, ld_out, use_bulk, g_full, g_last, (int)blockIdx.x);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+emission_h16_img_kernel(const uint8_t* __restrict__ a_img, const float* __restrict__ inv2, int64_t n_frames, const uint8_t* __restrict__ b_packed,
+                        const float* __restrict__ cst_pad, int n_states, float* __restrict__ out, int ld_out, int g_full, int g_last) {
+    emission_h16_body<true>(reinterpret_cast<const float*>(a_img), inv2, n_frames, b_packed, cst_pad, n_states, out, ld_out, 1, g_full, g_last,
+                            (int)blockIdx.x);
 }
 
 // Several models in ONE launch (batched training: one word model per segment, hidden_markov_model.py:294-318 runs them one
@@ -426,7 +412,7 @@ emission_h16_multi_kernel(const float* __restrict__ feat, const uint8_t* __restr
     if (n <= 0 || g >= n_mtiles) return;
     const float* f = feat + begin * kDim;
     const int use_bulk = (reinterpret_cast<uintptr_t>(f) & 15) == 0 ? 1 : 0;
-    emission_h16_body(f, n, b_packed + (size_t)seg_tile[seg] * kBBytes, cst_pad + seg_tile[seg] * kStatesPerTile, seg_states[seg],
+    emission_h16_body<false>(f, nullptr, n, b_packed + (size_t)seg_tile[seg] * kBBytes, cst_pad + seg_tile[seg] * kStatesPerTile, seg_states[seg],
                       out + begin * ld_out + seg_col[seg], ld_out, use_bulk, 1, min(ctas_per_seg, n_mtiles), g);
 }
 
@@ -469,14 +455,10 @@ extern "C" int loe_emission_h16_multi_dev(const float* feat_dev, int dim, const 
     return LOE_OK;
 }
 
-extern "C" int loe_emission_h16_dev(const float* feat_dev, int64_t n_frames, int dim, const void* b_packed_dev,
-                                    const float* cst_pad_dev, int n_states, float* out_dev, int ld_out, void* stream) {
-    using namespace loe;
-    using namespace loe::h16;
-    if (n_frames <= 0 || n_states <= 0) return LOE_OK;
-    if (dim != kDim) { set_error("tensor-core emission path is built for dim == 39 (got %d)", dim); return LOE_ERR_UNSUPPORTED; }
-    if (ld_out < n_states) { set_error("ld_out (%d) < n_states (%d)", ld_out, n_states); return LOE_ERR_VALUE; }
-    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+namespace loe {
+namespace h16 {
+// divide the SMs over the column supertiles in proportion to their MMA cost (the last one may be narrower)
+static int plan_grid(int n_states, int64_t n_frames, int* g_full_out, int* g_last_out, unsigned* grid_out) {
     static int sm_count[64] = {0};
     int dev = 0;
     LOE_CUDA(cudaGetDevice(&dev));
@@ -484,8 +466,8 @@ extern "C" int loe_emission_h16_dev(const float* feat_dev, int64_t n_frames, int
     if (sm_count[dev] == 0) {
         LOE_CUDA(cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
         LOE_CUDA(cudaFuncSetAttribute(emission_h16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+        LOE_CUDA(cudaFuncSetAttribute(emission_h16_img_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
     }
-    // divide the SMs over the column supertiles in proportion to their MMA cost (the last one may be narrower)
     const int n_tiles = (n_states + kStatesPerTile - 1) / kStatesPerTile;
     const int n_super = (n_tiles + kHalves - 1) / kHalves;
     const int n_mtiles = (int)((n_frames + kTileM - 1) / kTileM);
@@ -509,10 +491,49 @@ extern "C" int loe_emission_h16_dev(const float* feat_dev, int64_t n_frames, int
     }
     if (g_full > n_mtiles) g_full = n_mtiles;
     if (g_last > n_mtiles) g_last = n_mtiles;
-    const unsigned grid = (unsigned)((n_super - 1) * g_full + g_last);
+    *g_full_out = g_full; *g_last_out = g_last;
+    *grid_out = (unsigned)((n_super - 1) * g_full + g_last);
+    return LOE_OK;
+}
+}  // namespace h16
+}  // namespace loe
+
+extern "C" int loe_emission_h16_dev(const float* feat_dev, int64_t n_frames, int dim, const void* b_packed_dev,
+                                    const float* cst_pad_dev, int n_states, float* out_dev, int ld_out, void* stream) {
+    using namespace loe;
+    using namespace loe::h16;
+    if (n_frames <= 0 || n_states <= 0) return LOE_OK;
+    if (dim != kDim) { set_error("tensor-core emission path is built for dim == 39 (got %d)", dim); return LOE_ERR_UNSUPPORTED; }
+    if (ld_out < n_states) { set_error("ld_out (%d) < n_states (%d)", ld_out, n_states); return LOE_ERR_VALUE; }
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    int g_full = 1, g_last = 1; unsigned grid = 1;
+    const int st = plan_grid(n_states, n_frames, &g_full, &g_last, &grid);
+    if (st != LOE_OK) return st;
     const int use_bulk = (reinterpret_cast<uintptr_t>(feat_dev) & 15) == 0 ? 1 : 0;
     emission_h16_kernel<<<grid, kThreads, sizeof(Smem), s>>>(feat_dev, n_frames, static_cast<const uint8_t*>(b_packed_dev), cst_pad_dev,
                                                              n_states, out_dev, ld_out, use_bulk, g_full, g_last);
     LOE_LAUNCH_CHECK("emission_h16_kernel");
+    return LOE_OK;
+}
+
+extern "C" int64_t loe_emission_h16_img_bytes(int64_t n_frames) {
+    return ((n_frames + loe::h16::kTileM - 1) / loe::h16::kTileM) * (int64_t)loe::h16::kImgTileBytes;
+}
+
+extern "C" int loe_emission_h16_img_dev(const void* a_img_dev, const float* inv2_dev, int64_t n_frames, const void* b_packed_dev,
+                                        const float* cst_pad_dev, int n_states, float* out_dev, int ld_out, void* stream) {
+    using namespace loe;
+    using namespace loe::h16;
+    if (n_frames <= 0 || n_states <= 0) return LOE_OK;
+    if (ld_out < n_states) { set_error("ld_out (%d) < n_states (%d)", ld_out, n_states); return LOE_ERR_VALUE; }
+    if ((reinterpret_cast<uintptr_t>(a_img_dev) & 15) != 0) { set_error("a_img_dev must be 16-byte aligned (bulk copies)"); return LOE_ERR_VALUE; }
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    int g_full = 1, g_last = 1; unsigned grid = 1;
+    const int st = plan_grid(n_states, n_frames, &g_full, &g_last, &grid);
+    if (st != LOE_OK) return st;
+    emission_h16_img_kernel<<<grid, kThreads, sizeof(Smem), s>>>(static_cast<const uint8_t*>(a_img_dev), inv2_dev, n_frames,
+                                                                 static_cast<const uint8_t*>(b_packed_dev), cst_pad_dev, n_states, out_dev,
+                                                                 ld_out, g_full, g_last);
+    LOE_LAUNCH_CHECK("emission_h16_img_kernel");
     return LOE_OK;
 }

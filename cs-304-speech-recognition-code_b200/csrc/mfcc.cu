@@ -11,6 +11,7 @@
 // The split is forced by power_to_db(ref=np.max): every frame needs the maximum over the whole
 // utterance (mfcc.py:35).  Algorithmic HBM bytes per frame: 640 (PCM) + 156 (features).
 #include "common.cuh"
+#include "h16_stage.cuh"
 #include <math.h>
 #include <atomic>
 #include <mutex>
@@ -412,7 +413,7 @@ constexpr int kOutPitch = kFeat;
 
 __global__ void __launch_bounds__(kRowsB)
 mfcc_ceps_kernel(const float* __restrict__ mel, const float* __restrict__ utt_max,
-                 const int64_t* __restrict__ frm_off, float* __restrict__ feat) {
+                 const int64_t* __restrict__ frm_off, float* __restrict__ feat, uint8_t* __restrict__ a_img, float* __restrict__ inv2) {
     __shared__ float s_lm[kRowsB * kMelPitch];  // dB mel rows; reused for the output tile (kTileB * 39 floats)
     __shared__ float s_c[kRowsB * kCepPitch];
     const int u = blockIdx.x;
@@ -495,8 +496,18 @@ mfcc_ceps_kernel(const float* __restrict__ mel, const float* __restrict__ utt_ma
     }
     __syncthreads();
     const int nt = t1 - t0;
-    float* __restrict__ dst = feat + (f0 + t0) * kFeat;
-    for (int i = tid; i < nt * kFeat; i += kRowsB) dst[i] = s_out[i];
+    if (feat) {
+        float* __restrict__ dst = feat + (f0 + t0) * kFeat;
+        for (int i = tid; i < nt * kFeat; i += kRowsB) dst[i] = s_out[i];
+    }
+    // optional second output: the row as the binary16 hi / lo A operand of the 3xFP16 emission kernel (h16_stage.cuh), in
+    // the tile-major image that kernel bulk-copies -- tile = global frame / 128, 16 bytes per row and chunk: consecutive
+    // threads write consecutive 16-byte pieces
+    if (a_img && tid < nt) {
+        const int64_t f = f0 + t0 + tid;
+        uint8_t* a_row = a_img + (size_t)(f >> 7) * h16::kImgTileBytes + (size_t)(f & 127) * 16;
+        inv2[f] = h16::stage_row(s_out + tid * kOutPitch, a_row);
+    }
 }
 
 }  // namespace loe
@@ -504,7 +515,8 @@ mfcc_ceps_kernel(const float* __restrict__ mel, const float* __restrict__ utt_ma
 static int mfcc_launch(const void* pcm_dev, int pcm_format, const int64_t* pcm_off_dev, const int64_t* frm_off_dev,
                        int n_utt, int64_t total_frames, int max_frames, int min_frames,
                        const int32_t* mel_bin_dev, const float* mel_w_dev, int mel_na, int mel_nb,
-                       float* mel_ws_dev, float* utt_max_dev, float* feat_dev, void* stream, int phases) {
+                       float* mel_ws_dev, float* utt_max_dev, float* feat_dev, void* stream, int phases,
+                       void* a_img_dev = nullptr, float* inv2_dev = nullptr) {
     using namespace loe;
     if (n_utt <= 0 || total_frames <= 0) return LOE_OK;
     if (min_frames < 9) {
@@ -547,7 +559,15 @@ static int mfcc_launch(const void* pcm_dev, int pcm_format, const int64_t* pcm_o
     }
     if (phases & 2) {
         dim3 gb((unsigned)n_utt, (unsigned)((max_frames + kTileB - 1) / kTileB));
-        mfcc_ceps_kernel<<<gb, kRowsB, 0, s>>>(mel_ws_dev, utt_max_dev, frm_off_dev, feat_dev);
+        if (a_img_dev) {
+            // rows of the last image tile beyond the batch: zero operand, unit scale (the kernel writes the rows that exist)
+            const int64_t full = (total_frames / 128) * 128;
+            if (full < total_frames) {
+                LOE_CUDA(cudaMemsetAsync(static_cast<uint8_t*>(a_img_dev) + (size_t)(total_frames / 128) * h16::kImgTileBytes, 0, h16::kImgTileBytes, s));
+                LOE_CUDA(cudaMemsetAsync(inv2_dev + full, 0, sizeof(float) * 128, s));
+            }
+        }
+        mfcc_ceps_kernel<<<gb, kRowsB, 0, s>>>(mel_ws_dev, utt_max_dev, frm_off_dev, feat_dev, static_cast<uint8_t*>(a_img_dev), inv2_dev);
         LOE_LAUNCH_CHECK("mfcc_ceps_kernel");
     }
     return LOE_OK;
@@ -559,6 +579,17 @@ extern "C" int loe_mfcc_dev(const void* pcm_dev, int pcm_format, const int64_t* 
                             float* mel_ws_dev, float* utt_max_dev, float* feat_dev, void* stream) {
     return mfcc_launch(pcm_dev, pcm_format, pcm_off_dev, frm_off_dev, n_utt, total_frames, max_frames, min_frames, mel_bin_dev,
                        mel_w_dev, mel_na, mel_nb, mel_ws_dev, utt_max_dev, feat_dev, stream, 3);
+}
+
+extern "C" int loe_mfcc_img_dev(const void* pcm_dev, int pcm_format, const int64_t* pcm_off_dev, const int64_t* frm_off_dev,
+                                int n_utt, int64_t total_frames, int max_frames, int min_frames,
+                                const int32_t* mel_bin_dev, const float* mel_w_dev, int mel_na, int mel_nb,
+                                float* mel_ws_dev, float* utt_max_dev, float* feat_dev, void* a_img_dev, float* inv2_dev, void* stream, int phases) {
+    using namespace loe;
+    if (!a_img_dev || !inv2_dev) { set_error("a_img_dev / inv2_dev required"); return LOE_ERR_VALUE; }
+    if ((reinterpret_cast<uintptr_t>(a_img_dev) & 15) != 0) { set_error("a_img_dev must be 16-byte aligned"); return LOE_ERR_VALUE; }
+    return mfcc_launch(pcm_dev, pcm_format, pcm_off_dev, frm_off_dev, n_utt, total_frames, max_frames, min_frames, mel_bin_dev,
+                       mel_w_dev, mel_na, mel_nb, mel_ws_dev, utt_max_dev, feat_dev, stream, phases, a_img_dev, inv2_dev);
 }
 
 extern "C" int loe_mfcc_phase_dev(const void* pcm_dev, int pcm_format, const int64_t* pcm_off_dev, const int64_t* frm_off_dev,

@@ -294,12 +294,20 @@ class Engine:
             self._mel_cache[key] = (self._to_dev(bins), self._to_dev(w), na, nb)
         return self._mel_cache[key]
 
+    def image_buffers(self, total_frames: int):
+        """(a_img uint8, inv2 float32) sized for ``total_frames`` frames: the pre-split A operand of the 3xFP16 emission kernel."""
+        torch = self.torch
+        n_bytes = int(self.lib.loe_emission_h16_img_bytes(total_frames))
+        return self.empty((n_bytes,), torch.uint8), self.empty((((total_frames + 127) // 128) * 128,), torch.float32)
+
     def mfcc_device(self, pcm, pcm_off, frm_off, n_utt, total_frames, max_frames, min_frames, sample_rate=16000,
-                    out=None, mel_ws=None, utt_max=None, phases=3):
-        """PCM (device) -> features [total_frames, 39] (device).  All tensors on this device."""
+                    out=None, mel_ws=None, utt_max=None, phases=3, image=None, want_feat=True):
+        """PCM (device) -> features [total_frames, 39] (device).  All tensors on this device.
+        ``image=(a_img, inv2)`` (see image_buffers) additionally writes every feature row as the pre-split operand of
+        emission_image(); with ``want_feat=False`` the float32 matrix is not written at all (decode path) and None returned."""
         torch = self.torch
         bins, w, na, nb = self._mel_tables(sample_rate)
-        if out is None:
+        if out is None and want_feat:
             out = self.empty((total_frames, 39), torch.float32)
         if mel_ws is None:
             mel_ws = self.empty((total_frames, 40), torch.float32)
@@ -311,6 +319,13 @@ class Engine:
             fmt = 0
         else:
             raise TypeError(f"PCM must be float32 or int16 on the device (got {pcm.dtype})")
+        if image is not None:
+            _native.check(self.lib.loe_mfcc_img_dev(pcm.data_ptr(), fmt, pcm_off.data_ptr(), frm_off.data_ptr(), n_utt, total_frames,
+                                                    max_frames, min_frames, bins.data_ptr(), w.data_ptr(), na, nb,
+                                                    mel_ws.data_ptr(), utt_max.data_ptr(), self._p(out if want_feat else None),
+                                                    image[0].data_ptr(), image[1].data_ptr(), self._stream(), phases))
+            self.launches += (phases & 1) + ((phases >> 1) & 1)
+            return out if want_feat else None
         _native.check(self.lib.loe_mfcc_phase_dev(pcm.data_ptr(), fmt, pcm_off.data_ptr(), frm_off.data_ptr(), n_utt, total_frames,
                                                   max_frames, min_frames, bins.data_ptr(), w.data_ptr(), na, nb,
                                                   mel_ws.data_ptr(), utt_max.data_ptr(), out.data_ptr(), self._stream(), phases))
@@ -406,6 +421,18 @@ class Engine:
         mean, u, cst = (gp.mean64, gp.u64, gp.cst64) if code == 1 else (gp.mean32, gp.u32, gp.cst32)
         _native.check(self.lib.loe_emission_dev(feat.data_ptr(), n_frames, dim, mean.data_ptr(), u.data_ptr(), cst.data_ptr(),
                                                 gp.n_states, out.data_ptr(), ld, code, self._stream()))
+        self.launches += 1
+        return out
+
+    def emission_image(self, image, n_frames: int, gp: GaussPack, out=None):
+        """[n_frames, S] scores from the pre-split operand mfcc_device(image=...) wrote: the 3xFP16 kernel without producer
+        work.  Bit-identical to emission(feat, gp, "h16")."""
+        if gp.b_h16 is None:
+            raise NotImplementedError("model has no 3xFP16 image (whitening matrix outside the binary16 range)")
+        if out is None:
+            out = self.empty((n_frames, gp.n_states), self.torch.float32)
+        _native.check(self.lib.loe_emission_h16_img_dev(image[0].data_ptr(), image[1].data_ptr(), n_frames, gp.b_h16.data_ptr(),
+                                                        gp.cst_pad.data_ptr(), gp.n_states, out.data_ptr(), int(out.shape[1]), self._stream()))
         self.launches += 1
         return out
 

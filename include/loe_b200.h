@@ -99,6 +99,13 @@ int loe_mfcc_phase_dev(const void* pcm_dev, int pcm_format, const int64_t* pcm_o
                        const int32_t* mel_bin_dev, const float* mel_w_dev, int mel_na, int mel_nb,
                        float* mel_ws_dev, float* utt_max_dev, float* feat_dev, void* stream, int phases);
 
+/* loe_mfcc_phase_dev with the A-operand image of the 3xFP16 emission kernel as an additional output of phase 2 (see
+ * loe_emission_h16_img_dev); feat_dev may be NULL when only the image is wanted (the decode path). */
+int loe_mfcc_img_dev(const void* pcm_dev, int pcm_format, const int64_t* pcm_off_dev, const int64_t* frm_off_dev,
+                     int n_utt, int64_t total_frames, int max_frames, int min_frames,
+                     const int32_t* mel_bin_dev, const float* mel_w_dev, int mel_na, int mel_nb,
+                     float* mel_ws_dev, float* utt_max_dev, float* feat_dev, void* a_img_dev, float* inv2_dev, void* stream, int phases);
+
 /* --------------------------------------------------------------------------------------
  * Parameterised MFCC front end (csrc/mfcc_ex.cu).  The reference hard-wires one parameter set (mfcc.py:31-34), which
  * loe_mfcc_dev serves; this entry point is the same pipeline (mfcc.py:24-44) with the stages made parameters, for
@@ -181,6 +188,14 @@ int loe_emission_tc_dev(const float* feat_dev, int64_t n_frames, int dim, const 
 int loe_emission_h16_tile_bytes(void);
 int loe_emission_h16_dev(const float* feat_dev, int64_t n_frames, int dim, const void* b_packed_dev,
                          const float* cst_pad_dev, int n_states, float* out_dev, int ld_out, void* stream);
+/* The same scores from the PRE-SPLIT operand (decode path): loe_mfcc_img_dev makes the cepstrum kernel write every feature
+ * row as the binary16 hi / lo A operand (tile-major image: per 128 frames 20 480 bytes = [chunk (10: hi 0-4, lo 5-9)][row (128)]
+ * [8 halfs], rows scaled by 2^-e when they reach 2^15) plus the row scales inv2 = 4^e; the emission kernel then bulk-copies
+ * tile after tile into its A stages and has no producer work.  Bit-identical to loe_emission_h16_dev on the same features.
+ *   a_img_dev: loe_emission_h16_img_bytes(total_frames) bytes, 16-byte aligned;  inv2_dev: ceil(total_frames / 128) * 128 floats */
+int64_t loe_emission_h16_img_bytes(int64_t n_frames);
+int loe_emission_h16_img_dev(const void* a_img_dev, const float* inv2_dev, int64_t n_frames, const void* b_packed_dev,
+                             const float* cst_pad_dev, int n_states, float* out_dev, int ld_out, void* stream);
 /* Several models in ONE launch (batched training, where the reference trains its word models one after the other,
  * hidden_markov_model.py:294-318): segment i scores the frames [seg_begin[i], seg_end[i]) of feat_dev with the
  * seg_states[i] (<= 12 = max_states bound) states whose image starts at tile seg_tile[i] of b_packed_dev / cst_pad_dev,
@@ -413,8 +428,9 @@ void loe_decoder_destroy(void* decoder);
  *            LOE_B200_NARROW=on|off in the environment when the decoder is created).  LOE_NARROW_AUTO (default):
  *            the decoder narrows while it samples, per chunk, its conversion rate (host clock) and the wire rate
  *            of its host->device copies (CUDA events); after 6 chunks of >= 2^20 samples each it keeps narrowing
- *            iff median conversion GB/s (float32 bytes) > 1.1 x median copy GB/s -- the condition under which a
- *            pipelined chunk period gets shorter -- and the verdict then stands for the decoder's lifetime.
+ *            iff median conversion GB/s (float32 bytes) > 1.25 x median copy GB/s -- a pipelined chunk period gets shorter
+ *            when the conversion beats the copy -- re-examines that on every later call (medians of the last 64 chunks)
+ *            and switches off, for the decoder's lifetime, once the margin falls below 1.05.
  *   loe_decoder_stats: out[0..LOE_DECODER_STATS) = {mode, narrowing on (1) / off (0) / still sampling (-1),
  *            median conversion GB/s (float32 bytes), median copy GB/s (wire bytes), worker threads, CPUs the workers
  *            are bound to (0 = floating), PCM bytes of the last call as the caller holds them, bytes that crossed

@@ -233,6 +233,41 @@ def test_emission_tc_many_tiles_and_ragged_sizes(eng, golden):
     assert eng.torch.equal(eng.emission(shifted, gp, "h16"), eng.emission(x, gp, "h16"))
 
 
+def test_emission_from_presplit_image_is_bit_identical(eng, golden):
+    """Decode hand-off: the cepstrum kernel writes the 3xFP16 kernel's A operand (loe_mfcc_img_dev) and the emission kernel
+    bulk-copies it (loe_emission_h16_img_dev).  Same split arithmetic, same MMAs: scores bit-identical to the kernel that
+    splits the float32 features itself; the features written alongside are unchanged; ragged batch, partial last tile,
+    more tiles than CTAs, guard bands, and the image path without the float32 matrix."""
+    torch = eng.torch
+    from loe_speech_recognition.synthetic import string_corpus
+    inf = _loop_inference(golden)
+    gp, _ = inf._packs()
+    for n_utts, n_digits in ((3, 2), (40, 7), (700, 7)):
+        utts, _ = string_corpus(seed=5 + n_utts, n_utts=n_utts, n_digits=n_digits)
+        utts = [u[: len(u) - 37 * (i % 5)] for i, u in enumerate(utts)]
+        pcm, pcm_off, frm_off_dev, frm_off, frames = eng.upload_pcm(utts)
+        n, F = len(utts), int(frm_off[-1])
+        feat = eng.mfcc_device(pcm, pcm_off, frm_off_dev, n, F, int(frames.max()), int(frames.min()))
+        ref = eng.emission(feat, gp, "h16")
+        G = 4096
+        img_all = torch.full((G + int(eng.lib.loe_emission_h16_img_bytes(F)) + G,), 0x5A, dtype=torch.uint8, device=eng.device)
+        inv_all = torch.full((G + ((F + 127) // 128) * 128 + G,), -3.0, dtype=torch.float32, device=eng.device)
+        image = (img_all[G:-G], inv_all[G:-G])
+        feat2 = eng.mfcc_device(pcm, pcm_off, frm_off_dev, n, F, int(frames.max()), int(frames.min()), image=image)
+        assert torch.equal(feat2, feat)
+        got = eng.emission_image(image, F, gp)
+        torch.cuda.synchronize()
+        assert torch.equal(got, ref), (n_utts, float((got - ref).abs().max()))
+        assert bool((img_all[:G] == 0x5A).all()) and bool((img_all[-G:] == 0x5A).all())
+        assert bool((inv_all[:G] == -3.0).all()) and bool((inv_all[-G:] == -3.0).all())
+        image2 = eng.image_buffers(F)
+        assert eng.mfcc_device(pcm, pcm_off, frm_off_dev, n, F, int(frames.max()), int(frames.min()), image=image2, want_feat=False) is None
+        assert torch.equal(eng.emission_image(image2, F, gp), ref)
+    # fewer states than a tile, and the host-buffer decoder (which uses this hand-off) against the torch-backed decode
+    gp5 = eng.pack_gaussians(inf._multivariate_normals[:5])
+    assert torch.equal(eng.emission_image(image2, F, gp5), eng.emission(feat, gp5, "h16"))
+
+
 def test_emission_h16_range_handling(eng, golden):
     """binary16 tops out at 65504: feature rows of any magnitude are rescaled inside the kernel, a model
     whose whitening matrix leaves the range gets no FP16 image and runs on the TF32 kernel."""
