@@ -8,8 +8,9 @@
 // block (none / per frame as the reference does / cepstral mean / mean and variance over the utterance).
 //
 //   mel_ex_kernel    PCM -> pre-emphasis -> window -> N-point real FFT (N/2-point complex Stockham radix-4 FFT of one
-//                    frame per warp in shared memory + real-input post-pass) -> |.|^2 -> triangular filterbank
-//                    -> mel energies [frames, n_mels] (+ per-utterance maximum for the dB mode)
+//                    frame per warp in shared memory, padded against bank conflicts, + real-input post-pass) -> |.|^2
+//                    -> triangular filterbank as a lane-balanced table -> mel energies [frames, n_mels]
+//                    (+ per-utterance maximum for the dB mode)
 //   ceps_ex_kernel   mel -> log -> DCT-II -> cepstra [frames, n_ceps]            (thread per frame)
 //   cmn_ex_kernel    per-utterance mean (and 1/std) of every cepstral coefficient, fixed summation order (CTA per utterance)
 //   feat_ex_kernel   normalised static block + Savitzky-Golay delta / delta-delta (width 9) -> features [frames, 3 n_ceps]
@@ -17,7 +18,6 @@
 // Algorithmic HBM bytes per frame: 4 * hop (PCM) + 12 * n_ceps (features).
 #include "common.cuh"
 #include <math.h>
-#include <stdlib.h>
 
 namespace loe {
 
@@ -30,26 +30,39 @@ __device__ __forceinline__ float sample_f32(const float* x, int64_t i) { return 
 __device__ __forceinline__ float sample_f32(const short* x, int64_t i) { return (float)__ldg(x + i); }
 
 // Shared memory of mel_ex_kernel<LOG2N>: per warp two ping-pong buffers of M = N/2 complex points (the second one
-// also takes the power spectrum), CTA-wide the twiddles W_M^j (j < M), W_N^k (k <= M) and the window.
+// also takes the power spectrum), CTA-wide the twiddles W_M^j (j < M), W_N^k (k <= M), the window, and the filterbank
+// as a lane-balanced table (built by the CTA from the per-filter rows the caller passes).
+// Buffer index i lives at pad(i) = i + (i >> 2): the strided stores of the first two Stockham passes (stride 4 and
+// blocks of 4 at stride 16) then hit 32 different banks per half-warp instead of 8.
+__device__ __forceinline__ int padE(int i) { return i + (i >> 2); }
+
 template <int LOG2N>
 struct SmemE {
-    static constexpr int N = 1 << LOG2N, M = N / 2;
-    float2 buf[kWarpsE][2][M];
+    static constexpr int N = 1 << LOG2N, M = N / 2, MP = M + M / 4 + 4;
+    float2 buf[kWarpsE][2][MP];
     float2 wm[M];
     float2 wn[M + 1];
     float win[N];
+    int binA[32], binB[32];
+    int na, nb, lb;
 };
+
+template <typename SampleT> struct PairE;
+template <> struct PairE<float> { using type = float2; };
+template <> struct PairE<short> { using type = short2; };
 
 template <typename SampleT, int LOG2N>
 __global__ void __launch_bounds__(kWarpsE * 32)
 mel_ex_kernel(const SampleT* __restrict__ pcm, const int64_t* __restrict__ pcm_off, const int64_t* __restrict__ frm_off,
               const float* __restrict__ window, int hop, float preemph,
               const int32_t* __restrict__ mel_start, const int32_t* __restrict__ mel_len, const float* __restrict__ mel_w,
-              int mel_pitch, int n_mels, int chunk, float* __restrict__ mel_out, float* __restrict__ utt_max, int knock) {
+              int mel_pitch, int n_mels, int chunk, float* __restrict__ mel_out, float* __restrict__ utt_max) {
     using S = SmemE<LOG2N>;
     constexpr int N = S::N, M = S::M;
+    constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smem_raw_e[];
     S& sm = *reinterpret_cast<S*>(smem_raw_e);
+    float* s_w = reinterpret_cast<float*>(smem_raw_e + sizeof(S));        // [(na + nb) * 32] lane table of filter weights
     const int u = blockIdx.x;
     const int64_t f0 = frm_off[u];
     const int T = (int)(frm_off[u + 1] - f0);
@@ -68,11 +81,43 @@ mel_ex_kernel(const SampleT* __restrict__ pcm, const int64_t* __restrict__ pcm_o
         sm.wn[k] = make_float2(c, s);
     }
     for (int i = tid; i < N; i += kWarpsE * 32) sm.win[i] = window[i];
+    // Filterbank as a lane table.  Round A: lane l owns filter l (l < 32), one bin per iteration, na = widest of them.
+    // Round B: the filters from 32 on share the warp, lb = 32 / (their count rounded up to a power of two) lanes each: lane
+    // q * lb + j walks the bins start + j, start + j + lb, ...; nb iterations; partial sums meet in xor shuffles.
+    const int nA = min(n_mels, 32), nB = n_mels - nA;
+    if (warp == 0) {
+        int la = lane < nA ? mel_len[lane] : 0;
+        int lbn = lane < nB ? mel_len[32 + lane] : 0;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) { la = max(la, __shfl_xor_sync(FULL, la, o)); lbn = max(lbn, __shfl_xor_sync(FULL, lbn, o)); }
+        int lb = 32;
+        while (lb > 1 && lb * nB > 32) lb >>= 1;
+        if (lane == 0) { sm.na = la; sm.lb = lb; sm.nb = nB ? (lbn + lb - 1) / lb : 0; }
+    }
     __syncthreads();
+    const int na = sm.na, nb = sm.nb, lb = sm.lb;
+    for (int i = tid; i < na * 32; i += kWarpsE * 32) {
+        const int it = i >> 5, l = i & 31;
+        s_w[i] = (l < nA && it < mel_len[l]) ? mel_w[(size_t)l * mel_pitch + it] : 0.f;
+    }
+    for (int i = tid; i < nb * 32; i += kWarpsE * 32) {
+        const int it = i >> 5, l = i & 31, q = l / lb, j = l % lb, m = 32 + q, e = j + lb * it;
+        s_w[na * 32 + i] = (q < nB && e < mel_len[m]) ? mel_w[(size_t)m * mel_pitch + e] : 0.f;
+    }
+    if (tid < 32) {
+        sm.binA[tid] = tid < nA ? mel_start[tid] : 0;
+        const int q = tid / lb;
+        sm.binB[tid] = q < nB ? mel_start[32 + q] + tid % lb : 0;
+    }
+    __syncthreads();
+    const int binA = sm.binA[lane], binB = sm.binB[lane];
 
     const int64_t s0 = pcm_off[u];
     const int64_t n_samples = pcm_off[u + 1] - s0;
     const SampleT* __restrict__ x = pcm + s0;
+    using PairT = typename PairE<SampleT>::type;
+    // two samples per load when every frame of this utterance starts on an even sample (base = hop t - N/2 + s0)
+    const bool pair_ok = ((s0 & 1) == 0) && ((hop & 1) == 0) && ((reinterpret_cast<uintptr_t>(pcm) & (2 * sizeof(SampleT) - 1)) == 0);
     float2* a = sm.buf[warp][0];
     float2* b = sm.buf[warp][1];
     float vmax = 0.f;
@@ -87,9 +132,25 @@ mel_ex_kernel(const SampleT* __restrict__ pcm, const int64_t* __restrict__ pcm_o
     for (int t = t_begin + warp; t < t_end; t += kWarpsE) {
         const int64_t base = (int64_t)hop * t - N / 2;
         // z[n] = (w[2n] y[2n], w[2n+1] y[2n+1])
-        if (!(knock & 1))
-        for (int n = lane; n < M; n += 32)
-            a[n] = make_float2(sm.win[2 * n] * emph(base + 2 * n), sm.win[2 * n + 1] * emph(base + 2 * n + 1));
+        if (pair_ok && base >= 1 && base + N <= n_samples) {
+            // interior frame: one 2-sample load per point; the sample before a lane's pair is the previous lane's second
+            // sample (lane 0: the last lane's of the round before, or one extra load)
+            float carry = sample_f32(x, base - 1);
+#pragma unroll 4
+            for (int n = lane; n < M; n += 32) {
+                const PairT p = __ldg(reinterpret_cast<const PairT*>(x + base + 2 * n));
+                const float c0 = (float)p.x, c1 = (float)p.y;
+                float prev = __shfl_up_sync(FULL, c1, 1);
+                if (lane == 0) prev = carry;
+                carry = __shfl_sync(FULL, c1, 31);
+                const float y0 = preemph == 0.f ? c0 : __fsub_rn(c0, __fmul_rn(preemph, prev));
+                const float y1 = preemph == 0.f ? c1 : __fsub_rn(c1, __fmul_rn(preemph, c0));
+                a[padE(n)] = make_float2(sm.win[2 * n] * y0, sm.win[2 * n + 1] * y1);
+            }
+        } else {
+            for (int n = lane; n < M; n += 32)
+                a[padE(n)] = make_float2(sm.win[2 * n] * emph(base + 2 * n), sm.win[2 * n + 1] * emph(base + 2 * n + 1));
+        }
         __syncwarp();
         // Stockham autosort FFT of M points: radix-4 passes (sub-transform size Ns = 1, 4, 16, ...), one radix-2 pass at
         // the end when log2 M is odd.  Pass: v[r] = in[j + r M/R] W^(r (j mod Ns) M / (Ns R)); out[expand(j) + r Ns] = DFT_R(v)[r]
@@ -98,11 +159,10 @@ mel_ex_kernel(const SampleT* __restrict__ pcm, const int64_t* __restrict__ pcm_o
         int Ns = 1;
 #pragma unroll 1
         for (; Ns * 4 <= M; Ns *= 4) {
-            if (knock & 2) continue;
             const int tw_step = M / (Ns * 4);
             for (int j = lane; j < M / 4; j += 32) {
                 const int k = j & (Ns - 1);
-                float2 v0 = in[j], v1 = in[j + M / 4], v2 = in[j + M / 2], v3 = in[j + 3 * M / 4];
+                float2 v0 = in[padE(j)], v1 = in[padE(j + M / 4)], v2 = in[padE(j + M / 2)], v3 = in[padE(j + 3 * M / 4)];
                 if (Ns > 1) {
                     v1 = cmulE(v1, sm.wm[k * tw_step]);
                     v2 = cmulE(v2, sm.wm[2 * k * tw_step]);
@@ -111,29 +171,28 @@ mel_ex_kernel(const SampleT* __restrict__ pcm, const int64_t* __restrict__ pcm_o
                 const float2 s0_ = make_float2(v0.x + v2.x, v0.y + v2.y), s1_ = make_float2(v0.x - v2.x, v0.y - v2.y);
                 const float2 s2_ = make_float2(v1.x + v3.x, v1.y + v3.y), s3_ = make_float2(v1.x - v3.x, v1.y - v3.y);
                 const int j0 = ((j - k) << 2) + k;
-                out[j0] = make_float2(s0_.x + s2_.x, s0_.y + s2_.y);
-                out[j0 + Ns] = make_float2(s1_.x + s3_.y, s1_.y - s3_.x);          // s1 - i s3
-                out[j0 + 2 * Ns] = make_float2(s0_.x - s2_.x, s0_.y - s2_.y);
-                out[j0 + 3 * Ns] = make_float2(s1_.x - s3_.y, s1_.y + s3_.x);      // s1 + i s3
+                out[padE(j0)] = make_float2(s0_.x + s2_.x, s0_.y + s2_.y);
+                out[padE(j0 + Ns)] = make_float2(s1_.x + s3_.y, s1_.y - s3_.x);          // s1 - i s3
+                out[padE(j0 + 2 * Ns)] = make_float2(s0_.x - s2_.x, s0_.y - s2_.y);
+                out[padE(j0 + 3 * Ns)] = make_float2(s1_.x - s3_.y, s1_.y + s3_.x);      // s1 + i s3
             }
             __syncwarp();
             float2* tmp = in; in = out; out = tmp;
         }
         if (Ns < M) {                                   // one radix-2 pass left (Ns == M / 2)
             for (int j = lane; j < M / 2; j += 32) {
-                const float2 v0 = in[j], v1 = cmulE(in[j + M / 2], sm.wm[j]);          // k = j, step = M / (2 Ns) = 1
-                out[j] = make_float2(v0.x + v1.x, v0.y + v1.y);
-                out[j + Ns] = make_float2(v0.x - v1.x, v0.y - v1.y);
+                const float2 v0 = in[padE(j)], v1 = cmulE(in[padE(j + M / 2)], sm.wm[j]);          // k = j, step = M / (2 Ns) = 1
+                out[padE(j)] = make_float2(v0.x + v1.x, v0.y + v1.y);
+                out[padE(j + Ns)] = make_float2(v0.x - v1.x, v0.y - v1.y);
             }
             __syncwarp();
             float2* tmp = in; in = out; out = tmp;
         }
         // real-input post-pass: X[k] = (E + W_N^k O) / 2 with E = Z[k] + conj Z[M-k], O = -i (Z[k] - conj Z[M-k]);
-        // power spectrum into the other buffer (M + 1 floats)
+        // power spectrum into the other buffer (M + 1 floats, unpadded)
         float* pw = reinterpret_cast<float*>(out);
-        if (!(knock & 4))
         for (int k = lane; k <= M; k += 32) {
-            const float2 A = in[k & (M - 1)], B = in[(M - k) & (M - 1)];
+            const float2 A = in[padE(k & (M - 1))], B = in[padE((M - k) & (M - 1))];
             const float2 e = make_float2(A.x + B.x, A.y - B.y);
             const float2 o = make_float2(A.y + B.y, B.x - A.x);
             const float2 wo = cmulE(sm.wn[k], o);
@@ -141,30 +200,30 @@ mel_ex_kernel(const SampleT* __restrict__ pcm, const int64_t* __restrict__ pcm_o
             pw[k] = 0.25f * (xr * xr + xi * xi);
         }
         __syncwarp();
-        // triangular filters: lane takes filters lane, lane + 32, ...
+        // triangular filters from the lane table (a zero weight may sit on a bin past the filter's end: finite, times 0)
+        float accA = 0.f, accB = 0.f;
+        for (int it = 0; it < na; ++it) accA = fmaf(s_w[it * 32 + lane], pw[min(binA + it, M)], accA);
+        for (int it = 0; it < nb; ++it) accB = fmaf(s_w[(na + it) * 32 + lane], pw[min(binB + lb * it, M)], accB);
+        for (int o = 1; o < lb; o <<= 1) accB += __shfl_xor_sync(FULL, accB, o);
         float* mo = mel_out + (f0 + t) * n_mels;
-        if (!(knock & 8))
-        for (int m = lane; m < n_mels; m += 32) {
-            const int st = mel_start[m], len = mel_len[m];
-            const float* w = mel_w + (size_t)m * mel_pitch;
-            float acc = 0.f;
-            for (int i = 0; i < len; ++i) acc = fmaf(__ldg(w + i), pw[st + i], acc);
-            mo[m] = acc;
-            vmax = fmaxf(vmax, acc);
-        }
+        if (lane < nA) { mo[lane] = accA; vmax = fmaxf(vmax, accA); }
+        if (lane % lb == 0 && lane / lb < nB) { mo[32 + lane / lb] = accB; vmax = fmaxf(vmax, accB); }
         __syncwarp();
     }
     if (utt_max) {
 #pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+        for (int o = 16; o >= 1; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(FULL, vmax, o));
         if (lane == 0) atomicMax(reinterpret_cast<int*>(utt_max + u), __float_as_int(vmax));        // mel >= 0
     }
 }
 
-// thread per frame: log, DCT-II (coefficient table in shared memory)
+// thread per frame: log, DCT-II (coefficient table in shared memory).  NM / NC > 0: compile-time sizes (the mel row and
+// the loops live in registers); 0: run-time sizes (local-memory row).
+template <int NM, int NC>
 __global__ void __launch_bounds__(128)
 ceps_ex_kernel(const float* __restrict__ mel, const float* __restrict__ utt_max, const int64_t* __restrict__ frm_off, int n_utt,
-               int64_t total_frames, const float* __restrict__ dct, int n_mels, int n_ceps, int log_mode, float* __restrict__ ceps) {
+               int64_t total_frames, const float* __restrict__ dct, int n_mels_rt, int n_ceps_rt, int log_mode, float* __restrict__ ceps) {
+    const int n_mels = NM > 0 ? NM : n_mels_rt, n_ceps = NC > 0 ? NC : n_ceps_rt;
     __shared__ float s_dct[kMaxCepsE * kMaxMelsE];
     for (int i = threadIdx.x; i < n_ceps * n_mels; i += blockDim.x) s_dct[i] = dct[i];
     __syncthreads();
@@ -176,18 +235,36 @@ ceps_ex_kernel(const float* __restrict__ mel, const float* __restrict__ utt_max,
         while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (frm_off[mid] <= f) lo = mid; else hi = mid; }
         ref_db = 10.0f * log10f(fmaxf(1e-10f, utt_max[lo]));
     }
-    float lm[kMaxMelsE];
+    float lm[NM > 0 ? NM : kMaxMelsE];
     const float* row = mel + f * n_mels;
+    if (NM > 0) {
+#pragma unroll
+        for (int m = 0; m < NM; ++m) {
+            const float e = fmaxf(1e-10f, __ldg(row + m));
+            lm[m] = log_mode == LOE_LOG_DB ? fmaxf(10.0f * log10f(e) - ref_db, -80.0f) : logf(e);
+        }
+    } else {
 #pragma unroll 1
-    for (int m = 0; m < n_mels; ++m) {
-        const float e = fmaxf(1e-10f, __ldg(row + m));
-        lm[m] = log_mode == LOE_LOG_DB ? fmaxf(10.0f * log10f(e) - ref_db, -80.0f) : logf(e);
+        for (int m = 0; m < n_mels; ++m) {
+            const float e = fmaxf(1e-10f, __ldg(row + m));
+            lm[m] = log_mode == LOE_LOG_DB ? fmaxf(10.0f * log10f(e) - ref_db, -80.0f) : logf(e);
+        }
     }
     float* o = ceps + f * n_ceps;
-    for (int k = 0; k < n_ceps; ++k) {
-        float acc = 0.f;
-        for (int m = 0; m < n_mels; ++m) acc = fmaf(s_dct[k * n_mels + m], lm[m], acc);
-        o[k] = acc;
+    if (NM > 0) {
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+            float acc = 0.f;
+#pragma unroll
+            for (int m = 0; m < NM; ++m) acc = fmaf(s_dct[k * NM + m], lm[m], acc);
+            o[k] = acc;
+        }
+    } else {
+        for (int k = 0; k < n_ceps; ++k) {
+            float acc = 0.f;
+            for (int m = 0; m < n_mels; ++m) acc = fmaf(s_dct[k * n_mels + m], lm[m], acc);
+            o[k] = acc;
+        }
     }
 }
 
@@ -250,17 +327,24 @@ feat_ex_kernel(const float* __restrict__ ceps, const float* __restrict__ stat, c
         for (int k = 0; k < n_ceps; ++k) o[k] = c[k];
     }
     const int cc = min(max(t, 4), T - 5);
-    for (int k = 0; k < n_ceps; ++k) {
-        float d1 = 0.f, d2 = 0.f;
+    float d1[kMaxCepsE], d2[kMaxCepsE];
 #pragma unroll
-        for (int q = -4; q <= 4; ++q) {
-            const float cv = __ldg(ceps + (f0 + cc + q) * n_ceps + k);
-            d1 = fmaf((float)q * (1.0f / 60.0f), cv, d1);
-            d2 = fmaf((float)(3 * q * q - 20) * (1.0f / 462.0f), cv, d2);
-        }
-        o[n_ceps + k] = d1;
-        o[2 * n_ceps + k] = d2;
+    for (int k = 0; k < kMaxCepsE; ++k) { d1[k] = 0.f; d2[k] = 0.f; }
+#pragma unroll
+    for (int q = -4; q <= 4; ++q) {                   // neighbour-major: every row of 13 coefficients is read as a run
+        const float* nrow = ceps + (f0 + cc + q) * n_ceps;
+        const float w1 = (float)q * (1.0f / 60.0f), w2 = (float)(3 * q * q - 20) * (1.0f / 462.0f);
+#pragma unroll
+        for (int k = 0; k < kMaxCepsE; ++k)
+            if (k < n_ceps) {
+                const float cv = __ldg(nrow + k);
+                d1[k] = fmaf(w1, cv, d1[k]);
+                d2[k] = fmaf(w2, cv, d2[k]);
+            }
     }
+#pragma unroll
+    for (int k = 0; k < kMaxCepsE; ++k)
+        if (k < n_ceps) { o[n_ceps + k] = d1[k]; o[2 * n_ceps + k] = d2[k]; }
 }
 
 template <typename SampleT, int LOG2N>
@@ -269,11 +353,12 @@ static int launch_mel_ex(const void* pcm_dev, const int64_t* pcm_off_dev, const 
                          const int32_t* mel_len_dev, const float* mel_w_dev, int mel_pitch, float* mel_ws_dev, float* utt_max_dev,
                          cudaStream_t s) {
     using S = SmemE<LOG2N>;
-    LOE_CUDA(cudaFuncSetAttribute(mel_ex_kernel<SampleT, LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S)));
+    const size_t smem = sizeof(S) + sizeof(float) * 64 * (size_t)mel_pitch;          // + lane table: (na + nb) * 32 <= 2 * pitch * 32
+    LOE_CUDA(cudaFuncSetAttribute(mel_ex_kernel<SampleT, LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)n_utt, (unsigned)((max_frames + chunk - 1) / chunk));
-    mel_ex_kernel<SampleT, LOG2N><<<grid, kWarpsE * 32, sizeof(S), s>>>(
+    mel_ex_kernel<SampleT, LOG2N><<<grid, kWarpsE * 32, smem, s>>>(
         (const SampleT*)pcm_dev, pcm_off_dev, frm_off_dev, window_dev, cfg->hop, cfg->preemph, mel_start_dev, mel_len_dev, mel_w_dev,
-        mel_pitch, cfg->n_mels, chunk, mel_ws_dev, cfg->log_mode == LOE_LOG_DB ? utt_max_dev : nullptr, getenv("LOE_MEL_EX_KNOCK") ? atoi(getenv("LOE_MEL_EX_KNOCK")) : 0);
+        mel_pitch, cfg->n_mels, chunk, mel_ws_dev, cfg->log_mode == LOE_LOG_DB ? utt_max_dev : nullptr);
     LOE_LAUNCH_CHECK("mel_ex_kernel");
     return LOE_OK;
 }
@@ -299,7 +384,7 @@ extern "C" int loe_mfcc_ex_dev(const void* pcm_dev, int pcm_format, const int64_
         return LOE_ERR_UNSUPPORTED;
     }
     if (cfg->hop <= 0 || cfg->n_mels <= 0 || cfg->n_mels > kMaxMelsE || cfg->n_ceps <= 0 || cfg->n_ceps > kMaxCepsE ||
-        cfg->n_ceps > cfg->n_mels || mel_pitch <= 0) {
+        cfg->n_ceps > cfg->n_mels || mel_pitch <= 0 || mel_pitch > 256) {
         set_error("bad front-end sizes (hop %d, n_mels %d <= %d, n_ceps %d <= %d)", cfg->hop, cfg->n_mels, kMaxMelsE, cfg->n_ceps, kMaxCepsE);
         return LOE_ERR_VALUE;
     }
@@ -328,8 +413,12 @@ extern "C" int loe_mfcc_ex_dev(const void* pcm_dev, int pcm_format, const int64_
 #undef LOE_EX
     if (st != LOE_OK) return st;
     const unsigned blocks = (unsigned)((total_frames + 127) / 128);
-    ceps_ex_kernel<<<blocks, 128, 0, s>>>(mel_ws_dev, utt_stat_dev, frm_off_dev, n_utt, total_frames, dct_dev, cfg->n_mels, cfg->n_ceps,
-                                          cfg->log_mode, ceps_ws_dev);
+    if (cfg->n_mels == 40 && cfg->n_ceps == 13)
+        ceps_ex_kernel<40, 13><<<blocks, 128, 0, s>>>(mel_ws_dev, utt_stat_dev, frm_off_dev, n_utt, total_frames, dct_dev, 40, 13,
+                                                      cfg->log_mode, ceps_ws_dev);
+    else
+        ceps_ex_kernel<0, 0><<<blocks, 128, 0, s>>>(mel_ws_dev, utt_stat_dev, frm_off_dev, n_utt, total_frames, dct_dev, cfg->n_mels,
+                                                    cfg->n_ceps, cfg->log_mode, ceps_ws_dev);
     LOE_LAUNCH_CHECK("ceps_ex_kernel");
     if (cfg->norm_mode == LOE_NORM_CMN || cfg->norm_mode == LOE_NORM_CMVN) {
         cmn_ex_kernel<<<(unsigned)n_utt, 128, 0, s>>>(ceps_ws_dev, frm_off_dev, cfg->n_ceps, utt_stat_dev);
