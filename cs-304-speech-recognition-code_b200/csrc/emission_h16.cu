@@ -416,6 +416,48 @@ emission_h16_multi_kernel(const float* __restrict__ feat, const uint8_t* __restr
                       out + begin * ld_out + seg_col[seg], ld_out, use_bulk, 1, min(ctas_per_seg, n_mtiles), g);
 }
 
+// The multi-model launch from PRE-SPLIT images (training: the features never change, so their A operand is built once by
+// h16_image_kernel and every iteration only bulk-copies it).  Segment i owns the image tiles from seg_img_tile[i]
+// (ceil(frames / 128) of them, rows beyond the segment zero) and the rows of inv2 from 128 * seg_img_tile[i].
+__global__ void __launch_bounds__(kThreads, 1)
+emission_h16_multi_img_kernel(const uint8_t* __restrict__ a_img, const float* __restrict__ inv2, const uint8_t* __restrict__ b_packed,
+                              const float* __restrict__ cst_pad, const int64_t* __restrict__ seg_begin, const int64_t* __restrict__ seg_end,
+                              const int32_t* __restrict__ seg_img_tile, const int32_t* __restrict__ seg_tile,
+                              const int32_t* __restrict__ seg_states, const int32_t* __restrict__ seg_col, const int32_t* __restrict__ active,
+                              float* __restrict__ out, int ld_out, int ctas_per_seg) {
+    const int seg = blockIdx.x / ctas_per_seg, g = blockIdx.x % ctas_per_seg;
+    if (active && active[seg] != 1) return;
+    const int64_t begin = seg_begin[seg], n = seg_end[seg] - begin;
+    const int n_mtiles = (int)((n + kTileM - 1) / kTileM);
+    if (n <= 0 || g >= n_mtiles) return;
+    const size_t t0 = (size_t)seg_img_tile[seg];
+    emission_h16_body<true>(reinterpret_cast<const float*>(a_img + t0 * kImgTileBytes), inv2 + t0 * kTileM, n,
+                            b_packed + (size_t)seg_tile[seg] * kBBytes, cst_pad + seg_tile[seg] * kStatesPerTile, seg_states[seg],
+                            out + begin * ld_out + seg_col[seg], ld_out, 1, 1, min(ctas_per_seg, n_mtiles), g);
+}
+
+// float32 features -> pre-split A image, one thread per image row (segment-relative tiles; rows past a segment's end: zero)
+__global__ void __launch_bounds__(128)
+h16_image_kernel(const float* __restrict__ feat, const int64_t* __restrict__ seg_begin, const int64_t* __restrict__ seg_end,
+                 const int32_t* __restrict__ seg_img_tile, int n_seg, uint8_t* __restrict__ a_img, float* __restrict__ inv2) {
+    const int tile = blockIdx.x, row = threadIdx.x;
+    int lo = 0, hi = n_seg;                              // segment of this tile: last one with seg_img_tile <= tile
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (seg_img_tile[mid] <= tile) lo = mid; else hi = mid; }
+    const int64_t local = (int64_t)(tile - seg_img_tile[lo]) * kTileM + row;
+    const int64_t f = seg_begin[lo] + local;
+    uint8_t* a_row = a_img + (size_t)tile * kImgTileBytes + (size_t)row * 16;
+    if (f < seg_end[lo]) {
+        float v[kDim];
+#pragma unroll
+        for (int c = 0; c < kDim; ++c) v[c] = __ldg(feat + f * kDim + c);
+        inv2[(size_t)tile * kTileM + row] = stage_row(v, a_row);
+    } else {
+#pragma unroll
+        for (int c = 0; c < 2 * kStageChunksPerPart; ++c) *reinterpret_cast<uint4*>(a_row + c * kStageLbo) = make_uint4(0, 0, 0, 0);
+        inv2[(size_t)tile * kTileM + row] = 1.0f;
+    }
+}
+
 static_assert(sizeof(Smem) <= 227 * 1024, "shared memory of the emission kernel");
 
 }  // namespace h16
@@ -513,6 +555,49 @@ extern "C" int loe_emission_h16_dev(const float* feat_dev, int64_t n_frames, int
     emission_h16_kernel<<<grid, kThreads, sizeof(Smem), s>>>(feat_dev, n_frames, static_cast<const uint8_t*>(b_packed_dev), cst_pad_dev,
                                                              n_states, out_dev, ld_out, use_bulk, g_full, g_last);
     LOE_LAUNCH_CHECK("emission_h16_kernel");
+    return LOE_OK;
+}
+
+extern "C" int loe_h16_image_dev(const float* feat_dev, int dim, int n_seg, const int64_t* seg_begin_dev, const int64_t* seg_end_dev,
+                                 const int32_t* seg_img_tile_dev, int n_img_tiles, void* a_img_dev, float* inv2_dev, void* stream) {
+    using namespace loe;
+    using namespace loe::h16;
+    if (n_seg <= 0 || n_img_tiles <= 0) return LOE_OK;
+    if (dim != kDim) { set_error("tensor-core emission path is built for dim == 39 (got %d)", dim); return LOE_ERR_UNSUPPORTED; }
+    if ((reinterpret_cast<uintptr_t>(a_img_dev) & 15) != 0) { set_error("a_img_dev must be 16-byte aligned"); return LOE_ERR_VALUE; }
+    h16_image_kernel<<<(unsigned)n_img_tiles, kTileM, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        feat_dev, seg_begin_dev, seg_end_dev, seg_img_tile_dev, n_seg, static_cast<uint8_t*>(a_img_dev), inv2_dev);
+    LOE_LAUNCH_CHECK("h16_image_kernel");
+    return LOE_OK;
+}
+
+extern "C" int loe_emission_h16_multi_img_dev(const void* a_img_dev, const float* inv2_dev, const void* b_packed_dev, const float* cst_pad_dev,
+                                              int n_seg, const int64_t* seg_begin_dev, const int64_t* seg_end_dev,
+                                              const int32_t* seg_img_tile_dev, const int32_t* seg_tile_dev, const int32_t* seg_states_dev,
+                                              const int32_t* seg_col_dev, const int32_t* active_dev, int max_states, float* out_dev,
+                                              int ld_out, void* stream) {
+    using namespace loe;
+    using namespace loe::h16;
+    if (n_seg <= 0) return LOE_OK;
+    if (max_states > kHalves * kStatesPerTile) {
+        set_error("a segment of the multi-model launch holds at most %d states (got %d)", kHalves * kStatesPerTile, max_states);
+        return LOE_ERR_UNSUPPORTED;
+    }
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    int dev = 0, sms = 0;
+    LOE_CUDA(cudaGetDevice(&dev));
+    LOE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    static bool attr_done[64] = {false};
+    if (dev < 64 && !attr_done[dev]) {
+        LOE_CUDA(cudaFuncSetAttribute(emission_h16_multi_img_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+        attr_done[dev] = true;
+    }
+    int per_seg = sms / n_seg;
+    if (per_seg < 1) per_seg = 1;
+    emission_h16_multi_img_kernel<<<(unsigned)(n_seg * per_seg), kThreads, sizeof(Smem), s>>>(
+        static_cast<const uint8_t*>(a_img_dev), inv2_dev, static_cast<const uint8_t*>(b_packed_dev), cst_pad_dev, seg_begin_dev, seg_end_dev,
+        seg_img_tile_dev, seg_tile_dev, seg_states_dev, seg_col_dev, active_dev, out_dev, ld_out, per_seg);
+    LOE_LAUNCH_CHECK("emission_h16_multi_img_kernel");
     return LOE_OK;
 }
 

@@ -45,6 +45,9 @@ SIGNATURES = {
     "loe_emission_h16_img_dev": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "loe_emission_h16_multi_dev": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                            c_void_p, c_int, c_void_p, c_int, c_void_p]),
+    "loe_h16_image_dev": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "loe_emission_h16_multi_img_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                               c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "loe_emission_gmm_tile_bytes": (c_int, []),
     "loe_emission_gmm_tiles": (c_int, [c_int, c_int]),
     "loe_emission_gmm_dev": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),

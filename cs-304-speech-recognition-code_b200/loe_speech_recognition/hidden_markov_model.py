@@ -398,6 +398,15 @@ class HiddenMarkovModelTrainable(HiddenMarkovModel):
         if multi_ok:
             seg_begin = eng._to_dev(np.array([frame_range[l][0] for l in labels], dtype=np.int64))
             seg_end = eng._to_dev(np.array([frame_range[l][1] for l in labels], dtype=np.int64))
+            # the features never change: their pre-split tensor-core operand is built once, per word on tile boundaries
+            seg_tiles = np.array([(frame_range[l][1] - frame_range[l][0] + 127) // 128 for l in labels], dtype=np.int64)
+            n_img_tiles = int(seg_tiles.sum())
+            seg_img_tile = eng._to_dev(np.concatenate(([0], np.cumsum(seg_tiles)[:-1])).astype(np.int32))
+            a_img = eng.empty((max(n_img_tiles, 1) * 20480,), torch.uint8)
+            inv2 = eng.empty((max(n_img_tiles, 1) * 128,), torch.float32)
+            _native.check(eng.lib.loe_h16_image_dev(batch.feat.data_ptr(), D, W, seg_begin.data_ptr(), seg_end.data_ptr(),
+                                                    seg_img_tile.data_ptr(), n_img_tiles, a_img.data_ptr(), inv2.data_ptr(), eng._stream()))
+            eng.launches += 1
         status_host = [torch.empty(W, dtype=torch.int32).pin_memory() for _ in range(2)]
         events = [None, None]
         maybe_active = np.ones(W, dtype=bool)          # host view of the active set, one iteration behind the device
@@ -437,10 +446,10 @@ class HiddenMarkovModelTrainable(HiddenMarkovModel):
             mark()
             if feats:
                 if multi_ok:            # all word models in one launch; converged ones are skipped on the device
-                    _native.check(eng.lib.loe_emission_h16_multi_dev(batch.feat.data_ptr(), D, b_h16.data_ptr(), cst_pad.data_ptr(), W,
-                                                                     seg_begin.data_ptr(), seg_end.data_ptr(), word_tile.data_ptr(),
-                                                                     word_n.data_ptr(), word_first.data_ptr(), active.data_ptr(),
-                                                                     int(sizes.max()), scores.data_ptr(), G, eng._stream()))
+                    _native.check(eng.lib.loe_emission_h16_multi_img_dev(a_img.data_ptr(), inv2.data_ptr(), b_h16.data_ptr(), cst_pad.data_ptr(), W,
+                                                                         seg_begin.data_ptr(), seg_end.data_ptr(), seg_img_tile.data_ptr(),
+                                                                         word_tile.data_ptr(), word_n.data_ptr(), word_first.data_ptr(),
+                                                                         active.data_ptr(), int(sizes.max()), scores.data_ptr(), G, eng._stream()))
                     eng.launches += 1
                 else:
                     for i, l in enumerate(labels):

@@ -206,6 +206,18 @@ int loe_emission_h16_multi_dev(const float* feat_dev, int dim, const void* b_pac
                                const int32_t* seg_states_dev, const int32_t* seg_col_dev, const int32_t* active_dev,
                                int max_states, float* out_dev, int ld_out, void* stream);
 
+/* The multi-model launch from pre-split images (training: the features do not change between iterations, so their A
+ * operand is built ONCE by loe_h16_image_dev and every iteration bulk-copies it).  Segment i owns ceil(frames_i / 128)
+ * image tiles from tile seg_img_tile[i] (rows past its end are zero) and the inv2 rows from 128 * seg_img_tile[i];
+ * n_img_tiles = sum of the segments' tiles; a_img_dev: n_img_tiles * 20 480 bytes, inv2_dev: n_img_tiles * 128 floats. */
+int loe_h16_image_dev(const float* feat_dev, int dim, int n_seg, const int64_t* seg_begin_dev, const int64_t* seg_end_dev,
+                      const int32_t* seg_img_tile_dev, int n_img_tiles, void* a_img_dev, float* inv2_dev, void* stream);
+int loe_emission_h16_multi_img_dev(const void* a_img_dev, const float* inv2_dev, const void* b_packed_dev, const float* cst_pad_dev,
+                                   int n_seg, const int64_t* seg_begin_dev, const int64_t* seg_end_dev,
+                                   const int32_t* seg_img_tile_dev, const int32_t* seg_tile_dev, const int32_t* seg_states_dev,
+                                   const int32_t* seg_col_dev, const int32_t* active_dev, int max_states, float* out_dev,
+                                   int ld_out, void* stream);
+
 /* --------------------------------------------------------------------------------------
  * Diagonal-covariance Gaussian-mixture emission scoring (csrc/emission_gmm.cu; BASELINE.json north_star kernel (2),
  * configs[0] extension set and configs[4]).  The live reference scores one full-covariance Gaussian per state

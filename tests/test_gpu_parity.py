@@ -268,6 +268,54 @@ def test_emission_from_presplit_image_is_bit_identical(eng, golden):
     assert torch.equal(eng.emission_image(image2, F, gp5), eng.emission(feat, gp5, "h16"))
 
 
+def test_multi_model_emission_launches_match_per_model(eng, golden):
+    """Training scores every word model on its own frames: loe_emission_h16_multi_dev (one launch, float32 features) and
+    loe_h16_image_dev + loe_emission_h16_multi_img_dev (one launch, pre-split operand built once) must write exactly what one
+    loe_emission_h16_dev launch per model writes; segments whose active flag is not 1 are left untouched."""
+    from loe_speech_recognition import _native
+    from loe_speech_recognition._engine import host_gauss_arrays, pack_h16_image
+    torch = eng.torch
+    words = ("1", "S", "Z", "7")
+    feats = [np.concatenate([golden[f"train_feat_{w if w != 'S' else '1'}_{i}"] for i in range(6)]) for w in words]
+    feats[1] = feats[1][:131]                                             # a segment that is not a multiple of the tile
+    begin = np.concatenate(([0], np.cumsum([len(f) for f in feats])[:-1])).astype(np.int64)
+    end = (begin + np.array([len(f) for f in feats])).astype(np.int64)
+    x = eng._to_dev(np.concatenate(feats).astype(np.float32))
+    sizes = np.array([N_STATES[w] for w in words], np.int32)
+    first = np.concatenate(([0], np.cumsum(sizes)[:-1])).astype(np.int32)
+    G, W = int(sizes.sum()), len(words)
+    tile_halves = eng.lib.loe_emission_h16_tile_bytes() // 2
+    img = np.zeros(W * tile_halves, np.float16); cst = np.zeros(W * 6, np.float32)
+    for i, w in enumerate(words):
+        means, us, c = host_gauss_arrays(trained_word_model(golden, w)._multivariate_normals)
+        img[i * tile_halves:(i + 1) * tile_halves] = pack_h16_image(means, us, c)
+        cst[i * 6:i * 6 + len(c)] = c.astype(np.float32)
+    b_h16, cst_pad = eng._to_dev(img), eng._to_dev(cst)
+    want = torch.full((int(end[-1]), G), -5.0, dtype=torch.float32, device=eng.device)
+    for i in range(W):
+        if i != 2:
+            eng.emission_h16_into(x[begin[i]:end[i]], b_h16, cst_pad, i, int(sizes[i]), want[begin[i]:end[i]], int(first[i]))
+    sb, se = eng._to_dev(begin), eng._to_dev(end)
+    st, sn, sc = eng._to_dev(np.arange(W, dtype=np.int32)), eng._to_dev(sizes), eng._to_dev(first)
+    active = eng._to_dev(np.array([1, 1, 0, 1], np.int32))                # the third model has converged: skipped
+    got = torch.full_like(want, -5.0)
+    _native.check(eng.lib.loe_emission_h16_multi_dev(x.data_ptr(), 39, b_h16.data_ptr(), cst_pad.data_ptr(), W, sb.data_ptr(), se.data_ptr(),
+                                                     st.data_ptr(), sn.data_ptr(), sc.data_ptr(), active.data_ptr(), 5, got.data_ptr(), G, eng._stream()))
+    assert torch.equal(got, want)
+    tiles = (end - begin + 127) // 128
+    img_tile = eng._to_dev(np.concatenate(([0], np.cumsum(tiles)[:-1])).astype(np.int32))
+    n_img = int(tiles.sum())
+    a_img = torch.full((n_img * 20480,), 0x77, dtype=torch.uint8, device=eng.device); inv2 = torch.full((n_img * 128,), -1.0, device=eng.device)
+    _native.check(eng.lib.loe_h16_image_dev(x.data_ptr(), 39, W, sb.data_ptr(), se.data_ptr(), img_tile.data_ptr(), n_img, a_img.data_ptr(),
+                                            inv2.data_ptr(), eng._stream()))
+    got2 = torch.full_like(want, -5.0)
+    _native.check(eng.lib.loe_emission_h16_multi_img_dev(a_img.data_ptr(), inv2.data_ptr(), b_h16.data_ptr(), cst_pad.data_ptr(), W, sb.data_ptr(),
+                                                         se.data_ptr(), img_tile.data_ptr(), st.data_ptr(), sn.data_ptr(), sc.data_ptr(),
+                                                         active.data_ptr(), 5, got2.data_ptr(), G, eng._stream()))
+    assert torch.equal(got2, want)
+    assert bool((inv2 > 0).all())
+
+
 def test_emission_h16_range_handling(eng, golden):
     """binary16 tops out at 65504: feature rows of any magnitude are rescaled inside the kernel, a model
     whose whitening matrix leaves the range gets no FP16 image and runs on the TF32 kernel."""
