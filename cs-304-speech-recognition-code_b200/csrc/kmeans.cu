@@ -79,6 +79,54 @@ __global__ void align_kernel(const int8_t* __restrict__ path, const int64_t* __r
     }
 }
 
+// Isolated training (remux == 0): one WARP per utterance, lanes over the frames.  The serial walk above reduces to two
+// prefix conditions -- a frame is credited while every frame so far is in range and the state sequence has not decreased
+// -- and the transition counts to one integer atomic per DISTINCT (from, to) pair of 32 consecutive frames (lanes with the
+// same pair elect a leader), instead of one per frame on a few dozen hot counters.
+__global__ void __launch_bounds__(128)
+align_warp_kernel(const int8_t* __restrict__ path, const int64_t* __restrict__ frm_off, int n_utt,
+                  const int32_t* __restrict__ tr_off, const int32_t* __restrict__ col, const int32_t* __restrict__ utt_tr, int n_glob,
+                  uint16_t* __restrict__ bucket, int32_t* __restrict__ counts) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const int u = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (u >= n_utt) return;
+    const int64_t f0 = frm_off[u];
+    const int T = (int)(frm_off[u + 1] - f0);
+    const int tr = utt_tr ? utt_tr[u] : 0;
+    const int p0 = tr_off[tr];
+    const int P = tr_off[tr + 1] - p0;
+    const int gbase = col[p0];
+    if (T <= 0) return;
+    const int first = (int)path[f0];
+    if (first < 0 || first >= P) {  // T == 1 gives path [-1]: nothing is credited, nothing counted (like the serial walk)
+        for (int t = lane; t < T; t += 32) bucket[f0 + t] = (uint16_t)0xFFFF;
+        return;
+    }
+    bool ok = true;                 // every frame before this round was credited
+    int carry = 0;                  // local state of the last frame of the previous round ("last" starts at 0)
+    bool carry_in = true;           // ... and whether it was in range (for the transition count of the round's first frame)
+    for (int tb = 0; tb < T; tb += 32) {
+        const int t = tb + lane;
+        const int local = t < T ? (int)path[f0 + t] : 0;
+        const bool in_range = t < T && local >= 0 && local < P;
+        int prev = __shfl_up_sync(FULL, local, 1);
+        bool prev_in = __shfl_up_sync(FULL, (int)in_range, 1) != 0;
+        if (lane == 0) { prev = carry; prev_in = carry_in; }
+        const bool good = in_range && local >= ((t == 0) ? 0 : prev);
+        const unsigned bad = __ballot_sync(FULL, t < T && !good);
+        const bool credited = ok && t < T && (bad == 0 || lane < __ffs(bad) - 1);
+        if (t < T) bucket[f0 + t] = credited ? (uint16_t)(gbase + local) : (uint16_t)0xFFFF;
+        ok = ok && bad == 0;
+        // transition (prev -> local) for t >= 1 with both ends in range
+        const bool count = t < T && t > 0 && in_range && prev_in;
+        const int key = count ? prev * P + local : -1;
+        const unsigned same = __match_any_sync(FULL, key);
+        if (count && lane == __ffs(same) - 1) atomicAdd(counts + (size_t)(gbase + prev) * n_glob + (gbase + local), __popc(same));
+        carry = __shfl_sync(FULL, local, 31);
+        carry_in = __shfl_sync(FULL, (int)in_range, 31) != 0;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // Outer-product accumulation, register tiled.  The augmented frame y = [x - shift, 1] has K = D + 1 <= 40
 // entries; sum y y^T is cut into 4 x 4 tiles of a 10 x 10 tile grid and only the 55 tiles on or above the
@@ -510,6 +558,12 @@ extern "C" int loe_align_dev(const int8_t* path_dev, const int64_t* frm_off_dev,
     if (n_utt <= 0) return LOE_OK;
     if (n_glob >= 0xFFFF) { set_error("too many global states"); return LOE_ERR_VALUE; }
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (!remux && !getenv("LOE_B200_ALIGN_SERIAL")) {
+        align_warp_kernel<<<(unsigned)((n_utt + 3) / 4), 128, 0, s>>>(path_dev, frm_off_dev, n_utt, tr_off_dev, col_dev, utt_tr_dev, n_glob,
+                                                                     bucket_dev, counts_dev);
+        LOE_LAUNCH_CHECK("align_warp_kernel");
+        return LOE_OK;
+    }
     align_kernel<<<(unsigned)((n_utt + 127) / 128), 128, 0, s>>>(path_dev, frm_off_dev, n_utt, tr_off_dev, col_dev, word_dev,
                                                                 word_lo_dev, utt_tr_dev, remux, n_glob, bucket_dev, counts_dev);
     LOE_LAUNCH_CHECK("align_kernel");
