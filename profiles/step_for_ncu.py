@@ -1,7 +1,7 @@
 """The device-resident decode step of bench.py (BASELINE.json configs[1], 10 000 utterances) and nothing else:
 the command the `ncu --set full` captures under profiles/ are taken from.
 
-    ncu --set full --clock-control none --import-source on -k regex:"mfcc|emission|viterbi" -s 4 -c 4 \
+    ncu --set full --clock-control none --import-source on -k regex:"mfcc|emission|viterbi" -s 5 -c 4 \
         -o gpurun_out/prof python profiles/step_for_ncu.py
 """
 import os
@@ -39,9 +39,10 @@ pcm = torch.from_numpy(np.concatenate(utts).astype(np.float32)).to(eng.device)
 po, fo = eng._to_dev(pcm_off), eng._to_dev(frm_off)
 gp, tp = inf._packs()
 skip = inf._model_boundaries._labels.index("S")
+image = eng.image_buffers(F)           # the decode hand-off of round 2: the cepstrum kernel writes the emission kernel's A operand
 for _ in range(2):
-    feat = eng.mfcc_device(pcm, po, fo, n, F, int(frames.max()), int(frames.min()), 16000)
-    scores = eng.emission(feat, gp, "auto")
+    eng.mfcc_device(pcm, po, fo, n, F, int(frames.max()), int(frames.min()), 16000, image=image, want_feat=False)
+    scores = eng.emission_image(image, F, gp)
     eng.viterbi(scores, fo, n, int(frames.max()), F, tp, loop=True, penalty=float(bench.PENALTY), penalty_f64=False,
                 want_end_scores=False, labels=(skip, 32))
 torch.cuda.synchronize()
