@@ -223,7 +223,9 @@ def train_block(args, eng, world, rank, dist):
         "gpu_launches": launches,
         "roofline": {"kernel": "align_kernel + bucket sort + accum2_kernel + reduce2_kernel (the statistics phase)", "bound": "hbm",
                      "achieved": stats_bytes / (phases["align_stats"] * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
-                     "frac": stats_bytes / (phases["align_stats"] * 1e-3) / 1e9 / hbm, "traffic": None,
+                     "frac": stats_bytes / (phases["align_stats"] * 1e-3) / 1e9 / hbm,
+                     "traffic": ncu_traffic().get("accum2_kernel", {}).get("bytes") if (world == 1 and args.train_utts == 100001) else None,
+                     "traffic_source": ncu_traffic().get("accum2_kernel", {}).get("capture"),
                      "algorithmic": f"{stats_bytes} bytes per rank and iteration ((4 x 39 + 2 + 1) B per frame)",
                      "fp64_gflops": 2 * 820 * frames_rank / (phases["align_stats"] * 1e-3) / 1e9,
                      "note": "sum [x,1][x,1]^T is 820 float64 FMAs per frame: the FP64 pipe (64 FMA/clk/SM, ~36 TFLOP/s at 1.9 GHz), "
@@ -492,7 +494,7 @@ def impl_b200(args):
         # mel energies in; out: the float32 features (156 B / frame) or, on the 3xFP16 path, the pre-split operand image
         # (160 B / frame) + 4 B row scale -- counted as the 156 B of features either way
         "mfcc_ceps_kernel": {"bound": "hbm", "alg": (160 + 156) * F, "ms": stage_ms["mfcc_ceps"]},
-        {"tc": "emission_tc_kernel", "h16": "emission_h16_kernel"}.get(precision, "emission_simt_kernel"):
+        {"tc": "emission_tc_kernel", "h16": "emission_h16_img_kernel"}.get(precision, "emission_simt_kernel"):
             {"bound": "tensor", "alg": FLOPS_PER_FRAME * F, "ms": stage_ms["emission"]},
         "viterbi_warp_kernel": {"bound": "hbm", "alg": (4 * 58 + 1) * F, "ms": stage_ms["viterbi"]},
     }
@@ -525,8 +527,8 @@ def impl_b200(args):
                 "issued_over_useful": issued / (FLOPS_PER_FRAME * F),
                 "note": "the kernel runs power-capped (ncu: 1.6 GHz SM clock); `achieved` counts the useful flops once, the "
                         "tensor pipe is issued 2.2x that (3-way operand split, triangular image at 65 % of dense, padding)"}
-        all_roof["emission_h16_kernel"]["issued"] = note
-        if dominant == "emission_h16_kernel":
+        all_roof["emission_h16_img_kernel"]["issued"] = note
+        if dominant == "emission_h16_img_kernel":
             roofline["issued"] = note
     if dominant == "mfcc_mel_kernel":
         roofline["note"] = ("nominally HBM-bound (796 B/frame) but limited by instruction issue and shared-memory wavefronts: ~320 warp "

@@ -128,48 +128,41 @@ mstep_cov_kernel(const double* __restrict__ stats, const int32_t* __restrict__ c
     for (int j = tid; j < n_glob; j += blockDim.x) counts_applied[(size_t)g * n_glob + j] = counts[(size_t)g * n_glob + j];
     __syncthreads();
     const bool bad_input = s_bad != 0;
-    // right-looking Cholesky of the reversed matrix, in place (lower triangle), and M^-1 by forward substitution: both in
-    // warp 0 alone (warp-level barriers: 39 dependent steps on a 39 x 39 matrix are latency, not work; three block barriers
-    // per step cost more than the arithmetic)
-    __shared__ double s_logdet;
-    if (tid < 32) {
-        const int lane = tid;
-        double log_pdet = 0.0, max_diag = 0.0;
-        for (int i = 0; i < kD; ++i) max_diag = fmax(max_diag, fabs(a[i][i]));
-        bool bad = bad_input;
-        for (int c = 0; c < kD && !bad; ++c) {
-            const double d = a[c][c];
-            if (!(d > 1e-7 * max_diag) || !isfinite(d)) { bad = true; break; }     // uniform: every lane reads the same d
-            const double l = sqrt(d);
-            log_pdet += 2.0 * log(l);
-            __syncwarp();
-            for (int i = c + lane; i < kD; i += 32) a[i][c] = (i == c) ? l : a[i][c] / l;
-            __syncwarp();
-            const int m = kD - 1 - c;             // trailing block (c+1 .. 38)^2, lower triangle
-            for (int e = lane; e < m * m; e += 32) {
-                const int i = c + 1 + e / m, j = c + 1 + e % m;
-                if (j <= i) a[i][j] -= a[i][c] * a[j][c];
-            }
-            __syncwarp();
+    // right-looking Cholesky of the reversed matrix, in place (lower triangle)
+    double log_pdet = 0.0;
+    double max_diag = 0.0;
+    for (int i = 0; i < kD; ++i) max_diag = fmax(max_diag, fabs(a[i][i]));
+    for (int c = 0; c < kD && !bad_input; ++c) {
+        const double d = a[c][c];
+        if (!(d > 1e-7 * max_diag) || !isfinite(d)) { if (tid == 0) s_bad = 1; break; }     // uniform: every thread reads the same d
+        const double l = sqrt(d);
+        log_pdet += 2.0 * log(l);
+        __syncthreads();
+        for (int i = c + tid; i < kD; i += blockDim.x) a[i][c] = (i == c) ? l : a[i][c] / l;
+        __syncthreads();
+        const int m = kD - 1 - c;                 // trailing block (c+1 .. 38)^2, lower triangle
+        for (int e = tid; e < m * m; e += blockDim.x) {
+            const int i = c + 1 + e / m, j = c + 1 + e % m;
+            if (j <= i) a[i][j] -= a[i][c] * a[j][c];
         }
-        if (lane == 0) { s_bad = bad ? 1 : 0; s_logdet = log_pdet; }
-        if (!bad) {
-            for (int j = lane; j < kD; j += 32) {                     // one column of M^-1 per lane (two for the first 7 lanes)
-                for (int i = 0; i < kD; ++i) minv[i][j] = 0.0;
-                for (int i = j; i < kD; ++i) {
-                    double acc = (i == j) ? 1.0 : 0.0;
-                    for (int k = j; k < i; ++k) acc -= a[i][k] * minv[k][j];
-                    minv[i][j] = acc / a[i][i];
-                }
-            }
-        }
+        __syncthreads();
     }
     __syncthreads();
     if (s_bad) {                                  // no image for this state: the word is parked until the host has looked at it
         if (tid == 0) { atomicOr(status + w, LOE_MSTEP_SUSPECT); active[w] = -2; }
         return;
     }
-    const double log_pdet = s_logdet;
+    // M^-1 by forward substitution, one column per thread
+    if (tid < kD) {
+        const int j = tid;
+        for (int i = 0; i < kD; ++i) minv[i][j] = 0.0;
+        for (int i = j; i < kD; ++i) {
+            double acc = (i == j) ? 1.0 : 0.0;
+            for (int k = j; k < i; ++k) acc -= a[i][k] * minv[k][j];
+            minv[i][j] = acc / a[i][i];
+        }
+    }
+    __syncthreads();
     // W[k][j] = M^-1[38 - j][38 - k] (lower triangular); bias row 39 = -mean . W; column 39 = 0
     if (tid < kKW) {
         const int j = tid;
