@@ -299,11 +299,10 @@ __global__ void reduce_kernel(const double* __restrict__ part, int n_chunks, int
 //        bucket_hist_kernel -> bucket_scan_kernel (exclusive offsets per (bucket, chunk)) -> bucket_plan_kernel (bases, work list)
 //        -> bucket_scatter_kernel (frame index lists, one contiguous list per bucket)
 //   2. accum2_kernel: one CTA per work item = up to 2048 consecutive list entries of ONE bucket.  The augmented frames
-//      y = [x - shift, 1] are gathered through the list into shared memory (float64, 64 per batch; the next batch's raw
-//      features are prefetched into registers meanwhile) and sum y y^T = Y^T Y is a contraction over the frames on the FP64
-//      TENSOR cores: mma.sync m8n8k4 (DMMA), 15 tiles of 8 x 8 on or above the diagonal of the 5 x 5 tile grid, 4 frames per
-//      instruction, all 15 accumulator tiles in the registers of every warp; 5 shared-memory loads feed 15 DMMAs (3 840
-//      FMAs).  The FP64 pipe bounds this kernel (960 FMAs per frame at 64 per clock and SM); with scalar DFMAs in 8 x 8
+//      y = [x - shift, 1] are gathered through the list, 4 frames per warp and step, three steps ahead of their use, and
+//      sum y y^T = Y^T Y is a contraction over the frames on the FP64 TENSOR cores: mma.sync m8n8k4 (DMMA), 15 tiles of
+//      8 x 8 on or above the diagonal of the 5 x 5 tile grid, 4 frames per instruction, all 15 accumulator tiles in the
+//      registers of every warp; 5 shared-memory loads feed 15 DMMAs (3 840 FMAs); no block barrier in the loop.  The FP64 pipe bounds this kernel (960 FMAs per frame at 64 per clock and SM); with scalar DFMAs in 8 x 8
 //      register tiles (the first version of this path) instruction issue and latency did: 15 % pipe utilisation (ncu).
 //      float64 is kept because the models must come out identical whatever the number of ranks the frames are sharded
 //      over -- split-precision products on the tcgen05 pipe give 2^-21 per product, not enough for that.
@@ -315,7 +314,7 @@ constexpr int kSortChunk = 2048;                 // frames per histogram / scatt
 constexpr int kSortThreads = 256;
 constexpr int kSortMaxGlob = 1024;
 constexpr int kSplit = 2048;                     // list entries per work item
-constexpr int kA2Frames = 64;                    // frames per staged batch (22.5 KB of float64 rows: two CTAs per SM)
+constexpr int kA2Depth = 3;                      // 4-frame steps each warp has in flight (gathered into registers ahead of use)
 constexpr int kA2RowPitch = 44;                  // doubles per staged row (40 used): conflict-free fragment loads
 
 __global__ void __launch_bounds__(kSortThreads)
@@ -424,56 +423,60 @@ accum2_kernel(const float* __restrict__ feat, const int* __restrict__ idx, const
     if (item >= work_range[n_glob]) return;
     const int g = work[3 * item], begin = work[3 * item + 1], end = work[3 * item + 2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    __shared__ __align__(16) double s_y[kA2Frames * kA2RowPitch];      // staged rows [frame][44]; reused for the final sum
+    // Every warp works on its own: steps of 4 frames (one DMMA K), step s of the item belongs to warp s % 8.  A step's 160
+    // raw values (4 rows x 40, 5 per lane) are gathered through the frame list kA2Depth steps ahead into registers, turned
+    // into y = [x - shift, 1] (float64) in the warp's private tile and multiplied: no block barrier in the loop, and
+    // 8 warps x kA2Depth steps of loads in flight per CTA cover the gather's HBM latency.
+    __shared__ __align__(16) double s_tile[8][4 * kA2RowPitch];        // per warp: 4 rows of 44 doubles
+    __shared__ double s_sum[40 * 41];
     __shared__ double s_shift[40];
-    // sum y y^T as 15 tiles of 8 x 8 (upper triangle of the 5 x 5 tile grid), all of them in the registers of every warp:
-    // tile t = (bi, bj), lane holds rows 8 bi + (lane >> 2), columns 8 bj + 2 (lane & 3) + {0, 1}
     double c[15][2];
 #pragma unroll
     for (int t = 0; t < 15; ++t) { c[t][0] = 0.0; c[t][1] = 0.0; }
     if (tid < 40) s_shift[tid] = (tid < D) ? (double)shift[(size_t)g * D + tid] : 0.0;
-    // The raw features of the NEXT batch are gathered into registers (kA2Pre independent loads per thread in flight) while
-    // the current batch is multiplied.  Element e = tid + 256 j of a batch is (row e / 40, column e % 40).
-    constexpr int kA2Pre = (kA2Frames * 40 + 255) / 256;
-    float pre[kA2Pre];
-    auto prefetch = [&](int b0) {
-        const int nb = min(kA2Frames, end - b0);
+    __syncthreads();
+    const int n_steps = (end - begin + 3) >> 2;
+    float pre[kA2Depth][5];
+    // element e = lane + 32 j of a step is (row e / 40, column e % 40); rows past the item's end and column 39 load nothing
+    auto prefetch = [&](int st, float* dst) {
 #pragma unroll
-        for (int j = 0; j < kA2Pre; ++j) {
-            const int e = tid + 256 * j, r = e / 40, k = e - r * 40;
-            pre[j] = (r < nb && k < D) ? __ldg(feat + (size_t)__ldg(idx + b0 + r) * D + k) : 0.f;
+        for (int j = 0; j < 5; ++j) {
+            const int e = lane + 32 * j, r = e / 40, k = e - r * 40;
+            const int f = begin + 4 * st + r;
+            dst[j] = (st < n_steps && f < end && k < D) ? __ldg(feat + (size_t)__ldg(idx + f) * D + k) : 0.f;
         }
     };
-    prefetch(begin);
-    __syncthreads();
-    for (int b0 = begin; b0 < end; b0 += kA2Frames) {
-        const int nb = min(kA2Frames, end - b0);
-        // rows beyond the batch are ZERO (also their constant-one column): the 4-frame steps below need no tail handling
 #pragma unroll
-        for (int j = 0; j < kA2Pre; ++j) {
-            const int e = tid + 256 * j, r = e / 40, k = e - r * 40;
-            if (r < kA2Frames) s_y[r * kA2RowPitch + k] = (r < nb) ? ((k < D) ? (double)pre[j] - s_shift[k] : 1.0) : 0.0;
-        }
-        __syncthreads();
-        if (b0 + kA2Frames < end) prefetch(b0 + kA2Frames);
-        const int n_steps = (nb + 3) >> 2;
-        for (int st = warp; st < n_steps; st += 8) {
+    for (int d = 0; d < kA2Depth; ++d) prefetch(warp + 8 * d, pre[d]);
+    double* tile = s_tile[warp];
+    for (int st = warp; st < n_steps; st += 8 * kA2Depth) {
+#pragma unroll
+        for (int d = 0; d < kA2Depth; ++d) {
+            const int cur = st + 8 * d;
+            if (cur >= n_steps) break;                                     // warp-uniform
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                const int e = lane + 32 * j, r = e / 40, k = e - r * 40;
+                const bool live = begin + 4 * cur + r < end;              // rows beyond the item are ZERO, also their constant 1
+                tile[r * kA2RowPitch + k] = live ? ((k < D) ? (double)pre[d][j] - s_shift[k] : 1.0) : 0.0;
+            }
+            prefetch(cur + 8 * kA2Depth, pre[d]);
+            __syncwarp();
             // one load per 8-wide block serves as the A fragment of the tiles in that block row and as the B fragment of
             // the tiles in that block column (pitch 44: the 16 lanes of a half-warp hit 32 different banks)
-            const double* p = s_y + (4 * st + (lane & 3)) * kA2RowPitch + (lane >> 2);
+            const double* p = tile + (lane & 3) * kA2RowPitch + (lane >> 2);
             double f[5];
 #pragma unroll
             for (int b = 0; b < 5; ++b) f[b] = p[8 * b];
+            __syncwarp();                                                  // the tile may be rewritten
             int t = 0;
 #pragma unroll
             for (int bi = 0; bi < 5; ++bi)
 #pragma unroll
                 for (int bj = bi; bj < 5; ++bj, ++t) dmma884(c[t][0], c[t][1], f[bi], f[bj]);
         }
-        __syncthreads();
     }
     // warps -> one 40 x 40 matrix in shared memory, fixed order
-    double* s_sum = s_y;                          // [40][41]
     for (int q = 0; q < 8; ++q) {
         if (warp == q) {
             int t = 0;
