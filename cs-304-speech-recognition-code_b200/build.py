@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libloe_b200.so")
-SOURCES = ["common.cu", "mfcc.cu", "mfcc_ex.cu", "emission.cu", "emission_tc.cu", "viterbi.cu", "viterbi_warp.cu", "viterbi_pair.cu", "kmeans.cu", "mstep.cu", "vad.cu", "dtw.cu", "decoder.cu", "emission_h16.cu", "emission_gmm.cu"]
+SOURCES = ["common.cu", "mfcc.cu", "mfcc_ex.cu", "emission.cu", "emission_tc.cu", "viterbi.cu", "viterbi_warp.cu", "kmeans.cu", "mstep.cu", "vad.cu", "dtw.cu", "decoder.cu", "emission_h16.cu", "emission_gmm.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 SPILL_SENSITIVE = {"emission_h16.cu"}
 

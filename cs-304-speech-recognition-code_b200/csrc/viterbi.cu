@@ -282,7 +282,6 @@ extern "C" int loe_viterbi_dev(const float* scores_dev, int ld, const int64_t* f
     a.path = path_dev; a.end_scores = end_scores_dev; a.max_ends = max_ends; a.best = best_dev; a.best_score = best_score_dev;
     a.bp_ws = bp_ws_dev; a.bp_in_smem = in_smem ? 1 : 0; a.max_frames = max_frames; a.max_pos = max_pos;
     a.word = word_dev; a.word_lo = word_lo_dev; a.skip_label = skip_label; a.words = words_dev; a.max_words = max_words; a.count = count_dev;
-    if (viterbi_pair_launch(a, n_utt, s)) return LOE_OK;      // digit-loop decode: two utterances per warp
     if (viterbi_warp_launch(a, n_utt, s)) return LOE_OK;      // one warp per utterance (the common case)
     LOE_CUDA(cudaGetLastError());
     const int threads = ((max_pos + 31) / 32) * 32;

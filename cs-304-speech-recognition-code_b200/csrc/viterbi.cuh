@@ -19,7 +19,5 @@ struct VitArgs {
 // One-warp-per-utterance kernel (viterbi_warp.cu).  Returns false when the utterances are too long
 // for its shared-memory back-pointer store; the caller then uses the CTA-per-utterance kernel.
 bool viterbi_warp_launch(const VitArgs& a, int n_utt, cudaStream_t s);
-// Two utterances per warp for loop decoding with 33..60 positions (viterbi_pair.cu); false = shape does not apply.
-bool viterbi_pair_launch(const VitArgs& a, int n_utt, cudaStream_t s);
 
 }  // namespace loe
