@@ -170,6 +170,72 @@ def workload_config(n_utts, pool, where):
 
 
 # ------------------------------------------------------------------------------------------------
+def gmm_block(args, eng, feat, frm_off_dev, n, max_t, F):
+    """BASELINE.json configs[4] shape: 40 phones x 3 states = 120 emission states with 16 diagonal Gaussians each, scored on
+    the frames of the decode batch (the features are the real MFCCs of the synthetic corpus; the mixture parameters are
+    seeded random draws around the feature statistics -- there is no trained phone model without a corpus), then the word
+    loop over a pronunciation lexicon (102 trellis positions sharing the phone states).  Reports the scoring kernel against
+    the tensor peak with the USEFUL flops of SURVEY §8d (2 (2D+1) S M per frame, counted once although three split-operand
+    products are issued) and the Viterbi over the wider trellis."""
+    import torch
+    from loe_speech_recognition import _trellis
+    from loe_speech_recognition.gmm import word_log_transitions
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from phone_fixture import LEXICON, ORDER
+    rng = np.random.default_rng(4)
+    S, M, D = 120, 16, 39
+    sub = feat[:: max(1, F // 20000)].cpu().numpy().astype(np.float64)
+    mu0, sd0 = sub.mean(0), sub.std(0) + 1e-3
+    means = mu0 + rng.normal(0, 1.0, size=(S, 1, D)) * sd0 + rng.normal(0, 0.4, size=(S, M, D)) * sd0
+    variances = (sd0 * rng.uniform(0.3, 0.9, size=(S, M, D))) ** 2
+    w = rng.uniform(0.5, 1.0, size=(S, M)); w /= w.sum(1, keepdims=True)
+    gp = eng.pack_gmm(w, means, variances)
+    assert gp.b_img is not None
+    out = torch.empty((F, S), dtype=torch.float32, device=eng.device)
+
+    def timed(fn):
+        fn(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            r = fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / args.steps, r
+    ms_tc, _ = timed(lambda: eng.emission_gmm(feat, gp, "tc", out=out))
+    # parity spot check against the float64 kernel on a slice (untimed)
+    ref = eng.emission_gmm(feat[:4096], gp, "fp64").cpu().numpy().astype(np.float64)
+    got = out[:4096].cpu().numpy().astype(np.float64)
+    cst = np.abs(np.log(w) - 0.5 * (D * np.log(2 * np.pi) + np.log(variances).sum(-1))).max()
+    worst = float(np.max(np.abs(got - ref) / np.maximum(np.abs(ref), cst)))
+    # lexicon-expanded word loop over the shared phone states
+    phones = sorted({p for ps in LEXICON.values() for p in ps})
+    phone_col = {p: 3 * i for i, p in enumerate(phones)}
+    with np.errstate(divide="ignore"):
+        logA = {p: np.log(np.array([[.7, .3, 0], [0, .7, .3], [0, 0, .7]], np.float32)) for p in phones}
+    dense = [word_log_transitions(logA, {p: float(np.log(0.3)) for p in phones}, LEXICON[wd]) for wd in ORDER]
+    tr = _trellis.build(dense, [0] * len(dense), list(range(len(dense))), "loop")
+    tr.col = np.asarray([phone_col[p] + j for wd in ORDER for p in LEXICON[wd] for j in range(3)], dtype=np.int32)
+    tp = eng.pack_trellises([tr])
+    ms_vit, _ = timed(lambda: eng.viterbi(out, frm_off_dev, n, max_t, F, tp, loop=True, penalty=-50.0, penalty_f64=False,
+                                          want_end_scores=False, labels=(ORDER.index("S"), 32)))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    bf16 = peaks.get("bf16_tflops", 1590.0)
+    flops = 2 * (2 * D + 1) * S * M
+    return {"workload": f"BASELINE.json configs[4] shape: {S} phone states x {M} diagonal Gaussians, D = {D}, {F} frames of the decode batch; "
+                        f"word loop over a pronunciation lexicon ({tr.n_pos} trellis positions on {3 * len(phones)} of the states)",
+            "emission_ms": ms_tc, "frames_per_s": F / (ms_tc * 1e-3), "viterbi_ms": ms_vit,
+            "max_err_vs_fp64_kernel_rel_to_scale": worst, "parity": "restated oracle only (oracle/gmm.py): unpinned by construction",
+            "roofline": {"kernel": "emission_gmm_tc_kernel<16>", "bound": "tensor", "achieved": flops * F / (ms_tc * 1e-3) / 1e12, "peak": bf16,
+                         "unit": "TFLOP/s", "frac": flops * F / (ms_tc * 1e-3) / 1e12 / bf16, "traffic": None,
+                         "algorithmic": f"{flops} flop/frame x {F} frames (2 (2D+1) S M, counted once; 3 split-operand products of K = 80 "
+                                        f"are issued: {3 * 2 * 80 * S * M} flop/frame on the tensor pipe)"}}
+
+
+# ------------------------------------------------------------------------------------------------
 def train_block(args, eng, world, rank, dist):
     """BASELINE.json configs[2]: segmental K-means training of the 11 digit HMMs (5 states) on 100 k synthetic single-digit
     utterances, STRONG scaling: the utterances are sharded over the ranks, one all-reduce of the packed float64 statistics
@@ -460,6 +526,10 @@ def impl_b200(args):
     del sink
     d2h = int(n * 32 + n * 4)
 
+    gmm = None
+    if rank == 0 and not args.no_gmm:
+        gmm = gmm_block(args, eng, feat if image is None else eng.mfcc_device(pcm_dev, pcm_off_dev, frm_off_dev, n, F, max_t, min_t, 16000,
+                                                                              out=feat, mel_ws=mel_ws, utt_max=utt_max), frm_off_dev, n, max_t, F)
     train = None if args.no_train else train_block(args, eng, world, rank, dist if world > 1 else None)
     sweep = None
     if rank == 0 and world == 1 and not args.no_sweep:
@@ -562,6 +632,7 @@ def impl_b200(args):
                            "api": "HiddenMarkovModelInference.decode_pcm_flat (torch tensors / streams as plumbing); identical strings"},
         "gpu_launches": launches,
         "train": train,
+        "gmm_phone_loop": gmm,
         "mfcc_sweep": sweep,
         "parity": parity,
         "clocks": clocks,
@@ -593,6 +664,7 @@ def main():
     ap.add_argument("--pool", type=int, default=500, help="distinct synthetic utterances (tiled to --utts)")
     ap.add_argument("--precision", default=os.environ.get("LOE_B200_EMISSION", "auto"), choices=["auto", "fp32", "fp64", "tc", "h16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gmm", action="store_true", help="skip the diagonal-GMM phone-loop block (BASELINE.json configs[4])")
     ap.add_argument("--no-train", action="store_true", help="skip the segmental K-means block (BASELINE.json configs[2])")
     ap.add_argument("--train-utts", type=int, default=100001, help="training utterances in total (sharded over the ranks)")
     ap.add_argument("--train-iters", type=int, default=8)
