@@ -17,8 +17,10 @@
 // accumulation in TMEM: 15 MMAs of M128 N240 K16 per 128-frame tile.  The epilogue thread (= frame row) reads the
 // accumulator columns and does the log-sum-exp over each state's mixtures in registers.
 // B-stationary CTAs: one column tile of 240 (state, mixture) columns resident in shared memory (77 KB), frame tiles
-// streamed through it: raw feature tiles by cp.async.bulk (TMA engine), 8 producer warps build the A operand, one
-// thread issues the MMAs, 4 warps drain TMEM.
+// streamed through it: raw feature tiles by cp.async.bulk (TMA engine), 4 producer warps (thread = row) build the A operand,
+// one thread issues the MMAs, 12 epilogue warps in three warpgroups drain TMEM -- each warpgroup 80 columns = whole states
+// of every row, so the exp / log work of a tile (30 720 exponentials at 16 mixtures) is spread over 12 warps instead of
+// the 4 the TMEM lane rule suggests (the first version: epilogue-bound at 4 % of the tensor peak, ncu: profiles/).
 // Rows whose |z| reaches 128 (z^2 near the binary16 range) or is not finite are computed by their epilogue thread with
 // plain float32 arithmetic from the unpacked model: any input gives the SIMT kernel's answer.
 //
@@ -39,8 +41,10 @@ constexpr int kBChunks = 2 * kChunksPerPart;
 constexpr int kTileN = 240;                 // (state, mixture) columns per tile; mixtures padded to a power of two <= 16
 constexpr int kTmemCols = 512;
 constexpr int kBufStride = 256;
-constexpr int kProducerThreads = 256;
-constexpr int kEpilogueThreads = 128;
+constexpr int kProducerThreads = 128;            // thread = frame row
+constexpr int kEpiGroups = 3;                    // epilogue warpgroups: each drains 80 of the 240 accumulator columns of every row
+constexpr int kEpiCols = kTileN / kEpiGroups;    // 80: a multiple of every padded mixture count (1, 2, 4, 8, 16)
+constexpr int kEpilogueThreads = 128 * kEpiGroups;
 constexpr int kThreads = kProducerThreads + kEpilogueThreads + 32;
 constexpr int kALbo = kTileM * 16;          // 2048
 constexpr int kBLbo = kTileN * 16;          // 3840
@@ -112,6 +116,16 @@ __device__ __forceinline__ float score_state(const T* x, const T* __restrict__ m
     return (float)(best + log(sum));
 }
 
+// the float32 path of one out-of-range row (rare): kept out of line so that its registers (the feature row, the component
+// values) do not weigh on the epilogue loop
+__device__ __noinline__ void score_row_slow(const float* __restrict__ feat_row, const float* __restrict__ mean32, const float* __restrict__ inv_var32,
+                                            const float* __restrict__ cst32, int s_begin, int s_end, int n_mix, float* __restrict__ o) {
+    float x[kDim];
+#pragma unroll
+    for (int c = 0; c < kDim; ++c) x[c] = __ldg(feat_row + c);
+    for (int s = s_begin; s < s_end; ++s) o[s - s_begin] = score_state<float>(x, mean32, inv_var32, cst32, s, n_mix);
+}
+
 template <int MP>
 __global__ void __launch_bounds__(kThreads, 1)
 emission_gmm_tc_kernel(const float* __restrict__ feat, int64_t n_frames, const uint8_t* __restrict__ b_packed,
@@ -170,8 +184,7 @@ emission_gmm_tc_kernel(const float* __restrict__ feat, int64_t n_frames, const u
             if (n_it > 0 && tile_full(0)) issue(0);
             if (n_it > 1 && tile_full(1)) issue(1);
         }
-        const int row_id = tid & (kTileM - 1);
-        const int half = tid >> 7;                          // 0: [z^2, 1] (chunks 0-4)   1: [z, 0] (chunks 5-9)
+        const int row_id = tid;
         for (int it = 0; it < n_it; ++it) {
             const int s = it & 1;
             const uint32_t k = (uint32_t)(it >> 1);
@@ -181,34 +194,37 @@ emission_gmm_tc_kernel(const float* __restrict__ feat, int64_t n_frames, const u
                 const int64_t f0 = (int64_t)(g + it * G) * kTileM;
                 const int total = (int)(n_frames - f0) * kDim;
                 for (int e = tid; e < kTileElems; e += kProducerThreads) sm.raw[s][e] = (e < total) ? __ldg(feat + f0 * kDim + e) : 0.f;
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                asm volatile("bar.sync 1, 128;" ::: "memory");
             }
             mbar_wait(&sm.a_empty[s], (k & 1) ^ 1);
             const float* row = sm.raw[s] + row_id * kDim;
-            float v[40];
-            float mx = 0.f;
-#pragma unroll
-            for (int c = 0; c < kDim; ++c) {
-                v[c] = (row[c] - sm.shift[c]) * sm.iscale[c];
-                mx = fmaxf(mx, fabsf(v[c]));
-            }
-            const bool slow = !(mx < kZMax);                // also NaN / inf
-            if (half == 0) {
-                sm.slow[it & 3][row_id] = slow ? 1 : 0;
-#pragma unroll
-                for (int c = 0; c < kDim; ++c) v[c] = slow ? 0.f : v[c] * v[c];
-                v[kDim] = slow ? 0.f : 1.0f;
-            } else {
-#pragma unroll
-                for (int c = 0; c < kDim; ++c) v[c] = slow ? 0.f : v[c];
-                v[kDim] = 0.f;
-            }
             uint8_t* a_row = sm.a[s] + row_id * 16;
+            float mx = 0.f;
+            // chunk by chunk (8 columns): z, then [z^2 | 1] into chunk kc and [z | 0] into chunk 5 + kc.  A row that turns out
+            // to be out of range (or not finite) is flagged afterwards: its operand may hold inf / NaN, which stays inside
+            // its own accumulator row, and that row is never read -- its epilogue threads score it in float32.
 #pragma unroll
-            for (int kc = 0; kc < 5; ++kc) split_store(v + kc * 8, a_row, half * 5 + kc);
+            for (int kc = 0; kc < 5; ++kc) {
+                float z[8], z2[8];
+#pragma unroll
+                for (int q8 = 0; q8 < 8; ++q8) {
+                    const int c = kc * 8 + q8;
+                    if (c < kDim) {
+                        z[q8] = (row[c] - sm.shift[c]) * sm.iscale[c];
+                        z2[q8] = z[q8] * z[q8];
+                        mx = fmaxf(mx, fabsf(z[q8]));
+                    } else {
+                        z[q8] = 0.f;                 // column 39: the constant 1 sits in the z^2 half
+                        z2[q8] = 1.0f;
+                    }
+                }
+                split_store(z2, a_row, kc);
+                split_store(z, a_row, 5 + kc);
+            }
+            sm.slow[it & 3][row_id] = (mx < kZMax) ? 0 : 1;            // NaN compares false: flagged
             fence_proxy_async();
             mbar_arrive(&sm.a_full[s]);
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            asm volatile("bar.sync 1, 128;" ::: "memory");
             if (tid == 0 && it + 2 < n_it && tile_full(it + 2)) issue(it + 2);
         }
     } else if (warp == (kProducerThreads + kEpilogueThreads) / 32) {
@@ -240,45 +256,49 @@ emission_gmm_tc_kernel(const float* __restrict__ feat, int64_t n_frames, const u
         }
     } else {
         // =========================== epilogue ===========================
+        // Three warpgroups; warp w may touch the TMEM lanes 32 (w % 4) .. + 31 (its rows), warpgroup grp takes the columns
+        // [80 grp, 80 grp + 80) of every row: whole states (80 is a multiple of MP), so every log-sum-exp stays inside one
+        // thread and twelve warps share the exp / log work of a tile.
         const int q = warp & 3;
+        const int grp = (warp - kProducerThreads / 32) >> 2;
         const int r = q * 32 + lane;
+        const int c0 = grp * kEpiCols;
+        const int st0 = c0 / MP;                                      // first state (local to the tile) of this warpgroup
         int it = 0;
         for (int m = g; m < n_mtiles; m += G, ++it) {
             const int s = it & 1;
             const uint32_t k = (uint32_t)(it >> 1);
             mbar_wait(&sm.tmem_full[s], k & 1);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * kBufStride);
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * kBufStride) + (uint32_t)c0;
             const int64_t f = (int64_t)m * kTileM + r;
             const bool live = f < n_frames;
             const bool slow = sm.slow[it & 3][r] != 0;
             float* o = out + (live ? f : 0) * ld_out + n_tile * SPT;
-            // rounds of 48 accumulator columns (a multiple of every MP): 5 rounds cover the 240 columns
-#pragma unroll 1
-            for (int c0 = 0; c0 < kTileN; c0 += 48) {
-                if (c0 >= valid * MP) break;                          // warp-uniform: a narrow last tile reads less
-                float v[48];
-                tmem_ld32(taddr + c0, v);
-                tmem_ld16(taddr + c0 + 32, v + 32);
-                tmem_ld_wait();
-                if (c0 + 48 >= kTileN || c0 + 48 >= valid * MP) {     // last round of this tile: hand the accumulator back
+            // two rounds (48 + 32 columns: both multiples of MP) keep the accumulator slice of a thread at 48 registers
+#pragma unroll
+            for (int rd = 0; rd < 2; ++rd) {
+                constexpr int kR0 = 48;
+                const int cb = rd * kR0, nc = rd ? kEpiCols - kR0 : kR0;          // 0 / 48 columns into the slice, 48 / 32 wide
+                float v[kR0];
+                if (c0 + cb < valid * MP) {                                       // warp-uniform: a narrow last tile reads less
+                    if (rd == 0) { tmem_ld32(taddr, v); tmem_ld16(taddr + 32, v + 32); }
+                    else tmem_ld32(taddr + kR0, v);
+                    tmem_ld_wait();
+                }
+                if (rd == 1) {                                                    // the accumulator has been read: hand it back
                     tc_fence_before();
                     mbar_arrive(&sm.tmem_empty[s]);
                 }
                 if (live && !slow) {
 #pragma unroll
-                    for (int j = 0; j < 48 / MP; ++j) {
-                        const int st = (c0 / MP) + j;
-                        if (st < valid) o[st] = lse<MP>(v + j * MP, n_mix);
-                    }
+                    for (int j = 0; j < kR0 / MP; ++j)
+                        if (j * MP < nc && st0 + cb / MP + j < valid) o[st0 + cb / MP + j] = lse<MP>(v + j * MP, n_mix);
                 }
             }
-            if (live && slow) {
-                float x[kDim];
-#pragma unroll
-                for (int c = 0; c < kDim; ++c) x[c] = __ldg(feat + f * kDim + c);
-                for (int st = 0; st < valid; ++st) o[st] = score_state<float>(x, mean32, inv_var32, cst32, n_tile * SPT + st, n_mix);
-            }
+            if (live && slow && st0 < valid)
+                score_row_slow(feat + f * kDim, mean32, inv_var32, cst32, n_tile * SPT + st0, n_tile * SPT + min(valid, st0 + kEpiCols / MP),
+                               n_mix, o + st0);
         }
     }
     tc_fence_before();
