@@ -78,18 +78,28 @@ __device__ __forceinline__ void split_store(const float* x, uint8_t* a_row, int 
     *reinterpret_cast<uint4*>(a_row + (kChunksPerPart + kc) * kALbo) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-// log sum exp over the first n_mix of MP consecutive accumulator columns (the padding columns are never read)
-template <int MP>
+// log sum exp over the first n_mix of MP consecutive accumulator columns, branch-free: 4 instructions per component (FMNMX,
+// FFMA, MUFU.EX2, FADD).  FULL: n_mix == MP, no padding columns; otherwise a padding column reads as -inf.  The exponent
+// is formed as fma(v, log2 e, -m log2 e): the rounding of m log2 e scales every term alike (2^-24 |m| on the result).
+// All components -inf gives -inf (the clamp keeps inf - inf out), a NaN component gives NaN.
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+template <int MP, bool FULL>
 __device__ __forceinline__ float lse(const float* v, int n_mix) {
     if (MP == 1) return v[0];
-    float m = v[0];
+    constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+    float vv[MP];
 #pragma unroll
-    for (int i = 1; i < MP; ++i) m = (i < n_mix) ? fmaxf(m, v[i]) : m;
-    if (!(m > -CUDART_INF_F)) return m;                         // every component -inf (or NaN): no exp of inf - inf
+    for (int i = 0; i < MP; ++i) vv[i] = (FULL || i < n_mix) ? v[i] : -CUDART_INF_F;
+    float m = vv[0];
+#pragma unroll
+    for (int i = 1; i < MP; ++i) m = fmaxf(m, vv[i]);
+    m = fmaxf(m, -3.0e38f);
+    const float nms = -m * kLog2e;
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < MP; ++i) s += (i < n_mix) ? __expf(v[i] - m) : 0.f;
-    return m + __logf(s);
+    for (int i = 0; i < MP; ++i) s += ex2_approx(fmaf(vv[i], kLog2e, nms));
+    return fmaf(lg2_approx(s), kLn2, m);
 }
 
 // exact float32 evaluation of one (frame, state): the slow path of the tensor-core kernel and the body of the SIMT kernel
@@ -126,7 +136,7 @@ __device__ __noinline__ void score_row_slow(const float* __restrict__ feat_row, 
     for (int s = s_begin; s < s_end; ++s) o[s - s_begin] = score_state<float>(x, mean32, inv_var32, cst32, s, n_mix);
 }
 
-template <int MP>
+template <int MP, bool FULL>
 __global__ void __launch_bounds__(kThreads, 1)
 emission_gmm_tc_kernel(const float* __restrict__ feat, int64_t n_frames, const uint8_t* __restrict__ b_packed,
                        const float* __restrict__ shift_scale, const float* __restrict__ mean32, const float* __restrict__ inv_var32,
@@ -293,7 +303,7 @@ emission_gmm_tc_kernel(const float* __restrict__ feat, int64_t n_frames, const u
                 if (live && !slow) {
 #pragma unroll
                     for (int j = 0; j < kR0 / MP; ++j)
-                        if (j * MP < nc && st0 + cb / MP + j < valid) o[st0 + cb / MP + j] = lse<MP>(v + j * MP, n_mix);
+                        if (j * MP < nc && st0 + cb / MP + j < valid) o[st0 + cb / MP + j] = lse<MP, FULL>(v + j * MP, n_mix);
                 }
             }
             if (live && slow && st0 < valid)
@@ -328,15 +338,15 @@ static int padded_mix(int n_mix) {
     return mp;
 }
 
-template <int MP>
-static int launch_tc(const float* feat_dev, int64_t n_frames, const void* b_packed_dev, const float* shift_scale_dev,
+template <int MP, bool FULL>
+static int launch_tc_impl(const float* feat_dev, int64_t n_frames, const void* b_packed_dev, const float* shift_scale_dev,
                      const float* mean32_dev, const float* inv_var32_dev, const float* cst32_dev, int n_states, int n_mix,
                      float* out_dev, int ld_out, cudaStream_t s) {
     constexpr int SPT = kTileN / MP;
     int dev = 0, sms = 0;
     LOE_CUDA(cudaGetDevice(&dev));
     LOE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    LOE_CUDA(cudaFuncSetAttribute(emission_gmm_tc_kernel<MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+    LOE_CUDA(cudaFuncSetAttribute(emission_gmm_tc_kernel<MP, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
     const int n_tiles = (n_states + SPT - 1) / SPT;
     const int n_mtiles = (int)((n_frames + kTileM - 1) / kTileM);
     const int valid_last = n_states - (n_tiles - 1) * SPT;
@@ -356,11 +366,16 @@ static int launch_tc(const float* feat_dev, int64_t n_frames, const void* b_pack
     if (g_last > n_mtiles) g_last = n_mtiles;
     const unsigned grid = (unsigned)((n_tiles - 1) * g_full + g_last);
     const int use_bulk = (reinterpret_cast<uintptr_t>(feat_dev) & 15) == 0 ? 1 : 0;
-    emission_gmm_tc_kernel<MP><<<grid, kThreads, sizeof(Smem), s>>>(feat_dev, n_frames, static_cast<const uint8_t*>(b_packed_dev),
+    emission_gmm_tc_kernel<MP, FULL><<<grid, kThreads, sizeof(Smem), s>>>(feat_dev, n_frames, static_cast<const uint8_t*>(b_packed_dev),
                                                                    shift_scale_dev, mean32_dev, inv_var32_dev, cst32_dev, n_states, n_mix,
                                                                    out_dev, ld_out, use_bulk, g_full, g_last);
     LOE_LAUNCH_CHECK("emission_gmm_tc_kernel");
     return LOE_OK;
+}
+
+template <int MP, typename... Args>
+static int launch_tc(int n_mix, Args... args) {
+    return n_mix == MP ? launch_tc_impl<MP, true>(args...) : launch_tc_impl<MP, false>(args...);
 }
 
 }  // namespace gmm
@@ -406,10 +421,10 @@ extern "C" int loe_emission_gmm_tc_dev(const float* feat_dev, int64_t n_frames, 
     if (ld_out < n_states) { set_error("ld_out (%d) < n_states (%d)", ld_out, n_states); return LOE_ERR_VALUE; }
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     switch (padded_mix(n_mix)) {
-        case 1: return launch_tc<1>(feat_dev, n_frames, b_packed_dev, shift_scale_dev, mean32_dev, inv_var32_dev, cst32_dev, n_states, n_mix, out_dev, ld_out, s);
-        case 2: return launch_tc<2>(feat_dev, n_frames, b_packed_dev, shift_scale_dev, mean32_dev, inv_var32_dev, cst32_dev, n_states, n_mix, out_dev, ld_out, s);
-        case 4: return launch_tc<4>(feat_dev, n_frames, b_packed_dev, shift_scale_dev, mean32_dev, inv_var32_dev, cst32_dev, n_states, n_mix, out_dev, ld_out, s);
-        case 8: return launch_tc<8>(feat_dev, n_frames, b_packed_dev, shift_scale_dev, mean32_dev, inv_var32_dev, cst32_dev, n_states, n_mix, out_dev, ld_out, s);
-        default: return launch_tc<16>(feat_dev, n_frames, b_packed_dev, shift_scale_dev, mean32_dev, inv_var32_dev, cst32_dev, n_states, n_mix, out_dev, ld_out, s);
+        case 1: return launch_tc<1>(n_mix, feat_dev, n_frames, b_packed_dev, shift_scale_dev, mean32_dev, inv_var32_dev, cst32_dev, n_states, n_mix, out_dev, ld_out, s);
+        case 2: return launch_tc<2>(n_mix, feat_dev, n_frames, b_packed_dev, shift_scale_dev, mean32_dev, inv_var32_dev, cst32_dev, n_states, n_mix, out_dev, ld_out, s);
+        case 4: return launch_tc<4>(n_mix, feat_dev, n_frames, b_packed_dev, shift_scale_dev, mean32_dev, inv_var32_dev, cst32_dev, n_states, n_mix, out_dev, ld_out, s);
+        case 8: return launch_tc<8>(n_mix, feat_dev, n_frames, b_packed_dev, shift_scale_dev, mean32_dev, inv_var32_dev, cst32_dev, n_states, n_mix, out_dev, ld_out, s);
+        default: return launch_tc<16>(n_mix, feat_dev, n_frames, b_packed_dev, shift_scale_dev, mean32_dev, inv_var32_dev, cst32_dev, n_states, n_mix, out_dev, ld_out, s);
     }
 }
