@@ -17,11 +17,11 @@
 // accumulation in TMEM: 15 MMAs of M128 N240 K16 per 128-frame tile.  The epilogue thread (= frame row) reads the
 // accumulator columns and does the log-sum-exp over each state's mixtures in registers.
 // B-stationary CTAs: one column tile of 240 (state, mixture) columns resident in shared memory (77 KB), frame tiles
-// streamed through it: raw feature tiles by cp.async.bulk (TMA engine), 4 producer warps (thread = row) build the A operand,
-// one thread issues the MMAs, 12 epilogue warps in three warpgroups drain TMEM -- each warpgroup 80 columns = whole states
+// streamed through it: raw feature tiles by cp.async.bulk (TMA engine), 4 producer warps (thread = row) build the A operand
+// (thread 0 also issues the MMAs, one tile behind), 12 epilogue warps in three warpgroups drain TMEM -- each warpgroup 80 columns = whole states
 // of every row, so the exp / log work of a tile (30 720 exponentials at 16 mixtures) is spread over 12 warps instead of
 // the 4 the TMEM lane rule suggests (the first version: epilogue-bound at 4 % of the tensor peak, ncu: profiles/).
-// Rows whose |z| reaches 128 (z^2 near the binary16 range) or is not finite are computed by their epilogue thread with
+// Rows whose |z| reaches 128 (z^2 near the binary16 range) or is not finite are computed by their producer thread with
 // plain float32 arithmetic from the unpacked model: any input gives the SIMT kernel's answer.
 //
 // SIMT path (loe_emission_gmm_dev): float32 / float64, thread per (frame, state); the float64 instance is the exact mode.
@@ -45,7 +45,8 @@ constexpr int kProducerThreads = 128;            // thread = frame row
 constexpr int kEpiGroups = 3;                    // epilogue warpgroups: each drains 80 of the 240 accumulator columns of every row
 constexpr int kEpiCols = kTileN / kEpiGroups;    // 80: a multiple of every padded mixture count (1, 2, 4, 8, 16)
 constexpr int kEpilogueThreads = 128 * kEpiGroups;
-constexpr int kThreads = kProducerThreads + kEpilogueThreads + 32;
+constexpr int kThreads = kProducerThreads + kEpilogueThreads;   // 16 warps: registers are allocated to a CTA in groups of four warps, a seventeenth
+                                                                // (a dedicated MMA warp) would cost 20 warps' worth and cap every thread at 96
 constexpr int kALbo = kTileM * 16;          // 2048
 constexpr int kBLbo = kTileN * 16;          // 3840
 constexpr int kABytes = kAChunks * kALbo;   // 40960
@@ -84,6 +85,22 @@ __device__ __forceinline__ void split_store(const float* x, uint8_t* a_row, int 
 // All components -inf gives -inf (the clamp keeps inf - inf out), a NaN component gives NaN.
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ unsigned long long pk2(float a, float b) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void upk2(unsigned long long p, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(p)); }
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
 template <int MP, bool FULL>
 __device__ __forceinline__ float lse(const float* v, int n_mix) {
     if (MP == 1) return v[0];
@@ -96,10 +113,18 @@ __device__ __forceinline__ float lse(const float* v, int n_mix) {
     for (int i = 1; i < MP; ++i) m = fmaxf(m, vv[i]);
     m = fmaxf(m, -3.0e38f);
     const float nms = -m * kLog2e;
-    float s = 0.f;
+    // accumulator columns come in aligned register pairs: the scaling and the summation run as packed f32x2 instructions
+    const unsigned long long l2 = pk2(kLog2e, kLog2e), n2 = pk2(nms, nms);
+    unsigned long long acc[2] = {0ull, 0ull};
 #pragma unroll
-    for (int i = 0; i < MP; ++i) s += ex2_approx(fmaf(vv[i], kLog2e, nms));
-    return fmaf(lg2_approx(s), kLn2, m);
+    for (int i = 0; i < MP; i += 2) {
+        float t0, t1;
+        upk2(fma2(pk2(vv[i], vv[i + 1]), l2, n2), t0, t1);
+        acc[(i >> 1) & 1] = add2(acc[(i >> 1) & 1], pk2(ex2_approx(t0), ex2_approx(t1)));
+    }
+    float s0, s1;
+    upk2(MP > 2 ? add2(acc[0], acc[1]) : acc[0], s0, s1);
+    return fmaf(lg2_approx(s0 + s1), kLn2, m);
 }
 
 // exact float32 evaluation of one (frame, state): the slow path of the tensor-core kernel and the body of the SIMT kernel
@@ -194,10 +219,35 @@ emission_gmm_tc_kernel(const float* __restrict__ feat, int64_t n_frames, const u
             if (n_it > 0 && tile_full(0)) issue(0);
             if (n_it > 1 && tile_full(1)) issue(1);
         }
+        // Thread 0 also issues the MMAs, one tile behind the staging: by the time tile it is staged, every producer has
+        // arrived on a_full of tile it - 1 (the group barrier below), so the issue never waits on the staging, and the
+        // tensor pipe works on tile it - 1 while tile it is being split.
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(n_cols >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);   // c F32, a / b F16, N >> 3, M >> 4
+        const uint32_t b_base = smem_u32(sm.b);
+        auto issue_mma = [&](int j) {
+            const int s = j & 1;
+            const uint32_t k = (uint32_t)(j >> 1);
+            mbar_wait(&sm.a_full[s], k & 1);
+            mbar_wait(&sm.tmem_empty[s], (k & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d = tmem_base + (uint32_t)(s * kBufStride);
+            const uint32_t a_base = smem_u32(sm.a[s]);
+#pragma unroll
+            for (int pass = 0; pass < 3; ++pass) {                        // hi*hi, lo*hi, hi*lo
+                const uint32_t a = a_base + ((pass == 1) ? kChunksPerPart * kALbo : 0);
+                const uint32_t b = b_base + ((pass == 2) ? kChunksPerPart * kBLbo : 0);
+#pragma unroll
+                for (int ks = 0; ks < kChunksPerPart / 2; ++ks)
+                    mma_f16(d, make_desc(a + ks * 2 * kALbo, kALbo), make_desc(b + ks * 2 * kBLbo, kBLbo), idesc, (pass | ks) ? 1u : 0u);
+            }
+            mma_commit(&sm.a_empty[s]);
+            mma_commit(&sm.tmem_full[s]);
+        };
         const int row_id = tid;
         for (int it = 0; it < n_it; ++it) {
             const int s = it & 1;
             const uint32_t k = (uint32_t)(it >> 1);
+            if (tid == 0 && it > 0) issue_mma(it - 1);
             if (tile_full(it)) {
                 mbar_wait(&sm.raw_full[s], k & 1);
             } else {
@@ -231,39 +281,19 @@ emission_gmm_tc_kernel(const float* __restrict__ feat, int64_t n_frames, const u
                 split_store(z2, a_row, kc);
                 split_store(z, a_row, 5 + kc);
             }
-            sm.slow[it & 3][row_id] = (mx < kZMax) ? 0 : 1;            // NaN compares false: flagged
+            const bool slow = !(mx < kZMax);                            // NaN compares false: flagged
+            sm.slow[it & 3][row_id] = slow ? 1 : 0;
             fence_proxy_async();
             mbar_arrive(&sm.a_full[s]);
             asm volatile("bar.sync 1, 128;" ::: "memory");
             if (tid == 0 && it + 2 < n_it && tile_full(it + 2)) issue(it + 2);
+            // an out-of-range row is scored here, by the thread that found it, in float32 from the unpacked model (rare;
+            // the producers have slack): the epilogue threads skip it
+            const int64_t f = (int64_t)(g + it * G) * kTileM + row_id;
+            if (slow && f < n_frames)
+                score_row_slow(feat + f * kDim, mean32, inv_var32, cst32, n_tile * SPT, n_tile * SPT + valid, n_mix, out + f * ld_out + n_tile * SPT);
         }
-    } else if (warp == (kProducerThreads + kEpilogueThreads) / 32) {
-        // =========================== MMA issuer ===========================
-        if (lane == 0) {
-            // c_format F32 (bit 4), a/b format F16 (0), N >> 3 at bit 17, M >> 4 at bit 24
-            const uint32_t idesc = (1u << 4) | ((uint32_t)(n_cols >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-            const uint32_t b_base = smem_u32(sm.b);
-            int it = 0;
-            for (int m = g; m < n_mtiles; m += G, ++it) {
-                const int s = it & 1;
-                const uint32_t k = (uint32_t)(it >> 1);
-                mbar_wait(&sm.a_full[s], k & 1);
-                mbar_wait(&sm.tmem_empty[s], (k & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t d = tmem_base + (uint32_t)(s * kBufStride);
-                const uint32_t a_base = smem_u32(sm.a[s]);
-#pragma unroll
-                for (int pass = 0; pass < 3; ++pass) {                        // hi*hi, lo*hi, hi*lo
-                    const uint32_t a = a_base + ((pass == 1) ? kChunksPerPart * kALbo : 0);
-                    const uint32_t b = b_base + ((pass == 2) ? kChunksPerPart * kBLbo : 0);
-#pragma unroll
-                    for (int ks = 0; ks < kChunksPerPart / 2; ++ks)
-                        mma_f16(d, make_desc(a + ks * 2 * kALbo, kALbo), make_desc(b + ks * 2 * kBLbo, kBLbo), idesc, (pass | ks) ? 1u : 0u);
-                }
-                mma_commit(&sm.a_empty[s]);
-                mma_commit(&sm.tmem_full[s]);
-            }
-        }
+        if (tid == 0 && n_it > 0) issue_mma(n_it - 1);
     } else {
         // =========================== epilogue ===========================
         // Three warpgroups; warp w may touch the TMEM lanes 32 (w % 4) .. + 31 (its rows), warpgroup grp takes the columns
@@ -274,41 +304,34 @@ emission_gmm_tc_kernel(const float* __restrict__ feat, int64_t n_frames, const u
         const int r = q * 32 + lane;
         const int c0 = grp * kEpiCols;
         const int st0 = c0 / MP;                                      // first state (local to the tile) of this warpgroup
+        const int n_mine = min(max(valid - st0, 0), kEpiCols / MP);   // states of this warpgroup's slice that exist
+        const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+        float* o_col = out + n_tile * SPT + st0;
         int it = 0;
         for (int m = g; m < n_mtiles; m += G, ++it) {
             const int s = it & 1;
-            const uint32_t k = (uint32_t)(it >> 1);
-            mbar_wait(&sm.tmem_full[s], k & 1);
+            mbar_wait(&sm.tmem_full[s], (uint32_t)(it >> 1) & 1);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * kBufStride) + (uint32_t)c0;
+            // the whole 80-column slice in one round of loads: the accumulator goes back to the MMA warp before any exp
+            float v[kEpiCols];
+            if (n_mine > 0) {                                         // warp-uniform: a narrow last tile reads nothing here
+                const uint32_t taddr = taddr0 + (uint32_t)(s * kBufStride);
+                tmem_ld32(taddr, v);
+                tmem_ld32(taddr + 32, v + 32);
+                tmem_ld16(taddr + 64, v + 64);
+                tmem_ld_wait();
+            }
+            tc_fence_before();
+            mbar_arrive(&sm.tmem_empty[s]);
             const int64_t f = (int64_t)m * kTileM + r;
-            const bool live = f < n_frames;
-            const bool slow = sm.slow[it & 3][r] != 0;
-            float* o = out + (live ? f : 0) * ld_out + n_tile * SPT;
-            // two rounds (48 + 32 columns: both multiples of MP) keep the accumulator slice of a thread at 48 registers
+            if (f < n_frames) {
+                float* o = o_col + f * ld_out;
+                if (sm.slow[it & 3][r] == 0) {
 #pragma unroll
-            for (int rd = 0; rd < 2; ++rd) {
-                constexpr int kR0 = 48;
-                const int cb = rd * kR0, nc = rd ? kEpiCols - kR0 : kR0;          // 0 / 48 columns into the slice, 48 / 32 wide
-                float v[kR0];
-                if (c0 + cb < valid * MP) {                                       // warp-uniform: a narrow last tile reads less
-                    if (rd == 0) { tmem_ld32(taddr, v); tmem_ld16(taddr + 32, v + 32); }
-                    else tmem_ld32(taddr + kR0, v);
-                    tmem_ld_wait();
-                }
-                if (rd == 1) {                                                    // the accumulator has been read: hand it back
-                    tc_fence_before();
-                    mbar_arrive(&sm.tmem_empty[s]);
-                }
-                if (live && !slow) {
-#pragma unroll
-                    for (int j = 0; j < kR0 / MP; ++j)
-                        if (j * MP < nc && st0 + cb / MP + j < valid) o[st0 + cb / MP + j] = lse<MP, FULL>(v + j * MP, n_mix);
+                    for (int j = 0; j < kEpiCols / MP; ++j)
+                        if (j < n_mine) o[j] = lse<MP, FULL>(v + j * MP, n_mix);
                 }
             }
-            if (live && slow && st0 < valid)
-                score_row_slow(feat + f * kDim, mean32, inv_var32, cst32, n_tile * SPT + st0, n_tile * SPT + min(valid, st0 + kEpiCols / MP),
-                               n_mix, o + st0);
         }
     }
     tc_fence_before();
