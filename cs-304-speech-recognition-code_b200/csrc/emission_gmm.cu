@@ -17,8 +17,8 @@
 // accumulation in TMEM: 15 MMAs of M128 N240 K16 per 128-frame tile.  The epilogue thread (= frame row) reads the
 // accumulator columns and does the log-sum-exp over each state's mixtures in registers.
 // B-stationary CTAs: one column tile of 240 (state, mixture) columns resident in shared memory (77 KB), frame tiles
-// streamed through it: raw feature tiles by cp.async.bulk (TMA engine), 4 producer warps (thread = row) build the A operand
-// (thread 0 also issues the MMAs, one tile behind), 12 epilogue warps in three warpgroups drain TMEM -- each warpgroup 80 columns = whole states
+// streamed through it: raw feature tiles by cp.async.bulk (TMA engine), 4 producer warps (thread = row) build the A operand,
+// one thread issues the MMAs, 12 epilogue warps in three warpgroups drain TMEM -- each warpgroup 80 columns = whole states
 // of every row, so the exp / log work of a tile (30 720 exponentials at 16 mixtures) is spread over 12 warps instead of
 // the 4 the TMEM lane rule suggests (the first version: epilogue-bound at 4 % of the tensor peak, ncu: profiles/).
 // Rows whose |z| reaches 128 (z^2 near the binary16 range) or is not finite are computed by their producer thread with
@@ -45,8 +45,8 @@ constexpr int kProducerThreads = 128;            // thread = frame row
 constexpr int kEpiGroups = 3;                    // epilogue warpgroups: each drains 80 of the 240 accumulator columns of every row
 constexpr int kEpiCols = kTileN / kEpiGroups;    // 80: a multiple of every padded mixture count (1, 2, 4, 8, 16)
 constexpr int kEpilogueThreads = 128 * kEpiGroups;
-constexpr int kThreads = kProducerThreads + kEpilogueThreads;   // 16 warps: registers are allocated to a CTA in groups of four warps, a seventeenth
-                                                                // (a dedicated MMA warp) would cost 20 warps' worth and cap every thread at 96
+constexpr int kThreads = kProducerThreads + kEpilogueThreads + 32;   // + the MMA warp.  17 warps are allocated as 20 (groups of four):
+                                                                     // 96 registers per thread, which a 48-column drain round fits
 constexpr int kALbo = kTileM * 16;          // 2048
 constexpr int kBLbo = kTileN * 16;          // 3840
 constexpr int kABytes = kAChunks * kALbo;   // 40960
@@ -219,35 +219,10 @@ emission_gmm_tc_kernel(const float* __restrict__ feat, int64_t n_frames, const u
             if (n_it > 0 && tile_full(0)) issue(0);
             if (n_it > 1 && tile_full(1)) issue(1);
         }
-        // Thread 0 also issues the MMAs, one tile behind the staging: by the time tile it is staged, every producer has
-        // arrived on a_full of tile it - 1 (the group barrier below), so the issue never waits on the staging, and the
-        // tensor pipe works on tile it - 1 while tile it is being split.
-        const uint32_t idesc = (1u << 4) | ((uint32_t)(n_cols >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);   // c F32, a / b F16, N >> 3, M >> 4
-        const uint32_t b_base = smem_u32(sm.b);
-        auto issue_mma = [&](int j) {
-            const int s = j & 1;
-            const uint32_t k = (uint32_t)(j >> 1);
-            mbar_wait(&sm.a_full[s], k & 1);
-            mbar_wait(&sm.tmem_empty[s], (k & 1) ^ 1);
-            tc_fence_after();
-            const uint32_t d = tmem_base + (uint32_t)(s * kBufStride);
-            const uint32_t a_base = smem_u32(sm.a[s]);
-#pragma unroll
-            for (int pass = 0; pass < 3; ++pass) {                        // hi*hi, lo*hi, hi*lo
-                const uint32_t a = a_base + ((pass == 1) ? kChunksPerPart * kALbo : 0);
-                const uint32_t b = b_base + ((pass == 2) ? kChunksPerPart * kBLbo : 0);
-#pragma unroll
-                for (int ks = 0; ks < kChunksPerPart / 2; ++ks)
-                    mma_f16(d, make_desc(a + ks * 2 * kALbo, kALbo), make_desc(b + ks * 2 * kBLbo, kBLbo), idesc, (pass | ks) ? 1u : 0u);
-            }
-            mma_commit(&sm.a_empty[s]);
-            mma_commit(&sm.tmem_full[s]);
-        };
         const int row_id = tid;
         for (int it = 0; it < n_it; ++it) {
             const int s = it & 1;
             const uint32_t k = (uint32_t)(it >> 1);
-            if (tid == 0 && it > 0) issue_mma(it - 1);
             if (tile_full(it)) {
                 mbar_wait(&sm.raw_full[s], k & 1);
             } else {
@@ -293,7 +268,33 @@ emission_gmm_tc_kernel(const float* __restrict__ feat, int64_t n_frames, const u
             if (slow && f < n_frames)
                 score_row_slow(feat + f * kDim, mean32, inv_var32, cst32, n_tile * SPT, n_tile * SPT + valid, n_mix, out + f * ld_out + n_tile * SPT);
         }
-        if (tid == 0 && n_it > 0) issue_mma(n_it - 1);
+    } else if (warp == (kProducerThreads + kEpilogueThreads) / 32) {
+        // =========================== MMA issuer ===========================
+        if (lane == 0) {
+            // c_format F32 (bit 4), a/b format F16 (0), N >> 3 at bit 17, M >> 4 at bit 24
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(n_cols >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+            const uint32_t b_base = smem_u32(sm.b);
+            int it = 0;
+            for (int m = g; m < n_mtiles; m += G, ++it) {
+                const int s = it & 1;
+                const uint32_t k = (uint32_t)(it >> 1);
+                mbar_wait(&sm.a_full[s], k & 1);
+                mbar_wait(&sm.tmem_empty[s], (k & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d = tmem_base + (uint32_t)(s * kBufStride);
+                const uint32_t a_base = smem_u32(sm.a[s]);
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {                        // hi*hi, lo*hi, hi*lo
+                    const uint32_t a = a_base + ((pass == 1) ? kChunksPerPart * kALbo : 0);
+                    const uint32_t b = b_base + ((pass == 2) ? kChunksPerPart * kBLbo : 0);
+#pragma unroll
+                    for (int ks = 0; ks < kChunksPerPart / 2; ++ks)
+                        mma_f16(d, make_desc(a + ks * 2 * kALbo, kALbo), make_desc(b + ks * 2 * kBLbo, kBLbo), idesc, (pass | ks) ? 1u : 0u);
+                }
+                mma_commit(&sm.a_empty[s]);
+                mma_commit(&sm.tmem_full[s]);
+            }
+        }
     } else {
         // =========================== epilogue ===========================
         // Three warpgroups; warp w may touch the TMEM lanes 32 (w % 4) .. + 31 (its rows), warpgroup grp takes the columns
@@ -312,25 +313,33 @@ emission_gmm_tc_kernel(const float* __restrict__ feat, int64_t n_frames, const u
             const int s = it & 1;
             mbar_wait(&sm.tmem_full[s], (uint32_t)(it >> 1) & 1);
             tc_fence_after();
-            // the whole 80-column slice in one round of loads: the accumulator goes back to the MMA warp before any exp
-            float v[kEpiCols];
+            // two rounds (48 + 32 columns: both multiples of MP): the accumulator slice of a thread stays at 48 registers
+            const uint32_t taddr = taddr0 + (uint32_t)(s * kBufStride);
+            const int64_t f = (int64_t)m * kTileM + r;
+            const bool work = f < n_frames && sm.slow[it & 3][r] == 0;
+            float* o = o_col + (f < n_frames ? f : 0) * ld_out;
+            constexpr int kR0 = 48, kS0 = kR0 / MP;                   // columns / states of the first round
+            float v[kR0];
             if (n_mine > 0) {                                         // warp-uniform: a narrow last tile reads nothing here
-                const uint32_t taddr = taddr0 + (uint32_t)(s * kBufStride);
                 tmem_ld32(taddr, v);
-                tmem_ld32(taddr + 32, v + 32);
-                tmem_ld16(taddr + 64, v + 64);
+                tmem_ld16(taddr + 32, v + 32);
+                tmem_ld_wait();
+            }
+            if (work) {
+#pragma unroll
+                for (int j = 0; j < kS0; ++j)
+                    if (j < n_mine) o[j] = lse<MP, FULL>(v + j * MP, n_mix);
+            }
+            if (n_mine > kS0) {
+                tmem_ld32(taddr + kR0, v);
                 tmem_ld_wait();
             }
             tc_fence_before();
-            mbar_arrive(&sm.tmem_empty[s]);
-            const int64_t f = (int64_t)m * kTileM + r;
-            if (f < n_frames) {
-                float* o = o_col + f * ld_out;
-                if (sm.slow[it & 3][r] == 0) {
+            mbar_arrive(&sm.tmem_empty[s]);                           // the accumulator has been read: hand it back
+            if (work) {
 #pragma unroll
-                    for (int j = 0; j < kEpiCols / MP; ++j)
-                        if (j < n_mine) o[j] = lse<MP, FULL>(v + j * MP, n_mix);
-                }
+                for (int j = kS0; j < kEpiCols / MP; ++j)
+                    if (j < n_mine) o[j] = lse<MP, FULL>(v + (j - kS0) * MP, n_mix);
             }
         }
     }
