@@ -98,7 +98,19 @@ static int ensure_tables() {
 // A warp works on batches of 10 frames: step 1 in 5 passes of 2 frames, step 2 in 2 passes of 5 frames
 // (30 lanes), then the mel filterbank one frame at a time with a filter per lane.
 constexpr int kWarpsA = 4;
-constexpr int kBatchA = 10;                 // frames per warp batch
+#ifndef LOE_MELR_MINB
+#define LOE_MELR_MINB 3
+#endif
+#ifndef LOE_MELR_PREFETCH
+#define LOE_MELR_PREFETCH 1
+#endif
+#ifndef LOE_MEL_BATCH
+#define LOE_MEL_BATCH 10
+#endif
+#ifndef LOE_MEL_MINB
+#define LOE_MEL_MINB 3
+#endif
+constexpr int kBatchA = LOE_MEL_BATCH;                 // frames per warp batch
 constexpr int kMinChunkA = 160;             // frames per CTA: at least this many
 constexpr int kSlotPitch = 17;              // complex entries per slot (16 used): step 2's slot reads spread over the banks
 constexpr int kSlots = 11;
@@ -217,7 +229,7 @@ template <> struct Pair<short> { using type = short2; };
 //                                     combined with two xor shuffles
 // entry (it, lane) = weight mel_w[it*32+lane] applied to power bin mel_bin[it*32+lane] (0-weight padding).
 template <typename SampleT, int NA, int NB>
-__global__ void __launch_bounds__(kWarpsA * 32, 3)
+__global__ void __launch_bounds__(kWarpsA * 32, LOE_MEL_MINB)
 mfcc_mel_kernel(const SampleT* __restrict__ pcm, const int64_t* __restrict__ pcm_off,
                 const int64_t* __restrict__ frm_off, const int32_t* __restrict__ mel_bin,
                 const float* __restrict__ mel_w, int na_rt, int nb_rt, int chunk,
@@ -336,9 +348,9 @@ mfcc_mel_kernel(const SampleT* __restrict__ pcm, const int64_t* __restrict__ pcm
         __syncwarp();
         // ---------------- step 2: two 16-point FFTs per thread, real-input post-pass, power spectrum
 #pragma unroll 1
-        for (int p = 0; p < 2; ++p) {
+        for (int p = 0; p < (kBatchA + 4) / 5; ++p) {
             const int fb = 5 * p + fl5;
-            const bool active = lane < 30 && tb + fb < t_end;
+            const bool active = lane < 30 && fb < kBatchA && tb + fb < t_end;
             float* fa = area + fb * kFramePitch;
             float2 za[16], zb[16];
             if (active) {
@@ -388,6 +400,274 @@ mfcc_mel_kernel(const SampleT* __restrict__ pcm, const int64_t* __restrict__ pcm
             mo[lane] = accA;
             if ((lane & 3) == 0) mo[32 + (lane >> 2)] = accB;
             vmax = fmaxf(vmax, fmaxf(accA, accB));
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(FULL, vmax, o));
+    if (lane == 0) atomicMax(reinterpret_cast<int*>(utt_max + u), __float_as_int(vmax));   // mel >= 0
+}
+
+// ------------------------------------------------------------------------------------------
+// Kernel A, real-input-first form (the 16 kHz table of every reference call site: na = 11, nb = 5)
+// ------------------------------------------------------------------------------------------
+// The 320-point real DFT is split 20 x 16 with the REAL transform first, so that no real-input post-pass exists:
+//   n = 16 n1 + n2, k = k1 + 20 k2
+//   step 1, thread (frame, n2):  T[k1][n2] = W_320^(n2 k1) * sum_n1 w[n] x[n] W_20^(n1 k1)   for k1 = 0..10 only (real input:
+//            k1 = 11..19 are conjugates).  The 20-point real DFT is a prime-factor 4 x 5 transform without twiddles:
+//            n1 = (5 a + 4 b) mod 20, k1 = c mod 4 = d mod 5; five real 4-point DFTs with the window folded into their
+//            first butterflies, then real 5-point DFTs for c = 0 and c = 2 and one complex 5-point DFT for c = 1
+//            (c = 3 is its conjugate).
+//   step 2, thread (frame, k1):  X[k1 + 20 k2] = sum_n2 T[k1][n2] W_16^(n2 k2): one 16-point FFT, whose 16 outputs are 16
+//            DIFFERENT bins of the power spectrum (bins above 160 are the mirror images 320 - k); the rows k1 = 0 and
+//            k1 = 10 mirror onto themselves and write 9 and 8 distinct bins.
+// A warp works on batches of 8 frames: step 1 in 4 passes of 2 frames x 16 lanes, step 2 in 3 passes of 8 frames x 4 rows,
+// then the filterbank for all 8 frames at once with a filter per lane: the power spectra are stored [plane of 4 frames][bin]
+// [frame], so one 16-byte load brings a bin of four frames and a weight is fetched once per 8 frames.
+// Shared memory per warp: 11 rows x 8 frames x (128 + 16) bytes; the two power planes take the place of rows 4..10, which is
+// why step 2 starts with the rows 8..10 (results kept in registers), then 4..7, then 0..3.
+namespace r20 {
+constexpr int kWarps = 4;
+constexpr int kBatch = 8;
+constexpr int kFrameB = 144;                 // bytes per (row, frame): 16 complex + 16: the 16-byte loads of 8 frames hit 8 bank groups
+constexpr int kRowB = kBatch * kFrameB;      // 1152
+constexpr int kRows = 11;
+constexpr int kAreaB = kRows * kRowB;        // 12672 bytes per warp
+constexpr int kPlaneB = 3136;                // 196 bins x 16 bytes; 16 banks mod 32: the two planes' stores never collide
+constexpr int kPlane0 = 4 * kRowB;
+constexpr int kNA = 11, kNB = 5;
+static_assert(kPlane0 + 2 * kPlaneB <= kAreaB, "power planes must fit the rows 4..10");
+static_assert(kBins * 16 <= kPlaneB, "plane too small");
+
+struct __align__(16) Smem {
+    unsigned char area[kWarps][kAreaB];
+    float mel_w[(kNA + kNB) * 32];
+};
+
+// real-input 5-point DFT: V[0] = v0, V[1] = m1 - i q1, V[4] = m1 + i q1, V[2] = m2 - i q2, V[3] = m2 + i q2
+__device__ __forceinline__ void rdft5(float r0, float r1, float r2, float r3, float r4,
+                                      float& v0, float& m1, float& q1, float& m2, float& q2) {
+    const float C1 = 0.30901699437494745f, C2 = -0.80901699437494745f;
+    const float S1 = 0.95105651629515353f, S2 = 0.58778525229247314f;
+    const float t1 = r1 + r4, t2 = r2 + r3, t3 = r1 - r4, t4 = r2 - r3;
+    v0 = (r0 + t1) + t2;
+    m1 = fmaf(C2, t2, fmaf(C1, t1, r0));
+    m2 = fmaf(C1, t2, fmaf(C2, t1, r0));
+    q1 = fmaf(S2, t4, S1 * t3);
+    q2 = fmaf(-S1, t4, S2 * t3);
+}
+}  // namespace r20
+
+template <typename SampleT>
+__global__ void __launch_bounds__(r20::kWarps * 32, LOE_MELR_MINB)
+mfcc_mel_r_kernel(const SampleT* __restrict__ pcm, const int64_t* __restrict__ pcm_off,
+                  const int64_t* __restrict__ frm_off, const int32_t* __restrict__ mel_bin,
+                  const float* __restrict__ mel_w, int chunk,
+                  float* __restrict__ mel_out, float* __restrict__ utt_max) {
+    using namespace r20;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+    const int u = blockIdx.x;
+    const int64_t f0 = frm_off[u];
+    const int T = (int)(frm_off[u + 1] - f0);
+    const int t_begin = blockIdx.y * chunk;
+    if (t_begin >= T) return;
+    const int t_end = min(T, t_begin + chunk);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr unsigned FULL = 0xffffffffu;
+
+    for (int i = tid; i < (kNA + kNB) * 32; i += kWarps * 32) sm.mel_w[i] = mel_w[i];
+    // power planes start out finite (zero-weight table entries read bins of frames that do not exist in a partial batch)
+    for (int i = tid; i < kWarps * kAreaB / 4; i += kWarps * 32) reinterpret_cast<float*>(&sm.area[0][0])[i] = 0.f;
+
+    // step 1 constants, thread = (frame parity fl, n2): window taps w[16 n1 + n2] and W_320^(n2 k1), k1 = 1..10
+    const int n2 = lane & 15, fl = lane >> 4;
+    float hw[20];
+    float2 tw[11];
+#pragma unroll
+    for (int n1 = 0; n1 < 20; ++n1) hw[n1] = g_mfcc_tables.hann[16 * n1 + n2];
+#pragma unroll
+    for (int k1 = 1; k1 <= 10; ++k1) tw[k1] = make_float2(g_mfcc_tables.w320_re[n2 * k1], g_mfcc_tables.w320_im[n2 * k1]);
+    // step 2: thread = (frame f8, row kq + 4 * pass)
+    const int f8 = lane & 7, kq = lane >> 3;
+    const int binA = mel_bin[lane], binB = mel_bin[kNA * 32 + lane];
+    __syncthreads();
+
+    const int64_t s0 = pcm_off[u];
+    const int64_t n_samples = pcm_off[u + 1] - s0;
+    const SampleT* __restrict__ x = pcm + s0;
+    unsigned char* area = sm.area[warp];
+    float vmax = 0.f;
+
+    // samples of one step-1 item: x[160 t - 160 + 16 n1 + n2], zero outside the utterance (centre padding)
+    auto fetch = [&](int t, float* dst) {
+        const int64_t base = (int64_t)kHop * t - kHalf;
+        if (base >= 0 && base + kNfft <= n_samples) {
+            const SampleT* __restrict__ xb = x + base + n2;
+#pragma unroll
+            for (int n1 = 0; n1 < 20; ++n1) dst[n1] = to_f32(__ldg(xb + 16 * n1));
+        } else {
+#pragma unroll
+            for (int n1 = 0; n1 < 20; ++n1) {
+                const int64_t i = base + 16 * n1 + n2;
+                dst[n1] = (i >= 0 && i < n_samples) ? to_f32(__ldg(x + i)) : 0.f;
+            }
+        }
+    };
+#if LOE_MELR_PREFETCH
+    float vn[20];
+#pragma unroll
+    for (int n1 = 0; n1 < 20; ++n1) vn[n1] = 0.f;
+    if (t_begin + warp * kBatch + fl < t_end) fetch(t_begin + warp * kBatch + fl, vn);
+#endif
+
+    for (int tb = t_begin + warp * kBatch; tb < t_end; tb += kWarps * kBatch) {
+        {   // pull the samples of this warp's next batch into L2
+            const int tbn = tb + kWarps * kBatch;
+            if (tbn < t_end) {
+                const int64_t lo = max((int64_t)0, (int64_t)kHop * tbn - kHalf);
+                const int64_t hi = min(n_samples, (int64_t)kHop * (tbn + kBatch) + kHalf);
+                constexpr int kPerLine = 128 / (int)sizeof(SampleT);
+                for (int64_t i = lo + (int64_t)lane * kPerLine; i < hi; i += 32 * kPerLine)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(x + i));
+            }
+        }
+        // ---------------- step 1
+#pragma unroll 1
+        for (int p = 0; p < kBatch / 2; ++p) {
+            const int fb = 2 * p + fl, t = tb + fb;
+            float v[20];
+#if LOE_MELR_PREFETCH
+#pragma unroll
+            for (int n1 = 0; n1 < 20; ++n1) v[n1] = vn[n1];
+            const int tn = (p < kBatch / 2 - 1) ? t + 2 : tb + kWarps * kBatch + fl;
+            if (tn < t_end) fetch(tn, vn);
+#else
+            if (t < t_end) fetch(t, v);
+#endif
+            if (t < t_end) {
+                // five real 4-point DFTs over a (n1 = (5 a + 4 b) mod 20), window folded into the first butterflies
+                float u0[5], u2[5];
+                float2 u1[5];
+#pragma unroll
+                for (int b = 0; b < 5; ++b) {
+                    const int i0 = (4 * b) % 20, i1 = (5 + 4 * b) % 20, i2 = (10 + 4 * b) % 20, i3 = (15 + 4 * b) % 20;
+                    const float p0 = hw[i0] * v[i0], p1 = hw[i1] * v[i1];
+                    const float s0_ = fmaf(hw[i2], v[i2], p0), s1_ = fmaf(-hw[i2], v[i2], p0);
+                    const float s2_ = fmaf(hw[i3], v[i3], p1), s3_ = fmaf(-hw[i3], v[i3], p1);
+                    u0[b] = s0_ + s2_;
+                    u2[b] = s0_ - s2_;
+                    u1[b] = make_float2(s1_, -s3_);
+                }
+                float2 Y[11];
+                {
+                    float v0, m1, q1, m2, q2;
+                    rdft5(u0[0], u0[1], u0[2], u0[3], u0[4], v0, m1, q1, m2, q2);      // c = 0: k1 = 0, 4 (d = 4), 8 (d = 3)
+                    Y[0] = make_float2(v0, 0.f); Y[4] = make_float2(m1, q1); Y[8] = make_float2(m2, q2);
+                    rdft5(u2[0], u2[1], u2[2], u2[3], u2[4], v0, m1, q1, m2, q2);      // c = 2: k1 = 10, 6 (d = 1), 2 (d = 2)
+                    Y[10] = make_float2(v0, 0.f); Y[6] = make_float2(m1, -q1); Y[2] = make_float2(m2, -q2);
+                    float2 V[5];
+                    dft5(u1[0], u1[1], u1[2], u1[3], u1[4], V);                           // c = 1: k1 = 5, 1, 17, 13, 9
+                    Y[5] = V[0]; Y[1] = V[1]; Y[9] = V[4];
+                    Y[3] = make_float2(V[2].x, -V[2].y);                                   // conj of k1 = 17
+                    Y[7] = make_float2(V[3].x, -V[3].y);                                   // conj of k1 = 13
+                }
+                float2* slot = reinterpret_cast<float2*>(area + fb * kFrameB) + n2;
+                slot[0] = Y[0];
+#pragma unroll
+                for (int k1 = 1; k1 < 10; ++k1) slot[k1 * (kRowB / 8)] = cmul(Y[k1], tw[k1]);
+                slot[10 * (kRowB / 8)] = make_float2(Y[10].x * tw[10].x, Y[10].x * tw[10].y);
+            }
+        }
+        __syncwarp();
+        // ---------------- step 2
+        const bool fvalid = tb + f8 < t_end;
+        float* plane = reinterpret_cast<float*>(area + kPlane0 + (f8 >> 2) * kPlaneB) + (f8 & 3);
+        auto load_row = [&](int k1, float2* z) {
+            const float4* src = reinterpret_cast<const float4*>(area + k1 * kRowB + f8 * kFrameB);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float4 q = src[c];
+                z[2 * c] = make_float2(q.x, q.y);
+                z[2 * c + 1] = make_float2(q.z, q.w);
+            }
+        };
+        auto store_pw = [&](int k1, const float* pw) {
+            float* lo = plane + 4 * k1;                    // bin k1 + 20 k2, k2 = 0..7
+            float* hi = plane + 4 * (320 - k1);            // bin 320 - k1 - 20 k2, k2 = 8..15
+#pragma unroll
+            for (int k2 = 0; k2 < 8; ++k2) lo[80 * k2] = pw[k2];
+#pragma unroll
+            for (int k2 = 8; k2 < 16; ++k2) hi[-80 * k2] = pw[k2];
+        };
+        float pc[16];
+        {
+            float2 z[16];
+            const bool act = fvalid && kq < 3;
+            if (act) {
+                load_row(8 + kq, z);
+                fft16(z);
+#pragma unroll
+                for (int k2 = 0; k2 < 16; ++k2) pc[k2] = fmaf(z[k2].x, z[k2].x, z[k2].y * z[k2].y);
+            }
+            float2 zb[16];
+            if (fvalid) load_row(4 + kq, zb);
+            __syncwarp();                                   // rows 4..10 are in registers: their area takes the power planes
+            if (act) store_pw(8 + kq, pc);
+            if (fvalid) {
+                fft16(zb);
+#pragma unroll
+                for (int k2 = 0; k2 < 16; ++k2) pc[k2] = fmaf(zb[k2].x, zb[k2].x, zb[k2].y * zb[k2].y);
+                store_pw(4 + kq, pc);
+                load_row(kq, z);
+                fft16(z);
+#pragma unroll
+                for (int k2 = 0; k2 < 16; ++k2) pc[k2] = fmaf(z[k2].x, z[k2].x, z[k2].y * z[k2].y);
+                store_pw(kq, pc);
+            }
+        }
+        __syncwarp();
+        // ---------------- mel filterbank, 8 frames at once
+        {
+            const int nf = min(kBatch, t_end - tb);
+            const unsigned char* pa = area + kPlane0 + binA * 16;
+            float acc[8];
+#pragma unroll
+            for (int f = 0; f < 8; ++f) acc[f] = 0.f;
+#pragma unroll
+            for (int it = 0; it < kNA; ++it) {
+                const float w = sm.mel_w[it * 32 + lane];
+                const float4 p = *reinterpret_cast<const float4*>(pa + it * 16);
+                const float4 q = *reinterpret_cast<const float4*>(pa + kPlaneB + it * 16);
+                acc[0] = fmaf(w, p.x, acc[0]); acc[1] = fmaf(w, p.y, acc[1]); acc[2] = fmaf(w, p.z, acc[2]); acc[3] = fmaf(w, p.w, acc[3]);
+                acc[4] = fmaf(w, q.x, acc[4]); acc[5] = fmaf(w, q.y, acc[5]); acc[6] = fmaf(w, q.z, acc[6]); acc[7] = fmaf(w, q.w, acc[7]);
+            }
+            float* mo = mel_out + (f0 + tb) * kMels + lane;
+#pragma unroll
+            for (int f = 0; f < 8; ++f)
+                if (f < nf) { mo[f * kMels] = acc[f]; vmax = fmaxf(vmax, acc[f]); }
+            const unsigned char* pb = area + kPlane0 + binB * 16;
+#pragma unroll
+            for (int f = 0; f < 8; ++f) acc[f] = 0.f;
+#pragma unroll
+            for (int it = 0; it < kNB; ++it) {
+                const float w = sm.mel_w[(kNA + it) * 32 + lane];
+                const float4 p = *reinterpret_cast<const float4*>(pb + it * 64);
+                const float4 q = *reinterpret_cast<const float4*>(pb + kPlaneB + it * 64);
+                acc[0] = fmaf(w, p.x, acc[0]); acc[1] = fmaf(w, p.y, acc[1]); acc[2] = fmaf(w, p.z, acc[2]); acc[3] = fmaf(w, p.w, acc[3]);
+                acc[4] = fmaf(w, q.x, acc[4]); acc[5] = fmaf(w, q.y, acc[5]); acc[6] = fmaf(w, q.z, acc[6]); acc[7] = fmaf(w, q.w, acc[7]);
+            }
+#pragma unroll
+            for (int f = 0; f < 8; ++f) {
+                acc[f] += __shfl_xor_sync(FULL, acc[f], 1);
+                acc[f] += __shfl_xor_sync(FULL, acc[f], 2);
+            }
+            float* mb = mel_out + (f0 + tb) * kMels + 32 + (lane >> 2);
+            if ((lane & 3) == 0) {
+#pragma unroll
+                for (int f = 0; f < 8; ++f)
+                    if (f < nf) { mb[f * kMels] = acc[f]; vmax = fmaxf(vmax, acc[f]); }
+            }
         }
         __syncwarp();
     }
@@ -541,20 +821,26 @@ static int mfcc_launch(const void* pcm_dev, int pcm_format, const int64_t* pcm_o
         int sms = 0, dev = 0;
         LOE_CUDA(cudaGetDevice(&dev));
         LOE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        const bool k16 = (mel_na == r20::kNA && mel_nb == r20::kNB);      // the 16 kHz table of every reference call site
+        const int round = k16 ? r20::kWarps * r20::kBatch : kWarpsA * kBatchA;    // whole rounds of the CTA's warps
         int64_t chunk64 = total_frames / (12 * (int64_t)sms);
-        chunk64 = ((chunk64 + kWarpsA * kBatchA - 1) / (kWarpsA * kBatchA)) * (kWarpsA * kBatchA);   // whole rounds of the CTA's warps
+        chunk64 = ((chunk64 + round - 1) / round) * round;
         const int chunk = (int)(chunk64 < kMinChunkA ? kMinChunkA : chunk64 > (1 << 20) ? (1 << 20) : chunk64);
         dim3 ga((unsigned)n_utt, (unsigned)((max_frames + chunk - 1) / chunk));
-        const bool k16 = (mel_na == 11 && mel_nb == 5);      // the 16 kHz table of every reference call site
-        // the kernel's shared memory (slots of 4 warps x 10 frames) exceeds the 48 KB default: opt in, once per device
-#define LOE_MEL_LAUNCH(T, A, B)                                                                                          \
-        LOE_CUDA(cudaFuncSetAttribute(mfcc_mel_kernel<T, A, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemA))); \
-        mfcc_mel_kernel<T, A, B><<<ga, kWarpsA * 32, sizeof(SmemA), s>>>((const T*)pcm_dev, pcm_off_dev, frm_off_dev, mel_bin_dev, \
+        // the kernels' shared memory (exchange area of 4 warps) exceeds the 48 KB default: opt in
+#define LOE_MEL_LAUNCH(T)                                                                                                \
+        LOE_CUDA(cudaFuncSetAttribute(mfcc_mel_kernel<T, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemA))); \
+        mfcc_mel_kernel<T, 0, 0><<<ga, kWarpsA * 32, sizeof(SmemA), s>>>((const T*)pcm_dev, pcm_off_dev, frm_off_dev, mel_bin_dev, \
                                                                         mel_w_dev, mel_na, mel_nb, chunk, mel_ws_dev, utt_max_dev)
-        if (pcm_format == LOE_PCM_F32) { if (k16) { LOE_MEL_LAUNCH(float, 11, 5); } else { LOE_MEL_LAUNCH(float, 0, 0); } }
-        else if (pcm_format == LOE_PCM_S16) { if (k16) { LOE_MEL_LAUNCH(short, 11, 5); } else { LOE_MEL_LAUNCH(short, 0, 0); } }
+#define LOE_MELR_LAUNCH(T)                                                                                               \
+        LOE_CUDA(cudaFuncSetAttribute(mfcc_mel_r_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(r20::Smem))); \
+        mfcc_mel_r_kernel<T><<<ga, r20::kWarps * 32, sizeof(r20::Smem), s>>>((const T*)pcm_dev, pcm_off_dev, frm_off_dev, mel_bin_dev, \
+                                                                            mel_w_dev, chunk, mel_ws_dev, utt_max_dev)
+        if (pcm_format == LOE_PCM_F32) { if (k16) { LOE_MELR_LAUNCH(float); } else { LOE_MEL_LAUNCH(float); } }
+        else if (pcm_format == LOE_PCM_S16) { if (k16) { LOE_MELR_LAUNCH(short); } else { LOE_MEL_LAUNCH(short); } }
         else { set_error("unknown pcm_format %d", pcm_format); return LOE_ERR_VALUE; }
 #undef LOE_MEL_LAUNCH
+#undef LOE_MELR_LAUNCH
         LOE_LAUNCH_CHECK("mfcc_mel_kernel");
     }
     if (phases & 2) {
