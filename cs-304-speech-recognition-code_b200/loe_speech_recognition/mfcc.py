@@ -8,7 +8,8 @@ power_to_db(ref=np.max), mfcc(n_mfcc=13), delta, delta order 2); the kernels res
 pipeline.  Only the filterbank weights are prepared on the host (once per
 sample rate).
 """
-from __future__ import annotations
+from __future__ import functools
+import annotations
 
 from dataclasses import dataclass, field
 from typing import List
@@ -83,6 +84,57 @@ def _distinct_bank_starts(first, last, span, lanes_per_filter):
     return chosen if place(0, set()) else None
 
 
+def _quarter_wavefronts(starts, first, last, span, lanes_per_filter):
+    """Shared-memory wavefronts of one quarter-warp walking its windows in the [bin][4 frames] power layout of
+    mfcc_mel_r_kernel (16 bytes per bin, loads of zero-weight entries predicated off): per iteration the largest
+    number of DIFFERENT active bins that share a 16-byte bank group (bin mod 8)."""
+    total = 0
+    for it in range(span // lanes_per_filter):
+        groups = {}
+        for f, w in enumerate(starts):
+            for j in range(lanes_per_filter):
+                b = w + j + lanes_per_filter * it
+                if first[f] <= b <= last[f]:
+                    groups.setdefault(b % 8, set()).add(b)
+        total += max((len(v) for v in groups.values()), default=0)
+    return total
+
+
+def _min_wavefront_starts(first, last, span, lanes_per_filter, restarts=120):
+    """Window starts (w[f] <= first[f], w[f] + span > last[f], w[f] >= 0) for the 16-byte-per-bin layout: per
+    quarter-warp (8 lanes = 8 / lanes_per_filter filters) coordinate descent on _quarter_wavefronts from the natural
+    starts and from seeded random starts (deterministic); staggering the supports of narrow filters over the
+    iterations halves the wavefronts of the natural starts at 16 kHz."""
+    import random
+    rnd = random.Random(304)
+    n = len(first)
+    per_q = 8 // lanes_per_filter
+    chosen = list(first)
+    for q0 in range(0, n, per_q):
+        fs = list(range(q0, min(n, q0 + per_q)))
+        cands = [[w for w in range(first[f], last[f] - span, -1) if w >= 0] for f in fs]
+        fi, la = [first[f] for f in fs], [last[f] for f in fs]
+        best = None
+        for r in range(restarts):
+            cur = list(fi) if r == 0 else [rnd.choice(c) for c in cands]
+            cost = _quarter_wavefronts(cur, fi, la, span, lanes_per_filter)
+            improved = True
+            while improved:
+                improved = False
+                for i in range(len(fs)):
+                    for w in cands[i]:
+                        trial = cur[:i] + [w] + cur[i + 1:]
+                        c = _quarter_wavefronts(trial, fi, la, span, lanes_per_filter)
+                        if c < cost:
+                            cost, cur, improved = c, trial, True
+            if best is None or cost < best[0]:
+                best = (cost, cur)
+        for f, w in zip(fs, best[1]):
+            chosen[f] = w
+    return chosen
+
+
+@functools.lru_cache(maxsize=8)
 def mel_lane_tables(sample_rate: float):
     """The filterbank in the lane-balanced layout loe_mfcc_dev reads (include/loe_b200.h):
     (bin int32 [(na+nb)*32], weight float32 [(na+nb)*32], na, nb).  Round A: lane l owns filter l
@@ -104,8 +156,13 @@ def mel_lane_tables(sample_rate: float):
     last = [int(nz[m][-1]) if len(nz[m]) else 0 for m in range(N_MELS)]
     for m in range(N_MELS):
         assert len(nz[m]) == 0 or np.array_equal(nz[m], np.arange(first[m], last[m] + 1))
-    start_a = _distinct_bank_starts(first[:32], last[:32], na, 1) or first[:32]
-    start_b = _distinct_bank_starts(first[32:], last[32:], 4 * nb, 4) or first[32:]
+    if (na, nb) == (11, 5):
+        # the 16 kHz table: mfcc_mel_r_kernel reads 16-byte [bin][4 frames] entries, a quarter-warp per wavefront
+        start_a = _min_wavefront_starts(first[:32], last[:32], na, 1)
+        start_b = _min_wavefront_starts(first[32:], last[32:], 4 * nb, 4)
+    else:
+        start_a = _distinct_bank_starts(first[:32], last[:32], na, 1) or first[:32]
+        start_b = _distinct_bank_starts(first[32:], last[32:], 4 * nb, 4) or first[32:]
     bins = np.zeros((na + nb, 32), dtype=np.int32)
     w = np.zeros((na + nb, 32), dtype=np.float32)
     n_bins = dense.shape[1]

@@ -101,6 +101,9 @@ constexpr int kWarpsA = 4;
 #ifndef LOE_MELR_MINB
 #define LOE_MELR_MINB 3
 #endif
+#ifndef LOE_MELR_PREFETCH
+#define LOE_MELR_PREFETCH 1
+#endif
 #ifndef LOE_MEL_BATCH
 #define LOE_MEL_BATCH 10
 #endif
@@ -496,37 +499,36 @@ mfcc_mel_r_kernel(const SampleT* __restrict__ pcm, const int64_t* __restrict__ p
     unsigned char* area = sm.area[warp];
     float vmax = 0.f;
 
-    const int ns = (int)n_samples;                    // one utterance: fits 32 bits
-    // samples of one step-1 item: x[160 t - 160 + 16 n1 + n2], zero outside the utterance (centre padding).
-    // Interior frames (all but the first and the last one or two of an utterance) are requested WITHOUT any test, from a
-    // base clamped into the utterance, as soon as the window butterflies have consumed the current samples (into the
-    // same registers: the loads are in flight for the rest of the item, across batches too).  A frame that reaches
-    // outside the utterance is fetched again, with bounds tests, when its turn comes.
-    const int base_max = ns - kNfft;                  // >= 0: an utterance has at least 9 frames
-    auto edge = [&](int t) { const int base = kHop * t - kHalf; return base < 0 || base > base_max; };
-    auto fetch_interior = [&](int t, float* dst) {
-        const SampleT* __restrict__ xb = x + min(max(kHop * t - kHalf, 0), base_max) + n2;
+    // samples of one step-1 item: x[160 t - 160 + 16 n1 + n2], zero outside the utterance (centre padding)
+    auto fetch = [&](int t, float* dst) {
+        const int64_t base = (int64_t)kHop * t - kHalf;
+        if (base >= 0 && base + kNfft <= n_samples) {
+            const SampleT* __restrict__ xb = x + base + n2;
 #pragma unroll
-        for (int n1 = 0; n1 < 20; ++n1) dst[n1] = to_f32(__ldg(xb + 16 * n1));
-    };
-    auto fetch_edge = [&](int t, float* dst) {
-        const int base = kHop * t - kHalf;
+            for (int n1 = 0; n1 < 20; ++n1) dst[n1] = to_f32(__ldg(xb + 16 * n1));
+        } else {
 #pragma unroll
-        for (int n1 = 0; n1 < 20; ++n1) {
-            const int i = base + 16 * n1 + n2;
-            dst[n1] = (i >= 0 && i < ns) ? to_f32(__ldg(x + i)) : 0.f;
+            for (int n1 = 0; n1 < 20; ++n1) {
+                const int64_t i = base + 16 * n1 + n2;
+                dst[n1] = (i >= 0 && i < n_samples) ? to_f32(__ldg(x + i)) : 0.f;
+            }
         }
     };
-    float v[20];
-    fetch_interior(t_begin + warp * kBatch + fl, v);
+#if LOE_MELR_PREFETCH
+    float vn[20];
+#pragma unroll
+    for (int n1 = 0; n1 < 20; ++n1) vn[n1] = 0.f;
+    if (t_begin + warp * kBatch + fl < t_end) fetch(t_begin + warp * kBatch + fl, vn);
+#endif
 
     for (int tb = t_begin + warp * kBatch; tb < t_end; tb += kWarps * kBatch) {
         {   // pull the samples of this warp's next batch into L2
             const int tbn = tb + kWarps * kBatch;
             if (tbn < t_end) {
+                const int64_t lo = max((int64_t)0, (int64_t)kHop * tbn - kHalf);
+                const int64_t hi = min(n_samples, (int64_t)kHop * (tbn + kBatch) + kHalf);
                 constexpr int kPerLine = 128 / (int)sizeof(SampleT);
-                const int lo = max(0, kHop * tbn - kHalf), hi = min(ns, kHop * (tbn + kBatch) + kHalf);
-                for (int i = lo + lane * kPerLine; i < hi; i += 32 * kPerLine)
+                for (int64_t i = lo + (int64_t)lane * kPerLine; i < hi; i += 32 * kPerLine)
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(x + i));
             }
         }
@@ -534,22 +536,29 @@ mfcc_mel_r_kernel(const SampleT* __restrict__ pcm, const int64_t* __restrict__ p
 #pragma unroll 1
         for (int p = 0; p < kBatch / 2; ++p) {
             const int fb = 2 * p + fl, t = tb + fb;
-            if (edge(t) && t < t_end) fetch_edge(t, v);
-            // five real 4-point DFTs over a (n1 = (5 a + 4 b) mod 20), window folded into the first butterflies
-            float u0[5], u2[5];
-            float2 u1[5];
+            float v[20];
+#if LOE_MELR_PREFETCH
 #pragma unroll
-            for (int b = 0; b < 5; ++b) {
-                const int i0 = (4 * b) % 20, i1 = (5 + 4 * b) % 20, i2 = (10 + 4 * b) % 20, i3 = (15 + 4 * b) % 20;
-                const float p0 = hw[i0] * v[i0], p1 = hw[i1] * v[i1];
-                const float s0_ = fmaf(hw[i2], v[i2], p0), s1_ = fmaf(-hw[i2], v[i2], p0);
-                const float s2_ = fmaf(hw[i3], v[i3], p1), s3_ = fmaf(-hw[i3], v[i3], p1);
-                u0[b] = s0_ + s2_;
-                u2[b] = s0_ - s2_;
-                u1[b] = make_float2(s1_, -s3_);
-            }
-            fetch_interior((p < kBatch / 2 - 1) ? t + 2 : tb + kWarps * kBatch + fl, v);
+            for (int n1 = 0; n1 < 20; ++n1) v[n1] = vn[n1];
+            const int tn = (p < kBatch / 2 - 1) ? t + 2 : tb + kWarps * kBatch + fl;
+            if (tn < t_end) fetch(tn, vn);
+#else
+            if (t < t_end) fetch(t, v);
+#endif
             if (t < t_end) {
+                // five real 4-point DFTs over a (n1 = (5 a + 4 b) mod 20), window folded into the first butterflies
+                float u0[5], u2[5];
+                float2 u1[5];
+#pragma unroll
+                for (int b = 0; b < 5; ++b) {
+                    const int i0 = (4 * b) % 20, i1 = (5 + 4 * b) % 20, i2 = (10 + 4 * b) % 20, i3 = (15 + 4 * b) % 20;
+                    const float p0 = hw[i0] * v[i0], p1 = hw[i1] * v[i1];
+                    const float s0_ = fmaf(hw[i2], v[i2], p0), s1_ = fmaf(-hw[i2], v[i2], p0);
+                    const float s2_ = fmaf(hw[i3], v[i3], p1), s3_ = fmaf(-hw[i3], v[i3], p1);
+                    u0[b] = s0_ + s2_;
+                    u2[b] = s0_ - s2_;
+                    u1[b] = make_float2(s1_, -s3_);
+                }
                 float2 Y[11];
                 {
                     float v0, m1, q1, m2, q2;

@@ -101,6 +101,9 @@ constexpr int kWarpsA = 4;
 #ifndef LOE_MELR_MINB
 #define LOE_MELR_MINB 3
 #endif
+#ifndef LOE_MELR_PRED
+#define LOE_MELR_PRED 1
+#endif
 #ifndef LOE_MEL_BATCH
 #define LOE_MEL_BATCH 10
 #endif
@@ -497,78 +500,89 @@ mfcc_mel_r_kernel(const SampleT* __restrict__ pcm, const int64_t* __restrict__ p
     float vmax = 0.f;
 
     const int ns = (int)n_samples;                    // one utterance: fits 32 bits
-    // samples of one step-1 item: x[160 t - 160 + 16 n1 + n2], zero outside the utterance (centre padding).
-    // Interior frames (all but the first and the last one or two of an utterance) are requested WITHOUT any test, from a
-    // base clamped into the utterance, as soon as the window butterflies have consumed the current samples (into the
-    // same registers: the loads are in flight for the rest of the item, across batches too).  A frame that reaches
-    // outside the utterance is fetched again, with bounds tests, when its turn comes.
-    const int base_max = ns - kNfft;                  // >= 0: an utterance has at least 9 frames
-    auto edge = [&](int t) { const int base = kHop * t - kHalf; return base < 0 || base > base_max; };
-    auto fetch_interior = [&](int t, float* dst) {
-        const SampleT* __restrict__ xb = x + min(max(kHop * t - kHalf, 0), base_max) + n2;
+    // H(t)[j] = x[160 (t - 1) + 16 j + n2], j = 0..9: the ten samples of this lane in the hop before frame centre t, zero
+    // outside the utterance (centre padding).  Frame t uses H(t) (n1 = 0..9) and H(t + 1) (n1 = 10..19): a thread walks
+    // four CONSECUTIVE frames per batch, so every sample is loaded once per batch and lane
+    auto fetch = [&](int t, float* dst) {
+        const int base = kHop * t - kHop;
+        if (base >= 0 && base + kHop <= ns) {
+            const SampleT* __restrict__ xb = x + base + n2;
 #pragma unroll
-        for (int n1 = 0; n1 < 20; ++n1) dst[n1] = to_f32(__ldg(xb + 16 * n1));
-    };
-    auto fetch_edge = [&](int t, float* dst) {
-        const int base = kHop * t - kHalf;
+            for (int j = 0; j < 10; ++j) dst[j] = to_f32(__ldg(xb + 16 * j));
+        } else {
 #pragma unroll
-        for (int n1 = 0; n1 < 20; ++n1) {
-            const int i = base + 16 * n1 + n2;
-            dst[n1] = (i >= 0 && i < ns) ? to_f32(__ldg(x + i)) : 0.f;
+            for (int j = 0; j < 10; ++j) {
+                const int i = base + 16 * j + n2;
+                dst[j] = (i >= 0 && i < ns) ? to_f32(__ldg(x + i)) : 0.f;
+            }
         }
     };
-    float v[20];
-    fetch_interior(t_begin + warp * kBatch + fl, v);
+    // window, 20-point real DFT, twiddles, store the 11 rows of frame slot fb
+    auto item = [&](int fb, const float* va, const float* vb) {
+        // five real 4-point DFTs over a (n1 = (5 a + 4 b) mod 20), window folded into the first butterflies
+        float u0[5], u2[5];
+        float2 u1[5];
+#pragma unroll
+        for (int b = 0; b < 5; ++b) {
+            const int i0 = (4 * b) % 20, i1 = (5 + 4 * b) % 20, i2 = (10 + 4 * b) % 20, i3 = (15 + 4 * b) % 20;
+#define LOE_V(i) ((i) < 10 ? va[(i) % 10] : vb[(i) % 10])
+            const float p0 = hw[i0] * LOE_V(i0), p1 = hw[i1] * LOE_V(i1);
+            const float s0_ = fmaf(hw[i2], LOE_V(i2), p0), s1_ = fmaf(-hw[i2], LOE_V(i2), p0);
+            const float s2_ = fmaf(hw[i3], LOE_V(i3), p1), s3_ = fmaf(-hw[i3], LOE_V(i3), p1);
+#undef LOE_V
+            u0[b] = s0_ + s2_;
+            u2[b] = s0_ - s2_;
+            u1[b] = make_float2(s1_, -s3_);
+        }
+        float2 Y[11];
+        {
+            float v0, m1, q1, m2, q2;
+            rdft5(u0[0], u0[1], u0[2], u0[3], u0[4], v0, m1, q1, m2, q2);      // c = 0: k1 = 0, 4 (d = 4), 8 (d = 3)
+            Y[0] = make_float2(v0, 0.f); Y[4] = make_float2(m1, q1); Y[8] = make_float2(m2, q2);
+            rdft5(u2[0], u2[1], u2[2], u2[3], u2[4], v0, m1, q1, m2, q2);      // c = 2: k1 = 10, 6 (d = 1), 2 (d = 2)
+            Y[10] = make_float2(v0, 0.f); Y[6] = make_float2(m1, -q1); Y[2] = make_float2(m2, -q2);
+            float2 V[5];
+            dft5(u1[0], u1[1], u1[2], u1[3], u1[4], V);                           // c = 1: k1 = 5, 1, 17, 13, 9
+            Y[5] = V[0]; Y[1] = V[1]; Y[9] = V[4];
+            Y[3] = make_float2(V[2].x, -V[2].y);                                   // conj of k1 = 17
+            Y[7] = make_float2(V[3].x, -V[3].y);                                   // conj of k1 = 13
+        }
+        float2* slot = reinterpret_cast<float2*>(area + fb * kFrameB) + n2;
+        slot[0] = Y[0];
+#pragma unroll
+        for (int k1 = 1; k1 < 10; ++k1) slot[k1 * (kRowB / 8)] = cmul(Y[k1], tw[k1]);
+        slot[10 * (kRowB / 8)] = make_float2(Y[10].x * tw[10].x, Y[10].x * tw[10].y);
+    };
+    float ha[10], hb[10], hc[10];
+    {
+        const int t0 = t_begin + warp * kBatch + 4 * fl;
+#pragma unroll
+        for (int j = 0; j < 10; ++j) { ha[j] = 0.f; hb[j] = 0.f; hc[j] = 0.f; }
+        if (t0 < t_end) { fetch(t0, ha); fetch(t0 + 1, hb); }
+    }
 
     for (int tb = t_begin + warp * kBatch; tb < t_end; tb += kWarps * kBatch) {
         {   // pull the samples of this warp's next batch into L2
             const int tbn = tb + kWarps * kBatch;
             if (tbn < t_end) {
                 constexpr int kPerLine = 128 / (int)sizeof(SampleT);
-                const int lo = max(0, kHop * tbn - kHalf), hi = min(ns, kHop * (tbn + kBatch) + kHalf);
+                const int lo = max(0, kHop * tbn - kHop), hi = min(ns, kHop * (tbn + kBatch));
                 for (int i = lo + lane * kPerLine; i < hi; i += 32 * kPerLine)
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(x + i));
             }
         }
-        // ---------------- step 1
-#pragma unroll 1
-        for (int p = 0; p < kBatch / 2; ++p) {
-            const int fb = 2 * p + fl, t = tb + fb;
-            if (edge(t) && t < t_end) fetch_edge(t, v);
-            // five real 4-point DFTs over a (n1 = (5 a + 4 b) mod 20), window folded into the first butterflies
-            float u0[5], u2[5];
-            float2 u1[5];
-#pragma unroll
-            for (int b = 0; b < 5; ++b) {
-                const int i0 = (4 * b) % 20, i1 = (5 + 4 * b) % 20, i2 = (10 + 4 * b) % 20, i3 = (15 + 4 * b) % 20;
-                const float p0 = hw[i0] * v[i0], p1 = hw[i1] * v[i1];
-                const float s0_ = fmaf(hw[i2], v[i2], p0), s1_ = fmaf(-hw[i2], v[i2], p0);
-                const float s2_ = fmaf(hw[i3], v[i3], p1), s3_ = fmaf(-hw[i3], v[i3], p1);
-                u0[b] = s0_ + s2_;
-                u2[b] = s0_ - s2_;
-                u1[b] = make_float2(s1_, -s3_);
-            }
-            fetch_interior((p < kBatch / 2 - 1) ? t + 2 : tb + kWarps * kBatch + fl, v);
-            if (t < t_end) {
-                float2 Y[11];
-                {
-                    float v0, m1, q1, m2, q2;
-                    rdft5(u0[0], u0[1], u0[2], u0[3], u0[4], v0, m1, q1, m2, q2);      // c = 0: k1 = 0, 4 (d = 4), 8 (d = 3)
-                    Y[0] = make_float2(v0, 0.f); Y[4] = make_float2(m1, q1); Y[8] = make_float2(m2, q2);
-                    rdft5(u2[0], u2[1], u2[2], u2[3], u2[4], v0, m1, q1, m2, q2);      // c = 2: k1 = 10, 6 (d = 1), 2 (d = 2)
-                    Y[10] = make_float2(v0, 0.f); Y[6] = make_float2(m1, -q1); Y[2] = make_float2(m2, -q2);
-                    float2 V[5];
-                    dft5(u1[0], u1[1], u1[2], u1[3], u1[4], V);                           // c = 1: k1 = 5, 1, 17, 13, 9
-                    Y[5] = V[0]; Y[1] = V[1]; Y[9] = V[4];
-                    Y[3] = make_float2(V[2].x, -V[2].y);                                   // conj of k1 = 17
-                    Y[7] = make_float2(V[3].x, -V[3].y);                                   // conj of k1 = 13
-                }
-                float2* slot = reinterpret_cast<float2*>(area + fb * kFrameB) + n2;
-                slot[0] = Y[0];
-#pragma unroll
-                for (int k1 = 1; k1 < 10; ++k1) slot[k1 * (kRowB / 8)] = cmul(Y[k1], tw[k1]);
-                slot[10 * (kRowB / 8)] = make_float2(Y[10].x * tw[10].x, Y[10].x * tw[10].y);
-            }
+        // ---------------- step 1: frames tb + 4 fl + {0, 1, 2, 3}; the hop after the next frame is requested one item ahead
+        {
+            const int t0 = tb + 4 * fl;
+            if (t0 + 1 < t_end) fetch(t0 + 2, hc);
+            if (t0 < t_end) item(4 * fl, ha, hb);
+            if (t0 + 2 < t_end) fetch(t0 + 3, ha);
+            if (t0 + 1 < t_end) item(4 * fl + 1, hb, hc);
+            if (t0 + 3 < t_end) fetch(t0 + 4, hb);
+            if (t0 + 2 < t_end) item(4 * fl + 2, hc, ha);
+            if (t0 + 3 < t_end) item(4 * fl + 3, ha, hb);
+            const int tn = t0 + kWarps * kBatch;            // the first two hops of the next batch: in flight during step 2
+            if (tn < t_end) { fetch(tn, ha); fetch(tn + 1, hb); }
         }
         __syncwarp();
         // ---------------- step 2
@@ -628,10 +642,12 @@ mfcc_mel_r_kernel(const SampleT* __restrict__ pcm, const int64_t* __restrict__ p
 #pragma unroll
             for (int it = 0; it < kNA; ++it) {
                 const float w = sm.mel_w[it * 32 + lane];
-                const float4 p = *reinterpret_cast<const float4*>(pa + it * 16);
-                const float4 q = *reinterpret_cast<const float4*>(pa + kPlaneB + it * 16);
-                acc[0] = fmaf(w, p.x, acc[0]); acc[1] = fmaf(w, p.y, acc[1]); acc[2] = fmaf(w, p.z, acc[2]); acc[3] = fmaf(w, p.w, acc[3]);
-                acc[4] = fmaf(w, q.x, acc[4]); acc[5] = fmaf(w, q.y, acc[5]); acc[6] = fmaf(w, q.z, acc[6]); acc[7] = fmaf(w, q.w, acc[7]);
+                if (!LOE_MELR_PRED || w != 0.f) {                                 // entries outside the filter's support: no load at all
+                    const float4 p = *reinterpret_cast<const float4*>(pa + it * 16);
+                    const float4 q = *reinterpret_cast<const float4*>(pa + kPlaneB + it * 16);
+                    acc[0] = fmaf(w, p.x, acc[0]); acc[1] = fmaf(w, p.y, acc[1]); acc[2] = fmaf(w, p.z, acc[2]); acc[3] = fmaf(w, p.w, acc[3]);
+                    acc[4] = fmaf(w, q.x, acc[4]); acc[5] = fmaf(w, q.y, acc[5]); acc[6] = fmaf(w, q.z, acc[6]); acc[7] = fmaf(w, q.w, acc[7]);
+                }
             }
             float* mo = mel_out + (f0 + tb) * kMels + lane;
 #pragma unroll
@@ -643,10 +659,12 @@ mfcc_mel_r_kernel(const SampleT* __restrict__ pcm, const int64_t* __restrict__ p
 #pragma unroll
             for (int it = 0; it < kNB; ++it) {
                 const float w = sm.mel_w[(kNA + it) * 32 + lane];
-                const float4 p = *reinterpret_cast<const float4*>(pb + it * 64);
-                const float4 q = *reinterpret_cast<const float4*>(pb + kPlaneB + it * 64);
-                acc[0] = fmaf(w, p.x, acc[0]); acc[1] = fmaf(w, p.y, acc[1]); acc[2] = fmaf(w, p.z, acc[2]); acc[3] = fmaf(w, p.w, acc[3]);
-                acc[4] = fmaf(w, q.x, acc[4]); acc[5] = fmaf(w, q.y, acc[5]); acc[6] = fmaf(w, q.z, acc[6]); acc[7] = fmaf(w, q.w, acc[7]);
+                if (!LOE_MELR_PRED || w != 0.f) {
+                    const float4 p = *reinterpret_cast<const float4*>(pb + it * 64);
+                    const float4 q = *reinterpret_cast<const float4*>(pb + kPlaneB + it * 64);
+                    acc[0] = fmaf(w, p.x, acc[0]); acc[1] = fmaf(w, p.y, acc[1]); acc[2] = fmaf(w, p.z, acc[2]); acc[3] = fmaf(w, p.w, acc[3]);
+                    acc[4] = fmaf(w, q.x, acc[4]); acc[5] = fmaf(w, q.y, acc[5]); acc[6] = fmaf(w, q.z, acc[6]); acc[7] = fmaf(w, q.w, acc[7]);
+                }
             }
 #pragma unroll
             for (int f = 0; f < 8; ++f) {

@@ -340,8 +340,8 @@ def test_h16_image_is_triangular_and_scores_like_the_whitening_matrix():
 
 def test_mel_lane_tables_exact_and_bank_conflict_free():
     """mel_lane_tables (host): the lane-balanced filterbank the MFCC kernel reads reproduces the dense slaney
-    filterbank exactly, every lane walks consecutive bins, and at 16 kHz the window starts are slid so that the 32
-    power-spectrum reads of each iteration fall into 32 different shared-memory banks."""
+    filterbank exactly, every lane walks consecutive bins, and at 16 kHz the window starts are slid to minimise the
+    shared-memory wavefronts of the 16-byte power-spectrum reads."""
     from loe_speech_recognition.mfcc import mel_filterbank, mel_lane_tables
     for sr in (16000, 8000, 22050):
         bins, w, na, nb = mel_lane_tables(sr)
@@ -358,6 +358,20 @@ def test_mel_lane_tables_exact_and_bank_conflict_free():
         assert np.array_equal(B[na:], B[na][None, :] + 4 * np.arange(nb)[:, None])
         assert B.min() >= 0 and B.max() < 161 + 3 + 32 + 64               # inside the kernel's frame area slack
         if sr == 16000:
+            # mfcc_mel_r_kernel reads 16-byte [bin][4 frames] entries, a quarter-warp per wavefront: the window starts
+            # are slid so that the wavefronts of the entries that carry weight are at most half those of the natural starts
+            from loe_speech_recognition.mfcc import _quarter_wavefronts
             assert (na, nb) == (11, 5)
-            for it in range(na + nb):
-                assert len(set(int(b) % 32 for b in B[it])) == 32
+            nz = [np.nonzero(dense[m])[0] for m in range(40)]
+            first, last = [int(z[0]) for z in nz], [int(z[-1]) for z in nz]
+
+            def total(starts_a, starts_b):
+                ta = sum(_quarter_wavefronts(list(starts_a[q:q + 8]), first[q:q + 8], last[q:q + 8], na, 1) for q in range(0, 32, 8))
+                tb = sum(_quarter_wavefronts(list(starts_b[q:q + 2]), first[32 + q:34 + q], last[32 + q:34 + q], 4 * nb, 4)
+                         for q in range(0, 8, 2))
+                return ta, tb
+            got = total([int(b) for b in B[0]], [int(b) for b in B[na][::4]])
+            nat = total(first[:32], first[32:])
+            assert got[0] <= 25 and got[1] <= 24 and got[0] * 2 <= nat[0], (got, nat)
+            assert all(B[0][m] <= first[m] and B[0][m] + na > last[m] for m in range(32))
+            assert all(B[na][4 * q] <= first[32 + q] and B[na][4 * q] + 4 * nb > last[32 + q] for q in range(8))
