@@ -8,8 +8,9 @@ power_to_db(ref=np.max), mfcc(n_mfcc=13), delta, delta order 2); the kernels res
 pipeline.  Only the filterbank weights are prepared on the host (once per
 sample rate).
 """
-from __future__ import functools
-import annotations
+from __future__ import annotations
+
+import functools
 
 from dataclasses import dataclass, field
 from typing import List
