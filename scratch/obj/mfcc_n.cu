@@ -1,11 +1,9 @@
 // MFCC front end for sm_100a.  Replaces mfcc.py:24-84 of the reference (librosa pipeline).
 //
-// Kernel A (mel):   PCM -> Hann window -> 320-point real DFT -> |.|^2 -> sparse slaney filterbank -> mel energies
-//                   [frames, 40] + per-utterance maximum (atomicMax on the float bits).  Two forms, both with every
-//                   sub-transform in the registers of one thread and ONE pass through shared memory:
-//                   mfcc_mel_r_kernel (the 16 kHz filterbank table of every reference call site): real-input-first
-//                   20 x 16 split, no real-input post-pass, filterbank over 8 frames at once;
-//                   mfcc_mel_kernel (any other table): 160-point complex FFT split 10 x 16 + real-input post-pass.
+// Kernel A (mel):   PCM -> Hann window -> 320-point real FFT (160-point complex FFT split 10 x 16 with every
+//                   sub-transform in the registers of one thread, one pass through shared memory, real-input
+//                   post-pass in registers; details at the kernel) -> |.|^2 -> sparse slaney filterbank -> mel
+//                   energies [frames, 40] + per-utterance maximum (atomicMax on the float bits).
 // Kernel B (ceps):  mel -> dB relative to the utterance maximum, floor at -80 dB -> DCT-II
 //                   (ortho) 13 ceps -> Savitzky-Golay delta / delta-delta (width 9, edge
 //                   frames take the value of the nearest full window) -> per-frame
@@ -499,78 +497,104 @@ mfcc_mel_r_kernel(const SampleT* __restrict__ pcm, const int64_t* __restrict__ p
     float vmax = 0.f;
 
     const int ns = (int)n_samples;                    // one utterance: fits 32 bits
-    // samples of one step-1 item: x[160 t - 160 + 16 n1 + n2], zero outside the utterance (centre padding).
-    // Interior frames (all but the first and the last one or two of an utterance) are requested WITHOUT any test, from a
-    // base clamped into the utterance, as soon as the window butterflies have consumed the current samples (into the
-    // same registers: the loads are in flight for the rest of the item, across batches too).  A frame that reaches
-    // outside the utterance is fetched again, with bounds tests, when its turn comes.
-    const int base_max = ns - kNfft;                  // >= 0: an utterance has at least 9 frames
-    auto edge = [&](int t) { const int base = kHop * t - kHalf; return base < 0 || base > base_max; };
-    auto fetch_interior = [&](int t, float* dst) {
-        const SampleT* __restrict__ xb = x + min(max(kHop * t - kHalf, 0), base_max) + n2;
+    // H(t)[j] = x[160 (t - 1) + 16 j + n2], j = 0..9: this lane's samples in the hop before frame centre t; frame t uses H(t)
+    // (n1 = 0..9) and H(t + 1) (n1 = 10..19), zero outside the utterance (centre padding).  A thread walks the four
+    // CONSECUTIVE frames tb + 4 fl + {0..3} of a batch, so the second hop of one frame is the first of the next: two
+    // register sets swap roles from frame to frame and every sample is loaded once per batch and lane.
+    // Hops are requested WITHOUT any test, from a base clamped into the utterance, as soon as the window butterflies
+    // have consumed the set they replace (the loads are in flight for the rest of the item, across batches too); a
+    // frame that reaches outside the utterance (the first, the last one or two) is fetched again with bounds tests.
+    const int hop_max = ns - kHop;                    // >= 0: an utterance has at least 9 frames
+    auto edge = [&](int t) { return t == 0 || kHop * t > hop_max; };
+    auto fetch_hop = [&](int t, float* dst) {
+        const SampleT* __restrict__ xb = x + min(max(kHop * t - kHop, 0), hop_max) + n2;
 #pragma unroll
-        for (int n1 = 0; n1 < 20; ++n1) dst[n1] = to_f32(__ldg(xb + 16 * n1));
+        for (int j = 0; j < 10; ++j) dst[j] = to_f32(__ldg(xb + 16 * j));
     };
-    auto fetch_edge = [&](int t, float* dst) {
-        const int base = kHop * t - kHalf;
+    auto fetch_edge = [&](int t, float* d0, float* d1) {
+        const int base = kHop * t - kHop + n2;
 #pragma unroll
-        for (int n1 = 0; n1 < 20; ++n1) {
-            const int i = base + 16 * n1 + n2;
-            dst[n1] = (i >= 0 && i < ns) ? to_f32(__ldg(x + i)) : 0.f;
+        for (int j = 0; j < 10; ++j) {
+            const int i0 = base + 16 * j, i1 = i0 + kHop;
+            d0[j] = (i0 >= 0 && i0 < ns) ? to_f32(__ldg(x + i0)) : 0.f;
+            d1[j] = (i1 >= 0 && i1 < ns) ? to_f32(__ldg(x + i1)) : 0.f;
         }
     };
-    float v[20];
-    fetch_interior(t_begin + warp * kBatch + fl, v);
+    // first part of an item: window and the five real 4-point DFTs over a (n1 = (5 a + 4 b) mod 20), the window folded
+    // into the first butterflies; consumes the samples
+    auto front = [&](const float* va, const float* vb, float* u0, float* u2, float2* u1) {
+#pragma unroll
+        for (int b = 0; b < 5; ++b) {
+            const int i0 = (4 * b) % 20, i1 = (5 + 4 * b) % 20, i2 = (10 + 4 * b) % 20, i3 = (15 + 4 * b) % 20;
+#define LOE_V(i) ((i) < 10 ? va[(i) % 10] : vb[(i) % 10])
+            const float p0 = hw[i0] * LOE_V(i0), p1 = hw[i1] * LOE_V(i1);
+            const float s0_ = fmaf(hw[i2], LOE_V(i2), p0), s1_ = fmaf(-hw[i2], LOE_V(i2), p0);
+            const float s2_ = fmaf(hw[i3], LOE_V(i3), p1), s3_ = fmaf(-hw[i3], LOE_V(i3), p1);
+#undef LOE_V
+            u0[b] = s0_ + s2_;
+            u2[b] = s0_ - s2_;
+            u1[b] = make_float2(s1_, -s3_);
+        }
+    };
+    // second part: the 5-point DFTs, twiddles, the 11 rows of frame slot fb
+    auto back = [&](int fb, const float* u0, const float* u2, const float2* u1) {
+        float2 Y[11];
+        {
+            float v0, m1, q1, m2, q2;
+            rdft5(u0[0], u0[1], u0[2], u0[3], u0[4], v0, m1, q1, m2, q2);      // c = 0: k1 = 0, 4 (d = 4), 8 (d = 3)
+            Y[0] = make_float2(v0, 0.f); Y[4] = make_float2(m1, q1); Y[8] = make_float2(m2, q2);
+            rdft5(u2[0], u2[1], u2[2], u2[3], u2[4], v0, m1, q1, m2, q2);      // c = 2: k1 = 10, 6 (d = 1), 2 (d = 2)
+            Y[10] = make_float2(v0, 0.f); Y[6] = make_float2(m1, -q1); Y[2] = make_float2(m2, -q2);
+            float2 V[5];
+            dft5(u1[0], u1[1], u1[2], u1[3], u1[4], V);                           // c = 1: k1 = 5, 1, 17, 13, 9
+            Y[5] = V[0]; Y[1] = V[1]; Y[9] = V[4];
+            Y[3] = make_float2(V[2].x, -V[2].y);                                   // conj of k1 = 17
+            Y[7] = make_float2(V[3].x, -V[3].y);                                   // conj of k1 = 13
+        }
+        float2* slot = reinterpret_cast<float2*>(area + fb * kFrameB) + n2;
+        slot[0] = Y[0];
+#pragma unroll
+        for (int k1 = 1; k1 < 10; ++k1) slot[k1 * (kRowB / 8)] = cmul(Y[k1], tw[k1]);
+        slot[10 * (kRowB / 8)] = make_float2(Y[10].x * tw[10].x, Y[10].x * tw[10].y);
+    };
+    float ha[10], hb[10], hc[10];
+    fetch_hop(t_begin + warp * kBatch + 4 * fl, ha);
+    fetch_hop(t_begin + warp * kBatch + 4 * fl + 1, hb);
+    fetch_hop(t_begin + warp * kBatch + 4 * fl + 2, hc);
 
     for (int tb = t_begin + warp * kBatch; tb < t_end; tb += kWarps * kBatch) {
         {   // pull the samples of this warp's next batch into L2
             const int tbn = tb + kWarps * kBatch;
             if (tbn < t_end) {
                 constexpr int kPerLine = 128 / (int)sizeof(SampleT);
-                const int lo = max(0, kHop * tbn - kHalf), hi = min(ns, kHop * (tbn + kBatch) + kHalf);
+                const int lo = max(0, kHop * tbn - kHop), hi = min(ns, kHop * (tbn + kBatch));
                 for (int i = lo + lane * kPerLine; i < hi; i += 32 * kPerLine)
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(x + i));
             }
         }
-        // ---------------- step 1
-#pragma unroll 1
-        for (int p = 0; p < kBatch / 2; ++p) {
-            const int fb = 2 * p + fl, t = tb + fb;
-            if (edge(t) && t < t_end) fetch_edge(t, v);
-            // five real 4-point DFTs over a (n1 = (5 a + 4 b) mod 20), window folded into the first butterflies
+        // ---------------- step 1: frames t0 .. t0 + 3 from the hops (ha, hb), (hb, hc), (hc, ha), (ha, hb); every hop is
+        // requested two frames (or a whole step 2) before its first use
+        {
+            const int t0 = tb + 4 * fl, fb = 4 * fl, tn = t0 + kWarps * kBatch;
             float u0[5], u2[5];
             float2 u1[5];
-#pragma unroll
-            for (int b = 0; b < 5; ++b) {
-                const int i0 = (4 * b) % 20, i1 = (5 + 4 * b) % 20, i2 = (10 + 4 * b) % 20, i3 = (15 + 4 * b) % 20;
-                const float p0 = hw[i0] * v[i0], p1 = hw[i1] * v[i1];
-                const float s0_ = fmaf(hw[i2], v[i2], p0), s1_ = fmaf(-hw[i2], v[i2], p0);
-                const float s2_ = fmaf(hw[i3], v[i3], p1), s3_ = fmaf(-hw[i3], v[i3], p1);
-                u0[b] = s0_ + s2_;
-                u2[b] = s0_ - s2_;
-                u1[b] = make_float2(s1_, -s3_);
-            }
-            fetch_interior((p < kBatch / 2 - 1) ? t + 2 : tb + kWarps * kBatch + fl, v);
-            if (t < t_end) {
-                float2 Y[11];
-                {
-                    float v0, m1, q1, m2, q2;
-                    rdft5(u0[0], u0[1], u0[2], u0[3], u0[4], v0, m1, q1, m2, q2);      // c = 0: k1 = 0, 4 (d = 4), 8 (d = 3)
-                    Y[0] = make_float2(v0, 0.f); Y[4] = make_float2(m1, q1); Y[8] = make_float2(m2, q2);
-                    rdft5(u2[0], u2[1], u2[2], u2[3], u2[4], v0, m1, q1, m2, q2);      // c = 2: k1 = 10, 6 (d = 1), 2 (d = 2)
-                    Y[10] = make_float2(v0, 0.f); Y[6] = make_float2(m1, -q1); Y[2] = make_float2(m2, -q2);
-                    float2 V[5];
-                    dft5(u1[0], u1[1], u1[2], u1[3], u1[4], V);                           // c = 1: k1 = 5, 1, 17, 13, 9
-                    Y[5] = V[0]; Y[1] = V[1]; Y[9] = V[4];
-                    Y[3] = make_float2(V[2].x, -V[2].y);                                   // conj of k1 = 17
-                    Y[7] = make_float2(V[3].x, -V[3].y);                                   // conj of k1 = 13
-                }
-                float2* slot = reinterpret_cast<float2*>(area + fb * kFrameB) + n2;
-                slot[0] = Y[0];
-#pragma unroll
-                for (int k1 = 1; k1 < 10; ++k1) slot[k1 * (kRowB / 8)] = cmul(Y[k1], tw[k1]);
-                slot[10 * (kRowB / 8)] = make_float2(Y[10].x * tw[10].x, Y[10].x * tw[10].y);
-            }
+            if (edge(t0) && t0 < t_end) fetch_edge(t0, ha, hb);
+            front(ha, hb, u0, u2, u1);
+            fetch_hop(t0 + 3, ha);
+            if (t0 < t_end) back(fb, u0, u2, u1);
+            if (edge(t0 + 1) && t0 + 1 < t_end) fetch_edge(t0 + 1, hb, hc);
+            front(hb, hc, u0, u2, u1);
+            fetch_hop(t0 + 4, hb);
+            if (t0 + 1 < t_end) back(fb + 1, u0, u2, u1);
+            if (edge(t0 + 2) && t0 + 2 < t_end) fetch_edge(t0 + 2, hc, ha);
+            front(hc, ha, u0, u2, u1);
+            fetch_hop(tn + 2, hc);
+            if (t0 + 2 < t_end) back(fb + 2, u0, u2, u1);
+            if (edge(t0 + 3) && t0 + 3 < t_end) fetch_edge(t0 + 3, ha, hb);
+            front(ha, hb, u0, u2, u1);
+            fetch_hop(tn, ha);
+            fetch_hop(tn + 1, hb);
+            if (t0 + 3 < t_end) back(fb + 3, u0, u2, u1);
         }
         __syncwarp();
         // ---------------- step 2

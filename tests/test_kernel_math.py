@@ -3,6 +3,10 @@
 * the 10 x 16 decomposition of the 160-point complex FFT and the in-thread real-input post-pass of
   csrc/mfcc.cu (mfcc_mel_kernel): prime-factor 10-point DFT, twiddles, the rotated eleventh slot that lets the
   a = 0 thread pair bin k with 160 - k like every other thread;
+* the real-input-first 20 x 16 decomposition of the 320-point real DFT of csrc/mfcc.cu (mfcc_mel_r_kernel): the
+  prime-factor real 20-point DFT (five real 4-point DFTs, real 5-point DFTs for c = 0 and 2, one complex 5-point DFT
+  for c = 1, conjugates for c = 3), the W_320 twiddles, one 16-point FFT per row, the mirrored bins, and the
+  shared-memory addresses of the exchange rows and of the [plane][bin][frame] power spectra;
 * the pairing table of csrc/emission_h16.cu (pair_chunk): the 8 MMAs of K = 16 cover the 15 split-operand chunk
   products exactly once, and no MMA is issued narrower than its chunks reach in the lower-triangular image.
 """
@@ -82,6 +86,80 @@ def test_mel_kernel_fft_decomposition():
             power[k], power[160 - k] = 0.25 * abs(e + t) ** 2, 0.25 * abs(e - t) ** 2
     assert not np.isnan(power).any()
     assert np.abs(power - ref).max() <= 1e-12 * ref.max()
+
+
+def _rdft5(r):
+    c1, c2, s1, s2 = np.cos(2 * np.pi / 5), np.cos(4 * np.pi / 5), np.sin(2 * np.pi / 5), np.sin(4 * np.pi / 5)
+    t1, t2, t3, t4 = r[1] + r[4], r[2] + r[3], r[1] - r[4], r[2] - r[3]
+    return r[0] + t1 + t2, r[0] + c1 * t1 + c2 * t2, s1 * t3 + s2 * t4, r[0] + c2 * t1 + c1 * t2, s2 * t3 - s1 * t4
+
+
+def _rdft20(y):
+    """mfcc_mel_r_kernel step 1: n1 = (5 a + 4 b) mod 20, k1 = c mod 4 = d mod 5; outputs k1 = 0..10."""
+    u0, u1, u2 = [], [], []
+    for b in range(5):
+        y0, y1, y2, y3 = (y[(5 * a + 4 * b) % 20] for a in range(4))
+        s0, s1, s2, s3 = y0 + y2, y0 - y2, y1 + y3, y1 - y3
+        u0.append(s0 + s2); u2.append(s0 - s2); u1.append(complex(s1, -s3))
+    Y = [None] * 11
+    v0, m1, q1, m2, q2 = _rdft5(u0)
+    Y[0], Y[4], Y[8] = complex(v0, 0), complex(m1, q1), complex(m2, q2)
+    v0, m1, q1, m2, q2 = _rdft5(u2)
+    Y[10], Y[6], Y[2] = complex(v0, 0), complex(m1, -q1), complex(m2, -q2)
+    V = _dft5(u1)
+    Y[5], Y[1], Y[9], Y[3], Y[7] = V[0], V[1], V[4], np.conj(V[2]), np.conj(V[3])
+    return Y
+
+
+def test_mel_r_kernel_real_first_decomposition():
+    src = open(os.path.join(CSRC, "mfcc.cu")).read()
+    const = {k: int(v) for k, v in re.findall(r"constexpr int (k\w+) = (\d+);", src[src.index("namespace r20 {"):])}
+    frame_b, plane_b, batch = const["kFrameB"], const["kPlaneB"], const["kBatch"]
+    row_b = batch * frame_b
+    plane0 = 4 * row_b
+    assert frame_b % 16 == 0 and (frame_b // 16) % 2 == 1          # 16-byte row loads of 8 frames: 8 different bank groups
+    assert (plane_b // 4) % 32 == 16 and plane0 + 2 * plane_b <= 11 * row_b and 161 * 16 <= plane_b
+    rng = np.random.default_rng(1)
+    y = rng.normal(size=20)
+    assert np.allclose(_rdft20(y), np.fft.fft(y)[:11])
+    hann = 0.5 - 0.5 * np.cos(2 * np.pi * np.arange(320) / 320)
+    area = {}
+    frames = [rng.normal(0, 3000, 320) * hann for _ in range(batch)]
+    # step 1, thread (frame, n2): rows k1 = 0..10 at byte k1 * row_b + fb * frame_b + n2 * 8
+    rows = np.zeros((batch, 11, 16), complex)
+    for fb, xw in enumerate(frames):
+        for n2 in range(16):
+            Y = _rdft20(xw[n2::16])
+            for k1 in range(11):
+                addr = k1 * row_b + fb * frame_b + n2 * 8
+                assert addr not in area and addr + 8 <= 11 * row_b
+                area[addr] = 1
+                rows[fb, k1, n2] = Y[k1] * _w(320, n2 * k1)
+    # step 2, thread (f8, k1): FFT16 of the row = bins k1 + 20 k2, mirrored above 160; float address in the planes
+    for f8, xw in enumerate(frames):
+        ref = np.abs(np.fft.rfft(xw)) ** 2
+        power, written = np.full(161, np.nan), {}
+        for k1 in range(11):
+            X = _fft16(rows[f8, k1])
+            for k2 in range(16):
+                off = 4 * k1 + 80 * k2 if k2 < 8 else 4 * (320 - k1) - 80 * k2     # store_pw: lo[80 k2] / hi[-80 k2]
+                b = off // 4
+                assert b == (k1 + 20 * k2 if k1 + 20 * k2 <= 160 and k2 < 8 else 320 - k1 - 20 * k2) and 0 <= b <= 160
+                byte = plane0 + (f8 >> 2) * plane_b + 4 * (off + (f8 & 3))
+                assert plane0 <= byte < 11 * row_b
+                power[b] = abs(X[k2]) ** 2
+                written.setdefault(b, []).append(k1)
+        assert not np.isnan(power).any() and np.abs(power - ref).max() <= 1e-12 * ref.max()
+        assert all(len(set(v)) == 1 for v in written.values())                      # a bin is only ever rewritten by its own thread
+    # store bank pattern: one instruction = fixed k2, lanes (f8 = 0..7, k1 = 4 pass + 0..3): 32 different banks
+    for p_ in range(3):
+        for k2 in range(16):
+            banks = set()
+            lanes = [(f8, 4 * p_ + kq) for kq in range(4) for f8 in range(8) if 4 * p_ + kq <= 10]
+            for f8, k1 in lanes:
+                off = 4 * k1 + 80 * k2 if k2 < 8 else 4 * (320 - k1) - 80 * k2
+                banks.add(((plane0 + (f8 >> 2) * plane_b) // 4 + off + (f8 & 3)) % 32)
+            assert len(banks) == len(lanes)
 
 
 def test_emission_h16_pairing_table():
