@@ -5,13 +5,16 @@
 //
 // Word-start rule of the loop grammar without a value/index shuffle reduction: float addition is
 // monotonic, so  max_w fl(pen + d_w) = fl(pen + max_w d_w);  the maximum of the word-end scores is
-// one REDUX on an order-preserving integer key, and np.argmax's "lowest index among equal
-// candidates" is the lowest set bit of a ballot of  fl(pen + d_w) == max.
+// one float REDUX, and np.argmax's "lowest index among equal candidates" is the lowest set bit of a
+// ballot of  fl(pen + d_w) == max.
 //
 // Back-pointers are 2-bit codes (0/1/2 = came from p, p-1, p-2; 3 = word-start took the cross-word
-// candidate recorded per frame, or "all candidates -inf -> position 0"), 16 codes per lane word,
+// candidate recorded per frame, or "all candidates -inf -> position 0"), 16 codes per word,
 // so a 460-frame, 58-state utterance needs 7.4 KB of shared memory instead of 26.7 KB and four
-// utterances share a CTA.
+// utterances share a CTA.  A word holds the codes of ONE position for 16 consecutive frames: the
+// backtrace then moves in RUNS -- one shared-memory load and one find-leading-one give the next
+// frame at which the path leaves its position (self loops dominate: ~70 runs for 400 frames), and
+// the whole warp writes the run's stretch of the path with one store.
 #include "viterbi.cuh"
 #include <type_traits>
 
@@ -21,11 +24,12 @@ constexpr int kWarpsPerCta = 4;
 constexpr int kPre = 8;
 constexpr size_t kWarpSmemCap = 200 * 1024;
 
-__device__ __forceinline__ int fkey(float f) {
-    const int i = __float_as_int(f);
-    return i ^ ((i >> 31) & 0x7fffffff);
+// warp-wide float maximum in one instruction (sm_100a: CREDUX.MAX.F32); the scores are never NaN
+__device__ __forceinline__ float warp_max(float v) {
+    float r;
+    asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+    return r;
 }
-__device__ __forceinline__ float fkey_inv(int k) { return __int_as_float(k ^ ((k >> 31) & 0x7fffffff)); }
 
 struct WarpLayout {
     int n_rows;          // back-pointer rows of 32 words
@@ -34,8 +38,7 @@ struct WarpLayout {
 
 __host__ __device__ inline WarpLayout warp_layout(int max_frames, int max_pos, int spl) {
     WarpLayout L;
-    const int fpw = 16 / spl;
-    L.n_rows = (max_frames + fpw - 1) / fpw;
+    L.n_rows = ((max_frames + 15) / 16) * spl;        // [16-frame group][slot]: 32 words, one per lane
     int o = L.n_rows * 128;
     L.off_cross = o; o += ((max_frames + 3) & ~3) + 4;
     L.off_path = o;  o += (max_frames + 3) & ~3;
@@ -53,8 +56,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32)
 viterbi_warp_kernel(VitArgs a, int n_utt) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr unsigned FULL = 0xffffffffu;
-    constexpr int FPW = 16 / SPL;                        // frames per back-pointer word
-    static_assert(kPre % 4 == 0 && (FPW % kPre == 0 || kPre % FPW == 0), "block size vs packing");
+    constexpr int FPW = 16;                              // frames per back-pointer word (one position)
+    static_assert(kPre == 8, "two blocks of the time loop fill a back-pointer word");
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int u = blockIdx.x * kWarpsPerCta + warp;
     if (u >= n_utt) return;
@@ -103,13 +106,13 @@ viterbi_warp_kernel(VitArgs a, int n_utt) {
         float lm = neg_inf();
 #pragma unroll
         for (int i = 0; i < SPL; ++i) lm = is_end[i] ? fmaxf(lm, d[i]) : lm;
-        return fkey_inv(__reduce_max_sync(FULL, fkey(lm)));
+        return warp_max(lm);
     };
 
     // t = 0
 #pragma unroll
     for (int i = 0; i < SPL; ++i) {
-        const float e0 = act[i] ? __ldg(src[i]) : 0.f;
+        const float e0 = __ldg(src[i]);
         const unsigned flg = act[i] ? s_flags[lane * SPL + i] : 0u;
         d[i] = (act[i] && (flg & LOE_POS_INIT)) ? __fadd_rn(e0, b0[i]) : neg_inf();
         src[i] += a.ld;
@@ -120,18 +123,29 @@ viterbi_warp_kernel(VitArgs a, int n_utt) {
     for (int k = 0; k < kPre; ++k)
 #pragma unroll
         for (int i = 0; i < SPL; ++i)
-            ecur[k][i] = (act[i] && 1 + k < T) ? __ldg(src[i] + (int64_t)k * a.ld) : 0.f;
-    uint32_t bits = 0, cbits = 0;
+            ecur[k][i] = (1 + k < T) ? __ldg(src[i] + (int64_t)k * a.ld) : 0.f;
+    uint32_t bits[SPL], cbits = 0;
+#pragma unroll
+    for (int i = 0; i < SPL; ++i) bits[i] = 0;
     // frame t = 1 + j;  j runs in blocks of kPre (jb is a multiple of kPre)
     for (int jb = 0; jb < T - 1; jb += kPre) {
 #pragma unroll
         for (int i = 0; i < SPL; ++i) src[i] += (int64_t)kPre * a.ld;
+        if (jb + 2 * kPre < T) {                            // the whole next block exists: no tests
 #pragma unroll
-        for (int k = 0; k < kPre; ++k)
+            for (int k = 0; k < kPre; ++k)
 #pragma unroll
-            for (int i = 0; i < SPL; ++i)
-                enext[k][i] = (act[i] && 1 + jb + kPre + k < T) ? __ldg(src[i] + (int64_t)k * a.ld) : 0.f;
-        const int slot_base = (FPW > kPre) ? (jb & (FPW - 1)) : 0;     // position of this block inside a bp word
+                for (int i = 0; i < SPL; ++i) enext[k][i] = __ldg(src[i] + (int64_t)k * a.ld);
+        } else {
+#pragma unroll
+            for (int k = 0; k < kPre; ++k)
+#pragma unroll
+                for (int i = 0; i < SPL; ++i)
+                    enext[k][i] = (1 + jb + kPre + k < T) ? __ldg(src[i] + (int64_t)k * a.ld) : 0.f;
+        }
+        uint32_t blk[SPL];                                  // the codes of this block: 2 bits per frame
+#pragma unroll
+        for (int i = 0; i < SPL; ++i) blk[i] = 0;
         // One frame of the recursion.  FAST = the block lies strictly before the utterance's last frame: no bounds test per
         // frame and the partial back-pointer / cross-word words are only flushed at their static positions.
         auto frame = [&](auto fast_tag, const int k) {
@@ -173,11 +187,10 @@ viterbi_warp_kernel(VitArgs a, int n_utt) {
                 const float p1 = (i >= 1) ? d[i >= 1 ? i - 1 : 0] : up1;
                 const float p2 = (i >= 2) ? d[i >= 2 ? i - 2 : 0] : (i == 1 ? up1 : up2);
                 const float e = ecur[k][i];
-                float best = __fadd_rn(b2[i], p2); unsigned code = 2;
-                const float c1 = __fadd_rn(b1[i], p1);
-                if (c1 > best) { best = c1; code = 1; }
-                const float c0 = __fadd_rn(b0[i], d[i]);
-                if (c0 > best) { best = c0; code = 0; }
+                // candidates in the reference's order p-2, p-1, p; a later one only wins when strictly larger
+                const float c2 = __fadd_rn(b2[i], p2), c1 = __fadd_rn(b1[i], p1), c0 = __fadd_rn(b0[i], d[i]);
+                const float best = fmaxf(fmaxf(c2, c1), c0);
+                unsigned code = (c2 == best) ? 2u : (c1 == best) ? 1u : 0u;
                 if (best == neg_inf()) code = 3;
                 float val = __fadd_rn(best, e);
                 if (LOOP) {
@@ -196,20 +209,26 @@ viterbi_warp_kernel(VitArgs a, int n_utt) {
                     }
                 }
                 nd[i] = val;                 // positions beyond the trellis have -inf bands and stay at -inf by themselves
-                const int slot = (FPW > kPre) ? (slot_base + k) : (k & (FPW - 1));
-                bits |= code << (2 * (slot * SPL + i));
+                blk[i] |= code << (2 * k);
             }
 #pragma unroll
             for (int i = 0; i < SPL; ++i) d[i] = nd[i];
-            const bool row_done = (FPW > kPre) ? (((slot_base + k) & (FPW - 1)) == FPW - 1) : ((k & (FPW - 1)) == FPW - 1);
-            if (row_done || (!FAST && j == T - 2)) { s_bp[(j / FPW) * 32 + lane] = bits; bits = 0; }
         };
-        if (jb + kPre < T - 1) {
+        const bool fast = jb + kPre < T - 1;
+        if (fast) {
 #pragma unroll
             for (int k = 0; k < kPre; ++k) frame(std::true_type{}, k);
         } else {
 #pragma unroll
             for (int k = 0; k < kPre; ++k) frame(std::false_type{}, k);
+        }
+        // the block's codes go into the low or the high half of the 16-frame words; a word is stored when it is full
+        // and after the utterance's last block
+        const int half = jb & kPre;
+#pragma unroll
+        for (int i = 0; i < SPL; ++i) {
+            bits[i] |= blk[i] << (2 * half);
+            if (half || !fast) { s_bp[((jb >> 4) * SPL + i) * 32 + lane] = bits[i]; bits[i] = 0; }
         }
 #pragma unroll
         for (int k = 0; k < kPre; ++k)
@@ -243,24 +262,33 @@ viterbi_warp_kernel(VitArgs a, int n_utt) {
         for (int w = n_end + lane; w < a.max_ends; w += 32) a.end_scores[(int64_t)u * a.max_ends + w] = neg_inf();
     }
 
-    // ---- backtrace (every lane walks the same chain; lane 0 records it).  frame t >= 1 is j = t-1
-    auto decode = [&](int t, int p) -> int {
-        const int j = t - 1;
-        const uint32_t w = s_bp[(j / FPW) * 32 + p / SPL];
-        const unsigned code = (w >> (2 * ((j % FPW) * SPL + p % SPL))) & 3u;
-        if (code < 3) return p - (int)code;
-        if (LOOP && (s_flags[p] & LOE_POS_START)) return (int)((s_cross[j >> 2] >> (8 * (j & 3))) & 0xffu);
-        return 0;
-    };
+    // ---- backtrace in runs (every lane walks the same chain).  q_t = position at frame t, q_(T-1) = end_pos; the code
+    // of the step into frame t is slot (t - 1) & 15 of word [(t - 1) >> 4][q_t].  The reference records the
+    // predecessor one frame late at the end (path[T-1] = path[T-2] = q_(T-2)).
     if (T == 1) {
         if (lane == 0) s_path[0] = -1;
     } else {
-        int prev = decode(T - 1, n_end > 0 ? end_pos : 0);
-        if (lane == 0) s_path[T - 1] = (int8_t)prev;
-        for (int t = T - 2; t >= 0; --t) {
-            if (lane == 0) s_path[t] = (int8_t)prev;
-            if (t >= 1) prev = decode(t, prev);
+        int pcur = n_end > 0 ? end_pos : 0;
+        int t_hi = T - 1;                               // frames (t_lo, t_hi] found so far hold position pcur
+        while (t_hi >= 1) {
+            const int j = t_hi - 1, g = j >> 4, sl = j & 15;
+            const uint32_t w = s_bp[(g * SPL + pcur % SPL) * 32 + pcur / SPL];
+            const uint32_t nz = (w | (w >> 1)) & 0x55555555u & ((2u << (2 * sl)) - 1u);   // steps <= j of this word that leave pcur
+            const int k = nz ? (31 - __clz(nz)) >> 1 : -1;
+            const int t_lo = (g << 4) + k + 1;          // frames t_lo .. t_hi hold pcur (k = -1: down to the word's first frame's predecessor)
+            for (int t = t_lo + lane; t <= t_hi; t += 32) s_path[t] = (int8_t)pcur;
+            if (nz) {
+                const unsigned code = (w >> (2 * k)) & 3u;
+                const int jj = (g << 4) + k;
+                int pn = pcur - (int)code;
+                if (code == 3) pn = (LOOP && (s_flags[pcur] & LOE_POS_START)) ? (int)((s_cross[jj >> 2] >> (8 * (jj & 3))) & 0xffu) : 0;
+                pcur = pn;
+            }
+            t_hi = nz ? t_lo - 1 : t_lo;                // no step left in this word: frame t_lo holds pcur too, go on in the word before
         }
+        if (lane == 0) s_path[0] = (int8_t)pcur;
+        __syncwarp();
+        if (lane == 0) s_path[T - 1] = s_path[T - 2];
     }
     __syncwarp();
     for (int t = lane; t < T; t += 32) a.path[f0 + t] = s_path[t];
