@@ -33,7 +33,7 @@ __device__ __forceinline__ float warp_max(float v) {
 
 struct WarpLayout {
     int n_rows;          // back-pointer rows of 32 words
-    int off_cross, off_path, off_ends, off_flags, off_wlo, off_whi, off_wlab, total;
+    int off_cross, off_path, off_ends, off_flags, off_wlo, off_whi, off_wlab, off_endp, total;
 };
 
 __host__ __device__ inline WarpLayout warp_layout(int max_frames, int max_pos, int spl) {
@@ -47,6 +47,7 @@ __host__ __device__ inline WarpLayout warp_layout(int max_frames, int max_pos, i
     L.off_wlo = o;   o += (max_pos + 3) & ~3;
     L.off_whi = o;   o += (max_pos + 3) & ~3;
     L.off_wlab = o;  o += (max_pos + 3) & ~3;
+    L.off_endp = o;  o += 32;
     L.total = (o + 15) & ~15;
     return L;
 }
@@ -96,6 +97,16 @@ viterbi_warp_kernel(VitArgs a, int n_utt) {
         is_end[i] = (flg & LOE_POS_END) != 0;
         end_mask[i] = __ballot_sync(FULL, is_end[i]);
     }
+    // Usual case (every word model has at least SPL states): no lane owns two END positions.  The cross-word argmax
+    // then needs one candidate per lane -- one add, one compare, one ballot -- and records the winning LANE; the
+    // backtrace maps it to the END position through a 32-entry table.
+    int my_ends = 0, end_slot = 0;
+#pragma unroll
+    for (int i = 0; i < SPL; ++i) { if (is_end[i]) { ++my_ends; end_slot = i; } }
+    const bool one_end = LOOP && !__any_sync(FULL, my_ends > 1);
+    const bool has_end = my_ends == 1;
+    uint8_t* s_endp = base + L.off_endp;
+    s_endp[lane] = (uint8_t)(has_end ? lane * SPL + end_slot : 0);
     // END positions are ordered by position = (lane, slot) lexicographically
     int n_end = 0, lower = 0;
 #pragma unroll
@@ -155,24 +166,41 @@ viterbi_warp_kernel(VitArgs a, int n_utt) {
             // ---- cross-word candidate: fl(pen + max END d); argmax = lowest END position reaching it
             float cross32 = neg_inf(); double cross64 = -CUDART_INF; int cross_arg = 0;
             if (LOOP) {
-                const float m = end_max();
-                int pos = 0x7fffffff;
-                if (PENF64) {
-                    cross64 = __dadd_rn(a.pen64, (double)m);
+                if (one_end) {
+                    float lm = d[0];
 #pragma unroll
-                    for (int i = 0; i < SPL; ++i) {
-                        const unsigned eq = __ballot_sync(FULL, __dadd_rn(a.pen64, (double)d[i]) == cross64) & end_mask[i];
-                        if (eq) pos = min(pos, (__ffs(eq) - 1) * SPL + i);
+                    for (int i = 1; i < SPL; ++i) lm = (end_slot == i) ? d[i] : lm;
+                    lm = has_end ? lm : neg_inf();
+                    const float m = warp_max(lm);
+                    unsigned eq;
+                    if (PENF64) {
+                        cross64 = __dadd_rn(a.pen64, (double)m);
+                        eq = __ballot_sync(FULL, has_end && __dadd_rn(a.pen64, (double)lm) == cross64);
+                    } else {
+                        cross32 = __fadd_rn(a.pen32, m);
+                        eq = __ballot_sync(FULL, has_end && __fadd_rn(a.pen32, lm) == cross32);
                     }
+                    cross_arg = eq ? __ffs(eq) - 1 : 255;        // a lane; 255 = no END position at all -> position 0
                 } else {
-                    cross32 = __fadd_rn(a.pen32, m);
+                    const float m = end_max();
+                    int pos = 0x7fffffff;
+                    if (PENF64) {
+                        cross64 = __dadd_rn(a.pen64, (double)m);
 #pragma unroll
-                    for (int i = 0; i < SPL; ++i) {
-                        const unsigned eq = __ballot_sync(FULL, __fadd_rn(a.pen32, d[i]) == cross32) & end_mask[i];
-                        if (eq) pos = min(pos, (__ffs(eq) - 1) * SPL + i);
+                        for (int i = 0; i < SPL; ++i) {
+                            const unsigned eq = __ballot_sync(FULL, __dadd_rn(a.pen64, (double)d[i]) == cross64) & end_mask[i];
+                            if (eq) pos = min(pos, (__ffs(eq) - 1) * SPL + i);
+                        }
+                    } else {
+                        cross32 = __fadd_rn(a.pen32, m);
+#pragma unroll
+                        for (int i = 0; i < SPL; ++i) {
+                            const unsigned eq = __ballot_sync(FULL, __fadd_rn(a.pen32, d[i]) == cross32) & end_mask[i];
+                            if (eq) pos = min(pos, (__ffs(eq) - 1) * SPL + i);
+                        }
                     }
+                    cross_arg = (pos == 0x7fffffff) ? 0 : pos;
                 }
-                cross_arg = (pos == 0x7fffffff) ? 0 : pos;
                 cbits |= (uint32_t)cross_arg << (8 * (k & 3));
                 if ((k & 3) == 3 || (!FAST && j == T - 2)) { s_cross[j >> 2] = cbits; cbits = 0; }
             }
@@ -281,7 +309,13 @@ viterbi_warp_kernel(VitArgs a, int n_utt) {
                 const unsigned code = (w >> (2 * k)) & 3u;
                 const int jj = (g << 4) + k;
                 int pn = pcur - (int)code;
-                if (code == 3) pn = (LOOP && (s_flags[pcur] & LOE_POS_START)) ? (int)((s_cross[jj >> 2] >> (8 * (jj & 3))) & 0xffu) : 0;
+                if (code == 3) {
+                    pn = 0;
+                    if (LOOP && (s_flags[pcur] & LOE_POS_START)) {
+                        pn = (int)((s_cross[jj >> 2] >> (8 * (jj & 3))) & 0xffu);
+                        if (one_end) pn = (pn == 255) ? 0 : s_endp[pn];
+                    }
+                }
                 pcur = pn;
             }
             t_hi = nz ? t_lo - 1 : t_lo;                // no step left in this word: frame t_lo holds pcur too, go on in the word before
