@@ -40,7 +40,7 @@ __host__ __device__ inline WarpLayout warp_layout(int max_frames, int max_pos, i
     WarpLayout L;
     L.n_rows = ((max_frames + 15) / 16) * spl;        // [16-frame group][slot]: 32 words, one per lane
     int o = L.n_rows * 128;
-    L.off_cross = o; o += ((max_frames + 3) & ~3) + 4;
+    L.off_cross = o; o += max_frames * 4 + 4;            // one word per frame: ballot of the lanes reaching the cross-word maximum
     L.off_path = o;  o += (max_frames + 3) & ~3;
     L.off_ends = o;  o += max_pos * 4;
     L.off_flags = o; o += (max_pos + 3) & ~3;
@@ -65,7 +65,7 @@ viterbi_warp_kernel(VitArgs a, int n_utt) {
     const WarpLayout L = warp_layout(a.max_frames, a.max_pos, SPL);
     unsigned char* base = smem_raw + (size_t)warp * L.total;
     uint32_t* s_bp = reinterpret_cast<uint32_t*>(base);
-    uint32_t* s_cross = reinterpret_cast<uint32_t*>(base + L.off_cross);   // 4 frames per word
+    uint32_t* s_cross = reinterpret_cast<uint32_t*>(base + L.off_cross);   // per frame: ballot (or position) of the cross-word argmax
     int8_t* s_path = reinterpret_cast<int8_t*>(base + L.off_path);
     uint8_t* s_flags = base + L.off_flags;
 
@@ -107,6 +107,13 @@ viterbi_warp_kernel(VitArgs a, int n_utt) {
     const bool has_end = my_ends == 1;
     uint8_t* s_endp = base + L.off_endp;
     s_endp[lane] = (uint8_t)(has_end ? lane * SPL + end_slot : 0);
+    // positions 0 and 1 have no p - 1 / p - 2: their bands are -inf (the trellis builder writes them so; enforced here
+    // because the time loop does not mask the shuffles of lane 0)
+    if (lane == 0) {
+        b1[0] = neg_inf(); b2[0] = neg_inf();
+        if (SPL >= 2) b2[SPL >= 2 ? 1 : 0] = neg_inf();
+    }
+    if (SPL == 1 && lane == 1) b2[0] = neg_inf();
     // END positions are ordered by position = (lane, slot) lexicographically
     int n_end = 0, lower = 0;
 #pragma unroll
@@ -135,7 +142,7 @@ viterbi_warp_kernel(VitArgs a, int n_utt) {
 #pragma unroll
         for (int i = 0; i < SPL; ++i)
             ecur[k][i] = (1 + k < T) ? __ldg(src[i] + (int64_t)k * a.ld) : 0.f;
-    uint32_t bits[SPL], cbits = 0;
+    uint32_t bits[SPL];
 #pragma unroll
     for (int i = 0; i < SPL; ++i) bits[i] = 0;
     // frame t = 1 + j;  j runs in blocks of kPre (jb is a multiple of kPre)
@@ -180,7 +187,7 @@ viterbi_warp_kernel(VitArgs a, int n_utt) {
                         cross32 = __fadd_rn(a.pen32, m);
                         eq = __ballot_sync(FULL, has_end && __fadd_rn(a.pen32, lm) == cross32);
                     }
-                    cross_arg = eq ? __ffs(eq) - 1 : 255;        // a lane; 255 = no END position at all -> position 0
+                    cross_arg = (int)eq;                         // the lanes reaching the maximum; the backtrace takes the lowest
                 } else {
                     const float m = end_max();
                     int pos = 0x7fffffff;
@@ -201,14 +208,13 @@ viterbi_warp_kernel(VitArgs a, int n_utt) {
                     }
                     cross_arg = (pos == 0x7fffffff) ? 0 : pos;
                 }
-                cbits |= (uint32_t)cross_arg << (8 * (k & 3));
-                if ((k & 3) == 3 || (!FAST && j == T - 2)) { s_cross[j >> 2] = cbits; cbits = 0; }
+                if (lane == 0) s_cross[j] = (uint32_t)cross_arg;
             }
             // ---- predecessors held by the lane below
             float up1 = __shfl_up_sync(FULL, d[SPL - 1], 1);
             float up2 = (SPL >= 2) ? __shfl_up_sync(FULL, d[SPL >= 2 ? SPL - 2 : 0], 1) : __shfl_up_sync(FULL, d[0], 2);
-            if (lane == 0) { up1 = neg_inf(); up2 = neg_inf(); }
-            if (SPL == 1 && lane == 1) up2 = neg_inf();
+            // (lane 0 -- and lane 1 for SPL = 1 -- receive their own values: the bands of the positions that have no
+            // p - 1 / p - 2 were set to -inf above, so those candidates are -inf whatever the shuffle delivers)
             float nd[SPL];
 #pragma unroll
             for (int i = 0; i < SPL; ++i) {
@@ -304,7 +310,7 @@ viterbi_warp_kernel(VitArgs a, int n_utt) {
             const uint32_t nz = (w | (w >> 1)) & 0x55555555u & ((2u << (2 * sl)) - 1u);   // steps <= j of this word that leave pcur
             const int k = nz ? (31 - __clz(nz)) >> 1 : -1;
             const int t_lo = (g << 4) + k + 1;          // frames t_lo .. t_hi hold pcur (k = -1: down to the word's first frame's predecessor)
-            for (int t = t_lo + lane; t <= t_hi; t += 32) s_path[t] = (int8_t)pcur;
+            if (t_lo + lane <= t_hi) s_path[t_lo + lane] = (int8_t)pcur;      // a run lies inside one word: at most 17 frames
             if (nz) {
                 const unsigned code = (w >> (2 * k)) & 3u;
                 const int jj = (g << 4) + k;
@@ -312,8 +318,8 @@ viterbi_warp_kernel(VitArgs a, int n_utt) {
                 if (code == 3) {
                     pn = 0;
                     if (LOOP && (s_flags[pcur] & LOE_POS_START)) {
-                        pn = (int)((s_cross[jj >> 2] >> (8 * (jj & 3))) & 0xffu);
-                        if (one_end) pn = (pn == 255) ? 0 : s_endp[pn];
+                        const uint32_t cw = s_cross[jj];
+                        pn = one_end ? (cw ? (int)s_endp[__ffs(cw) - 1] : 0) : (int)cw;
                     }
                 }
                 pcur = pn;
