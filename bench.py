@@ -560,7 +560,7 @@ def impl_b200(args):
     # (profiles/r1l_kernels.txt, emission_tc: r1f; dram__bytes_read.sum + dram__bytes_write.sum at this workload size)
     traffic = ncu_traffic() if (n == 10000 and args.pool == 500) else {}     # the captures are of the default workload
     kernels = {
-        "mfcc_mel_kernel": {"bound": "hbm", "alg": 4 * n_samples + 160 * F, "ms": stage_ms["mfcc_mel"]},
+        "mfcc_mel_r_kernel": {"bound": "hbm", "alg": 4 * n_samples + 160 * F, "ms": stage_ms["mfcc_mel"]},
         # mel energies in; out: the float32 features (156 B / frame) or, on the 3xFP16 path, the pre-split operand image
         # (160 B / frame) + 4 B row scale -- counted as the 156 B of features either way
         "mfcc_ceps_kernel": {"bound": "hbm", "alg": (160 + 156) * F, "ms": stage_ms["mfcc_ceps"]},
@@ -600,9 +600,12 @@ def impl_b200(args):
         all_roof["emission_h16_img_kernel"]["issued"] = note
         if dominant == "emission_h16_img_kernel":
             roofline["issued"] = note
-    if dominant == "mfcc_mel_kernel":
-        roofline["note"] = ("nominally HBM-bound (796 B/frame) but limited by instruction issue and shared-memory wavefronts: ~320 warp "
-                            "instructions and ~60 wavefronts per frame (thread-level 10 x 16 FFT), see profiles/")
+    all_roof["mfcc_mel_r_kernel"]["note"] = (
+        "nominally HBM-bound (800 B/frame) but limited by the L1 / shared-memory data pipe (ncu: 82 % of its wavefront peak: 53 shared "
+        "+ 18 global-load wavefronts per frame) and instruction issue (60 %: ~220 warp instructions per frame of the thread-level "
+        "real-input-first 20 x 16 DFT), see profiles/r2b_kernels.txt")
+    if dominant == "mfcc_mel_r_kernel":
+        roofline["note"] = all_roof["mfcc_mel_r_kernel"]["note"]
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
