@@ -706,14 +706,25 @@ mfcc_ceps_kernel(const float* __restrict__ mel, const float* __restrict__ utt_ma
     // mel rows are 160 bytes: four energies per 16-byte load (one row / column split per load instead of per value)
     const float4* __restrict__ src4 = reinterpret_cast<const float4*>(mel + (f0 + g0) * kMels);
     static_assert(kMels % 4 == 0, "vector loads of the mel rows");
-    for (int i = tid; i < ng * (kMels / 4); i += kRowsB) {
-        const int j = i / (kMels / 4), m = 4 * (i - j * (kMels / 4));
-        const float4 e = __ldg(src4 + i);
-        float* o = s_lm + j * kMelPitch + m;
-        o[0] = fmaxf(fmaf(kDbPerLog2, __log2f(fmaxf(1e-10f, e.x)), -ref_db), -80.0f);
-        o[1] = fmaxf(fmaf(kDbPerLog2, __log2f(fmaxf(1e-10f, e.y)), -ref_db), -80.0f);
-        o[2] = fmaxf(fmaf(kDbPerLog2, __log2f(fmaxf(1e-10f, e.z)), -ref_db), -80.0f);
-        o[3] = fmaxf(fmaf(kDbPerLog2, __log2f(fmaxf(1e-10f, e.w)), -ref_db), -80.0f);
+    // all of a thread's loads are requested before the first logarithm (128 rows x 10 pieces = 10 per thread)
+    constexpr int kPiecesB = kMels / 4;
+    float4 e[kPiecesB];
+#pragma unroll
+    for (int r = 0; r < kPiecesB; ++r) {
+        const int i = tid + r * kRowsB;
+        e[r] = (i < ng * kPiecesB) ? __ldg(src4 + i) : make_float4(1.f, 1.f, 1.f, 1.f);
+    }
+#pragma unroll
+    for (int r = 0; r < kPiecesB; ++r) {
+        const int i = tid + r * kRowsB;
+        if (i < ng * kPiecesB) {
+            const int j = i / kPiecesB, m = 4 * (i - j * kPiecesB);
+            float* o = s_lm + j * kMelPitch + m;
+            o[0] = fmaxf(fmaf(kDbPerLog2, __log2f(fmaxf(1e-10f, e[r].x)), -ref_db), -80.0f);
+            o[1] = fmaxf(fmaf(kDbPerLog2, __log2f(fmaxf(1e-10f, e[r].y)), -ref_db), -80.0f);
+            o[2] = fmaxf(fmaf(kDbPerLog2, __log2f(fmaxf(1e-10f, e[r].z)), -ref_db), -80.0f);
+            o[3] = fmaxf(fmaf(kDbPerLog2, __log2f(fmaxf(1e-10f, e[r].w)), -ref_db), -80.0f);
+        }
     }
     __syncthreads();
     float c[kCeps];

@@ -11,7 +11,7 @@
 // Back-pointers are 2-bit codes (0/1/2 = came from p, p-1, p-2; 3 = word-start took the cross-word
 // candidate recorded per frame, or "all candidates -inf -> position 0"), 16 codes per word,
 // so a 460-frame, 58-state utterance needs 7.4 KB of shared memory instead of 26.7 KB and four
-// utterances fit one SM many times over.  A word holds the codes of ONE position for 16 consecutive frames: the
+// utterances share a CTA.  A word holds the codes of ONE position for 16 consecutive frames: the
 // backtrace then moves in RUNS -- one shared-memory load and one find-leading-one give the next
 // frame at which the path leaves its position (self loops dominate: ~70 runs for 400 frames), and
 // the whole warp writes the run's stretch of the path with one store.
@@ -20,7 +20,7 @@
 
 namespace loe {
 
-constexpr int kWarpsPerCta = 1;       // a CTA lives as long as its longest utterance: one warp per CTA lets every slot free up on its own
+constexpr int kWarpsPerCta = 1;
 constexpr int kPre = 8;
 constexpr size_t kWarpSmemCap = 200 * 1024;
 
@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32)
 viterbi_warp_kernel(VitArgs a, int n_utt) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr unsigned FULL = 0xffffffffu;
+    constexpr int FPW = 16;                              // frames per back-pointer word (one position)
     static_assert(kPre == 8, "two blocks of the time loop fill a back-pointer word");
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int u = blockIdx.x * kWarpsPerCta + warp;
