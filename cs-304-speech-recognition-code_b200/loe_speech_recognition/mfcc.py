@@ -85,27 +85,28 @@ def _distinct_bank_starts(first, last, span, lanes_per_filter):
     return chosen if place(0, set()) else None
 
 
-def _quarter_wavefronts(starts, first, last, span, lanes_per_filter):
+def _quarter_wavefronts(starts, first, last, span, lanes_per_filter, predicated=False):
     """Shared-memory wavefronts of one quarter-warp walking its windows in the [bin][4 frames] power layout of
-    mfcc_mel_r_kernel (16 bytes per bin, loads of zero-weight entries predicated off): per iteration the largest
-    number of DIFFERENT active bins that share a 16-byte bank group (bin mod 8)."""
+    mfcc_mel_r_kernel (16 bytes per bin): per iteration the largest number of DIFFERENT bins that share a 16-byte bank
+    group (bin mod 8).  The kernel loads every entry of a window (zero weights included); ``predicated`` counts only
+    the entries inside the filters' supports."""
     total = 0
     for it in range(span // lanes_per_filter):
         groups = {}
         for f, w in enumerate(starts):
             for j in range(lanes_per_filter):
                 b = w + j + lanes_per_filter * it
-                if first[f] <= b <= last[f]:
+                if not predicated or first[f] <= b <= last[f]:
                     groups.setdefault(b % 8, set()).add(b)
         total += max((len(v) for v in groups.values()), default=0)
     return total
 
 
-def _min_wavefront_starts(first, last, span, lanes_per_filter, restarts=120):
+def _min_wavefront_starts(first, last, span, lanes_per_filter, restarts=40):
     """Window starts (w[f] <= first[f], w[f] + span > last[f], w[f] >= 0) for the 16-byte-per-bin layout: per
     quarter-warp (8 lanes = 8 / lanes_per_filter filters) coordinate descent on _quarter_wavefronts from the natural
-    starts and from seeded random starts (deterministic); staggering the supports of narrow filters over the
-    iterations halves the wavefronts of the natural starts at 16 kHz."""
+    starts and from seeded random starts (deterministic): at 16 kHz 69 wavefronts per 8 frames and plane where the
+    natural starts need 139 (64 = one per iteration and quarter-warp is the floor)."""
     import random
     rnd = random.Random(304)
     n = len(first)
