@@ -17,6 +17,7 @@
 //
 // Algorithmic HBM bytes per frame: 4 * hop (PCM) + 12 * n_ceps (features).
 #include "common.cuh"
+#include "fft_regs.cuh"
 #include <math.h>
 
 namespace loe {
@@ -217,6 +218,284 @@ mel_ex_kernel(const SampleT* __restrict__ pcm, const int64_t* __restrict__ pcm_o
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// mel_ex512_kernel: the 512-point case (the "spec" parameter set) in the real-input-first form of mfcc_mel_r_kernel
+// (mfcc.cu): 512 = 32 x 16, n = 16 n1 + n2, k = k1 + 32 k2.
+//   step 1, thread (frame, n2):  T[k1][n2] = W_512^(n2 k1) * sum_n1 w[n] y[n] W_32^(n1 k1) for k1 = 0..16 -- a 32-point real
+//            DFT in registers: 16-point complex FFT of z[m] = (y[2m], y[2m+1]) and the in-thread real-input post-pass
+//            (compile-time W_32 twiddles; its factor 1/2 rides in the W_512 twiddles);
+//   step 2, thread (frame, k1):  one 16-point FFT of the row = the 16 bins k1 + 32 k2 (mirrored above 256).
+// Warp-private batches of 8 frames, 17 rows x 8 frames x (128 + 16) bytes per warp; the power planes ([plane of 4 frames]
+// [bin][frame]) take the place of the rows 9..16, so step 2 runs the rows 13..16 first (powers kept in registers), then
+// 9..12, 5..8, 1..4 and 0.  The filterbank runs over the 8 frames at once from the lane table of mel_ex_kernel.
+// Pre-emphasis needs the sample before every sample: a second set of loads (the window then comes from shared memory
+// instead of registers).  Samples are requested without tests from a base clamped into the utterance as soon as the
+// previous item has consumed its own; frames reaching outside the utterance are fetched again with bounds tests.
+namespace r512 {
+constexpr int kWarps = 4;
+constexpr int kBatch = 8;
+constexpr int kN = 512;
+constexpr int kBinsN = kN / 2 + 1;
+constexpr int kRows = 17;
+constexpr int kFrameB = 144;
+constexpr int kRowB = kBatch * kFrameB;          // 1152
+constexpr int kAreaB = kRows * kRowB;            // 19584 bytes per warp
+constexpr int kPlaneB = 4160;                    // 260 bins x 16 bytes; 16 banks mod 32
+constexpr int kPlane0 = 9 * kRowB;
+constexpr int kWinPitch = 36;                    // floats per n2 row of the permuted window: 16-byte loads of 8 lanes hit 8 bank groups
+static_assert(kPlane0 + 2 * kPlaneB <= kAreaB && kBinsN * 16 <= kPlaneB && (kPlaneB / 4) % 32 == 16, "power planes");
+
+struct __align__(16) Smem {
+    unsigned char area[kWarps][kAreaB];
+    float win[16 * kWinPitch];                   // win[n2 * kWinPitch + n1] = window[16 n1 + n2]
+    int binA[32], binB[32];
+    int na, nb, lb;
+};
+}  // namespace r512
+
+template <typename SampleT, bool PREEMPH>
+__global__ void __launch_bounds__(r512::kWarps * 32, 2)
+mel_ex512_kernel(const SampleT* __restrict__ pcm, const int64_t* __restrict__ pcm_off, const int64_t* __restrict__ frm_off,
+                 const float* __restrict__ window, int hop, float preemph,
+                 const int32_t* __restrict__ mel_start, const int32_t* __restrict__ mel_len, const float* __restrict__ mel_w,
+                 int mel_pitch, int n_mels, int chunk, float* __restrict__ mel_out, float* __restrict__ utt_max) {
+    using namespace r512;
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int kThreads = kWarps * 32;
+    extern __shared__ __align__(16) unsigned char smem_raw_e[];
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw_e);
+    float* s_w = reinterpret_cast<float*>(smem_raw_e + sizeof(Smem));     // [(na + nb) * 32] lane table of filter weights
+    const int u = blockIdx.x;
+    const int64_t f0 = frm_off[u];
+    const int T = (int)(frm_off[u + 1] - f0);
+    const int t_begin = blockIdx.y * chunk;
+    if (t_begin >= T) return;
+    const int t_end = min(T, t_begin + chunk);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    for (int i = tid; i < kN; i += kThreads) sm.win[(i & 15) * kWinPitch + (i >> 4)] = window[i];
+    for (int i = tid; i < kWarps * kAreaB / 4; i += kThreads) reinterpret_cast<float*>(&sm.area[0][0])[i] = 0.f;
+    // filterbank as a lane table, as mel_ex_kernel builds it
+    const int nA = min(n_mels, 32), nB = n_mels - nA;
+    if (warp == 0) {
+        int la = lane < nA ? mel_len[lane] : 0;
+        int lbn = lane < nB ? mel_len[32 + lane] : 0;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) { la = max(la, __shfl_xor_sync(FULL, la, o)); lbn = max(lbn, __shfl_xor_sync(FULL, lbn, o)); }
+        int lb = 32;
+        while (lb > 1 && lb * nB > 32) lb >>= 1;
+        if (lane == 0) { sm.na = la; sm.lb = lb; sm.nb = nB ? (lbn + lb - 1) / lb : 0; }
+    }
+    __syncthreads();
+    const int na = sm.na, nb = sm.nb, lb = sm.lb;
+    for (int i = tid; i < na * 32; i += kThreads) {
+        const int it = i >> 5, l = i & 31;
+        s_w[i] = (l < nA && it < mel_len[l]) ? mel_w[(size_t)l * mel_pitch + it] : 0.f;
+    }
+    for (int i = tid; i < nb * 32; i += kThreads) {
+        const int it = i >> 5, l = i & 31, q = l / lb, j = l % lb, m = 32 + q, e = j + lb * it;
+        s_w[na * 32 + i] = (q < nB && e < mel_len[m]) ? mel_w[(size_t)m * mel_pitch + e] : 0.f;
+    }
+    if (tid < 32) {
+        sm.binA[tid] = tid < nA ? mel_start[tid] : 0;
+        const int q = tid / lb;
+        sm.binB[tid] = q < nB ? mel_start[32 + q] + tid % lb : 0;
+    }
+    __syncthreads();
+    const int binA = sm.binA[lane], binB = sm.binB[lane];
+
+    // step 1 constants, thread = (frame parity fl, n2)
+    const int n2 = lane & 15, fl = lane >> 4;
+    float2 hw[PREEMPH ? 1 : 16];                       // window taps (w[16 (2m) + n2], w[16 (2m + 1) + n2]); with pre-emphasis: shared memory
+    if (!PREEMPH) {
+#pragma unroll
+        for (int m = 0; m < 16; ++m) hw[m] = make_float2(sm.win[n2 * kWinPitch + 2 * m], sm.win[n2 * kWinPitch + 2 * m + 1]);
+    }
+    float2 tw[17];                                      // W_512^(n2 k1), halved for k1 = 1..15 (the real-input post-pass)
+#pragma unroll
+    for (int k1 = 1; k1 <= 16; ++k1) {
+        float sn, cs;
+        sincospif(-2.0f * (float)(n2 * k1) / (float)kN, &sn, &cs);
+        const float h = k1 < 16 ? 0.5f : 1.0f;
+        tw[k1] = make_float2(h * cs, h * sn);
+    }
+    const int f8 = lane & 7, kq = lane >> 3;
+
+    const int64_t s0 = pcm_off[u];
+    const int ns = (int)(pcm_off[u + 1] - s0);
+    const SampleT* __restrict__ x = pcm + s0;
+    unsigned char* area = sm.area[warp];
+    float vmax = 0.f;
+
+    constexpr int kLo = PREEMPH ? 1 : 0;               // an interior frame also owns the sample before its first
+    const int base_max = ns - kN;                       // >= kLo (the caller checks the shortest utterance)
+    auto edge = [&](int t) { const int base = hop * t - kN / 2; return base < kLo || base > base_max; };
+    auto fetch_interior = [&](int t, float* r, float* p) {
+        const SampleT* __restrict__ xb = x + min(max(hop * t - kN / 2, kLo), base_max) + n2;
+#pragma unroll
+        for (int n1 = 0; n1 < 32; ++n1) r[n1] = to_f32(__ldg(xb + 16 * n1));
+        if (PREEMPH) {
+#pragma unroll
+            for (int n1 = 0; n1 < 32; ++n1) p[n1] = to_f32(__ldg(xb + 16 * n1 - 1));
+        }
+    };
+    auto fetch_edge = [&](int t, float* r, float* p) {   // zero outside the utterance; the first sample is its own predecessor
+        const int base = hop * t - kN / 2 + n2;
+#pragma unroll
+        for (int n1 = 0; n1 < 32; ++n1) {
+            const int i = base + 16 * n1;
+            const bool in = i >= 0 && i < ns;
+            r[n1] = in ? to_f32(__ldg(x + i)) : 0.f;
+            if (PREEMPH) p[n1] = in ? to_f32(__ldg(x + (i > 0 ? i - 1 : 0))) : 0.f;
+        }
+    };
+    float r[32], p[PREEMPH ? 32 : 1];
+    fetch_interior(t_begin + warp * kBatch + fl, r, p);
+
+    for (int tb = t_begin + warp * kBatch; tb < t_end; tb += kWarps * kBatch) {
+        // ---------------- step 1
+#pragma unroll 1
+        for (int ps = 0; ps < kBatch / 2; ++ps) {
+            const int fb = 2 * ps + fl, t = tb + fb;
+            if (edge(t) && t < t_end) fetch_edge(t, r, p);
+            float2 z[16];
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {
+                float y0 = r[2 * m], y1 = r[2 * m + 1];
+                if (PREEMPH) {                         // never contracted: float32 and int16 PCM agree bit for bit
+                    y0 = __fsub_rn(y0, __fmul_rn(preemph, p[2 * m]));
+                    y1 = __fsub_rn(y1, __fmul_rn(preemph, p[2 * m + 1]));
+                }
+                float2 w;
+                if (PREEMPH) w = *reinterpret_cast<const float2*>(&sm.win[n2 * kWinPitch + 2 * m]);
+                else w = hw[PREEMPH ? 0 : m];
+                z[m] = emul(make_float2(y0, y1), w);
+            }
+            fetch_interior((ps < kBatch / 2 - 1) ? t + 2 : tb + kWarps * kBatch + fl, r, p);
+            if (t < t_end) {
+                fft16(z);
+                // real-input post-pass: 2 Y[k] = e + w o, 2 Y[16 - k] = conj(e - w o), e = Z[k] + conj Z[16 - k],
+                // o = -i (Z[k] - conj Z[16 - k]), w = W_32^k
+                float2 Y[17];
+                Y[0] = make_float2(z[0].x + z[0].y, 0.f);
+                Y[16] = make_float2(z[0].x - z[0].y, 0.f);
+                Y[8] = make_float2(2.f * z[8].x, -2.f * z[8].y);
+                {
+                    constexpr float C32[8] = {1.f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f,
+                                              0.70710678118654752f, 0.55557023301960218f, 0.38268343236508977f, 0.19509032201612825f};
+                    constexpr float S32[8] = {0.f, 0.19509032201612825f, 0.38268343236508977f, 0.55557023301960218f,
+                                              0.70710678118654752f, 0.83146961230254524f, 0.92387953251128674f, 0.98078528040323043f};
+#pragma unroll
+                    for (int k = 1; k < 8; ++k) {
+                        const float2 A = z[k], B = z[16 - k];
+                        const float2 e = make_float2(A.x + B.x, A.y - B.y);
+                        const float2 o = make_float2(A.y + B.y, B.x - A.x);
+                        const float2 wo = cmul(make_float2(C32[k], -S32[k]), o);
+                        Y[k] = cadd(e, wo);
+                        const float2 d = csub(e, wo);
+                        Y[16 - k] = make_float2(d.x, -d.y);
+                    }
+                }
+                float2* slot = reinterpret_cast<float2*>(area + fb * kFrameB) + n2;
+                slot[0] = Y[0];
+#pragma unroll
+                for (int k1 = 1; k1 < 16; ++k1) slot[k1 * (kRowB / 8)] = cmul(Y[k1], tw[k1]);
+                slot[16 * (kRowB / 8)] = make_float2(Y[16].x * tw[16].x, Y[16].x * tw[16].y);
+            }
+        }
+        __syncwarp();
+        // ---------------- step 2
+        const bool fvalid = tb + f8 < t_end;
+        float* plane = reinterpret_cast<float*>(area + kPlane0 + (f8 >> 2) * kPlaneB) + (f8 & 3);
+        auto load_row = [&](int k1, float2* zz) {
+            const float4* src = reinterpret_cast<const float4*>(area + k1 * kRowB + f8 * kFrameB);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float4 q = src[c];
+                zz[2 * c] = make_float2(q.x, q.y);
+                zz[2 * c + 1] = make_float2(q.z, q.w);
+            }
+        };
+        auto power = [&](const float2* zz, float* pw) {
+#pragma unroll
+            for (int k2 = 0; k2 < 16; ++k2) pw[k2] = fmaf(zz[k2].x, zz[k2].x, zz[k2].y * zz[k2].y);
+        };
+        auto store_pw = [&](int k1, const float* pw) {
+            float* lo = plane + 4 * k1;                    // bin k1 + 32 k2, k2 = 0..7
+            float* hi = plane + 4 * (kN - k1);             // bin 512 - k1 - 32 k2, k2 = 8..15
+#pragma unroll
+            for (int k2 = 0; k2 < 8; ++k2) lo[128 * k2] = pw[k2];
+#pragma unroll
+            for (int k2 = 8; k2 < 16; ++k2) hi[-128 * k2] = pw[k2];
+        };
+        {
+            float pc[16], pd[16];
+            float2 za[16], zb[16];
+            if (fvalid) { load_row(13 + kq, za); fft16(za); power(za, pc); }
+            if (fvalid) load_row(9 + kq, zb);
+            __syncwarp();                                   // rows 9..16 are in registers: their area takes the power planes
+            if (fvalid) {
+                store_pw(13 + kq, pc);
+                fft16(zb); power(zb, pd); store_pw(9 + kq, pd);
+                load_row(5 + kq, za); fft16(za); power(za, pc); store_pw(5 + kq, pc);
+                load_row(1 + kq, zb); fft16(zb); power(zb, pd); store_pw(1 + kq, pd);
+                if (kq == 0) { load_row(0, za); fft16(za); power(za, pc); store_pw(0, pc); }
+            }
+        }
+        __syncwarp();
+        // ---------------- mel filterbank, 8 frames at once (run-time trip counts: any number of filters up to 64)
+        {
+            const int nf = min(kBatch, t_end - tb);
+            const unsigned char* planes = area + kPlane0;
+            float acc[8];
+#pragma unroll
+            for (int f = 0; f < 8; ++f) acc[f] = 0.f;
+            for (int it = 0; it < na; ++it) {
+                const float w = s_w[it * 32 + lane];
+                const unsigned char* pb_ = planes + min(binA + it, kN / 2) * 16;
+                const float4 a4 = *reinterpret_cast<const float4*>(pb_);
+                const float4 b4 = *reinterpret_cast<const float4*>(pb_ + kPlaneB);
+                acc[0] = fmaf(w, a4.x, acc[0]); acc[1] = fmaf(w, a4.y, acc[1]); acc[2] = fmaf(w, a4.z, acc[2]); acc[3] = fmaf(w, a4.w, acc[3]);
+                acc[4] = fmaf(w, b4.x, acc[4]); acc[5] = fmaf(w, b4.y, acc[5]); acc[6] = fmaf(w, b4.z, acc[6]); acc[7] = fmaf(w, b4.w, acc[7]);
+            }
+            if (lane < nA) {
+                float* mo = mel_out + (f0 + tb) * n_mels + lane;
+#pragma unroll
+                for (int f = 0; f < 8; ++f)
+                    if (f < nf) { mo[(size_t)f * n_mels] = acc[f]; vmax = fmaxf(vmax, acc[f]); }
+            }
+            if (nb > 0) {
+#pragma unroll
+                for (int f = 0; f < 8; ++f) acc[f] = 0.f;
+                for (int it = 0; it < nb; ++it) {
+                    const float w = s_w[(na + it) * 32 + lane];
+                    const unsigned char* pb_ = planes + min(binB + lb * it, kN / 2) * 16;
+                    const float4 a4 = *reinterpret_cast<const float4*>(pb_);
+                    const float4 b4 = *reinterpret_cast<const float4*>(pb_ + kPlaneB);
+                    acc[0] = fmaf(w, a4.x, acc[0]); acc[1] = fmaf(w, a4.y, acc[1]); acc[2] = fmaf(w, a4.z, acc[2]); acc[3] = fmaf(w, a4.w, acc[3]);
+                    acc[4] = fmaf(w, b4.x, acc[4]); acc[5] = fmaf(w, b4.y, acc[5]); acc[6] = fmaf(w, b4.z, acc[6]); acc[7] = fmaf(w, b4.w, acc[7]);
+                }
+                for (int o = 1; o < lb; o <<= 1) {
+#pragma unroll
+                    for (int f = 0; f < 8; ++f) acc[f] += __shfl_xor_sync(FULL, acc[f], o);
+                }
+                if (lane % lb == 0 && lane / lb < nB) {
+                    float* mb = mel_out + (f0 + tb) * n_mels + 32 + lane / lb;
+#pragma unroll
+                    for (int f = 0; f < 8; ++f)
+                        if (f < nf) { mb[(size_t)f * n_mels] = acc[f]; vmax = fmaxf(vmax, acc[f]); }
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (utt_max) {
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(FULL, vmax, o));
+        if (lane == 0) atomicMax(reinterpret_cast<int*>(utt_max + u), __float_as_int(vmax));        // mel >= 0
+    }
+}
+
 // thread per frame: log, DCT-II (coefficient table in shared memory).  NM / NC > 0: compile-time sizes (the mel row and
 // the loops live in registers); 0: run-time sizes (local-memory row).
 template <int NM, int NC>
@@ -363,6 +642,21 @@ static int launch_mel_ex(const void* pcm_dev, const int64_t* pcm_off_dev, const 
     return LOE_OK;
 }
 
+template <typename SampleT, bool PREEMPH>
+static int launch_mel_ex512(const void* pcm_dev, const int64_t* pcm_off_dev, const int64_t* frm_off_dev, int n_utt, int max_frames,
+                            int chunk, const loe_mfcc_config* cfg, const float* window_dev, const int32_t* mel_start_dev,
+                            const int32_t* mel_len_dev, const float* mel_w_dev, int mel_pitch, float* mel_ws_dev, float* utt_max_dev,
+                            cudaStream_t s) {
+    const size_t smem = sizeof(r512::Smem) + sizeof(float) * 64 * (size_t)mel_pitch;
+    LOE_CUDA(cudaFuncSetAttribute(mel_ex512_kernel<SampleT, PREEMPH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)n_utt, (unsigned)((max_frames + chunk - 1) / chunk));
+    mel_ex512_kernel<SampleT, PREEMPH><<<grid, r512::kWarps * 32, smem, s>>>(
+        (const SampleT*)pcm_dev, pcm_off_dev, frm_off_dev, window_dev, cfg->hop, cfg->preemph, mel_start_dev, mel_len_dev, mel_w_dev,
+        mel_pitch, cfg->n_mels, chunk, mel_ws_dev, cfg->log_mode == LOE_LOG_DB ? utt_max_dev : nullptr);
+    LOE_LAUNCH_CHECK("mel_ex512_kernel");
+    return LOE_OK;
+}
+
 }  // namespace loe
 
 extern "C" int loe_mfcc_ex_dev(const void* pcm_dev, int pcm_format, const int64_t* pcm_off_dev, const int64_t* frm_off_dev,
@@ -401,6 +695,23 @@ extern "C" int loe_mfcc_ex_dev(const void* pcm_dev, int pcm_format, const int64_
     chunk64 = ((chunk64 + kWarpsE - 1) / kWarpsE) * kWarpsE;
     const int chunk = (int)(chunk64 < 64 ? 64 : chunk64 > (1 << 20) ? (1 << 20) : chunk64);
     int st = LOE_OK;
+    // 512-point FFT (the "spec" set): the real-input-first register kernel, as long as the shortest utterance holds a whole
+    // frame plus the sample before it (the kernel's test-free loads are clamped into the utterance)
+    if (log2n == 9 && (int64_t)(min_frames - 1) * cfg->hop >= 514) {
+        const int round = r512::kWarps * r512::kBatch;
+        const int chunk5 = ((chunk + round - 1) / round) * round;
+        const bool pre = cfg->preemph != 0.f;
+        if (pcm_format == LOE_PCM_F32)
+            st = pre ? launch_mel_ex512<float, true>(pcm_dev, pcm_off_dev, frm_off_dev, n_utt, max_frames, chunk5, cfg, window_dev, mel_start_dev,
+                                                     mel_len_dev, mel_w_dev, mel_pitch, mel_ws_dev, utt_stat_dev, s)
+                     : launch_mel_ex512<float, false>(pcm_dev, pcm_off_dev, frm_off_dev, n_utt, max_frames, chunk5, cfg, window_dev, mel_start_dev,
+                                                      mel_len_dev, mel_w_dev, mel_pitch, mel_ws_dev, utt_stat_dev, s);
+        else
+            st = pre ? launch_mel_ex512<short, true>(pcm_dev, pcm_off_dev, frm_off_dev, n_utt, max_frames, chunk5, cfg, window_dev, mel_start_dev,
+                                                     mel_len_dev, mel_w_dev, mel_pitch, mel_ws_dev, utt_stat_dev, s)
+                     : launch_mel_ex512<short, false>(pcm_dev, pcm_off_dev, frm_off_dev, n_utt, max_frames, chunk5, cfg, window_dev, mel_start_dev,
+                                                      mel_len_dev, mel_w_dev, mel_pitch, mel_ws_dev, utt_stat_dev, s);
+    } else {
 #define LOE_EX(L)                                                                                                                    \
     case L:                                                                                                                          \
         st = pcm_format == LOE_PCM_F32                                                                                               \
@@ -411,6 +722,7 @@ extern "C" int loe_mfcc_ex_dev(const void* pcm_dev, int pcm_format, const int64_
         break
     switch (log2n) { LOE_EX(6); LOE_EX(7); LOE_EX(8); LOE_EX(9); LOE_EX(10); }
 #undef LOE_EX
+    }
     if (st != LOE_OK) return st;
     const unsigned blocks = (unsigned)((total_frames + 127) / 128);
     if (cfg->n_mels == 40 && cfg->n_ceps == 13)
