@@ -19,6 +19,8 @@
 #include "common.cuh"
 #include "fft_regs.cuh"
 #include <math.h>
+#include <atomic>
+#include <mutex>
 
 namespace loe {
 
@@ -231,6 +233,8 @@ mel_ex_kernel(const SampleT* __restrict__ pcm, const int64_t* __restrict__ pcm_o
 // Pre-emphasis needs the sample before every sample: a second set of loads (the window then comes from shared memory
 // instead of registers).  Samples are requested without tests from a base clamped into the utterance as soon as the
 // previous item has consumed its own; frames reaching outside the utterance are fetched again with bounds tests.
+__device__ float2 g_w512[256];                   // W_512^j, j < 256 (uploaded once per device, see ensure_w512)
+
 namespace r512 {
 constexpr int kWarps = 4;
 constexpr int kBatch = 8;
@@ -242,7 +246,7 @@ constexpr int kRowB = kBatch * kFrameB;          // 1152
 constexpr int kAreaB = kRows * kRowB;            // 19584 bytes per warp
 constexpr int kPlaneB = 4160;                    // 260 bins x 16 bytes; 16 banks mod 32
 constexpr int kPlane0 = 9 * kRowB;
-constexpr int kWinPitch = 36;                    // floats per n2 row of the permuted window: 16-byte loads of 8 lanes hit 8 bank groups
+constexpr int kWinPitch = 34;                    // floats per n2 row of the permuted window: the 8-byte loads of 16 lanes hit 32 banks
 static_assert(kPlane0 + 2 * kPlaneB <= kAreaB && kBinsN * 16 <= kPlaneB && (kPlaneB / 4) % 32 == 16, "power planes");
 
 struct __align__(16) Smem {
@@ -314,10 +318,9 @@ mel_ex512_kernel(const SampleT* __restrict__ pcm, const int64_t* __restrict__ pc
     float2 tw[17];                                      // W_512^(n2 k1), halved for k1 = 1..15 (the real-input post-pass)
 #pragma unroll
     for (int k1 = 1; k1 <= 16; ++k1) {
-        float sn, cs;
-        sincospif(-2.0f * (float)(n2 * k1) / (float)kN, &sn, &cs);
+        const float2 wv = g_w512[n2 * k1];              // n2 k1 <= 240
         const float h = k1 < 16 ? 0.5f : 1.0f;
-        tw[k1] = make_float2(h * cs, h * sn);
+        tw[k1] = make_float2(h * wv.x, h * wv.y);
     }
     const int f8 = lane & 7, kq = lane >> 3;
 
@@ -461,8 +464,10 @@ mel_ex512_kernel(const SampleT* __restrict__ pcm, const int64_t* __restrict__ pc
             if (lane < nA) {
                 float* mo = mel_out + (f0 + tb) * n_mels + lane;
 #pragma unroll
-                for (int f = 0; f < 8; ++f)
-                    if (f < nf) { mo[(size_t)f * n_mels] = acc[f]; vmax = fmaxf(vmax, acc[f]); }
+                for (int f = 0; f < 8; ++f) {
+                    if (f < nf) { *mo = acc[f]; vmax = fmaxf(vmax, acc[f]); }
+                    mo += n_mels;
+                }
             }
             if (nb > 0) {
 #pragma unroll
@@ -482,8 +487,10 @@ mel_ex512_kernel(const SampleT* __restrict__ pcm, const int64_t* __restrict__ pc
                 if (lane % lb == 0 && lane / lb < nB) {
                     float* mb = mel_out + (f0 + tb) * n_mels + 32 + lane / lb;
 #pragma unroll
-                    for (int f = 0; f < 8; ++f)
-                        if (f < nf) { mb[(size_t)f * n_mels] = acc[f]; vmax = fmaxf(vmax, acc[f]); }
+                    for (int f = 0; f < 8; ++f) {
+                        if (f < nf) { *mb = acc[f]; vmax = fmaxf(vmax, acc[f]); }
+                        mb += n_mels;
+                    }
                 }
             }
         }
@@ -579,51 +586,64 @@ cmn_ex_kernel(const float* __restrict__ ceps, const int64_t* __restrict__ frm_of
 __global__ void __launch_bounds__(128)
 feat_ex_kernel(const float* __restrict__ ceps, const float* __restrict__ stat, const int64_t* __restrict__ frm_off, int n_utt,
                int64_t total_frames, int n_ceps, int norm_mode, float* __restrict__ feat) {
-    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= total_frames) return;
-    int lo = 0, hi = n_utt;
-    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (frm_off[mid] <= f) lo = mid; else hi = mid; }
-    const int64_t f0 = frm_off[lo];
-    const int T = (int)(frm_off[lo + 1] - f0);
-    const int t = (int)(f - f0);
-    const float* c = ceps + f * n_ceps;
-    float* o = feat + f * 3 * n_ceps;
-    if (norm_mode == LOE_NORM_FRAME) {
-        float mean = 0.f;
-        for (int k = 0; k < n_ceps; ++k) mean += c[k];
-        mean /= (float)n_ceps;
-        float var = 0.f;
-        for (int k = 0; k < n_ceps; ++k) { const float d = c[k] - mean; var = fmaf(d, d, var); }
-        const float inv = 1.0f / (sqrtf(var / (float)n_ceps) + 1e-8f);
-        for (int k = 0; k < n_ceps; ++k) o[k] = (c[k] - mean) * inv;
-    } else if (norm_mode == LOE_NORM_CMN || norm_mode == LOE_NORM_CMVN) {
-        const float* st = stat + (size_t)lo * 2 * n_ceps;
-        for (int k = 0; k < n_ceps; ++k) {
-            const float d = c[k] - st[k];
-            o[k] = norm_mode == LOE_NORM_CMVN ? d * st[n_ceps + k] : d;
+    // a CTA's 128 frames are 128 consecutive rows of the feature matrix whatever utterances they belong to: the rows are
+    // put together in shared memory (odd pitch: row-per-lane stores hit 32 banks) and written out as one contiguous run
+    __shared__ float s_out[128 * (3 * kMaxCepsE + 1)];
+    const int width = 3 * n_ceps, pitch = width | 1;
+    const int64_t fb = (int64_t)blockIdx.x * blockDim.x;
+    const int64_t f = fb + threadIdx.x;
+    if (f < total_frames) {
+        int lo = 0, hi = n_utt;
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (frm_off[mid] <= f) lo = mid; else hi = mid; }
+        const int64_t f0 = frm_off[lo];
+        const int T = (int)(frm_off[lo + 1] - f0);
+        const int t = (int)(f - f0);
+        const float* c = ceps + f * n_ceps;
+        float* o = s_out + threadIdx.x * pitch;
+        if (norm_mode == LOE_NORM_FRAME) {
+            float mean = 0.f;
+            for (int k = 0; k < n_ceps; ++k) mean += c[k];
+            mean /= (float)n_ceps;
+            float var = 0.f;
+            for (int k = 0; k < n_ceps; ++k) { const float d = c[k] - mean; var = fmaf(d, d, var); }
+            const float inv = 1.0f / (sqrtf(var / (float)n_ceps) + 1e-8f);
+            for (int k = 0; k < n_ceps; ++k) o[k] = (c[k] - mean) * inv;
+        } else if (norm_mode == LOE_NORM_CMN || norm_mode == LOE_NORM_CMVN) {
+            const float* st = stat + (size_t)lo * 2 * n_ceps;
+            for (int k = 0; k < n_ceps; ++k) {
+                const float d = c[k] - st[k];
+                o[k] = norm_mode == LOE_NORM_CMVN ? d * st[n_ceps + k] : d;
+            }
+        } else {
+            for (int k = 0; k < n_ceps; ++k) o[k] = c[k];
         }
-    } else {
-        for (int k = 0; k < n_ceps; ++k) o[k] = c[k];
-    }
-    const int cc = min(max(t, 4), T - 5);
-    float d1[kMaxCepsE], d2[kMaxCepsE];
+        const int cc = min(max(t, 4), T - 5);
+        float d1[kMaxCepsE], d2[kMaxCepsE];
 #pragma unroll
-    for (int k = 0; k < kMaxCepsE; ++k) { d1[k] = 0.f; d2[k] = 0.f; }
+        for (int k = 0; k < kMaxCepsE; ++k) { d1[k] = 0.f; d2[k] = 0.f; }
 #pragma unroll
-    for (int q = -4; q <= 4; ++q) {                   // neighbour-major: every row of 13 coefficients is read as a run
-        const float* nrow = ceps + (f0 + cc + q) * n_ceps;
-        const float w1 = (float)q * (1.0f / 60.0f), w2 = (float)(3 * q * q - 20) * (1.0f / 462.0f);
+        for (int q = -4; q <= 4; ++q) {                   // neighbour-major: every row of 13 coefficients is read as a run
+            const float* nrow = ceps + (f0 + cc + q) * n_ceps;
+            const float w1 = (float)q * (1.0f / 60.0f), w2 = (float)(3 * q * q - 20) * (1.0f / 462.0f);
+#pragma unroll
+            for (int k = 0; k < kMaxCepsE; ++k)
+                if (k < n_ceps) {
+                    const float cv = __ldg(nrow + k);
+                    d1[k] = fmaf(w1, cv, d1[k]);
+                    d2[k] = fmaf(w2, cv, d2[k]);
+                }
+        }
 #pragma unroll
         for (int k = 0; k < kMaxCepsE; ++k)
-            if (k < n_ceps) {
-                const float cv = __ldg(nrow + k);
-                d1[k] = fmaf(w1, cv, d1[k]);
-                d2[k] = fmaf(w2, cv, d2[k]);
-            }
+            if (k < n_ceps) { o[n_ceps + k] = d1[k]; o[2 * n_ceps + k] = d2[k]; }
     }
-#pragma unroll
-    for (int k = 0; k < kMaxCepsE; ++k)
-        if (k < n_ceps) { o[n_ceps + k] = d1[k]; o[2 * n_ceps + k] = d2[k]; }
+    __syncthreads();
+    const int rows = (int)min((int64_t)blockDim.x, total_frames - fb);
+    float* __restrict__ dst = feat + fb * width;
+    for (int i = threadIdx.x; i < rows * width; i += blockDim.x) {
+        const int rr = i / width;
+        dst[i] = s_out[rr * pitch + (i - rr * width)];
+    }
 }
 
 template <typename SampleT, int LOG2N>
@@ -642,12 +662,35 @@ static int launch_mel_ex(const void* pcm_dev, const int64_t* pcm_off_dev, const 
     return LOE_OK;
 }
 
+// one-time upload of W_512^j per device (double-precision host values; the copy goes through the legacy stream from
+// pageable memory while the kernel runs on the caller's stream: the device is synchronised once, host threads serialised)
+static int ensure_w512() {
+    static std::atomic<bool> ready[64];
+    static std::mutex mtx;
+    int dev = 0;
+    LOE_CUDA(cudaGetDevice(&dev));
+    if (dev < 64 && ready[dev].load(std::memory_order_acquire)) return LOE_OK;
+    std::lock_guard<std::mutex> lock(mtx);
+    if (dev < 64 && ready[dev].load(std::memory_order_acquire)) return LOE_OK;
+    static float2 h[256];
+    for (int j = 0; j < 256; ++j) {
+        const double a = -2.0 * 3.14159265358979323846 * j / 512.0;
+        h[j] = make_float2((float)cos(a), (float)sin(a));
+    }
+    LOE_CUDA(cudaMemcpyToSymbol(g_w512, h, sizeof(h)));
+    LOE_CUDA(cudaDeviceSynchronize());
+    if (dev < 64) ready[dev].store(true, std::memory_order_release);
+    return LOE_OK;
+}
+
 template <typename SampleT, bool PREEMPH>
 static int launch_mel_ex512(const void* pcm_dev, const int64_t* pcm_off_dev, const int64_t* frm_off_dev, int n_utt, int max_frames,
                             int chunk, const loe_mfcc_config* cfg, const float* window_dev, const int32_t* mel_start_dev,
                             const int32_t* mel_len_dev, const float* mel_w_dev, int mel_pitch, float* mel_ws_dev, float* utt_max_dev,
                             cudaStream_t s) {
     const size_t smem = sizeof(r512::Smem) + sizeof(float) * 64 * (size_t)mel_pitch;
+    const int st = ensure_w512();
+    if (st != LOE_OK) return st;
     LOE_CUDA(cudaFuncSetAttribute(mel_ex512_kernel<SampleT, PREEMPH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)n_utt, (unsigned)((max_frames + chunk - 1) / chunk));
     mel_ex512_kernel<SampleT, PREEMPH><<<grid, r512::kWarps * 32, smem, s>>>(

@@ -245,6 +245,25 @@ class MFCCConfig:
             nz = np.nonzero(dense[m])[0]
             if len(nz):
                 start[m], length[m] = nz[0], nz[-1] - nz[0] + 1
+        first = start.copy()
+        if self.n_fft == 512 and self.n_mels > 0 and int(length.min()) > 0:
+            # mel_ex512_kernel reads 16-byte [bin][4 frames] entries, a quarter-warp per wavefront, and every lane walks a
+            # window as long as the widest filter of its round: a narrower filter may start earlier (leading zero weights)
+            # -- the starts are slid so that the loads of one iteration spread over the bank groups (same search as
+            # mel_lane_tables).  Round A: filters 0..31, one lane each; round B: the others, lb lanes each.
+            n_a = min(self.n_mels, 32)
+            n_b = self.n_mels - n_a
+            last = start + length - 1
+            span_a = int(length[:n_a].max())
+            start[:n_a] = _min_wavefront_starts([int(v) for v in first[:n_a]], [int(v) for v in last[:n_a]], span_a, 1)
+            if n_b:
+                lb = 32
+                while lb > 1 and lb * n_b > 32:
+                    lb >>= 1
+                if lb <= 8:
+                    span_b = lb * int(-(-int(length[n_a:].max()) // lb))
+                    start[n_a:] = _min_wavefront_starts([int(v) for v in first[n_a:]], [int(v) for v in last[n_a:]], span_b, lb)
+            length = (last - start + 1).astype(np.int32)
         pitch = max(1, int(length.max()))
         w = np.zeros((self.n_mels, pitch), dtype=np.float32)
         for m in range(self.n_mels):
