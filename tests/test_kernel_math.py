@@ -162,6 +162,55 @@ def test_mel_r_kernel_real_first_decomposition():
             assert len(banks) == len(lanes)
 
 
+def test_mel_ex512_real_first_decomposition():
+    """mel_ex512_kernel (csrc/mfcc_ex.cu): 512 = 32 x 16; the 32-point real DFT as a 16-point complex FFT of
+    z[m] = (y[2m], y[2m+1]) plus the in-thread post-pass whose factor 1/2 rides in the W_512 twiddles; rows, mirrored
+    bins and the shared-memory geometry."""
+    src = open(os.path.join(CSRC, "mfcc_ex.cu")).read()
+    const = {k: int(v) for k, v in re.findall(r"constexpr int (k\w+) = (\d+);", src[src.index("namespace r512 {"):])}
+    frame_b, plane_b, batch, win_pitch = const["kFrameB"], const["kPlaneB"], const["kBatch"], const["kWinPitch"]
+    row_b = batch * frame_b
+    plane0 = 9 * row_b
+    assert frame_b % 16 == 0 and (frame_b // 16) % 2 == 1
+    assert (plane_b // 4) % 32 == 16 and plane0 + 2 * plane_b <= 17 * row_b and 257 * 16 <= plane_b
+    assert win_pitch % 2 == 0 and (win_pitch // 2) % 2 == 1 and win_pitch >= 32     # 8-byte loads of 16 lanes: 32 banks
+    rng = np.random.default_rng(2)
+
+    def rdft32_doubled(y):
+        """what the thread holds before the W_512 twiddles: Y[0], Y[16] plain, 2 Y[k] for k = 1..15"""
+        Z = np.array(_fft16(list(y[0::2] + 1j * y[1::2])))
+        Y = np.zeros(17, complex)
+        Y[0], Y[16], Y[8] = Z[0].real + Z[0].imag, Z[0].real - Z[0].imag, 2 * np.conj(Z[8])
+        for k in range(1, 8):
+            A, B = Z[k], Z[16 - k]
+            e, o = complex(A.real + B.real, A.imag - B.imag), complex(A.imag + B.imag, B.real - A.real)
+            wo = _w(32, k) * o
+            Y[k], Y[16 - k] = e + wo, np.conj(e - wo)
+        return Y
+    y = rng.normal(size=32)
+    ref32 = np.fft.fft(y)[:17]
+    got = rdft32_doubled(y)
+    assert np.allclose(got[[0, 16]], ref32[[0, 16]]) and np.allclose(got[1:16], 2 * ref32[1:16])
+    xw = rng.normal(0, 3000, 512) * np.hamming(512)
+    rows = np.zeros((17, 16), complex)
+    for n2 in range(16):
+        Y = rdft32_doubled(xw[n2::16])
+        for k1 in range(17):
+            rows[k1, n2] = Y[k1] * _w(512, n2 * k1) * (0.5 if 1 <= k1 <= 15 else 1.0)
+    ref = np.abs(np.fft.rfft(xw)) ** 2
+    power = np.full(257, np.nan)
+    for k1 in range(17):
+        X = _fft16(rows[k1])
+        for k2 in range(16):
+            off = 4 * k1 + 128 * k2 if k2 < 8 else 4 * (512 - k1) - 128 * k2        # store_pw: lo[128 k2] / hi[-128 k2]
+            b = off // 4
+            assert b == (k1 + 32 * k2 if k2 < 8 else 512 - k1 - 32 * k2) and 0 <= b <= 256
+            power[b] = abs(X[k2]) ** 2
+    assert not np.isnan(power).any() and np.abs(power - ref).max() <= 1e-12 * ref.max()
+    # step 2 passes: rows 13..16 (kept in registers), 9..12, 5..8, 1..4, 0 -- the planes only cover rows 9..16
+    assert plane0 == 9 * row_b and [13 + kq for kq in range(4)][-1] == 16
+
+
 def test_emission_h16_pairing_table():
     src = open(os.path.join(CSRC, "emission_h16.cu")).read()
     body = src[src.index("constexpr int t[kNumMma][5] = {"):]
