@@ -605,15 +605,30 @@ def _prefer_spawn() -> None:
     """The reference's scripts map ``predict`` over ``concurrent.futures.ProcessPoolExecutor()``
     (scripts/project3_predict_simple.py:23-27, project5_test_*.py:33-41) after computing MFCCs in the
     parent.  A CUDA context does not survive fork(), so from the moment THIS process owns one, pools
-    created with the default context must spawn (workers then create their own engine lazily).  Done when
-    the engine is created -- never at import -- and only if the application has not chosen a start method
-    itself; LOE_B200_KEEP_START_METHOD=1 opts out."""
+    created with the default context must not fork it (workers create their own engine lazily).  The
+    default becomes ``forkserver`` with this package and torch preloaded into the server: the server never
+    touches CUDA, so its children are clean, and they start in milliseconds instead of re-importing torch
+    for every pool (the scripts open one pool per label / per penalty value: 22 pools in
+    project3_predict_simple.py, 100 in project5_find_trans_ndigits_with_sil.py).  Done when the engine is
+    created -- never at import -- and only if the application has not chosen a (non-fork) start method itself;
+    LOE_B200_START_METHOD=spawn selects plain spawn, LOE_B200_KEEP_START_METHOD=1 opts out."""
     import multiprocessing
     if os.environ.get("LOE_B200_KEEP_START_METHOD"):
         return
+    method = os.environ.get("LOE_B200_START_METHOD", "forkserver")
+    if method not in ("forkserver", "spawn"):
+        raise ValueError(f"LOE_B200_START_METHOD={method!r}: 'forkserver' or 'spawn' (a CUDA context does not survive fork)")
     try:
-        if multiprocessing.get_start_method(allow_none=True) is None:
-            multiprocessing.set_start_method("spawn")
+        # "fork" counts as not chosen: it is what an unset default turns into as soon as anything asks for a context
+        # (tqdm creates a multiprocessing lock for its first progress bar: scripts/project3_predict_simple.py:15 does so
+        # before the first MFCC), and a forked worker could never use this process's CUDA context anyway
+        current = multiprocessing.get_start_method(allow_none=True)
+        if current is None or current == "fork":
+            if method == "forkserver" and "forkserver" not in multiprocessing.get_all_start_methods():
+                method = "spawn"
+            multiprocessing.set_start_method(method, force=True)
+            if method == "forkserver":
+                multiprocessing.set_forkserver_preload(["__main__", "torch", __name__.split(".")[0]])
     except RuntimeError:
         pass
 
@@ -624,7 +639,7 @@ def get_engine() -> Engine:
     if _ENGINE is None or _ENGINE_PID != os.getpid():
         if _ENGINE is not None:
             raise RuntimeError("loe_speech_recognition: this process was forked from one that already owns a CUDA "
-                               "context; use the 'spawn' start method (multiprocessing.get_context('spawn'))")
+                               "context; use the 'forkserver' or 'spawn' start method (multiprocessing.get_context('spawn'))")
         _ENGINE = Engine()
         _ENGINE_PID = os.getpid()
         _prefer_spawn()

@@ -7,7 +7,7 @@ way the reference's drivers use it (scripts/project5_train_no_empty.py, project5
   -> concurrent.futures.ProcessPoolExecutor().map(partial(_make_prediction, hmm), labeled.items())
 
 Every hot-path call lands in the CUDA kernels; the process pool works because importing the package
-switches multiprocessing to "spawn".  Run on a GPU box:  python examples/digits_pipeline.py [workdir]
+switches multiprocessing to "forkserver" (torch preloaded, no CUDA in the server) when the engine is created.  Run on a GPU box:  python examples/digits_pipeline.py [workdir]
 """
 import concurrent.futures
 import functools
@@ -65,7 +65,7 @@ def main():
         batch_pred.extend(hmm_inference.predict_batch(feats))
     assert batch_pred == pred, "process-pool predictions differ from the batched entry point"
     acc = sum(a == b for a, b in zip(truth, pred)) / len(truth)
-    print(f"decoded {len(truth)} strings through a spawn process pool, exact-string accuracy {acc:.2f}; models in {model_dir}")
+    print(f"decoded {len(truth)} strings through a process pool, exact-string accuracy {acc:.2f}; models in {model_dir}")
     return acc
 
 

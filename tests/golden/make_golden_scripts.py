@@ -2,6 +2,7 @@
 when its own driver scripts run on the synthetic corpus of tests/ref_scripts_harness.py.
 
     python tests/golden/make_golden_scripts.py            (authoring container: needs /root/reference; ~2 min of CPU)
+    python tests/golden/make_golden_scripts.py --extra    (the seven other non-interactive drivers -> golden_scripts_extra.*)
 
 The three scripts are executed as files, unmodified, with PYTHONPATH = the reference's ``src`` + stub modules for its
 absent third-party imports (``librosa`` forwards to the restated oracle front end, see the harness).  The GPU test
@@ -78,5 +79,46 @@ def main():
         print("wrote golden_scripts.json / .npz:", len(record["csv"]), "csv files,", len(arrays), "arrays")
 
 
+def main_extra():
+    """The other non-interactive drivers (ref_scripts_harness.EXTRA_SCRIPTS) against the real reference: result lines,
+    CSV tables, the digit pairs project4_2digits.py drew and what it predicted for them, and the models
+    project5_train_no_empty.py trains (silence stripper -> MFCC -> segmental K-means, 11 digits + the silence model)."""
+    assert os.path.isdir(REF_SRC), "needs the reference checkout"
+    with tempfile.TemporaryDirectory() as ws:
+        made = H.build_corpus(ws)
+        stubs = H.write_stubs(os.path.join(ws, "_stubs"))
+        env_stubs = H.write_env_stubs(os.path.join(ws, "_env"))
+        pp = [REF_SRC, env_stubs, stubs, os.path.join(ROOT, "tests"), ROOT]
+        seed = ("import sys, numpy as np, ref_scripts_harness as H; "
+                f"g = np.load({os.path.join(HERE, 'golden_hmm.npz')!r}); H.seed_all_models(g)")
+        subprocess.run([sys.executable, "-c", seed], cwd=ws, env=dict(os.environ, PYTHONPATH=os.pathsep.join(pp)), check=True)
+        ws2 = H.second_workspace(ws)
+        record = {"corpus": made, "stdout": {}, "csv": {}, "returncode": {}, "exception": {}, "logged": {}}
+        for name in H.EXTRA_SCRIPTS:
+            cwd = ws2 if name == "project5_train_no_empty.py" else ws
+            before = set(os.listdir(os.path.join(cwd, "plots")))
+            start = H.log_size(cwd)
+            r = H.run_script(name, cwd, pp, timeout=3000)
+            record["stdout"][name] = H.stdout_record(r.stdout)
+            record["returncode"][name] = r.returncode
+            record["exception"][name] = H.last_exception(r.stderr)
+            record["logged"][name] = H.logged_predictions(cwd, start)
+            record["csv"][name] = {f: H.read_csv(os.path.join(cwd, "plots", f))
+                                   for f in sorted(set(os.listdir(os.path.join(cwd, "plots"))) - before) if f.endswith(".csv")}
+            print(name, r.returncode, record["exception"][name], record["stdout"][name][:4], len(record["logged"][name]),
+                  sorted(record["csv"][name]))
+            if r.returncode != 0:
+                print(r.stderr[-1500:])
+        arrays = {}
+        trained = os.path.join(ws2, ".cache", "big_model_speech_only")
+        if os.path.isdir(trained):
+            # model_arrays() finds the stub modules relative to <folder>/../../_stubs
+            os.symlink(stubs, os.path.join(ws2, "_stubs"))
+            model_arrays(trained, "p5t", arrays)
+        json.dump(record, open(os.path.join(HERE, "golden_scripts_extra.json"), "w"), indent=1, sort_keys=True)
+        np.savez_compressed(os.path.join(HERE, "golden_scripts_extra.npz"), **arrays)
+        print("wrote golden_scripts_extra.json / .npz:", len(arrays), "arrays")
+
+
 if __name__ == "__main__":
-    main()
+    main_extra() if "--extra" in sys.argv[1:] else main()

@@ -22,23 +22,30 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "cs-304-speech-recognition-code_b200")
 SCRIPTS = ("project3_train.py", "project5_test_ndigits_with_sil.py", "project6_train.py")
+# the rest of the reference's non-interactive drivers.  Not runnable under any replacement that owns a CUDA context:
+# project4_phone.py opens its process pool at module level without a __main__ guard (only fork() can serve that, and a CUDA
+# context does not survive fork); the *_interactive.py / record.py / mic_testing.py / play_all.py / project1.py drivers need
+# audio hardware.
+EXTRA_SCRIPTS = ("project3_predict_simple.py", "project4_2digits.py", "project5_test_1digit.py", "project5_test_ndigits_no_sil.py",
+                 "project5_find_trans_ndigits_no_sil.py", "project5_find_trans_ndigits_with_sil.py", "project5_train_no_empty.py")
 MODEL_ORDER = ("1", "2", "3", "4", "5", "6", "7", "8", "9", "O", "S", "Z")
 
 
 def scripts_dir():
     for d in ("/root/reference/scripts", os.path.join(ROOT, "oracle", "_ref", "scripts")):
-        if all(os.path.exists(os.path.join(d, s)) for s in SCRIPTS):
+        if all(os.path.exists(os.path.join(d, s)) for s in SCRIPTS + EXTRA_SCRIPTS):
             return d
     return None
 
 
-def write_seed_models(folder: str, golden) -> None:
+def write_seed_models(folder: str, golden, order=MODEL_ORDER) -> None:
     """Reference-format model folders (<label>/{log_trans_probs,multivariate_normals}.pickle) of the 12 word models the
-    unmodified reference trained for tests/golden/golden_hmm.npz.  Written by whichever ``loe_speech_recognition`` is
-    importable in the calling process (the pickles embed that module path, and both packages read each other's files)."""
+    unmodified reference trained for tests/golden/golden_hmm.npz (``order``: which of them).  Written by whichever
+    ``loe_speech_recognition`` is importable in the calling process (the pickles embed that module path, and both packages
+    read each other's files)."""
     from loe_speech_recognition.hidden_markov_model import HiddenMarkovModel, HiddenMarkovModelTrainable
     from loe_speech_recognition.transition_probability import LogTransitionProbabilities
-    for w in MODEL_ORDER:
+    for w in order:
         m = HiddenMarkovModel(w)
         m._multivariate_normals = HiddenMarkovModelTrainable.get_multivariate_normals(golden[f"train_means_{w}"], golden[f"train_covs_{w}"])
         ltp = LogTransitionProbabilities()
@@ -119,7 +126,12 @@ class feature:
     def delta(m, order=1):
         return _OM.delta(m, order)
 ''')
-    permissive = '''
+    for name in ("sounddevice.py", "uniplot.py", "soundfile.py", os.path.join("matplotlib", "__init__.py"), os.path.join("matplotlib", "pyplot.py")):
+        open(os.path.join(folder, name), "w").write(_PERMISSIVE)
+    return folder
+
+
+_PERMISSIVE = '''
 class _Any:
     def __call__(self, *a, **k): return _Any()
     def __getattr__(self, n):
@@ -129,9 +141,59 @@ def __getattr__(n):
     if n.startswith("__"): raise AttributeError(n)
     return _Any()
 '''
-    for name in ("sounddevice.py", "uniplot.py", "soundfile.py", os.path.join("matplotlib", "__init__.py"), os.path.join("matplotlib", "pyplot.py")):
-        open(os.path.join(folder, name), "w").write(permissive)
+
+
+DIGIT_ORDER = tuple(w for w in MODEL_ORDER if w != "S")
+
+
+def seed_all_models(golden) -> None:
+    """Every model folder the scripts load, under ./.cache of the current directory: the 12-model sets of the silence-aware
+    drivers and ``big_model`` = the 11 digit models (project3_predict_simple.py:42, project4_2digits.py:24,
+    project5_test_1digit.py:66, project5_test_ndigits_no_sil.py:58)."""
+    write_seed_models(".cache/big_model_speech_only_3", golden)
+    write_seed_models(".cache/big_model_speech_only", golden)
+    write_seed_models(".cache/big_model", golden, DIGIT_ORDER)
+
+
+def write_env_stubs(folder: str) -> str:
+    """What BOTH arms get on PYTHONPATH next to the package under test (test infrastructure, no arithmetic): a
+    ``sitecustomize`` that seeds Python's global RNG -- project4_2digits.py draws its ten digit pairs with an unseeded
+    ``random.sample`` -- and a permissive ``matplotlib`` for the plot calls (absent from this image)."""
+    os.makedirs(os.path.join(folder, "matplotlib"), exist_ok=True)
+    open(os.path.join(folder, "sitecustomize.py"), "w").write("import random\nrandom.seed(304)\n")
+    for name in (os.path.join("matplotlib", "__init__.py"), os.path.join("matplotlib", "pyplot.py")):
+        open(os.path.join(folder, name), "w").write(_PERMISSIVE)
     return folder
+
+
+def second_workspace(ws: str, name: str = "ws_train") -> str:
+    """A sibling working directory sharing the corpus (symlink) with its own ./.cache and ./plots: project5_train_no_empty.py
+    WRITES .cache/big_model_speech_only, which project6_train.py reads as its seed."""
+    ws2 = os.path.join(ws, name)
+    os.makedirs(os.path.join(ws2, "plots"), exist_ok=True)
+    link = os.path.join(ws2, "ConvertedTIDigits")
+    if not os.path.exists(link):
+        os.symlink(os.path.join(ws, "ConvertedTIDigits"), link)
+    return ws2
+
+
+def log_size(cwd: str) -> int:
+    p = os.path.join(cwd, "runtime.log")
+    return os.path.getsize(p) if os.path.exists(p) else 0
+
+
+def logged_predictions(cwd: str, start: int):
+    """(ground truth, prediction) pairs project4_2digits.py logs (scripts/project4_2digits.py:33), from byte ``start`` of
+    ./runtime.log on."""
+    import re
+    with open(os.path.join(cwd, "runtime.log")) as f:
+        f.seek(start)
+        return [[gt, pred] for pred, gt in re.findall(r"Predict labels: (\S*), ground truth: (\S+)", f.read())]
+
+
+def stdout_record(stdout: str):
+    """The result lines the drivers print: accuracies and the penalty of a sweep step."""
+    return [l for l in stdout.splitlines() if l.startswith(("In total", "Accuracy of", "For Log Transition"))]
 
 
 def run_script(name: str, cwd: str, pythonpath, timeout: int = 3000, extra_env=None) -> subprocess.CompletedProcess:

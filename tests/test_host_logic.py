@@ -29,19 +29,25 @@ def test_public_names_and_out_of_scope():
 
 
 def test_spawn_start_method_and_reference_fallback(tmp_path):
-    """Importing the package leaves the process-wide start method alone; it is switched to "spawn" only when this
-    process creates its CUDA engine (CUDA does not survive fork) and only if the application has not chosen one.
+    """Importing the package leaves the process-wide start method alone; it is switched to "forkserver" (torch and the
+    package preloaded into the server; LOE_B200_START_METHOD=spawn for plain spawn) only when this process creates its
+    CUDA engine (CUDA does not survive fork) and only if the application has not chosen one.
     Out-of-scope host modules can be borrowed from a reference checkout."""
     pkg = os.path.join(ROOT, "cs-304-speech-recognition-code_b200")
     code = ("import sys; sys.path.insert(0, %r); import multiprocessing, loe_speech_recognition as L; "
             "print(multiprocessing.get_start_method(allow_none=True)); "
             "from loe_speech_recognition import _engine; _engine._prefer_spawn(); "
             "print(multiprocessing.get_start_method(allow_none=True))" % pkg)
-    assert subprocess.check_output([sys.executable, "-c", code], text=True).split() == ["None", "spawn"]
+    assert subprocess.check_output([sys.executable, "-c", code], text=True).split() == ["None", "forkserver"]
+    env = dict(os.environ, LOE_B200_START_METHOD="spawn")
+    assert subprocess.check_output([sys.executable, "-c", code], text=True, env=env).split() == ["None", "spawn"]
     env = dict(os.environ, LOE_B200_KEEP_START_METHOD="1")
     assert subprocess.check_output([sys.executable, "-c", code], text=True, env=env).split() == ["None", "None"]
-    code_fs = code.replace("import multiprocessing, loe", "import multiprocessing; multiprocessing.set_start_method('forkserver'); import loe")
-    assert subprocess.check_output([sys.executable, "-c", code_fs], text=True).split() == ["forkserver", "forkserver"]
+    # an implicitly latched "fork" (tqdm's multiprocessing lock, scripts/project3_predict_simple.py:15) is replaced too
+    code_fork = code.replace("import multiprocessing, loe", "import multiprocessing; multiprocessing.get_context(); import loe")
+    assert subprocess.check_output([sys.executable, "-c", code_fork], text=True).split() == ["fork", "forkserver"]
+    code_fs = code.replace("import multiprocessing, loe", "import multiprocessing; multiprocessing.set_start_method('spawn'); import loe")
+    assert subprocess.check_output([sys.executable, "-c", code_fs], text=True).split() == ["spawn", "spawn"]
     ref = "/root/reference/src/loe_speech_recognition"
     if os.path.isdir(ref):
         # the reference's segmentation.py needs sounddevice at import: borrow it with a stub of that module
