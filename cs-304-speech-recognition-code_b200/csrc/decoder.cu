@@ -551,6 +551,32 @@ extern "C" int loe_decoder_stats(void* dec, double* out, int n) {
     return LOE_OK;
 }
 
+// Content fingerprint of a model's host arrays (the pack cache of the Python layer asks "were these edited in place?"
+// before every single-utterance call): four independent multiply-xor lanes over the 8-byte words of every block, tail
+// bytes folded in last.  Host only, no CUDA call.
+extern "C" uint64_t loe_host_fingerprint(const void* const* blocks, const int64_t* n_bytes, int n_blocks) {
+    const uint64_t k = 0x9E3779B97F4A7C15ull;
+    uint64_t h[4] = {0x243F6A8885A308D3ull, 0x13198A2E03707344ull, 0xA4093822299F31D0ull, 0x082EFA98EC4E6C89ull};
+    for (int b = 0; b < n_blocks; ++b) {
+        const unsigned char* p = static_cast<const unsigned char*>(blocks[b]);
+        const int64_t n = n_bytes[b];
+        if (!p || n <= 0) { h[0] = (h[0] ^ (uint64_t)(n + 1)) * k; continue; }
+        int64_t i = 0;
+        for (; i + 32 <= n; i += 32) {
+            uint64_t w[4];
+            memcpy(w, p + i, 32);
+            for (int l = 0; l < 4; ++l) { h[l] = (h[l] ^ w[l]) * k; h[l] ^= h[l] >> 29; }
+        }
+        uint64_t tail[4] = {0, 0, 0, 0};
+        memcpy(tail, p + i, (size_t)(n - i));
+        for (int l = 0; l < 4; ++l) h[l] = (h[l] ^ tail[l]) * k;
+        h[0] = (h[0] ^ (uint64_t)n) * k;
+    }
+    uint64_t r = 0;
+    for (int l = 0; l < 4; ++l) { r = (r ^ h[l]) * k; r ^= r >> 32; }
+    return r;
+}
+
 extern "C" int loe_host_alloc(void** ptr_out, size_t bytes) {
     using namespace loe;
     if (!ptr_out) { set_error("ptr_out is NULL"); return LOE_ERR_VALUE; }

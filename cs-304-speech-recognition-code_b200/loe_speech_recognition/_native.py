@@ -83,6 +83,7 @@ SIGNATURES = {
     "loe_decoder_stats": (c_int, [c_void_p, c_void_p, c_int]),
     "loe_host_alloc": (c_int, [c_void_p, ctypes.c_size_t]),
     "loe_host_free": (c_int, [c_void_p]),
+    "loe_host_fingerprint": (ctypes.c_uint64, [c_void_p, c_void_p, c_int]),
 }
 
 

@@ -73,7 +73,7 @@ class MultivariateNormal:
 class _PackCache:
     """Mixin: drops device handles when pickled (ProcessPoolExecutor ships models to workers)."""
 
-    _PACK_ATTRS = ("_pack_cache", "_native_decoder")
+    _PACK_ATTRS = ("_pack_cache", "_native_decoder", "_fingerprint")
 
     def __getstate__(self):
         state = dict(self.__dict__)
@@ -89,17 +89,56 @@ class _PackCache:
         return cache[1]
 
 
-def _model_key(normals, ltp):
-    """Identity of a model for the device-pack cache: object ids plus a content fingerprint (CRC of the means,
-    the whitening matrices and the transition table), so that in-place edits and recycled addresses are seen."""
-    crc = 0
-    for n in normals:
-        crc = zlib.crc32(np.ascontiguousarray(n._core.mean).view(np.uint8), crc)
-        crc = zlib.crc32(np.ascontiguousarray(n._core.cov_object._LP).view(np.uint8), crc)
-    if ltp._core:
-        crc = zlib.crc32(np.fromiter(ltp._core.values(), dtype=np.float64, count=len(ltp._core)).view(np.uint8), crc)
-        crc = zlib.crc32(np.array(list(ltp._core.keys()), dtype=np.int32).view(np.uint8), crc)
-    return (id(normals), len(normals), id(ltp), len(ltp._core), id(ltp._core), crc)
+class _Fingerprint:
+    """Content fingerprint of a model's Gaussians for the device-pack cache, cheap enough to take before every
+    single-utterance call (the reference re-reads its objects on every predict, so an in-place edit must be seen).
+    The arrays of the scipy objects are referenced here (kept alive: their addresses stay valid) together with a pointer
+    table, and one C call (loe_host_fingerprint, host code) hashes them all; per call the Python side only checks that
+    every object still holds the SAME array.  Arrays that are not contiguous in memory are hashed through zlib."""
+
+    __slots__ = ("arrays", "ptrs", "sizes", "odd")
+
+    def __init__(self, normals):
+        import ctypes
+        self.arrays = [a for n in normals for a in (n._core.mean, n._core.cov_object._LP)]
+        flat = [a for a in self.arrays if a.flags.forc]           # scipy's whitening matrices are Fortran-ordered
+        self.odd = [a for a in self.arrays if not a.flags.forc]
+        self.ptrs = (ctypes.c_void_p * max(len(flat), 1))(*[a.ctypes.data for a in flat])
+        self.sizes = (ctypes.c_int64 * max(len(flat), 1))(*[a.nbytes for a in flat])
+
+    def same_objects(self, normals) -> bool:
+        arrays = self.arrays
+        if 2 * len(normals) != len(arrays):
+            return False
+        i = 0
+        for n in normals:
+            core = n._core
+            if core.mean is not arrays[i] or core.cov_object._LP is not arrays[i + 1]:
+                return False
+            i += 2
+        return True
+
+    def value(self) -> int:
+        from . import _native
+        n = len(self.arrays) - len(self.odd)
+        h = int(_native.load().loe_host_fingerprint(self.ptrs, self.sizes, n))
+        for a in self.odd:
+            h = zlib.crc32(np.ascontiguousarray(a).view(np.uint8), h & 0xFFFFFFFF) | (h & ~0xFFFFFFFF)
+        return h
+
+
+def _model_key(normals, ltp, holder=None):
+    """Identity of a model for the device-pack cache: object ids plus a content fingerprint (of the means, the
+    whitening matrices and the transition table), so that in-place edits and recycled addresses are seen.  ``holder``
+    (the model's __dict__) keeps the _Fingerprint between calls."""
+    fp = holder.get("_fingerprint") if holder is not None else None
+    if fp is None or not fp.same_objects(normals):
+        fp = _Fingerprint(normals)
+        if holder is not None:
+            holder["_fingerprint"] = fp
+    core = ltp._core
+    trans = (hash(tuple(core)), hash(np.fromiter(core.values(), dtype=np.float64, count=len(core)).tobytes())) if core else (0, 0)
+    return (id(normals), len(normals), id(ltp), len(core), id(core), fp.value()) + trans
 
 
 @dataclass
@@ -132,7 +171,7 @@ class HiddenMarkovModel(_PackCache):
         def build():
             eng = _engine()
             return eng.pack_gaussians(self._multivariate_normals), eng.pack_trellises([self._host_trellis()])
-        return self._cached(_model_key(self._multivariate_normals, self._log_transition_probs), build)
+        return self._cached(_model_key(self._multivariate_normals, self._log_transition_probs, self.__dict__), build)
 
     def predict(self, signal: NDArray[np.float32]) -> Tuple[float, NDArray[np.int8]]:
         assert len(self._multivariate_normals) > 0
@@ -774,11 +813,13 @@ class HiddenMarkovModelInference(_PackCache):
             blocks = [dense[a:a + n, a:a + n] for a, n in zip(lows, sizes)]
             tr = _trellis.build(blocks, lows, list(range(len(sizes))), "loop")
             return eng.pack_gaussians(self._multivariate_normals), eng.pack_trellises([tr])
-        return self._cached(_model_key(self._multivariate_normals, self._log_transition_probs), build)
+        return self._cached(_model_key(self._multivariate_normals, self._log_transition_probs, self.__dict__), build)
 
     def predict(self, signal: NDArray[np.float32]) -> str:
-        score, path = self._viterbi(observation_sequence=signal)
-        return "".join(self._model_boundaries.get_labels(path))
+        """hidden_markov_model.py:458-461.  The word sequence is decoded by the Viterbi launch itself (fused labels); the
+        host label routine only sees what the device table cannot hold (T == 1, more than 32 words) and raises there
+        exactly like the reference."""
+        return self.predict_batch([signal])[0]
 
     def _viterbi(self, observation_sequence: NDArray[np.float32]) -> Tuple[float, NDArray[np.int8]]:
         scores, paths = self.viterbi_batch([observation_sequence])
@@ -924,7 +965,7 @@ class HiddenMarkovModelInference(_PackCache):
             blocks = [dense[a:a + n, a:a + n] for a, n in zip(lows, sizes)]
             tr = _trellis.build(blocks, lows, list(range(len(sizes))), "loop")
             return NativeDecoder(*host_gauss_arrays(self._multivariate_normals), tr, sample_rate, device)
-        key = ("native", float(sample_rate), int(device)) + tuple(_model_key(self._multivariate_normals, self._log_transition_probs))
+        key = ("native", float(sample_rate), int(device)) + tuple(_model_key(self._multivariate_normals, self._log_transition_probs, self.__dict__))
         return self._cached(key, build, slot="_native_decoder")
 
     def decode_pcm_host(self, pcm_flat, sample_offsets, sample_rate: float = 16000, n_chunks: int = 0,

@@ -462,6 +462,12 @@ double loe_decoder_narrow_rate(void* decoder);
 int loe_host_alloc(void** ptr_out, size_t bytes);
 int loe_host_free(void* ptr);
 
+/* 64-bit content fingerprint of n_blocks host memory blocks (no CUDA call).  The Python layer keeps the device copy of a
+ * model next to the reference's own objects (scipy frozen distributions + the dict-backed transition table,
+ * hidden_markov_model.py:20-48, transition_probability.py:11-40) and asks before every single-utterance call whether they
+ * were edited in place: the reference reads them afresh on every predict (hidden_markov_model.py:481-531). */
+uint64_t loe_host_fingerprint(const void* const* blocks, const int64_t* n_bytes, int n_blocks);
+
 #ifdef __cplusplus
 }
 #endif

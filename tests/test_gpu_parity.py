@@ -469,6 +469,34 @@ def test_loop_decode_strings(eng, golden, name):
     assert inf.predict(feats[0]) == want[0]
 
 
+def test_in_place_model_edits_reach_the_device(eng, golden):
+    """The reference reads its model objects afresh on every predict (hidden_markov_model.py:481-531); the drop-in keeps a
+    device copy, so an edit IN PLACE -- an entry of the transition dict, a mean inside a frozen scipy object -- must be
+    seen by the next call (content fingerprint of the pack cache)."""
+    def model():
+        m = _loop_inference(golden)
+        m._log_transition_probability_between_words = -100
+        return m
+    inf, fresh = model(), model()
+    x = golden["loop_feat_0"]
+    s0, p0 = inf._viterbi(x)
+    assert inf._viterbi(x)[0] == s0
+    st = int(p0[len(p0) // 4])                                   # a state the best path stays in: its self-loop is used
+    assert p0[len(p0) // 4 + 1] == st or p0[len(p0) // 4 - 1] == st
+    inf._log_transition_probs[(st, st)] = np.float32(inf._log_transition_probs[(st, st)] - 5.0)
+    s1, _ = inf._viterbi(x)
+    fresh._log_transition_probs[(st, st)] = np.float32(fresh._log_transition_probs[(st, st)] - 5.0)   # before its first pack
+    assert s1 != s0 and s1 == fresh._viterbi(x)[0]
+    mid = int(p0[len(p0) // 2])
+    inf._multivariate_normals[mid]._core.mean[:] += 3.0
+    s2, _ = inf._viterbi(x)
+    fresh = model()
+    fresh._log_transition_probs[(st, st)] = np.float32(fresh._log_transition_probs[(st, st)] - 5.0)
+    fresh._multivariate_normals[mid]._core.mean[:] += 3.0
+    assert s2 != s1 and s2 == fresh._viterbi(x)[0]
+    assert inf.predict(x) == fresh.predict(x)
+
+
 def test_edge_cases_short_utterances(eng, golden):
     """T = 2, 3, 9 (unreachable end states: -inf scores, back-pointer 0) and T = 1 (path [-1])."""
     inf = _loop_inference(golden)

@@ -381,3 +381,46 @@ def test_mel_lane_tables_exact_and_bank_conflict_free():
             assert got[0] <= 44 and got[1] <= 26 and sum(got) * 2 <= sum(nat), (got, nat)
             assert all(B[0][m] <= first[m] and B[0][m] + na > last[m] for m in range(32))
             assert all(B[na][4 * q] <= first[32 + q] and B[na][4 * q] + 4 * nb > last[32 + q] for q in range(8))
+
+
+def test_model_key_sees_in_place_edits(built_lib):
+    """The device-pack cache key (taken before every single-utterance call) changes when a mean, a whitening matrix or the
+    transition table is edited IN PLACE, when an array object is replaced, and is stable otherwise; the fingerprint state
+    is never pickled.  Host code only (loe_host_fingerprint)."""
+    import pickle
+    import time
+    from loe_speech_recognition.hidden_markov_model import HiddenMarkovModel, HiddenMarkovModelTrainable, _model_key
+    from loe_speech_recognition.transition_probability import LogTransitionProbabilities
+    rng = np.random.default_rng(3)
+    S, D = 58, 39
+    means = rng.normal(size=(S, D)).astype(np.float32)
+    a = rng.normal(size=(S, D, D))
+    covs = (a @ a.transpose(0, 2, 1) / D + np.eye(D)).astype(np.float32)
+    m = HiddenMarkovModel("x")
+    m._multivariate_normals = HiddenMarkovModelTrainable.get_multivariate_normals(means, covs)
+    m._log_transition_probs = LogTransitionProbabilities.from_dense(np.log(np.full((S, S), 1.0 / S, np.float32)))
+    key = lambda: _model_key(m._multivariate_normals, m._log_transition_probs, m.__dict__)
+    k0 = key()
+    assert key() == k0
+    t0 = time.perf_counter()
+    for _ in range(50):
+        key()
+    per_call = (time.perf_counter() - t0) / 50
+    print(f"_model_key: {per_call * 1e6:.0f} us per call for {S} Gaussians + {S * S} transitions")
+    m._multivariate_normals[17]._core.mean[5] += 1e-9                     # a mean, in place
+    k1 = key()
+    assert k1 != k0
+    m._multivariate_normals[40]._core.cov_object._LP[38, 38] *= 1.0000001    # a whitening matrix, last element
+    k2 = key()
+    assert k2 != k1
+    m._log_transition_probs[(3, 4)] = np.float32(-7.0)                     # the dict-backed table
+    k3 = key()
+    assert k3 != k2
+    core = m._multivariate_normals[2]._core
+    core.mean = core.mean.copy()                                           # same content, another array object: no change
+    assert key() == k3
+    core.mean = core.mean + 1.0
+    assert key() != k3
+    clone = pickle.loads(pickle.dumps(m))
+    assert "_fingerprint" not in clone.__dict__ and "_fingerprint" in m.__dict__
+    assert _model_key(clone._multivariate_normals, clone._log_transition_probs, clone.__dict__)[5:] == key()[5:]
