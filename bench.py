@@ -589,14 +589,15 @@ def impl_b200(args):
     if precision == "h16":
         # what the tensor pipe is actually issued: 8 MMAs of K = 16 per 128-frame tile and 6-state column tile (3-way
         # operand split, 15 chunk products paired into 8), each over the 48 (c + 1) columns its K chunk can reach in the
-        # lower-triangular image: N = 240 + 240 + 192 + 192 + 144 + 96 + 96 + 48 = 1248 of the dense 8 x 240
+        # lower-triangular image, products of (nearly) equal width sharing an MMA: N = 240 + 240 + 192 + 144 + 144 + 96 + 48 + 48
+        # = 1152 of the dense 8 x 240
         n_tiles = (58 + 5) // 6
-        issued = n_tiles * 1248 * 16 * 2 * F
+        issued = n_tiles * 1152 * 16 * 2 * F
         sustained = peaks.get("bf16_tflops_sustained") or bf16
         note = {"issued_tflops": issued / (stage_ms["emission"] * 1e-3) / 1e12, "sustained_bf16_tflops": sustained,
                 "issued_over_useful": issued / (FLOPS_PER_FRAME * F),
                 "note": "the kernel runs power-capped (ncu: 1.6 GHz SM clock); `achieved` counts the useful flops once, the "
-                        "tensor pipe is issued 2.2x that (3-way operand split, triangular image at 65 % of dense, padding)"}
+                        "tensor pipe is issued 2.04x that (3-way operand split, triangular image at 60 % of dense, padding)"}
         all_roof["emission_h16_img_kernel"]["issued"] = note
         if dominant == "emission_h16_img_kernel":
             roofline["issued"] = note

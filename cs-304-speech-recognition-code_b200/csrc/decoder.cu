@@ -552,28 +552,54 @@ extern "C" int loe_decoder_stats(void* dec, double* out, int n) {
 }
 
 // Content fingerprint of a model's host arrays (the pack cache of the Python layer asks "were these edited in place?"
-// before every single-utterance call): four independent multiply-xor lanes over the 8-byte words of every block, tail
-// bytes folded in last.  Host only, no CUDA call.
+// before every single-utterance call).  Every 8-byte word goes through h = rotl(h ^ w, 23) + k in one of 16 lanes (AVX2:
+// four 256-bit accumulators) -- a bijection of the lane for a given word and of the word for a given lane, so a change of
+// any single word always changes the result; tail bytes and block lengths are folded in with multiply-xor steps.  Host
+// only, no CUDA call.
+namespace loe {
+static inline uint64_t fp_mix(uint64_t h, uint64_t w) {
+    h ^= w;
+    return ((h << 23) | (h >> 41)) + 0x9E3779B97F4A7C15ull;
+}
+static void fp_words_scalar(uint64_t* h, const unsigned char* p, int64_t n_chunks) {       // chunks of 128 bytes
+    for (int64_t c = 0; c < n_chunks; ++c, p += 128) {
+        uint64_t w[16];
+        memcpy(w, p, 128);
+        for (int l = 0; l < 16; ++l) h[l] = fp_mix(h[l], w[l]);
+    }
+}
+__attribute__((target("avx2"))) static void fp_words_avx2(uint64_t* h, const unsigned char* p, int64_t n_chunks) {
+    __m256i a[4];
+    for (int v = 0; v < 4; ++v) a[v] = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(h + 4 * v));
+    const __m256i k = _mm256_set1_epi64x((long long)0x9E3779B97F4A7C15ull);
+    for (int64_t c = 0; c < n_chunks; ++c, p += 128)
+        for (int v = 0; v < 4; ++v) {
+            const __m256i x = _mm256_xor_si256(a[v], _mm256_loadu_si256(reinterpret_cast<const __m256i*>(p + 32 * v)));
+            a[v] = _mm256_add_epi64(_mm256_or_si256(_mm256_slli_epi64(x, 23), _mm256_srli_epi64(x, 41)), k);
+        }
+    for (int v = 0; v < 4; ++v) _mm256_storeu_si256(reinterpret_cast<__m256i*>(h + 4 * v), a[v]);
+}
+}  // namespace loe
+
 extern "C" uint64_t loe_host_fingerprint(const void* const* blocks, const int64_t* n_bytes, int n_blocks) {
+    using namespace loe;
+    static const bool avx2 = __builtin_cpu_supports("avx2");
     const uint64_t k = 0x9E3779B97F4A7C15ull;
-    uint64_t h[4] = {0x243F6A8885A308D3ull, 0x13198A2E03707344ull, 0xA4093822299F31D0ull, 0x082EFA98EC4E6C89ull};
+    uint64_t h[16];
+    for (int l = 0; l < 16; ++l) h[l] = 0x243F6A8885A308D3ull * (uint64_t)(2 * l + 1);
     for (int b = 0; b < n_blocks; ++b) {
         const unsigned char* p = static_cast<const unsigned char*>(blocks[b]);
         const int64_t n = n_bytes[b];
         if (!p || n <= 0) { h[0] = (h[0] ^ (uint64_t)(n + 1)) * k; continue; }
-        int64_t i = 0;
-        for (; i + 32 <= n; i += 32) {
-            uint64_t w[4];
-            memcpy(w, p + i, 32);
-            for (int l = 0; l < 4; ++l) { h[l] = (h[l] ^ w[l]) * k; h[l] ^= h[l] >> 29; }
-        }
-        uint64_t tail[4] = {0, 0, 0, 0};
-        memcpy(tail, p + i, (size_t)(n - i));
-        for (int l = 0; l < 4; ++l) h[l] = (h[l] ^ tail[l]) * k;
-        h[0] = (h[0] ^ (uint64_t)n) * k;
+        const int64_t chunks = n / 128;
+        if (avx2) fp_words_avx2(h, p, chunks); else fp_words_scalar(h, p, chunks);
+        uint64_t tail[16] = {0};
+        memcpy(tail, p + chunks * 128, (size_t)(n - chunks * 128));
+        for (int l = 0; l < 16; ++l) h[l] = fp_mix(h[l], tail[l]);
+        h[b & 15] = (h[b & 15] ^ (uint64_t)n) * k;
     }
     uint64_t r = 0;
-    for (int l = 0; l < 4; ++l) { r = (r ^ h[l]) * k; r ^= r >> 32; }
+    for (int l = 0; l < 16; ++l) { r = (r ^ h[l]) * k; r ^= r >> 32; }
     return r;
 }
 

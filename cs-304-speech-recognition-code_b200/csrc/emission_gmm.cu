@@ -270,7 +270,10 @@ emission_gmm_tc_kernel(const float* __restrict__ feat, int64_t n_frames, const u
         }
     } else if (warp == (kProducerThreads + kEpilogueThreads) / 32) {
         // =========================== MMA issuer ===========================
-        if (lane == 0) {
+        // whole warp in step, instructions predicated on one elected lane inside the asm: operands in uniform registers
+        // (see emission_h16.cu)
+        {
+            const uint32_t leader = elect_one();
             // c_format F32 (bit 4), a/b format F16 (0), N >> 3 at bit 17, M >> 4 at bit 24
             const uint32_t idesc = (1u << 4) | ((uint32_t)(n_cols >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
             const uint32_t b_base = smem_u32(sm.b);
@@ -289,10 +292,10 @@ emission_gmm_tc_kernel(const float* __restrict__ feat, int64_t n_frames, const u
                     const uint32_t b = b_base + ((pass == 2) ? kChunksPerPart * kBLbo : 0);
 #pragma unroll
                     for (int ks = 0; ks < kChunksPerPart / 2; ++ks)
-                        mma_f16(d, make_desc(a + ks * 2 * kALbo, kALbo), make_desc(b + ks * 2 * kBLbo, kBLbo), idesc, (pass | ks) ? 1u : 0u);
+                        mma_f16_elected(leader, d, make_desc(a + ks * 2 * kALbo, kALbo), make_desc(b + ks * 2 * kBLbo, kBLbo), idesc, (pass | ks) ? 1u : 0u);
                 }
-                mma_commit(&sm.a_empty[s]);
-                mma_commit(&sm.tmem_full[s]);
+                mma_commit_elected(leader, &sm.a_empty[s]);
+                mma_commit_elected(leader, &sm.tmem_full[s]);
             }
         }
     } else {

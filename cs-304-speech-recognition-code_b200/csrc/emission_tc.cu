@@ -166,7 +166,10 @@ emission_tc_kernel(const float* __restrict__ feat, int64_t n_frames, const float
         }
     } else if (warp == (kProducerThreads + kEpilogueThreads) / 32) {
         // =========================== MMA issuer ===========================
-        if (lane == 0) {
+        // whole warp in step, instructions predicated on one elected lane inside the asm: operands in uniform registers
+        // (see emission_h16.cu)
+        {
+            const uint32_t leader = elect_one();
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n_cols >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
             const uint32_t b_hi = smem_u32(sm.b_hi), b_lo = smem_u32(sm.b_lo);
             int it = 0;
@@ -184,11 +187,11 @@ emission_tc_kernel(const float* __restrict__ feat, int64_t n_frames, const float
                     const uint32_t b = (pass == 2) ? b_lo : b_hi;
 #pragma unroll
                     for (int ks = 0; ks < kKSteps; ++ks)
-                        mma_tf32(d, make_desc(a + ks * 2 * kALbo, kALbo), make_desc(b + ks * 2 * kBLbo, kBLbo), idesc,
+                        mma_tf32_elected(leader, d, make_desc(a + ks * 2 * kALbo, kALbo), make_desc(b + ks * 2 * kBLbo, kBLbo), idesc,
                                  (pass | ks) ? 1u : 0u);
                 }
-                mma_commit(&sm.a_empty[s]);
-                mma_commit(&sm.tmem_full[s]);
+                mma_commit_elected(leader, &sm.a_empty[s]);
+                mma_commit_elected(leader, &sm.tmem_full[s]);
             }
         }
     } else {

@@ -99,6 +99,47 @@ __device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64
         "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
 }
 
+// Whole-warp forms: every lane executes the asm, the instruction itself is predicated on ``leader`` (elect_one() of the
+// converged warp), so the C++ control flow around it stays uniform and the operands can sit in uniform registers.
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t is_leader;
+    asm volatile(
+        "{\n"
+        ".reg .pred e;\n"
+        "elect.sync _|e, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, e;\n"
+        "}\n" : "=r"(is_leader));
+    return is_leader;
+}
+__device__ __forceinline__ void mma_f16_elected(uint32_t leader, uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "setp.ne.b32 q, %5, 0;\n"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(leader) : "memory");
+}
+__device__ __forceinline__ void mma_tf32_elected(uint32_t leader, uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "setp.ne.b32 q, %5, 0;\n"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(leader) : "memory");
+}
+__device__ __forceinline__ void mma_commit_elected(uint32_t leader, uint64_t* bar) {
+    asm volatile(
+        "{\n"
+        ".reg .pred q;\n"
+        "setp.ne.b32 q, %1, 0;\n"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(leader) : "memory");
+}
+
 // Host: divide the SMs over the state tiles (6 states = 240 accumulator columns, 128-frame M tiles) in
 // proportion to their MMA cost; the last tile may be narrower and gets fewer CTAs.
 inline void split_sms(int n_states, int64_t n_frames, int sms, int* g_full_out, int* g_last_out) {

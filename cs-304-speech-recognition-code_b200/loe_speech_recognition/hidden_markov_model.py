@@ -127,6 +127,14 @@ class _Fingerprint:
         return h
 
 
+def _transitions_hash(ltp):
+    """(hash of the keys, hash of the values) of a dict-backed transition table."""
+    core = ltp._core
+    if not core:
+        return (0, 0)
+    return (hash(tuple(core)), hash(np.fromiter(core.values(), dtype=np.float64, count=len(core)).tobytes()))
+
+
 def _model_key(normals, ltp, holder=None):
     """Identity of a model for the device-pack cache: object ids plus a content fingerprint (of the means, the
     whitening matrices and the transition table), so that in-place edits and recycled addresses are seen.  ``holder``
@@ -136,9 +144,7 @@ def _model_key(normals, ltp, holder=None):
         fp = _Fingerprint(normals)
         if holder is not None:
             holder["_fingerprint"] = fp
-    core = ltp._core
-    trans = (hash(tuple(core)), hash(np.fromiter(core.values(), dtype=np.float64, count=len(core)).tobytes())) if core else (0, 0)
-    return (id(normals), len(normals), id(ltp), len(core), id(core), fp.value()) + trans
+    return (id(normals), len(normals), id(ltp), len(ltp._core), id(ltp._core), fp.value()) + _transitions_hash(ltp)
 
 
 @dataclass

@@ -9,13 +9,14 @@ from __future__ import annotations
 from dataclasses import dataclass, field
 from typing import List, Optional, Self, Sequence
 
+import itertools
 import os
 
 import numpy as np
 from numpy.typing import NDArray
 
 from . import _trellis
-from .hidden_markov_model import HiddenMarkovModel, _PackCache
+from .hidden_markov_model import HiddenMarkovModel, _Fingerprint, _PackCache
 from .ti_digits import TI_DIGITS_LABELS
 
 
@@ -35,7 +36,16 @@ class ModelCollection(_PackCache):
             tr = _trellis.build([m._log_transition_probs.to_dense() for m in self._models], cols,
                                 list(range(len(sizes))), "multi")
             return eng.pack_gaussians(normals), eng.pack_trellises([tr])
-        key = tuple((id(m), id(m._multivariate_normals), id(m._log_transition_probs)) for m in self._models)
+        # object ids + content (in-place edits of a word model are seen, like HiddenMarkovModel._packs): ONE fingerprint
+        # over the Gaussians of all word models, the transition tables hashed per model
+        normals = [mn for m in self._models for mn in m._multivariate_normals]
+        fp = self.__dict__.get("_fingerprint")
+        if fp is None or not fp.same_objects(normals):
+            fp = self.__dict__["_fingerprint"] = _Fingerprint(normals)
+        tables = [m._log_transition_probs._core for m in self._models]
+        values = np.fromiter(itertools.chain.from_iterable(t.values() for t in tables), dtype=np.float64)
+        key = (fp.value(), hash(values.tobytes()), tuple(hash(tuple(t)) for t in tables),
+               tuple((id(m), id(m._multivariate_normals), id(m._log_transition_probs)) for m in self._models))
         return self._cached(key, build)
 
     def scores_batch(self, signals: Sequence[NDArray[np.float32]], precision: Optional[str] = None) -> NDArray[np.float32]:
