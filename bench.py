@@ -644,6 +644,31 @@ def impl_b200(args):
         "roofline_all": all_roof,
         "stage_ms": stage_ms,
     }
+    if rank == 0:
+        # the reference's own API is one utterance per call (scripts/project5_test_*.py map predict over utterances): host
+        # wall clock per call through the drop-in, features / PCM in host memory, result back on the host
+        import time as _time
+        from loe_speech_recognition import ModelCollection
+
+        def per_call(fn, n_calls=100):
+            for _ in range(5):
+                fn()
+            t0 = _time.perf_counter()
+            for _ in range(n_calls):
+                fn()
+            return (_time.perf_counter() - t0) / n_calls * 1e6
+        x7 = MFCC.batch(utts[:1], 16000)[0]
+        mc = ModelCollection()
+        mc._models = [m for m in models if m.label != "S"]
+        x1 = np.ascontiguousarray(x7[:80])
+        line["api_latency_us"] = {
+            "MFCC(signal).feature_vector": per_call(lambda: MFCC(utts[0], 16000).feature_vector),
+            "HiddenMarkovModelInference.predict": per_call(lambda: inf.predict(x7)),
+            "ModelCollection.predict": per_call(lambda: mc.predict(x1)),
+            "HiddenMarkovModel.predict": per_call(lambda: models[0].predict(x1)),
+            "frames": {"string": int(x7.shape[0]), "word": int(x1.shape[0])},
+            "note": "host wall clock per single-utterance call of the reference's API (mean of 100 calls, one utterance "
+                    "in flight: latency, not throughput); the reference takes ~1 s for the same predict (cpu_baseline)"}
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         n_sample = max(2, min(2 * cores, 64))

@@ -237,7 +237,7 @@ def test_emission_h16_pairing_table():
     want = [(pa, pb, c) for c in range(5) for pa, pb in (("hi", "hi"), ("lo", "hi"), ("hi", "lo"))]
     assert sorted(products) == sorted(want)                 # hi*hi + lo*hi + hi*lo of every chunk, once each
     assert rows[0][4] == 5                                  # the first MMA (accumulate = 0) overwrites all 240 columns
-    assert sum(r[4] for r in rows) * 48 == 1248             # 65 % of the dense 8 x 240
+    assert sum(r[4] for r in rows) * 48 == 1152             # 60 % of the dense 8 x 240 (products paired by width)
 
 
 def _stockham_real_power(x, N):
