@@ -159,9 +159,6 @@ emission_h16_body(const float* __restrict__ feat, const float* __restrict__ inv2
     const int H = min(kHalves, n_tiles - sup * kHalves);                               // state tiles of this CTA
     const int n_mtiles = (int)((n_frames + kTileM - 1) / kTileM);
     auto valid_of = [&](int h) { return min(kStatesPerTile, n_states - (sup * kHalves + h) * kStatesPerTile); };
-    // 8-byte stores of score pairs need an even row pitch and an 8-byte aligned matrix (and an even number of states
-    // in the tile, else the odd last state would be lost): otherwise scalar stores
-    const bool pair_ok = ((ld_out & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 7) == 0);
 
     // ---- one-time setup: barriers, TMEM, resident B tile
     if (tid == 0) {
@@ -300,6 +297,9 @@ emission_h16_body(const float* __restrict__ feat, const float* __restrict__ inv2
         // One warp per TMEM lane quarter (thread = frame row).  The stores of a tile are deferred until the first
         // TMEM loads of the next tile have been issued.
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kEpilogueRegs));
+        // 8-byte stores of score pairs need an even row pitch and an 8-byte aligned matrix (and an even number of states
+        // in the tile, else the odd last state would be lost): otherwise scalar stores
+        const bool pair_ok = ((ld_out & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 7) == 0);
         const int q = warp & 3;                             // TMEM lane quarter this warp may touch
         const int r = q * 32 + lane;
         float2* stage = reinterpret_cast<float2*>(sm.out_stage[q]);
