@@ -603,6 +603,29 @@ extern "C" uint64_t loe_host_fingerprint(const void* const* blocks, const int64_
     return r;
 }
 
+// Word-id tables -> text (host code): utterance i contributes the single-character labels of its first count[i] word ids
+// followed by ``sep``; an utterance whose count does not fit the table (count < 0: T == 1, or count > max_words)
+// contributes ``sep`` alone -- the caller decodes those from the state path.  Returns the number of bytes written
+// (at most n_utt * (max_words + 1)).
+extern "C" int64_t loe_labels_text_host(const int8_t* words_host, const int32_t* count_host, int n_utt, int max_words,
+                                        const char* label_chars, int n_labels, char sep, char* out_host) {
+    if (!words_host || !count_host || !label_chars || !out_host || n_utt <= 0 || max_words <= 0 || n_labels <= 0) return 0;
+    char* o = out_host;
+    for (int i = 0; i < n_utt; ++i) {
+        const int c = count_host[i];
+        if (c >= 0 && c <= max_words) {
+            const int8_t* w = words_host + (size_t)i * max_words;
+            for (int k = 0; k < c; ++k) {
+                int id = w[k];
+                id = id < 0 ? 0 : id >= n_labels ? n_labels - 1 : id;
+                *o++ = label_chars[id];
+            }
+        }
+        *o++ = sep;
+    }
+    return (int64_t)(o - out_host);
+}
+
 extern "C" int loe_host_alloc(void** ptr_out, size_t bytes) {
     using namespace loe;
     if (!ptr_out) { set_error("ptr_out is NULL"); return LOE_ERR_VALUE; }

@@ -84,6 +84,7 @@ SIGNATURES = {
     "loe_host_alloc": (c_int, [c_void_p, ctypes.c_size_t]),
     "loe_host_free": (c_int, [c_void_p]),
     "loe_host_fingerprint": (ctypes.c_uint64, [c_void_p, c_void_p, c_int]),
+    "loe_labels_text_host": (c_int64, [c_void_p, c_void_p, c_int, c_int, c_char_p, c_int, ctypes.c_char, c_void_p]),
 }
 
 

