@@ -299,11 +299,14 @@ __global__ void reduce_kernel(const double* __restrict__ part, int n_chunks, int
 //        bucket_hist_kernel -> bucket_scan_kernel (exclusive offsets per (bucket, chunk)) -> bucket_plan_kernel (bases, work list)
 //        -> bucket_scatter_kernel (frame index lists, one contiguous list per bucket)
 //   2. accum2_kernel: one CTA per work item = up to 2048 consecutive list entries of ONE bucket.  The augmented frames
-//      y = [x - shift, 1] are gathered through the list, 4 frames per warp and step, three steps ahead of their use, and
-//      sum y y^T = Y^T Y is a contraction over the frames on the FP64 TENSOR cores: mma.sync m8n8k4 (DMMA), 15 tiles of
-//      8 x 8 on or above the diagonal of the 5 x 5 tile grid, 4 frames per instruction, all 15 accumulator tiles in the
-//      registers of every warp; 5 shared-memory loads feed 15 DMMAs (3 840 FMAs); no block barrier in the loop.  The FP64 pipe bounds this kernel (960 FMAs per frame at 64 per clock and SM); with scalar DFMAs in 8 x 8
-//      register tiles (the first version of this path) instruction issue and latency did: 15 % pipe utilisation (ncu).
+//      y = [x - shift, 1] are gathered through the list, 4 frames per warp and step, kA2Depth steps ahead of their use
+//      (and the list entries one step earlier still), and sum y y^T = Y^T Y is a contraction over the frames on the FP64
+//      TENSOR cores: mma.sync m8n8k4 (DMMA), 15 tiles of 8 x 8 on or above the diagonal of the 5 x 5 tile grid, 4 frames
+//      per instruction, all 15 accumulator tiles in the registers of every warp; every lane gathers exactly the five
+//      values that are its elements of the A and B fragments, so 5 global loads + 5 conversions feed 15 DMMAs (3 840 FMAs)
+//      with no shared memory and no barrier in the loop.  The FP64 pipe bounds this kernel (960 FMAs per frame at 64 per
+//      clock and SM: scratch/dmma_peak.cu measures 37 TFLOP/s); with scalar DFMAs in 8 x 8 register tiles (the first
+//      version of this path) instruction issue and latency did: 15 % pipe utilisation (ncu).
 //      float64 is kept because the models must come out identical whatever the number of ranks the frames are sharded
 //      over -- split-precision products on the tcgen05 pipe give 2^-21 per product, not enough for that.
 //   3. reduce2_kernel: partials of a bucket summed in work-list order.
@@ -314,8 +317,10 @@ constexpr int kSortChunk = 2048;                 // frames per histogram / scatt
 constexpr int kSortThreads = 256;
 constexpr int kSortMaxGlob = 1024;
 constexpr int kSplit = 2048;                     // list entries per work item
-constexpr int kA2Depth = 3;                      // 4-frame steps each warp has in flight (gathered into registers ahead of use)
-constexpr int kA2RowPitch = 44;                  // doubles per staged row (40 used): conflict-free fragment loads
+#ifndef LOE_A2_DEPTH
+#define LOE_A2_DEPTH 4
+#endif
+constexpr int kA2Depth = LOE_A2_DEPTH;           // 4-frame steps each warp has in flight (gathered into registers ahead of use)
 
 __global__ void __launch_bounds__(kSortThreads)
 bucket_hist_kernel(const uint16_t* __restrict__ bucket, int64_t total_frames, int n_glob, int* __restrict__ chunk_hist) {
@@ -423,52 +428,55 @@ accum2_kernel(const float* __restrict__ feat, const int* __restrict__ idx, const
     if (item >= work_range[n_glob]) return;
     const int g = work[3 * item], begin = work[3 * item + 1], end = work[3 * item + 2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // Every warp works on its own: steps of 4 frames (one DMMA K), step s of the item belongs to warp s % 8.  A step's 160
-    // raw values (4 rows x 40, 5 per lane) are gathered through the frame list kA2Depth steps ahead into registers, turned
-    // into y = [x - shift, 1] (float64) in the warp's private tile and multiplied: no block barrier in the loop, and
-    // 8 warps x kA2Depth steps of loads in flight per CTA cover the gather's HBM latency.
-    __shared__ __align__(16) double s_tile[8][4 * kA2RowPitch];        // per warp: 4 rows of 44 doubles
+    // Every warp works on its own: steps of 4 frames (one DMMA K), step s of the item belongs to warp s % 8.  With Y the
+    // 4 x 40 block of a step (rows y = [x - shift, 1]), tile (bi, bj) of Y^T Y takes A = (Y^T)[8 bi .., :] and B = Y[:, 8 bj ..],
+    // and lane l's element of BOTH fragments is Y[l & 3][8 b + (l >> 2)]: a lane needs five values of ONE frame of the step
+    // (columns (l >> 2) + 8 b), and it is the lane that loads them -- the fragments go from the gather straight into the
+    // DMMAs without passing through shared memory.  A step's loads are issued kA2Depth steps of the warp ahead of their use,
+    // and the frame-list entry they go through one step earlier still (the address of a gather never waits for the list).
     __shared__ double s_sum[40 * 41];
-    __shared__ double s_shift[40];
     double c[15][2];
 #pragma unroll
     for (int t = 0; t < 15; ++t) { c[t][0] = 0.0; c[t][1] = 0.0; }
-    if (tid < 40) s_shift[tid] = (tid < D) ? (double)shift[(size_t)g * D + tid] : 0.0;
-    __syncthreads();
+    const int row = lane & 3, col0 = lane >> 2;
+    const bool one = col0 == 7;                                // block 4 of this lane is column 39: the constant 1
+    double sh[5];
+#pragma unroll
+    for (int b = 0; b < 5; ++b) sh[b] = (col0 + 8 * b < D) ? (double)__ldg(shift + (size_t)g * D + col0 + 8 * b) : 0.0;
     const int n_steps = (end - begin + 3) >> 2;
     float pre[kA2Depth][5];
-    // element e = lane + 32 j of a step is (row e / 40, column e % 40); rows past the item's end and column 39 load nothing
-    auto prefetch = [&](int st, float* dst) {
+    int nidx[kA2Depth];
+    // frame of this lane's row in step st (-1: past the item's end)
+    auto list_entry = [&](int st) -> int {
+        const int f = begin + 4 * st + row;
+        return (st < n_steps && f < end) ? __ldg(idx + f) : -1;
+    };
+    auto gather = [&](int fi, float* dst) {
+        const float* p = feat + (size_t)max(fi, 0) * D + col0;
+        const bool on = fi >= 0;
 #pragma unroll
-        for (int j = 0; j < 5; ++j) {
-            const int e = lane + 32 * j, r = e / 40, k = e - r * 40;
-            const int f = begin + 4 * st + r;
-            dst[j] = (st < n_steps && f < end && k < D) ? __ldg(feat + (size_t)__ldg(idx + f) * D + k) : 0.f;
-        }
+        for (int b = 0; b < 4; ++b) dst[b] = on ? __ldg(p + 8 * b) : 0.f;
+        dst[4] = (on && !one) ? __ldg(p + 32) : 1.f;          // column 39 carries 1 (its shift entry is 0)
     };
 #pragma unroll
-    for (int d = 0; d < kA2Depth; ++d) prefetch(warp + 8 * d, pre[d]);
-    double* tile = s_tile[warp];
+    for (int d = 0; d < kA2Depth; ++d) nidx[d] = list_entry(warp + 8 * d);
+#pragma unroll
+    for (int d = 0; d < kA2Depth; ++d) { gather(nidx[d], pre[d]); nidx[d] = list_entry(warp + 8 * (d + kA2Depth)); }
     for (int st = warp; st < n_steps; st += 8 * kA2Depth) {
 #pragma unroll
         for (int d = 0; d < kA2Depth; ++d) {
             const int cur = st + 8 * d;
             if (cur >= n_steps) break;                                     // warp-uniform
-#pragma unroll
-            for (int j = 0; j < 5; ++j) {
-                const int e = lane + 32 * j, r = e / 40, k = e - r * 40;
-                const bool live = begin + 4 * cur + r < end;              // rows beyond the item are ZERO, also their constant 1
-                tile[r * kA2RowPitch + k] = live ? ((k < D) ? (double)pre[d][j] - s_shift[k] : 1.0) : 0.0;
-            }
-            prefetch(cur + 8 * kA2Depth, pre[d]);
-            __syncwarp();
-            // one load per 8-wide block serves as the A fragment of the tiles in that block row and as the B fragment of
-            // the tiles in that block column (pitch 44: the 16 lanes of a half-warp hit 32 different banks)
-            const double* p = tile + (lane & 3) * kA2RowPitch + (lane >> 2);
             double f[5];
 #pragma unroll
-            for (int b = 0; b < 5; ++b) f[b] = p[8 * b];
-            __syncwarp();                                                  // the tile may be rewritten
+            for (int b = 0; b < 5; ++b) f[b] = (double)pre[d][b] - sh[b];
+            if (begin + 4 * cur + 3 >= end) {                              // warp-uniform: the item's last, partial step --
+                const bool live = begin + 4 * cur + row < end;            // rows beyond the item are ZERO, also their constant 1
+#pragma unroll
+                for (int b = 0; b < 5; ++b) f[b] = live ? f[b] : 0.0;
+            }
+            gather(nidx[d], pre[d]);                                       // step cur + 8 kA2Depth
+            nidx[d] = list_entry(cur + 16 * kA2Depth);
             int t = 0;
 #pragma unroll
             for (int bi = 0; bi < 5; ++bi)
