@@ -320,6 +320,8 @@ constexpr int kSplit = 2048;                     // list entries per work item
 #ifndef LOE_A2_DEPTH
 #define LOE_A2_DEPTH 4
 #endif
+constexpr int kA2WarpDoubles = 15 * 2 * 32;       // accumulator values of one warp
+constexpr int kA2Smem = 8 * kA2WarpDoubles * (int)sizeof(double);
 constexpr int kA2Depth = LOE_A2_DEPTH;           // 4-frame steps each warp has in flight (gathered into registers ahead of use)
 
 __global__ void __launch_bounds__(kSortThreads)
@@ -434,7 +436,7 @@ accum2_kernel(const float* __restrict__ feat, const int* __restrict__ idx, const
     // (columns (l >> 2) + 8 b), and it is the lane that loads them -- the fragments go from the gather straight into the
     // DMMAs without passing through shared memory.  A step's loads are issued kA2Depth steps of the warp ahead of their use,
     // and the frame-list entry they go through one step earlier still (the address of a gather never waits for the list).
-    __shared__ double s_sum[40 * 41];
+    extern __shared__ double s_w[];                            // [8 warps][15 tiles x 2 halves][32 lanes], used after the loop
     double c[15][2];
 #pragma unroll
     for (int t = 0; t < 15; ++t) { c[t][0] = 0.0; c[t][1] = 0.0; }
@@ -484,22 +486,20 @@ accum2_kernel(const float* __restrict__ feat, const int* __restrict__ idx, const
                 for (int bj = bi; bj < 5; ++bj, ++t) dmma884(c[t][0], c[t][1], f[bi], f[bj]);
         }
     }
-    // warps -> one 40 x 40 matrix in shared memory, fixed order
-    for (int q = 0; q < 8; ++q) {
-        if (warp == q) {
-            int t = 0;
+    // the eight warps' accumulators meet in shared memory ([warp][tile, half][lane]: conflict-free, one barrier) and every
+    // output element is summed over the warps in warp order by the thread that stores it
+    {
+        double* mine = s_w + warp * kA2WarpDoubles;
+        int t = 0;
 #pragma unroll
-            for (int bi = 0; bi < 5; ++bi)
+        for (int bi = 0; bi < 5; ++bi)
 #pragma unroll
-                for (int bj = bi; bj < 5; ++bj, ++t)
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        double* d = &s_sum[(8 * bi + (lane >> 2)) * 41 + 8 * bj + 2 * (lane & 3) + h];
-                        *d = (q == 0) ? c[t][h] : (*d + c[t][h]);
-                    }
-        }
-        __syncthreads();
+            for (int bj = bi; bj < 5; ++bj, ++t) {
+                mine[(2 * t) * 32 + lane] = c[t][0];
+                mine[(2 * t + 1) * 32 + lane] = c[t][1];
+            }
     }
+    __syncthreads();
     constexpr int stride = 1 + D + D * (D + 1) / 2;
     double* dst = part + (size_t)item * stride;
     for (int e = tid; e < stride; e += 256) {
@@ -510,7 +510,14 @@ accum2_kernel(const float* __restrict__ feat, const int* __restrict__ idx, const
             while (r >= D - row) { r -= D - row; ++row; }
             i = row; j = row + r;
         }
-        dst[e] = s_sum[i * 41 + j];
+        // element (i, j), i <= j, sits in tile (i / 8, j / 8) of the triangular tile order, in lane 4 (i % 8) + (j % 8) / 2, half j % 2
+        const int bi = i >> 3, bj = j >> 3;
+        const int t = bi * 5 - (bi * (bi - 1)) / 2 + (bj - bi);
+        const int q = (2 * t + (j & 1)) * 32 + ((i & 7) << 2) + ((j & 7) >> 1);
+        double a = s_w[q];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) a += s_w[w * kA2WarpDoubles + q];
+        dst[e] = a;
     }
 }
 
@@ -607,6 +614,7 @@ extern "C" int loe_kmeans_dev(const float* feat_dev, const uint16_t* bucket_dev,
         const size_t scatter_smem = sizeof(int) * 9 * (size_t)n_glob;
         if (dev < 64 && !attr_done[dev]) {
             LOE_CUDA(cudaFuncSetAttribute(bucket_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(int) * 9 * kSortMaxGlob)));
+            LOE_CUDA(cudaFuncSetAttribute(accum2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kA2Smem));
             attr_done[dev] = true;
         }
         bucket_hist_kernel<<<(unsigned)L.n_chunks, kSortThreads, sizeof(int) * (size_t)n_glob, s>>>(bucket_dev, total_frames, n_glob, hist);
@@ -617,7 +625,7 @@ extern "C" int loe_kmeans_dev(const float* feat_dev, const uint16_t* bucket_dev,
         LOE_LAUNCH_CHECK("bucket_plan_kernel");
         bucket_scatter_kernel<<<(unsigned)L.n_chunks, kSortThreads, scatter_smem, s>>>(bucket_dev, total_frames, n_glob, hist, base, idx);
         LOE_LAUNCH_CHECK("bucket_scatter_kernel");
-        accum2_kernel<<<(unsigned)L.n_work_max, 256, 0, s>>>(feat_dev, idx, work, range, n_glob, shift_dev, part_ws_dev);
+        accum2_kernel<<<(unsigned)L.n_work_max, 256, kA2Smem, s>>>(feat_dev, idx, work, range, n_glob, shift_dev, part_ws_dev);
         LOE_LAUNCH_CHECK("accum2_kernel");
         reduce2_kernel<<<(unsigned)n_glob, 256, 0, s>>>(part_ws_dev, range, stride, stats_dev);
         LOE_LAUNCH_CHECK("reduce2_kernel");
