@@ -294,7 +294,14 @@ def train_block(args, eng, world, rank, dist):
                      "traffic_source": ncu_traffic().get("accum2_kernel", {}).get("capture"),
                      "algorithmic": f"{stats_bytes} bytes per rank and iteration ((4 x 39 + 2 + 1) B per frame)",
                      "fp64_gflops": 2 * 820 * frames_rank / (phases["align_stats"] * 1e-3) / 1e9,
-                     "note": "sum [x,1][x,1]^T is 820 float64 FMAs per frame: the FP64 pipe (64 FMA/clk/SM, ~36 TFLOP/s at 1.9 GHz), "
+                     "fp64_tensor": {"issued_tflops": 2 * 960 * frames_rank / (phases["align_stats"] * 1e-3) / 1e12,
+                                     "peak_tflops": 37.1, "frac": 2 * 960 * frames_rank / (phases["align_stats"] * 1e-3) / 1e12 / 37.1,
+                                     "peak_source": "scratch/dmma_peak.cu on this pool's B200 (profiles/r2e_dmma_peak.log): mma.sync m8n8k4 "
+                                                    "f64 sustains 37.1 TFLOP/s = 64 FMA/clk/SM",
+                                     "note": "960 FMAs per frame are issued (15 tiles of 8 x 8 for the 820 distinct sums); the whole "
+                                             "statistics phase (alignment + counting sort + accum2 + reduce2) is divided by, so the "
+                                             "fraction of accum2_kernel alone is higher (ncu: DMMA pipe 79 % active)"},
+                     "note": "sum [x,1][x,1]^T is 820 float64 FMAs per frame: the FP64 tensor pipe (64 FMA/clk/SM, 37 TFLOP/s measured), "
                              "not HBM, bounds this phase; float64 keeps the statistics exact enough for models that are identical "
                              "across 1..8 ranks"},
     }
