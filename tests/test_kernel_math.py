@@ -8,7 +8,9 @@
   for c = 1, conjugates for c = 3), the W_320 twiddles, one 16-point FFT per row, the mirrored bins, and the
   shared-memory addresses of the exchange rows and of the [plane][bin][frame] power spectra;
 * the pairing table of csrc/emission_h16.cu (pair_chunk): the 8 MMAs of K = 16 cover the 15 split-operand chunk
-  products exactly once, and no MMA is issued narrower than its chunks reach in the lower-triangular image.
+  products exactly once, and no MMA is issued narrower than its chunks reach in the lower-triangular image;
+* the fragment / accumulator / epilogue maps of csrc/kmeans.cu (accum2_kernel): every lane gathers exactly its own
+  elements of the FP64 tensor-core fragments, and the packed statistics come out of the accumulator layout.
 """
 import os
 import re
@@ -309,3 +311,58 @@ def test_reversed_cholesky_gives_the_lower_triangular_whitening_matrix():
     x = rng.normal(size=(5, D)); mu = rng.normal(size=D)
     ref = np.einsum("ti,ij,tj->t", x - mu, np.linalg.inv(cov), x - mu)
     assert np.allclose(np.sum(((x - mu) @ W) ** 2, axis=1), ref, rtol=1e-9)
+
+
+def test_accum2_fragments_come_straight_from_the_gather():
+    """csrc/kmeans.cu (accum2_kernel): with Y the 4 x 40 block of a step (rows [x - shift, 1]), lane l feeds
+    Y[l & 3][8 b + (l >> 2)] to the DMMAs as its element of BOTH the A fragment (A[m][k] = Y[k][8 bi + m], lane holds
+    A[l >> 2][l & 3]) and the B fragment (B[k][n] = Y[k][8 bj + n], lane holds B[l & 3][l >> 2]) of tile (bi, bj) of
+    Y^T Y; the accumulator layout D[l >> 2][2 (l & 3) + h] and the (tile, half, lane) -> (i, j) map of the epilogue
+    must then reproduce the packed statistics [N | sum y | upper triangle of sum y y^T]."""
+    rng = np.random.default_rng(3)
+    D, n_frames = 39, 10                                    # 10 frames: two full steps and a partial one
+    x = rng.normal(size=(n_frames, D))
+    shift = rng.normal(size=D)
+    tiles = [(bi, bj) for bi in range(5) for bj in range(bi, 5)]
+    c = np.zeros((15, 2, 32))
+    for step in range((n_frames + 3) // 4):
+        f = np.zeros((32, 5))                               # f[lane][b]
+        for lane in range(32):
+            row, col0 = lane & 3, lane >> 2
+            fr = 4 * step + row
+            for b in range(5):
+                k = col0 + 8 * b
+                pre = (x[fr, k] if k < D else 1.0) if fr < n_frames else (1.0 if b == 4 else 0.0)     # what gather() leaves
+                v = pre - (shift[k] if k < D else 0.0)
+                f[lane, b] = v if fr < n_frames else 0.0                                               # the partial-step select
+        for t, (bi, bj) in enumerate(tiles):
+            A = np.zeros((8, 4)); B = np.zeros((4, 8))
+            for lane in range(32):
+                A[lane >> 2, lane & 3] = f[lane, bi]
+                B[lane & 3, lane >> 2] = f[lane, bj]
+            Dm = A @ B
+            for lane in range(32):
+                for h in range(2):
+                    c[t, h, lane] += Dm[lane >> 2, 2 * (lane & 3) + h]
+    y = np.concatenate((x - shift, np.ones((n_frames, 1))), axis=1)
+    full = y.T @ y
+    stride = 1 + D + D * (D + 1) // 2
+    out = np.zeros(stride)
+    for e in range(stride):
+        i = j = D
+        if 1 <= e <= D:
+            i, j = e - 1, D
+        elif e > D:
+            r, row = e - 1 - D, 0
+            while r >= D - row:
+                r -= D - row
+                row += 1
+            i, j = row, row + r
+        bi, bj = i >> 3, j >> 3
+        t = bi * 5 - (bi * (bi - 1)) // 2 + (bj - bi)
+        assert tiles[t] == (bi, bj)
+        out[e] = c[t, j & 1, ((i & 7) << 2) + ((j & 7) >> 1)]
+    iu = np.triu_indices(D)
+    want = np.concatenate(([n_frames], (x - shift).sum(0), ((x - shift).T @ (x - shift))[iu]))
+    assert np.allclose(out, want, rtol=1e-12, atol=1e-12)
+    assert np.allclose(full[D, D], n_frames)
